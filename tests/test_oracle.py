@@ -1,0 +1,126 @@
+"""Pins the oracle (oracle/) against the reference's own golden vectors -- CPU only.
+
+Reference pins used (paths relative to the reference tree):
+  tests/test_sstar.py:25-104                       KATs on Sstar.compute
+  tests/test_preprocess.py:25-88                   20 + 40 row golden TSVs
+  tests/test_infer.py:26-60                        8 row features TSV (50 kb / 50 kb, phased)
+  tests/utils/test_utils.py:32-44                  split_genome windows
+plus outputs of the reference itself frozen by tests/golden/make_golden.py.
+"""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import FIXTURES
+from oracle import c_oracle, sstar_port, tiling_port
+from oracle.sstar_port import NAN_SENTINEL
+
+
+def _one_window(fn, case):
+    b, mx, p = case["params"]
+    pos = case["pos"]
+    lo = int(pos.min()) if len(pos) else 0
+    hi = int(pos.max()) if len(pos) else 0
+    return fn(case["ref"], case["tgt"], pos, [lo], [hi], b, mx, p)
+
+
+def test_kat_all_zero():
+    out = sstar_port.compute_float(ref_gts=np.zeros((3, 2), int), tgt_gts=np.zeros((3, 2), int),
+                                   pos=np.array([10, 50, 100]))
+    assert np.all(np.isnan(out["sstar"]))
+
+
+def test_kat_bonus_plus_distance():
+    tgt = np.array([[1, 1], [2, 0], [1, 1]])
+    out = sstar_port.compute_float(ref_gts=np.zeros((3, 2), int), tgt_gts=tgt,
+                                   pos=np.array([0, 50, 100]), match_bonus=5000)
+    assert out["sstar"][0] == 5100 and np.isnan(out["sstar"][1])
+    s, _ = sstar_port.compute_int(np.zeros((3, 2), int), tgt, np.array([0, 50, 100]))
+    assert s[0] == 5100 and s[1] == NAN_SENTINEL
+
+
+def test_kat_close_or_few():
+    out = sstar_port.compute_float(ref_gts=np.zeros((3, 2), int), tgt_gts=np.ones((3, 2), int),
+                                   pos=np.array([0, 5, 8]))
+    assert np.all(np.isnan(out["sstar"]))
+    out = sstar_port.compute_float(ref_gts=np.zeros((2, 2), int), tgt_gts=np.array([[1, 0], [0, 1]]),
+                                   pos=np.array([0, 100]))
+    assert np.all(np.isnan(out["sstar"]))
+
+
+def test_kat_missing_kwargs():
+    with pytest.raises(ValueError, match="Missing required arguments"):
+        sstar_port.compute_float()
+
+
+def test_worked_example_ind1():
+    # unphased, window [30001, 80000], ind1 -> S* 9270, 5 SNPs
+    data, _, _ = tiling_port.load_populations(
+        os.path.join(FIXTURES, "test.vcf"), os.path.join(FIXTURES, "test.ref.ind.list"),
+        os.path.join(FIXTURES, "test.tgt.ind.list"), False, "21")
+    rg, tg, pos = data["21"]
+    s, n = sstar_port.score_windows(rg, tg, pos, [30001], [80000], impl="int")
+    assert s[0, 0] == 9270 and n[0, 0] == 5
+
+
+@pytest.mark.parametrize("impl", ["float", "int", "c"])
+def test_fuzz_against_reference_outputs(fuzz_cases, impl):
+    for case in fuzz_cases:
+        if impl == "c":
+            s, n = _one_window(c_oracle.score_windows, case)
+        else:
+            s, n = _one_window(lambda *a: sstar_port.score_windows(*a, impl=impl), case)
+        assert np.array_equal(s[0], case["score"])
+        assert np.array_equal(n[0], case["nsnp"])
+
+
+@pytest.mark.parametrize("phased", [False, True])
+def test_test0_windows_against_reference_outputs(test0_golden, phased):
+    tag = "phased" if phased else "unphased"
+    data, _, _ = tiling_port.load_populations(
+        os.path.join(FIXTURES, "test.0.vcf"), os.path.join(FIXTURES, "test.0.ref.ind.list"),
+        os.path.join(FIXTURES, "test.0.tgt.ind.list"), phased, "1")
+    rg, tg, pos = data["1"]
+    wins = tiling_port.split_windows(pos, 50000, 10000)
+    assert np.array_equal(np.asarray(wins), test0_golden[f"{tag}_win"])
+    ws, we = zip(*wins)
+    for fn in (c_oracle.score_windows, sstar_port.score_windows):
+        s, n = fn(rg, tg, pos, ws, we)
+        assert np.array_equal(s, test0_golden[f"{tag}_score"])
+        assert np.array_equal(n, test0_golden[f"{tag}_nsnp"])
+
+
+@pytest.mark.parametrize("phased,step,expected", [
+    (False, 10000, "test.sstar.unphased.expected.tsv"),
+    (True, 10000, "test.sstar.phased.expected.tsv"),
+    (True, 50000, "test.infer.expected.features.tsv"),
+])
+def test_golden_tsv_end_to_end(tmp_path, phased, step, expected):
+    data, _, tgt_names = tiling_port.load_populations(
+        os.path.join(FIXTURES, "test.vcf"), os.path.join(FIXTURES, "test.ref.ind.list"),
+        os.path.join(FIXTURES, "test.tgt.ind.list"), phased, "21")
+    rg, tg, pos = data["21"]
+    wins = tiling_port.split_windows(pos, 50000, step)
+    ws, we = zip(*wins)
+    s, n = c_oracle.score_windows(rg, tg, pos, ws, we)
+    s2, n2 = sstar_port.score_windows(rg, tg, pos, ws, we)
+    assert np.array_equal(s, s2) and np.array_equal(n, n2)
+    out = tmp_path / "o.tsv"
+    tiling_port.rows_to_tsv(out, "21", wins, tiling_port.sample_labels(tgt_names, 2, phased), s, n)
+    got = pd.read_csv(out, sep="\t")
+    want = pd.read_csv(os.path.join(FIXTURES, expected), sep="\t")
+    pd.testing.assert_frame_equal(got, want, check_dtype=False, check_exact=True)
+    # byte-identical too (the golden files were written by the reference's to_csv)
+    assert open(out).read() == open(os.path.join(FIXTURES, expected)).read()
+
+
+def test_split_windows_rules():
+    pos = np.array([261, 592, 619, 693, 1008, 1125, 1307, 1424, 1436, 1491, 1743, 1853, 1917, 2075])
+    assert tiling_port.split_windows(pos, 50000, 10000) == [(1, 50000)]
+    assert tiling_port.split_windows(np.array([1, 2, 3, 4, 5]), 3, 2)[0] == (1, 3)
+    with pytest.raises(ValueError):
+        tiling_port.split_windows(pos, 50000, -1)
+    with pytest.raises(ValueError):
+        tiling_port.split_windows(np.array([]), 50000, 10000)
