@@ -1,0 +1,132 @@
+/* sstar_b200 -- C-ABI of the B200-native S* scoring engine.
+ *
+ * The reference (xin-huang/sstar, sstar2 2.0.0) is pure Python and has no FFI for this
+ * path; the entry points below are what a ctypes binding behind its three Python seams
+ * would bind (paths relative to the reference tree):
+ *
+ *   S3  Sstar.compute(**kwargs)                 sstar/sstar.py:43-106
+ *   S2  mp_manager(job, data_generator, n)      sstar/mp_manager.py:98-188
+ *   S1  preprocess(vcf_file, chr_name, ...)     sstar/preprocess.py:28-122
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every call returns 0 on success or a negative SSTAR_B200_E* code; the message is
+ *     available from sstar_b200_last_error() (thread-local);
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t, NULL = default
+ *     stream) of CUDA device `device`; the caller synchronises;
+ *   - the callee never allocates or frees caller-visible memory: device scratch comes in
+ *     through `d_workspace` (size it with sstar_b200_workspace_bytes);
+ *   - no global mutable state except the thread-local error string, so the library may be
+ *     driven concurrently from one host thread / process per GPU;
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ *
+ * Data layout (exactly what the reference holds in numpy):
+ *   ref_gt  int8  [V, R] row-major   reference genotypes (haplotype alleles or dosages)
+ *   tgt_gt  int8  [V, T] row-major   target genotypes
+ *   pos     int32 [V]                variant positions, STRICTLY ascending
+ *   windows int32 [W] start / end    1-based CLOSED intervals (utils.py:480-488)
+ *   score   int64 [W, T]             S* score; SSTAR_B200_NAN where the reference yields NaN
+ *   nsnp    int32 [W, T]             Region_ind_SNP_number
+ */
+#ifndef SSTAR_B200_H
+#define SSTAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSTAR_B200_ABI_VERSION 1
+#define SSTAR_B200_NAN INT64_MIN
+
+/* error codes */
+#define SSTAR_B200_OK 0
+#define SSTAR_B200_EINVAL (-1)    /* bad argument */
+#define SSTAR_B200_ECUDA (-2)     /* CUDA runtime error (no device, launch failure, ...) */
+#define SSTAR_B200_EWORKSPACE (-3) /* workspace too small */
+
+/* algorithm selector (sstar_b200_options.algo) */
+#define SSTAR_B200_ALGO_AUTO 0     /* prefix-max DP; windows with genotypes outside {0,1,2} go pairwise */
+#define SSTAR_B200_ALGO_PAIRWISE 1 /* literal O(n^2) recurrence of sstar/sstar.py:208-212 for every window */
+
+/* status bits written to the first int32 of the workspace (read it back after the stream syncs) */
+#define SSTAR_B200_ST_LIST_OVERFLOW 1u /* a window held more variants than max_win_variants */
+
+typedef struct sstar_b200_options {
+    int32_t algo;             /* SSTAR_B200_ALGO_* */
+    int32_t max_win_variants; /* upper bound on variants inside any window (hi - lo); 0 = unknown:
+                                 the library sizes for the worst case V */
+    int32_t reserved[6];      /* must be zero */
+} sstar_b200_options;
+
+/* replaces: nothing in the reference (library identification) */
+int sstar_b200_version(void);
+
+/* replaces: the str(e) that mp_worker puts on the out queue, sstar/mp_manager.py:244-246 */
+const char *sstar_b200_last_error(void);
+
+/* Number of CUDA devices visible, or a negative error code. */
+int sstar_b200_device_count(void);
+
+/* Scratch bytes needed by sstar_b200_score_windows* for these shapes. */
+size_t sstar_b200_workspace_bytes(int64_t V, int32_t R, int32_t T, int32_t W,
+                                  int32_t max_win_variants);
+
+/* Whole-chromosome scoring: every (window, target column) unit in one call.
+ * replaces: WindowDataGenerator slicing      sstar/generators/window_data_generator.py:106-129
+ *           mp_manager fan-out / gather      sstar/mp_manager.py:162-179
+ *           FeatureVectorPreprocessor.run    sstar/feature_vector_preprocessor.py:71-137
+ *           Sstar.compute / _calc_sstar      sstar/sstar.py:43-244
+ * All pointers are DEVICE pointers. */
+int sstar_b200_score_windows(int device, void *stream, const int8_t *d_ref_gt,
+                             const int8_t *d_tgt_gt, const int32_t *d_pos, int64_t V, int32_t R,
+                             int32_t T, const int32_t *d_win_start, const int32_t *d_win_end,
+                             int32_t W, int32_t match_bonus, int32_t max_mismatch,
+                             int32_t mismatch_penalty, int64_t *d_score, int32_t *d_nsnp,
+                             void *d_workspace, size_t workspace_bytes);
+
+/* Same, with options (algorithm choice, size hints). `opts` may be NULL. */
+int sstar_b200_score_windows_ex(int device, void *stream, const int8_t *d_ref_gt,
+                                const int8_t *d_tgt_gt, const int32_t *d_pos, int64_t V, int32_t R,
+                                int32_t T, const int32_t *d_win_start, const int32_t *d_win_end,
+                                int32_t W, int32_t match_bonus, int32_t max_mismatch,
+                                int32_t mismatch_penalty, int64_t *d_score, int32_t *d_nsnp,
+                                void *d_workspace, size_t workspace_bytes,
+                                const sstar_b200_options *opts);
+
+/* Replicate-batched scoring for the simulate/train path: Nrep independent replicates are
+ * concatenated along the variant axis (replicate r owns rows d_rep_offset[r] .. d_rep_offset[r+1]),
+ * positions ascend inside each replicate, and every replicate is scored on ONE window
+ * [win_start, win_end] (the reference uses [1, seq_len]).  Outputs are [Nrep, T].
+ * replaces: MsprimeSimulator._build_feature_input_from_ts + FeatureVectorPreprocessor.run per
+ *           replicate, sstar/msprime_simulator.py:179-256, fanned out by sstar/simulate.py:147-151 */
+int sstar_b200_score_replicates(int device, void *stream, const int8_t *d_ref_gt,
+                                const int8_t *d_tgt_gt, const int32_t *d_pos, int64_t V, int32_t R,
+                                int32_t T, const int32_t *d_rep_offset, int32_t Nrep,
+                                int32_t win_start, int32_t win_end, int32_t match_bonus,
+                                int32_t max_mismatch, int32_t mismatch_penalty, int64_t *d_score,
+                                int32_t *d_nsnp, void *d_workspace, size_t workspace_bytes,
+                                const sstar_b200_options *opts);
+
+/* The two halves of the pipeline, exposed so the packing kernel can be timed alone.
+ * pack:  genotype matrices -> bit-planes + absent mask inside the workspace   (sstar.py:87-92,163-164)
+ * score: window bounds + chain DP on an already packed workspace              (sstar.py:183-217) */
+int sstar_b200_pack(int device, void *stream, const int8_t *d_ref_gt, const int8_t *d_tgt_gt,
+                    int64_t V, int32_t R, int32_t T, void *d_workspace, size_t workspace_bytes);
+
+int sstar_b200_score_packed(int device, void *stream, const int8_t *d_tgt_gt, const int32_t *d_pos,
+                            int64_t V, int32_t R, int32_t T, const int32_t *d_win_start,
+                            const int32_t *d_win_end, int32_t W, int32_t match_bonus,
+                            int32_t max_mismatch, int32_t mismatch_penalty, int64_t *d_score,
+                            int32_t *d_nsnp, void *d_workspace, size_t workspace_bytes,
+                            const sstar_b200_options *opts);
+
+/* Number of kernels the last sstar_b200_score_* / pack call on this thread enqueued. */
+int sstar_b200_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSTAR_B200_H */

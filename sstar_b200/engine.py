@@ -1,0 +1,273 @@
+"""Device-side plumbing for the S* engine: PyTorch owns the buffers, the C-ABI does the work.
+
+``ScoreEngine`` is the host mirror of what the reference spreads over
+``WindowDataGenerator`` (slicing), ``mp_manager`` (fan-out / gather) and
+``FeatureVectorPreprocessor.run`` -> ``Sstar.compute`` (scoring): one call scores every
+(window, target column) unit of a chromosome.
+
+PyTorch is used for device memory, pinned host memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import NAN_SENTINEL, SstarB200Error
+
+
+def as_int8(a, name: str) -> np.ndarray:
+    """Genotype matrix -> C-contiguous int8, refusing values the int8 layout cannot hold.
+
+    The reference carries int8 (phased, scikit-allel) or int64 dosages (``np.sum`` over the
+    ploidy axis, sstar/utils/utils.py:305-306); both are tiny integers.
+    """
+    a = np.asarray(a)
+    if a.ndim != 2:
+        raise ValueError(f"{name} must be 2-D (n_sites, n_samples), got shape {a.shape}")
+    if a.dtype == np.int8:
+        return np.ascontiguousarray(a)
+    if a.dtype == np.bool_:
+        return np.ascontiguousarray(a, dtype=np.int8)
+    if not np.issubdtype(a.dtype, np.integer):
+        if a.size and not np.all(np.equal(np.mod(a, 1), 0)):
+            raise ValueError(f"{name} holds non-integer genotypes")
+    if a.size and (a.min() < -128 or a.max() > 127):
+        raise ValueError(f"{name} holds genotypes outside the int8 range")
+    return np.ascontiguousarray(a, dtype=np.int8)
+
+
+def check_positions(pos) -> np.ndarray:
+    p = np.asarray(pos)
+    if p.ndim != 1:
+        raise ValueError("pos must be 1-D")
+    if p.size and (p.min() < -(2 ** 31) or p.max() > 2 ** 31 - 1):
+        raise ValueError("pos does not fit int32")
+    p = np.ascontiguousarray(p, dtype=np.int32)
+    if p.size > 1 and not np.all(p[1:] > p[:-1]):
+        raise ValueError("pos must be strictly ascending (unique, sorted variant positions)")
+    return p
+
+
+def max_window_variants(pos: np.ndarray, win_start, win_end) -> int:
+    if len(win_start) == 0 or len(pos) == 0:
+        return 0
+    lo = np.searchsorted(pos, np.asarray(win_start, dtype=np.int64), side="left")
+    hi = np.searchsorted(pos, np.asarray(win_end, dtype=np.int64), side="right")
+    return int(max(0, (hi - lo).max()))
+
+
+class ScoreEngine:
+    """One engine per GPU. Not thread-safe; use one per host thread / process."""
+
+    def __init__(self, device: int = 0):
+        import torch
+
+        self.torch = torch
+        self.lib = _cabi.load()
+        if not torch.cuda.is_available():
+            raise SstarB200Error("sstar_b200 needs a CUDA device (there is no CPU fallback)")
+        if device >= torch.cuda.device_count():
+            raise SstarB200Error(f"CUDA device {device} not present")
+        self.device = int(device)
+        self.tdev = torch.device("cuda", self.device)
+        self._dev = {}
+        self._pin = {}
+        self.launches = 0  # kernels enqueued by the last call
+
+    # ------------------------------------------------------------------ buffers
+    def _dbuf(self, key, nbytes_elems, dtype):
+        t = self._dev.get(key)
+        if t is None or t.numel() < nbytes_elems or t.dtype != dtype:
+            t = self.torch.empty(max(int(nbytes_elems), 1), dtype=dtype, device=self.tdev)
+            self._dev[key] = t
+        return t
+
+    def _pbuf(self, key, n, dtype):
+        t = self._pin.get(key)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = self.torch.empty(max(int(n), 1), dtype=dtype, pin_memory=True)
+            self._pin[key] = t
+        return t
+
+    def workspace(self, V, R, T, W, max_win_variants=0):
+        need = self.lib.sstar_b200_workspace_bytes(int(V), int(R), int(T), int(W), int(max_win_variants))
+        if need == 0:
+            raise SstarB200Error("invalid shapes for workspace sizing")
+        return self._dbuf("ws", need, self.torch.uint8)
+
+    def _stream_ptr(self, stream=None):
+        s = stream if stream is not None else self.torch.cuda.current_stream(self.tdev)
+        return ctypes.c_void_p(s.cuda_stream)
+
+    # ------------------------------------------------------------------ device API
+    def score_device(self, ref_d, tgt_d, pos_d, ws_d, we_d, match_bonus=5000, max_mismatch=5,
+                     mismatch_penalty=-10000, algo="auto", max_win_variants=0, out=None, stream=None):
+        """All inputs are device tensors (int8 [V,R], int8 [V,T], int32 [V], int32 [W] x2)."""
+        torch = self.torch
+        V, R = ref_d.shape
+        T = tgt_d.shape[1]
+        W = ws_d.shape[0]
+        assert ref_d.dtype == torch.int8 and tgt_d.dtype == torch.int8 and pos_d.dtype == torch.int32
+        assert ref_d.is_contiguous() and tgt_d.is_contiguous() and tgt_d.shape[0] == V
+        if out is None:
+            score = torch.empty((W, T), dtype=torch.int64, device=self.tdev)
+            nsnp = torch.empty((W, T), dtype=torch.int32, device=self.tdev)
+        else:
+            score, nsnp = out
+        ws = self.workspace(V, R, T, W, max_win_variants)
+        opts = _cabi.Options(algo=_cabi.ALGOS[algo], max_win_variants=int(max_win_variants))
+        rc = self.lib.sstar_b200_score_windows_ex(
+            self.device, self._stream_ptr(stream), ref_d.data_ptr(), tgt_d.data_ptr(), pos_d.data_ptr(),
+            V, R, T, ws_d.data_ptr(), we_d.data_ptr(), W, int(match_bonus), int(max_mismatch),
+            int(mismatch_penalty), score.data_ptr(), nsnp.data_ptr(), ws.data_ptr(), ws.numel(),
+            ctypes.byref(opts))
+        _cabi.check(rc)
+        self.launches = self.lib.sstar_b200_last_launch_count()
+        return score, nsnp
+
+    def pack_device(self, ref_d, tgt_d, W=1, max_win_variants=0, stream=None):
+        V, R = ref_d.shape
+        T = tgt_d.shape[1]
+        ws = self.workspace(V, R, T, W, max_win_variants)
+        rc = self.lib.sstar_b200_pack(self.device, self._stream_ptr(stream), ref_d.data_ptr(),
+                                      tgt_d.data_ptr(), V, R, T, ws.data_ptr(), ws.numel())
+        _cabi.check(rc)
+        self.launches = self.lib.sstar_b200_last_launch_count()
+        return ws
+
+    def score_packed_device(self, R, tgt_d, pos_d, ws_d, we_d, match_bonus=5000, max_mismatch=5,
+                            mismatch_penalty=-10000, algo="auto", max_win_variants=0, out=None,
+                            stream=None):
+        torch = self.torch
+        V, T = tgt_d.shape
+        W = ws_d.shape[0]
+        if out is None:
+            score = torch.empty((W, T), dtype=torch.int64, device=self.tdev)
+            nsnp = torch.empty((W, T), dtype=torch.int32, device=self.tdev)
+        else:
+            score, nsnp = out
+        ws = self.workspace(V, R, T, W, max_win_variants)
+        opts = _cabi.Options(algo=_cabi.ALGOS[algo], max_win_variants=int(max_win_variants))
+        rc = self.lib.sstar_b200_score_packed(
+            self.device, self._stream_ptr(stream), tgt_d.data_ptr(), pos_d.data_ptr(), V, R, T,
+            ws_d.data_ptr(), we_d.data_ptr(), W, int(match_bonus), int(max_mismatch),
+            int(mismatch_penalty), score.data_ptr(), nsnp.data_ptr(), ws.data_ptr(), ws.numel(),
+            ctypes.byref(opts))
+        _cabi.check(rc)
+        self.launches = self.lib.sstar_b200_last_launch_count()
+        return score, nsnp
+
+    def score_replicates_device(self, ref_d, tgt_d, pos_d, rep_off_d, win_start, win_end,
+                                match_bonus=5000, max_mismatch=5, mismatch_penalty=-10000,
+                                algo="auto", max_win_variants=0, stream=None):
+        torch = self.torch
+        V, R = ref_d.shape
+        T = tgt_d.shape[1]
+        N = rep_off_d.shape[0] - 1
+        score = torch.empty((N, T), dtype=torch.int64, device=self.tdev)
+        nsnp = torch.empty((N, T), dtype=torch.int32, device=self.tdev)
+        ws = self.workspace(V, R, T, N, max_win_variants)
+        opts = _cabi.Options(algo=_cabi.ALGOS[algo], max_win_variants=int(max_win_variants))
+        rc = self.lib.sstar_b200_score_replicates(
+            self.device, self._stream_ptr(stream), ref_d.data_ptr(), tgt_d.data_ptr(), pos_d.data_ptr(),
+            V, R, T, rep_off_d.data_ptr(), N, int(win_start), int(win_end), int(match_bonus),
+            int(max_mismatch), int(mismatch_penalty), score.data_ptr(), nsnp.data_ptr(), ws.data_ptr(),
+            ws.numel(), ctypes.byref(opts))
+        _cabi.check(rc)
+        self.launches = self.lib.sstar_b200_last_launch_count()
+        return score, nsnp
+
+    # ------------------------------------------------------------------ host API
+    def _h2d(self, key, arr: np.ndarray, tdtype):
+        """numpy -> pinned staging -> device (async on the current stream)."""
+        torch = self.torch
+        n = arr.size
+        pin = self._pbuf("pin_" + key, n, tdtype)[:n]
+        if n:
+            pin.copy_(torch.from_numpy(arr.reshape(-1)))
+        dev = self._dbuf("dev_" + key, n, tdtype)[:n]
+        dev.copy_(pin, non_blocking=True)
+        return dev
+
+    def score_host(self, ref_gts, tgt_gts, pos, win_start, win_end, match_bonus=5000, max_mismatch=5,
+                   mismatch_penalty=-10000, algo="auto"):
+        """numpy in, numpy out: (score[W,T] int64 with NAN_SENTINEL, nsnp[W,T] int32)."""
+        torch = self.torch
+        ref = as_int8(ref_gts, "ref_gts")
+        tgt = as_int8(tgt_gts, "tgt_gts")
+        p = check_positions(pos)
+        V, R = ref.shape
+        T = tgt.shape[1]
+        if tgt.shape[0] != V or p.shape[0] != V:
+            raise ValueError("ref_gts, tgt_gts and pos must have the same number of sites")
+        if R < 1 or T < 1:
+            raise ValueError("at least one reference and one target column are required")
+        ws = np.ascontiguousarray(win_start, dtype=np.int32)
+        we = np.ascontiguousarray(win_end, dtype=np.int32)
+        W = ws.shape[0]
+        hint = max_window_variants(p, ws, we)
+        with torch.cuda.device(self.tdev):
+            ref_d = self._h2d("ref", ref, torch.int8).view(V, R)
+            tgt_d = self._h2d("tgt", tgt, torch.int8).view(V, T)
+            pos_d = self._h2d("pos", p, torch.int32)
+            ws_d = self._h2d("ws", ws, torch.int32)
+            we_d = self._h2d("we", we, torch.int32)
+            score_d = self._dbuf("score", W * T, torch.int64)[:W * T].view(W, T)
+            nsnp_d = self._dbuf("nsnp", W * T, torch.int32)[:W * T].view(W, T)
+            self.score_device(ref_d, tgt_d, pos_d, ws_d, we_d, match_bonus, max_mismatch,
+                              mismatch_penalty, algo=algo, max_win_variants=hint, out=(score_d, nsnp_d))
+            score_h = self._pbuf("pin_score", W * T, torch.int64)[:W * T]
+            nsnp_h = self._pbuf("pin_nsnp", W * T, torch.int32)[:W * T]
+            score_h.copy_(score_d.view(-1), non_blocking=True)
+            nsnp_h.copy_(nsnp_d.view(-1), non_blocking=True)
+            torch.cuda.current_stream(self.tdev).synchronize()
+        return score_h.numpy().reshape(W, T).copy(), nsnp_h.numpy().reshape(W, T).copy()
+
+    def score_replicates_host(self, ref_gts, tgt_gts, pos, rep_offset, win_start, win_end,
+                              match_bonus=5000, max_mismatch=5, mismatch_penalty=-10000, algo="auto"):
+        """Concatenated replicates (simulate path): outputs are [Nrep, T]."""
+        torch = self.torch
+        ref = as_int8(ref_gts, "ref_gts")
+        tgt = as_int8(tgt_gts, "tgt_gts")
+        p = np.ascontiguousarray(pos, dtype=np.int32)
+        off = np.ascontiguousarray(rep_offset, dtype=np.int32)
+        V, R = ref.shape
+        T = tgt.shape[1]
+        N = off.shape[0] - 1
+        if off[0] != 0 or off[-1] != V or np.any(np.diff(off) < 0):
+            raise ValueError("rep_offset must rise from 0 to V")
+        for r in range(N):
+            seg = p[off[r]:off[r + 1]]
+            if seg.size > 1 and not np.all(seg[1:] > seg[:-1]):
+                raise ValueError(f"positions of replicate {r} are not strictly ascending")
+        hint = int(np.diff(off).max()) if N else 0
+        with torch.cuda.device(self.tdev):
+            ref_d = self._h2d("ref", ref, torch.int8).view(V, R)
+            tgt_d = self._h2d("tgt", tgt, torch.int8).view(V, T)
+            pos_d = self._h2d("pos", p, torch.int32)
+            off_d = self._h2d("off", off, torch.int32)
+            score_d, nsnp_d = self.score_replicates_device(
+                ref_d, tgt_d, pos_d, off_d, win_start, win_end, match_bonus, max_mismatch,
+                mismatch_penalty, algo=algo, max_win_variants=hint)
+            score = score_d.cpu().numpy()
+            nsnp = nsnp_d.cpu().numpy()
+        return score, nsnp
+
+
+_ENGINES = {}
+
+
+def get_engine(device: int = 0) -> ScoreEngine:
+    eng = _ENGINES.get(device)
+    if eng is None:
+        eng = _ENGINES[device] = ScoreEngine(device)
+    return eng
+
+
+def scores_to_float(score: np.ndarray) -> np.ndarray:
+    """int64 with NAN_SENTINEL -> float64 with NaN (what the reference returns)."""
+    out = score.astype(np.float64)
+    out[score == NAN_SENTINEL] = np.nan
+    return out

@@ -1,0 +1,77 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol the
+header declares, and argument validation works without a GPU (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import REPO
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from sstar_b200 import _cabi
+    return _cabi.load()
+
+
+def _declared_functions():
+    text = open(os.path.join(REPO, "include", "sstar_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sstar_b200_[a-z_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib):
+    names = _declared_functions()
+    assert len(names) >= 9
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/sstar_b200.h but not exported"
+
+
+def test_binding_table_matches_header(lib):
+    from sstar_b200 import _cabi
+    assert sorted(_cabi.SIGNATURES) == _declared_functions()
+
+
+def test_version_and_workspace_sizing(lib):
+    assert lib.sstar_b200_version() == 1
+    small = lib.sstar_b200_workspace_bytes(1000, 10, 20, 50, 100)
+    big = lib.sstar_b200_workspace_bytes(1_000_000, 1000, 1000, 25_000, 400)
+    assert 0 < small < big
+    # two bit-planes of ceil(V/32) x roundup(T,32) words dominate
+    assert big >= 2 * (1_000_000 // 32) * 1024 * 4
+    assert lib.sstar_b200_workspace_bytes(-1, 1, 1, 1, 0) == 0
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    from sstar_b200 import _cabi
+    rc = lib.sstar_b200_score_windows(0, None, None, None, None, 10, 0, 5, None, None, 1, 5000, 5, -10000,
+                                      None, None, None, 0)
+    assert rc == -1 and b"R must be" in lib.sstar_b200_last_error()
+    rc = lib.sstar_b200_score_windows(0, None, None, None, None, 10, 2, 5, None, None, 1, 5000, 5, -10000,
+                                      None, None, None, 0)
+    assert rc == -1 and b"workspace" in lib.sstar_b200_last_error()
+    with pytest.raises(_cabi.SstarB200Error):
+        _cabi.check(rc)
+
+
+def test_no_cpu_fallback():
+    import torch
+    from sstar_b200 import SstarB200Error
+    from sstar_b200.engine import ScoreEngine
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(SstarB200Error, match="no CPU fallback"):
+        ScoreEngine(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(REPO, "sstar_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "libsstar_oracle" not in src, f

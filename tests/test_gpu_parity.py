@@ -1,0 +1,174 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) vs the oracle and the golden fixtures.
+
+Bar: bit-exact (integer scores, NaN-ness, SNP counts)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import FIXTURES
+from oracle import c_oracle, tiling_port
+from oracle.sstar_port import NAN_SENTINEL
+
+pytestmark = pytest.mark.gpu
+
+ALGOS = ["auto", "pairwise"]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import __graft_entry__ as g
+    g.build()
+    from sstar_b200.engine import get_engine
+    return get_engine(0)
+
+
+# ---- the reference's own KATs (tests/test_sstar.py:25-104), through the drop-in Sstar.compute
+def test_kat_all_zero_returns_nan():
+    from sstar_b200.sstar import Sstar
+    out = Sstar.compute(ref_gts=np.zeros((3, 2), dtype=int), tgt_gts=np.zeros((3, 2), dtype=int),
+                        pos=np.array([10, 50, 100], dtype=int))["sstar"]
+    assert out == [np.nan, np.nan]
+
+
+def test_kat_two_matching_loci_far_apart():
+    from sstar_b200.sstar import Sstar
+    tgt = np.array([[1, 1], [2, 0], [1, 1]], dtype=int)
+    out = Sstar.compute(ref_gts=np.zeros((3, 2), dtype=int), tgt_gts=tgt,
+                        pos=np.array([0, 50, 100], dtype=int), match_bonus=5000)["sstar"]
+    assert len(out) == 2 and out[0] == 5100 and np.isnan(out[1])
+
+
+def test_kat_close_positions_or_too_few_loci():
+    from sstar_b200.sstar import Sstar
+    out = Sstar.compute(ref_gts=np.zeros((3, 2), dtype=int), tgt_gts=np.ones((3, 2), dtype=int),
+                        pos=np.array([0, 5, 8], dtype=int))["sstar"]
+    assert len(out) == 2 and np.all(np.isnan(out))
+    out = Sstar.compute(ref_gts=np.zeros((2, 2), dtype=int), tgt_gts=np.array([[1, 0], [0, 1]]),
+                        pos=np.array([0, 100], dtype=int))["sstar"]
+    assert len(out) == 2 and np.all(np.isnan(out))
+
+
+def test_kat_missing_params():
+    from sstar_b200.sstar import Sstar
+    with pytest.raises(ValueError, match="Missing required arguments"):
+        Sstar.compute()
+
+
+# ---- golden vectors produced by the reference itself
+@pytest.mark.parametrize("algo", ALGOS)
+def test_fuzz_golden(eng, fuzz_cases, algo):
+    for i, case in enumerate(fuzz_cases):
+        b, mx, p = case["params"]
+        pos = case["pos"]
+        if len(pos) == 0:
+            ws, we = [0], [0]
+        else:
+            ws, we = [int(pos[0])], [int(pos[-1])]
+        s, n = eng.score_host(case["ref"], case["tgt"], pos, ws, we, b, mx, p, algo=algo)
+        assert np.array_equal(s[0], case["score"]), (i, algo, s[0], case["score"])
+        assert np.array_equal(n[0], case["nsnp"]), (i, algo)
+
+
+def test_fuzz_golden_batched_as_replicates(eng, fuzz_cases):
+    # all cases with the same shape/params in ONE replicate-batched call (the simulate path)
+    groups = {}
+    for case in fuzz_cases:
+        key = (case["ref"].shape[1], case["tgt"].shape[1], case["params"])
+        groups.setdefault(key, []).append(case)
+    for (R, T, (b, mx, p)), cases in groups.items():
+        ref = np.concatenate([c["ref"] for c in cases])
+        tgt = np.concatenate([c["tgt"] for c in cases])
+        pos = np.concatenate([c["pos"] for c in cases])
+        off = np.cumsum([0] + [len(c["pos"]) for c in cases])
+        s, n = eng.score_replicates_host(ref, tgt, pos, off, -5, 2 ** 31 - 1, b, mx, p)
+        assert np.array_equal(s, np.stack([c["score"] for c in cases]))
+        assert np.array_equal(n, np.stack([c["nsnp"] for c in cases]))
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("phased", [False, True])
+def test_test0_vcf_windows(eng, test0_golden, phased, algo):
+    tag = "phased" if phased else "unphased"
+    data, _, _ = tiling_port.load_populations(
+        os.path.join(FIXTURES, "test.0.vcf"), os.path.join(FIXTURES, "test.0.ref.ind.list"),
+        os.path.join(FIXTURES, "test.0.tgt.ind.list"), phased, "1")
+    rg, tg, pos = data["1"]
+    wins = test0_golden[f"{tag}_win"]
+    s, n = eng.score_host(rg, tg, pos, wins[:, 0], wins[:, 1], algo=algo)
+    assert np.array_equal(s, test0_golden[f"{tag}_score"])
+    assert np.array_equal(n, test0_golden[f"{tag}_nsnp"])
+
+
+# ---- seeded synthetic chromosomes vs the C oracle
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("n_ref,n_tgt,phased,length", [
+    (100, 50, False, 1_500_000),   # C2 shape
+    (5, 10, False, 600_000),       # tutorial shape: small panel, large n
+    (20, 33, True, 800_000),       # odd T (66 columns)
+    (3, 70, True, 300_000),        # T > 128 columns
+])
+def test_synthetic_vs_oracle(eng, algo, n_ref, n_tgt, phased, length):
+    from sstar_b200.synth import regular_windows, synth_chromosome
+    ref, tgt, pos = synth_chromosome(length, n_ref, n_tgt, phased, seed=1000 + n_ref)
+    ws, we = regular_windows(pos, 50_000, 10_000)
+    s, n = eng.score_host(ref, tgt, pos, ws, we, algo=algo)
+    so, no = c_oracle.score_windows(ref, tgt, pos, ws, we)
+    assert np.array_equal(s, so)
+    assert np.array_equal(n, no)
+
+
+@pytest.mark.parametrize("params", [(5000, 5, -10000), (5000, 0, -10000), (1, 1, 0), (123, 4, -7),
+                                    (2_000_000_000, 5, -2_000_000_000)])
+def test_parameters_and_missing_data(eng, params):
+    from sstar_b200.synth import regular_windows, synth_chromosome
+    ref, tgt, pos = synth_chromosome(500_000, 10, 24, False, seed=77)
+    rng = np.random.default_rng(5)
+    tgt = tgt.copy()
+    miss = rng.random(tgt.shape) < 0.01          # sprinkle missing calls: negative dosages
+    tgt[miss] = rng.choice([-2, -1], size=int(miss.sum())).astype(np.int8)
+    ref = ref.copy()
+    ref[rng.random(ref.shape) < 0.002] = -1      # signed sums may cancel to 0
+    ws, we = regular_windows(pos, 50_000, 10_000)
+    so, no = c_oracle.score_windows(ref, tgt, pos, ws, we, *params)
+    for algo in ALGOS:
+        s, n = eng.score_host(ref, tgt, pos, ws, we, *params, algo=algo)
+        assert np.array_equal(s, so), algo
+        assert np.array_equal(n, no), algo
+
+
+def test_edge_windows(eng):
+    # empty windows, windows past the data, single-variant windows, ragged overlap
+    pos = np.array([5, 14, 15, 24, 25, 40, 1000, 1010, 1020, 5000], dtype=np.int32)
+    tgt = np.array([[1, 2, 0]] * 10, dtype=np.int8)
+    tgt[3, 0] = 0
+    ref = np.zeros((10, 2), dtype=np.int8)
+    ref[6] = [1, 0]
+    ws = np.array([1, 1, 6, 41, 1000, 6000, 15, -50], dtype=np.int32)
+    we = np.array([5000, 4, 40, 999, 1020, 7000, 15, 2_000_000_000], dtype=np.int32)
+    so, no = c_oracle.score_windows(ref, tgt, pos, ws, we)
+    for algo in ALGOS:
+        s, n = eng.score_host(ref, tgt, pos, ws, we, algo=algo)
+        assert np.array_equal(s, so) and np.array_equal(n, no), algo
+
+
+def test_long_window_many_variants(eng):
+    # one window holding thousands of carried sites (pairwise lists spill to the global arena)
+    rng = np.random.default_rng(3)
+    V = 6000
+    pos = np.cumsum(rng.integers(1, 40, size=V)).astype(np.int32)
+    tgt = rng.choice([0, 1, 2], size=(V, 5), p=[0.3, 0.4, 0.3]).astype(np.int8)
+    tgt[:, 4] = rng.choice([0, 1, 2, 3, -1], size=V).astype(np.int8)  # exotic column -> pairwise path
+    ref = np.zeros((V, 3), dtype=np.int8)
+    ref[rng.random(V) < 0.2, 1] = 1
+    ws = np.array([1, 1000], dtype=np.int32)
+    we = np.array([int(pos[-1]), 60000], dtype=np.int32)
+    so, no = c_oracle.score_windows(ref, tgt, pos, ws, we)
+    for algo in ALGOS:
+        s, n = eng.score_host(ref, tgt, pos, ws, we, algo=algo)
+        assert np.array_equal(s, so) and np.array_equal(n, no), algo
+
+
+def test_rejects_unsorted_positions(eng):
+    with pytest.raises(ValueError, match="strictly ascending"):
+        eng.score_host(np.zeros((3, 1), np.int8), np.ones((3, 1), np.int8), [10, 5, 20], [1], [30])
