@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- S* (window x individual) scores/sec on B200, with the CPU path beside it.
+
+    python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path (oracle port)
+
+Workload (BASELINE.json configs[1], "C2"): one synthetic 10 Mb msprime-style chromosome,
+100 reference + 50 target diploids, unphased dosages, 50 kb windows / 10 kb step.  One "step" is one
+pass of the hot path over that chromosome: pack -> window bounds -> chain DP for every
+(window, target column) unit.  With N > 1 (torchrun, one rank per GPU) every rank scores its own
+chromosome of the same shape (different seed): weak scaling, no collective on the data path.
+
+value  : units/s with inputs resident in HBM (CUDA events around each step, max over ranks).
+e2e    : units/s through ScoreEngine.score_pinned (one C-ABI call: H2D of the int8 matrices from
+         pinned host memory, kernels, D2H of both result tables), wall clock, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "S* (window x individual) scores/sec"
+UNIT = "scores/s"
+PARAMS = (5000, 5, -10000)
+WORKLOADS = {
+    # name: (length bp, n_ref, n_tgt, phased, win_len, win_step, description)
+    "c2": (10_000_000, 100, 50, False, 50_000, 10_000,
+           "C2: synthetic 10 Mb msprime-style chromosome, 100 ref + 50 target diploids (unphased), "
+           "50 kb windows / 10 kb step"),
+    "c2-small": (1_000_000, 100, 50, False, 50_000, 10_000, "C2 shape at 1 Mb (debug)"),
+}
+
+
+def make_workload(name, rank):
+    from sstar_b200.synth import regular_windows, synth_chromosome
+    length, n_ref, n_tgt, phased, wl, wstep, desc = WORKLOADS[name]
+    seed = 12345 + 1 + 1000 * rank
+    ref, tgt, pos = synth_chromosome(length, n_ref, n_tgt, phased, seed)
+    ws, we = regular_windows(pos, wl, wstep)
+    return dict(ref=ref, tgt=tgt, pos=pos, ws=ws, we=we, seed=seed, desc=desc, name=name)
+
+
+def workload_stats(wk):
+    pos, ws, we = wk["pos"], wk["ws"], wk["we"]
+    absent = wk["ref"].astype(np.int32).sum(axis=1) == 0
+    car = ((wk["tgt"] != 0) & absent[:, None]).astype(np.int32)
+    csum = np.concatenate([np.zeros((1, car.shape[1]), np.int64), np.cumsum(car, axis=0)])
+    lo = np.searchsorted(pos, ws, side="left")
+    hi = np.searchsorted(pos, we, side="right")
+    n = csum[hi] - csum[lo]
+    return dict(V=int(pos.size), R=int(wk["ref"].shape[1]), T=int(wk["tgt"].shape[1]), W=int(ws.size),
+                units=int(ws.size * wk["tgt"].shape[1]), sum_n=int(n.sum()),
+                sum_pairs=int((n * (n - 1) // 2).sum()), max_n=int(n.max()),
+                mean_window_variants=float((hi - lo).mean()), max_window_variants=int((hi - lo).max()))
+
+
+def algorithmic_bytes(st):
+    """every int8 genotype read once + pos + 12 B per unit written."""
+    pack = st["V"] * (st["R"] + st["T"])
+    return dict(pipeline=pack + 4 * st["V"] + 12 * st["units"], pack=pack,
+                score=4 * st["V"] + 12 * st["units"])
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(workload, kernel):
+    """DRAM bytes per launch from the committed ncu --set full capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh).get(workload, {}).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed regions run."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index, period=0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.marks = [], []
+        self.stop_flag = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.max_mhz = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, rs))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def mark(self):
+        self.marks.append(time.perf_counter())
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        sel = self.samples
+        if len(self.marks) >= 2:
+            inside = [s for s in self.samples if self.marks[0] <= s[0] <= self.marks[-1]]
+            sel = inside or self.samples
+        bits = 0
+        for _, _, rs in sel:
+            bits |= rs
+        return {"sm_mhz": statistics.median(m for _, m, _ in sel), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(v for k, v in self.REASONS.items() if bits & k), "samples": len(sel)}
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+def run_reference(args, world, rank):
+    """The reference's CPU path (numpy port of its recipe) on all host cores, rank 0 only."""
+    if rank != 0:
+        return
+    from oracle.cpu_baseline import CpuBaseline
+    wk = make_workload(args.workload, 0)
+    st = workload_stats(wk)
+    cores = os.cpu_count() or 1
+    base = CpuBaseline(wk["ref"], wk["tgt"], wk["pos"], wk["ws"], wk["we"], PARAMS, cores)
+    per_win = base.per_window_seconds()
+    # bounded sample: ~20 s of CPU work per step, at most the whole chromosome
+    work = min(20.0, 150.0 * cores / max(args.steps + args.warmup, 1))  # keep the whole run within minutes
+    n_win = int(min(st["W"], max(cores, work / max(per_win, 1e-6))))
+    sample = np.linspace(0, st["W"] - 1, num=n_win).astype(int)
+    for _ in range(args.warmup):
+        base.run(sample[: max(cores, len(sample) // 8)])
+    secs = []
+    for _ in range(args.steps):
+        dt, _ = base.run(sample)
+        secs.append(dt)
+    base.close()
+    units = n_win * st["T"]
+    value = units / statistics.mean(secs)
+    sample_desc = f"{n_win} of {st['W']} windows x {st['T']} columns of the {wk['name']} chromosome per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(secs),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": wk["desc"], **{k: st[k] for k in ("V", "R", "T", "W", "units")},
+                   "seed": wk["seed"], "params": list(PARAMS)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample_desc + "; pool pre-forked and warm, no mp_manager 5 s tail"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, world, rank, local):
+    import torch
+    import __graft_entry__ as entry
+    if rank == 0:
+        entry.build()
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    else:
+        dist = None
+    from sstar_b200.engine import get_engine
+    from sstar_b200 import NAN_SENTINEL
+
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    eng = get_engine(local)
+    wk = make_workload(args.workload, rank)
+    st = workload_stats(wk)
+    V, R, T, W = st["V"], st["R"], st["T"], st["W"]
+    hint = st["max_window_variants"]
+
+    # host (pinned) and device copies of the inputs
+    pin = {k: torch.from_numpy(np.ascontiguousarray(wk[k])).pin_memory() for k in ("ref", "tgt", "pos", "ws", "we")}
+    d = {k: v.to(dev) for k, v in pin.items()}
+    score_d = torch.empty((W, T), dtype=torch.int64, device=dev)
+    nsnp_d = torch.empty((W, T), dtype=torch.int32, device=dev)
+    score_p = torch.empty((W, T), dtype=torch.int64).pin_memory()
+    nsnp_p = torch.empty((W, T), dtype=torch.int32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_device(ev=None):
+        if ev:
+            ev[0].record()
+        eng.pack_device(d["ref"], d["tgt"], W=W, max_win_variants=hint)
+        n_l = eng.launches
+        if ev:
+            ev[1].record()
+        eng.score_packed_device(R, d["tgt"], d["pos"], d["ws"], d["we"], *PARAMS, max_win_variants=hint,
+                                out=(score_d, nsnp_d))
+        if ev:
+            ev[2].record()
+        return n_l + eng.launches
+
+    def step_e2e():
+        eng.score_pinned(pin["ref"], pin["tgt"], pin["pos"], pin["ws"], pin["we"], score_p, nsnp_p,
+                         *PARAMS, max_win_variants=hint, sync=True)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if use_dist:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        flush.fill_(1)
+        launches_per_step = step_device()
+        step_e2e()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    # ---- region A: device-resident inputs, CUDA events per step, L2 flushed between steps
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    barrier()
+    sampler.mark()
+    for i in range(args.steps):
+        flush.fill_(i & 1)
+        step_device(evs[i])
+    barrier()
+    sampler.mark()
+    tot_ms = sum(e[0].elapsed_time(e[2]) for e in evs)
+    pack_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
+    score_ms = sum(e[1].elapsed_time(e[2]) for e in evs)
+
+    # ---- region B: end to end from pinned host buffers, wall clock per step (includes the sync)
+    barrier()
+    e2e_s = 0.0
+    for i in range(args.steps):
+        flush.fill_(i & 1)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        step_e2e()
+        e2e_s += time.perf_counter() - t0
+    barrier()
+    sampler.mark()
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    times = torch.tensor([tot_ms, e2e_s * 1e3, pack_ms, score_ms], dtype=torch.float64, device=dev)
+    units_t = torch.tensor([float(st["units"])], dtype=torch.float64, device=dev)
+    if use_dist:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(units_t, op=dist.ReduceOp.SUM)
+    tot_ms, e2e_ms, pack_ms, score_ms = (float(x) for x in times.tolist())
+    total_units = float(units_t.item())
+
+    # ---- parity in the same run (outside the timed regions): GPU vs C oracle, bit-exact
+    parity = None
+    cpu = None
+    if rank == 0:
+        from oracle import c_oracle
+        so, no = c_oracle.score_windows(wk["ref"], wk["tgt"], wk["pos"], wk["ws"], wk["we"], *PARAMS)
+        ok = bool(np.array_equal(score_p.numpy(), so) and np.array_equal(nsnp_p.numpy(), no)
+                  and np.array_equal(score_d.cpu().numpy(), so))
+        parity = {"checked_units": int(so.size), "bit_exact_vs_oracle": ok}
+        if not ok:
+            raise SystemExit("bench: GPU result differs from the oracle -- refusing to report a number")
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle.cpu_baseline import CpuBaseline
+            cores = os.cpu_count() or 1
+            base = CpuBaseline(wk["ref"], wk["tgt"], wk["pos"], wk["ws"], wk["we"], PARAMS, cores)
+            per_win = base.per_window_seconds()
+            n_win = int(min(W, max(cores, 20.0 / max(per_win, 1e-6))))
+            sample = np.linspace(0, W - 1, num=n_win).astype(int)
+            base.run(sample[: max(cores, n_win // 8)])
+            dt, res = base.run(sample)
+            base.close()
+            for w, (s, n) in res.items():  # the CPU-scored units must equal the GPU's
+                assert np.array_equal(s, so[w]) and np.array_equal(n, no[w]), "CPU port != GPU"
+            cpu = {"value": n_win * T / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{n_win} of {W} windows x {T} columns of the {wk['name']} chromosome, one pass "
+                             f"({dt:.2f} s wall); numpy port of the reference recipe, pool pre-forked and warm, "
+                             "no mp_manager 5 s tail",
+                   "in_process_us_per_unit": 1e6 * per_win / T}
+
+    if rank == 0:
+        ab = algorithmic_bytes(st)
+        peak, peak_src = measured_peak()
+        k = args.steps
+        dom = "pack_kernel" if pack_ms >= score_ms else "score_prefix_kernel"
+        dom_ms = (pack_ms if dom == "pack_kernel" else score_ms) / k
+        dom_bytes = ab["pack"] if dom == "pack_kernel" else ab["score"]
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+        pipe_achieved = ab["pipeline"] / (tot_ms / k * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": total_units / (tot_ms / k * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": k, "warmup": max(args.warmup, 3), "ms_per_step": tot_ms / k, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int8 genotypes -> int64 scores",
+            "data": "synthetic",
+            "config": {"workload": wk["desc"], **st, "seed": wk["seed"], "params": list(PARAMS),
+                       "per_rank": "every rank scores its own chromosome of this shape",
+                       "l2": "flushed between timed iterations (256 MiB device write)",
+                       "timing": "CUDA events on the launching stream around each step, summed over K steps"},
+            "e2e": {"value": total_units / (e2e_ms / k * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(V * (R + T) + 4 * V + 8 * W),
+                    "d2h_bytes_per_step": int(12 * W * T), "ms_per_step": e2e_ms / k,
+                    "api": "ScoreEngine.score_pinned -> sstar_b200_score_windows_host (pinned host buffers, "
+                           "wall clock incl. stream sync)"},
+            "gpu_launches": int(launches_per_step * k),
+            "kernels_per_step": int(launches_per_step),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": recorded_traffic(wk["name"], dom),
+                         "peak_source": peak_src, "algorithmic_bytes": dom_bytes, "kernel_ms": dom_ms,
+                         "pack_ms": pack_ms / k, "score_ms": score_ms / k,
+                         "pipeline": {"algorithmic_bytes": ab["pipeline"], "achieved": pipe_achieved,
+                                      "frac": pipe_achieved / peak}},
+            "cpu_baseline": cpu,
+            "clocks": sampler.summary(),
+            "parity": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if use_dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world, rank, local = dist_setup(args.gpus)
+    if args.impl == "reference":
+        run_reference(args, world, rank)
+        return
+    run_ours(args, world, rank, local)
+
+
+if __name__ == "__main__":
+    main()

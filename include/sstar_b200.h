@@ -51,13 +51,10 @@ extern "C" {
 #define SSTAR_B200_ALGO_AUTO 0     /* prefix-max DP; windows with genotypes outside {0,1,2} go pairwise */
 #define SSTAR_B200_ALGO_PAIRWISE 1 /* literal O(n^2) recurrence of sstar/sstar.py:208-212 for every window */
 
-/* status bits written to the first int32 of the workspace (read it back after the stream syncs) */
-#define SSTAR_B200_ST_LIST_OVERFLOW 1u /* a window held more variants than max_win_variants */
-
 typedef struct sstar_b200_options {
     int32_t algo;             /* SSTAR_B200_ALGO_* */
-    int32_t max_win_variants; /* upper bound on variants inside any window (hi - lo); 0 = unknown:
-                                 the library sizes for the worst case V */
+    int32_t max_win_variants; /* upper bound on variants inside any window (hi - lo), used only to
+                                 size the pairwise list arena; 0 = unknown (sized for V) */
     int32_t reserved[6];      /* must be zero */
 } sstar_b200_options;
 
@@ -122,6 +119,22 @@ int sstar_b200_score_packed(int device, void *stream, const int8_t *d_tgt_gt, co
                             int32_t max_mismatch, int32_t mismatch_penalty, int64_t *d_score,
                             int32_t *d_nsnp, void *d_workspace, size_t workspace_bytes,
                             const sstar_b200_options *opts);
+
+/* Host-buffer entry (the end-to-end call): copies the inputs host->device, scores, and copies the
+ * two result tables device->host, all enqueued on `stream`; the caller synchronises the stream
+ * before reading h_score / h_nsnp.  Host buffers should be page-locked for the copies to be
+ * asynchronous.  `d_scratch` is device memory of at least sstar_b200_host_scratch_bytes(...).
+ * replaces: the same reference functions as sstar_b200_score_windows, fed from numpy arrays. */
+size_t sstar_b200_host_scratch_bytes(int64_t V, int32_t R, int32_t T, int32_t W,
+                                     int32_t max_win_variants);
+
+int sstar_b200_score_windows_host(int device, void *stream, const int8_t *h_ref_gt,
+                                  const int8_t *h_tgt_gt, const int32_t *h_pos, int64_t V, int32_t R,
+                                  int32_t T, const int32_t *h_win_start, const int32_t *h_win_end,
+                                  int32_t W, int32_t match_bonus, int32_t max_mismatch,
+                                  int32_t mismatch_penalty, int64_t *h_score, int32_t *h_nsnp,
+                                  void *d_scratch, size_t scratch_bytes,
+                                  const sstar_b200_options *opts);
 
 /* Number of kernels the last sstar_b200_score_* / pack call on this thread enqueued. */
 int sstar_b200_last_launch_count(void);

@@ -43,6 +43,9 @@ SIGNATURES = {
                                                _i32, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _OPT]),
     "sstar_b200_score_replicates": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _i32,
                                                _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _OPT]),
+    "sstar_b200_host_scratch_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32]),
+    "sstar_b200_score_windows_host": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp,
+                                                 _i32, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _OPT]),
     "sstar_b200_pack": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _sz]),
     "sstar_b200_score_packed": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _i32,
                                            _i32, _i32, _i32, _vp, _vp, _vp, _sz, _OPT]),

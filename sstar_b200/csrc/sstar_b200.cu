@@ -563,7 +563,8 @@ int launch_score(cudaStream_t st, const int8_t *d_tgt, const int32_t *d_pos, int
 }
 
 int check_common(int device, int64_t V, int32_t R, int32_t T, int32_t W, const void *ws,
-                 size_t ws_bytes, const sstar_b200_options *opts, WsLayout *L, int *algo) {
+                 size_t ws_bytes, const sstar_b200_options *opts, WsLayout *L, int *algo,
+                 bool pack_only = false) {
     g_launches = 0;
     int rc = check_shapes(V, R, T, W);
     if (rc) return rc;
@@ -574,7 +575,9 @@ int check_common(int device, int64_t V, int32_t R, int32_t T, int32_t W, const v
     if (hint < 0) return fail(SSTAR_B200_EINVAL, "max_win_variants must be >= 0%s");
     *L = make_layout(V, T, W, hint);
     if (!ws) return fail(SSTAR_B200_EINVAL, "workspace pointer is null%s");
-    if (ws_bytes < L->total) return fail(SSTAR_B200_EWORKSPACE, "workspace too small%s");
+    // the packed planes sit at the front of the workspace and do not depend on W / the hint
+    if (ws_bytes < (pack_only ? L->off_win_lo : L->total))
+        return fail(SSTAR_B200_EWORKSPACE, "workspace too small%s");
     if (((uintptr_t)ws & 255) != 0) return fail(SSTAR_B200_EINVAL, "workspace must be 256-byte aligned%s");
     (void)device;
     return 0;
@@ -606,7 +609,7 @@ size_t sstar_b200_workspace_bytes(int64_t V, int32_t R, int32_t T, int32_t W, in
 int sstar_b200_pack(int device, void *stream, const int8_t *d_ref_gt, const int8_t *d_tgt_gt, int64_t V,
                     int32_t R, int32_t T, void *d_workspace, size_t workspace_bytes) {
     WsLayout L; int algo;
-    int rc = check_common(device, V, R, T, 0, d_workspace, workspace_bytes, nullptr, &L, &algo);
+    int rc = check_common(device, V, R, T, 0, d_workspace, workspace_bytes, nullptr, &L, &algo, true);
     if (rc) return rc;
     if (V > 0 && (!d_ref_gt || !d_tgt_gt)) return fail(SSTAR_B200_EINVAL, "null genotype pointer%s");
     DeviceGuard guard(device);
@@ -687,3 +690,79 @@ int sstar_b200_score_replicates(int device, void *stream, const int8_t *d_ref_gt
 }
 
 }  // extern "C"
+
+namespace {
+struct HostScratch {
+    size_t off_ref, off_tgt, off_pos, off_ws, off_we, off_score, off_nsnp, off_work, total;
+};
+HostScratch make_host_scratch(int64_t V, int32_t R, int32_t T, int32_t W, int32_t hint) {
+    HostScratch h;
+    size_t off = 0;
+    size_t v = (size_t)(V > 0 ? V : 1), w = (size_t)(W > 0 ? W : 1);
+    h.off_ref = off;   off = align_up(off + v * (size_t)R, 256);
+    h.off_tgt = off;   off = align_up(off + v * (size_t)T, 256);
+    h.off_pos = off;   off = align_up(off + v * 4, 256);
+    h.off_ws = off;    off = align_up(off + w * 4, 256);
+    h.off_we = off;    off = align_up(off + w * 4, 256);
+    h.off_score = off; off = align_up(off + w * (size_t)T * 8, 256);
+    h.off_nsnp = off;  off = align_up(off + w * (size_t)T * 4, 256);
+    h.off_work = off;  off += make_layout(V, T, W, hint).total;
+    h.total = off;
+    return h;
+}
+}  // namespace
+
+extern "C" size_t sstar_b200_host_scratch_bytes(int64_t V, int32_t R, int32_t T, int32_t W,
+                                                int32_t max_win_variants) {
+    if (V < 0 || R < 1 || T < 1 || W < 0) return 0;
+    return make_host_scratch(V, R, T, W, max_win_variants < 0 ? 0 : max_win_variants).total;
+}
+
+extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int8_t *h_ref_gt,
+                                             const int8_t *h_tgt_gt, const int32_t *h_pos, int64_t V,
+                                             int32_t R, int32_t T, const int32_t *h_win_start,
+                                             const int32_t *h_win_end, int32_t W, int32_t match_bonus,
+                                             int32_t max_mismatch, int32_t mismatch_penalty,
+                                             int64_t *h_score, int32_t *h_nsnp, void *d_scratch,
+                                             size_t scratch_bytes, const sstar_b200_options *opts) {
+    g_launches = 0;
+    int rc = check_shapes(V, R, T, W);
+    if (rc) return rc;
+    const int32_t hint = opts ? opts->max_win_variants : 0;
+    if (hint < 0) return fail(SSTAR_B200_EINVAL, "max_win_variants must be >= 0%s");
+    if (!d_scratch) return fail(SSTAR_B200_EINVAL, "scratch pointer is null%s");
+    if (((uintptr_t)d_scratch & 255) != 0) return fail(SSTAR_B200_EINVAL, "scratch must be 256-byte aligned%s");
+    const HostScratch h = make_host_scratch(V, R, T, W, hint);
+    if (scratch_bytes < h.total) return fail(SSTAR_B200_EWORKSPACE, "scratch too small%s");
+    if (W > 0 && (!h_win_start || !h_win_end || !h_score || !h_nsnp))
+        return fail(SSTAR_B200_EINVAL, "null window/output pointer%s");
+    if (V > 0 && (!h_pos || !h_tgt_gt || !h_ref_gt)) return fail(SSTAR_B200_EINVAL, "null input pointer%s");
+    uint8_t *d = (uint8_t *)d_scratch;
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        DeviceGuard guard(device);
+        if (guard.err != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+        if (V > 0) {
+            CUDA_TRY(cudaMemcpyAsync(d + h.off_pos, h_pos, (size_t)V * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(d + h.off_ref, h_ref_gt, (size_t)V * R, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(d + h.off_tgt, h_tgt_gt, (size_t)V * T, cudaMemcpyHostToDevice, st));
+        }
+        if (W > 0) {
+            CUDA_TRY(cudaMemcpyAsync(d + h.off_ws, h_win_start, (size_t)W * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(d + h.off_we, h_win_end, (size_t)W * 4, cudaMemcpyHostToDevice, st));
+        }
+    }
+    rc = sstar_b200_score_windows_ex(device, stream, (const int8_t *)(d + h.off_ref),
+                                     (const int8_t *)(d + h.off_tgt), (const int32_t *)(d + h.off_pos), V,
+                                     R, T, (const int32_t *)(d + h.off_ws), (const int32_t *)(d + h.off_we),
+                                     W, match_bonus, max_mismatch, mismatch_penalty,
+                                     (int64_t *)(d + h.off_score), (int32_t *)(d + h.off_nsnp),
+                                     d + h.off_work, scratch_bytes - h.off_work, opts);
+    if (rc) return rc;
+    if (W > 0) {
+        DeviceGuard guard(device);
+        CUDA_TRY(cudaMemcpyAsync(h_score, d + h.off_score, (size_t)W * T * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h_nsnp, d + h.off_nsnp, (size_t)W * T * 4, cudaMemcpyDeviceToHost, st));
+    }
+    return 0;
+}

@@ -191,9 +191,45 @@ class ScoreEngine:
         dev.copy_(pin, non_blocking=True)
         return dev
 
-    def score_host(self, ref_gts, tgt_gts, pos, win_start, win_end, match_bonus=5000, max_mismatch=5,
-                   mismatch_penalty=-10000, algo="auto"):
-        """numpy in, numpy out: (score[W,T] int64 with NAN_SENTINEL, nsnp[W,T] int32)."""
+    def score_pinned(self, ref_p, tgt_p, pos_p, ws_p, we_p, score_p, nsnp_p, match_bonus=5000,
+                     max_mismatch=5, mismatch_penalty=-10000, algo="auto", max_win_variants=0,
+                     stream=None, sync=True):
+        """End-to-end call on HOST tensors (page-locked torch CPU tensors): one C-ABI call enqueues
+        H2D copies, the kernels and the D2H copies of both result tables.
+
+        ref_p int8 [V,R], tgt_p int8 [V,T], pos_p int32 [V], ws_p/we_p int32 [W],
+        score_p int64 [W,T] and nsnp_p int32 [W,T] (outputs, written when the stream has synced).
+        """
+        V, R = ref_p.shape
+        T = tgt_p.shape[1]
+        W = ws_p.shape[0]
+        need = self.lib.sstar_b200_host_scratch_bytes(V, R, T, W, int(max_win_variants))
+        if need == 0:
+            raise SstarB200Error("invalid shapes for scratch sizing")
+        scratch = self._dbuf("host_scratch", need, self.torch.uint8)
+        opts = _cabi.Options(algo=_cabi.ALGOS[algo], max_win_variants=int(max_win_variants))
+        s = stream if stream is not None else self.torch.cuda.current_stream(self.tdev)
+        rc = self.lib.sstar_b200_score_windows_host(
+            self.device, ctypes.c_void_p(s.cuda_stream), ref_p.data_ptr(), tgt_p.data_ptr(),
+            pos_p.data_ptr(), V, R, T, ws_p.data_ptr(), we_p.data_ptr(), W, int(match_bonus),
+            int(max_mismatch), int(mismatch_penalty), score_p.data_ptr(), nsnp_p.data_ptr(),
+            scratch.data_ptr(), scratch.numel(), ctypes.byref(opts))
+        _cabi.check(rc)
+        self.launches = self.lib.sstar_b200_last_launch_count()
+        if sync:
+            s.synchronize()
+
+    def _pin_copy(self, key, arr: np.ndarray, tdtype, shape):
+        n = arr.size
+        pin = self._pbuf("pin_" + key, n, tdtype)[:n]
+        if n:
+            pin.copy_(self.torch.from_numpy(arr.reshape(-1)))
+        return pin.view(*shape)
+
+    def score_host_async(self, ref_gts, tgt_gts, pos, win_start, win_end, match_bonus=5000,
+                         max_mismatch=5, mismatch_penalty=-10000, algo="auto"):
+        """Enqueue one chromosome (numpy in) and return a handle for :meth:`wait`.
+        One call may be in flight per engine (the pinned staging buffers are reused)."""
         torch = self.torch
         ref = as_int8(ref_gts, "ref_gts")
         tgt = as_int8(tgt_gts, "tgt_gts")
@@ -208,22 +244,29 @@ class ScoreEngine:
         we = np.ascontiguousarray(win_end, dtype=np.int32)
         W = ws.shape[0]
         hint = max_window_variants(p, ws, we)
+        score_h = self._pbuf("pin_score", W * T, torch.int64)[:W * T].view(W, T)
+        nsnp_h = self._pbuf("pin_nsnp", W * T, torch.int32)[:W * T].view(W, T)
         with torch.cuda.device(self.tdev):
-            ref_d = self._h2d("ref", ref, torch.int8).view(V, R)
-            tgt_d = self._h2d("tgt", tgt, torch.int8).view(V, T)
-            pos_d = self._h2d("pos", p, torch.int32)
-            ws_d = self._h2d("ws", ws, torch.int32)
-            we_d = self._h2d("we", we, torch.int32)
-            score_d = self._dbuf("score", W * T, torch.int64)[:W * T].view(W, T)
-            nsnp_d = self._dbuf("nsnp", W * T, torch.int32)[:W * T].view(W, T)
-            self.score_device(ref_d, tgt_d, pos_d, ws_d, we_d, match_bonus, max_mismatch,
-                              mismatch_penalty, algo=algo, max_win_variants=hint, out=(score_d, nsnp_d))
-            score_h = self._pbuf("pin_score", W * T, torch.int64)[:W * T]
-            nsnp_h = self._pbuf("pin_nsnp", W * T, torch.int32)[:W * T]
-            score_h.copy_(score_d.view(-1), non_blocking=True)
-            nsnp_h.copy_(nsnp_d.view(-1), non_blocking=True)
-            torch.cuda.current_stream(self.tdev).synchronize()
-        return score_h.numpy().reshape(W, T).copy(), nsnp_h.numpy().reshape(W, T).copy()
+            stream = torch.cuda.current_stream(self.tdev)
+            self.score_pinned(self._pin_copy("ref", ref, torch.int8, (V, R)),
+                              self._pin_copy("tgt", tgt, torch.int8, (V, T)),
+                              self._pin_copy("pos", p, torch.int32, (V,)),
+                              self._pin_copy("ws", ws, torch.int32, (W,)),
+                              self._pin_copy("we", we, torch.int32, (W,)),
+                              score_h, nsnp_h, match_bonus, max_mismatch, mismatch_penalty, algo=algo,
+                              max_win_variants=hint, stream=stream, sync=False)
+        return (stream, score_h, nsnp_h)
+
+    def wait(self, handle):
+        stream, score_h, nsnp_h = handle
+        stream.synchronize()
+        return score_h.numpy().copy(), nsnp_h.numpy().copy()
+
+    def score_host(self, ref_gts, tgt_gts, pos, win_start, win_end, match_bonus=5000, max_mismatch=5,
+                   mismatch_penalty=-10000, algo="auto"):
+        """numpy in, numpy out: (score[W,T] int64 with NAN_SENTINEL, nsnp[W,T] int32)."""
+        return self.wait(self.score_host_async(ref_gts, tgt_gts, pos, win_start, win_end, match_bonus,
+                                               max_mismatch, mismatch_penalty, algo=algo))
 
     def score_replicates_host(self, ref_gts, tgt_gts, pos, rep_offset, win_start, win_end,
                               match_bonus=5000, max_mismatch=5, mismatch_penalty=-10000, algo="auto"):

@@ -1,0 +1,80 @@
+"""Columnar result table + the byte-exact TSV emitter.
+
+The reference builds one dict per (window, sample) row and lets pandas print them
+(sstar/feature_vector_preprocessor.py:139-183, sstar/preprocess.py:117-122).  Here the results stay
+as the two ``[W, T]`` arrays the GPU produced; rows / dicts are materialised only on request.
+
+Text format reproduced from ``DataFrame.to_csv(sep="\\t", index=False, na_rep="NA")``:
+float score column printed as ``51470.0`` (``repr`` of an integral float), NaN as ``NA``,
+integer columns plain, ``\\n`` line ends, header ``Chromosome .. Region_ind_SNP_number``.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from ._cabi import NAN_SENTINEL
+
+COLUMNS = ["Chromosome", "Start", "End", "Sample", "S*_score", "Region_ind_SNP_number"]
+
+
+def sample_labels(tgt_samples, ploidy: int, is_phased: bool) -> list[str]:
+    """Row labels, sstar/feature_vector_preprocessor.py:162-178."""
+    if is_phased:
+        return [f"{tgt_samples[i // ploidy]}_{i % ploidy + 1}" for i in range(len(tgt_samples) * ploidy)]
+    return [tgt_samples[i] for i in range(len(tgt_samples))]
+
+
+class FeatureTable:
+    def __init__(self, chr_name, win_start, win_end, labels, score, nsnp, replicate=None):
+        self.chr_name = chr_name
+        self.win_start = np.asarray(win_start)
+        self.win_end = np.asarray(win_end)
+        self.labels = list(labels)
+        self.score = np.asarray(score)
+        self.nsnp = np.asarray(nsnp)
+        self.replicate = replicate
+        W, T = self.score.shape
+        if len(self.labels) != T or self.win_start.shape[0] != W or self.nsnp.shape != (W, T):
+            raise ValueError("inconsistent feature table shapes")
+
+    def __len__(self):
+        return self.score.size
+
+    def rows(self) -> list[dict]:
+        """The reference's row dicts, in (window, sample) order."""
+        out = []
+        for w in range(self.score.shape[0]):
+            s, e = int(self.win_start[w]), int(self.win_end[w])
+            sc, ns = self.score[w].tolist(), self.nsnp[w].tolist()
+            for t, lab in enumerate(self.labels):
+                row = {"Chromosome": self.chr_name, "Start": s, "End": e, "Sample": lab,
+                       "S*_score": np.nan if sc[t] == NAN_SENTINEL else float(sc[t]),
+                       "Region_ind_SNP_number": int(ns[t])}
+                if self.replicate is not None:
+                    row["Replicate"] = self.replicate[w]
+                out.append(row)
+        return out
+
+    def to_tsv(self, path, header: bool = True, mode: str = "w") -> None:
+        """Byte-identical to the reference's ``pd.DataFrame(rows).to_csv(sep='\\t', na_rep='NA')``."""
+        out_dir = os.path.dirname(str(path))
+        if out_dir:
+            os.makedirs(out_dir, exist_ok=True)
+        W, T = self.score.shape
+        chrom = str(self.chr_name)
+        with open(path, mode) as fh:
+            if header:
+                fh.write("\t".join(COLUMNS) + "\n")
+            block = 4096
+            for w0 in range(0, W, block):
+                w1 = min(W, w0 + block)
+                parts = []
+                for w in range(w0, w1):
+                    head = f"{chrom}\t{int(self.win_start[w])}\t{int(self.win_end[w])}\t"
+                    sc, ns = self.score[w].tolist(), self.nsnp[w].tolist()
+                    parts.extend(
+                        f"{head}{lab}\tNA\t{n}\n" if s == NAN_SENTINEL else f"{head}{lab}\t{s}.0\t{n}\n"
+                        for lab, s, n in zip(self.labels, sc, ns))
+                fh.write("".join(parts))

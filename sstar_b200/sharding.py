@@ -1,0 +1,85 @@
+"""Multi-GPU sharding of one chromosome by window range.
+
+Windows are independent, so there is no collective on the data path: each GPU receives the
+variant rows its window range touches (its own step range plus a halo of ``win_len - win_step``
+bp), scores them, and the host concatenates the ``[W_g, T]`` blocks in window order -- the
+equivalent of the reference's gather + stable sort (sstar/mp_manager.py:172-179,
+sstar/preprocess.py:117).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def visible_devices(devices=None) -> list[int]:
+    """``devices`` argument > ``SSTAR_GPUS`` env ("4" or "0,2,3") > [0]."""
+    if devices is None:
+        env = os.environ.get("SSTAR_GPUS", "").strip()
+        if not env:
+            return [0]
+        devices = [int(x) for x in env.split(",")] if "," in env else int(env)
+    if isinstance(devices, int):
+        return list(range(devices))
+    return [int(d) for d in devices]
+
+
+def plan_window_shards(pos, win_start, win_end, n_shards: int):
+    """Contiguous window ranges with ~equal (variants-in-window) work.
+
+    -> list of (w0, w1, k0, k1): windows [w0, w1) need variant rows [k0, k1).
+    Shards may be fewer than ``n_shards`` when there are few windows; empty shards are dropped.
+    """
+    pos = np.asarray(pos)
+    ws = np.asarray(win_start, dtype=np.int64)
+    we = np.asarray(win_end, dtype=np.int64)
+    W = ws.shape[0]
+    if W == 0:
+        return []
+    lo = np.searchsorted(pos, ws, side="left")
+    hi = np.searchsorted(pos, we, side="right")
+    hi = np.maximum(hi, lo)
+    work = np.cumsum((hi - lo) + 8)  # +8: fixed cost per window
+    n_shards = max(1, min(int(n_shards), W))
+    cuts = [0]
+    for s in range(1, n_shards):
+        cuts.append(int(np.searchsorted(work, work[-1] * s / n_shards, side="left")) + 1)
+    cuts.append(W)
+    shards = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        a, b = min(a, W), min(b, W)
+        if b <= a:
+            continue
+        k0, k1 = int(lo[a:b].min()), int(hi[a:b].max())
+        shards.append((a, b, k0, max(k1, k0)))
+    return shards
+
+
+def score_chromosome(ref_gts, tgt_gts, pos, win_start, win_end, match_bonus, max_mismatch,
+                     mismatch_penalty, devices=None, algo="auto"):
+    """All windows of one chromosome on one or several GPUs -> (score[W,T], nsnp[W,T])."""
+    from .engine import as_int8, check_positions, get_engine
+    devs = visible_devices(devices)
+    ref = as_int8(ref_gts, "ref_gts")
+    tgt = as_int8(tgt_gts, "tgt_gts")
+    p = check_positions(pos)
+    ws = np.asarray(win_start, dtype=np.int64)
+    we = np.asarray(win_end, dtype=np.int64)
+    if ws.size and (ws.min() < -(2 ** 31) or we.max() > 2 ** 31 - 1):
+        raise ValueError("window coordinates do not fit int32")
+    if len(devs) == 1:
+        return get_engine(devs[0]).score_host(ref, tgt, p, ws, we, match_bonus, max_mismatch,
+                                              mismatch_penalty, algo=algo)
+    W, T = ws.shape[0], tgt.shape[1]
+    score = np.empty((W, T), dtype=np.int64)
+    nsnp = np.empty((W, T), dtype=np.int32)
+    pending = []
+    for dev, (w0, w1, k0, k1) in zip(devs, plan_window_shards(p, ws, we, len(devs))):
+        eng = get_engine(dev)
+        handle = eng.score_host_async(ref[k0:k1], tgt[k0:k1], p[k0:k1], ws[w0:w1], we[w0:w1],
+                                      match_bonus, max_mismatch, mismatch_penalty, algo=algo)
+        pending.append((w0, w1, eng, handle))
+    for w0, w1, eng, handle in pending:  # host gather, window order
+        score[w0:w1], nsnp[w0:w1] = eng.wait(handle)
+    return score, nsnp
