@@ -38,29 +38,51 @@ WORKLOADS = {
            "C2: synthetic 10 Mb msprime-style chromosome, 100 ref + 50 target diploids (unphased), "
            "50 kb windows / 10 kb step"),
     "c2-small": (1_000_000, 100, 50, False, 50_000, 10_000, "C2 shape at 1 Mb (debug)"),
+    # large shapes (generated on the device; not the headline line -- roofline evidence)
+    "c3-shard": (31_250_000, 500, 500, True, 50_000, 10_000,
+                 "C3 shard: 1/8 of a 250 Mb chromosome, 500 ref + 500 target diploids, haplotype mode "
+                 "(R = T = 1000 columns), 50 kb / 10 kb"),
+    "c4-shard": (30_000_000, 100, 2000, False, 50_000, 10_000,
+                 "C4 shard: 30 Mb, 100 ref + 2000 target diploids (unphased), 50 kb / 10 kb"),
+    "c5": (0, 5, 10, False, 50_000, 50_000, "C5 (see bench_large.py)"),
 }
+LARGE = {"c3-shard", "c4-shard"}
 
 
 def make_workload(name, rank):
-    from sstar_b200.synth import regular_windows, synth_chromosome
+    from sstar_b200.synth import regular_windows, synth_chromosome, synth_chromosome_device
     length, n_ref, n_tgt, phased, wl, wstep, desc = WORKLOADS[name]
     seed = 12345 + 1 + 1000 * rank
-    ref, tgt, pos = synth_chromosome(length, n_ref, n_tgt, phased, seed)
+    if name in LARGE:
+        import torch
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        r, t, p = synth_chromosome_device(torch, dev, length, n_ref, n_tgt, phased, seed)
+        ref, tgt, pos = r.cpu().numpy(), t.cpu().numpy(), p.cpu().numpy()
+        del r, t, p
+        torch.cuda.empty_cache()
+    else:
+        ref, tgt, pos = synth_chromosome(length, n_ref, n_tgt, phased, seed)
     ws, we = regular_windows(pos, wl, wstep)
     return dict(ref=ref, tgt=tgt, pos=pos, ws=ws, we=we, seed=seed, desc=desc, name=name)
 
 
 def workload_stats(wk):
+    """Shape + work statistics; n (carried ref-absent sites per unit) is exact for T <= 64 columns
+    and estimated from a 64-column sample beyond that."""
     pos, ws, we = wk["pos"], wk["ws"], wk["we"]
-    absent = wk["ref"].astype(np.int32).sum(axis=1) == 0
-    car = ((wk["tgt"] != 0) & absent[:, None]).astype(np.int32)
-    csum = np.concatenate([np.zeros((1, car.shape[1]), np.int64), np.cumsum(car, axis=0)])
+    absent = wk["ref"].sum(axis=1, dtype=np.int32) == 0
     lo = np.searchsorted(pos, ws, side="left")
     hi = np.searchsorted(pos, we, side="right")
+    T = wk["tgt"].shape[1]
+    cols = np.arange(T) if T <= 64 else np.unique(np.linspace(0, T - 1, 64).astype(int))
+    car = ((wk["tgt"][:, cols] != 0) & absent[:, None]).astype(np.int64)
+    csum = np.concatenate([np.zeros((1, car.shape[1]), np.int64), np.cumsum(car, axis=0)])
     n = csum[hi] - csum[lo]
-    return dict(V=int(pos.size), R=int(wk["ref"].shape[1]), T=int(wk["tgt"].shape[1]), W=int(ws.size),
-                units=int(ws.size * wk["tgt"].shape[1]), sum_n=int(n.sum()),
-                sum_pairs=int((n * (n - 1) // 2).sum()), max_n=int(n.max()),
+    scale = T / len(cols)
+    return dict(V=int(pos.size), R=int(wk["ref"].shape[1]), T=int(T), W=int(ws.size),
+                units=int(ws.size * T), sum_n=int(n.sum() * scale),
+                sum_pairs=int((n * (n - 1) // 2).sum() * scale), max_n=int(n.max()),
+                n_exact=bool(T <= 64), absent_fraction=float(absent.mean()),
                 mean_window_variants=float((hi - lo).mean()), max_window_variants=int((hi - lo).max()))
 
 
@@ -294,13 +316,14 @@ def run_ours(args, world, rank, local):
     cpu = None
     if rank == 0:
         from oracle import c_oracle
-        so, no = c_oracle.score_windows(wk["ref"], wk["tgt"], wk["pos"], wk["ws"], wk["we"], *PARAMS)
-        ok = bool(np.array_equal(score_p.numpy(), so) and np.array_equal(nsnp_p.numpy(), no)
-                  and np.array_equal(score_d.cpu().numpy(), so))
+        sel = np.arange(W) if wk["name"] not in LARGE else np.unique(np.linspace(0, W - 1, 48).astype(int))
+        so, no = c_oracle.score_windows(wk["ref"], wk["tgt"], wk["pos"], wk["ws"][sel], wk["we"][sel], *PARAMS)
+        ok = bool(np.array_equal(score_p.numpy()[sel], so) and np.array_equal(nsnp_p.numpy()[sel], no)
+                  and np.array_equal(score_d.cpu().numpy()[sel], so))
         parity = {"checked_units": int(so.size), "bit_exact_vs_oracle": ok}
         if not ok:
             raise SystemExit("bench: GPU result differs from the oracle -- refusing to report a number")
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and wk["name"] not in LARGE:
             from oracle.cpu_baseline import CpuBaseline
             cores = os.cpu_count() or 1
             base = CpuBaseline(wk["ref"], wk["tgt"], wk["pos"], wk["ws"], wk["we"], PARAMS, cores)
@@ -311,7 +334,8 @@ def run_ours(args, world, rank, local):
             dt, res = base.run(sample)
             base.close()
             for w, (s, n) in res.items():  # the CPU-scored units must equal the GPU's
-                assert np.array_equal(s, so[w]) and np.array_equal(n, no[w]), "CPU port != GPU"
+                assert np.array_equal(s, score_p.numpy()[w]) and np.array_equal(n, nsnp_p.numpy()[w]), \
+                    "CPU port != GPU"
             cpu = {"value": n_win * T / dt, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{n_win} of {W} windows x {T} columns of the {wk['name']} chromosome, one pass "
                              f"({dt:.2f} s wall); numpy port of the reference recipe, pool pre-forked and warm, "

@@ -1,0 +1,78 @@
+// sstar_b200 -- shared definitions of the CUDA kernels and the host-side C-ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sstar {
+
+constexpr int kMinPairDistance = 10;  // sstar/sstar.py:195: pairs closer than 10 bp never link
+constexpr int64_t kNegInf64 = INT64_MIN;
+
+constexpr int kPackThreads = 256;
+constexpr int kScoreMaxThreads = 128;
+constexpr int kRingSlots = 16;      // >= 10: at most 10 distinct integer positions lie within 9 bp
+constexpr int kPairWarps = 4;
+constexpr int kPairSmemCap = 1024;  // pairwise list entries per warp kept in shared memory
+constexpr int kNumSM = 148;
+
+// First 64 bytes of the workspace.
+struct WsHeader {
+    uint32_t status;
+    int32_t n_slow;  // windows routed to the pairwise kernel (written by prep, bumped by K2)
+    int32_t pad[14];
+};
+
+struct WsLayout {
+    int64_t G;   // 32-variant groups
+    int32_t Tp;  // plane row pitch in words (T rounded up to 32)
+    size_t off_absent, off_exotic, off_carried, off_two, off_win_lo, off_win_hi, off_slow, off_arena;
+    size_t arena_entries;
+    size_t total;
+};
+
+struct BoundsArgs {
+    const int32_t *pos;
+    const int32_t *win_start, *win_end;  // [W] or null (then fixed_start / fixed_end)
+    const int32_t *seg;                  // [W+1] search segment per window, or null (0..V)
+    int32_t fixed_start, fixed_end;
+    int32_t V, W;
+    int32_t *win_lo, *win_hi, *slow_list;
+    WsHeader *hdr;
+    int force_slow;
+};
+
+struct PackArgs {
+    const int8_t *ref, *tgt;
+    int32_t V, R, T, Tp;
+    int32_t G, gpc;
+    uint32_t ref_tile_bytes;  // smem bytes reserved per tile (incl. alignment slack)
+    uint32_t tgt_tile_bytes;
+    uint32_t *absent_bits, *exotic, *carried, *two;
+};
+
+struct ScoreArgs {
+    const int32_t *pos;
+    const int8_t *tgt;
+    const uint32_t *absent_bits, *exotic, *carried, *two;
+    const int32_t *win_lo, *win_hi;
+    const int32_t *win_start, *win_end;  // or null: fixed_start / fixed_end
+    int32_t fixed_start, fixed_end;
+    int32_t *slow_list;
+    WsHeader *hdr;
+    int32_t T, Tp, W, tchunks;
+    int32_t bonus, max_mm, penalty;
+    int64_t *score;
+    int32_t *nsnp;
+    uint8_t *arena;  // pairwise only
+    uint64_t arena_entries;
+};
+
+__host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-
+// serialization attribute may start while its predecessor drains; it must not touch the
+// predecessor's outputs before pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
+}  // namespace sstar

@@ -1,0 +1,303 @@
+// sstar_b200 -- "prep" launch: genotype packing (K1) and window bounds (K0) in ONE grid.
+//
+// CTAs [0, n_pack) pack 32-variant groups into bit-planes; CTAs [n_pack, ...) resolve window
+// bounds with a warp-cooperative 32-ary search.  The two jobs are independent, so fusing them
+// takes the latency-bound search off the critical path of small problems.
+#pragma once
+#include "common.cuh"
+
+namespace sstar {
+
+// ------------------------------------------------------------------------------------------
+// K0: window bounds -- sstar/generators/window_data_generator.py:113 (pos >= start) & (pos <= end)
+// becomes [lo, hi) = [lower_bound(start), lower_bound(end + 1)) on the ascending position array.
+// One warp per window; each round 32 lanes probe 32 pivots, shrinking the range ~33x.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t warp_lower_bound(const int32_t *__restrict__ pos, int32_t lo, int32_t hi,
+                                                    int64_t x, int lane) {
+    // invariant: pos[k] < x for k < lo, pos[k] >= x for k >= hi
+    while (hi - lo > 32) {
+        const int32_t step = (hi - lo + 32) / 33;
+        const int32_t idx = lo + step * (lane + 1) - 1;
+        const bool below = idx < hi && (int64_t)__ldg(pos + idx) < x;
+        const int c = __popc(__ballot_sync(0xffffffffu, below));  // monotone: the first c lanes
+        const int32_t new_hi = lo + step * (c + 1) - 1;  // pivot of lane c, the first one not below x
+        if (c > 0) lo = lo + step * c;
+        if (c < 32 && new_hi < hi) hi = new_hi;
+    }
+    const int32_t idx = lo + lane;
+    const bool below = idx < hi && (int64_t)__ldg(pos + idx) < x;
+    return lo + __popc(__ballot_sync(0xffffffffu, below));
+}
+
+__device__ __forceinline__ void bounds_block(const BoundsArgs &a, int block, int nthreads, int tid) {
+    const int lane = tid & 31;
+    const int w = block * (nthreads >> 5) + (tid >> 5);
+    if (block == 0 && tid == 0) a.hdr->n_slow = a.force_slow ? a.W : 0;
+    if (w >= a.W) return;
+    const int32_t sb = a.seg ? a.seg[w] : 0;
+    const int32_t se = a.seg ? a.seg[w + 1] : a.V;
+    const int64_t s = a.win_start ? a.win_start[w] : a.fixed_start;
+    const int64_t e = a.win_end ? a.win_end[w] : a.fixed_end;
+    const int32_t lo = warp_lower_bound(a.pos, sb, se, s, lane);
+    int32_t hi = warp_lower_bound(a.pos, lo, se, e + 1, lane);
+    if (hi < lo) hi = lo;
+    if (lane == 0) {
+        a.win_lo[w] = lo;
+        a.win_hi[w] = hi;
+        if (a.force_slow) a.slow_list[w] = w;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: pack.  One CTA per `gpc` groups of 32 variants.
+//
+// Staging: the CTA's rows of a row-major int8 matrix are ONE contiguous byte span whatever the
+// row pitch is, so it moves global -> shared as aligned 128-bit streaming loads (the source's
+// 16-byte phase is kept; head/tail bytes go separately).
+// Compute (SIMD within a 32-bit word, 4 genotype bytes at a time):
+//   A  ref rows   : signed row sum by dp4a, one warp per row            -> absent flag  (sstar.py:87-88)
+//   B  tgt columns: a thread owns 4 adjacent columns x 32 rows; per row one (unaligned-capable)
+//                   word read, "byte != 0" and "byte == 2" folded to bit 0 of each byte and
+//                   shifted into per-8-row accumulators; PRMT transposes them into 4 column
+//                   words per plane; masked by the group's absent word   (sstar.py:163-164)
+//   Genotypes outside {0,1,2} are detected by two running ORs; only a thread that sees one
+//   rescans its 32x4 bytes exactly (absent rows, real columns) and raises the group's flag.
+// Output planes are word-major [G][Tp]: 128-bit coalesced stores here, coalesced loads in K2.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream_v4(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// Returns the shared-memory byte offset (from sdst) at which byte 0 of the span landed.
+__device__ __forceinline__ uint32_t stage_span(uint8_t *sdst, const int8_t *gsrc, size_t nbytes, int tid,
+                                               int nthreads) {
+    const uint32_t phase = (uint32_t)((uintptr_t)gsrc & 15);
+    uint8_t *s0 = sdst + phase;
+    size_t head = (16 - phase) & 15;
+    if (head > nbytes) head = nbytes;
+    if ((size_t)tid < head) s0[tid] = (uint8_t)gsrc[tid];
+    const size_t nvec = (nbytes - head) >> 4;
+    const uint4 *gv = reinterpret_cast<const uint4 *>(gsrc + head);
+    uint4 *sv = reinterpret_cast<uint4 *>(s0 + head);
+    size_t i = tid;
+    for (; i + 3 * (size_t)nthreads < nvec; i += 4 * (size_t)nthreads) {  // 4 loads in flight / thread
+        const uint4 v0 = ldg_stream_v4(gv + i);
+        const uint4 v1 = ldg_stream_v4(gv + i + nthreads);
+        const uint4 v2 = ldg_stream_v4(gv + i + 2 * (size_t)nthreads);
+        const uint4 v3 = ldg_stream_v4(gv + i + 3 * (size_t)nthreads);
+        sv[i] = v0;
+        sv[i + nthreads] = v1;
+        sv[i + 2 * (size_t)nthreads] = v2;
+        sv[i + 3 * (size_t)nthreads] = v3;
+    }
+    for (; i < nvec; i += nthreads) sv[i] = ldg_stream_v4(gv + i);
+    const size_t done = head + (nvec << 4);
+    if (done + tid < nbytes) s0[done + tid] = (uint8_t)gsrc[done + tid];  // tail < 16 bytes
+    return phase;
+}
+
+// 32-bit read at an arbitrary byte offset of a 4-byte-aligned shared region.
+template <bool kAligned>
+__device__ __forceinline__ uint32_t lds_word(const uint8_t *region, uint32_t off) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(region + (off & ~3u));
+    if (kAligned) return w[0];
+    return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
+}
+
+// 4x4 byte transpose: a0..a3 hold (rows 0-7, 8-15, 16-23, 24-31) x (4 columns, one per byte);
+// c[k] becomes the 32-row word of column k.
+__device__ __forceinline__ void transpose4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t c[4]) {
+    const uint32_t t0 = __byte_perm(a0, a1, 0x5140), t1 = __byte_perm(a2, a3, 0x5140);
+    const uint32_t t2 = __byte_perm(a0, a1, 0x7362), t3 = __byte_perm(a2, a3, 0x7362);
+    c[0] = __byte_perm(t0, t1, 0x5410);
+    c[1] = __byte_perm(t0, t1, 0x7632);
+    c[2] = __byte_perm(t2, t3, 0x5410);
+    c[3] = __byte_perm(t2, t3, 0x7632);
+}
+
+template <bool kAligned>
+__device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int32_t g0, int ng, int nrows,
+                                          uint32_t ref_phase, uint32_t tgt_phase) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nwarps = kPackThreads / 32;
+    uint8_t *s_flag = smem;                                                  // [gpc*32] absent per row
+    uint32_t *s_word = reinterpret_cast<uint32_t *>(smem + a.gpc * 32);      // [gpc] absent word
+    uint32_t *s_exo = s_word + a.gpc;                                        // [gpc] exotic flag
+    const uint8_t *s_ref = smem + a.gpc * 32 + align16(a.gpc * 8);
+    const uint8_t *s_tgt = s_ref + a.ref_tile_bytes;
+
+    // A: signed row sums of the reference panel
+    const int nwr = (a.R + 3) >> 2;
+    const uint32_t last_mask = (a.R & 3) ? ((1u << (8 * (a.R & 3))) - 1u) : 0xffffffffu;
+    for (int r = warp; r < ng * 32; r += nwarps) {
+        int sum = 0;
+        if (r < nrows) {
+            const uint32_t row = ref_phase + (uint32_t)r * (uint32_t)a.R;
+            for (int i = lane; i < nwr; i += 32) {
+                uint32_t w = lds_word<kAligned>(s_ref, row + 4u * i);
+                if (i == nwr - 1) w &= last_mask;
+                sum = __dp4a((int)w, 0x01010101, sum);
+            }
+        }
+        sum = __reduce_add_sync(0xffffffffu, sum);
+        if (lane == 0) s_flag[r] = (r < nrows) && (sum == 0);
+    }
+    __syncthreads();
+    for (int gl = warp; gl < ng; gl += nwarps) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, s_flag[gl * 32 + lane] != 0);
+        if (lane == 0) {
+            s_word[gl] = bits;
+            s_exo[gl] = 0;
+            a.absent_bits[g0 + gl] = bits;
+        }
+    }
+    __syncthreads();
+
+    // B: 4 columns x 32 rows per thread
+    const int nq = (a.T + 3) >> 2;
+    const int nitems = ng * nq;
+    for (int it = tid; it < nitems; it += kPackThreads) {
+        const int gl = it / nq, q = it - gl * nq;
+        const uint32_t base = tgt_phase + (uint32_t)(gl * 32) * (uint32_t)a.T + 4u * q;
+        uint32_t nz[4], tw[4], e_or = 0, e_and = 0;
+#pragma unroll
+        for (int blk = 0; blk < 4; ++blk) {
+            uint32_t an = 0, at = 0;
+#pragma unroll
+            for (int rr = 7; rr >= 0; --rr) {  // row 7 first: it ends up in bit 7 of each byte
+                const uint32_t w = lds_word<kAligned>(s_tgt, base + (uint32_t)(blk * 8 + rr) * (uint32_t)a.T);
+                const uint32_t h = w >> 1;
+                an = an + an + ((w | h) & 0x01010101u);  // byte in {1,2,3} -> bit 0
+                at = at + at + (h & 0x01010101u);        // byte in {2,3}   -> bit 0
+                e_or |= w;
+                e_and |= w & h;
+            }
+            nz[blk] = an;
+            tw[blk] = at;
+        }
+        const uint32_t ab = s_word[gl];
+        uint32_t car[4], two[4];
+        transpose4(nz[0], nz[1], nz[2], nz[3], car);
+        transpose4(tw[0], tw[1], tw[2], tw[3], two);
+        const int ncol = min(4, a.T - 4 * q);
+        bool exotic = false;
+        if ((e_or & 0xfcfcfcfcu) | (e_and & 0x01010101u)) {
+            // a byte outside {0,1,2} somewhere in this 32x4 block (or in the padding bytes of a
+            // ragged last quad / tail rows): redo it exactly, byte by byte
+            const uint8_t *bytes = s_tgt + base;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c >= ncol) continue;
+                uint32_t m_nz = 0, m_two = 0;
+                for (int r = 0; r < 32; ++r) {
+                    const int b = (int8_t)bytes[(uint32_t)r * (uint32_t)a.T + c];
+                    const uint32_t isab = (ab >> r) & 1u;
+                    m_nz |= ((uint32_t)(b != 0) & isab) << r;
+                    m_two |= ((uint32_t)(b == 2) & isab) << r;
+                    exotic |= ((unsigned)b > 2u) && isab;
+                }
+                car[c] = m_nz;
+                two[c] = m_two;
+            }
+        }
+        const size_t o = (size_t)(g0 + gl) * a.Tp + 4 * q;
+        if (ncol == 4) {
+            *reinterpret_cast<uint4 *>(a.carried + o) = make_uint4(car[0] & ab, car[1] & ab, car[2] & ab, car[3] & ab);
+            *reinterpret_cast<uint4 *>(a.two + o) = make_uint4(two[0] & ab, two[1] & ab, two[2] & ab, two[3] & ab);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (c >= ncol) continue;
+                a.carried[o + c] = car[c] & ab;
+                a.two[o + c] = two[c] & ab;
+            }
+        }
+        if (exotic) atomicOr(&s_exo[gl], 1u);
+    }
+    __syncthreads();
+    if (tid < ng) a.exotic[g0 + tid] = s_exo[tid];
+}
+
+// Fallback for rows too wide to stage (32 * (R + T) bytes beyond shared memory): byte-wise from
+// global memory, same outputs.
+__device__ __forceinline__ void pack_tile_direct(const PackArgs &a, uint8_t *smem, int32_t g0, int ng, int nrows) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nwarps = kPackThreads / 32;
+    uint8_t *s_flag = smem;
+    uint32_t *s_word = reinterpret_cast<uint32_t *>(smem + a.gpc * 32);
+    uint32_t *s_exo = s_word + a.gpc;
+    const int8_t *rbase = a.ref + (size_t)g0 * 32 * a.R;
+    const int8_t *tbase = a.tgt + (size_t)g0 * 32 * a.T;
+    for (int r = warp; r < ng * 32; r += nwarps) {
+        int sum = 0;
+        if (r < nrows) {
+            const int8_t *row = rbase + (size_t)r * a.R;
+            for (int c = lane; c < a.R; c += 32) sum += row[c];
+        }
+        sum = __reduce_add_sync(0xffffffffu, sum);
+        if (lane == 0) s_flag[r] = (r < nrows) && (sum == 0);
+    }
+    __syncthreads();
+    for (int gl = warp; gl < ng; gl += nwarps) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, s_flag[gl * 32 + lane] != 0);
+        if (lane == 0) {
+            s_word[gl] = bits;
+            s_exo[gl] = 0;
+            a.absent_bits[g0 + gl] = bits;
+        }
+    }
+    __syncthreads();
+    const int nitems = ng * a.T;
+    for (int it = tid; it < nitems; it += kPackThreads) {
+        const int gl = it / a.T, t = it - gl * a.T;
+        const int rmax = min(32, nrows - gl * 32);
+        const int8_t *col = tbase + (size_t)(gl * 32) * a.T + t;
+        const uint32_t ab = s_word[gl];
+        uint32_t car = 0, two = 0, ex = 0;
+        for (int r = 0; r < rmax; ++r) {
+            const int b = col[(size_t)r * a.T];
+            const uint32_t isab = (ab >> r) & 1u;
+            car |= ((uint32_t)(b != 0) & isab) << r;
+            two |= ((uint32_t)(b == 2) & isab) << r;
+            ex |= (uint32_t)((unsigned)b > 2u) & isab;
+        }
+        const size_t o = (size_t)(g0 + gl) * a.Tp + t;
+        a.carried[o] = car;
+        a.two[o] = two;
+        if (ex) atomicOr(&s_exo[gl], 1u);
+    }
+    __syncthreads();
+    if (tid < ng) a.exotic[g0 + tid] = s_exo[tid];
+}
+
+// mode: 0 = staged word path, 1 = direct byte path
+__global__ void __launch_bounds__(kPackThreads) prep_kernel(PackArgs p, BoundsArgs b, int n_pack, int mode) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    pdl_launch_dependents();  // let the next kernel's CTAs get scheduled while this grid drains
+    if ((int)blockIdx.x >= n_pack) {
+        bounds_block(b, (int)blockIdx.x - n_pack, kPackThreads, threadIdx.x);
+        return;
+    }
+    const int32_t g0 = blockIdx.x * p.gpc;
+    const int ng = min(p.gpc, p.G - g0);
+    const int32_t k0 = g0 * 32;
+    const int nrows = min(ng * 32, p.V - k0);
+    if (mode == 1) {
+        pack_tile_direct(p, smem, g0, ng, nrows);
+        return;
+    }
+    uint8_t *s_ref = smem + p.gpc * 32 + align16(p.gpc * 8);
+    uint8_t *s_tgt = s_ref + p.ref_tile_bytes;
+    const uint32_t rph = stage_span(s_ref, p.ref + (size_t)k0 * p.R, (size_t)nrows * p.R, threadIdx.x, kPackThreads);
+    const uint32_t tph = stage_span(s_tgt, p.tgt + (size_t)k0 * p.T, (size_t)nrows * p.T, threadIdx.x, kPackThreads);
+    __syncthreads();
+    const bool aligned = ((rph | tph | (uint32_t)p.R | (uint32_t)p.T) & 3u) == 0;
+    if (aligned) pack_tile<true>(p, smem, g0, ng, nrows, rph, tph);
+    else         pack_tile<false>(p, smem, g0, ng, nrows, rph, tph);
+}
+
+}  // namespace sstar

@@ -172,3 +172,21 @@ def test_long_window_many_variants(eng):
 def test_rejects_unsorted_positions(eng):
     with pytest.raises(ValueError, match="strictly ascending"):
         eng.score_host(np.zeros((3, 1), np.int8), np.ones((3, 1), np.int8), [10, 5, 20], [1], [30])
+
+
+def test_window_bounds_every_range_length(eng):
+    # exercises the 32-ary warp search at every range length around its pivots (1..200 variants
+    # left and right of a window edge), checked through Region_ind_SNP_number and the scores
+    rng = np.random.default_rng(11)
+    V = 1500
+    pos = np.cumsum(rng.integers(1, 30, size=V)).astype(np.int32)
+    tgt = rng.choice([0, 1, 2], size=(V, 3), p=[0.5, 0.3, 0.2]).astype(np.int8)
+    ref = (rng.random((V, 2)) < 0.3).astype(np.int8)
+    ws, we = [], []
+    for k in range(0, 400):
+        ws.append(int(pos[k])); we.append(int(pos[min(V - 1, k + (k * 7) % 230)]))
+        ws.append(int(pos[0]) - 3); we.append(int(pos[k]) + (k % 3))
+        ws.append(int(pos[V - 1 - k])); we.append(int(pos[-1]) + 5)
+    so, no = c_oracle.score_windows(ref, tgt, pos, ws, we)
+    s, n = eng.score_host(ref, tgt, pos, ws, we)
+    assert np.array_equal(n, no) and np.array_equal(s, so)
