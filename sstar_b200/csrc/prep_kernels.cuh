@@ -72,30 +72,42 @@ __device__ __forceinline__ uint4 ldg_stream_v4(const uint4 *p) {
     return r;
 }
 
-// Returns the shared-memory byte offset (from sdst) at which byte 0 of the span landed.
-__device__ __forceinline__ uint32_t stage_span(uint8_t *sdst, const int8_t *gsrc, size_t nbytes, int tid,
+// ---- bulk asynchronous copy (TMA engine, SASS: UBLKCP) + mbarrier completion ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+
+// Fallback staging for spans the bulk engine cannot take (base not 16-byte aligned, ragged tail
+// tile): 128-bit streaming loads keeping the source's 16-byte phase.  Returns that phase, i.e.
+// the offset from sdst at which byte 0 of the span landed.
+__device__ __forceinline__ uint32_t stage_span(uint8_t *sdst, const int8_t *gsrc, uint32_t nbytes, int tid,
                                                int nthreads) {
     const uint32_t phase = (uint32_t)((uintptr_t)gsrc & 15);
     uint8_t *s0 = sdst + phase;
-    size_t head = (16 - phase) & 15;
+    uint32_t head = (16 - phase) & 15;
     if (head > nbytes) head = nbytes;
-    if ((size_t)tid < head) s0[tid] = (uint8_t)gsrc[tid];
-    const size_t nvec = (nbytes - head) >> 4;
+    if ((uint32_t)tid < head) s0[tid] = (uint8_t)gsrc[tid];
+    const uint32_t nvec = (nbytes - head) >> 4;
     const uint4 *gv = reinterpret_cast<const uint4 *>(gsrc + head);
     uint4 *sv = reinterpret_cast<uint4 *>(s0 + head);
-    size_t i = tid;
-    for (; i + 3 * (size_t)nthreads < nvec; i += 4 * (size_t)nthreads) {  // 4 loads in flight / thread
-        const uint4 v0 = ldg_stream_v4(gv + i);
-        const uint4 v1 = ldg_stream_v4(gv + i + nthreads);
-        const uint4 v2 = ldg_stream_v4(gv + i + 2 * (size_t)nthreads);
-        const uint4 v3 = ldg_stream_v4(gv + i + 3 * (size_t)nthreads);
-        sv[i] = v0;
-        sv[i + nthreads] = v1;
-        sv[i + 2 * (size_t)nthreads] = v2;
-        sv[i + 3 * (size_t)nthreads] = v3;
-    }
-    for (; i < nvec; i += nthreads) sv[i] = ldg_stream_v4(gv + i);
-    const size_t done = head + (nvec << 4);
+    for (uint32_t i = tid; i < nvec; i += nthreads) sv[i] = ldg_stream_v4(gv + i);
+    const uint32_t done = head + (nvec << 4);
     if (done + tid < nbytes) s0[done + tid] = (uint8_t)gsrc[done + tid];  // tail < 16 bytes
     return phase;
 }
@@ -130,17 +142,45 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
     const uint8_t *s_ref = smem + a.gpc * 32 + align16(a.gpc * 8);
     const uint8_t *s_tgt = s_ref + a.ref_tile_bytes;
 
-    // A: signed row sums of the reference panel
-    const int nwr = (a.R + 3) >> 2;
-    const uint32_t last_mask = (a.R & 3) ? ((1u << (8 * (a.R & 3))) - 1u) : 0xffffffffu;
+    // A: signed row sums of the reference panel (dp4a over the widest aligned vector)
+    const uint32_t ralign = (ref_phase | (uint32_t)a.R) & 15u;
     for (int r = warp; r < ng * 32; r += nwarps) {
         int sum = 0;
         if (r < nrows) {
             const uint32_t row = ref_phase + (uint32_t)r * (uint32_t)a.R;
-            for (int i = lane; i < nwr; i += 32) {
-                uint32_t w = lds_word<kAligned>(s_ref, row + 4u * i);
-                if (i == nwr - 1) w &= last_mask;
-                sum = __dp4a((int)w, 0x01010101, sum);
+            if (ralign == 0) {
+                const uint4 *vp = reinterpret_cast<const uint4 *>(s_ref + row);
+                const int nv = a.R >> 4;
+#pragma unroll 2
+                for (int i = lane; i < nv; i += 32) {
+                    const uint4 v = vp[i];
+                    sum = __dp4a((int)v.x, 0x01010101, sum);
+                    sum = __dp4a((int)v.y, 0x01010101, sum);
+                    sum = __dp4a((int)v.z, 0x01010101, sum);
+                    sum = __dp4a((int)v.w, 0x01010101, sum);
+                }
+            } else if ((ralign & 7u) == 0) {
+                const uint2 *vp = reinterpret_cast<const uint2 *>(s_ref + row);
+                const int nv = a.R >> 3;
+#pragma unroll 4
+                for (int i = lane; i < nv; i += 32) {
+                    const uint2 v = vp[i];
+                    sum = __dp4a((int)v.x, 0x01010101, sum);
+                    sum = __dp4a((int)v.y, 0x01010101, sum);
+                }
+            } else if ((ralign & 3u) == 0) {
+                const uint32_t *vp = reinterpret_cast<const uint32_t *>(s_ref + row);
+                const int nv = a.R >> 2;
+#pragma unroll 4
+                for (int i = lane; i < nv; i += 32) sum = __dp4a((int)vp[i], 0x01010101, sum);
+            } else {
+                const int nwr = (a.R + 3) >> 2;
+                const uint32_t last_mask = (a.R & 3) ? ((1u << (8 * (a.R & 3))) - 1u) : 0xffffffffu;
+                for (int i = lane; i < nwr; i += 32) {
+                    uint32_t w = lds_word<false>(s_ref, row + 4u * i);
+                    if (i == nwr - 1) w &= last_mask;
+                    sum = __dp4a((int)w, 0x01010101, sum);
+                }
             }
         }
         sum = __reduce_add_sync(0xffffffffu, sum);
@@ -275,13 +315,16 @@ __device__ __forceinline__ void pack_tile_direct(const PackArgs &a, uint8_t *sme
 }
 
 // mode: 0 = staged word path, 1 = direct byte path
-__global__ void __launch_bounds__(kPackThreads) prep_kernel(PackArgs p, BoundsArgs b, int n_pack, int mode) {
+__global__ void __launch_bounds__(kPackThreads)
+prep_kernel(const __grid_constant__ PackArgs p, const __grid_constant__ BoundsArgs b, int n_pack, int mode) {
     extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ __align__(8) uint64_t s_bar[2];
     pdl_launch_dependents();  // let the next kernel's CTAs get scheduled while this grid drains
     if ((int)blockIdx.x >= n_pack) {
         bounds_block(b, (int)blockIdx.x - n_pack, kPackThreads, threadIdx.x);
         return;
     }
+    const int tid = threadIdx.x;
     const int32_t g0 = blockIdx.x * p.gpc;
     const int ng = min(p.gpc, p.G - g0);
     const int32_t k0 = g0 * 32;
@@ -292,10 +335,28 @@ __global__ void __launch_bounds__(kPackThreads) prep_kernel(PackArgs p, BoundsAr
     }
     uint8_t *s_ref = smem + p.gpc * 32 + align16(p.gpc * 8);
     uint8_t *s_tgt = s_ref + p.ref_tile_bytes;
-    const uint32_t rph = stage_span(s_ref, p.ref + (size_t)k0 * p.R, (size_t)nrows * p.R, threadIdx.x, kPackThreads);
-    const uint32_t tph = stage_span(s_tgt, p.tgt + (size_t)k0 * p.T, (size_t)nrows * p.T, threadIdx.x, kPackThreads);
-    __syncthreads();
-    const bool aligned = ((rph | tph | (uint32_t)p.R | (uint32_t)p.T) & 3u) == 0;
+    const int8_t *gref = p.ref + (size_t)k0 * p.R;
+    const int8_t *gtgt = p.tgt + (size_t)k0 * p.T;
+    const uint32_t ref_bytes = (uint32_t)nrows * (uint32_t)p.R, tgt_bytes = (uint32_t)nrows * (uint32_t)p.T;
+    uint32_t rph = 0, tph = 0;
+    const bool bulk = ((((uintptr_t)gref | (uintptr_t)gtgt) & 15) == 0) && (((ref_bytes | tgt_bytes) & 15u) == 0);
+    if (bulk) {
+        // one thread hands both spans to the TMA engine; no registers, no issue slots for the copy
+        if (tid == 0) {
+            mbar_init(&s_bar[0], 1);
+            fence_mbar_init();
+            mbar_expect_tx(&s_bar[0], ref_bytes + tgt_bytes);
+            bulk_g2s(s_ref, gref, ref_bytes, &s_bar[0]);
+            bulk_g2s(s_tgt, gtgt, tgt_bytes, &s_bar[0]);
+        }
+        __syncthreads();  // barrier initialised before anyone polls it
+        mbar_wait(&s_bar[0], 0);
+    } else {
+        rph = stage_span(s_ref, gref, ref_bytes, tid, kPackThreads);
+        tph = stage_span(s_tgt, gtgt, tgt_bytes, tid, kPackThreads);
+        __syncthreads();
+    }
+    const bool aligned = ((tph | (uint32_t)p.T) & 3u) == 0;
     if (aligned) pack_tile<true>(p, smem, g0, ng, nrows, rph, tph);
     else         pack_tile<false>(p, smem, g0, ng, nrows, rph, tph);
 }

@@ -32,93 +32,123 @@ template <> struct Sentinel<int64_t> {
     static constexpr int64_t THR = -(int64_t(1) << 61);
 };
 
-template <typename acc_t>
+// Per-unit DP.  kStaged: the unit's plane words and the window's positions were staged in shared
+// memory by the CTA (thread-private columns car[j*bd+tid] / two[j*bd+tid], shared rel. positions);
+// otherwise everything is read from global memory (very long windows, unknown size hint).
+// Each lane walks ITS OWN set bits across word boundaries, so a warp iterates max_lane(n) times,
+// not sum_words max_lane(popc).
+template <typename acc_t, bool kStaged>
 __device__ __forceinline__ void prefix_dp_unit(const ScoreArgs &a, int t, int32_t lo, int32_t hi, int32_t p0,
-                                               uint8_t *ring_raw, int tid, int bd, int &n_out, int64_t &score_out) {
+                                               uint8_t *ring_raw, const uint32_t *s_car, const uint32_t *s_two,
+                                               const uint32_t *s_pos, int tid, int bd, int &n_out,
+                                               int64_t &score_out) {
     constexpr acc_t NEG = Sentinel<acc_t>::NEG, THR = Sentinel<acc_t>::THR;
-    uint32_t *ring_p = reinterpret_cast<uint32_t *>(ring_raw);                      // [slots][bd]
+    uint32_t *ring_p = reinterpret_cast<uint32_t *>(ring_raw);                          // [slots][bd]
     acc_t *ring_v = reinterpret_cast<acc_t *>(ring_raw + (size_t)kRingSlots * bd * 4);  // [slots][bd]
     acc_t A0 = NEG, A1 = NEG, B0 = NEG, B1 = NEG, top = NEG;
     const acc_t bonus = (acc_t)a.bonus;
     const acc_t pen_eff = (a.max_mm >= 1) ? (acc_t)a.penalty : NEG;
-    bool pend = false;       // the previous carried site, not yet an eligible predecessor
+    bool pend = false;  // the previous carried site, not yet an eligible predecessor
     acc_t pend_p = 0, pend_v = 0;
     int pend_c = 0;
-    int q = 0, head = 0;     // older pending sites (crowded positions only)
+    int q = 0, head = 0;  // older pending sites (crowded positions only)
     int n = 0;
 
-    const int gi0 = lo >> 5, gi1 = (hi - 1) >> 5;
-    for (int gb = gi0; gb <= gi1; gb += 4) {
-        uint32_t cw[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            cw[u] = (gb + u <= gi1) ? __ldg(a.carried + (size_t)(gb + u) * a.Tp + t) : 0u;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int gi = gb + u;
-            uint32_t c = cw[u];
-            if (gi == gi0) c &= 0xffffffffu << (lo & 31);
-            if (gi == gi1) c &= 0xffffffffu >> (31 - ((hi - 1) & 31));
-            if (!c) continue;
-            const uint32_t tw = __ldg(a.two + (size_t)gi * a.Tp + t);
+    const int gi0 = lo >> 5, nw = ((hi - 1) >> 5) - gi0 + 1;
+    const int lo_bit = lo & 31;
+    const uint32_t first_mask = 0xffffffffu << lo_bit;
+    const uint32_t last_mask = 0xffffffffu >> (31 - ((hi - 1) & 31));
+    auto load_car = [&](int j) -> uint32_t {
+        if (kStaged) return s_car[j * bd + tid];
+        uint32_t c = __ldg(a.carried + (size_t)(gi0 + j) * a.Tp + t);
+        if (j == 0) c &= first_mask;
+        if (j == nw - 1) c &= last_mask;
+        return c;
+    };
+    int j = 0;
+    uint32_t c = load_car(0), tw = 0;
+    bool need_tw = true;
+    if (!kStaged) n = 0;
+    for (;;) {
+        while (c == 0) {
+            if (++j >= nw) goto done;
+            c = load_car(j);
+            need_tw = true;
+        }
+        if (need_tw) {
+            tw = kStaged ? s_two[j * bd + tid] : __ldg(a.two + (size_t)(gi0 + j) * a.Tp + t);
+            need_tw = false;
             n += __popc(c);
-            do {
-                const int b = __ffs(c) - 1;
-                c &= c - 1;
-                const acc_t p = (acc_t)((int64_t)__ldg(a.pos + (gi << 5) + b) - (int64_t)p0);
-                const int cls = (tw >> b) & 1;
-                while (q > 0) {  // rare: crowded sites that have fallen >= 10 bp behind
-                    const acc_t pi = (acc_t)ring_p[head * bd + tid];
-                    if (p - pi < kMinPairDistance) break;
-                    const acc_t vv = ring_v[head * bd + tid];
-                    const acc_t v = vv >> 1;
-                    if (vv & 1) { A1 = max(A1, v - pi); B1 = max(B1, v); }
-                    else        { A0 = max(A0, v - pi); B0 = max(B0, v); }
-                    head = (head + 1) & (kRingSlots - 1);
-                    --q;
+        }
+        {
+            const int b = __ffs(c) - 1;
+            c &= c - 1;
+            const int idx = (j << 5) + b - lo_bit;  // variant index relative to lo
+            const acc_t p = kStaged ? (acc_t)s_pos[idx]
+                                    : (acc_t)((int64_t)__ldg(a.pos + lo + idx) - (int64_t)p0);
+            const int cls = (tw >> b) & 1;
+            while (q > 0) {  // rare: crowded sites that have fallen >= 10 bp behind
+                const acc_t pi = (acc_t)ring_p[head * bd + tid];
+                if (p - pi < kMinPairDistance) break;
+                const acc_t vv = ring_v[head * bd + tid];
+                const acc_t v = vv >> 1;
+                if (vv & 1) { A1 = max(A1, v - pi); B1 = max(B1, v); }
+                else        { A0 = max(A0, v - pi); B0 = max(B0, v); }
+                head = (head + 1) & (kRingSlots - 1);
+                --q;
+            }
+            if (pend) {
+                if (q == 0 && p - pend_p >= kMinPairDistance) {
+                    if (pend_c) { A1 = max(A1, pend_v - pend_p); B1 = max(B1, pend_v); }
+                    else        { A0 = max(A0, pend_v - pend_p); B0 = max(B0, pend_v); }
+                } else {
+                    const int tail = (head + q) & (kRingSlots - 1);
+                    ring_p[tail * bd + tid] = (uint32_t)pend_p;  // 0 <= p < 2^32
+                    ring_v[tail * bd + tid] = (pend_v << 1) | (acc_t)pend_c;
+                    ++q;
                 }
-                if (pend) {
-                    if (q == 0 && p - pend_p >= kMinPairDistance) {
-                        if (pend_c) { A1 = max(A1, pend_v - pend_p); B1 = max(B1, pend_v); }
-                        else        { A0 = max(A0, pend_v - pend_p); B0 = max(B0, pend_v); }
-                    } else {
-                        const int tail = (head + q) & (kRingSlots - 1);
-                        ring_p[tail * bd + tid] = (uint32_t)pend_p;  // 0 <= p < 2^32
-                        ring_v[tail * bd + tid] = (pend_v << 1) | (acc_t)pend_c;
-                        ++q;
-                    }
-                }
-                const acc_t same = cls ? A1 : A0;
-                const acc_t other = cls ? B0 : B1;
-                const acc_t m = max(same + (p + bonus), other + pen_eff);
-                top = max(top, m);
-                pend = true;
-                pend_p = p;
-                pend_v = max(m, (acc_t)0);
-                pend_c = cls;
-            } while (c);
+            }
+            const acc_t same = cls ? A1 : A0;
+            const acc_t other = cls ? B0 : B1;
+            const acc_t m = max(same + (p + bonus), other + pen_eff);
+            top = max(top, m);
+            pend = true;
+            pend_p = p;
+            pend_v = max(m, (acc_t)0);
+            pend_c = cls;
         }
     }
+done:
     n_out = n;
     score_out = (n <= 2 || top <= THR) ? kNegInf64 : (int64_t)top;
 }
 
-__global__ void __launch_bounds__(kScoreMaxThreads) score_prefix_kernel(ScoreArgs a) {
-    extern __shared__ __align__(16) uint8_t ring_raw[];
+// grid: x = column chunk, (y, z) = window; dynamic smem: ring | car tile | two tile | positions
+__global__ void __launch_bounds__(kScoreMaxThreads)
+score_prefix_kernel(const __grid_constant__ ScoreArgs a, int words_cap, int pos_cap) {
+    extern __shared__ __align__(16) uint8_t dyn[];
     __shared__ int s_nabs;
     __shared__ uint32_t s_ex;
     pdl_launch_dependents();
     const int tid = threadIdx.x, bd = blockDim.x;
-    const int w = blockIdx.x / a.tchunks;
-    const int t = (blockIdx.x - w * a.tchunks) * bd + tid;
+    const int w = blockIdx.z * gridDim.y + blockIdx.y;
+    if (w >= a.W) return;
+    const int t = blockIdx.x * bd + tid;
+    uint8_t *ring_raw = dyn;
+    uint32_t *s_car = reinterpret_cast<uint32_t *>(dyn + (size_t)kRingSlots * bd * 12);
+    uint32_t *s_two = s_car + (size_t)words_cap * bd;
+    uint32_t *s_pos = s_two + (size_t)words_cap * bd;
     if (tid == 0) { s_nabs = 0; s_ex = 0; }
     pdl_wait();  // bit-planes and window bounds come from the prep launch
     const int32_t lo = a.win_lo[w], hi = a.win_hi[w];
     __syncthreads();
 
-    // window-level quantities, computed once per CTA: #absent variants and the exotic flag
+    int n = 0;
+    int32_t p0 = 0;
+    bool staged = false;
     if (hi > lo) {
-        const int gi0 = lo >> 5, gi1 = (hi - 1) >> 5;
+        const int gi0 = lo >> 5, gi1 = (hi - 1) >> 5, nw = gi1 - gi0 + 1;
+        // window-level quantities, once per CTA: #absent variants and the exotic flag
         int na = 0;
         uint32_t ex = 0;
         for (int gi = gi0 + tid; gi <= gi1; gi += bd) {
@@ -134,26 +164,58 @@ __global__ void __launch_bounds__(kScoreMaxThreads) score_prefix_kernel(ScoreArg
             atomicAdd(&s_nabs, na);
             if (ex) atomicOr(&s_ex, ex);
         }
+        p0 = __ldg(a.pos + lo);
+        staged = nw <= words_cap && (hi - lo) <= pos_cap;
+        if (staged) {
+            // every thread stages ITS column (coalesced across the warp, all loads in flight at once)
+            if (t < a.T) {
+                const uint32_t *cp = a.carried + (size_t)gi0 * a.Tp + t;
+                const uint32_t *tp = a.two + (size_t)gi0 * a.Tp + t;
+                for (int jb = 0; jb < nw; jb += 4) {
+                    uint32_t cw[4], tw[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) cw[u] = (jb + u < nw) ? __ldg(cp + (size_t)(jb + u) * a.Tp) : 0u;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (jb + u == 0) cw[u] &= 0xffffffffu << (lo & 31);
+                        if (jb + u == nw - 1) cw[u] &= 0xffffffffu >> (31 - ((hi - 1) & 31));
+                        tw[u] = cw[u] ? __ldg(tp + (size_t)(jb + u) * a.Tp) : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (jb + u < nw) {
+                            s_car[(jb + u) * bd + tid] = cw[u];
+                            s_two[(jb + u) * bd + tid] = tw[u];
+                            n += __popc(cw[u]);
+                        }
+                    }
+                }
+            }
+            for (int i = tid; i < hi - lo; i += bd) s_pos[i] = (uint32_t)(__ldg(a.pos + lo + i) - p0);
+        }
     }
     __syncthreads();
     if (s_ex) {  // genotypes outside {0,1,2}: the whole window goes to the pairwise kernel
-        if (tid == 0 && blockIdx.x == (unsigned)(w * a.tchunks)) a.slow_list[atomicAdd(&a.hdr->n_slow, 1)] = w;
+        if (tid == 0 && blockIdx.x == 0) a.slow_list[atomicAdd(&a.hdr->n_slow, 1)] = w;
         return;
     }
     if (t >= a.T) return;
 
-    int n = 0;
     int64_t score = kNegInf64;
     if (hi > lo) {
-        const int32_t p0 = __ldg(a.pos + lo);
         const int64_t span = (int64_t)__ldg(a.pos + hi - 1) - (int64_t)p0;
-        int64_t nmax = span / kMinPairDistance + 1;
-        if (nmax > hi - lo) nmax = hi - lo;
         const int64_t mag = (int64_t)(a.bonus < 0 ? -(int64_t)a.bonus : a.bonus) +
                             (int64_t)(a.penalty < 0 ? -(int64_t)a.penalty : a.penalty);
-        const int64_t bound = span + (nmax + 1) * mag;
-        if (bound < (int64_t(1) << 28)) prefix_dp_unit<int32_t>(a, t, lo, hi, p0, ring_raw, tid, bd, n, score);
-        else                            prefix_dp_unit<int64_t>(a, t, lo, hi, p0, ring_raw, tid, bd, n, score);
+        const int64_t bound = span + (int64_t)(hi - lo + 1) * mag;  // |any chain score| <= bound
+        const bool small = bound < (int64_t(1) << 28);
+        if (staged) {
+            int n2 = 0;  // n was counted while staging
+            if (small) prefix_dp_unit<int32_t, true>(a, t, lo, hi, p0, ring_raw, s_car, s_two, s_pos, tid, bd, n2, score);
+            else       prefix_dp_unit<int64_t, true>(a, t, lo, hi, p0, ring_raw, s_car, s_two, s_pos, tid, bd, n2, score);
+        } else {
+            if (small) prefix_dp_unit<int32_t, false>(a, t, lo, hi, p0, ring_raw, s_car, s_two, s_pos, tid, bd, n, score);
+            else       prefix_dp_unit<int64_t, false>(a, t, lo, hi, p0, ring_raw, s_car, s_two, s_pos, tid, bd, n, score);
+        }
     }
     const size_t o = (size_t)w * a.T + t;
     a.score[o] = score;

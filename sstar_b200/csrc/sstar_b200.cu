@@ -172,7 +172,7 @@ int launch_prep(cudaStream_t st, bool do_pack, const int8_t *d_ref, const int8_t
 int launch_score(cudaStream_t st, const int8_t *d_tgt, const int32_t *d_pos, int32_t T, const int32_t *d_ws,
                  const int32_t *d_we, int32_t fixed_s, int32_t fixed_e, int32_t W, int32_t bonus,
                  int32_t max_mm, int32_t penalty, int64_t *d_score, int32_t *d_nsnp, uint8_t *ws,
-                 const WsLayout &L, int algo) {
+                 const WsLayout &L, int algo, int32_t max_win_variants) {
     if (W == 0) return 0;
     ScoreArgs s = {};
     s.pos = d_pos; s.tgt = d_tgt;
@@ -193,11 +193,41 @@ int launch_score(cudaStream_t st, const int8_t *d_tgt, const int32_t *d_pos, int
     if (algo != SSTAR_B200_ALGO_PAIRWISE) {
         int bd = (T + 31) / 32 * 32;
         if (bd > kScoreMaxThreads) bd = kScoreMaxThreads;
-        s.tchunks = (T + bd - 1) / bd;
-        const int64_t grid = (int64_t)W * s.tchunks;
-        if (grid > INT32_MAX) return fail(SSTAR_B200_EINVAL, "W * ceil(T/128) exceeds the grid limit%s");
-        const size_t ring = (size_t)kRingSlots * bd * 12;
-        cudaError_t e = launch(score_prefix_kernel, (unsigned)grid, (unsigned)bd, ring, st, true, s);
+        const int tchunks = (T + bd - 1) / bd;
+        s.tchunks = tchunks;
+        const int gy = W < 32768 ? W : 32768;
+        const int gz = (W + gy - 1) / gy;
+        // stage each unit's plane words + the window's positions in shared memory when the caller
+        // bounded the window size and it fits; otherwise the kernel reads global memory directly
+        size_t smem = (size_t)kRingSlots * bd * 12;
+        int words_cap = 0, pos_cap = 0;
+        if (max_win_variants > 0) {
+            const int wc = (max_win_variants + 30) / 32 + 1;
+            const size_t extra = (size_t)wc * bd * 8 + (size_t)wc * 32 * 4;
+            if (smem + extra <= (size_t)96 << 10) {
+                words_cap = wc;
+                pos_cap = wc * 32;
+                smem += extra;
+            }
+        }
+        static thread_local size_t k2_smem_set = 48 << 10;
+        if (smem > k2_smem_set) {
+            cudaError_t e = cudaFuncSetAttribute(score_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaFuncSetAttribute(prefix): %s", cudaGetErrorString(e));
+            k2_smem_set = smem;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)tchunks, (unsigned)gy, (unsigned)gz);
+        cfg.blockDim = dim3((unsigned)bd);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        ++g_launches;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, score_prefix_kernel, s, words_cap, pos_cap);
         if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "score_prefix_kernel launch: %s", cudaGetErrorString(e));
     }
     const size_t psmem = (size_t)kPairWarps * kPairSmemCap * 13;
@@ -240,13 +270,13 @@ int run_pipeline(int device, cudaStream_t st, bool do_pack, const int8_t *d_ref,
                  const int32_t *d_pos, int64_t V, int32_t R, int32_t T, const int32_t *d_ws,
                  const int32_t *d_we, const int32_t *d_seg, int32_t fixed_s, int32_t fixed_e, int32_t W,
                  int32_t bonus, int32_t max_mm, int32_t penalty, int64_t *d_score, int32_t *d_nsnp,
-                 uint8_t *ws, const WsLayout &L, int algo) {
+                 uint8_t *ws, const WsLayout &L, int algo, int32_t max_win_variants) {
     DeviceGuard guard(device);
     if (guard.err != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
     int rc = launch_prep(st, do_pack, d_ref, d_tgt, V, R, T, d_pos, d_ws, d_we, d_seg, fixed_s, fixed_e, W, ws, L, algo);
     if (rc) return rc;
     return launch_score(st, d_tgt, d_pos, T, d_ws, d_we, fixed_s, fixed_e, W, bonus, max_mm, penalty, d_score,
-                        d_nsnp, ws, L, algo);
+                        d_nsnp, ws, L, algo, max_win_variants);
 }
 
 }  // namespace
@@ -298,7 +328,7 @@ int sstar_b200_score_packed(int device, void *stream, const int8_t *d_tgt_gt, co
     if (V > 0 && (!d_pos || !d_tgt_gt)) return fail(SSTAR_B200_EINVAL, "null pos/tgt pointer%s");
     return run_pipeline(device, (cudaStream_t)stream, false, nullptr, d_tgt_gt, d_pos, V, R, T, d_win_start,
                         d_win_end, nullptr, 0, 0, W, match_bonus, max_mismatch, mismatch_penalty, d_score,
-                        d_nsnp, (uint8_t *)d_workspace, L, algo);
+                        d_nsnp, (uint8_t *)d_workspace, L, algo, opts ? opts->max_win_variants : 0);
 }
 
 int sstar_b200_score_windows_ex(int device, void *stream, const int8_t *d_ref_gt, const int8_t *d_tgt_gt,
@@ -315,7 +345,7 @@ int sstar_b200_score_windows_ex(int device, void *stream, const int8_t *d_ref_gt
     if (V > 0 && (!d_pos || !d_tgt_gt || !d_ref_gt)) return fail(SSTAR_B200_EINVAL, "null input pointer%s");
     return run_pipeline(device, (cudaStream_t)stream, true, d_ref_gt, d_tgt_gt, d_pos, V, R, T, d_win_start,
                         d_win_end, nullptr, 0, 0, W, match_bonus, max_mismatch, mismatch_penalty, d_score,
-                        d_nsnp, (uint8_t *)d_workspace, L, algo);
+                        d_nsnp, (uint8_t *)d_workspace, L, algo, opts ? opts->max_win_variants : 0);
 }
 
 int sstar_b200_score_windows(int device, void *stream, const int8_t *d_ref_gt, const int8_t *d_tgt_gt,
@@ -342,7 +372,7 @@ int sstar_b200_score_replicates(int device, void *stream, const int8_t *d_ref_gt
     if (V > 0 && (!d_pos || !d_tgt_gt || !d_ref_gt)) return fail(SSTAR_B200_EINVAL, "null input pointer%s");
     return run_pipeline(device, (cudaStream_t)stream, true, d_ref_gt, d_tgt_gt, d_pos, V, R, T, nullptr, nullptr,
                         d_rep_offset, win_start, win_end, Nrep, match_bonus, max_mismatch, mismatch_penalty,
-                        d_score, d_nsnp, (uint8_t *)d_workspace, L, algo);
+                        d_score, d_nsnp, (uint8_t *)d_workspace, L, algo, opts ? opts->max_win_variants : 0);
 }
 
 }  // extern "C"
