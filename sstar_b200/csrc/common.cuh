@@ -3,14 +3,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-namespace sstar {
+#include "dp_core.cuh"
 
-constexpr int kMinPairDistance = 10;  // sstar/sstar.py:195: pairs closer than 10 bp never link
-constexpr int64_t kNegInf64 = INT64_MIN;
+namespace sstar {
 
 constexpr int kPackThreads = 256;
 constexpr int kScoreMaxThreads = 128;
-constexpr int kRingSlots = 16;      // >= 10: at most 10 distinct integer positions lie within 9 bp
+constexpr int kMaxGroup = 16;       // windows one score CTA walks at most
+constexpr int kScoreWordsCap = 64;  // staged position tile of a window group: 64 words = 2048 variants
+constexpr int kScoreListBytes = 24 << 10;  // shared memory for the per-column site lists of one CTA
 constexpr int kPairWarps = 4;
 constexpr int kPairSmemCap = 1024;  // pairwise list entries per warp kept in shared memory
 constexpr int kNumSM = 148;
@@ -25,7 +26,7 @@ struct WsHeader {
 struct WsLayout {
     int64_t G;   // 32-variant groups
     int32_t Tp;  // plane row pitch in words (T rounded up to 32)
-    size_t off_absent, off_exotic, off_carried, off_two, off_win_lo, off_win_hi, off_slow, off_arena;
+    size_t off_absent, off_exotic, off_carried, off_two, off_win_lo, off_win_hi, off_win_pfirst, off_win_plast, off_slow, off_arena;
     size_t arena_entries;
     size_t total;
 };
@@ -37,6 +38,7 @@ struct BoundsArgs {
     int32_t fixed_start, fixed_end;
     int32_t V, W;
     int32_t *win_lo, *win_hi, *slow_list;
+    int32_t *win_pfirst, *win_plast;  // position of the first / last variant of each non-empty window
     WsHeader *hdr;
     int force_slow;
 };
@@ -54,12 +56,12 @@ struct ScoreArgs {
     const int32_t *pos;
     const int8_t *tgt;
     const uint32_t *absent_bits, *exotic, *carried, *two;
-    const int32_t *win_lo, *win_hi;
+    const int32_t *win_lo, *win_hi, *win_pfirst, *win_plast;
     const int32_t *win_start, *win_end;  // or null: fixed_start / fixed_end
     int32_t fixed_start, fixed_end;
     int32_t *slow_list;
     WsHeader *hdr;
-    int32_t T, Tp, W, tchunks;
+    int32_t V, T, Tp, W, tchunks;
     int32_t bonus, max_mm, penalty;
     int64_t *score;
     int32_t *nsnp;

@@ -1,0 +1,174 @@
+// sstar_b200 -- the per-unit chain DP, written once for device and host.
+//
+// These two functions are the arithmetic of the score kernel.  They compile for the GPU (called
+// from score_kernels.cuh) and, unchanged, for the host, where tests/emul builds them with g++ and
+// checks them against the oracle without a GPU.  Nothing in the product calls the host build.
+//
+// Recurrence (sstar/sstar.py:195-217).  With v_i = max(M[i], 0):
+//     M[j] = max_{i<j, p_j-p_i>=10} s(j,i) + v_i
+// and for carried genotypes in {1,2}:  g_i == g_j -> s = (p_j - p_i) + bonus
+//                                      g_i != g_j -> s = penalty      (only if max_mismatch >= 1)
+// so  M[j] = max( p_j + bonus + max_{g_i=g_j}(v_i - p_i) ,  penalty + max_{g_i!=g_j} v_i ):
+// four running maxima (A0, A1, B0, B1).  Positions ascend, so the eligible predecessors of site j
+// are a prefix of the sites before it: a site is "committed" to the maxima once the current site is
+// >= 10 bp ahead.  At most 10 distinct integer positions fit in 9 bp, so at most 10 sites wait; the
+// newest waits in registers, older ones in a 16-slot ring.
+//
+// "-inf" is a sentinel NEG with |real values| < |NEG| / 4: invalid candidates stay below THR
+// without selects, m = max(same + p + bonus, other + penalty) is valid iff m > THR, and
+// v = max(m, 0) is 0 for an invalid m -- exactly max(M[i] + s, s) of the reference.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SSTAR_HD __host__ __device__ __forceinline__
+#else
+#define SSTAR_HD inline
+#endif
+
+namespace sstar {
+
+constexpr int kMinPairDistance = 10;  // sstar/sstar.py:195: pairs closer than 10 bp never link
+constexpr int kRingSlots = 16;        // >= 10 waiting sites
+constexpr int64_t kNegInf64 = INT64_MIN;
+
+template <typename acc_t> struct Sentinel;
+template <> struct Sentinel<int32_t> {
+    static constexpr int32_t NEG = -(1 << 30);
+    static constexpr int32_t THR = -(1 << 29);
+};
+template <> struct Sentinel<int64_t> {
+    static constexpr int64_t NEG = -(int64_t(1) << 62);
+    static constexpr int64_t THR = -(int64_t(1) << 61);
+};
+// int32 arithmetic is exact while |any chain score| < 2^28
+constexpr int64_t kSmallBound = int64_t(1) << 28;
+
+template <typename T> SSTAR_HD T imax(T a, T b) { return a > b ? a : b; }
+SSTAR_HD int ctz32(uint32_t x) {  // x != 0
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+
+// |any chain score| inside a span of `span` bp holding `nvar` variants
+SSTAR_HD int64_t score_bound(int64_t span, int64_t nvar, int32_t bonus, int32_t penalty) {
+    const int64_t mag = (bonus < 0 ? -(int64_t)bonus : (int64_t)bonus) +
+                        (penalty < 0 ? -(int64_t)penalty : (int64_t)penalty);
+    return span + (nvar + 1) * mag;
+}
+
+// ---------------------------------------------------------------------------------------------
+// List DP (int32).  `list` holds one column's carried reference-absent sites of a window GROUP in
+// ascending position, entry = (position relative to the group's first variant) << 1 | (genotype==2);
+// consecutive entries are `ls` words apart, ring slots `rs` words apart (strided shared-memory
+// columns on the device, 1 on the host).  Scores the window [plo, phi] (relative positions,
+// closed).  `a` is the list cursor: windows of a group are visited with non-decreasing plo, so it
+// only moves forward.
+// ---------------------------------------------------------------------------------------------
+SSTAR_HD void list_dp_window(const uint32_t *list, int ls, int32_t *ring, int rs, int &a, int cnt,
+                             uint32_t plo, uint32_t phi, int32_t bonus, int32_t pen_eff, int &n_out,
+                             int64_t &score_out) {
+    constexpr int32_t NEG = Sentinel<int32_t>::NEG, THR = Sentinel<int32_t>::THR;
+    while (a < cnt && (list[a * ls] >> 1) < plo) ++a;
+    int k = a, c = a;  // next site to score, next site to commit
+    int32_t A0 = NEG, A1 = NEG, B0 = NEG, B1 = NEG, top = NEG;
+    uint32_t pe = 0;  // entry k-1 and its v
+    int32_t pv = 0;
+    while (k < cnt) {
+        const uint32_t e = list[k * ls];
+        if ((e >> 1) > phi) break;
+        const int32_t p = (int32_t)(e >> 1);
+        if (c == k - 1) {  // common case: only the previous site waits, in registers
+            const int32_t pc = (int32_t)(pe >> 1);
+            if (p - pc >= kMinPairDistance) {
+                if (pe & 1u) { A1 = imax(A1, pv - pc); B1 = imax(B1, pv); }
+                else         { A0 = imax(A0, pv - pc); B0 = imax(B0, pv); }
+                c = k;
+            } else {
+                ring[((k - 1) & (kRingSlots - 1)) * rs] = pv;  // k-1 keeps waiting: park its v
+            }
+        } else if (c < k) {  // crowded sites: older ones wait in the ring
+            while (c < k) {
+                uint32_t ec;
+                int32_t vc;
+                if (c == k - 1) { ec = pe; vc = pv; }
+                else            { ec = list[c * ls]; vc = ring[(c & (kRingSlots - 1)) * rs]; }
+                const int32_t pc = (int32_t)(ec >> 1);
+                if (p - pc < kMinPairDistance) break;
+                if (ec & 1u) { A1 = imax(A1, vc - pc); B1 = imax(B1, vc); }
+                else         { A0 = imax(A0, vc - pc); B0 = imax(B0, vc); }
+                ++c;
+            }
+            if (c < k) ring[((k - 1) & (kRingSlots - 1)) * rs] = pv;
+        }
+        const bool cls = (e & 1u) != 0;
+        const int32_t same = cls ? A1 : A0;
+        const int32_t other = cls ? B0 : B1;
+        const int32_t m = imax(same + (p + bonus), other + pen_eff);
+        top = imax(top, m);
+        pe = e;
+        pv = imax(m, (int32_t)0);
+        ++k;
+    }
+    n_out = k - a;
+    score_out = (n_out <= 2 || top <= THR) ? kNegInf64 : (int64_t)top;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Walk DP: the same recurrence straight from the word-major bit-planes in global memory, for
+// units the list path cannot take (very long windows, a column with more sites than list slots,
+// scores beyond int32).  Column t of plane word g is plane[g * Tp + t].  The waiting sites live in
+// two small per-thread arrays.
+// ---------------------------------------------------------------------------------------------
+template <typename acc_t, typename LoadU32, typename LoadPos>
+SSTAR_HD void walk_dp_unit(LoadU32 ld, LoadPos ldpos, const uint32_t *carried, const uint32_t *two, int32_t Tp,
+                           int t, int32_t lo, int32_t hi, int32_t bonus_i, int32_t penalty_i, int32_t max_mm,
+                           int &n_out, int64_t &score_out) {
+    constexpr acc_t NEG = Sentinel<acc_t>::NEG, THR = Sentinel<acc_t>::THR;
+    const acc_t bonus = (acc_t)bonus_i;
+    const acc_t pen_eff = (max_mm >= 1) ? (acc_t)penalty_i : NEG;
+    acc_t A0 = NEG, A1 = NEG, B0 = NEG, B1 = NEG, top = NEG;
+    acc_t wait_p[kRingSlots], wait_v[kRingSlots];  // v << 1 | class
+    int q = 0, head = 0, n = 0;
+    const int64_t p0 = ldpos(lo);
+    const int gi0 = lo >> 5, gi1 = (hi - 1) >> 5;
+    for (int gi = gi0; gi <= gi1; ++gi) {
+        uint32_t c = ld(carried + (size_t)gi * Tp + t);
+        if (gi == gi0) c &= 0xffffffffu << (lo & 31);
+        if (gi == gi1) c &= 0xffffffffu >> (31 - ((hi - 1) & 31));
+        if (c == 0) continue;
+        const uint32_t tw = ld(two + (size_t)gi * Tp + t);
+        while (c) {
+            const int b = ctz32(c);
+            c &= c - 1;
+            const acc_t p = (acc_t)(ldpos((gi << 5) + b) - p0);
+            const int cls = (int)((tw >> b) & 1u);
+            while (q > 0) {
+                const acc_t pi = wait_p[head];
+                if (p - pi < kMinPairDistance) break;
+                const acc_t vv = wait_v[head];
+                const acc_t v = vv >> 1;
+                if (vv & 1) { A1 = imax(A1, v - pi); B1 = imax(B1, v); }
+                else        { A0 = imax(A0, v - pi); B0 = imax(B0, v); }
+                head = (head + 1) & (kRingSlots - 1);
+                --q;
+            }
+            const acc_t same = cls ? A1 : A0;
+            const acc_t other = cls ? B0 : B1;
+            const acc_t m = imax(same + (p + bonus), other + pen_eff);
+            top = imax(top, m);
+            const int tail = (head + q) & (kRingSlots - 1);
+            wait_p[tail] = p;
+            wait_v[tail] = (imax(m, (acc_t)0) << 1) | (acc_t)cls;
+            ++q;
+            ++n;
+        }
+    }
+    n_out = n;
+    score_out = (n <= 2 || top <= THR) ? kNegInf64 : (int64_t)top;
+}
+
+}  // namespace sstar

@@ -42,6 +42,10 @@ __device__ __forceinline__ void bounds_block(const BoundsArgs &a, int block, int
     const int32_t lo = warp_lower_bound(a.pos, sb, se, s, lane);
     int32_t hi = warp_lower_bound(a.pos, lo, se, e + 1, lane);
     if (hi < lo) hi = lo;
+    if (lane < 2 && hi > lo) {  // first / last position, so the score kernel need not chase them
+        const int32_t v = __ldg(a.pos + (lane == 0 ? lo : hi - 1));
+        (lane == 0 ? a.win_pfirst : a.win_plast)[w] = v;
+    }
     if (lane == 0) {
         a.win_lo[w] = lo;
         a.win_hi[w] = hi;

@@ -5,221 +5,223 @@
 namespace sstar {
 
 // ------------------------------------------------------------------------------------------
-// K2: prefix-max chain DP, one THREAD per (window, column) unit; CTA = (window, <=128 columns).
+// K2: prefix-max chain DP (dp_core.cuh), one THREAD per target column, one CTA per GROUP of up
+// to kMaxGroup consecutive windows x <=128 columns.
 //
-// With v_i = max(M[i], 0) the recurrence of sstar/sstar.py:208-212 reads
-//     M[j] = max_{i<j, p_j-p_i>=10} s(j,i) + v_i .
-// For carried genotypes in {1,2}:  g_i == g_j -> s = (p_j - p_i) + bonus
-//                                  g_i != g_j -> s = penalty          (only if max_mismatch >= 1)
-// hence  M[j] = max( p_j + bonus + max_{g_i=g_j}(v_i - p_i) ,  penalty + max_{g_i!=g_j} v_i ):
-// four running maxima (A0,A1,B0,B1).  Positions ascend, so eligible predecessors form a prefix:
-// the previous site waits in registers and is committed to the maxima as soon as the current site
-// is >= 10 bp ahead; only when carried sites crowd within 9 bp do entries queue in a per-thread
-// shared-memory ring (<= 10 distinct integer positions fit in 9 bp, ring has 16 slots).
+// Overlapping windows (50 kb / 10 kb: 5x) share most of their variants, so the CTA turns the
+// group's union variant range into per-column site lists ONCE -- each thread pulls its column's
+// plane words (coalesced across the warp), and writes (relative position << 1 | genotype==2) for
+// every carried reference-absent site into its own shared-memory column -- and then every window
+// of the group is a cursor walk over that list: no bit scanning, no position lookups, no global
+// loads inside the DP.  Window-level quantities (#absent variants, exotic flag, first / last
+// relative position) are computed by one thread per window.
 //
-// "-inf" is a sentinel NEG with |real values| < |NEG|/4, so invalid candidates stay below THR
-// without any select: m = max(same + p + bonus, other + penalty) is valid iff m > THR, and
-// v = max(m, 0) is 0 for an invalid m -- exactly max(M[i] + s, s) of the reference.
-// Arithmetic is int32 when the window's score bound allows it (decided per window), else int64.
+// A group the list path cannot take (non-monotone windows, a union range wider than the staged
+// position tile, scores beyond int32) and a column with more sites than list slots fall back to
+// walk_dp_unit straight from the planes in global memory.  Results are identical on every path.
 // ------------------------------------------------------------------------------------------
-template <typename acc_t> struct Sentinel;
-template <> struct Sentinel<int32_t> {
-    static constexpr int32_t NEG = -(1 << 30);
-    static constexpr int32_t THR = -(1 << 29);
+struct GroupShared {
+    int32_t lo[kMaxGroup], hi[kMaxGroup];
+    int32_t pfirst[kMaxGroup], plast[kMaxGroup];
+    uint32_t plo[kMaxGroup], phi[kMaxGroup];
+    int32_t nabs[kMaxGroup];
+    uint32_t ex[kMaxGroup];
+    int32_t red_nabs;
+    uint32_t red_ex;
 };
-template <> struct Sentinel<int64_t> {
-    static constexpr int64_t NEG = -(int64_t(1) << 62);
-    static constexpr int64_t THR = -(int64_t(1) << 61);
+
+struct LdgU32 { __device__ __forceinline__ uint32_t operator()(const uint32_t *p) const { return __ldg(p); } };
+struct LdgPos {
+    const int32_t *pos;
+    __device__ __forceinline__ int64_t operator()(int32_t k) const { return (int64_t)__ldg(pos + k); }
 };
 
-// Per-unit DP.  kStaged: the unit's plane words and the window's positions were staged in shared
-// memory by the CTA (thread-private columns car[j*bd+tid] / two[j*bd+tid], shared rel. positions);
-// otherwise everything is read from global memory (very long windows, unknown size hint).
-// Each lane walks ITS OWN set bits across word boundaries, so a warp iterates max_lane(n) times,
-// not sum_words max_lane(popc).
-template <typename acc_t, bool kStaged>
-__device__ __forceinline__ void prefix_dp_unit(const ScoreArgs &a, int t, int32_t lo, int32_t hi, int32_t p0,
-                                               uint8_t *ring_raw, const uint32_t *s_car, const uint32_t *s_two,
-                                               const uint32_t *s_pos, int tid, int bd, int &n_out,
-                                               int64_t &score_out) {
-    constexpr acc_t NEG = Sentinel<acc_t>::NEG, THR = Sentinel<acc_t>::THR;
-    uint32_t *ring_p = reinterpret_cast<uint32_t *>(ring_raw);                          // [slots][bd]
-    acc_t *ring_v = reinterpret_cast<acc_t *>(ring_raw + (size_t)kRingSlots * bd * 4);  // [slots][bd]
-    acc_t A0 = NEG, A1 = NEG, B0 = NEG, B1 = NEG, top = NEG;
-    const acc_t bonus = (acc_t)a.bonus;
-    const acc_t pen_eff = (a.max_mm >= 1) ? (acc_t)a.penalty : NEG;
-    bool pend = false;  // the previous carried site, not yet an eligible predecessor
-    acc_t pend_p = 0, pend_v = 0;
-    int pend_c = 0;
-    int q = 0, head = 0;  // older pending sites (crowded positions only)
-    int n = 0;
-
-    const int gi0 = lo >> 5, nw = ((hi - 1) >> 5) - gi0 + 1;
-    const int lo_bit = lo & 31;
-    const uint32_t first_mask = 0xffffffffu << lo_bit;
-    const uint32_t last_mask = 0xffffffffu >> (31 - ((hi - 1) & 31));
-    auto load_car = [&](int j) -> uint32_t {
-        if (kStaged) return s_car[j * bd + tid];
-        uint32_t c = __ldg(a.carried + (size_t)(gi0 + j) * a.Tp + t);
-        if (j == 0) c &= first_mask;
-        if (j == nw - 1) c &= last_mask;
-        return c;
-    };
-    int j = 0;
-    uint32_t c = load_car(0), tw = 0;
-    bool need_tw = true;
-    if (!kStaged) n = 0;
-    for (;;) {
-        while (c == 0) {
-            if (++j >= nw) goto done;
-            c = load_car(j);
-            need_tw = true;
-        }
-        if (need_tw) {
-            tw = kStaged ? s_two[j * bd + tid] : __ldg(a.two + (size_t)(gi0 + j) * a.Tp + t);
-            need_tw = false;
-            n += __popc(c);
-        }
-        {
-            const int b = __ffs(c) - 1;
-            c &= c - 1;
-            const int idx = (j << 5) + b - lo_bit;  // variant index relative to lo
-            const acc_t p = kStaged ? (acc_t)s_pos[idx]
-                                    : (acc_t)((int64_t)__ldg(a.pos + lo + idx) - (int64_t)p0);
-            const int cls = (tw >> b) & 1;
-            while (q > 0) {  // rare: crowded sites that have fallen >= 10 bp behind
-                const acc_t pi = (acc_t)ring_p[head * bd + tid];
-                if (p - pi < kMinPairDistance) break;
-                const acc_t vv = ring_v[head * bd + tid];
-                const acc_t v = vv >> 1;
-                if (vv & 1) { A1 = max(A1, v - pi); B1 = max(B1, v); }
-                else        { A0 = max(A0, v - pi); B0 = max(B0, v); }
-                head = (head + 1) & (kRingSlots - 1);
-                --q;
-            }
-            if (pend) {
-                if (q == 0 && p - pend_p >= kMinPairDistance) {
-                    if (pend_c) { A1 = max(A1, pend_v - pend_p); B1 = max(B1, pend_v); }
-                    else        { A0 = max(A0, pend_v - pend_p); B0 = max(B0, pend_v); }
-                } else {
-                    const int tail = (head + q) & (kRingSlots - 1);
-                    ring_p[tail * bd + tid] = (uint32_t)pend_p;  // 0 <= p < 2^32
-                    ring_v[tail * bd + tid] = (pend_v << 1) | (acc_t)pend_c;
-                    ++q;
-                }
-            }
-            const acc_t same = cls ? A1 : A0;
-            const acc_t other = cls ? B0 : B1;
-            const acc_t m = max(same + (p + bonus), other + pen_eff);
-            top = max(top, m);
-            pend = true;
-            pend_p = p;
-            pend_v = max(m, (acc_t)0);
-            pend_c = cls;
-        }
-    }
-done:
-    n_out = n;
-    score_out = (n <= 2 || top <= THR) ? kNegInf64 : (int64_t)top;
-}
-
-// grid: x = column chunk, (y, z) = window; dynamic smem: ring | car tile | two tile | positions
+// grid.x = tchunks * ngroups; dynamic smem: list [L][bd] | max(ring [16][bd], positions [words_cap*32])
 __global__ void __launch_bounds__(kScoreMaxThreads)
-score_prefix_kernel(const __grid_constant__ ScoreArgs a, int words_cap, int pos_cap) {
+score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words_cap) {
     extern __shared__ __align__(16) uint8_t dyn[];
-    __shared__ int s_nabs;
-    __shared__ uint32_t s_ex;
+    __shared__ GroupShared g;
     pdl_launch_dependents();
     const int tid = threadIdx.x, bd = blockDim.x;
-    const int w = blockIdx.z * gridDim.y + blockIdx.y;
-    if (w >= a.W) return;
-    const int t = blockIdx.x * bd + tid;
-    uint8_t *ring_raw = dyn;
-    uint32_t *s_car = reinterpret_cast<uint32_t *>(dyn + (size_t)kRingSlots * bd * 12);
-    uint32_t *s_two = s_car + (size_t)words_cap * bd;
-    uint32_t *s_pos = s_two + (size_t)words_cap * bd;
-    if (tid == 0) { s_nabs = 0; s_ex = 0; }
+    const int chunk = blockIdx.x % a.tchunks, grp = blockIdx.x / a.tchunks;
+    const int w0 = grp * wg;
+    const int nwin = min(wg, a.W - w0);
+    const int t = chunk * bd + tid;
+    // the position tile is only read while the lists are built, the ring only during the DP:
+    // they share one region (a barrier separates the two phases)
+    uint32_t *s_list = reinterpret_cast<uint32_t *>(dyn);
+    uint32_t *s_pos = s_list + (size_t)L * bd;
+    int32_t *s_ring = reinterpret_cast<int32_t *>(s_pos);
+
     pdl_wait();  // bit-planes and window bounds come from the prep launch
-    const int32_t lo = a.win_lo[w], hi = a.win_hi[w];
+    if (tid < nwin) {
+        g.lo[tid] = a.win_lo[w0 + tid];
+        g.hi[tid] = a.win_hi[w0 + tid];
+        g.pfirst[tid] = a.win_pfirst[w0 + tid];  // (undefined for empty windows, never used then)
+        g.plast[tid] = a.win_plast[w0 + tid];
+        g.nabs[tid] = 0;
+        g.ex[tid] = 0;
+    }
     __syncthreads();
 
-    int n = 0;
-    int32_t p0 = 0;
-    bool staged = false;
-    if (hi > lo) {
-        const int gi0 = lo >> 5, gi1 = (hi - 1) >> 5, nw = gi1 - gi0 + 1;
-        // window-level quantities, once per CTA: #absent variants and the exotic flag
-        int na = 0;
-        uint32_t ex = 0;
-        for (int gi = gi0 + tid; gi <= gi1; gi += bd) {
+    // the group's union variant range [rlo, rhi) over its non-empty windows
+    int32_t rlo = INT32_MAX, rhi = -1, prev_lo = -1, maxnv = 0, p0 = 0, plast = INT32_MIN;
+    bool mono = true;
+    for (int i = 0; i < nwin; ++i) {
+        const int32_t lo = g.lo[i], hi = g.hi[i];
+        if (hi > lo) {
+            mono = mono && lo >= prev_lo;
+            prev_lo = lo;
+            if (lo < rlo) { rlo = lo; p0 = g.pfirst[i]; }
+            rhi = max(rhi, hi);
+            plast = max(plast, g.plast[i]);
+            maxnv = max(maxnv, hi - lo);
+        }
+    }
+    if (rhi < 0) {  // nothing but empty windows: NaN, 0 SNPs (sstar.py:191-193 with n = 0)
+        if (t < a.T)
+            for (int i = 0; i < nwin; ++i) {
+                const size_t o = (size_t)(w0 + i) * a.T + t;
+                a.score[o] = kNegInf64;
+                a.nsnp[o] = 0;
+            }
+        return;
+    }
+    const int gi0 = rlo >> 5, nwr = ((rhi - 1) >> 5) - gi0 + 1;
+    const int64_t span = (int64_t)plast - (int64_t)p0;
+    const bool fast = mono && nwr <= words_cap && score_bound(span, maxnv, a.bonus, a.penalty) < kSmallBound;
+    const int32_t pen_eff = (a.max_mm >= 1) ? a.penalty : Sentinel<int32_t>::NEG;
+
+    if (fast) {
+        // positions of the union range, relative to its first variant (word-aligned tile)
+        const int32_t base = gi0 << 5;
+        const int32_t npos = min(nwr << 5, a.V - base);
+        for (int i = tid; i < npos; i += bd) s_pos[i] = (uint32_t)(__ldg(a.pos + base + i) - p0);
+        if (tid < nwin) {
+            const int32_t lo = g.lo[tid], hi = g.hi[tid];
+            g.plo[tid] = hi > lo ? (uint32_t)(g.pfirst[tid] - p0) : 1u;
+            g.phi[tid] = hi > lo ? (uint32_t)(g.plast[tid] - p0) : 0u;
+        }
+        // #absent variants and the exotic flag per window: one (window, word) item per thread
+        for (int it = tid; it < nwin * nwr; it += bd) {
+            const int i = it / nwr, gi = gi0 + (it - i * nwr);
+            const int32_t lo = g.lo[i], hi = g.hi[i];
+            if (hi <= lo || gi < (lo >> 5) || gi > ((hi - 1) >> 5)) continue;
             uint32_t rm = 0xffffffffu;
-            if (gi == gi0) rm &= 0xffffffffu << (lo & 31);
-            if (gi == gi1) rm &= 0xffffffffu >> (31 - ((hi - 1) & 31));
-            na += __popc(__ldg(a.absent_bits + gi) & rm);
-            ex |= __ldg(a.exotic + gi);
+            if (gi == (lo >> 5)) rm &= 0xffffffffu << (lo & 31);
+            if (gi == ((hi - 1) >> 5)) rm &= 0xffffffffu >> (31 - ((hi - 1) & 31));
+            const int na = __popc(__ldg(a.absent_bits + gi) & rm);
+            if (na) atomicAdd(&g.nabs[i], na);
+            if (__ldg(a.exotic + gi)) atomicOr(&g.ex[i], 1u);
         }
-        na = __reduce_add_sync(0xffffffffu, na);
-        ex = __reduce_or_sync(0xffffffffu, ex);
-        if ((tid & 31) == 0 && (na | ex)) {
-            atomicAdd(&s_nabs, na);
-            if (ex) atomicOr(&s_ex, ex);
-        }
-        p0 = __ldg(a.pos + lo);
-        staged = nw <= words_cap && (hi - lo) <= pos_cap;
-        if (staged) {
-            // every thread stages ITS column (coalesced across the warp, all loads in flight at once)
-            if (t < a.T) {
-                const uint32_t *cp = a.carried + (size_t)gi0 * a.Tp + t;
-                const uint32_t *tp = a.two + (size_t)gi0 * a.Tp + t;
-                for (int jb = 0; jb < nw; jb += 4) {
-                    uint32_t cw[4], tw[4];
+        __syncthreads();
+
+        // this thread's column: plane words -> site list
+        int cnt = 0;
+        if (t < a.T) {
+            const uint32_t *cp = a.carried + (size_t)gi0 * a.Tp + t;
+            const uint32_t *tp = a.two + (size_t)gi0 * a.Tp + t;
+            const uint32_t first_mask = 0xffffffffu << (rlo & 31);
+            const uint32_t last_mask = 0xffffffffu >> (31 - ((rhi - 1) & 31));
+            for (int jb = 0; jb < nwr; jb += 4) {
+                uint32_t cw[4], tw[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) cw[u] = (jb + u < nw) ? __ldg(cp + (size_t)(jb + u) * a.Tp) : 0u;
+                for (int u = 0; u < 4; ++u) cw[u] = (jb + u < nwr) ? __ldg(cp + (size_t)(jb + u) * a.Tp) : 0u;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (jb + u == 0) cw[u] &= 0xffffffffu << (lo & 31);
-                        if (jb + u == nw - 1) cw[u] &= 0xffffffffu >> (31 - ((hi - 1) & 31));
-                        tw[u] = cw[u] ? __ldg(tp + (size_t)(jb + u) * a.Tp) : 0u;
-                    }
+                for (int u = 0; u < 4; ++u) {
+                    if (jb + u == 0) cw[u] &= first_mask;
+                    if (jb + u == nwr - 1) cw[u] &= last_mask;
+                    tw[u] = (jb + u < nwr) ? __ldg(tp + (size_t)(jb + u) * a.Tp) : 0u;  // not chained to cw
+                }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (jb + u < nw) {
-                            s_car[(jb + u) * bd + tid] = cw[u];
-                            s_two[(jb + u) * bd + tid] = tw[u];
-                            n += __popc(cw[u]);
-                        }
+                for (int u = 0; u < 4; ++u) {
+                    uint32_t c = cw[u];
+                    const uint32_t *sp = s_pos + ((jb + u) << 5);
+                    while (c) {
+                        const int b = __ffs(c) - 1;
+                        c &= c - 1;
+                        if (cnt < L) s_list[cnt * bd + tid] = (sp[b] << 1) | ((tw[u] >> b) & 1u);
+                        ++cnt;
                     }
                 }
             }
-            for (int i = tid; i < hi - lo; i += bd) s_pos[i] = (uint32_t)(__ldg(a.pos + lo + i) - p0);
         }
-    }
-    __syncthreads();
-    if (s_ex) {  // genotypes outside {0,1,2}: the whole window goes to the pairwise kernel
-        if (tid == 0 && blockIdx.x == 0) a.slow_list[atomicAdd(&a.hdr->n_slow, 1)] = w;
+        __syncthreads();       // every list is built: the position tile becomes the ring
+        if (t >= a.T) return;  // no block-wide barrier below this point on the fast path
+        const bool overflow = cnt > L;
+        int cur = 0;
+        for (int i = 0; i < nwin; ++i) {
+            const int w = w0 + i;
+            if (g.ex[i]) {  // genotypes outside {0,1,2}: the whole window goes to the pairwise kernel
+                if (chunk == 0 && tid == 0) a.slow_list[atomicAdd(&a.hdr->n_slow, 1)] = w;
+                continue;
+            }
+            const int32_t lo = g.lo[i], hi = g.hi[i];
+            int n = 0;
+            int64_t score = kNegInf64;
+            if (hi > lo) {
+                if (!overflow)
+                    list_dp_window(s_list + tid, bd, s_ring + tid, bd, cur, cnt, g.plo[i], g.phi[i], a.bonus,
+                                   pen_eff, n, score);
+                else
+                    walk_dp_unit<int32_t>(LdgU32(), LdgPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus,
+                                          a.penalty, a.max_mm, n, score);
+            }
+            const size_t o = (size_t)w * a.T + t;
+            a.score[o] = score;
+            a.nsnp[o] = (hi - lo) - g.nabs[i] + n;
+        }
         return;
     }
-    if (t >= a.T) return;
 
-    int64_t score = kNegInf64;
-    if (hi > lo) {
-        const int64_t span = (int64_t)__ldg(a.pos + hi - 1) - (int64_t)p0;
-        const int64_t mag = (int64_t)(a.bonus < 0 ? -(int64_t)a.bonus : a.bonus) +
-                            (int64_t)(a.penalty < 0 ? -(int64_t)a.penalty : a.penalty);
-        const int64_t bound = span + (int64_t)(hi - lo + 1) * mag;  // |any chain score| <= bound
-        const bool small = bound < (int64_t(1) << 28);
-        if (staged) {
-            int n2 = 0;  // n was counted while staging
-            if (small) prefix_dp_unit<int32_t, true>(a, t, lo, hi, p0, ring_raw, s_car, s_two, s_pos, tid, bd, n2, score);
-            else       prefix_dp_unit<int64_t, true>(a, t, lo, hi, p0, ring_raw, s_car, s_two, s_pos, tid, bd, n2, score);
-        } else {
-            if (small) prefix_dp_unit<int32_t, false>(a, t, lo, hi, p0, ring_raw, s_car, s_two, s_pos, tid, bd, n, score);
-            else       prefix_dp_unit<int64_t, false>(a, t, lo, hi, p0, ring_raw, s_car, s_two, s_pos, tid, bd, n, score);
+    // ---- fallback: window by window from global memory
+    for (int i = 0; i < nwin; ++i) {
+        const int w = w0 + i;
+        const int32_t lo = g.lo[i], hi = g.hi[i];
+        if (tid == 0) { g.red_nabs = 0; g.red_ex = 0; }
+        __syncthreads();
+        if (hi > lo) {
+            const int wi0 = lo >> 5, wi1 = (hi - 1) >> 5;
+            int na = 0;
+            uint32_t ex = 0;
+            for (int gi = wi0 + tid; gi <= wi1; gi += bd) {
+                uint32_t rm = 0xffffffffu;
+                if (gi == wi0) rm &= 0xffffffffu << (lo & 31);
+                if (gi == wi1) rm &= 0xffffffffu >> (31 - ((hi - 1) & 31));
+                na += __popc(__ldg(a.absent_bits + gi) & rm);
+                ex |= __ldg(a.exotic + gi);
+            }
+            na = __reduce_add_sync(0xffffffffu, na);
+            ex = __reduce_or_sync(0xffffffffu, ex);
+            if ((tid & 31) == 0 && (na | ex)) {
+                atomicAdd(&g.red_nabs, na);
+                if (ex) atomicOr(&g.red_ex, ex);
+            }
         }
+        __syncthreads();
+        const int32_t nabs = g.red_nabs;
+        const uint32_t wex = g.red_ex;
+        __syncthreads();  // everyone has read the reduction before the next window resets it
+        if (wex) {
+            if (chunk == 0 && tid == 0) a.slow_list[atomicAdd(&a.hdr->n_slow, 1)] = w;
+            continue;
+        }
+        if (t >= a.T) continue;
+        int n = 0;
+        int64_t score = kNegInf64;
+        if (hi > lo) {
+            const int64_t wspan = (int64_t)g.plast[i] - (int64_t)g.pfirst[i];
+            if (score_bound(wspan, hi - lo, a.bonus, a.penalty) < kSmallBound)
+                walk_dp_unit<int32_t>(LdgU32(), LdgPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus, a.penalty,
+                                      a.max_mm, n, score);
+            else
+                walk_dp_unit<int64_t>(LdgU32(), LdgPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus, a.penalty,
+                                      a.max_mm, n, score);
+        }
+        const size_t o = (size_t)w * a.T + t;
+        a.score[o] = score;
+        a.nsnp[o] = (hi - lo) - nabs + n;
     }
-    const size_t o = (size_t)w * a.T + t;
-    a.score[o] = score;
-    a.nsnp[o] = (hi - lo) - s_nabs + n;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -55,6 +55,8 @@ WsLayout make_layout(int64_t V, int32_t T, int32_t W, int32_t max_win_variants) 
     size_t w = (size_t)(W > 0 ? W : 1);
     L.off_win_lo = off;  off = align_up(off + w * 4, 256);
     L.off_win_hi = off;  off = align_up(off + w * 4, 256);
+    L.off_win_pfirst = off; off = align_up(off + w * 4, 256);
+    L.off_win_plast = off;  off = align_up(off + w * 4, 256);
     L.off_slow = off;    off = align_up(off + w * 4, 256);
     // pairwise list arena: at least one slab of the worst-case window must fit
     size_t worst = (size_t)(V > 0 ? V : 1);
@@ -128,12 +130,16 @@ int launch_prep(cudaStream_t st, bool do_pack, const int8_t *d_ref, const int8_t
         p.exotic = reinterpret_cast<uint32_t *>(ws + L.off_exotic);
         p.carried = reinterpret_cast<uint32_t *>(ws + L.off_carried);
         p.two = reinterpret_cast<uint32_t *>(ws + L.off_two);
-        // groups per CTA: staged tile <= ~64 KB, at most 8 groups, and >= 4 CTAs per SM when possible
+        // groups per CTA: staged tile <= ~64 KB, at most 8 groups; small problems get the fewest
+        // groups per CTA that still fit the whole grid in ONE wave (6 CTAs per SM by registers)
         const size_t per_group = (size_t)32 * ((size_t)R + (size_t)T);
-        int gpc = (int)((size_t)(64 << 10) / per_group);
-        if (gpc > 8) gpc = 8;
-        while (gpc > 1 && (L.G + gpc - 1) / gpc < 4 * kNumSM) --gpc;
-        if (gpc < 1) gpc = 1;
+        int gpc_max = (int)((size_t)(64 << 10) / per_group);
+        if (gpc_max > 8) gpc_max = 8;
+        if (gpc_max < 1) gpc_max = 1;
+        const int64_t wave = (int64_t)6 * kNumSM - (W + (kPackThreads / 32) - 1) / (kPackThreads / 32);
+        int gpc = 1;
+        while (gpc < gpc_max && (L.G + gpc - 1) / gpc > (wave > kNumSM ? wave : kNumSM)) ++gpc;
+        if ((L.G + gpc - 1) / gpc > 4 * (int64_t)6 * kNumSM) gpc = gpc_max;  // many waves anyway: biggest tiles
         p.gpc = gpc;
         p.ref_tile_bytes = (uint32_t)align_up((size_t)gpc * 32 * R + 32, 16);
         p.tgt_tile_bytes = (uint32_t)align_up((size_t)gpc * 32 * T + 32, 16);
@@ -152,6 +158,8 @@ int launch_prep(cudaStream_t st, bool do_pack, const int8_t *d_ref, const int8_t
         b.V = (int32_t)V; b.W = W;
         b.win_lo = reinterpret_cast<int32_t *>(ws + L.off_win_lo);
         b.win_hi = reinterpret_cast<int32_t *>(ws + L.off_win_hi);
+        b.win_pfirst = reinterpret_cast<int32_t *>(ws + L.off_win_pfirst);
+        b.win_plast = reinterpret_cast<int32_t *>(ws + L.off_win_plast);
         b.slow_list = reinterpret_cast<int32_t *>(ws + L.off_slow);
         b.hdr = reinterpret_cast<WsHeader *>(ws);
         b.force_slow = (algo == SSTAR_B200_ALGO_PAIRWISE);
@@ -169,7 +177,7 @@ int launch_prep(cudaStream_t st, bool do_pack, const int8_t *d_ref, const int8_t
     return 0;
 }
 
-int launch_score(cudaStream_t st, const int8_t *d_tgt, const int32_t *d_pos, int32_t T, const int32_t *d_ws,
+int launch_score(cudaStream_t st, const int8_t *d_tgt, const int32_t *d_pos, int64_t V, int32_t T, const int32_t *d_ws,
                  const int32_t *d_we, int32_t fixed_s, int32_t fixed_e, int32_t W, int32_t bonus,
                  int32_t max_mm, int32_t penalty, int64_t *d_score, int32_t *d_nsnp, uint8_t *ws,
                  const WsLayout &L, int algo, int32_t max_win_variants) {
@@ -182,10 +190,12 @@ int launch_score(cudaStream_t st, const int8_t *d_tgt, const int32_t *d_pos, int
     s.two = reinterpret_cast<const uint32_t *>(ws + L.off_two);
     s.win_lo = reinterpret_cast<const int32_t *>(ws + L.off_win_lo);
     s.win_hi = reinterpret_cast<const int32_t *>(ws + L.off_win_hi);
+    s.win_pfirst = reinterpret_cast<const int32_t *>(ws + L.off_win_pfirst);
+    s.win_plast = reinterpret_cast<const int32_t *>(ws + L.off_win_plast);
     s.win_start = d_ws; s.win_end = d_we; s.fixed_start = fixed_s; s.fixed_end = fixed_e;
     s.slow_list = reinterpret_cast<int32_t *>(ws + L.off_slow);
     s.hdr = reinterpret_cast<WsHeader *>(ws);
-    s.T = T; s.Tp = L.Tp; s.W = W;
+    s.V = (int32_t)V; s.T = T; s.Tp = L.Tp; s.W = W;
     s.bonus = bonus; s.max_mm = max_mm; s.penalty = penalty;
     s.score = d_score; s.nsnp = d_nsnp;
     s.arena = ws + L.off_arena; s.arena_entries = L.arena_entries;
@@ -195,40 +205,29 @@ int launch_score(cudaStream_t st, const int8_t *d_tgt, const int32_t *d_pos, int
         if (bd > kScoreMaxThreads) bd = kScoreMaxThreads;
         const int tchunks = (T + bd - 1) / bd;
         s.tchunks = tchunks;
-        const int gy = W < 32768 ? W : 32768;
-        const int gz = (W + gy - 1) / gy;
-        // stage each unit's plane words + the window's positions in shared memory when the caller
-        // bounded the window size and it fits; otherwise the kernel reads global memory directly
-        size_t smem = (size_t)kRingSlots * bd * 12;
-        int words_cap = 0, pos_cap = 0;
+        // Windows per CTA: as many as share variants (amortises the list build), but keep at least
+        // ~4 CTAs per SM in flight and keep a group's union range inside the staged position tile.
+        const int words_cap = kScoreWordsCap;
+        int wg = 8;
         if (max_win_variants > 0) {
-            const int wc = (max_win_variants + 30) / 32 + 1;
-            const size_t extra = (size_t)wc * bd * 8 + (size_t)wc * 32 * 4;
-            if (smem + extra <= (size_t)96 << 10) {
-                words_cap = wc;
-                pos_cap = wc * 32;
-                smem += extra;
-            }
+            const int fit = (words_cap * 32) / max_win_variants;  // disjoint windows (replicates) still fit
+            if (fit < wg) wg = fit < 1 ? 1 : fit;
         }
-        static thread_local size_t k2_smem_set = 48 << 10;
+        while (wg > 1 && (int64_t)((W + wg - 1) / wg) * tchunks < 4 * kNumSM) wg >>= 1;
+        const int64_t ngroups = (W + wg - 1) / wg;
+        if (ngroups * tchunks > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "too many (window group, column chunk) tiles%s");
+        const int L = kScoreListBytes / (bd * 4);  // list slots per column
+        const size_t ring_b = (size_t)kRingSlots * bd * 4, pos_b = (size_t)words_cap * 32 * 4;
+        const size_t smem = (size_t)L * bd * 4 + (ring_b > pos_b ? ring_b : pos_b);
+        static thread_local size_t k2_smem_set = 0;
         if (smem > k2_smem_set) {
-            cudaError_t e = cudaFuncSetAttribute(score_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaFuncSetAttribute(prefix): %s", cudaGetErrorString(e));
+            cudaError_t e = cudaFuncSetAttribute(score_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaFuncSetAttribute(score_group): %s", cudaGetErrorString(e));
             k2_smem_set = smem;
         }
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)tchunks, (unsigned)gy, (unsigned)gz);
-        cfg.blockDim = dim3((unsigned)bd);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        ++g_launches;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, score_prefix_kernel, s, words_cap, pos_cap);
-        if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "score_prefix_kernel launch: %s", cudaGetErrorString(e));
+        cudaError_t e = launch(score_group_kernel, (unsigned)(ngroups * tchunks), (unsigned)bd, smem, st, true, s, wg, L,
+                               words_cap);
+        if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "score_group_kernel launch: %s", cudaGetErrorString(e));
     }
     const size_t psmem = (size_t)kPairWarps * kPairSmemCap * 13;
     static thread_local bool pair_attr = false;
@@ -275,7 +274,7 @@ int run_pipeline(int device, cudaStream_t st, bool do_pack, const int8_t *d_ref,
     if (guard.err != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
     int rc = launch_prep(st, do_pack, d_ref, d_tgt, V, R, T, d_pos, d_ws, d_we, d_seg, fixed_s, fixed_e, W, ws, L, algo);
     if (rc) return rc;
-    return launch_score(st, d_tgt, d_pos, T, d_ws, d_we, fixed_s, fixed_e, W, bonus, max_mm, penalty, d_score,
+    return launch_score(st, d_tgt, d_pos, V, T, d_ws, d_we, fixed_s, fixed_e, W, bonus, max_mm, penalty, d_score,
                         d_nsnp, ws, L, algo, max_win_variants);
 }
 

@@ -179,6 +179,35 @@ class ScoreEngine:
         self.launches = self.lib.sstar_b200_last_launch_count()
         return score, nsnp
 
+    def plan_device(self, ref_d, tgt_d, pos_d, ws_d, we_d, match_bonus=5000, max_mismatch=5,
+                    mismatch_penalty=-10000, algo="auto", max_win_variants=0, out=None):
+        """Capture one whole scoring pass over fixed device buffers into a CUDA graph.
+
+        Returns a :class:`ScorePlan`; ``plan.run()`` replays pack -> bounds -> DP with ONE host
+        call (the three launches keep their programmatic-dependent-launch edges inside the graph),
+        which is what small chromosomes need: at C2 size the kernels take ~20 us and the host-side
+        launch path would otherwise dominate.  Refill the input tensors in place between runs.
+        """
+        torch = self.torch
+        W, T = ws_d.shape[0], tgt_d.shape[1]
+        if out is None:
+            out = (torch.empty((W, T), dtype=torch.int64, device=self.tdev),
+                   torch.empty((W, T), dtype=torch.int32, device=self.tdev))
+        kw = dict(match_bonus=match_bonus, max_mismatch=max_mismatch, mismatch_penalty=mismatch_penalty,
+                  algo=algo, max_win_variants=max_win_variants, out=out)
+        with torch.cuda.device(self.tdev):
+            side = torch.cuda.Stream(self.tdev)
+            side.wait_stream(torch.cuda.current_stream(self.tdev))
+            with torch.cuda.stream(side):  # warm-up: sizes the workspace, sets kernel attributes
+                self.score_device(ref_d, tgt_d, pos_d, ws_d, we_d, **kw)
+            torch.cuda.current_stream(self.tdev).wait_stream(side)
+            side.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.score_device(ref_d, tgt_d, pos_d, ws_d, we_d, **kw)
+            launches = self.launches
+        return ScorePlan(graph, out[0], out[1], launches, (ref_d, tgt_d, pos_d, ws_d, we_d, self._dev.get("ws")))
+
     # ------------------------------------------------------------------ host API
     def _h2d(self, key, arr: np.ndarray, tdtype):
         """numpy -> pinned staging -> device (async on the current stream)."""
@@ -297,6 +326,19 @@ class ScoreEngine:
             score = score_d.cpu().numpy()
             nsnp = nsnp_d.cpu().numpy()
         return score, nsnp
+
+
+class ScorePlan:
+    """A captured scoring pass (see :meth:`ScoreEngine.plan_device`)."""
+
+    def __init__(self, graph, score, nsnp, launches, keepalive):
+        self.graph, self.score, self.nsnp, self.launches = graph, score, nsnp, launches
+        self._keepalive = keepalive  # the graph holds raw pointers into these tensors
+
+    def run(self):
+        """Enqueue the pass on the current stream; results land in ``self.score`` / ``self.nsnp``."""
+        self.graph.replay()
+        return self.score, self.nsnp
 
 
 _ENGINES = {}

@@ -1,0 +1,160 @@
+// Host emulation of score_group_kernel's control flow around the REAL DP core (dp_core.cuh,
+// compiled here for the host).  TEST INFRASTRUCTURE: lets `pytest -m "not gpu"` check the device
+// arithmetic against the oracle without a GPU.  One "thread" = one column; the planes, the group
+// logic and the list build mirror sstar_b200/csrc/{prep,score}_kernels.cuh in scalar form.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+#include "../../sstar_b200/csrc/dp_core.cuh"
+
+using namespace sstar;
+
+namespace {
+struct HostLd { uint32_t operator()(const uint32_t *p) const { return *p; } };
+struct HostPos {
+    const int32_t *pos;
+    int64_t operator()(int32_t k) const { return (int64_t)pos[k]; }
+};
+int32_t lower_bound_i64(const int32_t *pos, int64_t V, int64_t x) {
+    int64_t lo = 0, hi = V;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)pos[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    return (int32_t)lo;
+}
+}  // namespace
+
+extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const int32_t *pos, int64_t V, int32_t R,
+                                  int32_t T, const int32_t *ws, const int32_t *we, int32_t W, int32_t bonus,
+                                  int32_t max_mm, int32_t penalty, int32_t wg, int32_t L, int32_t words_cap,
+                                  int64_t *score, int32_t *nsnp, uint8_t *slow /*[W]*/, int32_t *path /*[W,T]*/) {
+    const int64_t G = (V + 31) / 32;
+    const int32_t Tp = (T + 31) / 32 * 32;
+    std::vector<uint32_t> absent(G > 0 ? G : 1, 0), exotic(G > 0 ? G : 1, 0);
+    std::vector<uint32_t> carried((size_t)(G > 0 ? G : 1) * Tp, 0), two((size_t)(G > 0 ? G : 1) * Tp, 0);
+    for (int64_t k = 0; k < V; ++k) {
+        int sum = 0;
+        for (int r = 0; r < R; ++r) sum += ref[k * R + r];
+        if (sum != 0) continue;
+        absent[k >> 5] |= 1u << (k & 31);
+        for (int t = 0; t < T; ++t) {
+            const int b = tgt[k * T + t];
+            if (b != 0) carried[(size_t)(k >> 5) * Tp + t] |= 1u << (k & 31);
+            if (b == 2) two[(size_t)(k >> 5) * Tp + t] |= 1u << (k & 31);
+            if ((unsigned)b > 2u) exotic[k >> 5] = 1;
+        }
+    }
+    std::vector<int32_t> wlo(W), whi(W);
+    for (int w = 0; w < W; ++w) {
+        wlo[w] = lower_bound_i64(pos, V, ws[w]);
+        whi[w] = std::max(wlo[w], lower_bound_i64(pos, V, (int64_t)we[w] + 1));
+    }
+    memset(slow, 0, W);
+    const int32_t pen_eff = (max_mm >= 1) ? penalty : Sentinel<int32_t>::NEG;
+    std::vector<uint32_t> list(L), spos;
+    int32_t ring[kRingSlots];
+    auto window_absent = [&](int32_t lo, int32_t hi, int32_t &na, uint32_t &ex) {
+        na = 0; ex = 0;
+        if (hi <= lo) return;
+        for (int gi = lo >> 5; gi <= ((hi - 1) >> 5); ++gi) {
+            uint32_t rm = 0xffffffffu;
+            if (gi == (lo >> 5)) rm &= 0xffffffffu << (lo & 31);
+            if (gi == ((hi - 1) >> 5)) rm &= 0xffffffffu >> (31 - ((hi - 1) & 31));
+            na += __builtin_popcount(absent[gi] & rm);
+            ex |= exotic[gi];
+        }
+    };
+    for (int w0 = 0; w0 < W; w0 += wg) {
+        const int nwin = std::min(wg, W - w0);
+        int32_t rlo = INT32_MAX, rhi = -1, prev_lo = -1, maxnv = 0;
+        bool mono = true;
+        for (int i = 0; i < nwin; ++i) {
+            const int32_t lo = wlo[w0 + i], hi = whi[w0 + i];
+            if (hi > lo) {
+                mono = mono && lo >= prev_lo;
+                prev_lo = lo;
+                rlo = std::min(rlo, lo); rhi = std::max(rhi, hi); maxnv = std::max(maxnv, hi - lo);
+            }
+        }
+        if (rhi < 0) {
+            for (int i = 0; i < nwin; ++i)
+                for (int t = 0; t < T; ++t) {
+                    score[(size_t)(w0 + i) * T + t] = kNegInf64; nsnp[(size_t)(w0 + i) * T + t] = 0; path[(size_t)(w0 + i) * T + t] = 0;
+                }
+            continue;
+        }
+        const int gi0 = rlo >> 5, nwr = ((rhi - 1) >> 5) - gi0 + 1;
+        const int32_t p0 = pos[rlo];
+        const int64_t span = (int64_t)pos[rhi - 1] - p0;
+        const bool fast = mono && nwr <= words_cap && score_bound(span, maxnv, bonus, penalty) < kSmallBound;
+        if (fast) {
+            const int32_t base = gi0 << 5;
+            const int32_t npos = (int32_t)std::min<int64_t>((int64_t)nwr << 5, V - base);
+            spos.assign((size_t)nwr << 5, 0);
+            for (int i = 0; i < npos; ++i) spos[i] = (uint32_t)(pos[base + i] - p0);
+            for (int t = 0; t < T; ++t) {
+                int cnt = 0;
+                for (int j = 0; j < nwr; ++j) {
+                    uint32_t c = carried[(size_t)(gi0 + j) * Tp + t];
+                    if (j == 0) c &= 0xffffffffu << (rlo & 31);
+                    if (j == nwr - 1) c &= 0xffffffffu >> (31 - ((rhi - 1) & 31));
+                    const uint32_t tw = two[(size_t)(gi0 + j) * Tp + t];
+                    while (c) {
+                        const int b = __builtin_ctz(c);
+                        c &= c - 1;
+                        if (cnt < L) list[cnt] = (spos[(j << 5) + b] << 1) | ((tw >> b) & 1u);
+                        ++cnt;
+                    }
+                }
+                const bool overflow = cnt > L;
+                int cur = 0;
+                for (int i = 0; i < nwin; ++i) {
+                    const int w = w0 + i;
+                    const int32_t lo = wlo[w], hi = whi[w];
+                    int32_t na; uint32_t ex;
+                    window_absent(lo, hi, na, ex);
+                    if (ex) { slow[w] = 1; continue; }
+                    int n = 0; int64_t sc = kNegInf64;
+                    if (hi > lo) {
+                        const uint32_t plo = (uint32_t)(pos[lo] - p0), phi = (uint32_t)(pos[hi - 1] - p0);
+                        if (!overflow) list_dp_window(list.data(), 1, ring, 1, cur, cnt, plo, phi, bonus, pen_eff, n, sc);
+                        else walk_dp_unit<int32_t>(HostLd(), HostPos{pos}, carried.data(), two.data(), Tp, t, lo, hi, bonus, penalty, max_mm, n, sc);
+                    }
+                    score[(size_t)w * T + t] = sc;
+                    nsnp[(size_t)w * T + t] = (hi - lo) - na + n;
+                    path[(size_t)w * T + t] = overflow ? 2 : 1;
+                }
+            }
+            continue;
+        }
+        for (int i = 0; i < nwin; ++i) {
+            const int w = w0 + i;
+            const int32_t lo = wlo[w], hi = whi[w];
+            int32_t na; uint32_t ex;
+            window_absent(lo, hi, na, ex);
+            if (ex) { slow[w] = 1; continue; }
+            for (int t = 0; t < T; ++t) {
+                int n = 0; int64_t sc = kNegInf64;
+                int pth = 0;
+                if (hi > lo) {
+                    const int64_t wspan = (int64_t)pos[hi - 1] - (int64_t)pos[lo];
+                    if (score_bound(wspan, hi - lo, bonus, penalty) < kSmallBound) {
+                        walk_dp_unit<int32_t>(HostLd(), HostPos{pos}, carried.data(), two.data(), Tp, t, lo, hi, bonus, penalty, max_mm, n, sc);
+                        pth = 3;
+                    } else {
+                        walk_dp_unit<int64_t>(HostLd(), HostPos{pos}, carried.data(), two.data(), Tp, t, lo, hi, bonus, penalty, max_mm, n, sc);
+                        pth = 4;
+                    }
+                }
+                score[(size_t)w * T + t] = sc;
+                nsnp[(size_t)w * T + t] = (hi - lo) - na + n;
+                path[(size_t)w * T + t] = pth;
+            }
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,130 @@
+"""The device DP core (sstar_b200/csrc/dp_core.cuh) compiled for the host and driven through a
+scalar emulation of score_group_kernel (tests/emul/emul_score.cpp), against the C oracle.
+
+Runs without a GPU: it pins the arithmetic of the kernels (list DP, waiting-site ring, walk DP,
+int32/int64 switch, group logic) before any GPU time is spent.  Bit-exact."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+from sstar_b200.synth import regular_windows, synth_chromosome
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "emul", "emul_score.cpp")
+LIB = os.path.join(HERE, "emul", "libemul_score.so")
+CORE = os.path.join(os.path.dirname(HERE), "sstar_b200", "csrc", "dp_core.cuh")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(CORE)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", LIB, SRC])
+    lib = ctypes.CDLL(LIB)
+    lib.emul_score_windows.restype = ctypes.c_int
+    lib.emul_score_windows.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                                               ctypes.c_void_p, ctypes.c_void_p] + \
+        [ctypes.c_int32] * 7 + [ctypes.c_void_p] * 4
+
+    def run(ref, tgt, pos, ws, we, params=(5000, 5, -10000), wg=8, L=64, words_cap=64):
+        ref = np.ascontiguousarray(ref, dtype=np.int8)
+        tgt = np.ascontiguousarray(tgt, dtype=np.int8)
+        pos = np.ascontiguousarray(pos, dtype=np.int32)
+        ws = np.ascontiguousarray(ws, dtype=np.int32)
+        we = np.ascontiguousarray(we, dtype=np.int32)
+        V, R = ref.shape
+        T = tgt.shape[1]
+        W = len(ws)
+        score = np.empty((W, T), np.int64)
+        nsnp = np.empty((W, T), np.int32)
+        slow = np.zeros(W, np.uint8)
+        path = np.zeros((W, T), np.int32)
+        rc = lib.emul_score_windows(ref.ctypes.data, tgt.ctypes.data, pos.ctypes.data, V, R, T, ws.ctypes.data,
+                                    we.ctypes.data, W, *params, wg, L, words_cap, score.ctypes.data,
+                                    nsnp.ctypes.data, slow.ctypes.data, path.ctypes.data)
+        assert rc == 0
+        return score, nsnp, slow.astype(bool), path
+    return run
+
+
+def check(emul, ref, tgt, pos, ws, we, params=(5000, 5, -10000), **kw):
+    s, n, slow, path = emul(ref, tgt, pos, ws, we, params, **kw)
+    so, no = c_oracle.score_windows(ref, tgt, pos, ws, we, *params)
+    keep = ~slow
+    assert np.array_equal(s[keep], so[keep])
+    assert np.array_equal(n[keep], no[keep])
+    return path[keep], slow
+
+
+@pytest.mark.parametrize("wg", [1, 3, 8, 16])
+@pytest.mark.parametrize("shape", [(100, 50, False, 1_500_000), (5, 10, False, 500_000), (20, 33, True, 800_000)])
+def test_list_path_matches_oracle(emul, wg, shape):
+    n_ref, n_tgt, phased, length = shape
+    ref, tgt, pos = synth_chromosome(length, n_ref, n_tgt, phased, seed=500 + n_ref)
+    ws, we = regular_windows(pos, 50_000, 10_000)
+    path, slow = check(emul, ref, tgt, pos, ws, we, wg=wg, L=512)
+    assert not slow.any() and (path[path > 0] == 1).all()
+
+
+def test_list_overflow_falls_back_per_column(emul):
+    ref, tgt, pos = synth_chromosome(600_000, 5, 10, False, seed=9)
+    ws, we = regular_windows(pos, 50_000, 10_000)
+    path, _ = check(emul, ref, tgt, pos, ws, we, wg=8, L=24)
+    assert (path == 2).any() and (path == 1).any()
+
+
+def test_crowded_positions_exercise_the_ring(emul):
+    # many carried sites within 9 bp of each other: several sites wait at once
+    rng = np.random.default_rng(4)
+    V = 4000
+    pos = np.cumsum(rng.choice([1, 1, 2, 3, 9, 10, 11, 40], size=V)).astype(np.int32)
+    tgt = rng.choice([0, 1, 2], size=(V, 7), p=[0.2, 0.5, 0.3]).astype(np.int8)
+    ref = np.zeros((V, 2), np.int8)
+    ref[rng.random(V) < 0.15, 0] = 1
+    ws = np.arange(1, int(pos[-1]), 300, dtype=np.int32)
+    we = ws + 1499
+    for params in [(5000, 5, -10000), (1, 1, 0), (7, 0, -3), (123, 4, -7)]:
+        path, _ = check(emul, ref, tgt, pos, ws, we, params, wg=8, L=1024)
+        assert (path == 1).mean() > 0.9
+        check(emul, ref, tgt, pos, ws, we, params, wg=4, L=8)       # per-column overflow -> walk DP
+        check(emul, ref, tgt, pos, ws, we, params, wg=8, words_cap=2)  # group too wide -> walk DP
+
+
+def test_missing_data_routes_windows_to_slow_list(emul):
+    ref, tgt, pos = synth_chromosome(500_000, 10, 24, False, seed=77)
+    rng = np.random.default_rng(5)
+    tgt = tgt.copy()
+    miss = rng.random(tgt.shape) < 0.0001
+    tgt[miss] = -1
+    ref = ref.copy()
+    ref[rng.random(ref.shape) < 0.002] = -1
+    ws, we = regular_windows(pos, 50_000, 10_000)
+    _, slow = check(emul, ref, tgt, pos, ws, we, wg=8)
+    assert slow.any() and not slow.all()
+
+
+def test_int64_switch_and_odd_windows(emul):
+    rng = np.random.default_rng(8)
+    V = 3000
+    pos = np.cumsum(rng.integers(1, 60, size=V)).astype(np.int32)
+    tgt = rng.choice([0, 1, 2], size=(V, 5), p=[0.5, 0.3, 0.2]).astype(np.int8)
+    ref = (rng.random((V, 3)) < 0.2).astype(np.int8)
+    # non-monotone, empty, nested and out-of-range windows in one group
+    ws = np.array([5000, 1, 70000, 300, 300, 10_000_000, -5, 40000, 20000], dtype=np.int32)
+    we = np.array([9000, 90000, 70001, 200, 5000, 10_000_100, 2_000_000_000, 45000, 20000], dtype=np.int32)
+    check(emul, ref, tgt, pos, ws, we, wg=4)
+    path, _ = check(emul, ref, tgt, pos, ws, we, (2_000_000_000, 5, -2_000_000_000), wg=4)
+    assert (path == 4).any()
+    mono_s = np.sort(ws[[0, 2, 4, 7, 8]])
+    check(emul, ref, tgt, pos, mono_s, mono_s + 4000, (2_000_000_000, 5, -2_000_000_000), wg=4)
+
+
+def test_replicate_style_disjoint_windows(emul):
+    ref, tgt, pos = synth_chromosome(800_000, 5, 10, False, seed=21)
+    ws = np.arange(1, 800_000, 50_000, dtype=np.int32)
+    we = ws + 49_999
+    path, _ = check(emul, ref, tgt, pos, ws, we, wg=8, L=512, words_cap=64)
+    assert (path[path > 0] == 1).any()
