@@ -51,11 +51,20 @@ extern "C" {
 #define SSTAR_B200_ALGO_AUTO 0     /* prefix-max DP; windows with genotypes outside {0,1,2} go pairwise */
 #define SSTAR_B200_ALGO_PAIRWISE 1 /* literal O(n^2) recurrence of sstar/sstar.py:208-212 for every window */
 
+/* sstar_b200_options.flags */
+#define SSTAR_B200_FLAG_STAGED_COPIES 1 /* host entry: always copy through device staging buffers,
+                                           even when the host buffers are mapped (zero-copy capable) */
+/* host entry, mapped buffers: tuning knobs of the pipelined path */
+#define SSTAR_B200_FLAG_COPY_OUTPUTS 4      /* result tables always by D2H copies (default: only when >= 8 MB) */
+#define SSTAR_B200_FLAG_SINGLE_CHUNK 8      /* no row chunking */
+
 typedef struct sstar_b200_options {
     int32_t algo;             /* SSTAR_B200_ALGO_* */
-    int32_t max_win_variants; /* upper bound on variants inside any window (hi - lo), used only to
-                                 size the pairwise list arena; 0 = unknown (sized for V) */
-    int32_t reserved[6];      /* must be zero */
+    int32_t max_win_variants; /* upper bound on variants inside any window (hi - lo): sizes the
+                                 pairwise list arena and the window groups of the score kernel;
+                                 0 = unknown (sized for V) */
+    int32_t flags;            /* SSTAR_B200_FLAG_* */
+    int32_t reserved[5];      /* must be zero */
 } sstar_b200_options;
 
 /* replaces: nothing in the reference (library identification) */
@@ -120,11 +129,16 @@ int sstar_b200_score_packed(int device, void *stream, const int8_t *d_tgt_gt, co
                             int32_t *d_nsnp, void *d_workspace, size_t workspace_bytes,
                             const sstar_b200_options *opts);
 
-/* Host-buffer entry (the end-to-end call): copies the inputs host->device, scores, and copies the
- * two result tables device->host, all enqueued on `stream`; the caller synchronises the stream
- * before reading h_score / h_nsnp.  Host buffers should be page-locked for the copies to be
- * asynchronous.  `d_scratch` is device memory of at least sstar_b200_host_scratch_bytes(...).
- * replaces: the same reference functions as sstar_b200_score_windows, fed from numpy arrays. */
+/* Host-buffer entry (the end-to-end call).  All work is enqueued on `stream` (plus an internal
+ * copy stream that `stream` joins before the call's last kernel); the caller synchronises
+ * `stream` before reading h_score / h_nsnp.
+ *   - If every host buffer is page-locked AND mapped (cudaHostAlloc / cudaHostRegister / torch
+ *     pin_memory) the call is pipelined: the genotype matrices move host->device in row chunks
+ *     while earlier chunks are packed and their windows scored, and the score kernels store the
+ *     result tables straight into h_score / h_nsnp over PCIe.
+ *   - Otherwise (pageable memory, or SSTAR_B200_FLAG_STAGED_COPIES) inputs are copied to device
+ *     staging buffers, scored, and the tables copied back, all on `stream`.
+ * `d_scratch` is device memory of at least sstar_b200_host_scratch_bytes(...) either way. */
 size_t sstar_b200_host_scratch_bytes(int64_t V, int32_t R, int32_t T, int32_t W,
                                      int32_t max_win_variants);
 

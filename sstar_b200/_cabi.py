@@ -19,7 +19,10 @@ ALGOS = {"auto": ALGO_AUTO, "pairwise": ALGO_PAIRWISE}
 
 class Options(ctypes.Structure):
     _fields_ = [("algo", ctypes.c_int32), ("max_win_variants", ctypes.c_int32),
-                ("reserved", ctypes.c_int32 * 6)]
+                ("flags", ctypes.c_int32), ("reserved", ctypes.c_int32 * 5)]
+
+
+FLAG_STAGED_COPIES = 1
 
 
 class SstarB200Error(RuntimeError):

@@ -16,11 +16,13 @@ constexpr int kPairWarps = 4;
 constexpr int kPairSmemCap = 1024;  // pairwise list entries per warp kept in shared memory
 constexpr int kNumSM = 148;
 
-// First 64 bytes of the workspace.
+constexpr int kMaxSlots = 32;       // independent score launches (window chunks) per call
+
+// First 256 bytes of the workspace.
 struct WsHeader {
     uint32_t status;
-    int32_t n_slow;  // windows routed to the pairwise kernel (written by prep, bumped by K2)
-    int32_t pad[14];
+    int32_t pad[31];
+    int32_t n_slow[kMaxSlots];  // per score launch: windows routed to the pairwise kernel
 };
 
 struct WsLayout {
@@ -46,7 +48,7 @@ struct BoundsArgs {
 struct PackArgs {
     const int8_t *ref, *tgt;
     int32_t V, R, T, Tp;
-    int32_t G, gpc;
+    int32_t g_begin, g_end, gpc;  // 32-variant groups [g_begin, g_end) packed by this launch
     uint32_t ref_tile_bytes;  // smem bytes reserved per tile (incl. alignment slack)
     uint32_t tgt_tile_bytes;
     uint32_t *absent_bits, *exotic, *carried, *two;
@@ -61,7 +63,10 @@ struct ScoreArgs {
     int32_t fixed_start, fixed_end;
     int32_t *slow_list;
     WsHeader *hdr;
-    int32_t V, T, Tp, W, tchunks;
+    int32_t V, T, Tp, tchunks;
+    int32_t w_begin, w_end;  // windows scored by this launch
+    int32_t slot;            // its counter in WsHeader::n_slow; its slow-list segment starts at w_begin
+    int32_t force_slow;      // every window of the launch goes to the pairwise kernel
     int32_t bonus, max_mm, penalty;
     int64_t *score;
     int32_t *nsnp;

@@ -33,7 +33,7 @@ __device__ __forceinline__ int32_t warp_lower_bound(const int32_t *__restrict__ 
 __device__ __forceinline__ void bounds_block(const BoundsArgs &a, int block, int nthreads, int tid) {
     const int lane = tid & 31;
     const int w = block * (nthreads >> 5) + (tid >> 5);
-    if (block == 0 && tid == 0) a.hdr->n_slow = a.force_slow ? a.W : 0;
+    if (block == 0 && tid < kMaxSlots) a.hdr->n_slow[tid] = 0;
     if (w >= a.W) return;
     const int32_t sb = a.seg ? a.seg[w] : 0;
     const int32_t se = a.seg ? a.seg[w + 1] : a.V;
@@ -49,7 +49,6 @@ __device__ __forceinline__ void bounds_block(const BoundsArgs &a, int block, int
     if (lane == 0) {
         a.win_lo[w] = lo;
         a.win_hi[w] = hi;
-        if (a.force_slow) a.slow_list[w] = w;
     }
 }
 
@@ -329,8 +328,8 @@ prep_kernel(const __grid_constant__ PackArgs p, const __grid_constant__ BoundsAr
         return;
     }
     const int tid = threadIdx.x;
-    const int32_t g0 = blockIdx.x * p.gpc;
-    const int ng = min(p.gpc, p.G - g0);
+    const int32_t g0 = p.g_begin + blockIdx.x * p.gpc;
+    const int ng = min(p.gpc, p.g_end - g0);
     const int32_t k0 = g0 * 32;
     const int nrows = min(ng * 32, p.V - k0);
     if (mode == 1) {

@@ -44,8 +44,8 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
     pdl_launch_dependents();
     const int tid = threadIdx.x, bd = blockDim.x;
     const int chunk = blockIdx.x % a.tchunks, grp = blockIdx.x / a.tchunks;
-    const int w0 = grp * wg;
-    const int nwin = min(wg, a.W - w0);
+    const int w0 = a.w_begin + grp * wg;
+    const int nwin = min(wg, a.w_end - w0);
     const int t = chunk * bd + tid;
     // the position tile is only read while the lists are built, the ring only during the DP:
     // they share one region (a barrier separates the two phases)
@@ -153,7 +153,7 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
         for (int i = 0; i < nwin; ++i) {
             const int w = w0 + i;
             if (g.ex[i]) {  // genotypes outside {0,1,2}: the whole window goes to the pairwise kernel
-                if (chunk == 0 && tid == 0) a.slow_list[atomicAdd(&a.hdr->n_slow, 1)] = w;
+                if (chunk == 0 && tid == 0) a.slow_list[a.w_begin + atomicAdd(&a.hdr->n_slow[a.slot], 1)] = w;
                 continue;
             }
             const int32_t lo = g.lo[i], hi = g.hi[i];
@@ -203,7 +203,7 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
         const uint32_t wex = g.red_ex;
         __syncthreads();  // everyone has read the reduction before the next window resets it
         if (wex) {
-            if (chunk == 0 && tid == 0) a.slow_list[atomicAdd(&a.hdr->n_slow, 1)] = w;
+            if (chunk == 0 && tid == 0) a.slow_list[a.w_begin + atomicAdd(&a.hdr->n_slow[a.slot], 1)] = w;
             continue;
         }
         if (t >= a.T) continue;
@@ -242,13 +242,14 @@ __global__ void __launch_bounds__(kPairWarps * 32) score_pairwise_kernel(ScoreAr
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_maxvw = 0;
     pdl_wait();  // slow_list / n_slow come from the previous launches
-    const int n_slow = a.hdr->n_slow;
+    const int n_slow = a.force_slow ? a.w_end - a.w_begin : a.hdr->n_slow[a.slot];
     if (n_slow <= 0) return;
+    auto slow_window = [&](int64_t i) -> int { return a.force_slow ? a.w_begin + (int)i : a.slow_list[a.w_begin + i]; };
     __syncthreads();
     {   // largest routed window decides where the lists live
         int mv = 0;
         for (int i = threadIdx.x; i < n_slow; i += blockDim.x) {
-            const int w = a.slow_list[i];
+            const int w = slow_window(i);
             mv = max(mv, a.win_hi[w] - a.win_lo[w]);
         }
         mv = __reduce_max_sync(0xffffffffu, mv);
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(kPairWarps * 32) score_pairwise_kernel(ScoreAr
     if (cap == 0) {  // every routed window is empty
         for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
              it += (int64_t)gridDim.x * blockDim.x) {
-            const size_t o = (size_t)a.slow_list[it / a.T] * a.T + (size_t)(it % a.T);
+            const size_t o = (size_t)slow_window(it / a.T) * a.T + (size_t)(it % a.T);
             a.score[o] = kNegInf64;
             a.nsnp[o] = 0;
         }
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(kPairWarps * 32) score_pairwise_kernel(ScoreAr
     int8_t *Gt = reinterpret_cast<int8_t *>(slab + (size_t)slab_cap * 12);
 
     for (int64_t it = gw; it < total; it += nw) {
-        const int w = a.slow_list[it / a.T];
+        const int w = slow_window(it / a.T);
         const int t = (int)(it % a.T);
         const int32_t lo = a.win_lo[w], hi = a.win_hi[w];
         int n = 0, nabs = 0;

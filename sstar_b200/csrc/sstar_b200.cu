@@ -114,18 +114,22 @@ cudaError_t launch(void (*kernel)(KArgs...), unsigned grid, unsigned block, size
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-// One "prep" grid: pack CTAs (if do_pack) followed by window-bounds CTAs (if W > 0).
-int launch_prep(cudaStream_t st, bool do_pack, const int8_t *d_ref, const int8_t *d_tgt, int64_t V, int32_t R,
-                int32_t T, const int32_t *d_pos, const int32_t *d_ws, const int32_t *d_we,
+// One "prep" grid: pack CTAs for the 32-variant groups [g_begin, g_end) (if any) followed by
+// window-bounds CTAs for W windows (if W > 0).
+int launch_prep(cudaStream_t st, int64_t g_begin, int64_t g_end, const int8_t *d_ref, const int8_t *d_tgt,
+                int64_t V, int32_t R, int32_t T, const int32_t *d_pos, const int32_t *d_ws, const int32_t *d_we,
                 const int32_t *d_seg, int32_t fixed_s, int32_t fixed_e, int32_t W, uint8_t *ws,
-                const WsLayout &L, int algo) {
+                const WsLayout &L) {
     PackArgs p = {};
     BoundsArgs b = {};
     int n_pack = 0, mode = 0;
     size_t smem = 0;
-    if (do_pack && V > 0) {
+    const int n_bounds = W > 0 ? (W + (kPackThreads / 32) - 1) / (kPackThreads / 32) : 0;
+    if (g_end > g_begin) {
+        const int64_t ngroups = g_end - g_begin;
         p.ref = d_ref; p.tgt = d_tgt;
-        p.V = (int32_t)V; p.R = R; p.T = T; p.Tp = L.Tp; p.G = (int32_t)L.G;
+        p.V = (int32_t)V; p.R = R; p.T = T; p.Tp = L.Tp;
+        p.g_begin = (int32_t)g_begin; p.g_end = (int32_t)g_end;
         p.absent_bits = reinterpret_cast<uint32_t *>(ws + L.off_absent);
         p.exotic = reinterpret_cast<uint32_t *>(ws + L.off_exotic);
         p.carried = reinterpret_cast<uint32_t *>(ws + L.off_carried);
@@ -136,10 +140,10 @@ int launch_prep(cudaStream_t st, bool do_pack, const int8_t *d_ref, const int8_t
         int gpc_max = (int)((size_t)(64 << 10) / per_group);
         if (gpc_max > 8) gpc_max = 8;
         if (gpc_max < 1) gpc_max = 1;
-        const int64_t wave = (int64_t)6 * kNumSM - (W + (kPackThreads / 32) - 1) / (kPackThreads / 32);
+        const int64_t wave = (int64_t)6 * kNumSM - n_bounds;
         int gpc = 1;
-        while (gpc < gpc_max && (L.G + gpc - 1) / gpc > (wave > kNumSM ? wave : kNumSM)) ++gpc;
-        if ((L.G + gpc - 1) / gpc > 4 * (int64_t)6 * kNumSM) gpc = gpc_max;  // many waves anyway: biggest tiles
+        while (gpc < gpc_max && (ngroups + gpc - 1) / gpc > (wave > kNumSM ? wave : kNumSM)) ++gpc;
+        if ((ngroups + gpc - 1) / gpc > 4 * (int64_t)6 * kNumSM) gpc = gpc_max;  // many waves anyway: biggest tiles
         p.gpc = gpc;
         p.ref_tile_bytes = (uint32_t)align_up((size_t)gpc * 32 * R + 32, 16);
         p.tgt_tile_bytes = (uint32_t)align_up((size_t)gpc * 32 * T + 32, 16);
@@ -149,9 +153,8 @@ int launch_prep(cudaStream_t st, bool do_pack, const int8_t *d_ref, const int8_t
             mode = 1;
             smem = fixed;
         }
-        n_pack = (int)((L.G + gpc - 1) / gpc);
+        n_pack = (int)((ngroups + gpc - 1) / gpc);
     }
-    int n_bounds = 0;
     if (W > 0) {
         b.pos = d_pos; b.win_start = d_ws; b.win_end = d_we; b.seg = d_seg;
         b.fixed_start = fixed_s; b.fixed_end = fixed_e;
@@ -160,10 +163,7 @@ int launch_prep(cudaStream_t st, bool do_pack, const int8_t *d_ref, const int8_t
         b.win_hi = reinterpret_cast<int32_t *>(ws + L.off_win_hi);
         b.win_pfirst = reinterpret_cast<int32_t *>(ws + L.off_win_pfirst);
         b.win_plast = reinterpret_cast<int32_t *>(ws + L.off_win_plast);
-        b.slow_list = reinterpret_cast<int32_t *>(ws + L.off_slow);
         b.hdr = reinterpret_cast<WsHeader *>(ws);
-        b.force_slow = (algo == SSTAR_B200_ALGO_PAIRWISE);
-        n_bounds = (W + (kPackThreads / 32) - 1) / (kPackThreads / 32);
     }
     if (n_pack + n_bounds == 0) return 0;
     static thread_local size_t smem_set = 0;
@@ -177,13 +177,28 @@ int launch_prep(cudaStream_t st, bool do_pack, const int8_t *d_ref, const int8_t
     return 0;
 }
 
-int launch_score(cudaStream_t st, const int8_t *d_tgt, const int32_t *d_pos, int64_t V, int32_t T, const int32_t *d_ws,
-                 const int32_t *d_we, int32_t fixed_s, int32_t fixed_e, int32_t W, int32_t bonus,
-                 int32_t max_mm, int32_t penalty, int64_t *d_score, int32_t *d_nsnp, uint8_t *ws,
-                 const WsLayout &L, int algo, int32_t max_win_variants) {
-    if (W == 0) return 0;
+struct ScoreCall {
+    const int8_t *d_tgt;
+    const int32_t *d_pos;
+    int64_t V;
+    int32_t T;
+    int32_t bonus, max_mm, penalty;
+    int64_t *d_score;
+    int32_t *d_nsnp;
+    uint8_t *ws;
+    int algo;
+    int32_t max_win_variants;
+};
+
+// Scores windows [w_begin, w_end) (bounds and planes must be in the workspace): the grouped
+// prefix-max kernel, then the pairwise kernel for whatever it routed to the slow list.
+int launch_score(cudaStream_t st, const ScoreCall &c, const WsLayout &L, int32_t w_begin, int32_t w_end, int slot) {
+    const int32_t W = w_end - w_begin;
+    if (W <= 0) return 0;
+    if (slot < 0 || slot >= kMaxSlots) return fail(SSTAR_B200_EINVAL, "internal: bad score slot%s");
+    uint8_t *ws = c.ws;
     ScoreArgs s = {};
-    s.pos = d_pos; s.tgt = d_tgt;
+    s.pos = c.d_pos; s.tgt = c.d_tgt;
     s.absent_bits = reinterpret_cast<const uint32_t *>(ws + L.off_absent);
     s.exotic = reinterpret_cast<const uint32_t *>(ws + L.off_exotic);
     s.carried = reinterpret_cast<const uint32_t *>(ws + L.off_carried);
@@ -192,15 +207,17 @@ int launch_score(cudaStream_t st, const int8_t *d_tgt, const int32_t *d_pos, int
     s.win_hi = reinterpret_cast<const int32_t *>(ws + L.off_win_hi);
     s.win_pfirst = reinterpret_cast<const int32_t *>(ws + L.off_win_pfirst);
     s.win_plast = reinterpret_cast<const int32_t *>(ws + L.off_win_plast);
-    s.win_start = d_ws; s.win_end = d_we; s.fixed_start = fixed_s; s.fixed_end = fixed_e;
     s.slow_list = reinterpret_cast<int32_t *>(ws + L.off_slow);
     s.hdr = reinterpret_cast<WsHeader *>(ws);
-    s.V = (int32_t)V; s.T = T; s.Tp = L.Tp; s.W = W;
-    s.bonus = bonus; s.max_mm = max_mm; s.penalty = penalty;
-    s.score = d_score; s.nsnp = d_nsnp;
+    s.V = (int32_t)c.V; s.T = c.T; s.Tp = L.Tp;
+    s.w_begin = w_begin; s.w_end = w_end; s.slot = slot;
+    s.force_slow = (c.algo == SSTAR_B200_ALGO_PAIRWISE);
+    s.bonus = c.bonus; s.max_mm = c.max_mm; s.penalty = c.penalty;
+    s.score = c.d_score; s.nsnp = c.d_nsnp;
     s.arena = ws + L.off_arena; s.arena_entries = L.arena_entries;
+    const int32_t T = c.T;
 
-    if (algo != SSTAR_B200_ALGO_PAIRWISE) {
+    if (!s.force_slow) {
         int bd = (T + 31) / 32 * 32;
         if (bd > kScoreMaxThreads) bd = kScoreMaxThreads;
         const int tchunks = (T + bd - 1) / bd;
@@ -209,24 +226,24 @@ int launch_score(cudaStream_t st, const int8_t *d_tgt, const int32_t *d_pos, int
         // ~4 CTAs per SM in flight and keep a group's union range inside the staged position tile.
         const int words_cap = kScoreWordsCap;
         int wg = 8;
-        if (max_win_variants > 0) {
-            const int fit = (words_cap * 32) / max_win_variants;  // disjoint windows (replicates) still fit
+        if (c.max_win_variants > 0) {
+            const int fit = (words_cap * 32) / c.max_win_variants;  // disjoint windows (replicates) still fit
             if (fit < wg) wg = fit < 1 ? 1 : fit;
         }
         while (wg > 1 && (int64_t)((W + wg - 1) / wg) * tchunks < 4 * kNumSM) wg >>= 1;
         const int64_t ngroups = (W + wg - 1) / wg;
         if (ngroups * tchunks > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "too many (window group, column chunk) tiles%s");
-        const int L = kScoreListBytes / (bd * 4);  // list slots per column
+        const int Lslots = kScoreListBytes / (bd * 4);  // list slots per column
         const size_t ring_b = (size_t)kRingSlots * bd * 4, pos_b = (size_t)words_cap * 32 * 4;
-        const size_t smem = (size_t)L * bd * 4 + (ring_b > pos_b ? ring_b : pos_b);
+        const size_t smem = (size_t)Lslots * bd * 4 + (ring_b > pos_b ? ring_b : pos_b);
         static thread_local size_t k2_smem_set = 0;
         if (smem > k2_smem_set) {
             cudaError_t e = cudaFuncSetAttribute(score_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaFuncSetAttribute(score_group): %s", cudaGetErrorString(e));
             k2_smem_set = smem;
         }
-        cudaError_t e = launch(score_group_kernel, (unsigned)(ngroups * tchunks), (unsigned)bd, smem, st, true, s, wg, L,
-                               words_cap);
+        cudaError_t e = launch(score_group_kernel, (unsigned)(ngroups * tchunks), (unsigned)bd, smem, st, true, s, wg,
+                               Lslots, words_cap);
         if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "score_group_kernel launch: %s", cudaGetErrorString(e));
     }
     const size_t psmem = (size_t)kPairWarps * kPairSmemCap * 13;
@@ -264,7 +281,7 @@ int check_common(int device, int64_t V, int32_t R, int32_t T, int32_t W, const v
     return 0;
 }
 
-// pack (optional) + bounds + score, the common body of every scoring entry point
+// pack (optional) + bounds + score, the common body of every device-pointer entry point
 int run_pipeline(int device, cudaStream_t st, bool do_pack, const int8_t *d_ref, const int8_t *d_tgt,
                  const int32_t *d_pos, int64_t V, int32_t R, int32_t T, const int32_t *d_ws,
                  const int32_t *d_we, const int32_t *d_seg, int32_t fixed_s, int32_t fixed_e, int32_t W,
@@ -272,10 +289,11 @@ int run_pipeline(int device, cudaStream_t st, bool do_pack, const int8_t *d_ref,
                  uint8_t *ws, const WsLayout &L, int algo, int32_t max_win_variants) {
     DeviceGuard guard(device);
     if (guard.err != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
-    int rc = launch_prep(st, do_pack, d_ref, d_tgt, V, R, T, d_pos, d_ws, d_we, d_seg, fixed_s, fixed_e, W, ws, L, algo);
+    int rc = launch_prep(st, 0, do_pack ? L.G : 0, d_ref, d_tgt, V, R, T, d_pos, d_ws, d_we, d_seg, fixed_s, fixed_e, W,
+                         ws, L);
     if (rc) return rc;
-    return launch_score(st, d_tgt, d_pos, V, T, d_ws, d_we, fixed_s, fixed_e, W, bonus, max_mm, penalty, d_score,
-                        d_nsnp, ws, L, algo, max_win_variants);
+    const ScoreCall c = {d_tgt, d_pos, V, T, bonus, max_mm, penalty, d_score, d_nsnp, ws, algo, max_win_variants};
+    return launch_score(st, c, L, 0, W, 0);
 }
 
 }  // namespace
@@ -309,8 +327,8 @@ int sstar_b200_pack(int device, void *stream, const int8_t *d_ref_gt, const int8
     if (V > 0 && (!d_ref_gt || !d_tgt_gt)) return fail(SSTAR_B200_EINVAL, "null genotype pointer%s");
     DeviceGuard guard(device);
     if (guard.err != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
-    return launch_prep((cudaStream_t)stream, true, d_ref_gt, d_tgt_gt, V, R, T, nullptr, nullptr, nullptr, nullptr,
-                       0, 0, 0, (uint8_t *)d_workspace, L, algo);
+    return launch_prep((cudaStream_t)stream, 0, L.G, d_ref_gt, d_tgt_gt, V, R, T, nullptr, nullptr, nullptr, nullptr,
+                       0, 0, 0, (uint8_t *)d_workspace, L);
 }
 
 int sstar_b200_score_packed(int device, void *stream, const int8_t *d_tgt_gt, const int32_t *d_pos,
@@ -403,6 +421,57 @@ extern "C" size_t sstar_b200_host_scratch_bytes(int64_t V, int32_t R, int32_t T,
     return make_host_scratch(V, R, T, W, max_win_variants < 0 ? 0 : max_win_variants).total;
 }
 
+namespace {
+
+// Per (host thread, device): one copy stream and a ring of events for the host pipeline.  Created
+// on first use and kept for the life of the thread (not caller-visible memory).
+constexpr int kMaxChunks = 16;
+constexpr int kMaxDevices = 64;
+struct PipeCtx {
+    bool ready = false;
+    cudaStream_t copy = nullptr;
+    cudaEvent_t entry = nullptr, done = nullptr;
+    cudaEvent_t chunk[kMaxChunks] = {};
+};
+thread_local PipeCtx g_pipe[kMaxDevices];
+
+int pipe_ctx(int device, PipeCtx **out) {
+    if (device < 0 || device >= kMaxDevices) return fail(SSTAR_B200_EINVAL, "device index out of range%s");
+    PipeCtx &c = g_pipe[device];
+    if (!c.ready) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&c.entry, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+        for (int i = 0; i < kMaxChunks; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c.chunk[i], cudaEventDisableTiming));
+        c.ready = true;
+    }
+    *out = &c;
+    return 0;
+}
+
+bool mapped_pointer(const void *h, void **dptr) {
+    if (!h) { *dptr = nullptr; return true; }  // absent because V == 0 or W == 0
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+    *dptr = at.devicePointer;
+    return true;
+}
+
+}  // namespace
+
+// The end-to-end call.  PCIe is the bound (the genotype matrices are 100x the kernels' HBM time),
+// so the job is to keep both directions of the link busy and hide everything else under it:
+//   * the two genotype matrices go host->device in row chunks on an internal copy stream
+//     (copy engine: full PCIe read rate even for small transfers);
+//   * while chunk k+1 is in flight the caller's stream packs chunk k and scores every window whose
+//     variants are now all packed (windows sorted by end), so only the last chunk's kernels are
+//     exposed;
+//   * the score kernels store both result tables straight into the mapped host buffers (posted
+//     PCIe writes that overlap the inbound copies -- the link is full duplex -- and no D2H copy
+//     latency at the end).  pos / windows are small and latency-critical (the bounds search
+//     chases them), so they are copied to the device first.
+// Pageable buffers or SSTAR_B200_FLAG_STAGED_COPIES take plain H2D / D2H copies on `stream`.
 extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int8_t *h_ref_gt,
                                              const int8_t *h_tgt_gt, const int32_t *h_pos, int64_t V,
                                              int32_t R, int32_t T, const int32_t *h_win_start,
@@ -424,30 +493,115 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
     if (V > 0 && (!h_pos || !h_tgt_gt || !h_ref_gt)) return fail(SSTAR_B200_EINVAL, "null input pointer%s");
     uint8_t *d = (uint8_t *)d_scratch;
     cudaStream_t st = (cudaStream_t)stream;
-    {
-        DeviceGuard guard(device);
-        if (guard.err != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    WsLayout L; int algo;
+    rc = check_common(device, V, R, T, W, d + h.off_work, scratch_bytes - h.off_work, opts, &L, &algo);
+    if (rc) return rc;
+    uint8_t *ws = d + h.off_work;
+    int8_t *d_ref = (int8_t *)(d + h.off_ref), *d_tgt = (int8_t *)(d + h.off_tgt);
+    int32_t *d_pos = (int32_t *)(d + h.off_pos);
+
+    // the pipelined path needs page-locked inputs (truly asynchronous copies next to the caller's
+    // stream) and mapped output tables (stored in place by the kernels)
+    void *m_score = nullptr, *m_nsnp = nullptr, *m_any = nullptr;
+    bool mapped = !(opts && (opts->flags & SSTAR_B200_FLAG_STAGED_COPIES));
+    mapped = mapped && mapped_pointer(h_pos, &m_any) && mapped_pointer(h_win_start, &m_any) &&
+             mapped_pointer(h_win_end, &m_any) && mapped_pointer(h_score, &m_score) && mapped_pointer(h_nsnp, &m_nsnp) &&
+             mapped_pointer(h_ref_gt, &m_any) && mapped_pointer(h_tgt_gt, &m_any);
+
+    if (!mapped) {  // staged: copy in, run, copy out, all on the caller's stream
         if (V > 0) {
-            CUDA_TRY(cudaMemcpyAsync(d + h.off_pos, h_pos, (size_t)V * 4, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(d + h.off_ref, h_ref_gt, (size_t)V * R, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(d + h.off_tgt, h_tgt_gt, (size_t)V * T, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(d_pos, h_pos, (size_t)V * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(d_ref, h_ref_gt, (size_t)V * R, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(d_tgt, h_tgt_gt, (size_t)V * T, cudaMemcpyHostToDevice, st));
         }
         if (W > 0) {
             CUDA_TRY(cudaMemcpyAsync(d + h.off_ws, h_win_start, (size_t)W * 4, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(d + h.off_we, h_win_end, (size_t)W * 4, cudaMemcpyHostToDevice, st));
         }
+        rc = run_pipeline(device, st, true, d_ref, d_tgt, d_pos, V, R, T, (const int32_t *)(d + h.off_ws),
+                          (const int32_t *)(d + h.off_we), nullptr, 0, 0, W, match_bonus, max_mismatch,
+                          mismatch_penalty, (int64_t *)(d + h.off_score), (int32_t *)(d + h.off_nsnp), ws, L, algo, hint);
+        if (rc) return rc;
+        if (W > 0) {
+            CUDA_TRY(cudaMemcpyAsync(h_score, d + h.off_score, (size_t)W * T * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(h_nsnp, d + h.off_nsnp, (size_t)W * T * 4, cudaMemcpyDeviceToHost, st));
+        }
+        return 0;
     }
-    rc = sstar_b200_score_windows_ex(device, stream, (const int8_t *)(d + h.off_ref),
-                                     (const int8_t *)(d + h.off_tgt), (const int32_t *)(d + h.off_pos), V,
-                                     R, T, (const int32_t *)(d + h.off_ws), (const int32_t *)(d + h.off_we),
-                                     W, match_bonus, max_mismatch, mismatch_penalty,
-                                     (int64_t *)(d + h.off_score), (int32_t *)(d + h.off_nsnp),
-                                     d + h.off_work, scratch_bytes - h.off_work, opts);
+
+    // ---- pipelined path on mapped host buffers
+    PipeCtx *pc;
+    rc = pipe_ctx(device, &pc);
     if (rc) return rc;
+    const int32_t flags = opts ? opts->flags : 0;
+    // small result tables are stored in place by the kernels (no D2H copy latency at the end);
+    // large ones (>= 8 MB) go through per-chunk D2H copies, which the copy engine moves faster
+    // than SM stores to host memory (measured on the C4 shard: 5.66 vs 6.08 ms)
+    const bool copy_out = (flags & SSTAR_B200_FLAG_COPY_OUTPUTS) != 0 || (int64_t)W * T * 12 >= ((int64_t)8 << 20);
+    // chunk the variant rows: >= 8 MB of genotypes per chunk (below that the per-chunk launches and
+    // event hops cost more than the overlap wins: measured on C2, 4.9 MB), whole 256-row blocks
+    // (any pack tile size divides 256 rows), at most kMaxChunks
+    const int64_t row_bytes = (int64_t)R + T;
+    int nchunks = (int)((V * row_bytes) / ((int64_t)8 << 20));
+    if (nchunks > kMaxChunks) nchunks = kMaxChunks;
+    if (nchunks < 1 || (flags & SSTAR_B200_FLAG_SINGLE_CHUNK)) nchunks = 1;
+    int64_t rows_per = ((V + nchunks - 1) / nchunks + 255) / 256 * 256;
+    if (rows_per < 256) rows_per = 256;
+    nchunks = V > 0 ? (int)((V + rows_per - 1) / rows_per) : 1;
+    // windows can be scored chunk by chunk only if they are sorted by end
+    bool sorted = true;
+    for (int32_t w = 1; w < W && sorted; ++w) sorted = h_win_end[w] >= h_win_end[w - 1];
+
+    // the copy stream starts after whatever the caller already queued (it reuses the scratch)
+    CUDA_TRY(cudaEventRecord(pc->entry, st));
+    CUDA_TRY(cudaStreamWaitEvent(pc->copy, pc->entry, 0));
+    if (V > 0) CUDA_TRY(cudaMemcpyAsync(d_pos, h_pos, (size_t)V * 4, cudaMemcpyHostToDevice, st));
     if (W > 0) {
-        DeviceGuard guard(device);
-        CUDA_TRY(cudaMemcpyAsync(h_score, d + h.off_score, (size_t)W * T * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(h_nsnp, d + h.off_nsnp, (size_t)W * T * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(d + h.off_ws, h_win_start, (size_t)W * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d + h.off_we, h_win_end, (size_t)W * 4, cudaMemcpyHostToDevice, st));
+    }
+    // bounds first: they only need pos and the windows
+    rc = launch_prep(st, 0, 0, nullptr, nullptr, V, R, T, d_pos, (const int32_t *)(d + h.off_ws),
+                     (const int32_t *)(d + h.off_we), nullptr, 0, 0, W, ws, L);
+    if (rc) return rc;
+    int64_t *o_score = copy_out ? (int64_t *)(d + h.off_score) : (int64_t *)m_score;
+    int32_t *o_nsnp = copy_out ? (int32_t *)(d + h.off_nsnp) : (int32_t *)m_nsnp;
+    const ScoreCall c = {d_tgt, d_pos, V, T, match_bonus, max_mismatch, mismatch_penalty, o_score, o_nsnp, ws, algo, hint};
+    int32_t w_done = 0;
+    for (int k = 0; k < nchunks; ++k) {
+        const int64_t r0 = (int64_t)k * rows_per, r1 = (r0 + rows_per < V) ? r0 + rows_per : V;
+        if (r1 > r0) {
+            CUDA_TRY(cudaMemcpyAsync(d_ref + r0 * R, h_ref_gt + r0 * R, (size_t)(r1 - r0) * R, cudaMemcpyHostToDevice, pc->copy));
+            CUDA_TRY(cudaMemcpyAsync(d_tgt + r0 * T, h_tgt_gt + r0 * T, (size_t)(r1 - r0) * T, cudaMemcpyHostToDevice, pc->copy));
+            CUDA_TRY(cudaEventRecord(pc->chunk[k], pc->copy));
+            CUDA_TRY(cudaStreamWaitEvent(st, pc->chunk[k], 0));
+            rc = launch_prep(st, r0 / 32, (r1 + 31) / 32, d_ref, d_tgt, V, R, T, d_pos, nullptr, nullptr, nullptr, 0, 0, 0,
+                             ws, L);
+            if (rc) return rc;
+        }
+        // windows whose last variant lies in the rows packed so far: end < pos[r1] (all, at the end)
+        int32_t w_ready = W;
+        if (k + 1 < nchunks) {
+            if (!sorted) continue;
+            const int64_t limit = h_pos[r1];
+            int32_t lo = w_done, hi = W;
+            while (lo < hi) {
+                const int32_t mid = lo + (hi - lo) / 2;
+                if ((int64_t)h_win_end[mid] < limit) lo = mid + 1; else hi = mid;
+            }
+            w_ready = lo;
+        }
+        rc = launch_score(st, c, L, w_done, w_ready, k);
+        if (rc) return rc;
+        if (copy_out && w_ready > w_done) {
+            CUDA_TRY(cudaMemcpyAsync(h_score + (size_t)w_done * T, o_score + (size_t)w_done * T,
+                                     (size_t)(w_ready - w_done) * T * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(h_nsnp + (size_t)w_done * T, o_nsnp + (size_t)w_done * T,
+                                     (size_t)(w_ready - w_done) * T * 4, cudaMemcpyDeviceToHost, st));
+        }
+        w_done = w_ready;
     }
     return 0;
 }

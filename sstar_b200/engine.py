@@ -222,9 +222,10 @@ class ScoreEngine:
 
     def score_pinned(self, ref_p, tgt_p, pos_p, ws_p, we_p, score_p, nsnp_p, match_bonus=5000,
                      max_mismatch=5, mismatch_penalty=-10000, algo="auto", max_win_variants=0,
-                     stream=None, sync=True):
-        """End-to-end call on HOST tensors (page-locked torch CPU tensors): one C-ABI call enqueues
-        H2D copies, the kernels and the D2H copies of both result tables.
+                     stream=None, sync=True, staged=False, flags=0):
+        """End-to-end call on HOST tensors: one C-ABI call.  With page-locked (pinned) tensors the
+        kernels read the inputs and write both result tables in place over PCIe (zero-copy);
+        ``staged=True`` (or pageable tensors) goes through H2D / D2H copies instead.
 
         ref_p int8 [V,R], tgt_p int8 [V,T], pos_p int32 [V], ws_p/we_p int32 [W],
         score_p int64 [W,T] and nsnp_p int32 [W,T] (outputs, written when the stream has synced).
@@ -236,7 +237,8 @@ class ScoreEngine:
         if need == 0:
             raise SstarB200Error("invalid shapes for scratch sizing")
         scratch = self._dbuf("host_scratch", need, self.torch.uint8)
-        opts = _cabi.Options(algo=_cabi.ALGOS[algo], max_win_variants=int(max_win_variants))
+        opts = _cabi.Options(algo=_cabi.ALGOS[algo], max_win_variants=int(max_win_variants),
+                             flags=(_cabi.FLAG_STAGED_COPIES if staged else 0) | int(flags))
         s = stream if stream is not None else self.torch.cuda.current_stream(self.tdev)
         rc = self.lib.sstar_b200_score_windows_host(
             self.device, ctypes.c_void_p(s.cuda_stream), ref_p.data_ptr(), tgt_p.data_ptr(),

@@ -190,3 +190,25 @@ def test_window_bounds_every_range_length(eng):
     so, no = c_oracle.score_windows(ref, tgt, pos, ws, we)
     s, n = eng.score_host(ref, tgt, pos, ws, we)
     assert np.array_equal(n, no) and np.array_equal(s, so)
+
+
+def test_host_entry_zero_copy_and_staged_agree(eng):
+    # the host entry point on mapped (pinned) buffers streams them over PCIe from inside the
+    # kernels; forced staging and pageable buffers take the copy path: same tables either way
+    import torch
+    from sstar_b200.synth import regular_windows, synth_chromosome
+    ref, tgt, pos = synth_chromosome(700_000, 12, 40, False, seed=31)
+    ws, we = regular_windows(pos, 50_000, 10_000)
+    so, no = c_oracle.score_windows(ref, tgt, pos, ws, we)
+    W, T = so.shape
+    hint = int(max(np.searchsorted(pos, we, "right") - np.searchsorted(pos, ws, "left")))
+    for pinned, staged in [(True, False), (True, True), (False, False)]:
+        mk = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()) if pinned else \
+             (lambda a: torch.from_numpy(np.ascontiguousarray(a)))
+        outs = torch.zeros((W, T), dtype=torch.int64), torch.zeros((W, T), dtype=torch.int32)
+        if pinned:
+            outs = tuple(o.pin_memory() for o in outs)
+        eng.score_pinned(mk(ref), mk(tgt), mk(pos), mk(ws), mk(we), outs[0], outs[1], 5000, 5, -10000,
+                         max_win_variants=hint, staged=staged)
+        assert np.array_equal(outs[0].numpy(), so), (pinned, staged)
+        assert np.array_equal(outs[1].numpy(), no), (pinned, staged)
