@@ -212,6 +212,117 @@ def run_reference(args, world, rank):
     print(json.dumps(line), flush=True)
 
 
+class DeviceCase:
+    """One workload resident on one GPU: the captured pass and the timing helpers."""
+
+    def __init__(self, torch, eng, dev, wk, use_graph=True):
+        self.torch, self.eng, self.dev, self.wk = torch, eng, dev, wk
+        self.st = st = workload_stats(wk)
+        self.hint = st["max_window_variants"]
+        W, T = st["W"], st["T"]
+        self.pin = {k: torch.from_numpy(np.ascontiguousarray(wk[k])).pin_memory()
+                    for k in ("ref", "tgt", "pos", "ws", "we")}
+        self.d = {k: v.to(dev) for k, v in self.pin.items()}
+        self.score_d = torch.empty((W, T), dtype=torch.int64, device=dev)
+        self.nsnp_d = torch.empty((W, T), dtype=torch.int32, device=dev)
+        self.score_p = torch.empty((W, T), dtype=torch.int64).pin_memory()
+        self.nsnp_p = torch.empty((W, T), dtype=torch.int32).pin_memory()
+        # the whole pass (pack -> bounds -> DP) captured once: ONE host call per step
+        self.plan = None
+        if use_graph:
+            d = self.d
+            self.plan = eng.plan_device(d["ref"], d["tgt"], d["pos"], d["ws"], d["we"], *PARAMS,
+                                        max_win_variants=self.hint, out=(self.score_d, self.nsnp_d))
+
+    def step_device(self):
+        if self.plan is not None:
+            self.plan.run()
+            return self.plan.launches
+        d = self.d
+        self.eng.score_device(d["ref"], d["tgt"], d["pos"], d["ws"], d["we"], *PARAMS,
+                              max_win_variants=self.hint, out=(self.score_d, self.nsnp_d))
+        return self.eng.launches
+
+    def step_pack(self):
+        self.eng.pack_device(self.d["ref"], self.d["tgt"], W=self.st["W"], max_win_variants=self.hint)
+
+    def step_score(self):
+        d = self.d
+        self.eng.score_packed_device(self.st["R"], d["tgt"], d["pos"], d["ws"], d["we"], *PARAMS,
+                                     max_win_variants=self.hint, out=(self.score_d, self.nsnp_d))
+
+    def step_e2e(self, staged=False):
+        p = self.pin
+        self.eng.score_pinned(p["ref"], p["tgt"], p["pos"], p["ws"], p["we"], self.score_p, self.nsnp_p,
+                              *PARAMS, max_win_variants=self.hint, sync=True, staged=staged)
+
+    def timed(self, fn, steps, flush, barrier):
+        """K steps, L2 flushed before each, CUDA events around each step on the launching stream."""
+        torch = self.torch
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(steps)]
+        barrier()
+        for i in range(steps):
+            flush.fill_(i & 1)
+            evs[i][0].record()
+            fn()
+            evs[i][1].record()
+        barrier()
+        return sum(e[0].elapsed_time(e[1]) for e in evs)
+
+    def wall(self, fn, steps, flush):
+        torch = self.torch
+        tot = 0.0
+        for i in range(steps):
+            flush.fill_(i & 1)
+            torch.cuda.synchronize(self.dev)
+            t0 = time.perf_counter()
+            fn()
+            tot += time.perf_counter() - t0
+        return tot
+
+    def check_parity(self, large):
+        """GPU vs the C oracle, bit-exact (all windows, or 48 spread ones for the large shapes)."""
+        from oracle import c_oracle
+        wk, W = self.wk, self.st["W"]
+        sel = np.arange(W) if not large else np.unique(np.linspace(0, W - 1, 48).astype(int))
+        so, no = c_oracle.score_windows(wk["ref"], wk["tgt"], wk["pos"], wk["ws"][sel], wk["we"][sel], *PARAMS)
+        ok = bool(np.array_equal(self.score_p.numpy()[sel], so) and np.array_equal(self.nsnp_p.numpy()[sel], no)
+                  and np.array_equal(self.score_d.cpu().numpy()[sel], so)
+                  and np.array_equal(self.nsnp_d.cpu().numpy()[sel], no))
+        if not ok:
+            raise SystemExit("bench: GPU result differs from the oracle -- refusing to report a number")
+        return {"checked_units": int(so.size), "bit_exact_vs_oracle": ok}
+
+
+def roofline_block(name, st, k, tot_ms, pack_ms, score_ms, launches):
+    """Pass-level and per-kernel HBM roofline (SURVEY.md section 8d bytes; measured peak)."""
+    ab = algorithmic_bytes(st)
+    peak, peak_src = measured_peak()
+
+    def kern(kname, ms, nbytes, note=None):
+        out = {"kernel": kname, "ms": ms / k, "algorithmic_bytes": nbytes,
+               "achieved": nbytes / (ms / k * 1e-3) / 1e9, "frac": nbytes / (ms / k * 1e-3) / 1e9 / peak,
+               "traffic": recorded_traffic(name, kname)}
+        if note:
+            out["note"] = note
+        return out
+
+    pipe = ab["pipeline"] / (tot_ms / k * 1e-3) / 1e9
+    return {
+        "bound": "hbm",
+        "kernel": "one pass = prep_kernel (pack + window bounds) -> score_group_kernel -> score_pairwise_kernel",
+        "achieved": pipe, "peak": peak, "unit": "GB/s", "frac": pipe / peak,
+        "traffic": sum(filter(None, (recorded_traffic(name, x) for x in ("prep_kernel", "score_group_kernel")))) or None,
+        "peak_source": peak_src, "algorithmic_bytes": ab["pipeline"],
+        "bytes_per_unit": ab["pipeline"] / st["units"], "pass_ms": tot_ms / k, "launches_per_pass": launches,
+        "kernels": [
+            kern("prep_kernel", pack_ms, ab["pack"], "HBM bound: every int8 genotype read once; timed alone"),
+            kern("score_group_kernel", score_ms, ab["score"],
+                 "integer-ALU / latency bound, not HBM bound (its bytes are pos + the two result tables); "
+                 "timed alone together with the chained pairwise launch")],
+    }
+
+
 def run_ours(args, world, rank, local):
     import torch
     import __graft_entry__ as entry
@@ -226,50 +337,15 @@ def run_ours(args, world, rank, local):
     else:
         dist = None
     from sstar_b200.engine import get_engine
-    from sstar_b200 import NAN_SENTINEL
 
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     eng = get_engine(local)
-    wk = make_workload(args.workload, rank)
-    st = workload_stats(wk)
-    V, R, T, W = st["V"], st["R"], st["T"], st["W"]
-    hint = st["max_window_variants"]
-
-    # host (pinned) and device copies of the inputs
-    pin = {k: torch.from_numpy(np.ascontiguousarray(wk[k])).pin_memory() for k in ("ref", "tgt", "pos", "ws", "we")}
-    d = {k: v.to(dev) for k, v in pin.items()}
-    score_d = torch.empty((W, T), dtype=torch.int64, device=dev)
-    nsnp_d = torch.empty((W, T), dtype=torch.int32, device=dev)
-    score_p = torch.empty((W, T), dtype=torch.int64).pin_memory()
-    nsnp_p = torch.empty((W, T), dtype=torch.int32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    # the whole pass (pack -> bounds -> DP) captured once: ONE host call per step
-    plan = None
-    if not args.no_graph:
-        plan = eng.plan_device(d["ref"], d["tgt"], d["pos"], d["ws"], d["we"], *PARAMS, max_win_variants=hint,
-                               out=(score_d, nsnp_d))
-        launches_per_step = plan.launches
-
-    def step_device():
-        if plan is not None:
-            plan.run()
-            return plan.launches
-        eng.score_device(d["ref"], d["tgt"], d["pos"], d["ws"], d["we"], *PARAMS, max_win_variants=hint,
-                         out=(score_d, nsnp_d))
-        return eng.launches
-
-    def step_pack():
-        eng.pack_device(d["ref"], d["tgt"], W=W, max_win_variants=hint)
-
-    def step_score():
-        eng.score_packed_device(R, d["tgt"], d["pos"], d["ws"], d["we"], *PARAMS, max_win_variants=hint,
-                                out=(score_d, nsnp_d))
-
-    def step_e2e(staged=False):
-        eng.score_pinned(pin["ref"], pin["tgt"], pin["pos"], pin["ws"], pin["we"], score_p, nsnp_p,
-                         *PARAMS, max_win_variants=hint, sync=True, staged=staged)
+    case = DeviceCase(torch, eng, dev, make_workload(args.workload, rank), use_graph=not args.no_graph)
+    wk, st = case.wk, case.st
+    V, R, T, W = st["V"], st["R"], st["T"], st["W"]
+    k = args.steps
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -277,79 +353,54 @@ def run_ours(args, world, rank, local):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    if args.only_device:  # profiling aid: nothing but the device-resident pass is launched
+        for i in range(max(args.warmup, 3) + k):
+            flush.fill_(i & 1)
+            case.step_device()
+        torch.cuda.synchronize(dev)
+        print(json.dumps({"only_device": True, "workload": wk["name"], "passes": max(args.warmup, 3) + k}))
+        return
+
     for _ in range(max(args.warmup, 3)):
         flush.fill_(1)
-        launches_per_step = step_device()
-        step_pack()
-        step_score()
-        step_e2e()
-        step_e2e(staged=True)
+        launches_per_step = case.step_device()
+        case.step_pack()
+        case.step_score()
+        case.step_e2e()
+        case.step_e2e(staged=True)
 
     sampler = ClockSampler(local)
     sampler.start()
-
-    def timed(fn):
-        """K steps, L2 flushed before each, CUDA events around each step on the launching stream."""
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
-        barrier()
-        for i in range(args.steps):
-            flush.fill_(i & 1)
-            evs[i][0].record()
-            fn()
-            evs[i][1].record()
-        barrier()
-        return sum(e[0].elapsed_time(e[1]) for e in evs)
-
     # ---- region A: device-resident inputs, the whole pass per step
     sampler.mark()
-    tot_ms = timed(step_device)
+    tot_ms = case.timed(case.step_device, k, flush, barrier)
     sampler.mark()
     # ---- per-kernel split for the roofline: the pack launch alone, the DP launches alone
-    pack_ms = timed(step_pack)
-    score_ms = timed(step_score)
-
+    pack_ms = case.timed(case.step_pack, k, flush, barrier)
+    score_ms = case.timed(case.step_score, k, flush, barrier)
     # ---- region B: end to end from pinned host buffers, wall clock per step (includes the sync)
     barrier()
-    e2e_s = 0.0
-    for i in range(args.steps):
-        flush.fill_(i & 1)
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        step_e2e()
-        e2e_s += time.perf_counter() - t0
+    staged_s = case.wall(lambda: case.step_e2e(staged=True), k, flush)  # plain H2D / D2H copies, for comparison
     barrier()
     sampler.mark()
-    staged_s = 0.0  # the same call forced through H2D / D2H staging copies, for comparison
-    for i in range(args.steps):
-        flush.fill_(i & 1)
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        step_e2e(staged=True)
-        staged_s += time.perf_counter() - t0
+    e2e_s = case.wall(case.step_e2e, k, flush)
     barrier()
+    sampler.mark()
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
-    times = torch.tensor([tot_ms, e2e_s * 1e3, pack_ms, score_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([tot_ms, e2e_s * 1e3, pack_ms, score_ms, staged_s * 1e3], dtype=torch.float64, device=dev)
     units_t = torch.tensor([float(st["units"])], dtype=torch.float64, device=dev)
     if use_dist:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(units_t, op=dist.ReduceOp.SUM)
-    tot_ms, e2e_ms, pack_ms, score_ms = (float(x) for x in times.tolist())
+    tot_ms, e2e_ms, pack_ms, score_ms, staged_ms = (float(x) for x in times.tolist())
     total_units = float(units_t.item())
 
-    # ---- parity in the same run (outside the timed regions): GPU vs C oracle, bit-exact
-    parity = None
-    cpu = None
+    parity = cpu = at_scale = None
     if rank == 0:
-        from oracle import c_oracle
-        sel = np.arange(W) if wk["name"] not in LARGE else np.unique(np.linspace(0, W - 1, 48).astype(int))
-        so, no = c_oracle.score_windows(wk["ref"], wk["tgt"], wk["pos"], wk["ws"][sel], wk["we"][sel], *PARAMS)
-        ok = bool(np.array_equal(score_p.numpy()[sel], so) and np.array_equal(nsnp_p.numpy()[sel], no)
-                  and np.array_equal(score_d.cpu().numpy()[sel], so))
-        parity = {"checked_units": int(so.size), "bit_exact_vs_oracle": ok}
-        if not ok:
-            raise SystemExit("bench: GPU result differs from the oracle -- refusing to report a number")
+        # ---- parity in the same run (outside the timed regions): GPU vs C oracle, bit-exact
+        parity = case.check_parity(wk["name"] in LARGE)
         if world == 1 and not args.no_cpu_baseline and wk["name"] not in LARGE:
             from oracle.cpu_baseline import CpuBaseline
             cores = os.cpu_count() or 1
@@ -358,64 +409,66 @@ def run_ours(args, world, rank, local):
             n_win = int(min(W, max(cores, 20.0 / max(per_win, 1e-6))))
             sample = np.linspace(0, W - 1, num=n_win).astype(int)
             base.run(sample[: max(cores, n_win // 8)])
-            dt, res = base.run(sample)
+            passes = int(min(10, max(1, round(12.0 / max(per_win * n_win, 1e-6)))))  # ~12 core-seconds of work
+            dts = []
+            for _ in range(passes):
+                dt, res = base.run(sample)
+                dts.append(dt)
             base.close()
-            for w, (s, n) in res.items():  # the CPU-scored units must equal the GPU's
-                assert np.array_equal(s, score_p.numpy()[w]) and np.array_equal(n, nsnp_p.numpy()[w]), \
+            for w, (s_, n_) in res.items():  # the CPU-scored units must equal the GPU's
+                assert np.array_equal(s_, case.score_p.numpy()[w]) and np.array_equal(n_, case.nsnp_p.numpy()[w]), \
                     "CPU port != GPU"
+            dt = statistics.mean(dts)
             cpu = {"value": n_win * T / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{n_win} of {W} windows x {T} columns of the {wk['name']} chromosome, one pass "
-                             f"({dt:.2f} s wall); numpy port of the reference recipe, pool pre-forked and warm, "
-                             "no mp_manager 5 s tail",
+                   "sample": f"{n_win} of {W} windows x {T} columns of the {wk['name']} chromosome, mean of {passes} "
+                             f"passes ({dt:.2f} s wall each); numpy port of the reference recipe, pool pre-forked and "
+                             "warm, no mp_manager 5 s tail",
                    "in_process_us_per_unit": 1e6 * per_win / T}
+        if world == 1 and args.at_scale != "none" and args.at_scale != wk["name"]:
+            # the same kernels on a shape that fills the machine (C2 is a 5.6 MB problem: launch bound)
+            big = DeviceCase(torch, eng, dev, make_workload(args.at_scale, 0), use_graph=not args.no_graph)
+            kb = 20
+            for _ in range(3):
+                flush.fill_(1)
+                nl = big.step_device(); big.step_pack(); big.step_score(); big.step_e2e()
+            b_tot = big.timed(big.step_device, kb, flush, barrier)
+            b_pack = big.timed(big.step_pack, kb, flush, barrier)
+            b_score = big.timed(big.step_score, kb, flush, barrier)
+            b_e2e = big.wall(big.step_e2e, 5, flush)
+            at_scale = {"workload": big.wk["desc"], **{x: big.st[x] for x in ("V", "R", "T", "W", "units")},
+                        "value": big.st["units"] / (b_tot / kb * 1e-3), "unit": UNIT, "ms_per_step": b_tot / kb,
+                        "e2e": {"value": big.st["units"] / (b_e2e / 5), "unit": UNIT, "ms_per_step": 1e3 * b_e2e / 5},
+                        "roofline": roofline_block(big.wk["name"], big.st, kb, b_tot, b_pack, b_score, nl),
+                        "parity": big.check_parity(True)}
 
     if rank == 0:
-        ab = algorithmic_bytes(st)
-        peak, peak_src = measured_peak()
-        k = args.steps
-        dom = "prep_kernel" if pack_ms >= score_ms else "score_group_kernel"
-        dom_ms = (pack_ms if dom == "prep_kernel" else score_ms) / k
-        dom_bytes = ab["pack"] if dom == "prep_kernel" else ab["score"]
-        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-        pipe_achieved = ab["pipeline"] / (tot_ms / k * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": total_units / (tot_ms / k * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": k, "warmup": max(args.warmup, 3), "ms_per_step": tot_ms / k, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int8 genotypes -> int64 scores",
+            "scaling": "weak", "vs_baseline": None, "dtype": "int8 genotypes -> int32/int64 max-plus DP -> int64 scores",
             "data": "synthetic",
             "config": {"workload": wk["desc"], **st, "seed": wk["seed"], "params": list(PARAMS),
                        "per_rank": "every rank scores its own chromosome of this shape",
                        "l2": "flushed between timed iterations (256 MiB device write)",
                        "timing": "CUDA events on the launching stream around each step, summed over K steps",
-                       "launch": "direct launches" if plan is None else "CUDA graph replay of the pass (ScoreEngine.plan_device)"},
+                       "launch": "direct launches" if args.no_graph
+                                 else "CUDA graph replay of the pass (ScoreEngine.plan_device)"},
             "e2e": {"value": total_units / (e2e_ms / k * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(V * (R + T) + 4 * V + 8 * W),
                     "d2h_bytes_per_step": int(12 * W * T), "ms_per_step": e2e_ms / k,
-                    "api": "ScoreEngine.score_pinned -> sstar_b200_score_windows_host (pinned host buffers read "
-                           "and written in place over PCIe by the kernels; wall clock incl. stream sync)",
-                    "staged_copies_ms_per_step": 1e3 * staged_s / k},
+                    "api": "ScoreEngine.score_pinned -> sstar_b200_score_windows_host: pinned host buffers, chunked "
+                           "H2D on a copy stream overlapped with pack + scoring, result tables stored in place "
+                           "into host memory; wall clock incl. the stream sync",
+                    "staged_copies_ms_per_step": staged_ms / k},
             "gpu_launches": int(launches_per_step * k),
             "kernels_per_step": int(launches_per_step),
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": recorded_traffic(wk["name"], dom),
-                         "peak_source": peak_src, "algorithmic_bytes": dom_bytes, "kernel_ms": dom_ms,
-                         "pack_ms": pack_ms / k, "score_ms": score_ms / k,
-                         "kernels": [
-                             {"kernel": "prep_kernel", "ms": pack_ms / k, "algorithmic_bytes": ab["pack"],
-                              "achieved": ab["pack"] / (pack_ms / k * 1e-3) / 1e9,
-                              "frac": ab["pack"] / (pack_ms / k * 1e-3) / 1e9 / peak,
-                              "traffic": recorded_traffic(wk["name"], "prep_kernel")},
-                             {"kernel": "score_group_kernel", "ms": score_ms / k, "algorithmic_bytes": ab["score"],
-                              "achieved": ab["score"] / (score_ms / k * 1e-3) / 1e9,
-                              "frac": ab["score"] / (score_ms / k * 1e-3) / 1e9 / peak,
-                              "traffic": recorded_traffic(wk["name"], "score_group_kernel"),
-                              "note": "integer-ALU / latency bound, not HBM bound; includes the chained (empty) pairwise launch"}],
-                         "pipeline": {"algorithmic_bytes": ab["pipeline"], "achieved": pipe_achieved,
-                                      "frac": pipe_achieved / peak}},
+            "roofline": roofline_block(wk["name"], st, k, tot_ms, pack_ms, score_ms, int(launches_per_step)),
             "cpu_baseline": cpu,
             "clocks": sampler.summary(),
             "parity": parity,
         }
+        if at_scale:
+            line["at_scale"] = at_scale
         print(json.dumps(line), flush=True)
     if use_dist:
         dist.barrier()
@@ -430,6 +483,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--at-scale", default="c3-shard", choices=["none"] + sorted(LARGE),
+                    help="N=1 only: also time the same kernels on a shape that fills the GPU")
+    ap.add_argument("--only-device", action="store_true", help="profiling aid: run only the device-resident passes")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels directly instead of replaying the CUDA graph")
     args = ap.parse_args()
     world, rank, local = dist_setup(args.gpus)
