@@ -150,6 +150,28 @@ int sstar_b200_score_windows_host(int device, void *stream, const int8_t *h_ref_
                                   void *d_scratch, size_t scratch_bytes,
                                   const sstar_b200_options *opts);
 
+/* Result emitter: the feature table as TSV text (no header line), formatted on the device.
+ * replaces: the row dicts of FeatureVectorPreprocessor._fmt_res (sstar/feature_vector_preprocessor.py:167-181)
+ *           printed by pd.DataFrame(rows).to_csv(sep="\t", index=False, na_rep="NA")
+ *           (sstar/preprocess.py:122, sstar/simulate.py:195) -- same bytes.
+ * Row: chrom \t start \t end \t label \t score \t nsnp [\t replicate] \n ; score prints as "51470.0",
+ * SSTAR_B200_NAN as "NA".  Rows are in (window, k) order and show column d_col_order[k] (NULL =
+ * identity; the simulate path sorts rows by sample NAME).  d_labels holds the T labels
+ * concatenated, label t = d_labels[d_label_off[t] .. d_label_off[t+1]).  d_replicate (NULL = no
+ * such column) is per window.  All d_* pointers are device memory.
+ * On return (after the stream syncs) the first 16 bytes of d_workspace hold
+ *   int64 total_bytes; uint32 status  (bit 0: d_out too small, bit 1: |score| >= 1e16, where
+ *   the reference switches to exponent notation -- nothing is written, format on the host). */
+size_t sstar_b200_tsv_max_bytes(int32_t W, int32_t T, int32_t chrom_len, int32_t max_label_len,
+                                int32_t has_replicate);
+size_t sstar_b200_tsv_workspace_bytes(int32_t W, int32_t T);
+int sstar_b200_format_tsv(int device, void *stream, const int64_t *d_score, const int32_t *d_nsnp,
+                          const int32_t *d_win_start, const int32_t *d_win_end, int32_t W, int32_t T,
+                          const char *chrom, const char *d_labels, const int32_t *d_label_off,
+                          int32_t max_label_len, const int32_t *d_replicate,
+                          const int32_t *d_col_order, char *d_out, size_t out_capacity,
+                          void *d_workspace, size_t workspace_bytes);
+
 /* Number of kernels the last sstar_b200_score_* / pack call on this thread enqueued. */
 int sstar_b200_last_launch_count(void);
 

@@ -52,6 +52,10 @@ SIGNATURES = {
     "sstar_b200_pack": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _sz]),
     "sstar_b200_score_packed": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _i32,
                                            _i32, _i32, _i32, _vp, _vp, _vp, _sz, _OPT]),
+    "sstar_b200_tsv_max_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
+    "sstar_b200_tsv_workspace_bytes": (_sz, [_i32, _i32]),
+    "sstar_b200_format_tsv": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _c.c_char_p, _vp, _vp,
+                                         _i32, _vp, _vp, _vp, _sz, _vp, _sz]),
 }
 
 _lib = None

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "prep_kernels.cuh"
 #include "score_kernels.cuh"
+#include "emit_kernels.cuh"
 
 using namespace sstar;
 
@@ -603,5 +604,78 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
         }
         w_done = w_ready;
     }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Result emitter
+// ---------------------------------------------------------------------------------------------
+namespace {
+int emit_row_cap(int32_t chrom_len, int32_t max_label_len, int has_replicate) {
+    // chrom \t start \t end \t label \t score(sign + 17 digits + ".0") \t nsnp [\t replicate] \n
+    return chrom_len + 1 + 11 + 1 + 11 + 1 + max_label_len + 1 + 20 + 1 + 11 + (has_replicate ? 12 : 0) + 1;
+}
+}  // namespace
+
+extern "C" size_t sstar_b200_tsv_max_bytes(int32_t W, int32_t T, int32_t chrom_len, int32_t max_label_len,
+                                           int32_t has_replicate) {
+    if (W < 0 || T < 1 || chrom_len < 0 || max_label_len < 0) return 0;
+    return (size_t)W * (size_t)T * (size_t)emit_row_cap(chrom_len, max_label_len, has_replicate) + 16;
+}
+
+extern "C" size_t sstar_b200_tsv_workspace_bytes(int32_t W, int32_t T) {
+    if (W < 0 || T < 1) return 0;
+    const size_t nb = (size_t)(W > 0 ? W : 1) * (size_t)((T + kEmitThreads - 1) / kEmitThreads);
+    return 256 + align_up(nb * 8, 256);
+}
+
+extern "C" int sstar_b200_format_tsv(int device, void *stream, const int64_t *d_score, const int32_t *d_nsnp,
+                                     const int32_t *d_win_start, const int32_t *d_win_end, int32_t W, int32_t T,
+                                     const char *chrom, const char *d_labels, const int32_t *d_label_off,
+                                     int32_t max_label_len, const int32_t *d_replicate,
+                                     const int32_t *d_col_order, char *d_out, size_t out_capacity,
+                                     void *d_workspace, size_t workspace_bytes) {
+    g_launches = 0;
+    if (W < 0 || T < 1) return fail(SSTAR_B200_EINVAL, "bad table shape%s");
+    if (!chrom) return fail(SSTAR_B200_EINVAL, "chrom is null%s");
+    const size_t clen = strlen(chrom);
+    if (clen >= sizeof(EmitArgs::chrom)) return fail(SSTAR_B200_EINVAL, "chromosome name longer than 63 bytes%s");
+    if (!d_workspace || ((uintptr_t)d_workspace & 255)) return fail(SSTAR_B200_EINVAL, "workspace null or not 256-byte aligned%s");
+    if (workspace_bytes < sstar_b200_tsv_workspace_bytes(W, T)) return fail(SSTAR_B200_EWORKSPACE, "workspace too small%s");
+    if (W > 0 && (!d_score || !d_nsnp || !d_win_start || !d_win_end || !d_labels || !d_label_off || !d_out))
+        return fail(SSTAR_B200_EINVAL, "null table pointer%s");
+    if (max_label_len < 0) return fail(SSTAR_B200_EINVAL, "max_label_len must be >= 0%s");
+    const int row_cap = emit_row_cap((int32_t)clen, max_label_len, d_replicate != nullptr);
+    const size_t smem = (size_t)row_cap * kEmitThreads;
+    if (smem > (size_t)200 << 10) return fail(SSTAR_B200_EINVAL, "sample labels too long for the emitter%s");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *ws = (uint8_t *)d_workspace;
+    EmitArgs a = {};
+    a.score = d_score; a.nsnp = d_nsnp; a.win_start = d_win_start; a.win_end = d_win_end;
+    a.replicate = d_replicate; a.col_order = d_col_order; a.labels = d_labels; a.label_off = d_label_off;
+    a.W = W; a.T = T; a.blocks_per_win = (T + kEmitThreads - 1) / kEmitThreads; a.row_cap = row_cap;
+    a.chrom_len = (int32_t)clen;
+    memcpy(a.chrom, chrom, clen);
+    a.total = reinterpret_cast<int64_t *>(ws);          // header: total bytes, status
+    a.status = reinterpret_cast<uint32_t *>(ws + 8);
+    a.block_base = reinterpret_cast<int64_t *>(ws + 256);
+    a.out = d_out; a.capacity = (int64_t)out_capacity;
+    CUDA_TRY(cudaMemsetAsync(ws, 0, 256, st));
+    const int64_t nb = (int64_t)W * a.blocks_per_win;
+    if (nb > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "table too large for one emitter call%s");
+    if (nb == 0) return 0;
+    static thread_local size_t emit_smem_set = 0;
+    if (smem > emit_smem_set) {
+        CUDA_TRY(cudaFuncSetAttribute(emit_format_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        emit_smem_set = smem;
+    }
+    cudaError_t e = launch(emit_len_kernel, (unsigned)nb, kEmitThreads, 0, st, false, a);
+    if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "emit_len_kernel launch: %s", cudaGetErrorString(e));
+    e = launch(emit_scan_kernel, 1u, 1024u, 0, st, false, a, nb);
+    if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "emit_scan_kernel launch: %s", cudaGetErrorString(e));
+    e = launch(emit_format_kernel, (unsigned)nb, kEmitThreads, smem, st, false, a);
+    if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "emit_format_kernel launch: %s", cudaGetErrorString(e));
     return 0;
 }

@@ -208,6 +208,63 @@ class ScoreEngine:
             launches = self.launches
         return ScorePlan(graph, out[0], out[1], launches, (ref_d, tgt_d, pos_d, ws_d, we_d, self._dev.get("ws")))
 
+    # ------------------------------------------------------------------ result emitter
+    def format_tsv_device(self, score_d, nsnp_d, ws_d, we_d, chrom: str, labels, replicate_d=None,
+                          col_order_d=None, stream=None):
+        """Device tables -> TSV text on the device (no header line).  Returns ``(text_d, total,
+        status)``: a uint8 device tensor whose first ``total`` bytes are the rows; ``status != 0``
+        means the table must be formatted on the host (see include/sstar_b200.h)."""
+        torch = self.torch
+        W, T = score_d.shape
+        enc = [str(x).encode() for x in labels]
+        if len(enc) != T:
+            raise ValueError("one label per column is required")
+        off = np.zeros(T + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(b) for b in enc])
+        max_len = int(max((len(b) for b in enc), default=0))
+        with torch.cuda.device(self.tdev):
+            lab_d = torch.from_numpy(np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8).copy()).to(self.tdev)
+            off_d = torch.from_numpy(off).to(self.tdev)
+            cap = self.lib.sstar_b200_tsv_max_bytes(W, T, len(chrom.encode()), max_len, int(replicate_d is not None))
+            out = self._dbuf("tsv_out", cap, torch.uint8)
+            ws = self._dbuf("tsv_ws", self.lib.sstar_b200_tsv_workspace_bytes(W, T), torch.uint8)
+            s = stream if stream is not None else torch.cuda.current_stream(self.tdev)
+            rc = self.lib.sstar_b200_format_tsv(
+                self.device, ctypes.c_void_p(s.cuda_stream), score_d.data_ptr(), nsnp_d.data_ptr(), ws_d.data_ptr(),
+                we_d.data_ptr(), W, T, chrom.encode(), lab_d.data_ptr(), off_d.data_ptr(), max_len,
+                replicate_d.data_ptr() if replicate_d is not None else None,
+                col_order_d.data_ptr() if col_order_d is not None else None,
+                out.data_ptr(), out.numel(), ws.data_ptr(), ws.numel())
+            _cabi.check(rc)
+            self.launches = self.lib.sstar_b200_last_launch_count()
+            head = ws[:16].cpu().numpy()  # syncs the stream
+        total = int(head[:8].view(np.int64)[0])
+        status = int(head[8:12].view(np.uint32)[0])
+        return out, total, status
+
+    def format_tsv_host(self, score, nsnp, win_start, win_end, chrom, labels, replicate=None, col_order=None):
+        """numpy tables -> TSV text (rows only, a bytes-like view of a pinned buffer) through the
+        device emitter, or ``None`` when the table holds a score the device emitter does not print
+        (|score| >= 1e16)."""
+        torch = self.torch
+        with torch.cuda.device(self.tdev):
+            up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.tdev)
+            W = np.asarray(score).shape[0]
+            if W == 0:
+                return b""
+            text_d, total, status = self.format_tsv_device(
+                up(score, np.int64), up(nsnp, np.int32), up(win_start, np.int32), up(win_end, np.int32), str(chrom),
+                labels, None if replicate is None else up(replicate, np.int32),
+                None if col_order is None else up(col_order, np.int32))
+            if status & 1:
+                raise SstarB200Error("TSV emitter: output buffer too small (internal sizing error)")
+            if status:
+                return None
+            pin = self._pbuf("tsv_pin", total, torch.uint8)[:total]  # page-locked: D2H at PCIe rate
+            pin.copy_(text_d[:total], non_blocking=True)
+            torch.cuda.current_stream(self.tdev).synchronize()
+            return memoryview(pin.numpy())  # valid until the next emitter call on this engine
+
     # ------------------------------------------------------------------ host API
     def _h2d(self, key, arr: np.ndarray, tdtype):
         """numpy -> pinned staging -> device (async on the current stream)."""

@@ -30,5 +30,7 @@ def preprocess(vcf_file: str, chr_name: str, ref_ind_file: str, tgt_ind_file: st
     except Exception as e:
         print(f"sstar_b200: scoring failed ({e})")
         raise SystemExit("Some errors occurred, stopping the program ...")
-    # windows are already in (Chromosome, Start, End) order == the reference's stable sort
-    table.to_tsv(output_file)
+    # windows are already in (Chromosome, Start, End) order == the reference's stable sort;
+    # the rows are printed by the device emitter (same bytes as pandas' to_csv)
+    from .sharding import visible_devices
+    table.to_tsv(output_file, device=visible_devices()[0])

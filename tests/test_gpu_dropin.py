@@ -103,3 +103,42 @@ def test_replicate_batch_matches_per_replicate_oracle(phased):
         assert np.array_equal(table.score[i], so[0]) and np.array_equal(table.nsnp[i], no[0]), i
     rows = table.rows()
     assert rows[0]["Replicate"] == 100 and rows[-1]["Replicate"] == 139 and rows[0]["Sample"].startswith("tsk_5")
+
+
+# ---- result emitter: device-formatted TSV == the Python emitter == pandas
+def _table(W, T, seed, replicate, long_labels=False):
+    from sstar_b200.feature_table import FeatureTable
+    rng = np.random.default_rng(seed)
+    score = rng.integers(-10_000, 600_000, size=(W, T)).astype(np.int64)
+    score[rng.random((W, T)) < 0.25] = np.iinfo(np.int64).min          # NaN
+    score[rng.random((W, T)) < 0.05] = rng.integers(-9, 10, size=1)[0]  # tiny values, zero, negatives
+    if W and T:
+        score[0, 0] = 9_999_999_999_999_998                             # longest score the device emitter prints
+        score[-1, -1] = -9_999_999_999_999_998
+    nsnp = rng.integers(0, 3000, size=(W, T)).astype(np.int32)
+    ws = np.sort(rng.integers(-60_000, 250_000_000, size=W)).astype(np.int64)
+    labels = [f"{'NA' if t % 3 else 'sample_with_a_long_name_'}{t}_{t % 2 + 1}" if long_labels else f"tsk_{t}"
+              for t in range(T)]
+    rep = list(rng.integers(0, 100_000, size=W)) if replicate else None
+    return FeatureTable("chr21" if long_labels else 1, ws, ws + 49_999, labels, score, nsnp, replicate=rep)
+
+
+@pytest.mark.parametrize("W,T,replicate,long_labels", [(1, 1, False, False), (37, 50, False, True),
+                                                       (5, 700, True, False), (300, 257, True, True)])
+def test_device_emitter_matches_python_and_pandas(tmp_path, W, T, replicate, long_labels):
+    table = _table(W, T, W * 1000 + T, replicate, long_labels)
+    order = None if not replicate else list(np.argsort(np.array(table.labels, dtype=object), kind="stable"))
+    a, b = tmp_path / "dev.tsv", tmp_path / "py.tsv"
+    table.to_tsv(a, device=0, col_order=order)
+    table.to_tsv(b, col_order=order)
+    got = open(a, "rb").read()
+    assert got == open(b, "rb").read()
+    if order is None:  # pandas prints rows in table order
+        assert got.decode() == pd.DataFrame(table.rows()).to_csv(sep="\t", index=False, na_rep="NA")
+
+
+def test_device_emitter_defers_huge_scores_to_the_host(tmp_path):
+    table = _table(3, 4, 5, False)
+    table.score[1, 1] = 10 ** 16   # pandas prints 1e+16 here
+    table.to_tsv(tmp_path / "x.tsv", device=0)
+    assert open(tmp_path / "x.tsv").read() == pd.DataFrame(table.rows()).to_csv(sep="\t", index=False, na_rep="NA")
