@@ -172,6 +172,46 @@ int sstar_b200_format_tsv(int device, void *stream, const int64_t *d_score, cons
                           const int32_t *d_col_order, char *d_out, size_t out_capacity,
                           void *d_workspace, size_t workspace_bytes);
 
+/* Native VCF scanner (host code, multi-threaded; plain text or gzip).
+ * replaces: allel.read_vcf(vcf, alt_number=1, samples=..., region=chr_name) as used by
+ *           read_geno_data (sstar/utils/utils.py:80-109) -- scikit-allel is an un-vendored dependency.
+ * One pass over the file gives, per chromosome in order of first appearance: POS int32 [V], the REF
+ * and first-ALT allele strings, and GT int8 [V, N, 2] (-1 = missing allele) for ALL N samples of the
+ * header, in header order.  chr_name NULL keeps every chromosome.  Pointers returned by the
+ * accessors stay valid until sstar_b200_vcf_free.  Errors: negative code, text from
+ * sstar_b200_vcf_last_error(). */
+typedef struct sstar_b200_vcf sstar_b200_vcf;
+int sstar_b200_vcf_scan(const char *path, const char *chr_name, int nthreads, sstar_b200_vcf **out);
+void sstar_b200_vcf_free(sstar_b200_vcf *h);
+const char *sstar_b200_vcf_last_error(void);
+int32_t sstar_b200_vcf_n_samples(const sstar_b200_vcf *h);
+const char *sstar_b200_vcf_sample(const sstar_b200_vcf *h, int32_t i);
+int32_t sstar_b200_vcf_n_chroms(const sstar_b200_vcf *h);
+const char *sstar_b200_vcf_chrom(const sstar_b200_vcf *h, int32_t c);
+int64_t sstar_b200_vcf_n_variants(const sstar_b200_vcf *h, int32_t c);
+const int32_t *sstar_b200_vcf_pos(const sstar_b200_vcf *h, int32_t c);
+const int8_t *sstar_b200_vcf_gt(const sstar_b200_vcf *h, int32_t c);
+/* which: 0 = REF, 1 = first ALT; allele v = bytes[off[v] .. off[v+1]) */
+const char *sstar_b200_vcf_alleles(const sstar_b200_vcf *h, int32_t c, int32_t which, const int32_t **off);
+
+/* Ingest filters on the device: raw calls of one chromosome -> the matrices the tiler gets.
+ * replaces: the array half of read_geno_data / read_data (sstar/utils/utils.py:105-107 all-missing
+ *           rows per population, :167-222 shared positions, :282-291 sites fixed-alt in both
+ *           populations, :293-306 phased reshape / unphased allele sum, :363-423 ancestral-allele
+ *           polarisation with the keep/flip/drop decision per variant made on the host).
+ * d_gt int8 [V, N, 2] (-1 = missing allele, all N samples in header order), d_pos int32 [V],
+ * d_mode int8 [V] or NULL (0 keep, 1 flip g -> |g-1|, 2 drop), d_ref_cols / d_tgt_cols: sample
+ * indices of the two populations.  Outputs (capacity V rows): d_ref_out int8 [V', R],
+ * d_tgt_out int8 [V', T], d_pos_out int32 [V'] with R, T = n * 2 (phased) or n (unphased).
+ * After the stream syncs the first 16 bytes of d_workspace hold int64 V' and int64 the number of
+ * rows both populations shared before the fixed-site filter. */
+size_t sstar_b200_ingest_workspace_bytes(int64_t V);
+int sstar_b200_ingest(int device, void *stream, const int8_t *d_gt, const int32_t *d_pos,
+                      const int8_t *d_mode, int64_t V, int32_t N, const int32_t *d_ref_cols,
+                      int32_t n_ref, const int32_t *d_tgt_cols, int32_t n_tgt, int32_t is_phased,
+                      int8_t *d_ref_out, int8_t *d_tgt_out, int32_t *d_pos_out, void *d_workspace,
+                      size_t workspace_bytes);
+
 /* Number of kernels the last sstar_b200_score_* / pack call on this thread enqueued. */
 int sstar_b200_last_launch_count(void);
 

@@ -52,6 +52,20 @@ SIGNATURES = {
     "sstar_b200_pack": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _sz]),
     "sstar_b200_score_packed": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _i32,
                                            _i32, _i32, _i32, _vp, _vp, _vp, _sz, _OPT]),
+    "sstar_b200_vcf_scan": (_c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_int, _c.POINTER(_vp)]),
+    "sstar_b200_vcf_free": (None, [_vp]),
+    "sstar_b200_vcf_last_error": (_c.c_char_p, []),
+    "sstar_b200_vcf_n_samples": (_i32, [_vp]),
+    "sstar_b200_vcf_sample": (_c.c_char_p, [_vp, _i32]),
+    "sstar_b200_vcf_n_chroms": (_i32, [_vp]),
+    "sstar_b200_vcf_chrom": (_c.c_char_p, [_vp, _i32]),
+    "sstar_b200_vcf_n_variants": (_i64, [_vp, _i32]),
+    "sstar_b200_vcf_pos": (_vp, [_vp, _i32]),
+    "sstar_b200_vcf_gt": (_vp, [_vp, _i32]),
+    "sstar_b200_vcf_alleles": (_vp, [_vp, _i32, _i32, _c.POINTER(_vp)]),
+    "sstar_b200_ingest_workspace_bytes": (_sz, [_i64]),
+    "sstar_b200_ingest": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _vp, _i32, _i32,
+                                     _vp, _vp, _vp, _vp, _sz]),
     "sstar_b200_tsv_max_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "sstar_b200_tsv_workspace_bytes": (_sz, [_i32, _i32]),
     "sstar_b200_format_tsv": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _c.c_char_p, _vp, _vp,

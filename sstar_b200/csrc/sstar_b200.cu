@@ -19,6 +19,7 @@
 #include "prep_kernels.cuh"
 #include "score_kernels.cuh"
 #include "emit_kernels.cuh"
+#include "ingest_kernels.cuh"
 
 using namespace sstar;
 
@@ -677,5 +678,49 @@ extern "C" int sstar_b200_format_tsv(int device, void *stream, const int64_t *d_
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "emit_scan_kernel launch: %s", cudaGetErrorString(e));
     e = launch(emit_format_kernel, (unsigned)nb, kEmitThreads, smem, st, false, a);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "emit_format_kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ingest filters
+// ---------------------------------------------------------------------------------------------
+extern "C" size_t sstar_b200_ingest_workspace_bytes(int64_t V) {
+    if (V < 0) return 0;
+    const size_t nb = (size_t)((V + kIngestRowsPerBlock - 1) / kIngestRowsPerBlock);
+    return 256 + align_up((size_t)(V > 0 ? V : 1), 256) + align_up((nb > 0 ? nb : 1) * 4, 256);
+}
+
+extern "C" int sstar_b200_ingest(int device, void *stream, const int8_t *d_gt, const int32_t *d_pos,
+                                 const int8_t *d_mode, int64_t V, int32_t N, const int32_t *d_ref_cols,
+                                 int32_t n_ref, const int32_t *d_tgt_cols, int32_t n_tgt, int32_t is_phased,
+                                 int8_t *d_ref_out, int8_t *d_tgt_out, int32_t *d_pos_out, void *d_workspace,
+                                 size_t workspace_bytes) {
+    g_launches = 0;
+    if (V < 0 || V > (int64_t)INT32_MAX - 64) return fail(SSTAR_B200_EINVAL, "V out of range%s");
+    if (N < 1 || n_ref < 1 || n_tgt < 1) return fail(SSTAR_B200_EINVAL, "at least one sample per population is required%s");
+    if (!d_workspace || ((uintptr_t)d_workspace & 255)) return fail(SSTAR_B200_EINVAL, "workspace null or not 256-byte aligned%s");
+    if (workspace_bytes < sstar_b200_ingest_workspace_bytes(V)) return fail(SSTAR_B200_EWORKSPACE, "workspace too small%s");
+    if (!d_ref_cols || !d_tgt_cols) return fail(SSTAR_B200_EINVAL, "null column list%s");
+    if (V > 0 && (!d_gt || !d_pos || !d_ref_out || !d_tgt_out || !d_pos_out)) return fail(SSTAR_B200_EINVAL, "null pointer%s");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *ws = (uint8_t *)d_workspace;
+    CUDA_TRY(cudaMemsetAsync(ws, 0, 256, st));
+    if (V == 0) return 0;
+    const int64_t nb = (V + kIngestRowsPerBlock - 1) / kIngestRowsPerBlock;
+    IngestArgs a = {};
+    a.gt = d_gt; a.pos = d_pos; a.mode = d_mode; a.ref_cols = d_ref_cols; a.tgt_cols = d_tgt_cols;
+    a.V = V; a.N = N; a.n_ref = n_ref; a.n_tgt = n_tgt; a.phased = is_phased ? 1 : 0;
+    a.counts = reinterpret_cast<int64_t *>(ws);
+    a.keep = ws + 256;
+    a.block_base = reinterpret_cast<int32_t *>(ws + 256 + align_up((size_t)V, 256));
+    a.ref_out = d_ref_out; a.tgt_out = d_tgt_out; a.pos_out = d_pos_out;
+    cudaError_t e = launch(ingest_flag_kernel, (unsigned)nb, kIngestWarps * 32, 0, st, false, a);
+    if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "ingest_flag_kernel launch: %s", cudaGetErrorString(e));
+    e = launch(ingest_scan_kernel, 1u, 1024u, 0, st, false, a, nb);
+    if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "ingest_scan_kernel launch: %s", cudaGetErrorString(e));
+    e = launch(ingest_write_kernel, (unsigned)nb, kIngestWarps * 32, 0, st, false, a);
+    if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "ingest_write_kernel launch: %s", cudaGetErrorString(e));
     return 0;
 }

@@ -208,6 +208,37 @@ class ScoreEngine:
             launches = self.launches
         return ScorePlan(graph, out[0], out[1], launches, (ref_d, tgt_d, pos_d, ws_d, we_d, self._dev.get("ws")))
 
+    # ------------------------------------------------------------------ ingest filters
+    def ingest_device(self, gt, pos, ref_cols, tgt_cols, is_phased: bool, mode=None, stream=None):
+        """Raw calls ``gt`` int8 [V, N, 2] (numpy or device tensor) -> device tensors
+        ``(ref_gts [V', R], tgt_gts [V', T], pos [V'], n_shared)`` after the reference's ingest
+        filters (see include/sstar_b200.h, sstar_b200_ingest)."""
+        torch = self.torch
+        with torch.cuda.device(self.tdev):
+            up = lambda a, dt: a if isinstance(a, torch.Tensor) else \
+                torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.tdev)
+            gt_d, pos_d = up(gt, np.int8), up(pos, np.int32)
+            V, N = int(gt_d.shape[0]), int(gt_d.shape[1])
+            rc_d, tc_d = up(ref_cols, np.int32), up(tgt_cols, np.int32)
+            mode_d = None if mode is None else up(mode, np.int8)
+            n_ref, n_tgt = int(rc_d.numel()), int(tc_d.numel())
+            R, T = (n_ref * 2, n_tgt * 2) if is_phased else (n_ref, n_tgt)
+            ref_o = torch.empty((max(V, 1), R), dtype=torch.int8, device=self.tdev)
+            tgt_o = torch.empty((max(V, 1), T), dtype=torch.int8, device=self.tdev)
+            pos_o = torch.empty(max(V, 1), dtype=torch.int32, device=self.tdev)
+            ws = self._dbuf("ingest_ws", self.lib.sstar_b200_ingest_workspace_bytes(V), torch.uint8)
+            s = stream if stream is not None else torch.cuda.current_stream(self.tdev)
+            rc = self.lib.sstar_b200_ingest(
+                self.device, ctypes.c_void_p(s.cuda_stream), gt_d.data_ptr(), pos_d.data_ptr(),
+                mode_d.data_ptr() if mode_d is not None else None, V, N, rc_d.data_ptr(), n_ref, tc_d.data_ptr(),
+                n_tgt, int(bool(is_phased)), ref_o.data_ptr(), tgt_o.data_ptr(), pos_o.data_ptr(), ws.data_ptr(),
+                ws.numel())
+            _cabi.check(rc)
+            self.launches = self.lib.sstar_b200_last_launch_count()
+            head = ws[:16].cpu().numpy().view(np.int64)  # syncs the stream
+        kept, shared = int(head[0]), int(head[1])
+        return ref_o[:kept], tgt_o[:kept], pos_o[:kept], shared
+
     # ------------------------------------------------------------------ result emitter
     def format_tsv_device(self, score_d, nsnp_d, ws_d, we_d, chrom: str, labels, replicate_d=None,
                           col_order_d=None, stream=None):

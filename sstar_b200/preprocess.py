@@ -1,13 +1,100 @@
 """Seam S1: ``preprocess(...)`` with the reference's signature (sstar/preprocess.py:28-122).
 
-VCF + sample lists in, feature TSV out -- byte-identical to the reference's table.  The scoring
-runs on the GPU(s); ``nprocess`` is validated like the reference does and otherwise ignored.
+VCF + sample lists in, feature TSV out -- byte-identical to the reference's table.  ``nprocess`` is
+validated like the reference does and otherwise ignored.
+
+On one GPU the whole call is device-resident between the text parser and the file write:
+native VCF scan (host, threads) -> raw calls to the GPU -> ingest filters (``sstar_b200_ingest``)
+-> pack / window bounds / chain DP (``sstar_b200_score_windows``) -> TSV text
+(``sstar_b200_format_tsv``) -> one D2H copy of the text.  With several GPUs (``SSTAR_GPUS``) or
+``SSTAR_B200_HOST_INGEST=1`` the filters run in numpy (``utils.read_data``) and the windows are
+sharded over the devices; both routes print the same bytes.
 """
 from __future__ import annotations
 
+import os
+
+import numpy as np
+
+from .feature_table import COLUMNS, FeatureTable, sample_labels
 from .feature_vector_preprocessor import FeatureVectorPreprocessor
 from .generators import WindowDataGenerator
-from .utils import parse_ind_file
+from .utils import parse_ind_file, split_genome
+from .utils.utils import _scan_vcf, read_anc_allele, validate_unique_variant_positions
+
+
+def _anc_modes(rec: dict, anc_c: dict) -> np.ndarray:
+    """Per variant: 0 keep, 1 flip, 2 drop -- the decision of check_anc_allele (utils.py:363-423)."""
+    pos, ref, alt = rec["POS"], rec["REF"], rec["ALT"]
+    mode = np.full(len(pos), 2, dtype=np.int8)
+    for i in range(len(pos)):
+        a = anc_c.get(int(pos[i]))
+        if a is None:
+            continue
+        if a == ref[i]:
+            mode[i] = 0
+        elif a == alt[i]:
+            mode[i] = 1
+    return mode
+
+
+def _preprocess_device(device, vcf_file, chr_name, ref_ind_file, tgt_ind_file, win_len, win_step, output_file,
+                       match_bonus, max_mismatch, mismatch_penalty, is_phased, anc_allele_file):
+    from .engine import get_engine, max_window_variants
+    if win_len <= 0:
+        raise ValueError("win_len must be greater than 0.")
+    if win_step < 0:
+        raise ValueError("win_step must be non-negative.")
+    ref_samples, tgt_samples = parse_ind_file(ref_ind_file), parse_ind_file(tgt_ind_file)
+    anc = read_anc_allele(anc_allele_file) if anc_allele_file is not None else None
+    header, scanned = _scan_vcf(vcf_file, chr_name, need_alleles=anc is not None)
+    if not scanned or chr_name not in scanned:
+        raise ValueError(f"{chr_name} is not present in the VCF file.")
+    rec = scanned[chr_name]
+    validate_unique_variant_positions({chr_name: rec}, chr_name)
+    want_r, want_t = set(ref_samples), set(tgt_samples)
+    ref_cols = [i for i, s in enumerate(header) if s in want_r]
+    tgt_cols = [i for i, s in enumerate(header) if s in want_t]
+    mode = _anc_modes(rec, anc[chr_name]) if anc is not None else None
+    no_shared = ValueError("No shared variant positions between reference and target "
+                           f"on chromosome {chr_name} after filtering.")
+    if not ref_cols or not tgt_cols:
+        raise no_shared
+    eng = get_engine(device)
+    torch = eng.torch
+    ref_d, tgt_d, pos_d, shared = eng.ingest_device(rec["GT"], rec["POS"], ref_cols, tgt_cols, is_phased, mode)
+    if shared == 0:
+        raise no_shared
+    pos = pos_d.cpu().numpy()
+    windows = split_genome(pos=pos, chr_name=chr_name, polymorphism_size=win_len, step_size=win_step)
+    ws = np.asarray([w[1][0] for w in windows], dtype=np.int64)
+    we = np.asarray([w[1][1] for w in windows], dtype=np.int64)
+    if ws.size and (ws.min() < -(2 ** 31) or we.max() > 2 ** 31 - 1):
+        raise ValueError("window coordinates do not fit int32")
+    labels = sample_labels(tgt_samples, 2, is_phased)
+    if tgt_d.shape[1] != len(labels):
+        raise ValueError(f"tgt_gts has {tgt_d.shape[1]} columns but {len(labels)} sample labels follow from the "
+                         "target list / ploidy / phasing")
+    with torch.cuda.device(eng.tdev):
+        ws_d = torch.from_numpy(ws.astype(np.int32)).to(eng.tdev)
+        we_d = torch.from_numpy(we.astype(np.int32)).to(eng.tdev)
+        score_d, nsnp_d = eng.score_device(ref_d, tgt_d, pos_d, ws_d, we_d, match_bonus, max_mismatch,
+                                           mismatch_penalty, max_win_variants=max_window_variants(pos, ws, we))
+        text_d, total, status = eng.format_tsv_device(score_d, nsnp_d, ws_d, we_d, str(chr_name), labels)
+        if status & 1:
+            raise RuntimeError("TSV emitter: output buffer too small (internal sizing error)")
+        if status:  # a score the device emitter does not print: format on the host
+            FeatureTable(chr_name, ws, we, labels, score_d.cpu().numpy(), nsnp_d.cpu().numpy()).to_tsv(output_file)
+            return
+        pin = eng._pbuf("tsv_pin", total, torch.uint8)[:total]
+        pin.copy_(text_d[:total], non_blocking=True)
+        torch.cuda.current_stream(eng.tdev).synchronize()
+    out_dir = os.path.dirname(str(output_file))
+    if out_dir:
+        os.makedirs(out_dir, exist_ok=True)
+    with open(output_file, "wb") as fh:
+        fh.write(("\t".join(COLUMNS) + "\n").encode())
+        fh.write(memoryview(pin.numpy()))
 
 
 def preprocess(vcf_file: str, chr_name: str, ref_ind_file: str, tgt_ind_file: str, win_len: int,
@@ -16,6 +103,18 @@ def preprocess(vcf_file: str, chr_name: str, ref_ind_file: str, tgt_ind_file: st
                anc_allele_file: str = None) -> None:
     if nprocess <= 0:
         raise ValueError("Number of processes must be greater than 0.")
+    from .sharding import visible_devices
+    devices = visible_devices()
+    if len(devices) == 1 and ploidy == 2 and os.environ.get("SSTAR_B200_HOST_INGEST", "") != "1":
+        try:
+            _preprocess_device(devices[0], vcf_file, chr_name, ref_ind_file, tgt_ind_file, win_len, win_step,
+                               output_file, match_bonus, max_mismatch, mismatch_penalty, is_phased, anc_allele_file)
+        except (ValueError, KeyError, OSError):
+            raise  # the reference's own input errors
+        except Exception as e:
+            print(f"sstar_b200: scoring failed ({e})")
+            raise SystemExit("Some errors occurred, stopping the program ...")
+        return
 
     generator = WindowDataGenerator(vcf_file=vcf_file, ref_ind_file=ref_ind_file,
                                     tgt_ind_file=tgt_ind_file, anc_allele_file=anc_allele_file,
@@ -32,5 +131,4 @@ def preprocess(vcf_file: str, chr_name: str, ref_ind_file: str, tgt_ind_file: st
         raise SystemExit("Some errors occurred, stopping the program ...")
     # windows are already in (Chromosome, Start, End) order == the reference's stable sort;
     # the rows are printed by the device emitter (same bytes as pandas' to_csv)
-    from .sharding import visible_devices
-    table.to_tsv(output_file, device=visible_devices()[0])
+    table.to_tsv(output_file, device=devices[0])

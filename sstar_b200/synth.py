@@ -123,3 +123,27 @@ def regular_windows(pos, win_len: int, win_step: int):
     n = (last - start0) // win_step + 1 if last >= start0 else 0
     ws = start0 + win_step * np.arange(n, dtype=np.int64)
     return ws.astype(np.int32), (ws + win_len - 1).astype(np.int32)
+
+
+def write_vcf(path: str, chrom: str, pos, hap, missing_rate: float = 0.0, seed: int = 0, sample_prefix: str = "ind"):
+    """Phased haplotype matrix ``hap`` int8 [V, 2N] -> a plain-text VCF with N diploid samples
+    (``0|1`` calls, ``.`` for alleles made missing at ``missing_rate``).  Returns the sample names.
+    For tests and benchmarks of the ingest path."""
+    hap = np.asarray(hap)
+    V, H = hap.shape
+    n = H // 2
+    names = [f"{sample_prefix}{i}" for i in range(n)]
+    rng = np.random.default_rng(seed)
+    txt = np.where(hap == 0, "0", np.where(hap == 1, "1", "2")).astype("U1")
+    if missing_rate > 0:
+        txt[rng.random(hap.shape) < missing_rate] = "."
+    with open(path, "w") as fh:
+        fh.write("##fileformat=VCFv4.2\n##source=sstar_b200.synth\n")
+        fh.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(names) + "\n")
+        for a in range(0, V, 4096):
+            b = min(V, a + 4096)
+            calls = np.char.add(np.char.add(txt[a:b, 0::2], "|"), txt[a:b, 1::2])
+            rows = ["\t".join((chrom, str(int(p)), ".", "A", "T", ".", "PASS", ".", "GT") + tuple(c))
+                    for p, c in zip(pos[a:b], calls)]
+            fh.write("\n".join(rows) + "\n")
+    return names

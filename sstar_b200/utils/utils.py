@@ -1,8 +1,8 @@
 """Host-side ingest and tiling helpers with the reference's names and error behaviour.
 
 Mirror of ``sstar/utils/utils.py`` (reference paths in brackets).  scikit-allel is not a
-dependency here: the VCF is parsed once by :func:`_scan_vcf` and both populations are cut from
-that single pass (the reference reads the file twice, utils.py:267,273).
+dependency here: the VCF is parsed once by the native scanner behind :func:`_scan_vcf`
+(``csrc/vcf_scan.cpp``) and both populations are cut from that single pass (the reference reads the file twice, utils.py:267,273).
 
 What is reproduced (and pinned by the reference's golden TSVs):
   * samples come back in VCF header order, labels come from the ind-file order  [utils.py:80,86]
@@ -15,7 +15,6 @@ What is reproduced (and pinned by the reference's golden TSVs):
 """
 from __future__ import annotations
 
-import gzip
 from typing import Any
 
 import numpy as np
@@ -30,66 +29,54 @@ def parse_ind_file(filename: str) -> list[str]:
     return samples
 
 
-_GT_CACHE: dict[str, tuple[int, int]] = {}
+def _scan_vcf(path: str, chr_name: str | None, need_alleles: bool = True):
+    """One pass over a (optionally gzipped) text VCF -> header samples + per-chromosome columns,
+    through the native multi-threaded scanner (``sstar_b200_vcf_scan``, csrc/vcf_scan.cpp).
 
-
-def _gt_pair(field: str) -> tuple[int, int]:
-    hit = _GT_CACHE.get(field)
-    if hit is not None:
-        return hit
-    gt = field.split(":", 1)[0]
-    alleles = gt.replace("|", "/").split("/")
-    vals = [-1, -1]
-    for i, a in enumerate(alleles[:2]):
-        vals[i] = int(a) if a not in (".", "") else -1
-    out = (vals[0], vals[1])
-    if len(_GT_CACHE) < 4096:
-        _GT_CACHE[field] = out
-    return out
-
-
-def _scan_vcf(path: str, chr_name: str | None):
-    """One pass over a (optionally gzipped) text VCF -> header samples + per-chromosome columns."""
-    opener = gzip.open if str(path).endswith(".gz") else open
-    header = None
-    per_chrom: dict[str, dict[str, list]] = {}
-    with opener(str(path), "rt") as fh:
-        for line in fh:
-            if line.startswith("##"):
-                continue
-            if line.startswith("#CHROM"):
-                header = line.rstrip("\n").split("\t")[9:]
-                continue
-            tab = line.find("\t")
-            chrom = line[:tab]
-            if chr_name is not None and chrom != chr_name:
-                continue
-            f = line.rstrip("\n").split("\t")
-            rec = per_chrom.get(chrom)
-            if rec is None:
-                rec = per_chrom[chrom] = {"POS": [], "REF": [], "ALT": [], "GT": []}
-            rec["POS"].append(int(f[1]))
-            rec["REF"].append(f[3])
-            rec["ALT"].append(f[4].split(",", 1)[0])
-            rec["GT"].append([_gt_pair(x) for x in f[9:]])
-    if header is None:
-        raise ValueError(f"{path} has no #CHROM header line.")
-    out = {}
-    for c, rec in per_chrom.items():
-        n = len(rec["POS"])
-        out[c] = {
-            "POS": np.asarray(rec["POS"], dtype=np.int32),
-            "REF": np.asarray(rec["REF"], dtype=object),
-            "ALT": np.asarray(rec["ALT"], dtype=object),
-            "GT": np.asarray(rec["GT"], dtype=np.int8).reshape(n, len(header), 2),
-        }
+    ``REF`` / ``ALT`` are only materialised as Python strings when ``need_alleles`` (they are used
+    by the ancestral-allele polarisation alone)."""
+    import ctypes
+    from .. import _cabi
+    lib = _cabi.load()
+    with open(str(path), "rb"):  # same FileNotFoundError / PermissionError as the reference's reader
+        pass
+    handle = ctypes.c_void_p()
+    rc = lib.sstar_b200_vcf_scan(str(path).encode(), None if chr_name is None else str(chr_name).encode(), 0,
+                                 ctypes.byref(handle))
+    if rc != 0:
+        raise ValueError(lib.sstar_b200_vcf_last_error().decode("utf-8", "replace"))
+    try:
+        n = lib.sstar_b200_vcf_n_samples(handle)
+        header = [lib.sstar_b200_vcf_sample(handle, i).decode() for i in range(n)]
+        out = {}
+        for c in range(lib.sstar_b200_vcf_n_chroms(handle)):
+            name = lib.sstar_b200_vcf_chrom(handle, c).decode()
+            v = lib.sstar_b200_vcf_n_variants(handle, c)
+            pos = np.ctypeslib.as_array(ctypes.cast(lib.sstar_b200_vcf_pos(handle, c),
+                                                    ctypes.POINTER(ctypes.c_int32)), shape=(v,)).copy() \
+                if v else np.zeros(0, dtype=np.int32)
+            gt = np.ctypeslib.as_array(ctypes.cast(lib.sstar_b200_vcf_gt(handle, c),
+                                                   ctypes.POINTER(ctypes.c_int8)), shape=(v, n, 2)).copy() \
+                if v and n else np.zeros((v, n, 2), dtype=np.int8)
+            rec = {"POS": pos, "REF": None, "ALT": None, "GT": gt}
+            if need_alleles:
+                for key, which in (("REF", 0), ("ALT", 1)):
+                    off_p = ctypes.c_void_p()
+                    base = lib.sstar_b200_vcf_alleles(handle, c, which, ctypes.byref(off_p))
+                    off = np.ctypeslib.as_array(ctypes.cast(off_p, ctypes.POINTER(ctypes.c_int32)), shape=(v + 1,))
+                    raw = ctypes.string_at(base, int(off[v])) if v else b""
+                    rec[key] = np.asarray([raw[off[i]:off[i + 1]].decode() for i in range(v)], dtype=object)
+            out[name] = rec
+    finally:
+        lib.sstar_b200_vcf_free(handle)
     return header, out
 
 
 def filter_data(data: dict, c: str, index: np.ndarray) -> dict:
     """Keep the rows selected by ``index`` on chromosome ``c`` [utils.py:114-137]."""
     for key in ("POS", "REF", "ALT", "GT"):
-        data[c][key] = data[c][key][index]
+        if data[c][key] is not None:  # REF / ALT are only loaded for the ancestral-allele step
+            data[c][key] = data[c][key][index]
     return data
 
 
@@ -123,7 +110,7 @@ def _select_population(header, scanned, ind, filter_missing, anc_allele, chr_nam
 def read_geno_data(vcf: str, ind: list[str], anc_allele_file: str, filter_missing: bool,
                    chr_name: str = None) -> tuple[dict, np.ndarray]:
     """Genotypes of the listed samples [utils.py:49-111]."""
-    header, scanned = _scan_vcf(vcf, chr_name)
+    header, scanned = _scan_vcf(vcf, chr_name, need_alleles=anc_allele_file is not None)
     anc = read_anc_allele(anc_allele_file) if anc_allele_file is not None else None
     return _select_population(header, scanned, ind, filter_missing, anc, chr_name)
 
@@ -161,7 +148,7 @@ def read_data(vcf_file: str, ref_ind_file: str, tgt_ind_file: str, anc_allele_fi
     header = scanned = None
     anc = read_anc_allele(anc_allele_file) if anc_allele_file is not None else None
     if ref_ind_file is not None or tgt_ind_file is not None:
-        header, scanned = _scan_vcf(vcf_file, chr_name)
+        header, scanned = _scan_vcf(vcf_file, chr_name, need_alleles=anc is not None)
 
     def copy_scan():
         return {c: dict(rec) for c, rec in scanned.items()}

@@ -142,3 +142,92 @@ def test_device_emitter_defers_huge_scores_to_the_host(tmp_path):
     table.score[1, 1] = 10 ** 16   # pandas prints 1e+16 here
     table.to_tsv(tmp_path / "x.tsv", device=0)
     assert open(tmp_path / "x.tsv").read() == pd.DataFrame(table.rows()).to_csv(sep="\t", index=False, na_rep="NA")
+
+
+# ---- ingest filters on the device vs the numpy mirror of read_data
+def _write_case_vcf(tmp_path, seed, n_ind=14, V=900, anc=False):
+    """A VCF with every filter case: rows missing in a whole population, partially missing calls,
+    sites fixed in both populations, multi-allelic calls; optionally an ancestral-allele table."""
+    rng = np.random.default_rng(seed)
+    pos = np.sort(rng.choice(np.arange(1, 400_000), size=V, replace=False))
+    g = (rng.random((V, n_ind, 2)) < rng.random((V, 1, 1)) ** 2).astype(int)
+    g[rng.random((V, n_ind, 2)) < 0.03] = -1                      # scattered missing alleles
+    g[rng.random(V) < 0.05, : n_ind // 2] = -1                    # whole first half (ref pop) missing
+    g[rng.random(V) < 0.05, n_ind // 2:] = -1                     # whole second half missing
+    g[rng.random(V) < 0.06] = 1                                   # fixed alt everywhere
+    g[rng.random((V, n_ind, 2)) < 0.004] = 2                      # second alt allele
+    names = [f"s{i}" for i in range(n_ind)]
+    bases = np.array(list("ACGT"))
+    ref = bases[rng.integers(0, 4, V)]
+    alt = bases[(np.searchsorted(bases, ref) + rng.integers(1, 4, V)) % 4]
+    path = tmp_path / f"case{seed}.vcf"
+    with open(path, "w") as fh:
+        fh.write("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(names) + "\n")
+        for k in range(V):
+            calls = ["|".join("." if a < 0 else str(a) for a in g[k, i]) for i in range(n_ind)]
+            fh.write(f"9\t{pos[k]}\t.\t{ref[k]}\t{alt[k]},G\t.\t.\t.\tGT\t" + "\t".join(calls) + "\n")
+    # ind lists in an order different from the VCF header
+    (tmp_path / "ref.list").write_text("\n".join(reversed(names[: n_ind // 2])) + "\n")
+    (tmp_path / "tgt.list").write_text("\n".join(names[n_ind // 2:]) + "\n")
+    anc_path = None
+    if anc:
+        anc_path = tmp_path / "anc.bed"
+        with open(anc_path, "w") as fh:
+            for k in range(V):
+                u = rng.random()
+                if u < 0.1:
+                    continue                                      # unknown site -> dropped
+                allele = ref[k] if u < 0.6 else alt[k] if u < 0.9 else "N"
+                fh.write(f"9\t{pos[k] - 1}\t{pos[k]}\t{allele}\n")
+    return str(path), str(tmp_path / "ref.list"), str(tmp_path / "tgt.list"), None if anc_path is None else str(anc_path)
+
+
+@pytest.mark.parametrize("phased", [True, False])
+@pytest.mark.parametrize("anc", [False, True])
+def test_device_ingest_matches_read_data(tmp_path, phased, anc):
+    from sstar_b200.engine import get_engine
+    from sstar_b200.preprocess import _anc_modes
+    from sstar_b200.utils import parse_ind_file, read_data
+    from sstar_b200.utils.utils import _scan_vcf, read_anc_allele
+    vcf, rl, tl, anc_file = _write_case_vcf(tmp_path, 40 + int(anc), anc=anc)
+    ref_data, _, tgt_data, _ = read_data(vcf, rl, tl, anc_file, phased, chr_name="9")
+    header, scanned = _scan_vcf(vcf, "9", need_alleles=anc)
+    rec = scanned["9"]
+    rcols = [i for i, s in enumerate(header) if s in set(parse_ind_file(rl))]
+    tcols = [i for i, s in enumerate(header) if s in set(parse_ind_file(tl))]
+    mode = _anc_modes(rec, read_anc_allele(anc_file)["9"]) if anc else None
+    r, t, p, shared = get_engine(0).ingest_device(rec["GT"], rec["POS"], rcols, tcols, phased, mode)
+    assert np.array_equal(p.cpu().numpy(), tgt_data["9"]["POS"]) and shared >= len(p) > 100
+    assert np.array_equal(r.cpu().numpy(), ref_data["9"]["GT"])
+    assert np.array_equal(t.cpu().numpy(), tgt_data["9"]["GT"])
+
+
+@pytest.mark.parametrize("phased", [True, False])
+def test_preprocess_device_route_equals_host_route(tmp_path, monkeypatch, phased):
+    from sstar_b200.preprocess import preprocess
+    vcf, rl, tl, anc_file = _write_case_vcf(tmp_path, 7, n_ind=20, V=1500, anc=True)
+    kw = dict(vcf_file=vcf, chr_name="9", ref_ind_file=rl, tgt_ind_file=tl, win_len=50000, win_step=10000,
+              match_bonus=5000, max_mismatch=5, mismatch_penalty=-10000, nprocess=2, is_phased=phased,
+              anc_allele_file=anc_file)
+    preprocess(output_file=str(tmp_path / "dev.tsv"), **kw)
+    monkeypatch.setenv("SSTAR_B200_HOST_INGEST", "1")
+    preprocess(output_file=str(tmp_path / "host.tsv"), **kw)
+    a, b = open(tmp_path / "dev.tsv", "rb").read(), open(tmp_path / "host.tsv", "rb").read()
+    assert a == b and a.count(b"\n") > 100
+
+
+def test_preprocess_device_route_errors(tmp_path):
+    from sstar_b200.preprocess import preprocess
+    vcf, rl, tl, _ = _write_case_vcf(tmp_path, 3, n_ind=6, V=50)
+    kw = dict(ref_ind_file=rl, tgt_ind_file=tl, win_len=50000, win_step=10000, match_bonus=5000, max_mismatch=5,
+              mismatch_penalty=-10000, output_file=str(tmp_path / "o.tsv"))
+    with pytest.raises(ValueError, match="is not present in the VCF file"):
+        preprocess(vcf_file=vcf, chr_name="10", **kw)
+    dup = tmp_path / "dup.vcf"
+    lines = open(vcf).read().splitlines()
+    dup.write_text("\n".join(lines + [lines[-1]]) + "\n")
+    with pytest.raises(ValueError, match="Duplicate variant positions found on chromosome 9"):
+        preprocess(vcf_file=str(dup), chr_name="9", **kw)
+    (tmp_path / "none.list").write_text("nobody\n")
+    with pytest.raises(ValueError, match="No shared variant positions"):
+        preprocess(vcf_file=vcf, chr_name="9", **{**kw, "ref_ind_file": str(tmp_path / "none.list")})

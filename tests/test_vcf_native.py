@@ -1,0 +1,88 @@
+"""The native VCF scanner (csrc/vcf_scan.cpp, host code) against the oracle's plain-Python reader
+and the reference's fixtures.  CPU only."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from conftest import FIXTURES
+from oracle import tiling_port
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    import __graft_entry__ as g
+    g.build()
+
+
+def _same(path, chrom, tmp_names=None):
+    from sstar_b200.utils.utils import _scan_vcf
+    header, got = _scan_vcf(path, chrom)
+    want, names = tiling_port.read_vcf_text(path, header, chrom)
+    assert names == header
+    assert list(got) == list(want)
+    for c in want:
+        assert np.array_equal(got[c]["POS"], want[c]["POS"]) and got[c]["POS"].dtype == np.int32
+        assert np.array_equal(got[c]["GT"], want[c]["GT"]) and got[c]["GT"].dtype == np.int8
+        assert list(got[c]["REF"]) == list(want[c]["REF"])
+        assert list(got[c]["ALT"]) == list(want[c]["ALT"])
+    return header, got
+
+
+@pytest.mark.parametrize("name,chrom", [("test.vcf", "21"), ("test.vcf", None), ("test.0.vcf", "1")])
+def test_reference_fixtures(name, chrom):
+    header, got = _same(os.path.join(FIXTURES, name), chrom)
+    assert len(header) >= 6 and all(len(v["POS"]) > 0 for v in got.values())
+
+
+def test_gzip_and_absent_chromosome(tmp_path):
+    from sstar_b200.utils.utils import _scan_vcf
+    src = open(os.path.join(FIXTURES, "test.vcf"), "rb").read()
+    gz = tmp_path / "t.vcf.gz"
+    with gzip.open(gz, "wb") as fh:
+        fh.write(src)
+    _same(str(gz), "21")
+    header, got = _scan_vcf(str(gz), "22")
+    assert got == {} and len(header) == 6
+    with pytest.raises(FileNotFoundError):
+        _scan_vcf(str(tmp_path / "nope.vcf"), None)
+    bad = tmp_path / "bad.vcf"
+    bad.write_text("##fileformat=VCFv4.2\n1\t5\t.\tA\tT\t.\t.\t.\tGT\t0|1\n")
+    with pytest.raises(ValueError, match="no #CHROM header"):
+        _scan_vcf(str(bad), None)
+
+
+def test_odd_records(tmp_path):
+    # missing alleles, '/' and '|', extra FORMAT fields, multi-allelic ALT, haploid calls,
+    # multi-digit alleles, CRLF line ends, chromosomes interleaved, no trailing newline
+    lines = ["##fileformat=VCFv4.2", "##contig=<ID=1>",
+             "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ts1\ts2\ts3\ts4",
+             "1\t10\t.\tA\tT\t.\tPASS\t.\tGT\t0|1\t1/1\t.|.\t./1",
+             "2\t7\trs1\tG\tC,T\t50\tPASS\tAC=1\tGT:DP:GQ\t0|2:12:99\t2/1:3:4\t.:.:.\t1:5:6",
+             "1\t25\t.\tAC\tA\t.\t.\t.\tGT\t0|0\t0|10\t12|3\t1|.",
+             "X\t3\t.\tT\t<DEL>\t.\t.\t.\tGT:AD\t1\t0\t.\t1|1:4,5",
+             "1\t26\t.\tC\tG\t.\t.\t.\tGT\t1|1\t1|1\t1|1\t1|1"]
+    for ending, tail in (("\n", "\n"), ("\r\n", ""), ("\n", "")):
+        p = tmp_path / f"odd{len(ending)}{len(tail)}.vcf"
+        p.write_bytes((ending.join(lines) + tail).encode())
+        header, got = _same(str(p), None)
+        assert header == ["s1", "s2", "s3", "s4"] and list(got) == ["1", "2", "X"]
+        assert got["1"]["GT"][0].tolist() == [[0, 1], [1, 1], [-1, -1], [-1, 1]]
+        assert got["2"]["GT"][0].tolist() == [[0, 2], [2, 1], [-1, -1], [1, -1]]
+        assert got["1"]["GT"][1].tolist() == [[0, 0], [0, 10], [12, 3], [1, -1]]
+        assert list(got["2"]["ALT"]) == ["C"] and list(got["X"]["ALT"]) == ["<DEL>"]
+        _same(str(p), "1")
+
+
+def test_large_synthetic_vcf_round_trip(tmp_path):
+    # thousands of lines: exercises the threaded line parser; genotypes must survive text and back
+    from sstar_b200.synth import synth_chromosome, write_vcf
+    from sstar_b200.utils.utils import _scan_vcf
+    ref, tgt, pos = synth_chromosome(1_200_000, 20, 15, True, seed=3)
+    path = tmp_path / "big.vcf"
+    names = write_vcf(str(path), "7", pos, np.concatenate([ref, tgt], axis=1), missing_rate=0.01, seed=1)
+    header, got = _scan_vcf(str(path), "7")
+    assert header == names and np.array_equal(got["7"]["POS"], pos)
+    want, _ = tiling_port.read_vcf_text(str(path), header, "7")
+    assert np.array_equal(got["7"]["GT"], want["7"]["GT"])
