@@ -30,6 +30,7 @@ namespace sstar {
 
 constexpr int kMinPairDistance = 10;  // sstar/sstar.py:195: pairs closer than 10 bp never link
 constexpr int kRingSlots = 16;        // >= 10 waiting sites
+constexpr uint32_t kListSentinel = 0xffffffffu;  // list terminator: a position beyond any window
 constexpr int64_t kNegInf64 = INT64_MIN;
 
 template <typename acc_t> struct Sentinel;
@@ -66,19 +67,24 @@ SSTAR_HD int64_t score_bound(int64_t span, int64_t nvar, int32_t bonus, int32_t 
 // consecutive entries are `ls` words apart, ring slots `rs` words apart (strided shared-memory
 // columns on the device, 1 on the host).  Scores the window [plo, phi] (relative positions,
 // closed).  `a` is the list cursor: windows of a group are visited with non-decreasing plo, so it
-// only moves forward.
+// only moves forward.  The caller terminates the list with kListSentinel at index cnt.
 // ---------------------------------------------------------------------------------------------
 SSTAR_HD void list_dp_window(const uint32_t *list, int ls, int32_t *ring, int rs, int &a, int cnt,
                              uint32_t plo, uint32_t phi, int32_t bonus, int32_t pen_eff, int &n_out,
                              int64_t &score_out) {
+    // list[cnt] is a sentinel entry (kListSentinel: position beyond any window), so neither loop
+    // needs a bound check
     constexpr int32_t NEG = Sentinel<int32_t>::NEG, THR = Sentinel<int32_t>::THR;
-    while (a < cnt && (list[a * ls] >> 1) < plo) ++a;
-    int k = a, c = a;  // next site to score, next site to commit
+    (void)cnt;
+    const uint32_t *pa = list + a * ls;
+    while ((*pa >> 1) < plo) { pa += ls; ++a; }
+    const uint32_t *pk = pa;  // next site to score
+    int k = a, c = a;         // its index, and the index of the next site to commit
     int32_t A0 = NEG, A1 = NEG, B0 = NEG, B1 = NEG, top = NEG;
     uint32_t pe = 0;  // entry k-1 and its v
     int32_t pv = 0;
-    while (k < cnt) {
-        const uint32_t e = list[k * ls];
+    for (;;) {
+        const uint32_t e = *pk;
         if ((e >> 1) > phi) break;
         const int32_t p = (int32_t)(e >> 1);
         if (c == k - 1) {  // common case: only the previous site waits, in registers
@@ -111,6 +117,7 @@ SSTAR_HD void list_dp_window(const uint32_t *list, int ls, int32_t *ring, int rs
         top = imax(top, m);
         pe = e;
         pv = imax(m, (int32_t)0);
+        pk += ls;
         ++k;
     }
     n_out = k - a;

@@ -36,7 +36,7 @@ struct LdgPos {
     __device__ __forceinline__ int64_t operator()(int32_t k) const { return (int64_t)__ldg(pos + k); }
 };
 
-// grid.x = tchunks * ngroups; dynamic smem: list [L][bd] | max(ring [16][bd], positions [words_cap*32])
+// grid.x = tchunks * ngroups; dynamic smem: list [L + 1][bd] | max(ring [16][bd], positions [words_cap*32])
 __global__ void __launch_bounds__(kScoreMaxThreads)
 score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words_cap) {
     extern __shared__ __align__(16) uint8_t dyn[];
@@ -50,7 +50,7 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
     // the position tile is only read while the lists are built, the ring only during the DP:
     // they share one region (a barrier separates the two phases)
     uint32_t *s_list = reinterpret_cast<uint32_t *>(dyn);
-    uint32_t *s_pos = s_list + (size_t)L * bd;
+    uint32_t *s_pos = s_list + (size_t)(L + 1) * bd;  // row L of the list area is the spill slot
     int32_t *s_ring = reinterpret_cast<int32_t *>(s_pos);
 
     pdl_wait();  // bit-planes and window bounds come from the prep launch
@@ -116,13 +116,19 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
         }
         __syncthreads();
 
-        // this thread's column: plane words -> site list
+        // this thread's column: plane words -> site list.  Shared memory is addressed with 32-bit
+        // shared-window addresses (ld/st.shared) and the write cursor is clamped to a spill slot
+        // (index L) instead of branching on overflow.
         int cnt = 0;
         if (t < a.T) {
             const uint32_t *cp = a.carried + (size_t)gi0 * a.Tp + t;
             const uint32_t *tp = a.two + (size_t)gi0 * a.Tp + t;
             const uint32_t first_mask = 0xffffffffu << (rlo & 31);
             const uint32_t last_mask = 0xffffffffu >> (31 - ((rhi - 1) & 31));
+            const uint32_t pos_addr = (uint32_t)__cvta_generic_to_shared(s_pos);
+            const uint32_t step = (uint32_t)bd * 4u;
+            uint32_t w_addr = (uint32_t)__cvta_generic_to_shared(s_list + tid);
+            const uint32_t w_end = w_addr + (uint32_t)L * step;  // the spill slot
             for (int jb = 0; jb < nwr; jb += 4) {
                 uint32_t cw[4], tw[4];
 #pragma unroll
@@ -136,19 +142,24 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     uint32_t c = cw[u];
-                    const uint32_t *sp = s_pos + ((jb + u) << 5);
+                    const uint32_t sp = pos_addr + ((uint32_t)(jb + u) << 7);
+                    cnt += __popc(c);
                     while (c) {
                         const int b = __ffs(c) - 1;
                         c &= c - 1;
-                        if (cnt < L) s_list[cnt * bd + tid] = (sp[b] << 1) | ((tw[u] >> b) & 1u);
-                        ++cnt;
+                        uint32_t rel;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rel) : "r"(sp + 4u * (uint32_t)b));
+                        const uint32_t e = (rel << 1) | ((tw[u] >> b) & 1u);
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(w_addr), "r"(e) : "memory");
+                        w_addr = min(w_addr + step, w_end);
                     }
                 }
             }
         }
+        const bool overflow = cnt >= L;  // one slot is the terminator
+        if (t < a.T && !overflow) s_list[cnt * bd + tid] = kListSentinel;
         __syncthreads();       // every list is built: the position tile becomes the ring
         if (t >= a.T) return;  // no block-wide barrier below this point on the fast path
-        const bool overflow = cnt > L;
         int cur = 0;
         for (int i = 0; i < nwin; ++i) {
             const int w = w0 + i;

@@ -55,7 +55,7 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
     }
     memset(slow, 0, W);
     const int32_t pen_eff = (max_mm >= 1) ? penalty : Sentinel<int32_t>::NEG;
-    std::vector<uint32_t> list(L), spos;
+    std::vector<uint32_t> list(L + 1), spos;
     int32_t ring[kRingSlots];
     auto window_absent = [&](int32_t lo, int32_t hi, int32_t &na, uint32_t &ex) {
         na = 0; ex = 0;
@@ -110,7 +110,8 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
                         ++cnt;
                     }
                 }
-                const bool overflow = cnt > L;
+                const bool overflow = cnt >= L;  // one slot is the terminator
+                if (!overflow) list[cnt] = kListSentinel;
                 int cur = 0;
                 for (int i = 0; i < nwin; ++i) {
                     const int w = w0 + i;
