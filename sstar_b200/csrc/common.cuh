@@ -11,7 +11,7 @@ constexpr int kPackThreads = 256;
 constexpr int kScoreMaxThreads = 128;
 constexpr int kMaxGroup = 16;       // windows one score CTA walks at most
 constexpr int kScoreWordsCap = 64;  // staged position tile of a window group: 64 words = 2048 variants
-constexpr int kScoreListBytes = 24 << 10;  // shared memory for the per-column site lists of one CTA
+constexpr int kScoreListBytes = 22 << 10;  // shared memory for the per-column site lists of one CTA
 constexpr int kPairWarps = 4;
 constexpr int kPairSmemCap = 1024;  // pairwise list entries per warp kept in shared memory
 constexpr int kNumSM = 148;

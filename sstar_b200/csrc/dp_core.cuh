@@ -12,7 +12,7 @@
 // four running maxima (A0, A1, B0, B1).  Positions ascend, so the eligible predecessors of site j
 // are a prefix of the sites before it: a site is "committed" to the maxima once the current site is
 // >= 10 bp ahead.  At most 10 distinct integer positions fit in 9 bp, so at most 10 sites wait; the
-// newest waits in registers, older ones in a 16-slot ring.
+// newest waits in registers, older ones in a 16-slot thread-local ring.
 //
 // "-inf" is a sentinel NEG with |real values| < |NEG| / 4: invalid candidates stay below THR
 // without selects, m = max(same + p + bonus, other + penalty) is valid iff m > THR, and
@@ -64,28 +64,23 @@ SSTAR_HD int64_t score_bound(int64_t span, int64_t nvar, int32_t bonus, int32_t 
 // ---------------------------------------------------------------------------------------------
 // List DP (int32).  `list` holds one column's carried reference-absent sites of a window GROUP in
 // ascending position, entry = (position relative to the group's first variant) << 1 | (genotype==2);
-// consecutive entries are `ls` words apart, ring slots `rs` words apart (strided shared-memory
-// columns on the device, 1 on the host).  Scores the window [plo, phi] (relative positions,
+// consecutive entries are `ls` words apart (a strided shared-memory column on the device, 1 on the
+// host).  Scores the window [plo, phi] (relative positions,
 // closed).  `a` is the list cursor: windows of a group are visited with non-decreasing plo, so it
 // only moves forward.  The caller terminates the list with kListSentinel at index cnt.
 // ---------------------------------------------------------------------------------------------
-SSTAR_HD void list_dp_window(const uint32_t *list, int ls, int32_t *ring, int rs, int &a, int cnt,
-                             uint32_t plo, uint32_t phi, int32_t bonus, int32_t pen_eff, int &n_out,
-                             int64_t &score_out) {
-    // list[cnt] is a sentinel entry (kListSentinel: position beyond any window), so neither loop
-    // needs a bound check
+// Scores exactly the n sites starting at `base` (a run of one column's list).  n >= 1.
+SSTAR_HD int64_t list_dp_run(const uint32_t *base, int ls, int n, int32_t bonus, int32_t pen_eff) {
     constexpr int32_t NEG = Sentinel<int32_t>::NEG, THR = Sentinel<int32_t>::THR;
-    (void)cnt;
-    const uint32_t *pa = list + a * ls;
-    while ((*pa >> 1) < plo) { pa += ls; ++a; }
-    const uint32_t *pk = pa;  // next site to score
-    int k = a, c = a;         // its index, and the index of the next site to commit
+    int32_t ring[kRingSlots];  // v of waiting sites older than k-1: thread-local memory, touched only
+                               // when carried sites crowd within 9 bp (a few percent of the sites)
+    const uint32_t *pk = base;  // next site to score
+    int c = 0;                  // index of the next site to commit
     int32_t A0 = NEG, A1 = NEG, B0 = NEG, B1 = NEG, top = NEG;
     uint32_t pe = 0;  // entry k-1 and its v
     int32_t pv = 0;
-    for (;;) {
+    for (int k = 0; k < n; ++k) {
         const uint32_t e = *pk;
-        if ((e >> 1) > phi) break;
         const int32_t p = (int32_t)(e >> 1);
         if (c == k - 1) {  // common case: only the previous site waits, in registers
             const int32_t pc = (int32_t)(pe >> 1);
@@ -94,21 +89,21 @@ SSTAR_HD void list_dp_window(const uint32_t *list, int ls, int32_t *ring, int rs
                 else         { A0 = imax(A0, pv - pc); B0 = imax(B0, pv); }
                 c = k;
             } else {
-                ring[((k - 1) & (kRingSlots - 1)) * rs] = pv;  // k-1 keeps waiting: park its v
+                ring[(k - 1) & (kRingSlots - 1)] = pv;  // k-1 keeps waiting: park its v
             }
         } else if (c < k) {  // crowded sites: older ones wait in the ring
             while (c < k) {
                 uint32_t ec;
                 int32_t vc;
                 if (c == k - 1) { ec = pe; vc = pv; }
-                else            { ec = list[c * ls]; vc = ring[(c & (kRingSlots - 1)) * rs]; }
+                else            { ec = base[c * ls]; vc = ring[c & (kRingSlots - 1)]; }
                 const int32_t pc = (int32_t)(ec >> 1);
                 if (p - pc < kMinPairDistance) break;
                 if (ec & 1u) { A1 = imax(A1, vc - pc); B1 = imax(B1, vc); }
                 else         { A0 = imax(A0, vc - pc); B0 = imax(B0, vc); }
                 ++c;
             }
-            if (c < k) ring[((k - 1) & (kRingSlots - 1)) * rs] = pv;
+            if (c < k) ring[(k - 1) & (kRingSlots - 1)] = pv;
         }
         const bool cls = (e & 1u) != 0;
         const int32_t same = cls ? A1 : A0;
@@ -118,10 +113,29 @@ SSTAR_HD void list_dp_window(const uint32_t *list, int ls, int32_t *ring, int rs
         pe = e;
         pv = imax(m, (int32_t)0);
         pk += ls;
-        ++k;
     }
-    n_out = k - a;
-    score_out = (n_out <= 2 || top <= THR) ? kNegInf64 : (int64_t)top;
+    return (n <= 2 || top <= THR) ? kNegInf64 : (int64_t)top;
+}
+
+// Moves the cursors to the window [plo, phi]: a = first entry with position >= plo, b = first
+// entry with position > phi.  The list ends with kListSentinel, so no bound checks.  With
+// b_monotone the end cursor continues from where the previous window left it (windows whose ends
+// never decrease); otherwise it restarts at a.
+SSTAR_HD void list_window_range(const uint32_t *list, int ls, int &a, int &b, uint32_t plo, uint32_t phi,
+                                bool b_monotone) {
+    const uint32_t *pa = list + a * ls;
+    while ((*pa >> 1) < plo) { pa += ls; ++a; }
+    if (!b_monotone || b < a) b = a;
+    const uint32_t *pb = list + b * ls;
+    while ((*pb >> 1) <= phi) { pb += ls; ++b; }
+}
+
+SSTAR_HD void list_dp_window(const uint32_t *list, int ls, int &a, uint32_t plo, uint32_t phi, int32_t bonus,
+                             int32_t pen_eff, int &n_out, int64_t &score_out) {
+    int b = a;
+    list_window_range(list, ls, a, b, plo, phi, false);
+    n_out = b - a;
+    score_out = n_out <= 2 ? kNegInf64 : list_dp_run(list + a * ls, ls, n_out, bonus, pen_eff);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -28,6 +28,7 @@ struct GroupShared {
     uint32_t ex[kMaxGroup];
     int32_t red_nabs;
     uint32_t red_ex;
+    int32_t n_work;
 };
 
 struct LdgU32 { __device__ __forceinline__ uint32_t operator()(const uint32_t *p) const { return __ldg(p); } };
@@ -36,7 +37,7 @@ struct LdgPos {
     __device__ __forceinline__ int64_t operator()(int32_t k) const { return (int64_t)__ldg(pos + k); }
 };
 
-// grid.x = tchunks * ngroups; dynamic smem: list [L + 1][bd] | max(ring [16][bd], positions [words_cap*32])
+// grid.x = tchunks * ngroups; dynamic smem: list [L + 1][bd] | max(positions [words_cap*32], worklist [wg*bd])
 __global__ void __launch_bounds__(kScoreMaxThreads)
 score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words_cap) {
     extern __shared__ __align__(16) uint8_t dyn[];
@@ -47,11 +48,11 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
     const int w0 = a.w_begin + grp * wg;
     const int nwin = min(wg, a.w_end - w0);
     const int t = chunk * bd + tid;
-    // the position tile is only read while the lists are built, the ring only during the DP:
+    // the position tile is only read while the lists are built, the unit worklist only after:
     // they share one region (a barrier separates the two phases)
     uint32_t *s_list = reinterpret_cast<uint32_t *>(dyn);
     uint32_t *s_pos = s_list + (size_t)(L + 1) * bd;  // row L of the list area is the spill slot
-    int32_t *s_ring = reinterpret_cast<int32_t *>(s_pos);
+    uint32_t *s_work = s_pos;                         // [wg * bd] unit worklist, after the lists are built
 
     pdl_wait();  // bit-planes and window bounds come from the prep launch
     if (tid < nwin) {
@@ -65,13 +66,15 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
     __syncthreads();
 
     // the group's union variant range [rlo, rhi) over its non-empty windows
-    int32_t rlo = INT32_MAX, rhi = -1, prev_lo = -1, maxnv = 0, p0 = 0, plast = INT32_MIN;
-    bool mono = true;
+    int32_t rlo = INT32_MAX, rhi = -1, prev_lo = -1, prev_hi = -1, maxnv = 0, p0 = 0, plast = INT32_MIN;
+    bool mono = true, mono_hi = true;
     for (int i = 0; i < nwin; ++i) {
         const int32_t lo = g.lo[i], hi = g.hi[i];
         if (hi > lo) {
             mono = mono && lo >= prev_lo;
+            mono_hi = mono_hi && hi >= prev_hi;
             prev_lo = lo;
+            prev_hi = hi;
             if (lo < rlo) { rlo = lo; p0 = g.pfirst[i]; }
             rhi = max(rhi, hi);
             plast = max(plast, g.plast[i]);
@@ -158,8 +161,63 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
         }
         const bool overflow = cnt >= L;  // one slot is the terminator
         if (t < a.T && !overflow) s_list[cnt * bd + tid] = kListSentinel;
-        __syncthreads();       // every list is built: the position tile becomes the ring
-        if (t >= a.T) return;  // no block-wide barrier below this point on the fast path
+        if (tid == 0) g.n_work = 0;
+        __syncthreads();       // every list is built: the position tile becomes the worklist
+
+        if (nwin > 1 && mono_hi) {
+            // ---- balanced path.  Pass 1, one thread per column: both list cursors only move
+            // forward, so locating every window's run [a, a + n) costs O(list length); units with
+            // n <= 2 are NaN and finished here (most units of sparse haplotype data), the others
+            // are queued.  Pass 2: the CTA's threads share the queued units evenly, so a warp's DP
+            // loop no longer runs for the longest of 32 unrelated columns in every window.
+            int cur_a = 0, cur_b = 0;
+            for (int i = 0; i < nwin; ++i) {
+                const int w = w0 + i;
+                const int32_t lo = g.lo[i], hi = g.hi[i];
+                const bool ex = g.ex[i] != 0;
+                if (ex && chunk == 0 && tid == 0) a.slow_list[a.w_begin + atomicAdd(&a.hdr->n_slow[a.slot], 1)] = w;
+                int n = 0;
+                bool queued = false;
+                int64_t score = kNegInf64;
+                if (t < a.T && !ex && hi > lo) {
+                    if (!overflow) {
+                        list_window_range(s_list + tid, bd, cur_a, cur_b, g.plo[i], g.phi[i], true);
+                        n = cur_b - cur_a;
+                        queued = n > 2;
+                    } else {
+                        walk_dp_unit<int32_t>(LdgU32(), LdgPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus,
+                                              a.penalty, a.max_mm, n, score);
+                    }
+                }
+                // warp-aggregated append of (column, window, first entry, length)
+                const uint32_t qm = __ballot_sync(0xffffffffu, queued);
+                if (qm) {
+                    const int lane = tid & 31;
+                    int basei = 0;
+                    if (lane == __ffs(qm) - 1) basei = atomicAdd(&g.n_work, __popc(qm));
+                    basei = __shfl_sync(0xffffffffu, basei, __ffs(qm) - 1);
+                    if (queued)
+                        s_work[basei + __popc(qm & ((1u << lane) - 1u))] =
+                            (uint32_t)tid | ((uint32_t)i << 7) | ((uint32_t)cur_a << 11) | ((uint32_t)n << 21);
+                }
+                if (t < a.T && !ex) {
+                    const size_t o = (size_t)w * a.T + t;
+                    if (!queued) a.score[o] = score;  // NaN (n <= 2, empty window) or the overflow column's score
+                    a.nsnp[o] = (hi - lo) - g.nabs[i] + n;
+                }
+            }
+            __syncthreads();
+            const int n_work = g.n_work;
+            for (int u = tid; u < n_work; u += bd) {
+                const uint32_t e = s_work[u];
+                const int col = e & 127, i = (e >> 7) & 15, ua = (e >> 11) & 1023, n = e >> 21;
+                const int64_t score = list_dp_run(s_list + col + ua * bd, bd, n, a.bonus, pen_eff);
+                a.score[(size_t)(w0 + i) * a.T + chunk * bd + col] = score;
+            }
+            return;
+        }
+
+        if (t >= a.T) return;  // no block-wide barrier below this point
         int cur = 0;
         for (int i = 0; i < nwin; ++i) {
             const int w = w0 + i;
@@ -172,8 +230,7 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
             int64_t score = kNegInf64;
             if (hi > lo) {
                 if (!overflow)
-                    list_dp_window(s_list + tid, bd, s_ring + tid, bd, cur, cnt, g.plo[i], g.phi[i], a.bonus,
-                                   pen_eff, n, score);
+                    list_dp_window(s_list + tid, bd, cur, g.plo[i], g.phi[i], a.bonus, pen_eff, n, score);
                 else
                     walk_dp_unit<int32_t>(LdgU32(), LdgPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus,
                                           a.penalty, a.max_mm, n, score);

@@ -236,7 +236,7 @@ int launch_score(cudaStream_t st, const ScoreCall &c, const WsLayout &L, int32_t
         const int64_t ngroups = (W + wg - 1) / wg;
         if (ngroups * tchunks > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "too many (window group, column chunk) tiles%s");
         const int Lslots = kScoreListBytes / (bd * 4) - 1;  // list slots per column (one more row is the spill slot)
-        const size_t ring_b = (size_t)kRingSlots * bd * 4, pos_b = (size_t)words_cap * 32 * 4;
+        const size_t ring_b = (size_t)wg * bd * 4, pos_b = (size_t)words_cap * 32 * 4;  // worklist | position tile
         const size_t smem = (size_t)(Lslots + 1) * bd * 4 + (ring_b > pos_b ? ring_b : pos_b);  // +1: spill slot
         static thread_local size_t k2_smem_set = 0;
         if (smem > k2_smem_set) {

@@ -56,7 +56,6 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
     memset(slow, 0, W);
     const int32_t pen_eff = (max_mm >= 1) ? penalty : Sentinel<int32_t>::NEG;
     std::vector<uint32_t> list(L + 1), spos;
-    int32_t ring[kRingSlots];
     auto window_absent = [&](int32_t lo, int32_t hi, int32_t &na, uint32_t &ex) {
         na = 0; ex = 0;
         if (hi <= lo) return;
@@ -70,13 +69,14 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
     };
     for (int w0 = 0; w0 < W; w0 += wg) {
         const int nwin = std::min(wg, W - w0);
-        int32_t rlo = INT32_MAX, rhi = -1, prev_lo = -1, maxnv = 0;
-        bool mono = true;
+        int32_t rlo = INT32_MAX, rhi = -1, prev_lo = -1, prev_hi = -1, maxnv = 0;
+        bool mono = true, mono_hi = true;
         for (int i = 0; i < nwin; ++i) {
             const int32_t lo = wlo[w0 + i], hi = whi[w0 + i];
             if (hi > lo) {
                 mono = mono && lo >= prev_lo;
-                prev_lo = lo;
+                mono_hi = mono_hi && hi >= prev_hi;
+                prev_lo = lo; prev_hi = hi;
                 rlo = std::min(rlo, lo); rhi = std::max(rhi, hi); maxnv = std::max(maxnv, hi - lo);
             }
         }
@@ -112,7 +112,8 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
                 }
                 const bool overflow = cnt >= L;  // one slot is the terminator
                 if (!overflow) list[cnt] = kListSentinel;
-                int cur = 0;
+                int cur = 0, cur_b = 0;
+                const bool balanced = nwin > 1 && mono_hi;  // the kernel's two-pass path
                 for (int i = 0; i < nwin; ++i) {
                     const int w = w0 + i;
                     const int32_t lo = wlo[w], hi = whi[w];
@@ -122,7 +123,11 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
                     int n = 0; int64_t sc = kNegInf64;
                     if (hi > lo) {
                         const uint32_t plo = (uint32_t)(pos[lo] - p0), phi = (uint32_t)(pos[hi - 1] - p0);
-                        if (!overflow) list_dp_window(list.data(), 1, ring, 1, cur, cnt, plo, phi, bonus, pen_eff, n, sc);
+                        if (!overflow && balanced) {
+                            list_window_range(list.data(), 1, cur, cur_b, plo, phi, true);
+                            n = cur_b - cur;
+                            if (n > 2) sc = list_dp_run(list.data() + cur, 1, n, bonus, pen_eff);
+                        } else if (!overflow) list_dp_window(list.data(), 1, cur, plo, phi, bonus, pen_eff, n, sc);
                         else walk_dp_unit<int32_t>(HostLd(), HostPos{pos}, carried.data(), two.data(), Tp, t, lo, hi, bonus, penalty, max_mm, n, sc);
                     }
                     score[(size_t)w * T + t] = sc;
