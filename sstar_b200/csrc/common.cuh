@@ -28,7 +28,7 @@ struct WsHeader {
 struct WsLayout {
     int64_t G;   // 32-variant groups
     int32_t Tp;  // plane row pitch in words (T rounded up to 32)
-    size_t off_absent, off_exotic, off_carried, off_two, off_win_lo, off_win_hi, off_win_pfirst, off_win_plast, off_slow, off_arena;
+    size_t off_absent, off_exotic, off_carried, off_two, off_win_lo, off_win_hi, off_win_pfirst, off_win_plast, off_slow, off_bail, off_arena;
     size_t arena_entries;
     size_t total;
 };
@@ -41,6 +41,7 @@ struct BoundsArgs {
     int32_t V, W;
     int32_t *win_lo, *win_hi, *slow_list;
     int32_t *win_pfirst, *win_plast;  // position of the first / last variant of each non-empty window
+    uint32_t *win_bail;               // zeroed here: set once a window is routed to the pairwise kernel by a unit
     WsHeader *hdr;
     int force_slow;
 };
@@ -62,6 +63,7 @@ struct ScoreArgs {
     const int32_t *win_start, *win_end;  // or null: fixed_start / fixed_end
     int32_t fixed_start, fixed_end;
     int32_t *slow_list;
+    uint32_t *win_bail;
     WsHeader *hdr;
     int32_t V, T, Tp, tchunks;
     int32_t w_begin, w_end;  // windows scored by this launch

@@ -117,17 +117,81 @@ SSTAR_HD int64_t list_dp_run(const uint32_t *base, int ls, int n, int32_t bonus,
     return (n <= 2 || top <= THR) ? kNegInf64 : (int64_t)top;
 }
 
-// Moves the cursors to the window [plo, phi]: a = first entry with position >= plo, b = first
-// entry with position > phi.  The list ends with kListSentinel, so no bound checks.  With
-// b_monotone the end cursor continues from where the previous window left it (windows whose ends
-// never decrease); otherwise it restarts at a.
-SSTAR_HD void list_window_range(const uint32_t *list, int ls, int &a, int &b, uint32_t plo, uint32_t phi,
-                                bool b_monotone) {
+// ---------------------------------------------------------------------------------------------
+// General-genotype list DP: the same prefix-max recurrence for ANY int8 genotype (missing calls
+// give negative dosages, multi-allelic sites values > 2: sstar/utils/utils.py:305-306,
+// sstar/sstar.py:163-164,179).  Entry = (relative position << 8) | (genotype & 0xff).  The running
+// maxima are kept per distinct genotype value (class) in small thread-local tables:
+//     M[j] = max( p_j + bonus + A[g_j] ,  penalty + max_{g' != g_j, |g' - g_j| <= max_mm} B[g'] ).
+// Returns false when a unit holds more than kMaxClasses distinct values (the caller routes the
+// window to the pairwise kernel).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxClasses = 8;
+constexpr int kGeneralPosBits = 23;  // relative positions below 2^23 (8 Mb per window group)
+
+template <int kShift>
+SSTAR_HD void list_window_range_shifted(const uint32_t *list, int ls, int &a, int &b, uint32_t plo, uint32_t phi,
+                                        bool b_monotone) {
     const uint32_t *pa = list + a * ls;
-    while ((*pa >> 1) < plo) { pa += ls; ++a; }
+    while ((*pa >> kShift) < plo) { pa += ls; ++a; }
     if (!b_monotone || b < a) b = a;
     const uint32_t *pb = list + b * ls;
-    while ((*pb >> 1) <= phi) { pb += ls; ++b; }
+    while ((*pb >> kShift) <= phi) { pb += ls; ++b; }
+}
+
+SSTAR_HD bool list_dp_run_general(const uint32_t *base, int ls, int n, int32_t bonus, int32_t penalty, int32_t max_mm,
+                                  int64_t &score_out) {
+    constexpr int32_t NEG = Sentinel<int32_t>::NEG, THR = Sentinel<int32_t>::THR;
+    int32_t A[kMaxClasses], B[kMaxClasses], val[kMaxClasses];
+    int32_t ring_v[kRingSlots];
+    int K = 0;
+    int c = 0;  // next site to commit
+    int32_t top = NEG;
+    auto class_of = [&](int32_t g) -> int {
+        for (int i = 0; i < K; ++i)
+            if (val[i] == g) return i;
+        return -1;
+    };
+    for (int k = 0; k < n; ++k) {
+        const uint32_t e = base[k * ls];
+        const int32_t p = (int32_t)(e >> 8);
+        const int32_t g = (int32_t)(int8_t)(e & 0xffu);
+        while (c < k) {  // sites >= 10 bp behind become eligible predecessors
+            const uint32_t ec = base[c * ls];
+            const int32_t pc = (int32_t)(ec >> 8);
+            if (p - pc < kMinPairDistance) break;
+            const int ci = class_of((int32_t)(int8_t)(ec & 0xffu));  // registered when it was scored
+            const int32_t vc = ring_v[c & (kRingSlots - 1)];
+            A[ci] = imax(A[ci], vc - pc);
+            B[ci] = imax(B[ci], vc);
+            ++c;
+        }
+        int idx = class_of(g);
+        if (idx < 0) {
+            if (K == kMaxClasses) return false;
+            idx = K++;
+            val[idx] = g; A[idx] = NEG; B[idx] = NEG;
+        }
+        int32_t other = NEG;
+        for (int i = 0; i < K; ++i) {
+            const int32_t d = val[i] > g ? val[i] - g : g - val[i];
+            if (i != idx && d <= max_mm) other = imax(other, B[i]);
+        }
+        const int32_t m = imax(A[idx] + (p + bonus), other + penalty);
+        top = imax(top, m);
+        ring_v[k & (kRingSlots - 1)] = imax(m, (int32_t)0);
+    }
+    score_out = (n <= 2 || top <= THR) ? kNegInf64 : (int64_t)top;
+    return true;
+}
+
+// list_window_range_shifted moves the cursors to the window [plo, phi]: a = first entry with
+// position >= plo, b = first entry with position > phi.  The list ends with kListSentinel, so no
+// bound checks.  With b_monotone the end cursor continues from where the previous window left it
+// (windows whose ends never decrease); otherwise it restarts at a.
+SSTAR_HD void list_window_range(const uint32_t *list, int ls, int &a, int &b, uint32_t plo, uint32_t phi,
+                                bool b_monotone) {
+    list_window_range_shifted<1>(list, ls, a, b, plo, phi, b_monotone);
 }
 
 SSTAR_HD void list_dp_window(const uint32_t *list, int ls, int &a, uint32_t plo, uint32_t phi, int32_t bonus,

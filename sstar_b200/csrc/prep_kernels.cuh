@@ -49,6 +49,7 @@ __device__ __forceinline__ void bounds_block(const BoundsArgs &a, int block, int
     if (lane == 0) {
         a.win_lo[w] = lo;
         a.win_hi[w] = hi;
+        a.win_bail[w] = 0u;
     }
 }
 

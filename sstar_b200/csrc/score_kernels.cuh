@@ -119,6 +119,14 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
         }
         __syncthreads();
 
+        // Windows holding genotypes outside {0,1,2} (missing calls, multi-allelic sites): the whole
+        // group switches to general entries (relative position << 8 | genotype byte, fetched from
+        // the target matrix) and the per-class DP of dp_core.cuh.  Only when the group spans more
+        // than 2^23 bp do such windows go to the pairwise kernel instead.
+        bool any_ex = false;
+        for (int i = 0; i < nwin; ++i) any_ex = any_ex || g.ex[i] != 0;
+        const bool gen = any_ex && span < (int64_t(1) << kGeneralPosBits);
+
         // this thread's column: plane words -> site list.  Shared memory is addressed with 32-bit
         // shared-window addresses (ld/st.shared) and the write cursor is clamped to a spill slot
         // (index L) instead of branching on overflow.
@@ -152,7 +160,11 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
                         c &= c - 1;
                         uint32_t rel;
                         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rel) : "r"(sp + 4u * (uint32_t)b));
-                        const uint32_t e = (rel << 1) | ((tw[u] >> b) & 1u);
+                        uint32_t e = (rel << 1) | ((tw[u] >> b) & 1u);
+                        if (gen) {
+                            const int8_t gb = a.tgt[(size_t)(base + ((jb + u) << 5) + b) * a.T + t];
+                            e = (rel << 8) | (uint32_t)(uint8_t)gb;
+                        }
                         asm volatile("st.shared.u32 [%0], %1;" ::"r"(w_addr), "r"(e) : "memory");
                         w_addr = min(w_addr + step, w_end);
                     }
@@ -164,6 +176,13 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
         if (tid == 0) g.n_work = 0;
         __syncthreads();       // every list is built: the position tile becomes the worklist
 
+        // a unit the general DP cannot take (more than kMaxClasses genotype values, or its column
+        // overflowed the list): its window goes to the pairwise kernel, queued once
+        auto bail_window = [&](int w) {
+            if (atomicExch(&a.win_bail[w], 1u) == 0u)
+                a.slow_list[a.w_begin + atomicAdd(&a.hdr->n_slow[a.slot], 1)] = w;
+        };
+
         if (nwin > 1 && mono_hi) {
             // ---- balanced path.  Pass 1, one thread per column: both list cursors only move
             // forward, so locating every window's run [a, a + n) costs O(list length); units with
@@ -174,16 +193,19 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
             for (int i = 0; i < nwin; ++i) {
                 const int w = w0 + i;
                 const int32_t lo = g.lo[i], hi = g.hi[i];
-                const bool ex = g.ex[i] != 0;
+                const bool ex = !gen && g.ex[i] != 0;  // not representable here: pairwise kernel
                 if (ex && chunk == 0 && tid == 0) a.slow_list[a.w_begin + atomicAdd(&a.hdr->n_slow[a.slot], 1)] = w;
                 int n = 0;
                 bool queued = false;
                 int64_t score = kNegInf64;
                 if (t < a.T && !ex && hi > lo) {
                     if (!overflow) {
-                        list_window_range(s_list + tid, bd, cur_a, cur_b, g.plo[i], g.phi[i], true);
+                        if (gen) list_window_range_shifted<8>(s_list + tid, bd, cur_a, cur_b, g.plo[i], g.phi[i], true);
+                        else     list_window_range_shifted<1>(s_list + tid, bd, cur_a, cur_b, g.plo[i], g.phi[i], true);
                         n = cur_b - cur_a;
                         queued = n > 2;
+                    } else if (gen) {
+                        bail_window(w);
                     } else {
                         walk_dp_unit<int32_t>(LdgU32(), LdgPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus,
                                               a.penalty, a.max_mm, n, score);
@@ -211,7 +233,12 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
             for (int u = tid; u < n_work; u += bd) {
                 const uint32_t e = s_work[u];
                 const int col = e & 127, i = (e >> 7) & 15, ua = (e >> 11) & 1023, n = e >> 21;
-                const int64_t score = list_dp_run(s_list + col + ua * bd, bd, n, a.bonus, pen_eff);
+                int64_t score;
+                if (!gen) score = list_dp_run(s_list + col + ua * bd, bd, n, a.bonus, pen_eff);
+                else if (!list_dp_run_general(s_list + col + ua * bd, bd, n, a.bonus, a.penalty, a.max_mm, score)) {
+                    bail_window(w0 + i);
+                    continue;
+                }
                 a.score[(size_t)(w0 + i) * a.T + chunk * bd + col] = score;
             }
             return;
@@ -221,7 +248,7 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
         int cur = 0;
         for (int i = 0; i < nwin; ++i) {
             const int w = w0 + i;
-            if (g.ex[i]) {  // genotypes outside {0,1,2}: the whole window goes to the pairwise kernel
+            if (!gen && g.ex[i]) {  // not representable here: the whole window goes to the pairwise kernel
                 if (chunk == 0 && tid == 0) a.slow_list[a.w_begin + atomicAdd(&a.hdr->n_slow[a.slot], 1)] = w;
                 continue;
             }
@@ -229,11 +256,21 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
             int n = 0;
             int64_t score = kNegInf64;
             if (hi > lo) {
-                if (!overflow)
-                    list_dp_window(s_list + tid, bd, cur, g.plo[i], g.phi[i], a.bonus, pen_eff, n, score);
-                else
+                if (overflow) {
+                    if (gen) { bail_window(w); continue; }
                     walk_dp_unit<int32_t>(LdgU32(), LdgPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus,
                                           a.penalty, a.max_mm, n, score);
+                } else if (!gen) {
+                    list_dp_window(s_list + tid, bd, cur, g.plo[i], g.phi[i], a.bonus, pen_eff, n, score);
+                } else {
+                    int b = cur;
+                    list_window_range_shifted<8>(s_list + tid, bd, cur, b, g.plo[i], g.phi[i], false);
+                    n = b - cur;
+                    if (n > 2 && !list_dp_run_general(s_list + tid + cur * bd, bd, n, a.bonus, a.penalty, a.max_mm, score)) {
+                        bail_window(w);
+                        continue;
+                    }
+                }
             }
             const size_t o = (size_t)w * a.T + t;
             a.score[o] = score;

@@ -60,6 +60,7 @@ WsLayout make_layout(int64_t V, int32_t T, int32_t W, int32_t max_win_variants) 
     L.off_win_pfirst = off; off = align_up(off + w * 4, 256);
     L.off_win_plast = off;  off = align_up(off + w * 4, 256);
     L.off_slow = off;    off = align_up(off + w * 4, 256);
+    L.off_bail = off;    off = align_up(off + w * 4, 256);
     // pairwise list arena: at least one slab of the worst-case window must fit
     size_t worst = (size_t)(V > 0 ? V : 1);
     size_t want;
@@ -165,6 +166,7 @@ int launch_prep(cudaStream_t st, int64_t g_begin, int64_t g_end, const int8_t *d
         b.win_hi = reinterpret_cast<int32_t *>(ws + L.off_win_hi);
         b.win_pfirst = reinterpret_cast<int32_t *>(ws + L.off_win_pfirst);
         b.win_plast = reinterpret_cast<int32_t *>(ws + L.off_win_plast);
+        b.win_bail = reinterpret_cast<uint32_t *>(ws + L.off_bail);
         b.hdr = reinterpret_cast<WsHeader *>(ws);
     }
     if (n_pack + n_bounds == 0) return 0;
@@ -210,6 +212,7 @@ int launch_score(cudaStream_t st, const ScoreCall &c, const WsLayout &L, int32_t
     s.win_pfirst = reinterpret_cast<const int32_t *>(ws + L.off_win_pfirst);
     s.win_plast = reinterpret_cast<const int32_t *>(ws + L.off_win_plast);
     s.slow_list = reinterpret_cast<int32_t *>(ws + L.off_slow);
+    s.win_bail = reinterpret_cast<uint32_t *>(ws + L.off_bail);
     s.hdr = reinterpret_cast<WsHeader *>(ws);
     s.V = (int32_t)c.V; s.T = c.T; s.Tp = L.Tp;
     s.w_begin = w_begin; s.w_end = w_end; s.slot = slot;

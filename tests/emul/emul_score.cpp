@@ -96,6 +96,13 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
             const int32_t npos = (int32_t)std::min<int64_t>((int64_t)nwr << 5, V - base);
             spos.assign((size_t)nwr << 5, 0);
             for (int i = 0; i < npos; ++i) spos[i] = (uint32_t)(pos[base + i] - p0);
+            bool any_ex = false;
+            for (int i = 0; i < nwin; ++i) {
+                int32_t na; uint32_t ex;
+                window_absent(wlo[w0 + i], whi[w0 + i], na, ex);
+                any_ex = any_ex || ex;
+            }
+            const bool gen = any_ex && span < (int64_t(1) << kGeneralPosBits);
             for (int t = 0; t < T; ++t) {
                 int cnt = 0;
                 for (int j = 0; j < nwr; ++j) {
@@ -106,7 +113,9 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
                     while (c) {
                         const int b = __builtin_ctz(c);
                         c &= c - 1;
-                        if (cnt < L) list[cnt] = (spos[(j << 5) + b] << 1) | ((tw >> b) & 1u);
+                        uint32_t e = (spos[(j << 5) + b] << 1) | ((tw >> b) & 1u);
+                        if (gen) e = (spos[(j << 5) + b] << 8) | (uint32_t)(uint8_t)tgt[(size_t)(base + (j << 5) + b) * T + t];
+                        if (cnt < L) list[cnt] = e;
                         ++cnt;
                     }
                 }
@@ -119,11 +128,17 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
                     const int32_t lo = wlo[w], hi = whi[w];
                     int32_t na; uint32_t ex;
                     window_absent(lo, hi, na, ex);
-                    if (ex) { slow[w] = 1; continue; }
+                    if (ex && !gen) { slow[w] = 1; continue; }
                     int n = 0; int64_t sc = kNegInf64;
                     if (hi > lo) {
                         const uint32_t plo = (uint32_t)(pos[lo] - p0), phi = (uint32_t)(pos[hi - 1] - p0);
-                        if (!overflow && balanced) {
+                        if (gen) {
+                            if (overflow) { slow[w] = 1; continue; }
+                            if (!balanced) cur_b = cur;
+                            list_window_range_shifted<8>(list.data(), 1, cur, cur_b, plo, phi, balanced);
+                            n = cur_b - cur;
+                            if (n > 2 && !list_dp_run_general(list.data() + cur, 1, n, bonus, penalty, max_mm, sc)) { slow[w] = 1; continue; }
+                        } else if (!overflow && balanced) {
                             list_window_range(list.data(), 1, cur, cur_b, plo, phi, true);
                             n = cur_b - cur;
                             if (n > 2) sc = list_dp_run(list.data() + cur, 1, n, bonus, pen_eff);
@@ -132,7 +147,7 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
                     }
                     score[(size_t)w * T + t] = sc;
                     nsnp[(size_t)w * T + t] = (hi - lo) - na + n;
-                    path[(size_t)w * T + t] = overflow ? 2 : 1;
+                    path[(size_t)w * T + t] = gen ? 5 : overflow ? 2 : 1;
                 }
             }
             continue;

@@ -93,17 +93,42 @@ def test_crowded_positions_exercise_the_ring(emul):
         check(emul, ref, tgt, pos, ws, we, params, wg=8, words_cap=2)  # group too wide -> walk DP
 
 
-def test_missing_data_routes_windows_to_slow_list(emul):
+def test_missing_data_takes_the_general_dp(emul):
+    # negative dosages (missing calls) and signed reference sums: the per-class DP, not the slow list
     ref, tgt, pos = synth_chromosome(500_000, 10, 24, False, seed=77)
     rng = np.random.default_rng(5)
     tgt = tgt.copy()
-    miss = rng.random(tgt.shape) < 0.0001
-    tgt[miss] = -1
+    miss = rng.random(tgt.shape) < 0.01
+    tgt[miss] = rng.choice([-2, -1], size=int(miss.sum())).astype(np.int8)
     ref = ref.copy()
     ref[rng.random(ref.shape) < 0.002] = -1
     ws, we = regular_windows(pos, 50_000, 10_000)
-    _, slow = check(emul, ref, tgt, pos, ws, we, wg=8)
-    assert slow.any() and not slow.all()
+    for params in [(5000, 5, -10000), (5000, 0, -10000), (5000, 2, -10000), (1, 1, 0), (123, 3, -7)]:
+        for wg in (1, 8):
+            path, slow = check(emul, ref, tgt, pos, ws, we, params, wg=wg, L=512)
+            assert not slow.any() and (path == 5).mean() > 0.8
+
+
+def test_general_dp_many_classes_and_crowding(emul):
+    rng = np.random.default_rng(6)
+    V = 3000
+    pos = np.cumsum(rng.choice([1, 2, 3, 9, 10, 11, 40], size=V)).astype(np.int32)
+    ref = np.zeros((V, 2), np.int8)
+    ref[rng.random(V) < 0.1, 0] = 1
+    ws = np.arange(1, int(pos[-1]), 400, dtype=np.int32)
+    we = ws + 1999
+    # up to 7 distinct genotype values: still the general DP, with several sites waiting at once
+    tgt = rng.choice([0, -2, -1, 1, 2, 3, 4, 6], size=(V, 6), p=[0.3, 0.1, 0.1, 0.2, 0.15, 0.05, 0.05, 0.05]).astype(np.int8)
+    for params in [(5000, 5, -10000), (7, 1, -3), (50, 8, -20)]:
+        path, slow = check(emul, ref, tgt, pos, ws, we, params, wg=4, L=2048)
+        assert not slow.any() and (path == 5).all()
+    # more than 8 distinct values in one unit: that window is handed to the pairwise kernel
+    tgt2 = tgt.copy()
+    tgt2[:, 0] = rng.integers(-60, 60, size=V).astype(np.int8)
+    path, slow = check(emul, ref, tgt2, pos, ws, we, wg=4, L=2048)
+    assert slow.any()
+    # a column that overflows its list in general mode also routes its windows there
+    check(emul, ref, tgt, pos, ws, we, wg=4, L=16)
 
 
 def test_int64_switch_and_odd_windows(emul):
