@@ -22,8 +22,10 @@
 
 #if defined(__CUDACC__)
 #define SSTAR_HD __host__ __device__ __forceinline__
+#define SSTAR_HD_COLD __host__ __device__ __noinline__  // rare paths: keep them out of the hot kernel body
 #else
 #define SSTAR_HD inline
+#define SSTAR_HD_COLD inline
 #endif
 
 namespace sstar {
@@ -139,7 +141,7 @@ SSTAR_HD void list_window_range_shifted(const uint32_t *list, int ls, int &a, in
     while ((*pb >> kShift) <= phi) { pb += ls; ++b; }
 }
 
-SSTAR_HD bool list_dp_run_general(const uint32_t *base, int ls, int n, int32_t bonus, int32_t penalty, int32_t max_mm,
+SSTAR_HD_COLD bool list_dp_run_general(const uint32_t *base, int ls, int n, int32_t bonus, int32_t penalty, int32_t max_mm,
                                   int64_t &score_out) {
     constexpr int32_t NEG = Sentinel<int32_t>::NEG, THR = Sentinel<int32_t>::THR;
     int32_t A[kMaxClasses], B[kMaxClasses], val[kMaxClasses];

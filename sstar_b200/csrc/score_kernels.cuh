@@ -37,6 +37,185 @@ struct LdgPos {
     __device__ __forceinline__ int64_t operator()(int32_t k) const { return (int64_t)__ldg(pos + k); }
 };
 
+struct GroupCtx {
+    GroupShared *g;
+    uint32_t *s_list, *s_pos;
+    int tid, bd, chunk, t, w0, nwin, L;
+    int32_t rlo, rhi, gi0, nwr, pen_eff;
+    bool mono_hi;
+};
+
+// List build + DP of one window group.  kGen = false: genotypes in {0,1,2}, entries
+// (relative position << 1 | genotype==2), the four-maxima DP.  kGen = true: a window of the group
+// holds other genotypes (missing calls, multi-allelic sites): entries (relative position << 8 |
+// genotype byte, fetched from the target matrix) and the per-class DP of dp_core.cuh.
+template <bool kGen>
+__device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c) {
+    GroupShared &g = *c.g;
+    uint32_t *s_list = c.s_list;
+    uint32_t *s_work = c.s_pos;  // [wg * bd] unit worklist, once the lists are built
+    const int tid = c.tid, bd = c.bd, chunk = c.chunk, t = c.t, w0 = c.w0, nwin = c.nwin, L = c.L;
+    constexpr int kShift = kGen ? 8 : 1;
+
+    // this thread's column: plane words -> site list.  Shared memory is addressed with 32-bit
+    // shared-window addresses (ld/st.shared) and the write cursor is clamped to a spill slot
+    // (index L) instead of branching on overflow.
+    int cnt = 0;
+    if (t < a.T) {
+        const uint32_t *cp = a.carried + (size_t)c.gi0 * a.Tp + t;
+        const uint32_t *tp = a.two + (size_t)c.gi0 * a.Tp + t;
+        const uint32_t first_mask = 0xffffffffu << (c.rlo & 31);
+        const uint32_t last_mask = 0xffffffffu >> (31 - ((c.rhi - 1) & 31));
+        const uint32_t pos_addr = (uint32_t)__cvta_generic_to_shared(c.s_pos);
+        const uint32_t step = (uint32_t)bd * 4u;
+        uint32_t w_addr = (uint32_t)__cvta_generic_to_shared(s_list + tid);
+        const uint32_t w_end = w_addr + (uint32_t)L * step;  // the spill slot
+        const int nwr = c.nwr;
+        for (int jb = 0; jb < nwr; jb += 4) {
+            uint32_t cw[4], tw[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cw[u] = (jb + u < nwr) ? __ldg(cp + (size_t)(jb + u) * a.Tp) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (jb + u == 0) cw[u] &= first_mask;
+                if (jb + u == nwr - 1) cw[u] &= last_mask;
+                tw[u] = (!kGen && jb + u < nwr) ? __ldg(tp + (size_t)(jb + u) * a.Tp) : 0u;  // not chained to cw
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint32_t cbits = cw[u];
+                const uint32_t sp = pos_addr + ((uint32_t)(jb + u) << 7);
+                cnt += __popc(cbits);
+                while (cbits) {
+                    const int b = __ffs(cbits) - 1;
+                    cbits &= cbits - 1;
+                    uint32_t rel;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rel) : "r"(sp + 4u * (uint32_t)b));
+                    uint32_t e;
+                    if (kGen) {
+                        const int8_t gb = a.tgt[(size_t)(((c.gi0 + jb + u) << 5) + b) * a.T + t];
+                        e = (rel << 8) | (uint32_t)(uint8_t)gb;
+                    } else {
+                        e = (rel << 1) | ((tw[u] >> b) & 1u);
+                    }
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(w_addr), "r"(e) : "memory");
+                    w_addr = min(w_addr + step, w_end);
+                }
+            }
+        }
+    }
+    const bool overflow = cnt >= L;  // one slot is the terminator
+    if (t < a.T && !overflow) s_list[cnt * bd + tid] = kListSentinel;
+    if (tid == 0) g.n_work = 0;
+    __syncthreads();  // every list is built: the position tile becomes the worklist
+
+    // a unit the general DP cannot take (more than kMaxClasses genotype values, or its column
+    // overflowed the list): its window goes to the pairwise kernel, queued once
+    auto bail_window = [&](int w) {
+        if (atomicExch(&a.win_bail[w], 1u) == 0u) a.slow_list[a.w_begin + atomicAdd(&a.hdr->n_slow[a.slot], 1)] = w;
+    };
+    // windows with genotypes outside {0,1,2} that the list path is not taking in general mode
+    auto route_exotic = [&](int i) -> bool {
+        if (kGen || !g.ex[i]) return false;
+        if (chunk == 0 && tid == 0) a.slow_list[a.w_begin + atomicAdd(&a.hdr->n_slow[a.slot], 1)] = w0 + i;
+        return true;
+    };
+
+    if (nwin > 1 && c.mono_hi) {
+        // ---- balanced path.  Pass 1, one thread per column: both list cursors only move forward,
+        // so locating every window's run [a, a + n) costs O(list length); units with n <= 2 are
+        // NaN and finished here (most units of sparse haplotype data), the others are queued.
+        // Pass 2: the CTA's threads share the queued units evenly, so a warp's DP loop no longer
+        // runs for the longest of 32 unrelated columns in every window.
+        int cur_a = 0, cur_b = 0;
+        for (int i = 0; i < nwin; ++i) {
+            const int w = w0 + i;
+            const int32_t lo = g.lo[i], hi = g.hi[i];
+            const bool ex = route_exotic(i);
+            int n = 0;
+            bool queued = false;
+            int64_t score = kNegInf64;
+            if (t < a.T && !ex && hi > lo) {
+                if (!overflow) {
+                    list_window_range_shifted<kShift>(s_list + tid, bd, cur_a, cur_b, g.plo[i], g.phi[i], true);
+                    n = cur_b - cur_a;
+                    queued = n > 2;
+                } else if (kGen) {
+                    bail_window(w);
+                } else {
+                    walk_dp_unit<int32_t>(LdgU32(), LdgPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus, a.penalty,
+                                          a.max_mm, n, score);
+                }
+            }
+            // warp-aggregated append of (column, window, first entry, length)
+            const uint32_t qm = __ballot_sync(0xffffffffu, queued);
+            if (qm) {
+                const int lane = tid & 31;
+                int basei = 0;
+                if (lane == __ffs(qm) - 1) basei = atomicAdd(&g.n_work, __popc(qm));
+                basei = __shfl_sync(0xffffffffu, basei, __ffs(qm) - 1);
+                if (queued)
+                    s_work[basei + __popc(qm & ((1u << lane) - 1u))] =
+                        (uint32_t)tid | ((uint32_t)i << 7) | ((uint32_t)cur_a << 11) | ((uint32_t)n << 21);
+            }
+            if (t < a.T && !ex) {
+                const size_t o = (size_t)w * a.T + t;
+                if (!queued) a.score[o] = score;  // NaN (n <= 2, empty window) or the overflow column's score
+                a.nsnp[o] = (hi - lo) - g.nabs[i] + n;
+            }
+        }
+        __syncthreads();
+        const int n_work = g.n_work;
+        for (int u = tid; u < n_work; u += bd) {
+            const uint32_t e = s_work[u];
+            const int col = e & 127, i = (e >> 7) & 15, ua = (e >> 11) & 1023, n = e >> 21;
+            int64_t score;
+            if (!kGen) score = list_dp_run(s_list + col + ua * bd, bd, n, a.bonus, c.pen_eff);
+            else if (!list_dp_run_general(s_list + col + ua * bd, bd, n, a.bonus, a.penalty, a.max_mm, score)) {
+                bail_window(w0 + i);
+                continue;
+            }
+            a.score[(size_t)(w0 + i) * a.T + chunk * bd + col] = score;
+        }
+        return;
+    }
+
+    // ---- direct path (a single window, or window ends that do not ascend)
+    int cur = 0;
+    for (int i = 0; i < nwin; ++i) {
+        const int w = w0 + i;
+        if (route_exotic(i) || t >= a.T) continue;
+        const int32_t lo = g.lo[i], hi = g.hi[i];
+        int n = 0;
+        int64_t score = kNegInf64;
+        if (hi > lo) {
+            if (overflow) {
+                if (kGen) { bail_window(w); continue; }
+                walk_dp_unit<int32_t>(LdgU32(), LdgPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus, a.penalty,
+                                      a.max_mm, n, score);
+            } else {
+                int b = cur;
+                list_window_range_shifted<kShift>(s_list + tid, bd, cur, b, g.plo[i], g.phi[i], false);
+                n = b - cur;
+                if (n > 2) {
+                    if (!kGen) score = list_dp_run(s_list + tid + cur * bd, bd, n, a.bonus, c.pen_eff);
+                    else if (!list_dp_run_general(s_list + tid + cur * bd, bd, n, a.bonus, a.penalty, a.max_mm, score)) {
+                        bail_window(w);
+                        continue;
+                    }
+                }
+            }
+        }
+        const size_t o = (size_t)w * a.T + t;
+        a.score[o] = score;
+        a.nsnp[o] = (hi - lo) - g.nabs[i] + n;
+    }
+}
+
+// the general instantiation lives out of line: it is rare, and its per-class tables must not
+// cost the common kernel body registers or stack
+__device__ __noinline__ void group_body_general(const ScoreArgs &a, const GroupCtx &c) { group_body<true>(a, c); }
+
 // grid.x = tchunks * ngroups; dynamic smem: list [L + 1][bd] | max(positions [words_cap*32], worklist [wg*bd])
 __global__ void __launch_bounds__(kScoreMaxThreads)
 score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words_cap) {
@@ -52,7 +231,6 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
     // they share one region (a barrier separates the two phases)
     uint32_t *s_list = reinterpret_cast<uint32_t *>(dyn);
     uint32_t *s_pos = s_list + (size_t)(L + 1) * bd;  // row L of the list area is the spill slot
-    uint32_t *s_work = s_pos;                         // [wg * bd] unit worklist, after the lists are built
 
     pdl_wait();  // bit-planes and window bounds come from the prep launch
     if (tid < nwin) {
@@ -119,163 +297,16 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
         }
         __syncthreads();
 
-        // Windows holding genotypes outside {0,1,2} (missing calls, multi-allelic sites): the whole
-        // group switches to general entries (relative position << 8 | genotype byte, fetched from
-        // the target matrix) and the per-class DP of dp_core.cuh.  Only when the group spans more
-        // than 2^23 bp do such windows go to the pairwise kernel instead.
+        // Windows holding genotypes outside {0,1,2}: the whole group takes the general body.  Only
+        // when the group spans more than 2^23 bp do such windows go to the pairwise kernel.
         bool any_ex = false;
         for (int i = 0; i < nwin; ++i) any_ex = any_ex || g.ex[i] != 0;
-        const bool gen = any_ex && span < (int64_t(1) << kGeneralPosBits);
-
-        // this thread's column: plane words -> site list.  Shared memory is addressed with 32-bit
-        // shared-window addresses (ld/st.shared) and the write cursor is clamped to a spill slot
-        // (index L) instead of branching on overflow.
-        int cnt = 0;
-        if (t < a.T) {
-            const uint32_t *cp = a.carried + (size_t)gi0 * a.Tp + t;
-            const uint32_t *tp = a.two + (size_t)gi0 * a.Tp + t;
-            const uint32_t first_mask = 0xffffffffu << (rlo & 31);
-            const uint32_t last_mask = 0xffffffffu >> (31 - ((rhi - 1) & 31));
-            const uint32_t pos_addr = (uint32_t)__cvta_generic_to_shared(s_pos);
-            const uint32_t step = (uint32_t)bd * 4u;
-            uint32_t w_addr = (uint32_t)__cvta_generic_to_shared(s_list + tid);
-            const uint32_t w_end = w_addr + (uint32_t)L * step;  // the spill slot
-            for (int jb = 0; jb < nwr; jb += 4) {
-                uint32_t cw[4], tw[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) cw[u] = (jb + u < nwr) ? __ldg(cp + (size_t)(jb + u) * a.Tp) : 0u;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (jb + u == 0) cw[u] &= first_mask;
-                    if (jb + u == nwr - 1) cw[u] &= last_mask;
-                    tw[u] = (jb + u < nwr) ? __ldg(tp + (size_t)(jb + u) * a.Tp) : 0u;  // not chained to cw
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint32_t c = cw[u];
-                    const uint32_t sp = pos_addr + ((uint32_t)(jb + u) << 7);
-                    cnt += __popc(c);
-                    while (c) {
-                        const int b = __ffs(c) - 1;
-                        c &= c - 1;
-                        uint32_t rel;
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rel) : "r"(sp + 4u * (uint32_t)b));
-                        uint32_t e = (rel << 1) | ((tw[u] >> b) & 1u);
-                        if (gen) {
-                            const int8_t gb = a.tgt[(size_t)(base + ((jb + u) << 5) + b) * a.T + t];
-                            e = (rel << 8) | (uint32_t)(uint8_t)gb;
-                        }
-                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(w_addr), "r"(e) : "memory");
-                        w_addr = min(w_addr + step, w_end);
-                    }
-                }
-            }
-        }
-        const bool overflow = cnt >= L;  // one slot is the terminator
-        if (t < a.T && !overflow) s_list[cnt * bd + tid] = kListSentinel;
-        if (tid == 0) g.n_work = 0;
-        __syncthreads();       // every list is built: the position tile becomes the worklist
-
-        // a unit the general DP cannot take (more than kMaxClasses genotype values, or its column
-        // overflowed the list): its window goes to the pairwise kernel, queued once
-        auto bail_window = [&](int w) {
-            if (atomicExch(&a.win_bail[w], 1u) == 0u)
-                a.slow_list[a.w_begin + atomicAdd(&a.hdr->n_slow[a.slot], 1)] = w;
-        };
-
-        if (nwin > 1 && mono_hi) {
-            // ---- balanced path.  Pass 1, one thread per column: both list cursors only move
-            // forward, so locating every window's run [a, a + n) costs O(list length); units with
-            // n <= 2 are NaN and finished here (most units of sparse haplotype data), the others
-            // are queued.  Pass 2: the CTA's threads share the queued units evenly, so a warp's DP
-            // loop no longer runs for the longest of 32 unrelated columns in every window.
-            int cur_a = 0, cur_b = 0;
-            for (int i = 0; i < nwin; ++i) {
-                const int w = w0 + i;
-                const int32_t lo = g.lo[i], hi = g.hi[i];
-                const bool ex = !gen && g.ex[i] != 0;  // not representable here: pairwise kernel
-                if (ex && chunk == 0 && tid == 0) a.slow_list[a.w_begin + atomicAdd(&a.hdr->n_slow[a.slot], 1)] = w;
-                int n = 0;
-                bool queued = false;
-                int64_t score = kNegInf64;
-                if (t < a.T && !ex && hi > lo) {
-                    if (!overflow) {
-                        if (gen) list_window_range_shifted<8>(s_list + tid, bd, cur_a, cur_b, g.plo[i], g.phi[i], true);
-                        else     list_window_range_shifted<1>(s_list + tid, bd, cur_a, cur_b, g.plo[i], g.phi[i], true);
-                        n = cur_b - cur_a;
-                        queued = n > 2;
-                    } else if (gen) {
-                        bail_window(w);
-                    } else {
-                        walk_dp_unit<int32_t>(LdgU32(), LdgPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus,
-                                              a.penalty, a.max_mm, n, score);
-                    }
-                }
-                // warp-aggregated append of (column, window, first entry, length)
-                const uint32_t qm = __ballot_sync(0xffffffffu, queued);
-                if (qm) {
-                    const int lane = tid & 31;
-                    int basei = 0;
-                    if (lane == __ffs(qm) - 1) basei = atomicAdd(&g.n_work, __popc(qm));
-                    basei = __shfl_sync(0xffffffffu, basei, __ffs(qm) - 1);
-                    if (queued)
-                        s_work[basei + __popc(qm & ((1u << lane) - 1u))] =
-                            (uint32_t)tid | ((uint32_t)i << 7) | ((uint32_t)cur_a << 11) | ((uint32_t)n << 21);
-                }
-                if (t < a.T && !ex) {
-                    const size_t o = (size_t)w * a.T + t;
-                    if (!queued) a.score[o] = score;  // NaN (n <= 2, empty window) or the overflow column's score
-                    a.nsnp[o] = (hi - lo) - g.nabs[i] + n;
-                }
-            }
-            __syncthreads();
-            const int n_work = g.n_work;
-            for (int u = tid; u < n_work; u += bd) {
-                const uint32_t e = s_work[u];
-                const int col = e & 127, i = (e >> 7) & 15, ua = (e >> 11) & 1023, n = e >> 21;
-                int64_t score;
-                if (!gen) score = list_dp_run(s_list + col + ua * bd, bd, n, a.bonus, pen_eff);
-                else if (!list_dp_run_general(s_list + col + ua * bd, bd, n, a.bonus, a.penalty, a.max_mm, score)) {
-                    bail_window(w0 + i);
-                    continue;
-                }
-                a.score[(size_t)(w0 + i) * a.T + chunk * bd + col] = score;
-            }
-            return;
-        }
-
-        if (t >= a.T) return;  // no block-wide barrier below this point
-        int cur = 0;
-        for (int i = 0; i < nwin; ++i) {
-            const int w = w0 + i;
-            if (!gen && g.ex[i]) {  // not representable here: the whole window goes to the pairwise kernel
-                if (chunk == 0 && tid == 0) a.slow_list[a.w_begin + atomicAdd(&a.hdr->n_slow[a.slot], 1)] = w;
-                continue;
-            }
-            const int32_t lo = g.lo[i], hi = g.hi[i];
-            int n = 0;
-            int64_t score = kNegInf64;
-            if (hi > lo) {
-                if (overflow) {
-                    if (gen) { bail_window(w); continue; }
-                    walk_dp_unit<int32_t>(LdgU32(), LdgPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus,
-                                          a.penalty, a.max_mm, n, score);
-                } else if (!gen) {
-                    list_dp_window(s_list + tid, bd, cur, g.plo[i], g.phi[i], a.bonus, pen_eff, n, score);
-                } else {
-                    int b = cur;
-                    list_window_range_shifted<8>(s_list + tid, bd, cur, b, g.plo[i], g.phi[i], false);
-                    n = b - cur;
-                    if (n > 2 && !list_dp_run_general(s_list + tid + cur * bd, bd, n, a.bonus, a.penalty, a.max_mm, score)) {
-                        bail_window(w);
-                        continue;
-                    }
-                }
-            }
-            const size_t o = (size_t)w * a.T + t;
-            a.score[o] = score;
-            a.nsnp[o] = (hi - lo) - g.nabs[i] + n;
-        }
+        GroupCtx c;
+        c.g = &g; c.s_list = s_list; c.s_pos = s_pos;
+        c.tid = tid; c.bd = bd; c.chunk = chunk; c.t = t; c.w0 = w0; c.nwin = nwin; c.L = L;
+        c.rlo = rlo; c.rhi = rhi; c.gi0 = gi0; c.nwr = nwr; c.pen_eff = pen_eff; c.mono_hi = mono_hi;
+        if (any_ex && span < (int64_t(1) << kGeneralPosBits)) group_body_general(a, c);
+        else group_body<false>(a, c);
         return;
     }
 
