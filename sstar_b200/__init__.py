@@ -10,6 +10,7 @@ Only what the hot path needs lives here:
 * ``generators``                  window tiling                                  (generators/window_data_generator.py:30)
 * ``mp_manager``                  seam S2, GPU-sharded scheduler                 (mp_manager.py:98)
 * ``preprocess``                  seam S1, ``preprocess(vcf_file, ...)`` -> TSV  (preprocess.py:28)
+* ``simulate`` / ``msprime_simulator`` / ``simulate_batch``  the train-path tiler, replicate-batched (simulate.py:30)
 """
 __version__ = "0.1.0"
 

@@ -64,43 +64,41 @@ class FeatureTable:
         return (ok(self.win_start) and ok(self.win_end) and np.issubdtype(rep.dtype, np.integer) and ok(rep)
                 and len(str(self.chr_name).encode()) < 64)
 
-    def to_tsv(self, path, header: bool = True, mode: str = "w", device=None, col_order=None) -> None:
-        """Byte-identical to the reference's ``pd.DataFrame(rows).to_csv(sep='\\t', na_rep='NA')``.
+    def tsv_body(self, device=None, col_order=None) -> bytes:
+        """The rows as TSV text (no header), byte-identical to the reference's
+        ``pd.DataFrame(rows).to_csv(sep='\\t', na_rep='NA')``.
 
         ``device`` (a CUDA device index) formats the rows with the device emitter
         (``sstar_b200_format_tsv``); ``None`` formats them in Python.  ``col_order`` permutes the
         rows inside each window (the simulate path sorts rows by sample name)."""
-        out_dir = os.path.dirname(str(path))
-        if out_dir:
-            os.makedirs(out_dir, exist_ok=True)
         W, T = self.score.shape
         chrom = str(self.chr_name)
-        cols = COLUMNS + (["Replicate"] if self.replicate is not None else [])
         order = list(range(T)) if col_order is None else [int(c) for c in col_order]
-        body = None
         if device is not None and W > 0 and self._int32_table():
             from .engine import get_engine
             body = get_engine(device).format_tsv_host(self.score, self.nsnp, self.win_start, self.win_end, chrom,
                                                       self.labels, self.replicate, col_order)
-        if body is not None:
-            with open(path, mode + "b") as fh:
-                if header:
-                    fh.write(("\t".join(cols) + "\n").encode())
-                fh.write(body)
-            return
-        with open(path, mode) as fh:
+            if body is not None:
+                return bytes(body)
+        parts = []
+        for w in range(W):
+            head = f"{chrom}\t{int(self.win_start[w])}\t{int(self.win_end[w])}\t"
+            tail = "\n" if self.replicate is None else f"\t{self.replicate[w]}\n"
+            sc, ns = self.score[w].tolist(), self.nsnp[w].tolist()
+            parts.extend(
+                f"{head}{self.labels[t]}\tNA\t{ns[t]}{tail}" if sc[t] == NAN_SENTINEL
+                else f"{head}{self.labels[t]}\t{float(sc[t])!r}\t{ns[t]}{tail}"
+                for t in order)
+        return "".join(parts).encode()
+
+    def to_tsv(self, path, header: bool = True, mode: str = "w", device=None, col_order=None) -> None:
+        """Write the table (see :meth:`tsv_body`), creating the output directory like the reference
+        does (sstar/preprocess.py:119-121)."""
+        out_dir = os.path.dirname(str(path))
+        if out_dir:
+            os.makedirs(out_dir, exist_ok=True)
+        cols = COLUMNS + (["Replicate"] if self.replicate is not None else [])
+        with open(path, mode + "b") as fh:
             if header:
-                fh.write("\t".join(cols) + "\n")
-            block = 4096
-            for w0 in range(0, W, block):
-                w1 = min(W, w0 + block)
-                parts = []
-                for w in range(w0, w1):
-                    head = f"{chrom}\t{int(self.win_start[w])}\t{int(self.win_end[w])}\t"
-                    tail = "\n" if self.replicate is None else f"\t{self.replicate[w]}\n"
-                    sc, ns = self.score[w].tolist(), self.nsnp[w].tolist()
-                    parts.extend(
-                        f"{head}{self.labels[t]}\tNA\t{ns[t]}{tail}" if sc[t] == NAN_SENTINEL
-                        else f"{head}{self.labels[t]}\t{float(sc[t])!r}\t{ns[t]}{tail}"
-                        for t in order)
-                fh.write("".join(parts))
+                fh.write(("\t".join(cols) + "\n").encode())
+            fh.write(self.tsv_body(device=device, col_order=col_order))

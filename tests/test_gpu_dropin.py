@@ -231,3 +231,37 @@ def test_preprocess_device_route_errors(tmp_path):
     (tmp_path / "none.list").write_text("nobody\n")
     with pytest.raises(ValueError, match="No shared variant positions"):
         preprocess(vcf_file=vcf, chr_name="9", **{**kw, "ref_ind_file": str(tmp_path / "none.list")})
+
+
+# ---- simulate(): replicates scored in one device call, rows printed by
+# the device emitter, against the reference's logic restated with row dicts + the oracle
+@pytest.mark.parametrize("is_phased,is_shuffled", [(False, False), (True, True)])
+def test_simulate_device_path_matches_reference_logic(tmp_path, monkeypatch, is_phased, is_shuffled):
+    import test_simulate_host as host
+    import sstar_b200.msprime_simulator as ms
+    from sstar_b200.simulate import simulate
+    monkeypatch.setattr(ms.MsprimeSimulator, "simulate_replicate",
+                        lambda self, rep=None, seed=None: host._fake_replicate(rep, seed, self.nref, self.ntgt,
+                                                                               self.ploidy, self.seq_len))
+    kw = dict(demo_model_file="unused.yaml", nrep=9, nref=3, ntgt=12, ref_id="Ref", tgt_id="Tgt", ploidy=2,
+              seq_len=50_000, mut_rate=1e-8, rec_rate=1e-8, match_bonus=5000, max_mismatch=5,
+              mismatch_penalty=-10000, output_dir=str(tmp_path / "out"), output_prefix="t", nfeature=400,
+              is_phased=is_phased, is_shuffled=is_shuffled, keep_sim_data=False, seed=77, nprocess=1)
+    simulate(**kw)
+    got = open(tmp_path / "out" / "t.training.features.tsv").read()
+
+    class OracleSim(ms.MsprimeSimulator):   # scoring by the oracle, one replicate at a time
+        def score_batch(self, replicates, reps):
+            from sstar_b200.feature_table import FeatureTable, sample_labels
+            from sstar_b200.simulate_batch import build_feature_input, sample_names
+            sc, ns = [], []
+            for pos, gts in replicates:
+                r, t, p, s, e = build_feature_input(pos, gts, self.nref, self.ntgt, self.ploidy, self.seq_len, self.is_phased)
+                so, no = c_oracle.score_windows(r, t, p, [s], [e])
+                sc.append(so[0]); ns.append(no[0])
+            labels = sample_labels(sample_names(self.nref, self.ntgt)[1], self.ploidy, self.is_phased)
+            return FeatureTable("1", [1] * len(reps), [self.seq_len] * len(reps), labels, np.stack(sc), np.stack(ns),
+                                replicate=list(reps))
+    sim = OracleSim("unused.yaml", 3, 12, "Ref", "Tgt", 2, 50_000, 1e-8, 1e-8, "t", kw["output_dir"], is_phased,
+                    5000, 5, -10000)
+    assert got == host._reference_logic(sim, 9, 400, 77, is_shuffled)
