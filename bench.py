@@ -44,7 +44,6 @@ WORKLOADS = {
                  "(R = T = 1000 columns), 50 kb / 10 kb"),
     "c4-shard": (30_000_000, 100, 2000, False, 50_000, 10_000,
                  "C4 shard: 30 Mb, 100 ref + 2000 target diploids (unphased), 50 kb / 10 kb"),
-    "c5": (0, 5, 10, False, 50_000, 50_000, "C5 (see bench_large.py)"),
 }
 LARGE = {"c3-shard", "c4-shard"}
 
@@ -102,13 +101,32 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic(workload, kernel):
-    """DRAM bytes per launch from the committed ncu --set full capture, if any."""
+def recorded_traffic(workload, kernel, key="dram_bytes"):
+    """Per-launch counters from the committed ncu --set full capture (profiles/traffic.json), if any:
+    ``dram_bytes`` = dram__bytes_read.sum + dram__bytes_write.sum, ``warp_inst`` = smsp__inst_executed.sum."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            return json.load(fh).get(workload, {}).get(kernel)
+            rec = json.load(fh).get(workload, {}).get(kernel)
+        if isinstance(rec, dict):
+            return rec.get(key)
+        return rec if key == "dram_bytes" else None
     except Exception:
         return None
+
+
+def issue_peak_ginst():
+    """Warp instructions per second the SMs can issue: SMs x 4 schedulers x max SM clock."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            mhz = float(json.load(fh)["sm_max_mhz"])
+    except Exception:
+        mhz = 1965.0
+    try:
+        import torch
+        sms = torch.cuda.get_device_properties(0).multi_processor_count
+    except Exception:
+        sms = 148
+    return sms * 4 * mhz * 1e6 / 1e9, sms, mhz
 
 
 class ClockSampler(threading.Thread):
@@ -303,6 +321,12 @@ def roofline_block(name, st, k, tot_ms, pack_ms, score_ms, launches):
         out = {"kernel": kname, "ms": ms / k, "algorithmic_bytes": nbytes,
                "achieved": nbytes / (ms / k * 1e-3) / 1e9, "frac": nbytes / (ms / k * 1e-3) / 1e9 / peak,
                "traffic": recorded_traffic(name, kname)}
+        winst = recorded_traffic(name, kname, "warp_inst")
+        if winst:  # issue-slot view: executed warp instructions (ncu) over the live-measured duration
+            ipeak, sms, mhz = issue_peak_ginst()
+            out["issue"] = {"warp_inst": winst, "achieved": winst / (ms / k * 1e-3) / 1e9, "peak": ipeak,
+                            "unit": "G warp-inst/s", "frac": winst / (ms / k * 1e-3) / 1e9 / ipeak,
+                            "peak_source": f"{sms} SMs x 4 schedulers x {mhz:.0f} MHz"}
         if note:
             out["note"] = note
         return out

@@ -244,15 +244,19 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
     __syncthreads();
 
     // the group's union variant range [rlo, rhi) over its non-empty windows
-    int32_t rlo = INT32_MAX, rhi = -1, prev_lo = -1, prev_hi = -1, maxnv = 0, p0 = 0, plast = INT32_MIN;
+    int32_t rlo = INT32_MAX, rhi = -1, prev_lo = -1, prev_hi = -1, prev_pfirst = INT32_MIN, maxnv = 0, p0 = 0,
+            plast = INT32_MIN;
     bool mono = true, mono_hi = true;
     for (int i = 0; i < nwin; ++i) {
         const int32_t lo = g.lo[i], hi = g.hi[i];
         if (hi > lo) {
-            mono = mono && lo >= prev_lo;
+            // windows of one group must ascend in variant index AND in position (replicates
+            // concatenated along the variant axis restart their positions: never grouped)
+            mono = mono && lo >= prev_lo && g.pfirst[i] >= prev_pfirst && g.plast[i] >= g.pfirst[i];
             mono_hi = mono_hi && hi >= prev_hi;
             prev_lo = lo;
             prev_hi = hi;
+            prev_pfirst = g.pfirst[i];
             if (lo < rlo) { rlo = lo; p0 = g.pfirst[i]; }
             rhi = max(rhi, hi);
             plast = max(plast, g.plast[i]);

@@ -192,6 +192,7 @@ struct ScoreCall {
     uint8_t *ws;
     int algo;
     int32_t max_win_variants;
+    bool disjoint;  // every window is its own replicate (positions restart): one window per CTA
 };
 
 // Scores windows [w_begin, w_end) (bounds and planes must be in the workspace): the grouped
@@ -236,6 +237,7 @@ int launch_score(cudaStream_t st, const ScoreCall &c, const WsLayout &L, int32_t
             if (fit < wg) wg = fit < 1 ? 1 : fit;
         }
         while (wg > 1 && (int64_t)((W + wg - 1) / wg) * tchunks < 4 * kNumSM) wg >>= 1;
+        if (c.disjoint) wg = 1;  // replicates share no variants (and their positions restart)
         const int64_t ngroups = (W + wg - 1) / wg;
         if (ngroups * tchunks > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "too many (window group, column chunk) tiles%s");
         const int Lslots = kScoreListBytes / (bd * 4) - 1;  // list slots per column (one more row is the spill slot)
@@ -297,7 +299,8 @@ int run_pipeline(int device, cudaStream_t st, bool do_pack, const int8_t *d_ref,
     int rc = launch_prep(st, 0, do_pack ? L.G : 0, d_ref, d_tgt, V, R, T, d_pos, d_ws, d_we, d_seg, fixed_s, fixed_e, W,
                          ws, L);
     if (rc) return rc;
-    const ScoreCall c = {d_tgt, d_pos, V, T, bonus, max_mm, penalty, d_score, d_nsnp, ws, algo, max_win_variants};
+    const ScoreCall c = {d_tgt, d_pos, V, T, bonus, max_mm, penalty, d_score, d_nsnp, ws, algo, max_win_variants,
+                         d_seg != nullptr};
     return launch_score(st, c, L, 0, W, 0);
 }
 
@@ -573,7 +576,8 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
     if (rc) return rc;
     int64_t *o_score = copy_out ? (int64_t *)(d + h.off_score) : (int64_t *)m_score;
     int32_t *o_nsnp = copy_out ? (int32_t *)(d + h.off_nsnp) : (int32_t *)m_nsnp;
-    const ScoreCall c = {d_tgt, d_pos, V, T, match_bonus, max_mismatch, mismatch_penalty, o_score, o_nsnp, ws, algo, hint};
+    const ScoreCall c = {d_tgt, d_pos, V, T, match_bonus, max_mismatch, mismatch_penalty, o_score, o_nsnp, ws, algo, hint,
+                         false};
     int32_t w_done = 0;
     for (int k = 0; k < nchunks; ++k) {
         const int64_t r0 = (int64_t)k * rows_per, r1 = (r0 + rows_per < V) ? r0 + rows_per : V;

@@ -74,7 +74,7 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
         for (int i = 0; i < nwin; ++i) {
             const int32_t lo = wlo[w0 + i], hi = whi[w0 + i];
             if (hi > lo) {
-                mono = mono && lo >= prev_lo;
+                mono = mono && lo >= prev_lo;  // (positions ascend globally in this harness)
                 mono_hi = mono_hi && hi >= prev_hi;
                 prev_lo = lo; prev_hi = hi;
                 rlo = std::min(rlo, lo); rhi = std::max(rhi, hi); maxnv = std::max(maxnv, hi - lo);

@@ -265,3 +265,21 @@ def test_simulate_device_path_matches_reference_logic(tmp_path, monkeypatch, is_
     sim = OracleSim("unused.yaml", 3, 12, "Ref", "Tgt", 2, 50_000, 1e-8, 1e-8, "t", kw["output_dir"], is_phased,
                     5000, 5, -10000)
     assert got == host._reference_logic(sim, 9, 400, 77, is_shuffled)
+
+
+def test_many_replicates_one_call():
+    # thousands of replicates in one batch (BASELINE config 5 shape): positions restart in every
+    # replicate, so windows of different replicates must never share a list
+    from sstar_b200.engine import get_engine
+    from sstar_b200.synth import synth_chromosome
+    L, n_rep = 50_000, 3000
+    ref, tgt, pos = synth_chromosome(L * n_rep, 5, 10, False, seed=9)
+    rep_id = (pos.astype(np.int64) - 1) // L
+    off = np.searchsorted(rep_id, np.arange(n_rep + 1)).astype(np.int32)
+    pos_local = ((pos.astype(np.int64) - 1) % L + 1).astype(np.int32)
+    s, n = get_engine(0).score_replicates_host(ref, tgt, pos_local, off, 1, L)
+    assert s.shape == (n_rep, 10)
+    for r in np.unique(np.linspace(0, n_rep - 1, 150).astype(int)):
+        a, b = off[r], off[r + 1]
+        so, no = c_oracle.score_windows(ref[a:b], tgt[a:b], pos_local[a:b], [1], [L])
+        assert np.array_equal(s[r], so[0]) and np.array_equal(n[r], no[0]), r
