@@ -212,3 +212,38 @@ def test_host_entry_zero_copy_and_staged_agree(eng):
                          max_win_variants=hint, staged=staged)
         assert np.array_equal(outs[0].numpy(), so), (pinned, staged)
         assert np.array_equal(outs[1].numpy(), no), (pinned, staged)
+
+
+def test_large_shape_properties(eng):
+    # a C3-like shard (R = T = 1000 haplotype columns, ~34k variants, ~800 windows): too big for the
+    # oracle as a whole, so check it through properties that do not depend on size, plus samples
+    import torch
+    from sstar_b200.synth import regular_windows, synth_chromosome_device
+    dev = torch.device("cuda", 0)
+    r, t, p = synth_chromosome_device(torch, dev, 8_000_000, 500, 500, True, seed=99)
+    ref, tgt, pos = r.cpu().numpy(), t.cpu().numpy(), p.cpu().numpy()
+    ws, we = regular_windows(pos, 50_000, 10_000)
+    W = len(ws)
+    s, n = eng.score_host(ref, tgt, pos, ws, we)
+    assert s.shape == (W, 1000) and W > 700
+    # (a) any split of the window list gives the same rows
+    h = W // 2 + 3
+    s1, n1 = eng.score_host(ref, tgt, pos, ws[:h], we[:h])
+    s2, n2 = eng.score_host(ref, tgt, pos, ws[h:], we[h:])
+    assert np.array_equal(np.concatenate([s1, s2]), s) and np.array_equal(np.concatenate([n1, n2]), n)
+    # (b) target columns are independent of each other
+    sc, nc = eng.score_host(ref, tgt[:, 5::7], pos, ws, we)
+    assert np.array_equal(sc, s[:, 5::7]) and np.array_equal(nc, n[:, 5::7])
+    # (c) the literal pairwise recurrence agrees on a window sample, (d) so does the oracle
+    rng = np.random.default_rng(0)
+    sel = np.sort(rng.choice(W, size=40, replace=False))
+    sp, np_ = eng.score_host(ref, tgt, pos, ws[sel], we[sel], algo="pairwise")
+    assert np.array_equal(sp, s[sel]) and np.array_equal(np_, n[sel])
+    so, no = c_oracle.score_windows(ref, tgt, pos, ws[sel[:12]], we[sel[:12]])
+    assert np.array_equal(so, s[sel[:12]]) and np.array_equal(no, n[sel[:12]])
+    # (e) shifting every position by a constant shifts nothing but the coordinates
+    s3, n3 = eng.score_host(ref, tgt, pos + 1_000_003, ws + 1_000_003, we + 1_000_003)
+    assert np.array_equal(s3, s) and np.array_equal(n3, n)
+    # (f) scores are either NaN or at least the worst single link, counts bound the carried sites
+    valid = s != NAN_SENTINEL
+    assert (s[valid] >= -10000 * 200).all() and (n >= 0).all()
