@@ -44,6 +44,22 @@ int fail(int code, const char *fmt, const char *detail = "") {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// cudaFuncSetAttribute is per device: remember, per host thread AND device, the largest dynamic
+// shared-memory size already granted to each kernel (index = current device).
+constexpr int kAttrDevices = 64;
+struct SmemGrant { size_t bytes[kAttrDevices] = {}; };
+template <typename Kernel>
+cudaError_t grant_smem(SmemGrant &g, Kernel kernel, size_t smem) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kAttrDevices) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem <= g.bytes[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) g.bytes[dev] = smem;
+    return e;
+}
+
 WsLayout make_layout(int64_t V, int32_t T, int32_t W, int32_t max_win_variants) {
     WsLayout L;
     L.G = (V + 31) / 32;
@@ -170,13 +186,10 @@ int launch_prep(cudaStream_t st, int64_t g_begin, int64_t g_end, const int8_t *d
         b.hdr = reinterpret_cast<WsHeader *>(ws);
     }
     if (n_pack + n_bounds == 0) return 0;
-    static thread_local size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaFuncSetAttribute(prep): %s", cudaGetErrorString(e));
-        smem_set = smem;
-    }
-    cudaError_t e = launch(prep_kernel, (unsigned)(n_pack + n_bounds), kPackThreads, smem, st, false, p, b, n_pack, mode);
+    static thread_local SmemGrant prep_grant;
+    cudaError_t e = grant_smem(prep_grant, prep_kernel, smem);
+    if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaFuncSetAttribute(prep): %s", cudaGetErrorString(e));
+    e = launch(prep_kernel, (unsigned)(n_pack + n_bounds), kPackThreads, smem, st, false, p, b, n_pack, mode);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "prep_kernel launch: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -243,23 +256,17 @@ int launch_score(cudaStream_t st, const ScoreCall &c, const WsLayout &L, int32_t
         const int Lslots = kScoreListBytes / (bd * 4) - 1;  // list slots per column (one more row is the spill slot)
         const size_t ring_b = (size_t)wg * bd * 4, pos_b = (size_t)words_cap * 32 * 4;  // worklist | position tile
         const size_t smem = (size_t)(Lslots + 1) * bd * 4 + (ring_b > pos_b ? ring_b : pos_b);  // +1: spill slot
-        static thread_local size_t k2_smem_set = 0;
-        if (smem > k2_smem_set) {
-            cudaError_t e = cudaFuncSetAttribute(score_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaFuncSetAttribute(score_group): %s", cudaGetErrorString(e));
-            k2_smem_set = smem;
-        }
-        cudaError_t e = launch(score_group_kernel, (unsigned)(ngroups * tchunks), (unsigned)bd, smem, st, true, s, wg,
+        static thread_local SmemGrant group_grant;
+        cudaError_t e = grant_smem(group_grant, score_group_kernel, smem);
+        if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaFuncSetAttribute(score_group): %s", cudaGetErrorString(e));
+        e = launch(score_group_kernel, (unsigned)(ngroups * tchunks), (unsigned)bd, smem, st, true, s, wg,
                                Lslots, words_cap);
         if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "score_group_kernel launch: %s", cudaGetErrorString(e));
     }
     const size_t psmem = (size_t)kPairWarps * kPairSmemCap * 13;
-    static thread_local bool pair_attr = false;
-    if (!pair_attr) {
-        cudaError_t e = cudaFuncSetAttribute(score_pairwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
-        if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaFuncSetAttribute(pairwise): %s", cudaGetErrorString(e));
-        pair_attr = true;
-    }
+    static thread_local SmemGrant pair_grant;
+    cudaError_t ep = grant_smem(pair_grant, score_pairwise_kernel, psmem);
+    if (ep != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaFuncSetAttribute(pairwise): %s", cudaGetErrorString(ep));
     int64_t pgrid = ((int64_t)W * T + kPairWarps - 1) / kPairWarps;
     if (pgrid > kNumSM * 4) pgrid = kNumSM * 4;
     cudaError_t e = launch(score_pairwise_kernel, (unsigned)pgrid, kPairWarps * 32, psmem, st, true, s);
@@ -674,11 +681,8 @@ extern "C" int sstar_b200_format_tsv(int device, void *stream, const int64_t *d_
     const int64_t nb = (int64_t)W * a.blocks_per_win;
     if (nb > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "table too large for one emitter call%s");
     if (nb == 0) return 0;
-    static thread_local size_t emit_smem_set = 0;
-    if (smem > emit_smem_set) {
-        CUDA_TRY(cudaFuncSetAttribute(emit_format_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        emit_smem_set = smem;
-    }
+    static thread_local SmemGrant emit_grant;
+    CUDA_TRY(grant_smem(emit_grant, emit_format_kernel, smem));
     cudaError_t e = launch(emit_len_kernel, (unsigned)nb, kEmitThreads, 0, st, false, a);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "emit_len_kernel launch: %s", cudaGetErrorString(e));
     e = launch(emit_scan_kernel, 1u, 1024u, 0, st, false, a, nb);

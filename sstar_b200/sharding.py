@@ -74,12 +74,31 @@ def score_chromosome(ref_gts, tgt_gts, pos, win_start, win_end, match_bonus, max
     W, T = ws.shape[0], tgt.shape[1]
     score = np.empty((W, T), dtype=np.int64)
     nsnp = np.empty((W, T), dtype=np.int32)
-    pending = []
-    for dev, (w0, w1, k0, k1) in zip(devs, plan_window_shards(p, ws, we, len(devs))):
-        eng = get_engine(dev)
-        handle = eng.score_host_async(ref[k0:k1], tgt[k0:k1], p[k0:k1], ws[w0:w1], we[w0:w1],
-                                      match_bonus, max_mismatch, mismatch_penalty, algo=algo)
-        pending.append((w0, w1, eng, handle))
-    for w0, w1, eng, handle in pending:  # host gather, window order
-        score[w0:w1], nsnp[w0:w1] = eng.wait(handle)
+
+    # one host thread per GPU: staging a shard into pinned memory, the pipelined device call and the
+    # copy of its result block all overlap across devices (torch copies and ctypes calls release the GIL)
+    def work(dev, shard):
+        w0, w1, k0, k1 = shard
+        stream, s_pin, n_pin = get_engine(dev).score_host_async(ref[k0:k1], tgt[k0:k1], p[k0:k1], ws[w0:w1],
+                                                                we[w0:w1], match_bonus, max_mismatch,
+                                                                mismatch_penalty, algo=algo)
+        stream.synchronize()
+        score[w0:w1], nsnp[w0:w1] = s_pin.numpy(), n_pin.numpy()  # host gather, window order, one copy
+
+    shards = plan_window_shards(p, ws, we, len(devs))
+    futures = [_worker(dev).submit(work, dev, shard) for dev, shard in zip(devs, shards)]
+    for f in futures:
+        f.result()
     return score, nsnp
+
+
+_WORKERS: dict = {}
+
+
+def _worker(dev: int):
+    """A persistent single-thread executor per device (the C-ABI keeps per-thread, per-device state)."""
+    from concurrent.futures import ThreadPoolExecutor
+    ex = _WORKERS.get(dev)
+    if ex is None:
+        ex = _WORKERS[dev] = ThreadPoolExecutor(max_workers=1, thread_name_prefix=f"sstar-gpu{dev}")
+    return ex
