@@ -346,7 +346,7 @@ class ScoreEngine:
         return pin.view(*shape)
 
     def score_host_async(self, ref_gts, tgt_gts, pos, win_start, win_end, match_bonus=5000,
-                         max_mismatch=5, mismatch_penalty=-10000, algo="auto"):
+                         max_mismatch=5, mismatch_penalty=-10000, algo="auto", flags=0):
         """Enqueue one chromosome (numpy in) and return a handle for :meth:`wait`.
         One call may be in flight per engine (the pinned staging buffers are reused)."""
         torch = self.torch
@@ -373,7 +373,7 @@ class ScoreEngine:
                               self._pin_copy("ws", ws, torch.int32, (W,)),
                               self._pin_copy("we", we, torch.int32, (W,)),
                               score_h, nsnp_h, match_bonus, max_mismatch, mismatch_penalty, algo=algo,
-                              max_win_variants=hint, stream=stream, sync=False)
+                              max_win_variants=hint, stream=stream, sync=False, flags=flags)
         return (stream, score_h, nsnp_h)
 
     def wait(self, handle):
@@ -382,10 +382,10 @@ class ScoreEngine:
         return score_h.numpy().copy(), nsnp_h.numpy().copy()
 
     def score_host(self, ref_gts, tgt_gts, pos, win_start, win_end, match_bonus=5000, max_mismatch=5,
-                   mismatch_penalty=-10000, algo="auto"):
+                   mismatch_penalty=-10000, algo="auto", flags=0):
         """numpy in, numpy out: (score[W,T] int64 with NAN_SENTINEL, nsnp[W,T] int32)."""
         return self.wait(self.score_host_async(ref_gts, tgt_gts, pos, win_start, win_end, match_bonus,
-                                               max_mismatch, mismatch_penalty, algo=algo))
+                                               max_mismatch, mismatch_penalty, algo=algo, flags=flags))
 
     def score_replicates_host(self, ref_gts, tgt_gts, pos, rep_offset, win_start, win_end,
                               match_bonus=5000, max_mismatch=5, mismatch_penalty=-10000, algo="auto"):

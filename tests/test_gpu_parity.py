@@ -247,3 +247,44 @@ def test_large_shape_properties(eng):
     # (f) scores are either NaN or at least the worst single link, counts bound the carried sites
     valid = s != NAN_SENTINEL
     assert (s[valid] >= -10000 * 200).all() and (n >= 0).all()
+
+
+@pytest.mark.parametrize("n_ref,n_tgt,phased,length", [(3, 2, True, 300_000),      # T = 4
+                                                        (25, 32, True, 900_000),    # T = 64, R = 50 (R % 4 != 0)
+                                                        (8, 260, False, 700_000),   # T = 260: two item batches
+                                                        (50, 500, True, 400_000)])  # T = 1000
+def test_wide_and_narrow_panels_with_odd_genotypes(eng, n_ref, n_tgt, phased, length):
+    # column counts from 4 to 1000, reference widths that are not multiples of 4, tail rows
+    # (V % 32 != 0), missing calls and multi-allelic values, through the pipelined and the staged
+    # host entry
+    from sstar_b200 import _cabi
+    from sstar_b200.synth import regular_windows, synth_chromosome
+    ref, tgt, pos = synth_chromosome(length, n_ref, n_tgt, phased, seed=4000 + n_tgt)
+    assert tgt.shape[1] % 4 == 0
+    rng = np.random.default_rng(n_tgt)
+    tgt = tgt.copy()
+    m = rng.random(tgt.shape) < 0.003
+    tgt[m] = rng.choice([-2, -1, 3], size=int(m.sum())).astype(np.int8)
+    ref = ref.copy()
+    ref[rng.random(ref.shape) < 0.001] = -1
+    ws, we = regular_windows(pos, 50_000, 10_000)
+    so, no = c_oracle.score_windows(ref, tgt, pos, ws, we)
+    for flags in (0, _cabi.FLAG_STAGED_COPIES):
+        s, n = eng.score_host(ref, tgt, pos, ws, we, flags=flags)
+        assert np.array_equal(s, so) and np.array_equal(n, no), flags
+
+
+def test_degenerate_shapes(eng):
+    # no windows, no variants, one variant, one column, one reference column
+    z8 = lambda r, c: np.zeros((r, c), dtype=np.int8)
+    s, n = eng.score_host(z8(5, 2), np.ones((5, 3), np.int8), [1, 20, 40, 60, 80], [], [])
+    assert s.shape == (0, 3) and n.shape == (0, 3)
+    s, n = eng.score_host(z8(0, 2), z8(0, 3), [], [1, 50], [100, 60])
+    assert (s == NAN_SENTINEL).all() and (n == 0).all() and s.shape == (2, 3)
+    s, n = eng.score_host(z8(1, 1), np.ones((1, 1), np.int8), [7], [1, 7, 8], [10, 7, 9])
+    assert (s == NAN_SENTINEL).all() and n[:, 0].tolist() == [1, 1, 0]
+    pos = np.arange(10, 400, 30)
+    tgt = np.ones((len(pos), 1), np.int8)
+    so, no = c_oracle.score_windows(z8(len(pos), 1), tgt, pos, [1], [1000])
+    s, n = eng.score_host(z8(len(pos), 1), tgt, pos, [1], [1000])
+    assert np.array_equal(s, so) and np.array_equal(n, no) and s[0, 0] == (pos[-1] - pos[0]) + 5000 * (len(pos) - 1)
