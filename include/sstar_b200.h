@@ -172,6 +172,30 @@ int sstar_b200_format_tsv(int device, void *stream, const int64_t *d_score, cons
                           const int32_t *d_col_order, char *d_out, size_t out_capacity,
                           void *d_workspace, size_t workspace_bytes);
 
+/* The same emitter with options: row order and the prediction step of `sstar2 infer`.
+ * replaces: sstar/quantile_regression.py:108-135 -- the Predicted_S*_score column (NA where the
+ *           score is NA), rows sorted by (Sample, Chromosome, Start, End), and the BED file of the
+ *           units whose observed score exceeds the predicted one (Start - 1, no header).
+ * The model has ONE integer feature (Region_ind_SNP_number), so the caller evaluates it once per
+ * distinct value on the host and passes the table: entry v holds the prediction for feature
+ * value v (values beyond n_pred - 1 use the last entry).
+ * max_tsv_bytes for a table with predictions: sstar_b200_tsv_max_bytes(...) + W*T*(1 + max_pred_len). */
+typedef struct sstar_b200_table_options {
+    int32_t mode;               /* 0: feature rows (+ prediction column when d_pred_text), 1: BED rows */
+    int32_t sample_major;       /* 0: rows in (window, sample) order, 1: (sample, window) order */
+    const double *d_pred_value; /* [n_pred] predictions (device), or NULL */
+    const char *d_pred_text;    /* their decimal text, concatenated (device); mode 0 only */
+    const int32_t *d_pred_off;  /* [n_pred + 1] (device) */
+    int32_t n_pred;
+    int32_t max_pred_len;
+} sstar_b200_table_options;
+int sstar_b200_format_table(int device, void *stream, const int64_t *d_score, const int32_t *d_nsnp,
+                            const int32_t *d_win_start, const int32_t *d_win_end, int32_t W, int32_t T,
+                            const char *chrom, const char *d_labels, const int32_t *d_label_off,
+                            int32_t max_label_len, const int32_t *d_replicate,
+                            const int32_t *d_col_order, const sstar_b200_table_options *topts,
+                            char *d_out, size_t out_capacity, void *d_workspace, size_t workspace_bytes);
+
 /* Native VCF scanner (host code, multi-threaded; plain text or gzip).
  * replaces: allel.read_vcf(vcf, alt_number=1, samples=..., region=chr_name) as used by
  *           read_geno_data (sstar/utils/utils.py:80-109) -- scikit-allel is an un-vendored dependency.

@@ -22,6 +22,12 @@ class Options(ctypes.Structure):
                 ("flags", ctypes.c_int32), ("reserved", ctypes.c_int32 * 5)]
 
 
+class TableOptions(ctypes.Structure):
+    _fields_ = [("mode", ctypes.c_int32), ("sample_major", ctypes.c_int32), ("d_pred_value", ctypes.c_void_p),
+                ("d_pred_text", ctypes.c_void_p), ("d_pred_off", ctypes.c_void_p), ("n_pred", ctypes.c_int32),
+                ("max_pred_len", ctypes.c_int32)]
+
+
 FLAG_STAGED_COPIES = 1
 
 
@@ -68,6 +74,8 @@ SIGNATURES = {
                                      _vp, _vp, _vp, _vp, _sz]),
     "sstar_b200_tsv_max_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "sstar_b200_tsv_workspace_bytes": (_sz, [_i32, _i32]),
+    "sstar_b200_format_table": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _c.c_char_p, _vp, _vp,
+                                           _i32, _vp, _vp, _c.POINTER(TableOptions), _vp, _sz, _vp, _sz]),
     "sstar_b200_format_tsv": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _c.c_char_p, _vp, _vp,
                                          _i32, _vp, _vp, _vp, _sz, _vp, _sz]),
 }

@@ -29,7 +29,16 @@ struct EmitArgs {
     const int32_t *col_order;  // [T] row k of a window shows column col_order[k]; null = identity
     const char *labels;        // sample labels, concatenated
     const int32_t *label_off;  // [T + 1]
-    int32_t W, T, blocks_per_win, row_cap;  // row_cap: shared-memory bytes reserved per row
+    // optional prediction columns (sstar/quantile_regression.py:108-135): entry v of the table
+    // belongs to Region_ind_SNP_number == v (clamped to n_pred - 1)
+    const char *pred_text;      // decimal text of the predictions, concatenated; null = no such column
+    const int32_t *pred_off;    // [n_pred + 1]
+    const double *pred_value;   // [n_pred]
+    int32_t n_pred;
+    int32_t mode;        // 0: feature rows (+ prediction column when pred_text), 1: BED rows of the units
+                         //    whose score exceeds the prediction: chrom, start - 1, end, sample
+    int32_t sample_major;  // 0: rows ordered (window, sample k), 1: (sample k, window)
+    int32_t W, T, blocks_per_win, row_cap;  // blocks_per_win: blocks per OUTER index; row_cap: smem bytes per row
     int32_t chrom_len;
     char chrom[64];
     int64_t *block_base;  // [W * blocks_per_win]: block totals, then (after the scan) block offsets
@@ -66,18 +75,34 @@ struct EmitRow {
 };
 __device__ __forceinline__ EmitRow emit_row(const EmitArgs &a) {
     EmitRow r;
-    r.w = blockIdx.x / a.blocks_per_win;
-    const int k = (blockIdx.x % a.blocks_per_win) * kEmitThreads + threadIdx.x;
-    r.valid = k < a.T;
+    const int outer = blockIdx.x / a.blocks_per_win;
+    const int inner = (blockIdx.x % a.blocks_per_win) * kEmitThreads + threadIdx.x;
+    int k;  // position of the sample in the printed order
+    if (a.sample_major) { k = outer; r.w = inner; r.valid = inner < a.W; }
+    else                { k = inner; r.w = outer; r.valid = inner < a.T; }
+    if (!r.valid) r.w = 0;
     r.col = r.valid ? (a.col_order ? a.col_order[k] : k) : 0;
     return r;
 }
+__device__ __forceinline__ int emit_pred_index(const EmitArgs &a, const EmitRow &r) {
+    const int v = a.nsnp[(size_t)r.w * a.T + r.col];
+    return v < 0 ? 0 : (v >= a.n_pred ? a.n_pred - 1 : v);
+}
 __device__ __forceinline__ int emit_row_len(const EmitArgs &a, const EmitRow &r, int64_t s) {
+    if (a.mode == 1) {  // BED row, only where the observed score exceeds the predicted one
+        if (s == INT64_MIN || !((double)s > a.pred_value[emit_pred_index(a, r)])) return 0;
+        return a.chrom_len + 1 + len_i64((int64_t)a.win_start[r.w] - 1) + 1 + len_i64(a.win_end[r.w]) + 1 +
+               (a.label_off[r.col + 1] - a.label_off[r.col]) + 1;
+    }
     int n = a.chrom_len + 1 + len_i64(a.win_start[r.w]) + 1 + len_i64(a.win_end[r.w]) + 1 +
             (a.label_off[r.col + 1] - a.label_off[r.col]) + 1;
     n += (s == INT64_MIN) ? 2 : len_i64(s) + 2;
     n += 1 + len_i64(a.nsnp[(size_t)r.w * a.T + r.col]);
     if (a.replicate) n += 1 + len_i64(a.replicate[r.w]);
+    if (a.pred_text) {
+        const int pi = emit_pred_index(a, r);
+        n += 1 + ((s == INT64_MIN) ? 2 : a.pred_off[pi + 1] - a.pred_off[pi]);
+    }
     return n + 1;
 }
 
@@ -174,22 +199,32 @@ __global__ void __launch_bounds__(kEmitThreads) emit_format_kernel(const __grid_
     }
     int total;
     const int off = block_excl_scan(n, &total, s_warp);
-    if (r.valid) {
+    if (r.valid && n > 0) {
         char *p = s_text + off;
         for (int i = 0; i < a.chrom_len; ++i) *p++ = a.chrom[i];
         *p++ = '\t';
-        p += put_i64(p, a.win_start[r.w]);
+        p += put_i64(p, (int64_t)a.win_start[r.w] - (a.mode == 1 ? 1 : 0));
         *p++ = '\t';
         p += put_i64(p, a.win_end[r.w]);
         *p++ = '\t';
         const int l0 = a.label_off[r.col], l1 = a.label_off[r.col + 1];
         for (int i = l0; i < l1; ++i) *p++ = a.labels[i];
-        *p++ = '\t';
-        if (s == INT64_MIN) { *p++ = 'N'; *p++ = 'A'; }
-        else { p += put_i64(p, s); *p++ = '.'; *p++ = '0'; }
-        *p++ = '\t';
-        p += put_i64(p, a.nsnp[(size_t)r.w * a.T + r.col]);
-        if (a.replicate) { *p++ = '\t'; p += put_i64(p, a.replicate[r.w]); }
+        if (a.mode == 0) {
+            *p++ = '\t';
+            if (s == INT64_MIN) { *p++ = 'N'; *p++ = 'A'; }
+            else { p += put_i64(p, s); *p++ = '.'; *p++ = '0'; }
+            *p++ = '\t';
+            p += put_i64(p, a.nsnp[(size_t)r.w * a.T + r.col]);
+            if (a.replicate) { *p++ = '\t'; p += put_i64(p, a.replicate[r.w]); }
+            if (a.pred_text) {
+                *p++ = '\t';
+                if (s == INT64_MIN) { *p++ = 'N'; *p++ = 'A'; }
+                else {
+                    const int pi = emit_pred_index(a, r);
+                    for (int i = a.pred_off[pi]; i < a.pred_off[pi + 1]; ++i) *p++ = a.pred_text[i];
+                }
+            }
+        }
         *p++ = '\n';
     }
     __syncthreads();

@@ -640,16 +640,18 @@ extern "C" size_t sstar_b200_tsv_max_bytes(int32_t W, int32_t T, int32_t chrom_l
 
 extern "C" size_t sstar_b200_tsv_workspace_bytes(int32_t W, int32_t T) {
     if (W < 0 || T < 1) return 0;
-    const size_t nb = (size_t)(W > 0 ? W : 1) * (size_t)((T + kEmitThreads - 1) / kEmitThreads);
-    return 256 + align_up(nb * 8, 256);
+    // enough for either row order: blocks of 256 rows along the inner index
+    const size_t nb_w = (size_t)(W > 0 ? W : 1) * (size_t)((T + kEmitThreads - 1) / kEmitThreads);
+    const size_t nb_s = (size_t)T * (size_t)(((W > 0 ? W : 1) + kEmitThreads - 1) / kEmitThreads);
+    return 256 + align_up((nb_w > nb_s ? nb_w : nb_s) * 8, 256);
 }
 
-extern "C" int sstar_b200_format_tsv(int device, void *stream, const int64_t *d_score, const int32_t *d_nsnp,
-                                     const int32_t *d_win_start, const int32_t *d_win_end, int32_t W, int32_t T,
-                                     const char *chrom, const char *d_labels, const int32_t *d_label_off,
-                                     int32_t max_label_len, const int32_t *d_replicate,
-                                     const int32_t *d_col_order, char *d_out, size_t out_capacity,
-                                     void *d_workspace, size_t workspace_bytes) {
+extern "C" int sstar_b200_format_table(int device, void *stream, const int64_t *d_score, const int32_t *d_nsnp,
+                                       const int32_t *d_win_start, const int32_t *d_win_end, int32_t W, int32_t T,
+                                       const char *chrom, const char *d_labels, const int32_t *d_label_off,
+                                       int32_t max_label_len, const int32_t *d_replicate,
+                                       const int32_t *d_col_order, const sstar_b200_table_options *topts,
+                                       char *d_out, size_t out_capacity, void *d_workspace, size_t workspace_bytes) {
     g_launches = 0;
     if (W < 0 || T < 1) return fail(SSTAR_B200_EINVAL, "bad table shape%s");
     if (!chrom) return fail(SSTAR_B200_EINVAL, "chrom is null%s");
@@ -660,7 +662,16 @@ extern "C" int sstar_b200_format_tsv(int device, void *stream, const int64_t *d_
     if (W > 0 && (!d_score || !d_nsnp || !d_win_start || !d_win_end || !d_labels || !d_label_off || !d_out))
         return fail(SSTAR_B200_EINVAL, "null table pointer%s");
     if (max_label_len < 0) return fail(SSTAR_B200_EINVAL, "max_label_len must be >= 0%s");
-    const int row_cap = emit_row_cap((int32_t)clen, max_label_len, d_replicate != nullptr);
+    const int mode = topts ? topts->mode : 0;
+    const int sample_major = topts ? topts->sample_major : 0;
+    if (mode != 0 && mode != 1) return fail(SSTAR_B200_EINVAL, "unknown table mode%s");
+    const bool with_pred = topts && topts->d_pred_value;
+    if (mode == 1 && !with_pred) return fail(SSTAR_B200_EINVAL, "BED rows need the prediction table%s");
+    if (with_pred && (topts->n_pred < 1 || (mode == 0 && (!topts->d_pred_text || !topts->d_pred_off))))
+        return fail(SSTAR_B200_EINVAL, "incomplete prediction table%s");
+    const int max_pred_len = with_pred && mode == 0 ? topts->max_pred_len : 0;
+    if (max_pred_len < 0) return fail(SSTAR_B200_EINVAL, "max_pred_len must be >= 0%s");
+    const int row_cap = emit_row_cap((int32_t)clen, max_label_len, d_replicate != nullptr) + 1 + (max_pred_len > 2 ? max_pred_len : 2);
     const size_t smem = (size_t)row_cap * kEmitThreads;
     if (smem > (size_t)200 << 10) return fail(SSTAR_B200_EINVAL, "sample labels too long for the emitter%s");
     DeviceGuard guard(device);
@@ -670,7 +681,14 @@ extern "C" int sstar_b200_format_tsv(int device, void *stream, const int64_t *d_
     EmitArgs a = {};
     a.score = d_score; a.nsnp = d_nsnp; a.win_start = d_win_start; a.win_end = d_win_end;
     a.replicate = d_replicate; a.col_order = d_col_order; a.labels = d_labels; a.label_off = d_label_off;
-    a.W = W; a.T = T; a.blocks_per_win = (T + kEmitThreads - 1) / kEmitThreads; a.row_cap = row_cap;
+    a.mode = mode; a.sample_major = sample_major ? 1 : 0;
+    if (with_pred) {
+        a.pred_text = mode == 0 ? topts->d_pred_text : nullptr;
+        a.pred_off = topts->d_pred_off; a.pred_value = topts->d_pred_value; a.n_pred = topts->n_pred;
+    }
+    a.W = W; a.T = T; a.row_cap = row_cap;
+    const int inner = a.sample_major ? W : T, outer = a.sample_major ? T : W;
+    a.blocks_per_win = (inner + kEmitThreads - 1) / kEmitThreads;
     a.chrom_len = (int32_t)clen;
     memcpy(a.chrom, chrom, clen);
     a.total = reinterpret_cast<int64_t *>(ws);          // header: total bytes, status
@@ -678,9 +696,9 @@ extern "C" int sstar_b200_format_tsv(int device, void *stream, const int64_t *d_
     a.block_base = reinterpret_cast<int64_t *>(ws + 256);
     a.out = d_out; a.capacity = (int64_t)out_capacity;
     CUDA_TRY(cudaMemsetAsync(ws, 0, 256, st));
-    const int64_t nb = (int64_t)W * a.blocks_per_win;
+    const int64_t nb = (int64_t)outer * a.blocks_per_win;
     if (nb > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "table too large for one emitter call%s");
-    if (nb == 0) return 0;
+    if (nb == 0 || W == 0) return 0;
     static thread_local SmemGrant emit_grant;
     CUDA_TRY(grant_smem(emit_grant, emit_format_kernel, smem));
     cudaError_t e = launch(emit_len_kernel, (unsigned)nb, kEmitThreads, 0, st, false, a);
@@ -690,6 +708,17 @@ extern "C" int sstar_b200_format_tsv(int device, void *stream, const int64_t *d_
     e = launch(emit_format_kernel, (unsigned)nb, kEmitThreads, smem, st, false, a);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "emit_format_kernel launch: %s", cudaGetErrorString(e));
     return 0;
+}
+
+extern "C" int sstar_b200_format_tsv(int device, void *stream, const int64_t *d_score, const int32_t *d_nsnp,
+                                     const int32_t *d_win_start, const int32_t *d_win_end, int32_t W, int32_t T,
+                                     const char *chrom, const char *d_labels, const int32_t *d_label_off,
+                                     int32_t max_label_len, const int32_t *d_replicate,
+                                     const int32_t *d_col_order, char *d_out, size_t out_capacity,
+                                     void *d_workspace, size_t workspace_bytes) {
+    return sstar_b200_format_table(device, stream, d_score, d_nsnp, d_win_start, d_win_end, W, T, chrom, d_labels,
+                                   d_label_off, max_label_len, d_replicate, d_col_order, nullptr, d_out, out_capacity,
+                                   d_workspace, workspace_bytes);
 }
 
 // ---------------------------------------------------------------------------------------------

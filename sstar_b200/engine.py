@@ -241,10 +241,15 @@ class ScoreEngine:
 
     # ------------------------------------------------------------------ result emitter
     def format_tsv_device(self, score_d, nsnp_d, ws_d, we_d, chrom: str, labels, replicate_d=None,
-                          col_order_d=None, stream=None):
+                          col_order_d=None, stream=None, predictions=None, bed=False, sample_major=False):
         """Device tables -> TSV text on the device (no header line).  Returns ``(text_d, total,
         status)``: a uint8 device tensor whose first ``total`` bytes are the rows; ``status != 0``
-        means the table must be formatted on the host (see include/sstar_b200.h)."""
+        means the table must be formatted on the host (see include/sstar_b200.h).
+
+        ``predictions``: float64 array, entry v = the model's prediction for
+        ``Region_ind_SNP_number == v`` -- adds the ``Predicted_S*_score`` column, or with
+        ``bed=True`` prints the BED rows of the units whose score exceeds it.  ``sample_major``
+        orders the rows by (sample, window) instead of (window, sample)."""
         torch = self.torch
         W, T = score_d.shape
         enc = [str(x).encode() for x in labels]
@@ -256,15 +261,31 @@ class ScoreEngine:
         with torch.cuda.device(self.tdev):
             lab_d = torch.from_numpy(np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8).copy()).to(self.tdev)
             off_d = torch.from_numpy(off).to(self.tdev)
-            cap = self.lib.sstar_b200_tsv_max_bytes(W, T, len(chrom.encode()), max_len, int(replicate_d is not None))
+            topts, keep, extra = None, [], 0
+            if predictions is not None or sample_major or bed:
+                topts = _cabi.TableOptions(mode=1 if bed else 0, sample_major=int(bool(sample_major)))
+                if predictions is not None:
+                    pv = np.ascontiguousarray(predictions, dtype=np.float64)
+                    ptxt = [repr(float(x)).encode() for x in pv]  # what DataFrame.to_csv prints for a float
+                    poff = np.zeros(len(ptxt) + 1, dtype=np.int32)
+                    poff[1:] = np.cumsum([len(b) for b in ptxt])
+                    keep = [torch.from_numpy(pv).to(self.tdev),
+                            torch.from_numpy(np.frombuffer(b"".join(ptxt) + b"\0", dtype=np.uint8).copy()).to(self.tdev),
+                            torch.from_numpy(poff).to(self.tdev)]
+                    topts.d_pred_value, topts.d_pred_text, topts.d_pred_off = (k.data_ptr() for k in keep)
+                    topts.n_pred = len(pv)
+                    topts.max_pred_len = int(max(len(b) for b in ptxt))
+                    extra = W * T * (1 + topts.max_pred_len)
+            cap = self.lib.sstar_b200_tsv_max_bytes(W, T, len(chrom.encode()), max_len, int(replicate_d is not None)) + extra
             out = self._dbuf("tsv_out", cap, torch.uint8)
             ws = self._dbuf("tsv_ws", self.lib.sstar_b200_tsv_workspace_bytes(W, T), torch.uint8)
             s = stream if stream is not None else torch.cuda.current_stream(self.tdev)
-            rc = self.lib.sstar_b200_format_tsv(
+            rc = self.lib.sstar_b200_format_table(
                 self.device, ctypes.c_void_p(s.cuda_stream), score_d.data_ptr(), nsnp_d.data_ptr(), ws_d.data_ptr(),
                 we_d.data_ptr(), W, T, chrom.encode(), lab_d.data_ptr(), off_d.data_ptr(), max_len,
                 replicate_d.data_ptr() if replicate_d is not None else None,
                 col_order_d.data_ptr() if col_order_d is not None else None,
+                ctypes.byref(topts) if topts is not None else None,
                 out.data_ptr(), out.numel(), ws.data_ptr(), ws.numel())
             _cabi.check(rc)
             self.launches = self.lib.sstar_b200_last_launch_count()

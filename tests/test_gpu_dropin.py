@@ -283,3 +283,46 @@ def test_many_replicates_one_call():
         a, b = off[r], off[r + 1]
         so, no = c_oracle.score_windows(ref[a:b], tgt[a:b], pos_local[a:b], [1], [L])
         assert np.array_equal(s[r], so[0]) and np.array_equal(n[r], no[0]), r
+
+
+# ---- sstar2 infer (N3): feature table -> predictions -> tracts
+def test_infer_end_to_end_golden(tmp_path):
+    # reference tests/test_infer.py:26-60 (paths of the config rewritten to the fixtures)
+    import yaml
+    from sstar_b200.infer import infer
+    cfg = yaml.safe_load(open(os.path.join(FX, "test.config.yaml")))
+    pre = cfg["preprocessing"]
+    pre["vcf_file"] = os.path.join(FX, "test.vcf")
+    pre["ref_ind_file"] = os.path.join(FX, "test.ref.ind.list")
+    pre["tgt_ind_file"] = os.path.join(FX, "test.tgt.ind.list")
+    (tmp_path / "cfg.yaml").write_text(yaml.safe_dump(cfg))
+    feat, pred, tract = tmp_path / "f.tsv", tmp_path / "p.tsv", tmp_path / "t.bed"
+    infer(model=os.path.join(FX, "test.qr.model.onnx"), config=str(tmp_path / "cfg.yaml"), feat_file=feat,
+          pred_file=pred, tract_file=tract, match_bonus=5000, max_mismatch=5, mismatch_penalty=-10000)
+    assert open(feat).read() == open(os.path.join(FX, "test.infer.expected.features.tsv")).read()
+    pd.testing.assert_frame_equal(pd.read_csv(pred, sep="\t"),
+                                  pd.read_csv(os.path.join(FX, "test.infer.expected.pred.tsv"), sep="\t"),
+                                  check_dtype=False, check_exact=False, rtol=1e-6, atol=1e-8)
+    assert open(tract).read() == open(os.path.join(FX, "test.infer.expected.inferred.tracts.bed")).read()
+
+
+@pytest.mark.parametrize("W,T", [(1, 8), (300, 37), (19, 600)])
+def test_device_prediction_tables_match_the_pandas_route(tmp_path, W, T):
+    # prediction column, (Sample, Chromosome, Start, End) order and BED selection on the device ==
+    # the file-based mirror of the reference's pandas code, byte for byte
+    from sstar_b200 import quantile_regression as qr
+    from sstar_b200.feature_table import FeatureTable
+    rng = np.random.default_rng(W + T)
+    score = rng.integers(20_000, 120_000, size=(W, T)).astype(np.int64)
+    score[rng.random((W, T)) < 0.2] = np.iinfo(np.int64).min
+    nsnp = rng.integers(0, 420, size=(W, T)).astype(np.int32)
+    ws = (1 + 10_000 * np.arange(W)).astype(np.int64)
+    labels = [f"ind{t // 2 + 1}_{t % 2 + 1}" for t in range(T)]   # ind10_1 sorts before ind2_1
+    table = FeatureTable(21, ws, ws + 49_999, labels, score, nsnp)
+    model = os.path.join(FX, "test.qr.model.onnx")
+    table.to_tsv(tmp_path / "feat.tsv")
+    qr.infer(str(tmp_path / "feat.tsv"), model, str(tmp_path / "host.pred.tsv"), str(tmp_path / "host.bed"))
+    qr.infer_table_device(table, model, str(tmp_path / "dev.pred.tsv"), str(tmp_path / "dev.bed"))
+    assert open(tmp_path / "dev.pred.tsv").read() == open(tmp_path / "host.pred.tsv").read()
+    assert open(tmp_path / "dev.bed").read() == open(tmp_path / "host.bed").read()
+    assert open(tmp_path / "dev.bed").read().count("\n") > 0 or W * T < 10
