@@ -56,6 +56,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
     uint32_t *s_work = c.s_pos;  // [wg * bd] unit worklist, once the lists are built
     const int tid = c.tid, bd = c.bd, chunk = c.chunk, t = c.t, w0 = c.w0, nwin = c.nwin, L = c.L;
     constexpr int kShift = kGen ? 8 : 1;
+    constexpr int kBatch = 8;  // plane words fetched per round trip
 
     // this thread's column: plane words -> site list.  Shared memory is addressed with 32-bit
     // shared-window addresses (ld/st.shared) and the write cursor is clamped to a spill slot
@@ -71,18 +72,18 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
         uint32_t w_addr = (uint32_t)__cvta_generic_to_shared(s_list + tid);
         const uint32_t w_end = w_addr + (uint32_t)L * step;  // the spill slot
         const int nwr = c.nwr;
-        for (int jb = 0; jb < nwr; jb += 4) {
-            uint32_t cw[4], tw[4];
+        for (int jb = 0; jb < nwr; jb += kBatch) {
+            uint32_t cw[kBatch], tw[kBatch];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) cw[u] = (jb + u < nwr) ? __ldg(cp + (size_t)(jb + u) * a.Tp) : 0u;
+            for (int u = 0; u < kBatch; ++u) cw[u] = (jb + u < nwr) ? __ldg(cp + (size_t)(jb + u) * a.Tp) : 0u;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kBatch; ++u) {
                 if (jb + u == 0) cw[u] &= first_mask;
                 if (jb + u == nwr - 1) cw[u] &= last_mask;
                 tw[u] = (!kGen && jb + u < nwr) ? __ldg(tp + (size_t)(jb + u) * a.Tp) : 0u;  // not chained to cw
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kBatch; ++u) {
                 uint32_t cbits = cw[u];
                 const uint32_t sp = pos_addr + ((uint32_t)(jb + u) << 7);
                 cnt += __popc(cbits);
@@ -281,6 +282,7 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
         // positions of the union range, relative to its first variant (word-aligned tile)
         const int32_t base = gi0 << 5;
         const int32_t npos = min(nwr << 5, a.V - base);
+#pragma unroll 4
         for (int i = tid; i < npos; i += bd) s_pos[i] = (uint32_t)(__ldg(a.pos + base + i) - p0);
         if (tid < nwin) {
             const int32_t lo = g.lo[tid], hi = g.hi[tid];
