@@ -326,3 +326,21 @@ def test_device_prediction_tables_match_the_pandas_route(tmp_path, W, T):
     assert open(tmp_path / "dev.pred.tsv").read() == open(tmp_path / "host.pred.tsv").read()
     assert open(tmp_path / "dev.bed").read() == open(tmp_path / "host.bed").read()
     assert open(tmp_path / "dev.bed").read().count("\n") > 0 or W * T < 10
+
+
+def test_reference_ingest_cases_through_the_device_route(tmp_path):
+    # the reference's own read_data cases (tests/utils/test_utils.py:155-250) through preprocess()
+    import test_host_logic as hl
+    from sstar_b200.preprocess import preprocess
+    kw = dict(win_len=1000, win_step=1000, match_bonus=5000, max_mismatch=5, mismatch_penalty=-10000)
+    rows = ["1\t100\t.\tA\tG\t.\tPASS\t.\tGT\t0|0\t0|1\t0|1\t0|0", "1\t200\t.\tA\tG\t.\tPASS\t.\tGT\t.|.\t.|.\t0|1\t0|0",
+            "1\t300\t.\tA\tG\t.\tPASS\t.\tGT\t0|1\t0|0\t.|.\t.|.", "1\t400\t.\tA\tG\t.\tPASS\t.\tGT\t0|1\t0|0\t0|1\t0|0",
+            "1\t500\t.\tA\tG\t.\tPASS\t.\tGT\t1|1\t1|1\t1|1\t1|1"]
+    vcf, r, t = hl._write(tmp_path, "m.vcf", ["ref1", "ref2", "tgt1", "tgt2"], rows, ["ref1", "ref2"], ["tgt1", "tgt2"])
+    preprocess(vcf_file=vcf, chr_name="1", ref_ind_file=r, tgt_ind_file=t, output_file=str(tmp_path / "o.tsv"), **kw)
+    got = pd.read_csv(tmp_path / "o.tsv", sep="\t")
+    assert got["Region_ind_SNP_number"].tolist() == [2, 2, 2, 2] and got["S*_score"].isna().all()   # sites 100 and 400 survive
+    vcf, r, t = hl._write(tmp_path, "n.vcf", ["ref1", "tgt1"], ["1\t100\t.\tA\tG\t.\tPASS\t.\tGT\t0|1\t.|.",
+                                                                 "1\t200\t.\tA\tG\t.\tPASS\t.\tGT\t.|.\t0|1"], ["ref1"], ["tgt1"])
+    with pytest.raises(ValueError, match="No shared variant positions.*chromosome 1"):
+        preprocess(vcf_file=vcf, chr_name="1", ref_ind_file=r, tgt_ind_file=t, output_file=str(tmp_path / "o2.tsv"), **kw)

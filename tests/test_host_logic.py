@@ -189,3 +189,51 @@ def test_simulate_tiler_matches_port():
         assert r.shape == (len(p), nref * (ploidy if phased else 1))
         assert t.shape == (len(p), ntgt * (ploidy if phased else 1))
     assert sample_names(2, 2) == (["tsk_0", "tsk_1"], ["tsk_2", "tsk_3"])
+
+
+# ---- the reference's own ingest cases, verbatim inputs (tests/utils/test_utils.py:155-250,
+# tests/generators/test_window_data_generator.py:116-150)
+_HDR = "##fileformat=VCFv4.2\n##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n" \
+       "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t"
+
+
+def _write(tmp_path, name, samples, rows, ref, tgt):
+    (tmp_path / name).write_text(_HDR + "\t".join(samples) + "\n" + "\n".join(rows) + "\n")
+    (tmp_path / "ref.ind.list").write_text("\n".join(ref) + "\n")
+    (tmp_path / "tgt.ind.list").write_text("\n".join(tgt) + "\n")
+    return str(tmp_path / name), str(tmp_path / "ref.ind.list"), str(tmp_path / "tgt.ind.list")
+
+
+def test_reference_case_alignment_after_missing_filtering(tmp_path):
+    from sstar_b200.utils import read_data
+    rows = ["1\t100\t.\tA\tG\t.\tPASS\t.\tGT\t0|0\t0|1\t0|1\t0|0", "1\t200\t.\tA\tG\t.\tPASS\t.\tGT\t.|.\t.|.\t0|1\t0|0",
+            "1\t300\t.\tA\tG\t.\tPASS\t.\tGT\t0|1\t0|0\t.|.\t.|.", "1\t400\t.\tA\tG\t.\tPASS\t.\tGT\t0|1\t0|0\t0|1\t0|0",
+            "1\t500\t.\tA\tG\t.\tPASS\t.\tGT\t1|1\t1|1\t1|1\t1|1"]
+    vcf, r, t = _write(tmp_path, "m.vcf", ["ref1", "ref2", "tgt1", "tgt2"], rows, ["ref1", "ref2"], ["tgt1", "tgt2"])
+    ref_data, _, tgt_data, _ = read_data(vcf_file=vcf, ref_ind_file=r, tgt_ind_file=t, anc_allele_file=None, is_phased=True)
+    assert np.array_equal(ref_data["1"]["POS"], [100, 400]) and np.array_equal(tgt_data["1"]["POS"], [100, 400])
+    assert ref_data["1"]["GT"].shape[0] == tgt_data["1"]["GT"].shape[0] == 2
+
+
+def test_reference_case_duplicates_and_no_shared_positions(tmp_path):
+    from sstar_b200.utils import read_data
+    vcf, r, t = _write(tmp_path, "d.vcf", ["ref1", "tgt1"], ["1\t100\t.\tA\tG\t.\tPASS\t.\tGT\t0|1\t0|0",
+                                                              "1\t100\t.\tA\tT\t.\tPASS\t.\tGT\t0|0\t0|1"], ["ref1"], ["tgt1"])
+    with pytest.raises(ValueError, match="Duplicate variant positions.*100"):
+        read_data(vcf_file=vcf, ref_ind_file=r, tgt_ind_file=t, anc_allele_file=None, is_phased=True)
+    vcf, r, t = _write(tmp_path, "n.vcf", ["ref1", "tgt1"], ["1\t100\t.\tA\tG\t.\tPASS\t.\tGT\t0|1\t.|.",
+                                                              "1\t200\t.\tA\tG\t.\tPASS\t.\tGT\t.|.\t0|1"], ["ref1"], ["tgt1"])
+    with pytest.raises(ValueError, match="No shared variant positions.*chromosome 1"):
+        read_data(vcf_file=vcf, ref_ind_file=r, tgt_ind_file=t, anc_allele_file=None, is_phased=True)
+
+
+def test_reference_case_generator_scopes_alignment_to_requested_chromosome(tmp_path):
+    from sstar_b200.generators import WindowDataGenerator
+    rows = ["1\t100\t.\tA\tG\t.\tPASS\t.\tGT\t0|1\t0|0", "1\t200\t.\tA\tG\t.\tPASS\t.\tGT\t0|0\t0|1",
+            "2\t100\t.\tA\tG\t.\tPASS\t.\tGT\t0|1\t.|.", "2\t200\t.\tA\tG\t.\tPASS\t.\tGT\t.|.\t0|1"]
+    vcf, r, t = _write(tmp_path, "c.vcf", ["ref1", "tgt1"], rows, ["ref1"], ["tgt1"])
+    gen = WindowDataGenerator(vcf_file=vcf, chr_name="1", ref_ind_file=r, tgt_ind_file=t, win_len=1000, win_step=1000)
+    windows = list(gen.get())
+    assert len(windows) == 1 and windows[0]["chr_name"] == "1" and np.array_equal(windows[0]["pos"], [100, 200])
+    pos = np.array([1, 10, 20, 21, 30])   # closed interval boundaries (test_window_data_generator.py:107-113)
+    assert np.array_equal(pos[(pos >= 10) & (pos <= 20)], [10, 20])
