@@ -202,7 +202,7 @@ def run_reference(args, world, rank):
     base = CpuBaseline(wk["ref"], wk["tgt"], wk["pos"], wk["ws"], wk["we"], PARAMS, cores)
     per_win = base.per_window_seconds()
     # bounded sample: ~20 s of CPU work per step, at most the whole chromosome
-    work = min(20.0, 150.0 * cores / max(args.steps + args.warmup, 1))  # keep the whole run within minutes
+    work = min(20.0, 60.0 * cores / max(args.steps + args.warmup, 1))  # keep the whole run near a minute
     n_win = int(min(st["W"], max(cores, work / max(per_win, 1e-6))))
     sample = np.linspace(0, st["W"] - 1, num=n_win).astype(int)
     for _ in range(args.warmup):
@@ -504,8 +504,8 @@ def run_ours(args, world, rank, local):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
