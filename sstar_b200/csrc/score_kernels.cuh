@@ -40,7 +40,8 @@ struct LdgPos {
 struct GroupCtx {
     GroupShared *g;
     uint32_t *s_list, *s_pos;
-    int tid, bd, chunk, t, w0, nwin, L;
+    int tid, bd, chunk, t, w0, nwin, L;  // w0 / nwin: the sub-group this call lists and scores
+    int io;                              // its first window's slot in the GroupShared arrays
     int32_t rlo, rhi, gi0, nwr, pen_eff;
     bool mono_hi;
 };
@@ -52,6 +53,8 @@ struct GroupCtx {
 template <bool kGen>
 __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c) {
     GroupShared &g = *c.g;
+    const int32_t *glo = g.lo + c.io, *ghi = g.hi + c.io, *gnabs = g.nabs + c.io;
+    const uint32_t *gplo = g.plo + c.io, *gphi = g.phi + c.io, *gex = g.ex + c.io;
     uint32_t *s_list = c.s_list;
     uint32_t *s_work = c.s_pos;  // [wg * bd] unit worklist, once the lists are built
     const int tid = c.tid, bd = c.bd, chunk = c.chunk, t = c.t, w0 = c.w0, nwin = c.nwin, L = c.L;
@@ -117,7 +120,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
     };
     // windows with genotypes outside {0,1,2} that the list path is not taking in general mode
     auto route_exotic = [&](int i) -> bool {
-        if (kGen || !g.ex[i]) return false;
+        if (kGen || !gex[i]) return false;
         if (chunk == 0 && tid == 0) a.slow_list[a.w_begin + atomicAdd(&a.hdr->n_slow[a.slot], 1)] = w0 + i;
         return true;
     };
@@ -131,14 +134,14 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
         int cur_a = 0, cur_b = 0;
         for (int i = 0; i < nwin; ++i) {
             const int w = w0 + i;
-            const int32_t lo = g.lo[i], hi = g.hi[i];
+            const int32_t lo = glo[i], hi = ghi[i];
             const bool ex = route_exotic(i);
             int n = 0;
             bool queued = false;
             int64_t score = kNegInf64;
             if (t < a.T && !ex && hi > lo) {
                 if (!overflow) {
-                    list_window_range_shifted<kShift>(s_list + tid, bd, cur_a, cur_b, g.plo[i], g.phi[i], true);
+                    list_window_range_shifted<kShift>(s_list + tid, bd, cur_a, cur_b, gplo[i], gphi[i], true);
                     n = cur_b - cur_a;
                     queued = n > 2;
                 } else if (kGen) {
@@ -162,7 +165,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
             if (t < a.T && !ex) {
                 const size_t o = (size_t)w * a.T + t;
                 if (!queued) a.score[o] = score;  // NaN (n <= 2, empty window) or the overflow column's score
-                a.nsnp[o] = (hi - lo) - g.nabs[i] + n;
+                a.nsnp[o] = (hi - lo) - gnabs[i] + n;
             }
         }
         __syncthreads();
@@ -186,7 +189,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
     for (int i = 0; i < nwin; ++i) {
         const int w = w0 + i;
         if (route_exotic(i) || t >= a.T) continue;
-        const int32_t lo = g.lo[i], hi = g.hi[i];
+        const int32_t lo = glo[i], hi = ghi[i];
         int n = 0;
         int64_t score = kNegInf64;
         if (hi > lo) {
@@ -196,7 +199,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
                                       a.max_mm, n, score);
             } else {
                 int b = cur;
-                list_window_range_shifted<kShift>(s_list + tid, bd, cur, b, g.plo[i], g.phi[i], false);
+                list_window_range_shifted<kShift>(s_list + tid, bd, cur, b, gplo[i], gphi[i], false);
                 n = b - cur;
                 if (n > 2) {
                     if (!kGen) score = list_dp_run(s_list + tid + cur * bd, bd, n, a.bonus, c.pen_eff);
@@ -209,7 +212,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
         }
         const size_t o = (size_t)w * a.T + t;
         a.score[o] = score;
-        a.nsnp[o] = (hi - lo) - g.nabs[i] + n;
+        a.nsnp[o] = (hi - lo) - gnabs[i] + n;
     }
 }
 
@@ -244,125 +247,135 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
     }
     __syncthreads();
 
-    // the group's union variant range [rlo, rhi) over its non-empty windows
-    int32_t rlo = INT32_MAX, rhi = -1, prev_lo = -1, prev_hi = -1, prev_pfirst = INT32_MIN, maxnv = 0, p0 = 0,
-            plast = INT32_MIN;
-    bool mono = true, mono_hi = true;
-    for (int i = 0; i < nwin; ++i) {
-        const int32_t lo = g.lo[i], hi = g.hi[i];
-        if (hi > lo) {
-            // windows of one group must ascend in variant index AND in position (replicates
-            // concatenated along the variant axis restart their positions: never grouped)
-            mono = mono && lo >= prev_lo && g.pfirst[i] >= prev_pfirst && g.plast[i] >= g.pfirst[i];
-            mono_hi = mono_hi && hi >= prev_hi;
-            prev_lo = lo;
-            prev_hi = hi;
-            prev_pfirst = g.pfirst[i];
-            if (lo < rlo) { rlo = lo; p0 = g.pfirst[i]; }
-            rhi = max(rhi, hi);
-            plast = max(plast, g.plast[i]);
-            maxnv = max(maxnv, hi - lo);
-        }
-    }
-    if (rhi < 0) {  // nothing but empty windows: NaN, 0 SNPs (sstar.py:191-193 with n = 0)
-        if (t < a.T)
-            for (int i = 0; i < nwin; ++i) {
-                const size_t o = (size_t)(w0 + i) * a.T + t;
-                a.score[o] = kNegInf64;
-                a.nsnp[o] = 0;
-            }
-        return;
-    }
-    const int gi0 = rlo >> 5, nwr = ((rhi - 1) >> 5) - gi0 + 1;
-    const int64_t span = (int64_t)plast - (int64_t)p0;
-    const bool fast = mono && nwr <= words_cap && score_bound(span, maxnv, a.bonus, a.penalty) < kSmallBound;
     const int32_t pen_eff = (a.max_mm >= 1) ? a.penalty : Sentinel<int32_t>::NEG;
 
-    if (fast) {
-        // positions of the union range, relative to its first variant (word-aligned tile)
-        const int32_t base = gi0 << 5;
-        const int32_t npos = min(nwr << 5, a.V - base);
+    // The group is consumed as one or more SUB-GROUPS [s0, s1): the longest run of windows that
+    // ascend (in variant index and in position), whose union variant range fits the staged
+    // position tile and whose scores fit int32.  Regular overlapping windows give one sub-group;
+    // disjoint or unordered windows simply give shorter ones.  A window that does not fit even
+    // alone is walked straight from the planes.
+    int s0 = 0;
+    while (s0 < nwin) {
+        int32_t rlo = INT32_MAX, rhi = -1, prev_lo = -1, prev_hi = -1, prev_pfirst = INT32_MIN, maxnv = 0, p0 = 0,
+                plast = INT32_MIN;
+        bool mono_hi = true, alone = false;
+        int s1 = s0;
+        for (; s1 < nwin; ++s1) {
+            const int32_t lo = g.lo[s1], hi = g.hi[s1];
+            if (hi <= lo) continue;  // empty windows ride along
+            const int32_t n_rlo = min(rlo, lo), n_rhi = max(rhi, hi);
+            const int32_t n_p0 = lo < rlo ? g.pfirst[s1] : p0, n_plast = max(plast, g.plast[s1]);
+            const int32_t n_maxnv = max(maxnv, hi - lo);
+            const bool fits = lo >= prev_lo && g.pfirst[s1] >= prev_pfirst && g.plast[s1] >= g.pfirst[s1] &&
+                              ((n_rhi - 1) >> 5) - (n_rlo >> 5) + 1 <= words_cap &&
+                              score_bound((int64_t)n_plast - (int64_t)n_p0, n_maxnv, a.bonus, a.penalty) < kSmallBound;
+            if (!fits) {
+                if (rhi < 0) { alone = true; ++s1; }  // not even by itself: walk it
+                break;
+            }
+            mono_hi = mono_hi && hi >= prev_hi;
+            prev_lo = lo; prev_hi = hi; prev_pfirst = g.pfirst[s1];
+            rlo = n_rlo; rhi = n_rhi; p0 = n_p0; plast = n_plast; maxnv = n_maxnv;
+        }
+        const int nsub = s1 - s0;
+
+        if (alone) {
+            // ---- window by window from global memory
+            for (int i = s0; i < s1; ++i) {
+                const int w = w0 + i;
+                const int32_t lo = g.lo[i], hi = g.hi[i];
+                if (tid == 0) { g.red_nabs = 0; g.red_ex = 0; }
+                __syncthreads();
+                if (hi > lo) {
+                    const int wi0 = lo >> 5, wi1 = (hi - 1) >> 5;
+                    int na = 0;
+                    uint32_t ex = 0;
+                    for (int gi = wi0 + tid; gi <= wi1; gi += bd) {
+                        uint32_t rm = 0xffffffffu;
+                        if (gi == wi0) rm &= 0xffffffffu << (lo & 31);
+                        if (gi == wi1) rm &= 0xffffffffu >> (31 - ((hi - 1) & 31));
+                        na += __popc(__ldg(a.absent_bits + gi) & rm);
+                        ex |= __ldg(a.exotic + gi);
+                    }
+                    na = __reduce_add_sync(0xffffffffu, na);
+                    ex = __reduce_or_sync(0xffffffffu, ex);
+                    if ((tid & 31) == 0 && (na | ex)) {
+                        atomicAdd(&g.red_nabs, na);
+                        if (ex) atomicOr(&g.red_ex, ex);
+                    }
+                }
+                __syncthreads();
+                const int32_t nabs = g.red_nabs;
+                const uint32_t wex = g.red_ex;
+                __syncthreads();  // everyone has read the reduction before the next window resets it
+                if (wex) {
+                    if (chunk == 0 && tid == 0) a.slow_list[a.w_begin + atomicAdd(&a.hdr->n_slow[a.slot], 1)] = w;
+                    continue;
+                }
+                if (t >= a.T) continue;
+                int n = 0;
+                int64_t score = kNegInf64;
+                if (hi > lo) {
+                    const int64_t wspan = (int64_t)g.plast[i] - (int64_t)g.pfirst[i];
+                    if (score_bound(wspan, hi - lo, a.bonus, a.penalty) < kSmallBound)
+                        walk_dp_unit<int32_t>(LdgU32(), LdgPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus,
+                                              a.penalty, a.max_mm, n, score);
+                    else
+                        walk_dp_unit<int64_t>(LdgU32(), LdgPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus,
+                                              a.penalty, a.max_mm, n, score);
+                }
+                const size_t o = (size_t)w * a.T + t;
+                a.score[o] = score;
+                a.nsnp[o] = (hi - lo) - nabs + n;
+            }
+        } else if (rhi < 0) {
+            // ---- nothing but empty windows: NaN, 0 SNPs (sstar.py:191-193 with n = 0)
+            if (t < a.T)
+                for (int i = s0; i < s1; ++i) {
+                    const size_t o = (size_t)(w0 + i) * a.T + t;
+                    a.score[o] = kNegInf64;
+                    a.nsnp[o] = 0;
+                }
+        } else {
+            // ---- list path: positions of the union range, relative to its first variant
+            const int gi0 = rlo >> 5, nwr = ((rhi - 1) >> 5) - gi0 + 1;
+            const int64_t span = (int64_t)plast - (int64_t)p0;
+            const int32_t base = gi0 << 5;
+            const int32_t npos = min(nwr << 5, a.V - base);
 #pragma unroll 4
-        for (int i = tid; i < npos; i += bd) s_pos[i] = (uint32_t)(__ldg(a.pos + base + i) - p0);
-        if (tid < nwin) {
-            const int32_t lo = g.lo[tid], hi = g.hi[tid];
-            g.plo[tid] = hi > lo ? (uint32_t)(g.pfirst[tid] - p0) : 1u;
-            g.phi[tid] = hi > lo ? (uint32_t)(g.plast[tid] - p0) : 0u;
-        }
-        // #absent variants and the exotic flag per window: one (window, word) item per thread
-        for (int it = tid; it < nwin * nwr; it += bd) {
-            const int i = it / nwr, gi = gi0 + (it - i * nwr);
-            const int32_t lo = g.lo[i], hi = g.hi[i];
-            if (hi <= lo || gi < (lo >> 5) || gi > ((hi - 1) >> 5)) continue;
-            uint32_t rm = 0xffffffffu;
-            if (gi == (lo >> 5)) rm &= 0xffffffffu << (lo & 31);
-            if (gi == ((hi - 1) >> 5)) rm &= 0xffffffffu >> (31 - ((hi - 1) & 31));
-            const int na = __popc(__ldg(a.absent_bits + gi) & rm);
-            if (na) atomicAdd(&g.nabs[i], na);
-            if (__ldg(a.exotic + gi)) atomicOr(&g.ex[i], 1u);
-        }
-        __syncthreads();
-
-        // Windows holding genotypes outside {0,1,2}: the whole group takes the general body.  Only
-        // when the group spans more than 2^23 bp do such windows go to the pairwise kernel.
-        bool any_ex = false;
-        for (int i = 0; i < nwin; ++i) any_ex = any_ex || g.ex[i] != 0;
-        GroupCtx c;
-        c.g = &g; c.s_list = s_list; c.s_pos = s_pos;
-        c.tid = tid; c.bd = bd; c.chunk = chunk; c.t = t; c.w0 = w0; c.nwin = nwin; c.L = L;
-        c.rlo = rlo; c.rhi = rhi; c.gi0 = gi0; c.nwr = nwr; c.pen_eff = pen_eff; c.mono_hi = mono_hi;
-        if (any_ex && span < (int64_t(1) << kGeneralPosBits)) group_body_general(a, c);
-        else group_body<false>(a, c);
-        return;
-    }
-
-    // ---- fallback: window by window from global memory
-    for (int i = 0; i < nwin; ++i) {
-        const int w = w0 + i;
-        const int32_t lo = g.lo[i], hi = g.hi[i];
-        if (tid == 0) { g.red_nabs = 0; g.red_ex = 0; }
-        __syncthreads();
-        if (hi > lo) {
-            const int wi0 = lo >> 5, wi1 = (hi - 1) >> 5;
-            int na = 0;
-            uint32_t ex = 0;
-            for (int gi = wi0 + tid; gi <= wi1; gi += bd) {
+            for (int i = tid; i < npos; i += bd) s_pos[i] = (uint32_t)(__ldg(a.pos + base + i) - p0);
+            if (tid < nsub) {
+                const int32_t lo = g.lo[s0 + tid], hi = g.hi[s0 + tid];
+                g.plo[s0 + tid] = hi > lo ? (uint32_t)(g.pfirst[s0 + tid] - p0) : 1u;
+                g.phi[s0 + tid] = hi > lo ? (uint32_t)(g.plast[s0 + tid] - p0) : 0u;
+            }
+            // #absent variants and the exotic flag per window: one (window, word) item per thread
+            for (int it = tid; it < nsub * nwr; it += bd) {
+                const int i = s0 + it / nwr, gi = gi0 + it % nwr;
+                const int32_t lo = g.lo[i], hi = g.hi[i];
+                if (hi <= lo || gi < (lo >> 5) || gi > ((hi - 1) >> 5)) continue;
                 uint32_t rm = 0xffffffffu;
-                if (gi == wi0) rm &= 0xffffffffu << (lo & 31);
-                if (gi == wi1) rm &= 0xffffffffu >> (31 - ((hi - 1) & 31));
-                na += __popc(__ldg(a.absent_bits + gi) & rm);
-                ex |= __ldg(a.exotic + gi);
+                if (gi == (lo >> 5)) rm &= 0xffffffffu << (lo & 31);
+                if (gi == ((hi - 1) >> 5)) rm &= 0xffffffffu >> (31 - ((hi - 1) & 31));
+                const int na = __popc(__ldg(a.absent_bits + gi) & rm);
+                if (na) atomicAdd(&g.nabs[i], na);
+                if (__ldg(a.exotic + gi)) atomicOr(&g.ex[i], 1u);
             }
-            na = __reduce_add_sync(0xffffffffu, na);
-            ex = __reduce_or_sync(0xffffffffu, ex);
-            if ((tid & 31) == 0 && (na | ex)) {
-                atomicAdd(&g.red_nabs, na);
-                if (ex) atomicOr(&g.red_ex, ex);
-            }
+            __syncthreads();
+
+            // Windows holding genotypes outside {0,1,2}: the whole sub-group takes the general body.
+            // Only when it spans more than 2^23 bp do such windows go to the pairwise kernel.
+            bool any_ex = false;
+            for (int i = s0; i < s1; ++i) any_ex = any_ex || g.ex[i] != 0;
+            GroupCtx c;
+            c.g = &g; c.s_list = s_list; c.s_pos = s_pos;
+            c.tid = tid; c.bd = bd; c.chunk = chunk; c.t = t; c.w0 = w0 + s0; c.nwin = nsub; c.L = L; c.io = s0;
+            c.rlo = rlo; c.rhi = rhi; c.gi0 = gi0; c.nwr = nwr; c.pen_eff = pen_eff; c.mono_hi = mono_hi;
+            if (any_ex && span < (int64_t(1) << kGeneralPosBits)) group_body_general(a, c);
+            else group_body<false>(a, c);
         }
-        __syncthreads();
-        const int32_t nabs = g.red_nabs;
-        const uint32_t wex = g.red_ex;
-        __syncthreads();  // everyone has read the reduction before the next window resets it
-        if (wex) {
-            if (chunk == 0 && tid == 0) a.slow_list[a.w_begin + atomicAdd(&a.hdr->n_slow[a.slot], 1)] = w;
-            continue;
-        }
-        if (t >= a.T) continue;
-        int n = 0;
-        int64_t score = kNegInf64;
-        if (hi > lo) {
-            const int64_t wspan = (int64_t)g.plast[i] - (int64_t)g.pfirst[i];
-            if (score_bound(wspan, hi - lo, a.bonus, a.penalty) < kSmallBound)
-                walk_dp_unit<int32_t>(LdgU32(), LdgPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus, a.penalty,
-                                      a.max_mm, n, score);
-            else
-                walk_dp_unit<int64_t>(LdgU32(), LdgPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus, a.penalty,
-                                      a.max_mm, n, score);
-        }
-        const size_t o = (size_t)w * a.T + t;
-        a.score[o] = score;
-        a.nsnp[o] = (hi - lo) - nabs + n;
+        s0 = s1;
+        if (s0 < nwin) __syncthreads();  // the lists / worklist are reused by the next sub-group
     }
 }
 

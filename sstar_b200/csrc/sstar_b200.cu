@@ -241,15 +241,12 @@ int launch_score(cudaStream_t st, const ScoreCall &c, const WsLayout &L, int32_t
         if (bd > kScoreMaxThreads) bd = kScoreMaxThreads;
         const int tchunks = (T + bd - 1) / bd;
         s.tchunks = tchunks;
-        // Windows per CTA: as many as share variants (amortises the list build), but keep at least
-        // ~4 CTAs per SM in flight and keep a group's union range inside the staged position tile.
+        // Windows per CTA: up to 16 consecutive ones (the list build and the per-CTA set-up are
+        // shared by them; the kernel itself cuts a group into sub-groups that fit its position
+        // tile), but keep at least two full waves of CTAs (7 resident per SM) so the tail stays short.
         const int words_cap = kScoreWordsCap;
-        int wg = 8;
-        if (c.max_win_variants > 0) {
-            const int fit = (words_cap * 32) / c.max_win_variants;  // disjoint windows (replicates) still fit
-            if (fit < wg) wg = fit < 1 ? 1 : fit;
-        }
-        while (wg > 1 && (int64_t)((W + wg - 1) / wg) * tchunks < 4 * kNumSM) wg >>= 1;
+        int wg = kMaxGroup;
+        while (wg > 1 && (int64_t)((W + wg - 1) / wg) * tchunks < 2 * 7 * kNumSM) wg >>= 1;
         if (c.disjoint) wg = 1;  // replicates share no variants (and their positions restart)
         const int64_t ngroups = (W + wg - 1) / wg;
         if (ngroups * tchunks > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "too many (window group, column chunk) tiles%s");

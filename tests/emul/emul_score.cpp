@@ -69,112 +69,119 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
     };
     for (int w0 = 0; w0 < W; w0 += wg) {
         const int nwin = std::min(wg, W - w0);
-        int32_t rlo = INT32_MAX, rhi = -1, prev_lo = -1, prev_hi = -1, maxnv = 0;
-        bool mono = true, mono_hi = true;
-        for (int i = 0; i < nwin; ++i) {
-            const int32_t lo = wlo[w0 + i], hi = whi[w0 + i];
-            if (hi > lo) {
-                mono = mono && lo >= prev_lo;  // (positions ascend globally in this harness)
+        // greedy sub-groups, as in score_group_kernel
+        int s0 = 0;
+        while (s0 < nwin) {
+            int32_t rlo = INT32_MAX, rhi = -1, prev_lo = -1, prev_hi = -1, prev_pf = INT32_MIN, maxnv = 0, p0 = 0, plast = INT32_MIN;
+            bool mono_hi = true, alone = false;
+            int s1 = s0;
+            for (; s1 < nwin; ++s1) {
+                const int32_t lo = wlo[w0 + s1], hi = whi[w0 + s1];
+                if (hi <= lo) continue;
+                const int32_t pf = pos[lo], pl = pos[hi - 1];
+                const int32_t n_rlo = std::min(rlo, lo), n_rhi = std::max(rhi, hi);
+                const int32_t n_p0 = lo < rlo ? pf : p0, n_plast = std::max(plast, pl), n_maxnv = std::max(maxnv, hi - lo);
+                const bool fits = lo >= prev_lo && pf >= prev_pf && pl >= pf &&
+                                  ((n_rhi - 1) >> 5) - (n_rlo >> 5) + 1 <= words_cap &&
+                                  score_bound((int64_t)n_plast - (int64_t)n_p0, n_maxnv, bonus, penalty) < kSmallBound;
+                if (!fits) {
+                    if (rhi < 0) { alone = true; ++s1; }
+                    break;
+                }
                 mono_hi = mono_hi && hi >= prev_hi;
-                prev_lo = lo; prev_hi = hi;
-                rlo = std::min(rlo, lo); rhi = std::max(rhi, hi); maxnv = std::max(maxnv, hi - lo);
+                prev_lo = lo; prev_hi = hi; prev_pf = pf;
+                rlo = n_rlo; rhi = n_rhi; p0 = n_p0; plast = n_plast; maxnv = n_maxnv;
             }
-        }
-        if (rhi < 0) {
-            for (int i = 0; i < nwin; ++i)
-                for (int t = 0; t < T; ++t) {
-                    score[(size_t)(w0 + i) * T + t] = kNegInf64; nsnp[(size_t)(w0 + i) * T + t] = 0; path[(size_t)(w0 + i) * T + t] = 0;
-                }
-            continue;
-        }
-        const int gi0 = rlo >> 5, nwr = ((rhi - 1) >> 5) - gi0 + 1;
-        const int32_t p0 = pos[rlo];
-        const int64_t span = (int64_t)pos[rhi - 1] - p0;
-        const bool fast = mono && nwr <= words_cap && score_bound(span, maxnv, bonus, penalty) < kSmallBound;
-        if (fast) {
-            const int32_t base = gi0 << 5;
-            const int32_t npos = (int32_t)std::min<int64_t>((int64_t)nwr << 5, V - base);
-            spos.assign((size_t)nwr << 5, 0);
-            for (int i = 0; i < npos; ++i) spos[i] = (uint32_t)(pos[base + i] - p0);
-            bool any_ex = false;
-            for (int i = 0; i < nwin; ++i) {
-                int32_t na; uint32_t ex;
-                window_absent(wlo[w0 + i], whi[w0 + i], na, ex);
-                any_ex = any_ex || ex;
-            }
-            const bool gen = any_ex && span < (int64_t(1) << kGeneralPosBits);
-            for (int t = 0; t < T; ++t) {
-                int cnt = 0;
-                for (int j = 0; j < nwr; ++j) {
-                    uint32_t c = carried[(size_t)(gi0 + j) * Tp + t];
-                    if (j == 0) c &= 0xffffffffu << (rlo & 31);
-                    if (j == nwr - 1) c &= 0xffffffffu >> (31 - ((rhi - 1) & 31));
-                    const uint32_t tw = two[(size_t)(gi0 + j) * Tp + t];
-                    while (c) {
-                        const int b = __builtin_ctz(c);
-                        c &= c - 1;
-                        uint32_t e = (spos[(j << 5) + b] << 1) | ((tw >> b) & 1u);
-                        if (gen) e = (spos[(j << 5) + b] << 8) | (uint32_t)(uint8_t)tgt[(size_t)(base + (j << 5) + b) * T + t];
-                        if (cnt < L) list[cnt] = e;
-                        ++cnt;
-                    }
-                }
-                const bool overflow = cnt >= L;  // one slot is the terminator
-                if (!overflow) list[cnt] = kListSentinel;
-                int cur = 0, cur_b = 0;
-                const bool balanced = nwin > 1 && mono_hi;  // the kernel's two-pass path
-                for (int i = 0; i < nwin; ++i) {
+            if (alone) {
+                for (int i = s0; i < s1; ++i) {
                     const int w = w0 + i;
                     const int32_t lo = wlo[w], hi = whi[w];
                     int32_t na; uint32_t ex;
                     window_absent(lo, hi, na, ex);
-                    if (ex && !gen) { slow[w] = 1; continue; }
-                    int n = 0; int64_t sc = kNegInf64;
-                    if (hi > lo) {
-                        const uint32_t plo = (uint32_t)(pos[lo] - p0), phi = (uint32_t)(pos[hi - 1] - p0);
-                        if (gen) {
-                            if (overflow) { slow[w] = 1; continue; }
-                            if (!balanced) cur_b = cur;
-                            list_window_range_shifted<8>(list.data(), 1, cur, cur_b, plo, phi, balanced);
-                            n = cur_b - cur;
-                            if (n > 2 && !list_dp_run_general(list.data() + cur, 1, n, bonus, penalty, max_mm, sc)) { slow[w] = 1; continue; }
-                        } else if (!overflow && balanced) {
-                            list_window_range(list.data(), 1, cur, cur_b, plo, phi, true);
-                            n = cur_b - cur;
-                            if (n > 2) sc = list_dp_run(list.data() + cur, 1, n, bonus, pen_eff);
-                        } else if (!overflow) list_dp_window(list.data(), 1, cur, plo, phi, bonus, pen_eff, n, sc);
-                        else walk_dp_unit<int32_t>(HostLd(), HostPos{pos}, carried.data(), two.data(), Tp, t, lo, hi, bonus, penalty, max_mm, n, sc);
-                    }
-                    score[(size_t)w * T + t] = sc;
-                    nsnp[(size_t)w * T + t] = (hi - lo) - na + n;
-                    path[(size_t)w * T + t] = gen ? 5 : overflow ? 2 : 1;
-                }
-            }
-            continue;
-        }
-        for (int i = 0; i < nwin; ++i) {
-            const int w = w0 + i;
-            const int32_t lo = wlo[w], hi = whi[w];
-            int32_t na; uint32_t ex;
-            window_absent(lo, hi, na, ex);
-            if (ex) { slow[w] = 1; continue; }
-            for (int t = 0; t < T; ++t) {
-                int n = 0; int64_t sc = kNegInf64;
-                int pth = 0;
-                if (hi > lo) {
-                    const int64_t wspan = (int64_t)pos[hi - 1] - (int64_t)pos[lo];
-                    if (score_bound(wspan, hi - lo, bonus, penalty) < kSmallBound) {
-                        walk_dp_unit<int32_t>(HostLd(), HostPos{pos}, carried.data(), two.data(), Tp, t, lo, hi, bonus, penalty, max_mm, n, sc);
-                        pth = 3;
-                    } else {
-                        walk_dp_unit<int64_t>(HostLd(), HostPos{pos}, carried.data(), two.data(), Tp, t, lo, hi, bonus, penalty, max_mm, n, sc);
-                        pth = 4;
+                    if (ex) { slow[w] = 1; continue; }
+                    for (int t = 0; t < T; ++t) {
+                        int n = 0; int64_t sc = kNegInf64; int pth = 0;
+                        if (hi > lo) {
+                            const int64_t wspan = (int64_t)pos[hi - 1] - (int64_t)pos[lo];
+                            if (score_bound(wspan, hi - lo, bonus, penalty) < kSmallBound) {
+                                walk_dp_unit<int32_t>(HostLd(), HostPos{pos}, carried.data(), two.data(), Tp, t, lo, hi, bonus, penalty, max_mm, n, sc);
+                                pth = 3;
+                            } else {
+                                walk_dp_unit<int64_t>(HostLd(), HostPos{pos}, carried.data(), two.data(), Tp, t, lo, hi, bonus, penalty, max_mm, n, sc);
+                                pth = 4;
+                            }
+                        }
+                        score[(size_t)w * T + t] = sc; nsnp[(size_t)w * T + t] = (hi - lo) - na + n; path[(size_t)w * T + t] = pth;
                     }
                 }
-                score[(size_t)w * T + t] = sc;
-                nsnp[(size_t)w * T + t] = (hi - lo) - na + n;
-                path[(size_t)w * T + t] = pth;
+            } else if (rhi < 0) {
+                for (int i = s0; i < s1; ++i)
+                    for (int t = 0; t < T; ++t) {
+                        score[(size_t)(w0 + i) * T + t] = kNegInf64; nsnp[(size_t)(w0 + i) * T + t] = 0; path[(size_t)(w0 + i) * T + t] = 0;
+                    }
+            } else {
+                const int gi0 = rlo >> 5, nwr = ((rhi - 1) >> 5) - gi0 + 1;
+                const int64_t span = (int64_t)plast - p0;
+                const int32_t base = gi0 << 5;
+                const int32_t npos = (int32_t)std::min<int64_t>((int64_t)nwr << 5, V - base);
+                spos.assign((size_t)nwr << 5, 0);
+                for (int i = 0; i < npos; ++i) spos[i] = (uint32_t)(pos[base + i] - p0);
+                bool any_ex = false;
+                for (int i = s0; i < s1; ++i) {
+                    int32_t na; uint32_t ex;
+                    window_absent(wlo[w0 + i], whi[w0 + i], na, ex);
+                    any_ex = any_ex || ex;
+                }
+                const bool gen = any_ex && span < (int64_t(1) << kGeneralPosBits);
+                for (int t = 0; t < T; ++t) {
+                    int cnt = 0;
+                    for (int j = 0; j < nwr; ++j) {
+                        uint32_t c = carried[(size_t)(gi0 + j) * Tp + t];
+                        if (j == 0) c &= 0xffffffffu << (rlo & 31);
+                        if (j == nwr - 1) c &= 0xffffffffu >> (31 - ((rhi - 1) & 31));
+                        const uint32_t tw = two[(size_t)(gi0 + j) * Tp + t];
+                        while (c) {
+                            const int b = __builtin_ctz(c);
+                            c &= c - 1;
+                            uint32_t e = (spos[(j << 5) + b] << 1) | ((tw >> b) & 1u);
+                            if (gen) e = (spos[(j << 5) + b] << 8) | (uint32_t)(uint8_t)tgt[(size_t)(base + (j << 5) + b) * T + t];
+                            if (cnt < L) list[cnt] = e;
+                            ++cnt;
+                        }
+                    }
+                    const bool overflow = cnt >= L;  // one slot is the terminator
+                    if (!overflow) list[cnt] = kListSentinel;
+                    int cur = 0, cur_b = 0;
+                    const bool balanced = (s1 - s0) > 1 && mono_hi;  // the kernel's two-pass path
+                    for (int i = s0; i < s1; ++i) {
+                        const int w = w0 + i;
+                        const int32_t lo = wlo[w], hi = whi[w];
+                        int32_t na; uint32_t ex;
+                        window_absent(lo, hi, na, ex);
+                        if (ex && !gen) { slow[w] = 1; continue; }
+                        int n = 0; int64_t sc = kNegInf64;
+                        if (hi > lo) {
+                            const uint32_t plo = (uint32_t)(pos[lo] - p0), phi = (uint32_t)(pos[hi - 1] - p0);
+                            if (gen) {
+                                if (overflow) { slow[w] = 1; continue; }
+                                if (!balanced) cur_b = cur;
+                                list_window_range_shifted<8>(list.data(), 1, cur, cur_b, plo, phi, balanced);
+                                n = cur_b - cur;
+                                if (n > 2 && !list_dp_run_general(list.data() + cur, 1, n, bonus, penalty, max_mm, sc)) { slow[w] = 1; continue; }
+                            } else if (!overflow && balanced) {
+                                list_window_range(list.data(), 1, cur, cur_b, plo, phi, true);
+                                n = cur_b - cur;
+                                if (n > 2) sc = list_dp_run(list.data() + cur, 1, n, bonus, pen_eff);
+                            } else if (!overflow) list_dp_window(list.data(), 1, cur, plo, phi, bonus, pen_eff, n, sc);
+                            else walk_dp_unit<int32_t>(HostLd(), HostPos{pos}, carried.data(), two.data(), Tp, t, lo, hi, bonus, penalty, max_mm, n, sc);
+                        }
+                        score[(size_t)w * T + t] = sc;
+                        nsnp[(size_t)w * T + t] = (hi - lo) - na + n;
+                        path[(size_t)w * T + t] = gen ? 5 : overflow ? 2 : 1;
+                    }
+                }
             }
+            s0 = s1;
         }
     }
     return 0;
