@@ -60,8 +60,6 @@ struct ScoreArgs {
     const int8_t *tgt;
     const uint32_t *absent_bits, *exotic, *carried, *two;
     const int32_t *win_lo, *win_hi, *win_pfirst, *win_plast;
-    const int32_t *win_start, *win_end;  // or null: fixed_start / fixed_end
-    int32_t fixed_start, fixed_end;
     int32_t *slow_list;
     uint32_t *win_bail;
     WsHeader *hdr;
