@@ -236,6 +236,19 @@ int sstar_b200_ingest(int device, void *stream, const int8_t *d_gt, const int32_
                       int8_t *d_ref_out, int8_t *d_tgt_out, int32_t *d_pos_out, void *d_workspace,
                       size_t workspace_bytes);
 
+/* Source match rates of inferred tracts: integer numerators per (tract, source individual).
+ * replaces: the tract x source loops of run_match (sstar/match.py:497-545) around
+ *           _dosage_for_position_index (:88-162) and calc_match_pct (:30-73).
+ * d_gt int8 [V, N, 2] (-1 = missing allele) of one chromosome; tract k covers variant rows
+ * [d_tract_lo[k], d_tract_hi[k]) (start < POS <= end), compares target column d_tract_tgt[k]
+ * (diploid ALT dosage when d_tract_hap[k] < 0, else that haplotype's allele * ploidy) with each
+ * source column's diploid dosage.  d_numer[k, s] = sum over sites called in both of
+ * (ploidy - |x - y|); the rate is (numer / ploidy) / (hi - lo), averaged over the sources. */
+int sstar_b200_match_numerators(int device, void *stream, const int8_t *d_gt, int64_t V, int32_t N,
+                                const int32_t *d_tract_lo, const int32_t *d_tract_hi,
+                                const int32_t *d_tract_tgt, const int32_t *d_tract_hap, int32_t K,
+                                const int32_t *d_src_cols, int32_t S, int32_t ploidy, int64_t *d_numer);
+
 /* Number of kernels the last sstar_b200_score_* / pack call on this thread enqueued. */
 int sstar_b200_last_launch_count(void);
 

@@ -20,6 +20,7 @@
 #include "score_kernels.cuh"
 #include "emit_kernels.cuh"
 #include "ingest_kernels.cuh"
+#include "match_kernels.cuh"
 
 using namespace sstar;
 
@@ -759,5 +760,30 @@ extern "C" int sstar_b200_ingest(int device, void *stream, const int8_t *d_gt, c
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "ingest_scan_kernel launch: %s", cudaGetErrorString(e));
     e = launch(ingest_write_kernel, (unsigned)nb, kIngestWarps * 32, 0, st, false, a);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "ingest_write_kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Source match rates
+// ---------------------------------------------------------------------------------------------
+extern "C" int sstar_b200_match_numerators(int device, void *stream, const int8_t *d_gt, int64_t V, int32_t N,
+                                           const int32_t *d_tract_lo, const int32_t *d_tract_hi,
+                                           const int32_t *d_tract_tgt, const int32_t *d_tract_hap, int32_t K,
+                                           const int32_t *d_src_cols, int32_t S, int32_t ploidy, int64_t *d_numer) {
+    g_launches = 0;
+    if (V < 0 || V > (int64_t)INT32_MAX - 64 || N < 1) return fail(SSTAR_B200_EINVAL, "bad genotype array shape%s");
+    if (K < 0 || S < 1 || ploidy < 1) return fail(SSTAR_B200_EINVAL, "bad tract / source / ploidy count%s");
+    if (K == 0) return 0;
+    if (!d_gt || !d_tract_lo || !d_tract_hi || !d_tract_tgt || !d_tract_hap || !d_src_cols || !d_numer)
+        return fail(SSTAR_B200_EINVAL, "null pointer%s");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    MatchArgs a = {};
+    a.gt = d_gt; a.N = N; a.tract_lo = d_tract_lo; a.tract_hi = d_tract_hi; a.tract_tgt = d_tract_tgt;
+    a.tract_hap = d_tract_hap; a.src_cols = d_src_cols; a.K = K; a.S = S; a.P = ploidy; a.numer = d_numer;
+    const int64_t pairs = (int64_t)K * S, blocks = (pairs + 7) / 8;
+    if (blocks > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "too many (tract, source) pairs for one call%s");
+    cudaError_t e = launch(match_kernel, (unsigned)blocks, 256u, 0, (cudaStream_t)stream, false, a);
+    if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "match_kernel launch: %s", cudaGetErrorString(e));
     return 0;
 }

@@ -239,6 +239,27 @@ class ScoreEngine:
         kept, shared = int(head[0]), int(head[1])
         return ref_o[:kept], tgt_o[:kept], pos_o[:kept], shared
 
+    # ------------------------------------------------------------------ match rates
+    def match_numerators(self, gt, tract_lo, tract_hi, tract_tgt, tract_hap, src_cols, ploidy: int = 2):
+        """``gt`` int8 [V, N, 2]; per tract a variant row range, a target column and a haplotype
+        index (-1 = diploid).  Returns int64 [K, S]: sum over sites called in both samples of
+        ``ploidy - |x - y|`` (see include/sstar_b200.h, sstar_b200_match_numerators)."""
+        torch = self.torch
+        with torch.cuda.device(self.tdev):
+            up = lambda a, dt: a if isinstance(a, torch.Tensor) else \
+                torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.tdev)
+            gt_d = up(gt, np.int8)
+            V, N = int(gt_d.shape[0]), int(gt_d.shape[1])
+            d = [up(x, np.int32) for x in (tract_lo, tract_hi, tract_tgt, tract_hap, src_cols)]
+            K, S = int(d[0].numel()), int(d[4].numel())
+            out = torch.zeros((K, S), dtype=torch.int64, device=self.tdev)
+            rc = self.lib.sstar_b200_match_numerators(
+                self.device, self._stream_ptr(), gt_d.data_ptr(), V, N, d[0].data_ptr(), d[1].data_ptr(),
+                d[2].data_ptr(), d[3].data_ptr(), K, d[4].data_ptr(), S, int(ploidy), out.data_ptr())
+            _cabi.check(rc)
+            self.launches = self.lib.sstar_b200_last_launch_count()
+            return out.cpu().numpy()
+
     # ------------------------------------------------------------------ result emitter
     def format_tsv_device(self, score_d, nsnp_d, ws_d, we_d, chrom: str, labels, replicate_d=None,
                           col_order_d=None, stream=None, predictions=None, bed=False, sample_major=False):

@@ -344,3 +344,89 @@ def test_reference_ingest_cases_through_the_device_route(tmp_path):
                                                                  "1\t200\t.\tA\tG\t.\tPASS\t.\tGT\t.|.\t0|1"], ["ref1"], ["tgt1"])
     with pytest.raises(ValueError, match="No shared variant positions.*chromosome 1"):
         preprocess(vcf_file=vcf, chr_name="1", ref_ind_file=r, tgt_ind_file=t, output_file=str(tmp_path / "o2.tsv"), **kw)
+
+
+# ---- sstar2 match (N4): tract x source match rates
+_MATCH_COLS = ["chrom", "start", "end", "sample", "match_rate"]
+
+
+def _match_files(tmp_path, tract_text, src="src1\nsrc2\n"):
+    # the reference's own mini input (tests/test_match.py:43-64)
+    (tmp_path / "mini.vcf").write_text(
+        "##fileformat=VCFv4.2\n##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n"
+        "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tind1\tsrc1\tsrc2\n"
+        "21\t100\t.\tA\tG\t.\tPASS\t.\tGT\t0|0\t0|0\t1|1\n"
+        "21\t200\t.\tA\tG\t.\tPASS\t.\tGT\t0|1\t1|1\t0|1\n"
+        "21\t300\t.\tA\tG\t.\tPASS\t.\tGT\t1|1\t1|1\t.|.\n")
+    (tmp_path / "tgt.ind.list").write_text("ind1\n")
+    (tmp_path / "src.ind.list").write_text(src)
+    (tmp_path / "tract.bed").write_text(tract_text)
+    return dict(vcf_file=str(tmp_path / "mini.vcf"), tgt_ind_file=str(tmp_path / "tgt.ind.list"),
+                src_ind_file=str(tmp_path / "src.ind.list"), tract_file=str(tmp_path / "tract.bed"),
+                output_file=str(tmp_path / "nested" / "match.tsv"), ploidy=2)
+
+
+def test_run_match_reference_cases(tmp_path):
+    # tests/test_match.py:315-455
+    from sstar_b200.match import run_match
+    kw = _match_files(tmp_path, "21\t0\t250\tind1_1\n")
+    run_match(**kw)
+    df = pd.read_csv(kw["output_file"], sep="\t", header=None, names=_MATCH_COLS)
+    assert df["sample"].tolist() == ["ind1_1"] and df["match_rate"].tolist() == pytest.approx([0.375])
+    kw = _match_files(tmp_path, "21\t0\t250\tind1\n")
+    run_match(**kw)
+    assert pd.read_csv(kw["output_file"], sep="\t", header=None, names=_MATCH_COLS)["match_rate"].tolist() == \
+        pytest.approx([0.625])
+    kw = _match_files(tmp_path, "21\t0\t250\tind1_1\textra\n21\t0\t250\tind1_2\textra\nchr21\t400\t500\tind1_1\tx\n")
+    run_match(**kw)
+    df = pd.read_csv(kw["output_file"], sep="\t", header=None, names=_MATCH_COLS, keep_default_na=False)
+    assert df["sample"].tolist() == ["ind1_1", "ind1_2", "ind1_1"] and df["chrom"].tolist() == ["21", "21", "chr21"]
+    assert df["match_rate"].tolist() == ["0.375", "0.625", "NA"]
+    with pytest.raises(ValueError, match="tract file must contain at least four columns"):
+        run_match(**_match_files(tmp_path, "21\t0\t250\n"))
+    with pytest.raises(ValueError, match="Target and source sample lists must not overlap"):
+        run_match(**_match_files(tmp_path, "21\t0\t250\tind1_1\n", src="ind1\nsrc1\n"))
+
+
+def test_run_match_random_against_oracle(tmp_path):
+    from oracle import match_port
+    from sstar_b200.match import run_match
+    rng = np.random.default_rng(12)
+    n_tgt, n_src, V = 6, 9, 700
+    names = [f"t{i}" for i in range(n_tgt)] + [f"s{i}" for i in range(n_src)]
+    order = rng.permutation(len(names))           # VCF column order differs from the list order
+    pos = {"3": np.sort(rng.choice(np.arange(1, 200_000), V, replace=False)),
+           "chr4": np.sort(rng.choice(np.arange(1, 200_000), V // 2, replace=False))}
+    gts = {}
+    with open(tmp_path / "r.vcf", "w") as fh:
+        fh.write("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" +
+                 "\t".join(names[i] for i in order) + "\n")
+        for c, p in pos.items():
+            g = rng.choice([0, 1, 2, -1], size=(len(p), len(names), 2), p=[0.55, 0.35, 0.03, 0.07])
+            gts[c] = g
+            for k in range(len(p)):
+                calls = ["|".join("." if a < 0 else str(a) for a in g[k, j]) for j in range(len(names))]
+                fh.write(f"{c}\t{p[k]}\t.\tA\tG,T\t.\t.\t.\tGT\t" + "\t".join(calls) + "\n")
+    (tmp_path / "t.list").write_text("\n".join(names[:n_tgt]) + "\n")
+    (tmp_path / "s.list").write_text("\n".join(names[n_tgt:]) + "\n")
+    tracts = []
+    for _ in range(120):
+        c = rng.choice(["3", "chr3", "4", "chr4"])
+        a = int(rng.integers(0, 190_000))
+        b = a + int(rng.integers(0, 30_000))
+        lab = f"t{rng.integers(0, n_tgt)}" + rng.choice(["", "_1", "_2"])
+        tracts.append((c, a, b, lab))
+    (tmp_path / "tr.bed").write_text("".join(f"{c}\t{a}\t{b}\t{lab}\n" for c, a, b, lab in tracts))
+    run_match(str(tmp_path / "r.vcf"), str(tmp_path / "t.list"), str(tmp_path / "s.list"), str(tmp_path / "tr.bed"),
+              str(tmp_path / "out.tsv"), ploidy=2)
+    got = pd.read_csv(tmp_path / "out.tsv", sep="\t", header=None, names=_MATCH_COLS, keep_default_na=False)
+    col = {names[i]: j for j, i in enumerate(order)}
+    want = []
+    for c, a, b, lab in tracts:
+        key = c if c in gts else (c[3:] if c.startswith("chr") else "chr" + c)
+        base, _, suf = lab.partition("_")
+        r = match_port.tract_rate(gts[key], pos[key], col[base], None if not suf else int(suf) - 1,
+                                  [col[s] for s in names[n_tgt:]], a, b)
+        want.append("NA" if r == "NA" else repr(r))
+    assert got["match_rate"].tolist() == want          # bit-identical rates (ploidy 2)
+    assert "NA" in want and len(set(want)) > 50
