@@ -92,6 +92,38 @@ def score_chromosome(ref_gts, tgt_gts, pos, win_start, win_end, match_bonus, max
     return score, nsnp
 
 
+def score_chromosome_pinned(ref_p, tgt_p, pos_p, ws_p, we_p, score_p, nsnp_p, match_bonus=5000, max_mismatch=5,
+                            mismatch_penalty=-10000, devices=None, algo="auto"):
+    """The same sharding on PAGE-LOCKED torch CPU tensors (inputs and the two [W, T] output
+    tables): every GPU pulls its row range and stores its result block in place over its own PCIe
+    link, with no staging copy on the host -- the route that scales with the number of GPUs.
+    Returns when every shard is done."""
+    devs = visible_devices(devices)
+    pos = pos_p.numpy()
+    ws, we = ws_p.numpy(), we_p.numpy()
+    lo = np.searchsorted(pos, ws.astype(np.int64), side="left")
+    hi = np.searchsorted(pos, we.astype(np.int64), side="right")
+
+    def work(dev, shard):
+        w0, w1, k0, k1 = shard
+        hint = int(max(0, (hi[w0:w1] - lo[w0:w1]).max())) if w1 > w0 else 0
+        eng = get_engine_for(dev)
+        with eng.torch.cuda.device(eng.tdev):
+            eng.score_pinned(ref_p[k0:k1], tgt_p[k0:k1], pos_p[k0:k1], ws_p[w0:w1], we_p[w0:w1], score_p[w0:w1],
+                             nsnp_p[w0:w1], match_bonus, max_mismatch, mismatch_penalty, algo=algo,
+                             max_win_variants=hint, sync=True)
+
+    shards = plan_window_shards(pos, ws, we, len(devs))
+    futures = [_worker(dev).submit(work, dev, shard) for dev, shard in zip(devs, shards)]
+    for f in futures:
+        f.result()
+
+
+def get_engine_for(dev: int):
+    from .engine import get_engine
+    return get_engine(dev)
+
+
 _WORKERS: dict = {}
 
 
