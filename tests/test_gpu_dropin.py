@@ -80,6 +80,15 @@ def test_sharded_over_available_gpus_equals_single():
         else:
             s, c = score_chromosome(ref, tgt, pos, ws, we, 5000, 5, -10000, devices=devs)
         assert np.array_equal(s, so) and np.array_equal(c, no), devs
+    # the same shards on page-locked tensors, result blocks stored in place
+    from sstar_b200.sharding import score_chromosome_pinned
+    pin = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in (ref, tgt, pos, ws, we)]
+    sp = torch.zeros(so.shape, dtype=torch.int64).pin_memory()
+    cp = torch.zeros(no.shape, dtype=torch.int32).pin_memory()
+    for devs in ([0], list(range(n)), [0, 0, 0]):
+        sp.zero_(); cp.zero_()
+        score_chromosome_pinned(*pin, sp, cp, devices=devs)
+        assert np.array_equal(sp.numpy(), so) and np.array_equal(cp.numpy(), no), devs
 
 
 @pytest.mark.parametrize("phased", [True, False])
