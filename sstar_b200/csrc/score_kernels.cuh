@@ -9,16 +9,21 @@ namespace sstar {
 // to kMaxGroup consecutive windows x <=128 columns.
 //
 // Overlapping windows (50 kb / 10 kb: 5x) share most of their variants, so the CTA turns the
-// group's union variant range into per-column site lists ONCE -- each thread pulls its column's
-// plane words (coalesced across the warp), and writes (relative position << 1 | genotype==2) for
-// every carried reference-absent site into its own shared-memory column -- and then every window
-// of the group is a cursor walk over that list: no bit scanning, no position lookups, no global
-// loads inside the DP.  Window-level quantities (#absent variants, exotic flag, first / last
-// relative position) are computed by one thread per window.
+// union variant range of a run of windows into per-column site lists ONCE -- each thread pulls
+// its column's plane words (coalesced across the warp), and writes
+// (relative position << 1 | genotype==2) for every carried reference-absent site into its own
+// shared-memory column -- and then every window of the run is a cursor walk over that list: no
+// bit scanning, no position lookups, no global loads inside the DP.
 //
-// A group the list path cannot take (non-monotone windows, a union range wider than the staged
-// position tile, scores beyond int32) and a column with more sites than list slots fall back to
-// walk_dp_unit straight from the planes in global memory.  Results are identical on every path.
+// The group is consumed as SUB-GROUPS: the longest runs of windows that ascend in variant index
+// and position, whose union range fits the staged position tile and whose scores fit int32.
+// Regular overlapping windows give one sub-group; disjoint or unordered ones give shorter runs; a
+// window that does not fit even alone, and a column with more sites than list slots, are walked
+// straight from the planes (walk_dp_unit).  Inside a sub-group of several windows the DP runs
+// in two passes: every column locates its windows' runs with two forward-only cursors and
+// finishes the units with n <= 2 (NaN), the rest are queued and shared evenly by the CTA's
+// threads.  Genotypes outside {0,1,2} switch the sub-group to general entries and the per-class
+// DP (out of line).  Results are identical on every path.
 // ------------------------------------------------------------------------------------------
 struct GroupShared {
     int32_t lo[kMaxGroup], hi[kMaxGroup];
