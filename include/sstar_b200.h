@@ -57,6 +57,8 @@ extern "C" {
 /* host entry, mapped buffers: tuning knobs of the pipelined path */
 #define SSTAR_B200_FLAG_COPY_OUTPUTS 4      /* result tables always by D2H copies (default: only when >= 8 MB) */
 #define SSTAR_B200_FLAG_SINGLE_CHUNK 8      /* no row chunking */
+#define SSTAR_B200_FLAG_ZERO_COPY_INPUTS 32 /* the pack kernel reads the genotype matrices from mapped host memory */
+#define SSTAR_B200_FLAG_COPY_INPUTS 64      /* ... never (default: inputs below 32 MB are read in place, larger ones copied in chunks) */
 
 typedef struct sstar_b200_options {
     int32_t algo;             /* SSTAR_B200_ALGO_* */
@@ -133,9 +135,11 @@ int sstar_b200_score_packed(int device, void *stream, const int8_t *d_tgt_gt, co
  * copy stream that `stream` joins before the call's last kernel); the caller synchronises
  * `stream` before reading h_score / h_nsnp.
  *   - If every host buffer is page-locked AND mapped (cudaHostAlloc / cudaHostRegister / torch
- *     pin_memory) the call is pipelined: the genotype matrices move host->device in row chunks
- *     while earlier chunks are packed and their windows scored, and the score kernels store the
- *     result tables straight into h_score / h_nsnp over PCIe.
+ *     pin_memory) the call is pipelined.  Genotype matrices of 32 MB or more move host->device in
+ *     row chunks on the copy stream while earlier chunks are packed and their windows scored;
+ *     smaller ones are read in place by the pack kernel (its TMA tile loads are the transfer).
+ *     Result tables below 8 MB are stored by the score kernels straight into h_score / h_nsnp,
+ *     larger ones copied back per chunk.
  *   - Otherwise (pageable memory, or SSTAR_B200_FLAG_STAGED_COPIES) inputs are copied to device
  *     staging buffers, scored, and the tables copied back, all on `stream`.
  * `d_scratch` is device memory of at least sstar_b200_host_scratch_bytes(...) either way. */

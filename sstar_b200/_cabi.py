@@ -29,6 +29,10 @@ class TableOptions(ctypes.Structure):
 
 
 FLAG_STAGED_COPIES = 1
+FLAG_COPY_OUTPUTS = 4
+FLAG_SINGLE_CHUNK = 8
+FLAG_ZERO_COPY_INPUTS = 32
+FLAG_COPY_INPUTS = 64
 
 
 class SstarB200Error(RuntimeError):

@@ -517,11 +517,11 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
 
     // the pipelined path needs page-locked inputs (truly asynchronous copies next to the caller's
     // stream) and mapped output tables (stored in place by the kernels)
-    void *m_score = nullptr, *m_nsnp = nullptr, *m_any = nullptr;
+    void *m_score = nullptr, *m_nsnp = nullptr, *m_any = nullptr, *m_ref = nullptr, *m_tgt = nullptr;
     bool mapped = !(opts && (opts->flags & SSTAR_B200_FLAG_STAGED_COPIES));
     mapped = mapped && mapped_pointer(h_pos, &m_any) && mapped_pointer(h_win_start, &m_any) &&
              mapped_pointer(h_win_end, &m_any) && mapped_pointer(h_score, &m_score) && mapped_pointer(h_nsnp, &m_nsnp) &&
-             mapped_pointer(h_ref_gt, &m_any) && mapped_pointer(h_tgt_gt, &m_any);
+             mapped_pointer(h_ref_gt, &m_ref) && mapped_pointer(h_tgt_gt, &m_tgt);
 
     if (!mapped) {  // staged: copy in, run, copy out, all on the caller's stream
         if (V > 0) {
@@ -553,13 +553,21 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
     // large ones (>= 8 MB) go through per-chunk D2H copies, which the copy engine moves faster
     // than SM stores to host memory (measured on the C4 shard: 5.66 vs 6.08 ms)
     const bool copy_out = (flags & SSTAR_B200_FLAG_COPY_OUTPUTS) != 0 || (int64_t)W * T * 12 >= ((int64_t)8 << 20);
+    // How do the genotype matrices cross PCIe?  Large inputs go through the copy engine in chunks
+    // (55 GB/s, overlapped with the kernels).  Copies of a few MB do not reach that rate -- 31-34
+    // GB/s on a healthy link, ~12 GB/s on some hosts -- while the SMs' own reads of mapped host
+    // memory hold ~34 GB/s everywhere, so inputs below 32 MB are packed straight out of host
+    // memory: the pack CTAs' TMA tile loads ARE the transfer, and there is nothing to wait for.
+    const int64_t in_bytes = V * ((int64_t)R + T);
+    const bool zero_copy_in = (flags & SSTAR_B200_FLAG_ZERO_COPY_INPUTS) != 0 ||
+                              (!(flags & SSTAR_B200_FLAG_COPY_INPUTS) && in_bytes < ((int64_t)32 << 20));
     // chunk the variant rows: >= 8 MB of genotypes per chunk (below that the per-chunk launches and
     // event hops cost more than the overlap wins: measured on C2, 4.9 MB), whole 256-row blocks
     // (any pack tile size divides 256 rows), at most kMaxChunks
     const int64_t row_bytes = (int64_t)R + T;
     int nchunks = (int)((V * row_bytes) / ((int64_t)8 << 20));
     if (nchunks > kMaxChunks) nchunks = kMaxChunks;
-    if (nchunks < 1 || (flags & SSTAR_B200_FLAG_SINGLE_CHUNK)) nchunks = 1;
+    if (nchunks < 1 || (flags & SSTAR_B200_FLAG_SINGLE_CHUNK) || zero_copy_in) nchunks = 1;
     int64_t rows_per = ((V + nchunks - 1) / nchunks + 255) / 256 * 256;
     if (rows_per < 256) rows_per = 256;
     nchunks = V > 0 ? (int)((V + rows_per - 1) / rows_per) : 1;
@@ -581,17 +589,21 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
     if (rc) return rc;
     int64_t *o_score = copy_out ? (int64_t *)(d + h.off_score) : (int64_t *)m_score;
     int32_t *o_nsnp = copy_out ? (int32_t *)(d + h.off_nsnp) : (int32_t *)m_nsnp;
-    const ScoreCall c = {d_tgt, d_pos, V, T, match_bonus, max_mismatch, mismatch_penalty, o_score, o_nsnp, ws, algo, hint,
+    const int8_t *k_ref = zero_copy_in ? (const int8_t *)m_ref : d_ref;  // what the pack kernel reads
+    const int8_t *k_tgt = zero_copy_in ? (const int8_t *)m_tgt : d_tgt;
+    const ScoreCall c = {k_tgt, d_pos, V, T, match_bonus, max_mismatch, mismatch_penalty, o_score, o_nsnp, ws, algo, hint,
                          false};
     int32_t w_done = 0;
     for (int k = 0; k < nchunks; ++k) {
         const int64_t r0 = (int64_t)k * rows_per, r1 = (r0 + rows_per < V) ? r0 + rows_per : V;
         if (r1 > r0) {
-            CUDA_TRY(cudaMemcpyAsync(d_ref + r0 * R, h_ref_gt + r0 * R, (size_t)(r1 - r0) * R, cudaMemcpyHostToDevice, pc->copy));
-            CUDA_TRY(cudaMemcpyAsync(d_tgt + r0 * T, h_tgt_gt + r0 * T, (size_t)(r1 - r0) * T, cudaMemcpyHostToDevice, pc->copy));
-            CUDA_TRY(cudaEventRecord(pc->chunk[k], pc->copy));
-            CUDA_TRY(cudaStreamWaitEvent(st, pc->chunk[k], 0));
-            rc = launch_prep(st, r0 / 32, (r1 + 31) / 32, d_ref, d_tgt, V, R, T, d_pos, nullptr, nullptr, nullptr, 0, 0, 0,
+            if (!zero_copy_in) {
+                CUDA_TRY(cudaMemcpyAsync(d_ref + r0 * R, h_ref_gt + r0 * R, (size_t)(r1 - r0) * R, cudaMemcpyHostToDevice, pc->copy));
+                CUDA_TRY(cudaMemcpyAsync(d_tgt + r0 * T, h_tgt_gt + r0 * T, (size_t)(r1 - r0) * T, cudaMemcpyHostToDevice, pc->copy));
+                CUDA_TRY(cudaEventRecord(pc->chunk[k], pc->copy));
+                CUDA_TRY(cudaStreamWaitEvent(st, pc->chunk[k], 0));
+            }
+            rc = launch_prep(st, r0 / 32, (r1 + 31) / 32, k_ref, k_tgt, V, R, T, d_pos, nullptr, nullptr, nullptr, 0, 0, 0,
                              ws, L);
             if (rc) return rc;
         }

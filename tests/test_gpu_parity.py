@@ -202,16 +202,19 @@ def test_host_entry_zero_copy_and_staged_agree(eng):
     so, no = c_oracle.score_windows(ref, tgt, pos, ws, we)
     W, T = so.shape
     hint = int(max(np.searchsorted(pos, we, "right") - np.searchsorted(pos, ws, "left")))
-    for pinned, staged in [(True, False), (True, True), (False, False)]:
+    from sstar_b200 import _cabi
+    for pinned, staged, flags in [(True, False, 0), (True, True, 0), (False, False, 0),
+                                  (True, False, _cabi.FLAG_ZERO_COPY_INPUTS), (True, False, _cabi.FLAG_COPY_INPUTS),
+                                  (True, False, _cabi.FLAG_COPY_OUTPUTS | _cabi.FLAG_SINGLE_CHUNK)]:
         mk = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()) if pinned else \
              (lambda a: torch.from_numpy(np.ascontiguousarray(a)))
         outs = torch.zeros((W, T), dtype=torch.int64), torch.zeros((W, T), dtype=torch.int32)
         if pinned:
             outs = tuple(o.pin_memory() for o in outs)
         eng.score_pinned(mk(ref), mk(tgt), mk(pos), mk(ws), mk(we), outs[0], outs[1], 5000, 5, -10000,
-                         max_win_variants=hint, staged=staged)
-        assert np.array_equal(outs[0].numpy(), so), (pinned, staged)
-        assert np.array_equal(outs[1].numpy(), no), (pinned, staged)
+                         max_win_variants=hint, staged=staged, flags=flags)
+        assert np.array_equal(outs[0].numpy(), so), (pinned, staged, flags)
+        assert np.array_equal(outs[1].numpy(), no), (pinned, staged, flags)
 
 
 def test_large_shape_properties(eng):

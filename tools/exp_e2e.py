@@ -17,7 +17,8 @@ score_p = torch.empty((W, T), dtype=torch.int64).pin_memory()
 nsnp_p = torch.empty((W, T), dtype=torch.int32).pin_memory()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 ref_out = None
-for label, kw in [("staged", dict(staged=True)), ("pipelined", dict()), ("pipelined+copy_out", dict(flags=4)),
+for label, kw in [("staged", dict(staged=True)), ("pipelined (auto)", dict()), ("pipelined, copy engine inputs", dict(flags=64)),
+                  ("pipelined, zero-copy inputs", dict(flags=32)), ("pipelined+copy_out", dict(flags=4)),
                   ("pipelined+single_chunk", dict(flags=8))]:
     ts = []
     for i in range(25):
