@@ -567,7 +567,7 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
     const int64_t row_bytes = (int64_t)R + T;
     int nchunks = (int)((V * row_bytes) / ((int64_t)8 << 20));
     if (nchunks > kMaxChunks) nchunks = kMaxChunks;
-    if (nchunks < 1 || (flags & SSTAR_B200_FLAG_SINGLE_CHUNK) || zero_copy_in) nchunks = 1;
+    if (nchunks < 1 || (flags & SSTAR_B200_FLAG_SINGLE_CHUNK)) nchunks = 1;
     int64_t rows_per = ((V + nchunks - 1) / nchunks + 255) / 256 * 256;
     if (rows_per < 256) rows_per = 256;
     nchunks = V > 0 ? (int)((V + rows_per - 1) / rows_per) : 1;
@@ -578,6 +578,34 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
     // the copy stream starts after whatever the caller already queued (it reuses the scratch)
     CUDA_TRY(cudaEventRecord(pc->entry, st));
     CUDA_TRY(cudaStreamWaitEvent(pc->copy, pc->entry, 0));
+    if (zero_copy_in) {
+        // Small input read in place: the pack starts at once on the caller's stream while the copy
+        // stream brings pos / windows over and resolves the window bounds; they meet before the DP.
+        if (V > 0) CUDA_TRY(cudaMemcpyAsync(d_pos, h_pos, (size_t)V * 4, cudaMemcpyHostToDevice, pc->copy));
+        if (W > 0) {
+            CUDA_TRY(cudaMemcpyAsync(d + h.off_ws, h_win_start, (size_t)W * 4, cudaMemcpyHostToDevice, pc->copy));
+            CUDA_TRY(cudaMemcpyAsync(d + h.off_we, h_win_end, (size_t)W * 4, cudaMemcpyHostToDevice, pc->copy));
+        }
+        rc = launch_prep(pc->copy, 0, 0, nullptr, nullptr, V, R, T, d_pos, (const int32_t *)(d + h.off_ws),
+                         (const int32_t *)(d + h.off_we), nullptr, 0, 0, W, ws, L);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(pc->chunk[0], pc->copy));
+        rc = launch_prep(st, 0, L.G, (const int8_t *)m_ref, (const int8_t *)m_tgt, V, R, T, d_pos, nullptr, nullptr,
+                         nullptr, 0, 0, 0, ws, L);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamWaitEvent(st, pc->chunk[0], 0));
+        int64_t *z_score = copy_out ? (int64_t *)(d + h.off_score) : (int64_t *)m_score;
+        int32_t *z_nsnp = copy_out ? (int32_t *)(d + h.off_nsnp) : (int32_t *)m_nsnp;
+        const ScoreCall zc = {(const int8_t *)m_tgt, d_pos, V, T, match_bonus, max_mismatch, mismatch_penalty, z_score,
+                              z_nsnp, ws, algo, hint, false};
+        rc = launch_score(st, zc, L, 0, W, 0);
+        if (rc) return rc;
+        if (copy_out && W > 0) {
+            CUDA_TRY(cudaMemcpyAsync(h_score, z_score, (size_t)W * T * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(h_nsnp, z_nsnp, (size_t)W * T * 4, cudaMemcpyDeviceToHost, st));
+        }
+        return 0;
+    }
     if (V > 0) CUDA_TRY(cudaMemcpyAsync(d_pos, h_pos, (size_t)V * 4, cudaMemcpyHostToDevice, st));
     if (W > 0) {
         CUDA_TRY(cudaMemcpyAsync(d + h.off_ws, h_win_start, (size_t)W * 4, cudaMemcpyHostToDevice, st));
@@ -589,21 +617,17 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
     if (rc) return rc;
     int64_t *o_score = copy_out ? (int64_t *)(d + h.off_score) : (int64_t *)m_score;
     int32_t *o_nsnp = copy_out ? (int32_t *)(d + h.off_nsnp) : (int32_t *)m_nsnp;
-    const int8_t *k_ref = zero_copy_in ? (const int8_t *)m_ref : d_ref;  // what the pack kernel reads
-    const int8_t *k_tgt = zero_copy_in ? (const int8_t *)m_tgt : d_tgt;
-    const ScoreCall c = {k_tgt, d_pos, V, T, match_bonus, max_mismatch, mismatch_penalty, o_score, o_nsnp, ws, algo, hint,
+    const ScoreCall c = {d_tgt, d_pos, V, T, match_bonus, max_mismatch, mismatch_penalty, o_score, o_nsnp, ws, algo, hint,
                          false};
     int32_t w_done = 0;
     for (int k = 0; k < nchunks; ++k) {
         const int64_t r0 = (int64_t)k * rows_per, r1 = (r0 + rows_per < V) ? r0 + rows_per : V;
         if (r1 > r0) {
-            if (!zero_copy_in) {
-                CUDA_TRY(cudaMemcpyAsync(d_ref + r0 * R, h_ref_gt + r0 * R, (size_t)(r1 - r0) * R, cudaMemcpyHostToDevice, pc->copy));
-                CUDA_TRY(cudaMemcpyAsync(d_tgt + r0 * T, h_tgt_gt + r0 * T, (size_t)(r1 - r0) * T, cudaMemcpyHostToDevice, pc->copy));
-                CUDA_TRY(cudaEventRecord(pc->chunk[k], pc->copy));
-                CUDA_TRY(cudaStreamWaitEvent(st, pc->chunk[k], 0));
-            }
-            rc = launch_prep(st, r0 / 32, (r1 + 31) / 32, k_ref, k_tgt, V, R, T, d_pos, nullptr, nullptr, nullptr, 0, 0, 0,
+            CUDA_TRY(cudaMemcpyAsync(d_ref + r0 * R, h_ref_gt + r0 * R, (size_t)(r1 - r0) * R, cudaMemcpyHostToDevice, pc->copy));
+            CUDA_TRY(cudaMemcpyAsync(d_tgt + r0 * T, h_tgt_gt + r0 * T, (size_t)(r1 - r0) * T, cudaMemcpyHostToDevice, pc->copy));
+            CUDA_TRY(cudaEventRecord(pc->chunk[k], pc->copy));
+            CUDA_TRY(cudaStreamWaitEvent(st, pc->chunk[k], 0));
+            rc = launch_prep(st, r0 / 32, (r1 + 31) / 32, d_ref, d_tgt, V, R, T, d_pos, nullptr, nullptr, nullptr, 0, 0, 0,
                              ws, L);
             if (rc) return rc;
         }
