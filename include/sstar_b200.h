@@ -240,6 +240,33 @@ int sstar_b200_ingest(int device, void *stream, const int8_t *d_gt, const int32_
                       int8_t *d_ref_out, int8_t *d_tgt_out, int32_t *d_pos_out, void *d_workspace,
                       size_t workspace_bytes);
 
+/* S* SNP sets: the sites on the best chain of every (window, column) unit -- an extension of the
+ * scoring path.  The current reference stops at the score (sstar/sstar.py:205-217 never backtracks);
+ * its legacy fixtures tests/exp_results/test.score.{unphased,phased}.exp.results.tsv carry the
+ * columns S*_SNP_number / S*_SNPs, reproduced by the rule of SURVEY.md section 8a item 6: the
+ * backpointer of site j is the FIRST i < j attaining M[j]; there the chain is extended when
+ * M[i] >= 0 and starts afresh with the pair (i, j) otherwise; it ends at the FIRST j attaining
+ * max_j M[j].  The result is ragged, so it takes two calls around one host read:
+ *   1. sstar_b200_snp_set_offsets: packs, resolves the windows, runs the literal pairwise recurrence
+ *      with backpointers; writes d_score / d_nsnp (as sstar_b200_score_windows) and
+ *      d_set_off [W*T + 1] (int64): unit u = w*T + t owns entries [d_set_off[u], d_set_off[u+1]).
+ *   2. the caller reads d_set_off[W*T] (total entries), provides d_set_pos [total] (int32) and calls
+ *      sstar_b200_snp_set_fill with the SAME workspace and parameters: positions of the chain
+ *      sites, ascending, unit after unit.  Units whose entries would pass `capacity` are skipped.
+ * Workspace: sstar_b200_snp_set_workspace_bytes (a superset of sstar_b200_workspace_bytes). */
+size_t sstar_b200_snp_set_workspace_bytes(int64_t V, int32_t R, int32_t T, int32_t W, int32_t max_win_variants);
+int sstar_b200_snp_set_offsets(int device, void *stream, const int8_t *d_ref_gt, const int8_t *d_tgt_gt,
+                               const int32_t *d_pos, int64_t V, int32_t R, int32_t T,
+                               const int32_t *d_win_start, const int32_t *d_win_end, int32_t W,
+                               int32_t match_bonus, int32_t max_mismatch, int32_t mismatch_penalty,
+                               int64_t *d_score, int32_t *d_nsnp, int64_t *d_set_off, void *d_workspace,
+                               size_t workspace_bytes, const sstar_b200_options *opts);
+int sstar_b200_snp_set_fill(int device, void *stream, const int8_t *d_tgt_gt, const int32_t *d_pos, int64_t V,
+                            int32_t R, int32_t T, int32_t W, int32_t match_bonus, int32_t max_mismatch,
+                            int32_t mismatch_penalty, const int64_t *d_set_off, int32_t *d_set_pos,
+                            int64_t capacity, void *d_workspace, size_t workspace_bytes,
+                            const sstar_b200_options *opts);
+
 /* Source match rates of inferred tracts: integer numerators per (tract, source individual).
  * replaces: the tract x source loops of run_match (sstar/match.py:497-545) around
  *           _dosage_for_position_index (:88-162) and calc_match_pct (:30-73).

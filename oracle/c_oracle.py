@@ -28,6 +28,9 @@ def _lib():
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
             ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
             ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+        lib.sstar_oracle_snp_sets.restype = ctypes.c_int
+        lib.sstar_oracle_snp_sets.argtypes = lib.sstar_oracle_score_windows.argtypes + [
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
         _LIB = lib
     return _LIB
 
@@ -52,3 +55,29 @@ def score_windows(ref_gts, tgt_gts, pos, win_start, win_end, match_bonus=5000, m
     if rc != 0:
         raise MemoryError("C oracle allocation failed")
     return score, nsnp
+
+
+def snp_sets(ref_gts, tgt_gts, pos, win_start, win_end, match_bonus=5000, max_mismatch=5,
+             mismatch_penalty=-10000):
+    """(score, nsnp, set_off int64 [W*T+1], set_pos int32 [total]): scores plus the positions on
+    every unit's best chain, via the scalar C oracle."""
+    ref = np.ascontiguousarray(ref_gts, dtype=np.int8)
+    tgt = np.ascontiguousarray(tgt_gts, dtype=np.int8)
+    p = np.ascontiguousarray(pos, dtype=np.int32)
+    ws = np.ascontiguousarray(win_start, dtype=np.int32)
+    we = np.ascontiguousarray(win_end, dtype=np.int32)
+    V, R = ref.shape if ref.ndim == 2 else (0, 0)
+    T = tgt.shape[1]
+    W = len(ws)
+    score = np.empty((W, T), dtype=np.int64)
+    nsnp = np.empty((W, T), dtype=np.int32)
+    off = np.zeros(W * T + 1, dtype=np.int64)
+    args = [ref.ctypes.data, tgt.ctypes.data, p.ctypes.data, V, R, T, ws.ctypes.data, we.ctypes.data,
+            W, int(match_bonus), int(max_mismatch), int(mismatch_penalty), score.ctypes.data,
+            nsnp.ctypes.data, off.ctypes.data]
+    if _lib().sstar_oracle_snp_sets(*args, None, 0) != 0:
+        raise MemoryError("C oracle allocation failed")
+    sets = np.empty(max(int(off[-1]), 1), dtype=np.int32)
+    if _lib().sstar_oracle_snp_sets(*args, sets.ctypes.data, int(off[-1])) != 0:
+        raise MemoryError("C oracle allocation failed")
+    return score, nsnp, off, sets[:int(off[-1])]

@@ -202,3 +202,26 @@ def score_windows(ref_gts, tgt_gts, pos, win_start, win_end, match_bonus=5000,
         else:
             score[w], nsnp[w] = compute_int(**args)
     return score, nsnp
+
+
+def snp_sets_windows(ref_gts, tgt_gts, pos, win_start, win_end, match_bonus=5000, max_mismatch=5,
+                     mismatch_penalty=-10000):
+    """Per unit (w, t), in that order: (score or None, [positions on the best chain]) -- the legacy
+    columns S*_SNP_number / S*_SNPs (reference fixtures tests/exp_results/test.score.*.exp.results.tsv),
+    rule of SURVEY section 8a item 6.  Pure Python: small cases only."""
+    ref_gts = np.asarray(ref_gts)
+    tgt_gts = np.asarray(tgt_gts)
+    pos = np.asarray(pos)
+    out = []
+    for w in range(len(win_start)):
+        inside = (pos >= win_start[w]) & (pos <= win_end[w])
+        rg, tg, pp = ref_gts[inside], tgt_gts[inside], pos[inside]
+        absent = rg.astype(np.int64).sum(axis=1) == 0
+        apos, agt = pp[absent], tg[absent]
+        for t in range(tgt_gts.shape[1]):
+            keep = agt[:, t] != 0
+            p = [int(x) for x in apos[keep]]
+            g = [int(x) for x in agt[keep, t]]
+            s, chain = chain_int(p, g, int(match_bonus), int(max_mismatch), int(mismatch_penalty))
+            out.append((s, [p[k] for k in chain]))
+    return out

@@ -78,6 +78,11 @@ SIGNATURES = {
                                      _vp, _vp, _vp, _vp, _sz]),
     "sstar_b200_match_numerators": (_c.c_int, [_c.c_int, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32,
                                                _i32, _vp]),
+    "sstar_b200_snp_set_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32]),
+    "sstar_b200_snp_set_offsets": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _i32, _i32,
+                                              _i32, _i32, _vp, _vp, _vp, _vp, _sz, _c.POINTER(Options)]),
+    "sstar_b200_snp_set_fill": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp,
+                                           _vp, _i64, _vp, _sz, _c.POINTER(Options)]),
     "sstar_b200_tsv_max_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "sstar_b200_tsv_workspace_bytes": (_sz, [_i32, _i32]),
     "sstar_b200_format_table": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _c.c_char_p, _vp, _vp,

@@ -1,0 +1,264 @@
+// sstar_b200 -- S* SNP sets: which sites the best chain of a (window, column) unit runs through.
+//
+// An extension of the scoring path: the current reference never backtracks (its table ends at
+// Region_ind_SNP_number, sstar/feature_vector_preprocessor.py:167-181); the only pins are its
+// legacy fixtures tests/exp_results/test.score.{unphased,phased}.exp.results.tsv with the columns
+// S*_SNP_number and S*_SNPs.  The rule that reproduces them on the
+// literal recurrence of sstar/sstar.py:195-217:
+//     M[j] = max_{i<j} ( s(j,i) + max(M[i], 0) )        backpointer = the FIRST i attaining the max;
+//     at that i the chain is extended when M[i] >= 0, else it starts afresh with the pair (i, j);
+//     the chain ends at the FIRST j attaining max_j M[j].
+//
+// One warp per unit, as in the pairwise scoring kernel: lanes stride over i < j, the row max is a
+// REDUX pair, the first i attaining it a REDUX min.  The result is ragged, so the work is two
+// passes around a scan (lengths -> offsets -> fill); the fill pass recomputes the recurrence only for
+// units that have a chain.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace sstar {
+
+constexpr int kSetEntryBytes = 17;   // per list entry: M int64, P int32, B int32, G int8
+constexpr int kScanThreads = 256;
+constexpr int kScanPerThread = 16;
+constexpr int kScanPerBlock = kScanThreads * kScanPerThread;
+
+struct SnpSetArgs {
+    const int32_t *pos;
+    const int8_t *tgt;
+    const uint32_t *absent_bits;
+    const int32_t *win_lo, *win_hi;
+    int32_t T, W;
+    int32_t bonus, max_mm, penalty;
+    int64_t *score;          // lengths pass: [W, T] (INT64_MIN = NaN)
+    int32_t *nsnp;           // lengths pass: [W, T]
+    int32_t *set_len;        // lengths pass: [W * T] sites on the best chain (0 when the score is NaN)
+    const int64_t *set_off;  // fill pass: [W * T + 1]
+    int32_t *set_pos;        // fill pass: positions of the chain sites, ascending, unit after unit
+    int64_t capacity;        // fill pass: entries set_pos holds
+    uint8_t *arena;
+    uint64_t arena_bytes;
+};
+
+__device__ __forceinline__ int64_t set_warp_max_i64(int64_t v) {
+    const int32_t hi = (int32_t)(v >> 32);
+    const int32_t mh = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t lo = (hi == mh) ? (uint32_t)v : 0u;
+    const uint32_t ml = __reduce_max_sync(0xffffffffu, lo);
+    return ((int64_t)mh << 32) | (int64_t)ml;
+}
+
+template <bool kFill>
+__global__ void __launch_bounds__(kPairWarps * 32) snp_set_kernel(const __grid_constant__ SnpSetArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int s_maxvw;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_maxvw = 0;
+    __syncthreads();
+    {   // the largest window decides where the lists live
+        int mv = 0;
+        for (int w = threadIdx.x; w < a.W; w += blockDim.x) mv = max(mv, a.win_hi[w] - a.win_lo[w]);
+        mv = __reduce_max_sync(0xffffffffu, mv);
+        if (lane == 0 && mv > 0) atomicMax(&s_maxvw, mv);
+    }
+    __syncthreads();
+    const int64_t total = (int64_t)a.W * a.T;
+    const uint32_t cap = (uint32_t)((s_maxvw + 7) & ~7);
+    if (cap == 0) {  // every window is empty
+        if (!kFill) {
+            for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
+                 it += (int64_t)gridDim.x * blockDim.x) {
+                a.score[it] = INT64_MIN;
+                a.nsnp[it] = 0;
+                a.set_len[it] = 0;
+            }
+        }
+        return;
+    }
+    int64_t gw = (int64_t)blockIdx.x * kPairWarps + warp;
+    int64_t nw = (int64_t)gridDim.x * kPairWarps;
+    uint8_t *slab;
+    uint32_t slab_cap;
+    if (cap <= (uint32_t)kPairSmemCap) {
+        slab_cap = kPairSmemCap;
+        slab = smem + (size_t)warp * kPairSmemCap * kSetEntryBytes;
+    } else {
+        slab_cap = cap;
+        const int64_t nslabs = (int64_t)(a.arena_bytes / ((uint64_t)cap * kSetEntryBytes));
+        if (nslabs < nw) nw = nslabs;
+        if (gw >= nw) return;
+        slab = a.arena + (size_t)gw * cap * kSetEntryBytes;
+    }
+    int64_t *M = reinterpret_cast<int64_t *>(slab);
+    int32_t *P = reinterpret_cast<int32_t *>(slab + (size_t)slab_cap * 8);
+    int32_t *B = reinterpret_cast<int32_t *>(slab + (size_t)slab_cap * 12);
+    int8_t *Gt = reinterpret_cast<int8_t *>(slab + (size_t)slab_cap * 16);
+
+    for (int64_t it = gw; it < total; it += nw) {
+        int64_t off = 0;
+        int len = 0;
+        if (kFill) {
+            off = a.set_off[it];
+            len = (int)(a.set_off[it + 1] - off);
+            if (len == 0 || off + len > a.capacity) continue;  // warp-uniform
+        }
+        const int w = (int)(it / a.T);
+        const int t = (int)(it % a.T);
+        const int32_t lo = a.win_lo[w], hi = a.win_hi[w];
+        int n = 0, nabs = 0;
+        if (hi > lo) {
+            for (int gi = lo >> 5; gi <= ((hi - 1) >> 5); ++gi) {
+                const int k = (gi << 5) + lane;
+                const uint32_t ab = __ldg(a.absent_bits + gi);
+                const bool isab = k >= lo && k < hi && ((ab >> lane) & 1);
+                int g = 0;
+                if (isab) g = a.tgt[(size_t)k * a.T + t];
+                const uint32_t ab_m = __ballot_sync(0xffffffffu, isab);
+                const uint32_t car_m = __ballot_sync(0xffffffffu, g != 0);
+                nabs += __popc(ab_m);
+                if (g != 0) {
+                    const int idx = n + __popc(car_m & ((1u << lane) - 1u));
+                    P[idx] = __ldg(a.pos + k);
+                    Gt[idx] = (int8_t)g;
+                }
+                n += __popc(car_m);
+            }
+        }
+        __syncwarp();
+        int64_t top = INT64_MIN;
+        int top_j = -1;
+        if (n > 2) {
+            for (int j = 0; j < n; ++j) {
+                const int32_t pj = P[j];
+                const int gj = Gt[j];
+                int64_t best = INT64_MIN;
+                int bi = INT32_MAX;
+                for (int i = lane; i < j; i += 32) {
+                    const int64_t d = (int64_t)pj - (int64_t)P[i];
+                    int qd = gj - (int)Gt[i];
+                    qd = qd < 0 ? -qd : qd;
+                    if (d >= kMinPairDistance && qd <= a.max_mm) {
+                        const int64_t s = (qd == 0) ? d + a.bonus : (int64_t)a.penalty;
+                        const int64_t cand = s + max(M[i], (int64_t)0);
+                        if (cand > best) { best = cand; bi = i; }  // ascending i: the lane's first maximiser
+                    }
+                }
+                const int64_t m = set_warp_max_i64(best);
+                const int first = __reduce_min_sync(0xffffffffu, (best == m && bi != INT32_MAX) ? bi : INT32_MAX);
+                if (lane == 0) {
+                    M[j] = m;
+                    // extension of the chain ending at `first`, or a fresh start with the pair (first, j)
+                    B[j] = (first == INT32_MAX) ? INT32_MIN : (M[first] >= 0 ? first : -(first + 2));
+                }
+                if (m > top) { top = m; top_j = j; }
+                __syncwarp();
+            }
+        }
+        if (!kFill) {
+            if (lane == 0) {
+                int cnt = 0;
+                if (top_j >= 0) {
+                    int j = top_j;
+                    for (;;) {
+                        ++cnt;
+                        const int b = B[j];
+                        if (b >= 0) j = b; else { ++cnt; break; }
+                    }
+                }
+                a.score[it] = top;
+                a.nsnp[it] = (hi - lo) - nabs + n;
+                a.set_len[it] = cnt;
+            }
+        } else if (lane == 0 && top_j >= 0) {
+            int k = len - 1, j = top_j;
+            while (k >= 0) {
+                a.set_pos[off + k] = P[j];
+                --k;
+                const int b = B[j];
+                if (b >= 0) j = b;
+                else { if (k >= 0) a.set_pos[off + k] = P[-b - 2]; break; }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- exclusive scan int32 [n] -> int64 [n + 1] ------------------------------------------------
+__device__ __forceinline__ int64_t scan_block_excl(int64_t v, int64_t *total, int64_t *s_warp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int64_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int64_t tt = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t y = __shfl_up_sync(0xffffffffu, tt, d);
+            if (lane >= d) tt += y;
+        }
+        s_warp[lane] = tt;  // inclusive over warps
+    }
+    __syncthreads();
+    *total = s_warp[(blockDim.x >> 5) - 1];
+    const int64_t r = x - v + (warp ? s_warp[warp - 1] : 0);
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_sum_kernel(const int32_t *v, int64_t n, int64_t *block_sum) {
+    __shared__ int64_t s_warp[32];
+    const int64_t i0 = (int64_t)blockIdx.x * kScanPerBlock + (int64_t)threadIdx.x * kScanPerThread;
+    int64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) s += (i0 + k < n) ? v[i0 + k] : 0;
+    int64_t total;
+    scan_block_excl(s, &total, s_warp);
+    if (threadIdx.x == 0) block_sum[blockIdx.x] = total;
+}
+
+// in-place exclusive scan of the block sums, one CTA; the grand total goes to *total_out
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(int64_t *block_sum, int64_t nb, int64_t *total_out) {
+    __shared__ int64_t s_warp[32];
+    __shared__ int64_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < nb; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const int64_t v = i < nb ? block_sum[i] : 0;
+        int64_t total;
+        const int64_t ex = scan_block_excl(v, &total, s_warp);
+        const int64_t carry = s_carry;
+        if (i < nb) block_sum[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = s_carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const int32_t *v, int64_t n, const int64_t *block_base,
+                                                                  int64_t *off) {
+    __shared__ int64_t s_warp[32];
+    const int64_t i0 = (int64_t)blockIdx.x * kScanPerBlock + (int64_t)threadIdx.x * kScanPerThread;
+    int32_t x[kScanPerThread];
+    int64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) { x[k] = (i0 + k < n) ? v[i0 + k] : 0; s += x[k]; }
+    int64_t total;
+    int64_t run = block_base[blockIdx.x] + scan_block_excl(s, &total, s_warp);
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) {
+        if (i0 + k < n) off[i0 + k] = run;
+        run += x[k];
+    }
+}
+
+}  // namespace sstar

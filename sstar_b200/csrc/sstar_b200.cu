@@ -21,6 +21,7 @@
 #include "emit_kernels.cuh"
 #include "ingest_kernels.cuh"
 #include "match_kernels.cuh"
+#include "snpset_kernels.cuh"
 
 using namespace sstar;
 
@@ -822,4 +823,123 @@ extern "C" int sstar_b200_match_numerators(int device, void *stream, const int8_
     cudaError_t e = launch(match_kernel, (unsigned)blocks, 256u, 0, (cudaStream_t)stream, false, a);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "match_kernel launch: %s", cudaGetErrorString(e));
     return 0;
+}
+
+// ---- S* SNP sets (optional extension; see snpset_kernels.cuh) --------------------------------
+namespace {
+struct SetLayout {
+    size_t off_len, off_blocks, total;
+    uint64_t arena_bytes;
+    int64_t n, nb;
+};
+// The set kernels keep 17 bytes per list entry where the pairwise scorer keeps 13: their arena is
+// the workspace's last block grown in place, then the per-unit lengths and the scan's block sums.
+SetLayout make_set_layout(const WsLayout &L, int32_t W, int32_t T) {
+    SetLayout S;
+    S.arena_bytes = (uint64_t)L.arena_entries * kSetEntryBytes;
+    S.n = (int64_t)W * T;
+    S.nb = (S.n + kScanPerBlock - 1) / kScanPerBlock;
+    size_t off = align_up(L.off_arena + (size_t)S.arena_bytes, 256);
+    S.off_len = off;    off = align_up(off + (size_t)(S.n > 0 ? S.n : 1) * 4, 256);
+    S.off_blocks = off; off = align_up(off + (size_t)(S.nb > 0 ? S.nb : 1) * 8, 256);
+    S.total = off;
+    return S;
+}
+
+int launch_snp_sets(cudaStream_t st, bool fill, const int8_t *d_tgt, const int32_t *d_pos, int32_t T, int32_t W,
+                    int32_t bonus, int32_t max_mm, int32_t penalty, int64_t *d_score, int32_t *d_nsnp,
+                    const int64_t *d_set_off, int32_t *d_set_pos, int64_t capacity, uint8_t *ws, const WsLayout &L,
+                    const SetLayout &S) {
+    SnpSetArgs a = {};
+    a.pos = d_pos; a.tgt = d_tgt;
+    a.absent_bits = reinterpret_cast<const uint32_t *>(ws + L.off_absent);
+    a.win_lo = reinterpret_cast<const int32_t *>(ws + L.off_win_lo);
+    a.win_hi = reinterpret_cast<const int32_t *>(ws + L.off_win_hi);
+    a.T = T; a.W = W; a.bonus = bonus; a.max_mm = max_mm; a.penalty = penalty;
+    a.score = d_score; a.nsnp = d_nsnp;
+    a.set_len = reinterpret_cast<int32_t *>(ws + S.off_len);
+    a.set_off = d_set_off; a.set_pos = d_set_pos; a.capacity = capacity;
+    a.arena = ws + L.off_arena; a.arena_bytes = S.arena_bytes;
+    const size_t smem = (size_t)kPairWarps * kPairSmemCap * kSetEntryBytes;
+    int64_t grid = (S.n + kPairWarps - 1) / kPairWarps;
+    if (grid > kNumSM * 3) grid = kNumSM * 3;
+    cudaError_t e;
+    if (fill) {
+        static thread_local SmemGrant grant;
+        e = grant_smem(grant, snp_set_kernel<true>, smem);
+        if (e == cudaSuccess) e = launch(snp_set_kernel<true>, (unsigned)grid, kPairWarps * 32, smem, st, false, a);
+    } else {
+        static thread_local SmemGrant grant;
+        e = grant_smem(grant, snp_set_kernel<false>, smem);
+        if (e == cudaSuccess) e = launch(snp_set_kernel<false>, (unsigned)grid, kPairWarps * 32, smem, st, false, a);
+    }
+    if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "snp_set_kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+}  // namespace
+
+extern "C" size_t sstar_b200_snp_set_workspace_bytes(int64_t V, int32_t R, int32_t T, int32_t W,
+                                                     int32_t max_win_variants) {
+    (void)R;
+    if (V < 0 || T < 1 || W < 0) return 0;
+    return make_set_layout(make_layout(V, T, W, max_win_variants < 0 ? 0 : max_win_variants), W, T).total;
+}
+
+extern "C" int sstar_b200_snp_set_offsets(int device, void *stream, const int8_t *d_ref_gt, const int8_t *d_tgt_gt,
+                                          const int32_t *d_pos, int64_t V, int32_t R, int32_t T,
+                                          const int32_t *d_win_start, const int32_t *d_win_end, int32_t W,
+                                          int32_t match_bonus, int32_t max_mismatch, int32_t mismatch_penalty,
+                                          int64_t *d_score, int32_t *d_nsnp, int64_t *d_set_off, void *d_workspace,
+                                          size_t workspace_bytes, const sstar_b200_options *opts) {
+    WsLayout L; int algo;
+    int rc = check_common(device, V, R, T, W, d_workspace, workspace_bytes, opts, &L, &algo);
+    if (rc) return rc;
+    const SetLayout S = make_set_layout(L, W, T);
+    if (workspace_bytes < S.total) return fail(SSTAR_B200_EWORKSPACE, "workspace too small for SNP sets%s");
+    if (!d_set_off) return fail(SSTAR_B200_EINVAL, "null offsets pointer%s");
+    if (W > 0 && (!d_win_start || !d_win_end || !d_score || !d_nsnp))
+        return fail(SSTAR_B200_EINVAL, "null window/output pointer%s");
+    if (V > 0 && (!d_pos || !d_tgt_gt || !d_ref_gt)) return fail(SSTAR_B200_EINVAL, "null input pointer%s");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *ws = (uint8_t *)d_workspace;
+    if (S.n == 0) {
+        cudaError_t e = cudaMemsetAsync(d_set_off, 0, 8, st);
+        if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+        return 0;
+    }
+    rc = launch_prep(st, 0, L.G, d_ref_gt, d_tgt_gt, V, R, T, d_pos, d_win_start, d_win_end, nullptr, 0, 0, W, ws, L);
+    if (rc) return rc;
+    rc = launch_snp_sets(st, false, d_tgt_gt, d_pos, T, W, match_bonus, max_mismatch, mismatch_penalty, d_score, d_nsnp,
+                         nullptr, nullptr, 0, ws, L, S);
+    if (rc) return rc;
+    const int32_t *len = reinterpret_cast<const int32_t *>(ws + S.off_len);
+    int64_t *blocks = reinterpret_cast<int64_t *>(ws + S.off_blocks);
+    cudaError_t e = launch(scan_sum_kernel, (unsigned)S.nb, kScanThreads, 0, st, false, len, S.n, blocks);
+    if (e == cudaSuccess) e = launch(scan_blocks_kernel, 1u, 1024u, 0, st, false, blocks, S.nb, d_set_off + S.n);
+    if (e == cudaSuccess)
+        e = launch(scan_apply_kernel, (unsigned)S.nb, kScanThreads, 0, st, false, len, S.n, (const int64_t *)blocks, d_set_off);
+    if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "scan launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int sstar_b200_snp_set_fill(int device, void *stream, const int8_t *d_tgt_gt, const int32_t *d_pos,
+                                       int64_t V, int32_t R, int32_t T, int32_t W, int32_t match_bonus,
+                                       int32_t max_mismatch, int32_t mismatch_penalty, const int64_t *d_set_off,
+                                       int32_t *d_set_pos, int64_t capacity, void *d_workspace,
+                                       size_t workspace_bytes, const sstar_b200_options *opts) {
+    WsLayout L; int algo;
+    int rc = check_common(device, V, R, T, W, d_workspace, workspace_bytes, opts, &L, &algo);
+    if (rc) return rc;
+    const SetLayout S = make_set_layout(L, W, T);
+    if (workspace_bytes < S.total) return fail(SSTAR_B200_EWORKSPACE, "workspace too small for SNP sets%s");
+    if (capacity < 0) return fail(SSTAR_B200_EINVAL, "capacity must be >= 0%s");
+    if (S.n == 0 || capacity == 0) return 0;
+    if (!d_set_off || !d_set_pos || !d_pos || !d_tgt_gt) return fail(SSTAR_B200_EINVAL, "null pointer%s");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    return launch_snp_sets((cudaStream_t)stream, true, d_tgt_gt, d_pos, T, W, match_bonus, max_mismatch,
+                           mismatch_penalty, nullptr, nullptr, d_set_off, d_set_pos, capacity,
+                           (uint8_t *)d_workspace, L, S);
 }

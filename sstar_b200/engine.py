@@ -127,6 +127,60 @@ class ScoreEngine:
         self.launches = self.lib.sstar_b200_last_launch_count()
         return score, nsnp
 
+    def snp_sets_device(self, ref_d, tgt_d, pos_d, ws_d, we_d, match_bonus=5000, max_mismatch=5,
+                        mismatch_penalty=-10000, max_win_variants=0):
+        """Scores plus the sites on every unit's best chain (the legacy S*_SNP_number / S*_SNPs columns).
+
+        Device tensors in; returns device tensors (score [W,T] int64, nsnp [W,T] int32,
+        set_off [W*T+1] int64, set_pos [total] int32): unit u = w*T + t owns
+        set_pos[set_off[u]:set_off[u+1]], positions ascending.  One host read (the total) sits
+        between the two C-ABI calls."""
+        torch = self.torch
+        V, R = ref_d.shape
+        T = tgt_d.shape[1]
+        W = ws_d.shape[0]
+        assert ref_d.dtype == torch.int8 and tgt_d.dtype == torch.int8 and pos_d.dtype == torch.int32
+        assert ref_d.is_contiguous() and tgt_d.is_contiguous() and tgt_d.shape[0] == V
+        score = torch.empty((W, T), dtype=torch.int64, device=self.tdev)
+        nsnp = torch.empty((W, T), dtype=torch.int32, device=self.tdev)
+        set_off = torch.empty(W * T + 1, dtype=torch.int64, device=self.tdev)
+        need = self.lib.sstar_b200_snp_set_workspace_bytes(int(V), int(R), int(T), int(W), int(max_win_variants))
+        if need == 0:
+            raise SstarB200Error("invalid shapes for workspace sizing")
+        ws = self._dbuf("ws", need, torch.uint8)
+        opts = _cabi.Options(algo=_cabi.ALGOS["auto"], max_win_variants=int(max_win_variants))
+        params = (int(match_bonus), int(max_mismatch), int(mismatch_penalty))
+        rc = self.lib.sstar_b200_snp_set_offsets(
+            self.device, self._stream_ptr(), ref_d.data_ptr(), tgt_d.data_ptr(), pos_d.data_ptr(), V, R, T,
+            ws_d.data_ptr(), we_d.data_ptr(), W, *params, score.data_ptr(), nsnp.data_ptr(), set_off.data_ptr(),
+            ws.data_ptr(), ws.numel(), ctypes.byref(opts))
+        _cabi.check(rc)
+        launches = self.lib.sstar_b200_last_launch_count()
+        total = int(set_off[-1].item())
+        set_pos = torch.empty(max(total, 1), dtype=torch.int32, device=self.tdev)
+        rc = self.lib.sstar_b200_snp_set_fill(
+            self.device, self._stream_ptr(), tgt_d.data_ptr(), pos_d.data_ptr(), V, R, T, W, *params,
+            set_off.data_ptr(), set_pos.data_ptr(), total, ws.data_ptr(), ws.numel(), ctypes.byref(opts))
+        _cabi.check(rc)
+        self.launches = launches + self.lib.sstar_b200_last_launch_count()
+        return score, nsnp, set_off, set_pos[:total]
+
+    def snp_sets_host(self, ref_gts, tgt_gts, pos, win_start, win_end, match_bonus=5000, max_mismatch=5,
+                      mismatch_penalty=-10000):
+        """numpy in, numpy out: (score, nsnp, set_off, set_pos) as in ``snp_sets_device``."""
+        torch = self.torch
+        ref = as_int8(ref_gts, "ref_gts")
+        tgt = as_int8(tgt_gts, "tgt_gts")
+        p = check_positions(pos)
+        ws = np.ascontiguousarray(win_start, dtype=np.int32)
+        we = np.ascontiguousarray(win_end, dtype=np.int32)
+        if ref.shape[0] != tgt.shape[0] or ref.shape[0] != p.shape[0]:
+            raise SstarB200Error("ref_gts, tgt_gts and pos must have the same number of rows")
+        dev = lambda a: torch.from_numpy(a).to(self.tdev)
+        out = self.snp_sets_device(dev(ref), dev(tgt), dev(p), dev(ws), dev(we), match_bonus, max_mismatch,
+                                   mismatch_penalty, max_win_variants=max_window_variants(p, ws, we))
+        return tuple(t.cpu().numpy() for t in out)
+
     def pack_device(self, ref_d, tgt_d, W=1, max_win_variants=0, stream=None):
         V, R = ref_d.shape
         T = tgt_d.shape[1]

@@ -237,3 +237,29 @@ def test_reference_case_generator_scopes_alignment_to_requested_chromosome(tmp_p
     assert len(windows) == 1 and windows[0]["chr_name"] == "1" and np.array_equal(windows[0]["pos"], [100, 200])
     pos = np.array([1, 10, 20, 21, 30])   # closed interval boundaries (test_window_data_generator.py:107-113)
     assert np.array_equal(pos[(pos >= 10) & (pos <= 20)], [10, 20])
+
+
+@pytest.mark.parametrize("phased", [False, True])
+def test_legacy_score_table_format(phased):
+    """The legacy table writer (host side of the SNP-set extension) on chains from the oracle:
+    identical to the reference's legacy fixture but for the one unit whose score changed since."""
+    from oracle import c_oracle
+    from sstar_b200.snp_sets import legacy_score_table
+    data, _, tgt_names = tiling_port.load_populations(
+        os.path.join(FIXTURES, "test.vcf"), os.path.join(FIXTURES, "test.ref.ind.list"),
+        os.path.join(FIXTURES, "test.tgt.ind.list"), phased, "21")
+    rg, tg, pos = data["21"]
+    wins = tiling_port.split_windows(pos, 50000, 10000)
+    ws = np.array([w[0] for w in wins], dtype=np.int32)
+    we = np.array([w[1] for w in wins], dtype=np.int32)
+    labels = [f"{n}_{h}" for n in tgt_names for h in (1, 2)] if phased else list(tgt_names)
+    text = legacy_score_table("21", ws, we, labels, *c_oracle.snp_sets(rg, tg, pos, ws, we))
+    tag = "phased" if phased else "unphased"
+    with open(os.path.join(FIXTURES, f"test.score.{tag}.exp.results.tsv")) as f:
+        want = f.read().splitlines()
+    got = text.splitlines()
+    diff = [(g, w) for g, w in zip(got, want) if g != w]
+    assert len(got) == len(want)
+    assert len(diff) == (0 if phased else 1)
+    if diff:
+        assert diff[0][1] == "21\t30000\t80000\tind1\tNA\t5\tNA\tNA"
