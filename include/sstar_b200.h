@@ -64,7 +64,8 @@ typedef struct sstar_b200_options {
     int32_t algo;             /* SSTAR_B200_ALGO_* */
     int32_t max_win_variants; /* upper bound on variants inside any window (hi - lo): sizes the
                                  pairwise list arena and the window groups of the score kernel;
-                                 0 = unknown (sized for V) */
+                                 0 = unknown (sized for V).  An understated hint is safe: it
+                                 only leaves the pairwise kernel fewer concurrent list slabs */
     int32_t flags;            /* SSTAR_B200_FLAG_* */
     int32_t reserved[5];      /* must be zero */
 } sstar_b200_options;

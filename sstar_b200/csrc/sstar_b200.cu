@@ -91,6 +91,9 @@ WsLayout make_layout(int64_t V, int32_t T, int32_t W, int32_t max_win_variants) 
         want = worst > ((size_t)4 << 20) ? worst : ((size_t)4 << 20);
         if (want > worst * (size_t)(kNumSM * kPairWarps)) want = worst * (size_t)(kNumSM * kPairWarps);
     }
+    // whatever the hint says, one slab of a window spanning every variant always fits: an
+    // understated hint costs parallelism in the pairwise kernel, never results
+    if (want < worst + 8) want = worst + 8;
     L.arena_entries = align_up(want, 8);
     L.off_arena = off;   off = align_up(off + L.arena_entries * 13, 256);
     L.total = off;
@@ -580,8 +583,12 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
     CUDA_TRY(cudaEventRecord(pc->entry, st));
     CUDA_TRY(cudaStreamWaitEvent(pc->copy, pc->entry, 0));
     if (zero_copy_in) {
-        // Small input read in place: the pack starts at once on the caller's stream while the copy
-        // stream brings pos / windows over and resolves the window bounds; they meet before the DP.
+        // Small input read in place: the pack goes out first on the caller's stream (its tile loads
+        // are the transfer), then the copy stream brings pos / windows over and resolves the window
+        // bounds behind it; the two meet before the DP.
+        rc = launch_prep(st, 0, L.G, (const int8_t *)m_ref, (const int8_t *)m_tgt, V, R, T, d_pos, nullptr, nullptr,
+                         nullptr, 0, 0, 0, ws, L);
+        if (rc) return rc;
         if (V > 0) CUDA_TRY(cudaMemcpyAsync(d_pos, h_pos, (size_t)V * 4, cudaMemcpyHostToDevice, pc->copy));
         if (W > 0) {
             CUDA_TRY(cudaMemcpyAsync(d + h.off_ws, h_win_start, (size_t)W * 4, cudaMemcpyHostToDevice, pc->copy));
@@ -591,9 +598,6 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
                          (const int32_t *)(d + h.off_we), nullptr, 0, 0, W, ws, L);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(pc->chunk[0], pc->copy));
-        rc = launch_prep(st, 0, L.G, (const int8_t *)m_ref, (const int8_t *)m_tgt, V, R, T, d_pos, nullptr, nullptr,
-                         nullptr, 0, 0, 0, ws, L);
-        if (rc) return rc;
         CUDA_TRY(cudaStreamWaitEvent(st, pc->chunk[0], 0));
         int64_t *z_score = copy_out ? (int64_t *)(d + h.off_score) : (int64_t *)m_score;
         int32_t *z_nsnp = copy_out ? (int32_t *)(d + h.off_nsnp) : (int32_t *)m_nsnp;

@@ -291,3 +291,27 @@ def test_degenerate_shapes(eng):
     so, no = c_oracle.score_windows(z8(len(pos), 1), tgt, pos, [1], [1000])
     s, n = eng.score_host(z8(len(pos), 1), tgt, pos, [1], [1000])
     assert np.array_equal(s, so) and np.array_equal(n, no) and s[0, 0] == (pos[-1] - pos[0]) + 5000 * (len(pos) - 1)
+
+
+def test_understated_window_hint_is_safe(eng):
+    """options.max_win_variants far below the truth: the pairwise arena still holds a slab of the
+    largest window, so the results do not change (only the pairwise kernel's parallelism does)."""
+    import torch
+    rng = np.random.default_rng(11)
+    V = 4000
+    pos = np.cumsum(rng.integers(1, 30, size=V)).astype(np.int32)
+    tgt = rng.choice([0, 1, 2], size=(V, 6), p=[0.3, 0.4, 0.3]).astype(np.int8)
+    ref = np.zeros((V, 3), dtype=np.int8)
+    ref[rng.random(V) < 0.2, 1] = 1
+    ws = np.array([1, 500], dtype=np.int32)
+    we = np.array([int(pos[-1]), 40000], dtype=np.int32)
+    so, no = c_oracle.score_windows(ref, tgt, pos, ws, we)
+    dev = eng.tdev
+    d = [torch.from_numpy(x).to(dev) for x in (ref, tgt, pos, ws, we)]
+    for algo in ALGOS:
+        s, n = eng.score_device(*d, algo=algo, max_win_variants=1)
+        assert np.array_equal(s.cpu().numpy(), so) and np.array_equal(n.cpu().numpy(), no), algo
+    got = eng.snp_sets_device(*d, max_win_variants=1)
+    want = c_oracle.snp_sets(ref, tgt, pos, ws, we)
+    for a, b in zip(got, want):
+        assert np.array_equal(a.cpu().numpy(), b)
