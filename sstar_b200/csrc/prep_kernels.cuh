@@ -30,26 +30,49 @@ __device__ __forceinline__ int32_t warp_lower_bound(const int32_t *__restrict__ 
     return lo + __popc(__ballot_sync(0xffffffffu, below));
 }
 
+// Fetch CTA `blk` of n_fetch: its share of pos | win_start | win_end, mapped host memory -> device.
+__device__ __forceinline__ void fetch_block(const BoundsArgs &a, int blk, int nthreads, int tid) {
+    const int64_t V = a.V, W = a.W, nw = V + 2 * W;
+    const int64_t per = (((nw + a.n_fetch - 1) / a.n_fetch) + 3) & ~(int64_t)3;
+    const int64_t i0 = (int64_t)blk * per, i1 = min(nw, i0 + per);
+    int32_t *dpos = const_cast<int32_t *>(a.pos), *dws = const_cast<int32_t *>(a.win_start),
+            *dwe = const_cast<int32_t *>(a.win_end);
+#pragma unroll 4
+    for (int64_t i = i0 + tid; i < i1; i += nthreads) {
+        if (i < V) dpos[i] = a.src_pos[i];
+        else if (i < V + W) dws[i - V] = a.src_ws[i - V];
+        else dwe[i - V - W] = a.src_we[i - V - W];
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) flag_publish(a.fflag + blk, a.stamp);
+}
+
 __device__ __forceinline__ void bounds_block(const BoundsArgs &a, int block, int nthreads, int tid) {
     const int lane = tid & 31;
     const int w = block * (nthreads >> 5) + (tid >> 5);
     if (block == 0 && tid < kMaxSlots) a.hdr->n_slow[tid] = 0;
-    if (w >= a.W) return;
-    const int32_t sb = a.seg ? a.seg[w] : 0;
-    const int32_t se = a.seg ? a.seg[w + 1] : a.V;
-    const int64_t s = a.win_start ? a.win_start[w] : a.fixed_start;
-    const int64_t e = a.win_end ? a.win_end[w] : a.fixed_end;
-    const int32_t lo = warp_lower_bound(a.pos, sb, se, s, lane);
-    int32_t hi = warp_lower_bound(a.pos, lo, se, e + 1, lane);
-    if (hi < lo) hi = lo;
-    if (lane < 2 && hi > lo) {  // first / last position, so the score kernel need not chase them
-        const int32_t v = __ldg(a.pos + (lane == 0 ? lo : hi - 1));
-        (lane == 0 ? a.win_pfirst : a.win_plast)[w] = v;
+    if (a.n_fetch) {  // pos / windows are being fetched by the grid's first CTAs
+        if (tid < a.n_fetch) flag_wait(a.fflag + tid, a.stamp);
+        __syncthreads();
     }
-    if (lane == 0) {
-        a.win_lo[w] = lo;
-        a.win_hi[w] = hi;
-        a.win_bail[w] = 0u;
+    if (w < a.W) {
+        const int32_t sb = a.seg ? a.seg[w] : 0;
+        const int32_t se = a.seg ? a.seg[w + 1] : a.V;
+        const int64_t s = a.win_start ? a.win_start[w] : a.fixed_start;
+        const int64_t e = a.win_end ? a.win_end[w] : a.fixed_end;
+        const int32_t lo = warp_lower_bound(a.pos, sb, se, s, lane);
+        int32_t hi = warp_lower_bound(a.pos, lo, se, e + 1, lane);
+        if (hi < lo) hi = lo;
+        if (lane < 2 && hi > lo) {  // first / last position, so the score kernel need not chase them
+            const int32_t v = __ldg(a.pos + (lane == 0 ? lo : hi - 1));
+            (lane == 0 ? a.win_pfirst : a.win_plast)[w] = v;
+        }
+        if (lane == 0) {
+            a.win_lo[w] = lo;
+            a.win_hi[w] = hi;
+            a.win_bail[w] = 0u;
+        }
     }
 }
 
@@ -324,45 +347,61 @@ prep_kernel(const __grid_constant__ PackArgs p, const __grid_constant__ BoundsAr
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar[2];
     pdl_launch_dependents();  // let the next kernel's CTAs get scheduled while this grid drains
-    if ((int)blockIdx.x >= n_pack) {
-        bounds_block(b, (int)blockIdx.x - n_pack, kPackThreads, threadIdx.x);
+    if ((int)blockIdx.x < b.n_fetch) {
+        fetch_block(b, (int)blockIdx.x, kPackThreads, threadIdx.x);
+        return;
+    }
+    const int blk = (int)blockIdx.x - b.n_fetch;
+    if (blk >= n_pack) {
+        bounds_block(b, blk - n_pack, kPackThreads, threadIdx.x);
         return;
     }
     const int tid = threadIdx.x;
-    const int32_t g0 = p.g_begin + blockIdx.x * p.gpc;
-    const int ng = min(p.gpc, p.g_end - g0);
-    const int32_t k0 = g0 * 32;
-    const int nrows = min(ng * 32, p.V - k0);
-    if (mode == 1) {
-        pack_tile_direct(p, smem, g0, ng, nrows);
-        return;
+    // A pack CTA takes tiles blockIdx.x, blockIdx.x + n_pack, ...: one tile each in the usual grid;
+    // a grid cut short (p.n_tiles > n_pack) walks the matrix front to back with a bounded number of
+    // tiles in flight -- what a matrix read in place over PCIe wants.
+    uint32_t parity = 0;
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        fence_mbar_init();
     }
-    uint8_t *s_ref = smem + p.gpc * 32 + align16(p.gpc * 8);
-    uint8_t *s_tgt = s_ref + p.ref_tile_bytes;
-    const int8_t *gref = p.ref + (size_t)k0 * p.R;
-    const int8_t *gtgt = p.tgt + (size_t)k0 * p.T;
-    const uint32_t ref_bytes = (uint32_t)nrows * (uint32_t)p.R, tgt_bytes = (uint32_t)nrows * (uint32_t)p.T;
-    uint32_t rph = 0, tph = 0;
-    const bool bulk = ((((uintptr_t)gref | (uintptr_t)gtgt) & 15) == 0) && (((ref_bytes | tgt_bytes) & 15u) == 0);
-    if (bulk) {
-        // one thread hands both spans to the TMA engine; no registers, no issue slots for the copy
-        if (tid == 0) {
-            mbar_init(&s_bar[0], 1);
-            fence_mbar_init();
-            mbar_expect_tx(&s_bar[0], ref_bytes + tgt_bytes);
-            bulk_g2s(s_ref, gref, ref_bytes, &s_bar[0]);
-            bulk_g2s(s_tgt, gtgt, tgt_bytes, &s_bar[0]);
+    for (int tile = blk; tile < p.n_tiles; tile += n_pack) {
+        const int32_t g0 = p.g_begin + tile * p.gpc;
+        const int ng = min(p.gpc, p.g_end - g0);
+        const int32_t k0 = g0 * 32;
+        const int nrows = min(ng * 32, p.V - k0);
+        if (mode == 1) {
+            pack_tile_direct(p, smem, g0, ng, nrows);
+            __syncthreads();
+            continue;
         }
-        __syncthreads();  // barrier initialised before anyone polls it
-        mbar_wait(&s_bar[0], 0);
-    } else {
-        rph = stage_span(s_ref, gref, ref_bytes, tid, kPackThreads);
-        tph = stage_span(s_tgt, gtgt, tgt_bytes, tid, kPackThreads);
-        __syncthreads();
+        uint8_t *s_ref = smem + p.gpc * 32 + align16(p.gpc * 8);
+        uint8_t *s_tgt = s_ref + p.ref_tile_bytes;
+        const int8_t *gref = p.ref + (size_t)k0 * p.R;
+        const int8_t *gtgt = p.tgt + (size_t)k0 * p.T;
+        const uint32_t ref_bytes = (uint32_t)nrows * (uint32_t)p.R, tgt_bytes = (uint32_t)nrows * (uint32_t)p.T;
+        uint32_t rph = 0, tph = 0;
+        const bool bulk = ((((uintptr_t)gref | (uintptr_t)gtgt) & 15) == 0) && (((ref_bytes | tgt_bytes) & 15u) == 0);
+        if (bulk) {
+            // one thread hands both spans to the TMA engine; no registers, no issue slots for the copy
+            if (tid == 0) {
+                mbar_expect_tx(&s_bar[0], ref_bytes + tgt_bytes);
+                bulk_g2s(s_ref, gref, ref_bytes, &s_bar[0]);
+                bulk_g2s(s_tgt, gtgt, tgt_bytes, &s_bar[0]);
+            }
+            __syncthreads();  // barrier initialised before anyone polls it
+            mbar_wait(&s_bar[0], parity);
+            parity ^= 1u;
+        } else {
+            rph = stage_span(s_ref, gref, ref_bytes, tid, kPackThreads);
+            tph = stage_span(s_tgt, gtgt, tgt_bytes, tid, kPackThreads);
+            __syncthreads();
+        }
+        const bool aligned = ((tph | (uint32_t)p.T) & 3u) == 0;
+        if (aligned) pack_tile<true>(p, smem, g0, ng, nrows, rph, tph);
+        else         pack_tile<false>(p, smem, g0, ng, nrows, rph, tph);
+        __syncthreads();  // the tile and its flags are done with before the next one lands
     }
-    const bool aligned = ((tph | (uint32_t)p.T) & 3u) == 0;
-    if (aligned) pack_tile<true>(p, smem, g0, ng, nrows, rph, tph);
-    else         pack_tile<false>(p, smem, g0, ng, nrows, rph, tph);
 }
 
 }  // namespace sstar

@@ -14,6 +14,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <chrono>
+
 #include "sstar_b200.h"
 #include "common.cuh"
 #include "prep_kernels.cuh"
@@ -79,6 +82,7 @@ WsLayout make_layout(int64_t V, int32_t T, int32_t W, int32_t max_win_variants) 
     L.off_win_plast = off;  off = align_up(off + w * 4, 256);
     L.off_slow = off;    off = align_up(off + w * 4, 256);
     L.off_bail = off;    off = align_up(off + w * 4, 256);
+    L.off_fflag = off;   off += align_up((size_t)kMaxFetchCtas * 8, 256);
     // pairwise list arena: at least one slab of the worst-case window must fit
     size_t worst = (size_t)(V > 0 ? V : 1);
     size_t want;
@@ -143,12 +147,20 @@ cudaError_t launch(void (*kernel)(KArgs...), unsigned grid, unsigned block, size
 int launch_prep(cudaStream_t st, int64_t g_begin, int64_t g_end, const int8_t *d_ref, const int8_t *d_tgt,
                 int64_t V, int32_t R, int32_t T, const int32_t *d_pos, const int32_t *d_ws, const int32_t *d_we,
                 const int32_t *d_seg, int32_t fixed_s, int32_t fixed_e, int32_t W, uint8_t *ws,
-                const WsLayout &L) {
+                const WsLayout &L, int pack_ctas = 0, uint64_t stamp = 0, const int32_t *const *fetch_src = nullptr) {
     PackArgs p = {};
     BoundsArgs b = {};
+    b.stamp = stamp;
+    b.fflag = reinterpret_cast<uint64_t *>(ws + L.off_fflag);
+    if (fetch_src && W > 0 && stamp) {  // {pos, win_start, win_end} in mapped host memory
+        b.src_pos = fetch_src[0]; b.src_ws = fetch_src[1]; b.src_we = fetch_src[2];
+        const int64_t words = V + 2 * (int64_t)W;
+        b.n_fetch = (int32_t)((words + 2047) / 2048);
+        if (b.n_fetch > kMaxFetchCtas) b.n_fetch = kMaxFetchCtas;
+    }
     int n_pack = 0, mode = 0;
     size_t smem = 0;
-    const int n_bounds = W > 0 ? (W + (kPackThreads / 32) - 1) / (kPackThreads / 32) : 0;
+    const int n_bounds = W > 0 ? (W + kBoundsWindowsPerCta - 1) / kBoundsWindowsPerCta : 0;
     if (g_end > g_begin) {
         const int64_t ngroups = g_end - g_begin;
         p.ref = d_ref; p.tgt = d_tgt;
@@ -178,6 +190,8 @@ int launch_prep(cudaStream_t st, int64_t g_begin, int64_t g_end, const int8_t *d
             smem = fixed;
         }
         n_pack = (int)((ngroups + gpc - 1) / gpc);
+        p.n_tiles = n_pack;
+        if (pack_ctas > 0 && pack_ctas < n_pack) n_pack = pack_ctas;
     }
     if (W > 0) {
         b.pos = d_pos; b.win_start = d_ws; b.win_end = d_we; b.seg = d_seg;
@@ -191,12 +205,28 @@ int launch_prep(cudaStream_t st, int64_t g_begin, int64_t g_end, const int8_t *d
         b.hdr = reinterpret_cast<WsHeader *>(ws);
     }
     if (n_pack + n_bounds == 0) return 0;
+    const int n_fetch = b.n_fetch;
     static thread_local SmemGrant prep_grant;
     cudaError_t e = grant_smem(prep_grant, prep_kernel, smem);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaFuncSetAttribute(prep): %s", cudaGetErrorString(e));
-    e = launch(prep_kernel, (unsigned)(n_pack + n_bounds), kPackThreads, smem, st, false, p, b, n_pack, mode);
+    e = launch(prep_kernel, (unsigned)(n_fetch + n_pack + n_bounds), kPackThreads, smem, st, false, p, b, n_pack, mode);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "prep_kernel launch: %s", cudaGetErrorString(e));
     return 0;
+}
+
+// CTAs of the pack grid when the matrices are read in place over PCIe: 32 already saturate the
+// link (profiles/r01_side_measurements.txt); a short grid keeps the tiles arriving front to back
+constexpr int kInPlacePackCtas = 64;
+
+// A fresh 64-bit value per call: the fetch flags left in the workspace by earlier calls (or
+// whatever an uninitialised workspace holds) never match it.
+uint64_t next_stamp() {
+    static std::atomic<uint64_t> counter{(uint64_t)std::chrono::steady_clock::now().time_since_epoch().count()};
+    uint64_t z = counter.fetch_add(0x9e3779b97f4a7c15ull) + 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    z ^= z >> 31;
+    return z ? z : 1;
 }
 
 struct ScoreCall {
@@ -344,8 +374,9 @@ int sstar_b200_pack(int device, void *stream, const int8_t *d_ref_gt, const int8
     if (V > 0 && (!d_ref_gt || !d_tgt_gt)) return fail(SSTAR_B200_EINVAL, "null genotype pointer%s");
     DeviceGuard guard(device);
     if (guard.err != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    const char *env = getenv("SSTAR_B200_PACK_CTAS");  // experiment hook (tools/exp_pack_ctas.py)
     return launch_prep((cudaStream_t)stream, 0, L.G, d_ref_gt, d_tgt_gt, V, R, T, nullptr, nullptr, nullptr, nullptr,
-                       0, 0, 0, (uint8_t *)d_workspace, L);
+                       0, 0, 0, (uint8_t *)d_workspace, L, env ? atoi(env) : 0);
 }
 
 int sstar_b200_score_packed(int device, void *stream, const int8_t *d_tgt_gt, const int32_t *d_pos,
@@ -521,10 +552,11 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
 
     // the pipelined path needs page-locked inputs (truly asynchronous copies next to the caller's
     // stream) and mapped output tables (stored in place by the kernels)
-    void *m_score = nullptr, *m_nsnp = nullptr, *m_any = nullptr, *m_ref = nullptr, *m_tgt = nullptr;
+    void *m_score = nullptr, *m_nsnp = nullptr, *m_ref = nullptr, *m_tgt = nullptr, *m_pos = nullptr, *m_ws = nullptr,
+         *m_we = nullptr;
     bool mapped = !(opts && (opts->flags & SSTAR_B200_FLAG_STAGED_COPIES));
-    mapped = mapped && mapped_pointer(h_pos, &m_any) && mapped_pointer(h_win_start, &m_any) &&
-             mapped_pointer(h_win_end, &m_any) && mapped_pointer(h_score, &m_score) && mapped_pointer(h_nsnp, &m_nsnp) &&
+    mapped = mapped && mapped_pointer(h_pos, &m_pos) && mapped_pointer(h_win_start, &m_ws) &&
+             mapped_pointer(h_win_end, &m_we) && mapped_pointer(h_score, &m_score) && mapped_pointer(h_nsnp, &m_nsnp) &&
              mapped_pointer(h_ref_gt, &m_ref) && mapped_pointer(h_tgt_gt, &m_tgt);
 
     if (!mapped) {  // staged: copy in, run, copy out, all on the caller's stream
@@ -579,26 +611,16 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
     bool sorted = true;
     for (int32_t w = 1; w < W && sorted; ++w) sorted = h_win_end[w] >= h_win_end[w - 1];
 
-    // the copy stream starts after whatever the caller already queued (it reuses the scratch)
-    CUDA_TRY(cudaEventRecord(pc->entry, st));
-    CUDA_TRY(cudaStreamWaitEvent(pc->copy, pc->entry, 0));
     if (zero_copy_in) {
-        // Small input read in place: the pack goes out first on the caller's stream (its tile loads
-        // are the transfer), then the copy stream brings pos / windows over and resolves the window
-        // bounds behind it; the two meet before the DP.
-        rc = launch_prep(st, 0, L.G, (const int8_t *)m_ref, (const int8_t *)m_tgt, V, R, T, d_pos, nullptr, nullptr,
-                         nullptr, 0, 0, 0, ws, L);
+        // Small input read in place, in ONE prep grid on the caller's stream and without the copy
+        // engine.  Its first CTAs fetch pos / windows from mapped host memory; a short run of pack
+        // CTAs walks the matrices front to back, their tile loads being the transfer; the bounds
+        // CTAs wait for the fetch and resolve the windows.
+        const int32_t *const fetch_src[3] = {(const int32_t *)m_pos, (const int32_t *)m_ws, (const int32_t *)m_we};
+        rc = launch_prep(st, 0, L.G, (const int8_t *)m_ref, (const int8_t *)m_tgt, V, R, T, d_pos,
+                         (const int32_t *)(d + h.off_ws), (const int32_t *)(d + h.off_we), nullptr, 0, 0, W, ws, L,
+                         kInPlacePackCtas, next_stamp(), fetch_src);
         if (rc) return rc;
-        if (V > 0) CUDA_TRY(cudaMemcpyAsync(d_pos, h_pos, (size_t)V * 4, cudaMemcpyHostToDevice, pc->copy));
-        if (W > 0) {
-            CUDA_TRY(cudaMemcpyAsync(d + h.off_ws, h_win_start, (size_t)W * 4, cudaMemcpyHostToDevice, pc->copy));
-            CUDA_TRY(cudaMemcpyAsync(d + h.off_we, h_win_end, (size_t)W * 4, cudaMemcpyHostToDevice, pc->copy));
-        }
-        rc = launch_prep(pc->copy, 0, 0, nullptr, nullptr, V, R, T, d_pos, (const int32_t *)(d + h.off_ws),
-                         (const int32_t *)(d + h.off_we), nullptr, 0, 0, W, ws, L);
-        if (rc) return rc;
-        CUDA_TRY(cudaEventRecord(pc->chunk[0], pc->copy));
-        CUDA_TRY(cudaStreamWaitEvent(st, pc->chunk[0], 0));
         int64_t *z_score = copy_out ? (int64_t *)(d + h.off_score) : (int64_t *)m_score;
         int32_t *z_nsnp = copy_out ? (int32_t *)(d + h.off_nsnp) : (int32_t *)m_nsnp;
         const ScoreCall zc = {(const int8_t *)m_tgt, d_pos, V, T, match_bonus, max_mismatch, mismatch_penalty, z_score,
@@ -611,6 +633,9 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
         }
         return 0;
     }
+    // the copy stream starts after whatever the caller already queued (it reuses the scratch)
+    CUDA_TRY(cudaEventRecord(pc->entry, st));
+    CUDA_TRY(cudaStreamWaitEvent(pc->copy, pc->entry, 0));
     if (V > 0) CUDA_TRY(cudaMemcpyAsync(d_pos, h_pos, (size_t)V * 4, cudaMemcpyHostToDevice, st));
     if (W > 0) {
         CUDA_TRY(cudaMemcpyAsync(d + h.off_ws, h_win_start, (size_t)W * 4, cudaMemcpyHostToDevice, st));
