@@ -482,9 +482,12 @@ def run_ours(args, world, rank, local):
             "e2e": {"value": total_units / (e2e_ms / k * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(V * (R + T) + 4 * V + 8 * W),
                     "d2h_bytes_per_step": int(12 * W * T), "ms_per_step": e2e_ms / k,
-                    "api": "ScoreEngine.score_pinned -> sstar_b200_score_windows_host: pinned host buffers, chunked "
-                           "H2D on a copy stream overlapped with pack + scoring, result tables stored in place "
-                           "into host memory; wall clock incl. the stream sync",
+                    "api": "ScoreEngine.score_pinned -> sstar_b200_score_windows_host on pinned host buffers: "
+                           + ("matrices below 32 MB are packed in place over PCIe (the pack CTAs' tile loads are the "
+                              "H2D transfer), " if V * (R + T) < (32 << 20) else
+                              "matrices go H2D in row chunks on a copy stream overlapped with pack + scoring, ")
+                           + "result tables stored in place into host memory (D2H copies from 8 MB); wall clock "
+                             "incl. the stream sync",
                     "staged_copies_ms_per_step": staged_ms / k},
             "gpu_launches": int(launches_per_step * k),
             "kernels_per_step": int(launches_per_step),

@@ -282,6 +282,7 @@ int launch_score(cudaStream_t st, const ScoreCall &c, const WsLayout &L, int32_t
         const int words_cap = kScoreWordsCap;
         int wg = kMaxGroup;
         while (wg > 1 && (int64_t)((W + wg - 1) / wg) * tchunks < 2 * 7 * kNumSM) wg >>= 1;
+        if (const char *env = getenv("SSTAR_B200_WG")) { const int v = atoi(env); if (v >= 1 && v <= kMaxGroup) wg = v; }  // experiment hook
         if (c.disjoint) wg = 1;  // replicates share no variants (and their positions restart)
         const int64_t ngroups = (W + wg - 1) / wg;
         if (ngroups * tchunks > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "too many (window group, column chunk) tiles%s");

@@ -11,7 +11,7 @@ pin = {k: torch.from_numpy(np.ascontiguousarray(wk[k])).pin_memory() for k in ("
 d = {k: v.to(dev) for k, v in pin.items()}
 s = torch.cuda.current_stream()
 ws_ref = None
-for ctas in (0, 16, 32, 64, 96, 128, 192, 256, 384):
+for ctas in [int(x) for x in os.environ.get("CTAS", "0,16,32,64,96,128,192,256,384").split(",")]:
     os.environ["SSTAR_B200_PACK_CTAS"] = str(ctas)
     for label, src in (("PCIe", pin), ("HBM", d)):
         ts = []
