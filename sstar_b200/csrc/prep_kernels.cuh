@@ -83,7 +83,8 @@ __device__ __forceinline__ void bounds_block(const BoundsArgs &a, int block, int
 // row pitch is, so it moves global -> shared as aligned 128-bit streaming loads (the source's
 // 16-byte phase is kept; head/tail bytes go separately).
 // Compute (SIMD within a 32-bit word, 4 genotype bytes at a time):
-//   A  ref rows   : signed row sum by dp4a, one warp per row            -> absent flag  (sstar.py:87-88)
+//   A  ref rows   : signed row sum by dp4a, eight lanes per row, four rows per warp step
+//                                                                       -> absent flag  (sstar.py:87-88)
 //   B  tgt columns: a thread owns 4 adjacent columns x 32 rows; per row one (unaligned-capable)
 //                   word read, "byte != 0" and "byte == 2" folded to bit 0 of each byte and
 //                   shifted into per-8-row accumulators; PRMT transposes them into 4 column
@@ -169,9 +170,14 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
     const uint8_t *s_ref = smem + a.gpc * 32 + align16(a.gpc * 8);
     const uint8_t *s_tgt = s_ref + a.ref_tile_bytes;
 
-    // A: signed row sums of the reference panel (dp4a over the widest aligned vector)
+    // A: signed row sums of the reference panel (dp4a over the widest aligned vector).  A warp takes
+    // four rows at a time, eight lanes per row: four independent chains of loads per warp and a
+    // three-step shuffle sum instead of one row, one REDUX.
     const uint32_t ralign = (ref_phase | (uint32_t)a.R) & 15u;
-    for (int r = warp; r < ng * 32; r += nwarps) {
+    constexpr int kLpr = 8, kRpw = 32 / kLpr;  // lanes per row (4 and 16 measure the same or worse), rows per warp step
+    const int sub = lane / kLpr, l8 = lane % kLpr;
+    for (int r4 = warp * kRpw; r4 < ng * 32; r4 += nwarps * kRpw) {
+        const int r = r4 + sub;
         int sum = 0;
         if (r < nrows) {
             const uint32_t row = ref_phase + (uint32_t)r * (uint32_t)a.R;
@@ -179,7 +185,7 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
                 const uint4 *vp = reinterpret_cast<const uint4 *>(s_ref + row);
                 const int nv = a.R >> 4;
 #pragma unroll 2
-                for (int i = lane; i < nv; i += 32) {
+                for (int i = l8; i < nv; i += kLpr) {
                     const uint4 v = vp[i];
                     sum = __dp4a((int)v.x, 0x01010101, sum);
                     sum = __dp4a((int)v.y, 0x01010101, sum);
@@ -190,7 +196,7 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
                 const uint2 *vp = reinterpret_cast<const uint2 *>(s_ref + row);
                 const int nv = a.R >> 3;
 #pragma unroll 4
-                for (int i = lane; i < nv; i += 32) {
+                for (int i = l8; i < nv; i += kLpr) {
                     const uint2 v = vp[i];
                     sum = __dp4a((int)v.x, 0x01010101, sum);
                     sum = __dp4a((int)v.y, 0x01010101, sum);
@@ -199,19 +205,20 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
                 const uint32_t *vp = reinterpret_cast<const uint32_t *>(s_ref + row);
                 const int nv = a.R >> 2;
 #pragma unroll 4
-                for (int i = lane; i < nv; i += 32) sum = __dp4a((int)vp[i], 0x01010101, sum);
+                for (int i = l8; i < nv; i += kLpr) sum = __dp4a((int)vp[i], 0x01010101, sum);
             } else {
                 const int nwr = (a.R + 3) >> 2;
                 const uint32_t last_mask = (a.R & 3) ? ((1u << (8 * (a.R & 3))) - 1u) : 0xffffffffu;
-                for (int i = lane; i < nwr; i += 32) {
+                for (int i = l8; i < nwr; i += kLpr) {
                     uint32_t w = lds_word<false>(s_ref, row + 4u * i);
                     if (i == nwr - 1) w &= last_mask;
                     sum = __dp4a((int)w, 0x01010101, sum);
                 }
             }
         }
-        sum = __reduce_add_sync(0xffffffffu, sum);
-        if (lane == 0) s_flag[r] = (r < nrows) && (sum == 0);
+#pragma unroll
+        for (int d = 1; d < kLpr; d <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        if (l8 == 0) s_flag[r] = (r < nrows) && (sum == 0);
     }
     __syncthreads();
     for (int gl = warp; gl < ng; gl += nwarps) {
