@@ -315,3 +315,59 @@ def test_understated_window_hint_is_safe(eng):
     want = c_oracle.snp_sets(ref, tgt, pos, ws, we)
     for a, b in zip(got, want):
         assert np.array_equal(a.cpu().numpy(), b)
+
+
+def test_random_shapes_through_every_entry(eng):
+    """Seeded random chromosomes and window layouts (overlapping, disjoint, nested, empty, unsorted
+    ends), odd panel widths, random parameters, occasional missing / multi-allelic calls: the host
+    entry (in place and staged), the device entry and the SNP-set entry against the C oracle."""
+    import torch
+    from sstar_b200 import _cabi
+    rng = np.random.default_rng(20240607)
+    for case in range(24):
+        V = int(rng.choice([0, 1, 2, 31, 32, 33, 500, 3000]))
+        R = int(rng.integers(1, 70))
+        T = int(rng.integers(1, 140))
+        pos = np.cumsum(rng.integers(1, 60, size=V)).astype(np.int32)
+        ref = (rng.random((V, R)) < 0.02).astype(np.int8)
+        tgt = rng.choice([0, 1, 2], size=(V, T), p=[0.6, 0.3, 0.1]).astype(np.int8)
+        if case % 3 == 0 and V:
+            m = rng.random(tgt.shape) < 0.01
+            tgt[m] = rng.choice([-1, 3, 7], size=int(m.sum())).astype(np.int8)
+            ref[rng.random(ref.shape) < 0.005] = -1
+        span = int(pos[-1]) if V else 1000
+        W = int(rng.choice([1, 2, 7, 40, 300]))
+        ws = rng.integers(-50, span + 50, size=W).astype(np.int32)
+        we = (ws + rng.integers(0, max(2, span // 3), size=W)).astype(np.int32)
+        if case % 2 == 0:  # the usual layout: sorted starts
+            order = np.argsort(ws, kind="stable")
+            ws, we = ws[order], we[order]
+        params = [(5000, 5, -10000), (1, 1, 0), (77, 0, -3), (2_000_000_000, 5, -2_000_000_000)][case % 4]
+        so, no = c_oracle.score_windows(ref, tgt, pos, ws, we, *params)
+        for flags in (0, _cabi.FLAG_STAGED_COPIES, _cabi.FLAG_COPY_INPUTS):
+            s, n = eng.score_host(ref, tgt, pos, ws, we, *params, flags=flags)
+            assert np.array_equal(s, so) and np.array_equal(n, no), (case, flags, V, R, T, W)
+        if V:
+            d = [torch.from_numpy(x).to(eng.tdev) for x in (ref, tgt, pos, ws, we)]
+            s, n = eng.score_device(*d, *params)
+            assert np.array_equal(s.cpu().numpy(), so) and np.array_equal(n.cpu().numpy(), no), (case, "device")
+            got = eng.snp_sets_device(*d, *params)
+            want = c_oracle.snp_sets(ref, tgt, pos, ws, we, *params)
+            for a, b in zip(got, want):
+                assert np.array_equal(a.cpu().numpy(), b), (case, "snp sets")
+
+
+def test_many_small_windows_in_place(eng):
+    # 70,000 windows over 20,000 variants: the in-place host entry's fetch CTAs hit their cap and
+    # the bounds CTAs run in several waves behind them
+    rng = np.random.default_rng(8)
+    V, T = 20_000, 12
+    pos = np.cumsum(rng.integers(1, 30, size=V)).astype(np.int32)
+    ref = (rng.random((V, 6)) < 0.05).astype(np.int8)
+    tgt = rng.choice([0, 1, 2], size=(V, T), p=[0.5, 0.3, 0.2]).astype(np.int8)
+    ws = np.sort(rng.integers(0, int(pos[-1]), size=70_000)).astype(np.int32)
+    we = (ws + rng.integers(0, 400, size=ws.size)).astype(np.int32)
+    so, no = c_oracle.score_windows(ref, tgt, pos, ws, we)
+    for flags in (0, 1):
+        s, n = eng.score_host(ref, tgt, pos, ws, we, flags=flags)
+        assert np.array_equal(s, so) and np.array_equal(n, no), flags
