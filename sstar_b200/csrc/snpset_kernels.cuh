@@ -9,10 +9,13 @@
 //     at that i the chain is extended when M[i] >= 0, else it starts afresh with the pair (i, j);
 //     the chain ends at the FIRST j attaining max_j M[j].
 //
-// One warp per unit, as in the pairwise scoring kernel: lanes stride over i < j, the row max is a
-// REDUX pair, the first i attaining it a REDUX min.  The result is ragged, so the work is two
-// passes around a scan (lengths -> offsets -> fill); the fill pass recomputes the recurrence only for
-// units that have a chain.
+// snp_count_kernel, one thread per unit: n from the packed planes (popcounts), the SNP count, and
+// -- most units of sparse data end here -- NaN for n <= 2; the others are queued.
+// snp_set_kernel, one warp per QUEUED unit: the site list comes from the planes (genotype bytes are
+// fetched only in windows holding values outside {0,1,2}), lanes stride over i < j, the row max is
+// a REDUX pair, the first i attaining it a REDUX min.  The result is ragged, so the work is two
+// passes around a scan (lengths -> offsets -> fill); the fill pass walks the same queue and recomputes
+// the recurrence for the units that have a chain.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,9 +32,12 @@ constexpr int kScanPerBlock = kScanThreads * kScanPerThread;
 struct SnpSetArgs {
     const int32_t *pos;
     const int8_t *tgt;
-    const uint32_t *absent_bits;
+    const uint32_t *absent_bits, *exotic, *carried, *two;
     const int32_t *win_lo, *win_hi;
-    int32_t T, W;
+    uint32_t *win_ex;        // [W] count pass: the window holds genotypes outside {0,1,2}
+    int32_t *queue;          // [W * T] units with n > 2, in no particular order
+    int32_t *queue_n;        // their number (zeroed before the count pass)
+    int32_t T, Tp, W;
     int32_t bonus, max_mm, penalty;
     int64_t *score;          // lengths pass: [W, T] (INT64_MIN = NaN)
     int32_t *nsnp;           // lengths pass: [W, T]
@@ -41,6 +47,7 @@ struct SnpSetArgs {
     int64_t capacity;        // fill pass: entries set_pos holds
     uint8_t *arena;
     uint64_t arena_bytes;
+    int32_t smem_cap;        // list entries per warp that fit the launch's shared memory (larger windows: arena)
 };
 
 __device__ __forceinline__ int64_t set_warp_max_i64(int64_t v) {
@@ -49,6 +56,61 @@ __device__ __forceinline__ int64_t set_warp_max_i64(int64_t v) {
     const uint32_t lo = (hi == mh) ? (uint32_t)v : 0u;
     const uint32_t ml = __reduce_max_sync(0xffffffffu, lo);
     return ((int64_t)mh << 32) | (int64_t)ml;
+}
+
+constexpr int kCountThreads = 128;
+
+// grid.x = W * ceil(T / blockDim.x): one window x one run of columns per CTA
+__global__ void __launch_bounds__(kCountThreads) snp_count_kernel(const __grid_constant__ SnpSetArgs a) {
+    __shared__ int s_nabs;
+    __shared__ uint32_t s_ex;
+    const int tid = threadIdx.x, bd = blockDim.x;
+    const int tchunks = (a.T + bd - 1) / bd;
+    const int w = blockIdx.x / tchunks, t = (blockIdx.x % tchunks) * bd + tid;
+    if (tid == 0) { s_nabs = 0; s_ex = 0; }
+    __syncthreads();
+    const int32_t lo = a.win_lo[w], hi = a.win_hi[w];
+    int n = 0;
+    if (hi > lo) {
+        const int wi0 = lo >> 5, wi1 = (hi - 1) >> 5;
+        const uint32_t m0 = 0xffffffffu << (lo & 31), m1 = 0xffffffffu >> (31 - ((hi - 1) & 31));
+        int na = 0;
+        uint32_t ex = 0;
+        for (int gi = wi0 + tid; gi <= wi1; gi += bd) {
+            const uint32_t rm = (gi == wi0 ? m0 : 0xffffffffu) & (gi == wi1 ? m1 : 0xffffffffu);
+            na += __popc(__ldg(a.absent_bits + gi) & rm);
+            ex |= __ldg(a.exotic + gi);
+        }
+        na = __reduce_add_sync(0xffffffffu, na);
+        ex = __reduce_or_sync(0xffffffffu, ex);
+        if ((tid & 31) == 0 && (na | ex)) {
+            atomicAdd(&s_nabs, na);
+            if (ex) atomicOr(&s_ex, 1u);
+        }
+        if (t < a.T) {
+            const uint32_t *cp = a.carried + (size_t)wi0 * a.Tp + t;
+            for (int gi = wi0; gi <= wi1; ++gi, cp += a.Tp) {
+                const uint32_t rm = (gi == wi0 ? m0 : 0xffffffffu) & (gi == wi1 ? m1 : 0xffffffffu);
+                n += __popc(__ldg(cp) & rm);
+            }
+        }
+    }
+    __syncthreads();
+    if (blockIdx.x % tchunks == 0 && tid == 0) a.win_ex[w] = s_ex;
+    const bool queued = t < a.T && n > 2;
+    if (t < a.T) {
+        const size_t o = (size_t)w * a.T + t;
+        a.nsnp[o] = (hi - lo) - s_nabs + n;
+        if (!queued) { a.score[o] = INT64_MIN; a.set_len[o] = 0; }
+    }
+    const uint32_t qm = __ballot_sync(0xffffffffu, queued);
+    if (qm) {
+        const int lane = tid & 31, leader = __ffs(qm) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(a.queue_n, __popc(qm));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (queued) a.queue[base + __popc(qm & ((1u << lane) - 1u))] = w * a.T + t;
+    }
 }
 
 template <bool kFill>
@@ -65,26 +127,16 @@ __global__ void __launch_bounds__(kPairWarps * 32) snp_set_kernel(const __grid_c
         if (lane == 0 && mv > 0) atomicMax(&s_maxvw, mv);
     }
     __syncthreads();
-    const int64_t total = (int64_t)a.W * a.T;
+    const int64_t total = *a.queue_n;
     const uint32_t cap = (uint32_t)((s_maxvw + 7) & ~7);
-    if (cap == 0) {  // every window is empty
-        if (!kFill) {
-            for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
-                 it += (int64_t)gridDim.x * blockDim.x) {
-                a.score[it] = INT64_MIN;
-                a.nsnp[it] = 0;
-                a.set_len[it] = 0;
-            }
-        }
-        return;
-    }
+    if (cap == 0 || total == 0) return;  // the count pass has written every unit
     int64_t gw = (int64_t)blockIdx.x * kPairWarps + warp;
     int64_t nw = (int64_t)gridDim.x * kPairWarps;
     uint8_t *slab;
     uint32_t slab_cap;
-    if (cap <= (uint32_t)kPairSmemCap) {
-        slab_cap = kPairSmemCap;
-        slab = smem + (size_t)warp * kPairSmemCap * kSetEntryBytes;
+    if (cap <= (uint32_t)a.smem_cap) {
+        slab_cap = (uint32_t)a.smem_cap;
+        slab = smem + (size_t)warp * a.smem_cap * kSetEntryBytes;
     } else {
         slab_cap = cap;
         const int64_t nslabs = (int64_t)(a.arena_bytes / ((uint64_t)cap * kSetEntryBytes));
@@ -97,7 +149,8 @@ __global__ void __launch_bounds__(kPairWarps * 32) snp_set_kernel(const __grid_c
     int32_t *B = reinterpret_cast<int32_t *>(slab + (size_t)slab_cap * 12);
     int8_t *Gt = reinterpret_cast<int8_t *>(slab + (size_t)slab_cap * 16);
 
-    for (int64_t it = gw; it < total; it += nw) {
+    for (int64_t q = gw; q < total; q += nw) {
+        const int64_t it = a.queue[q];
         int64_t off = 0;
         int len = 0;
         if (kFill) {
@@ -108,23 +161,34 @@ __global__ void __launch_bounds__(kPairWarps * 32) snp_set_kernel(const __grid_c
         const int w = (int)(it / a.T);
         const int t = (int)(it % a.T);
         const int32_t lo = a.win_lo[w], hi = a.win_hi[w];
-        int n = 0, nabs = 0;
-        if (hi > lo) {
-            for (int gi = lo >> 5; gi <= ((hi - 1) >> 5); ++gi) {
-                const int k = (gi << 5) + lane;
-                const uint32_t ab = __ldg(a.absent_bits + gi);
-                const bool isab = k >= lo && k < hi && ((ab >> lane) & 1);
-                int g = 0;
-                if (isab) g = a.tgt[(size_t)k * a.T + t];
-                const uint32_t ab_m = __ballot_sync(0xffffffffu, isab);
-                const uint32_t car_m = __ballot_sync(0xffffffffu, g != 0);
-                nabs += __popc(ab_m);
-                if (g != 0) {
-                    const int idx = n + __popc(car_m & ((1u << lane) - 1u));
-                    P[idx] = __ldg(a.pos + k);
-                    Gt[idx] = (int8_t)g;
+        const bool wex = a.win_ex[w] != 0;
+        int n = 0;
+        {   // the unit's carried, reference-absent sites: one plane word per 32 variants.  Lanes
+            // fetch 32 words of the column at once (one round trip), then the warp walks them.
+            const int wi0 = lo >> 5, wi1 = (hi - 1) >> 5;
+            for (int gb = wi0; gb <= wi1; gb += 32) {
+                const int gl = gb + lane;
+                uint32_t my_cw = 0, my_tw = 0;
+                if (gl <= wi1) {
+                    my_cw = __ldg(a.carried + (size_t)gl * a.Tp + t);
+                    my_tw = __ldg(a.two + (size_t)gl * a.Tp + t);
+                    if (gl == wi0) my_cw &= 0xffffffffu << (lo & 31);
+                    if (gl == wi1) my_cw &= 0xffffffffu >> (31 - ((hi - 1) & 31));
                 }
-                n += __popc(car_m);
+                uint32_t live = __ballot_sync(0xffffffffu, my_cw != 0);  // words holding a site
+                while (live) {
+                    const int src = __ffs(live) - 1;
+                    live &= live - 1;
+                    const uint32_t cw = __shfl_sync(0xffffffffu, my_cw, src);
+                    const uint32_t tw = __shfl_sync(0xffffffffu, my_tw, src);
+                    if ((cw >> lane) & 1u) {
+                        const int k = ((gb + src) << 5) + lane;
+                        const int idx = n + __popc(cw & ((1u << lane) - 1u));
+                        P[idx] = __ldg(a.pos + k);
+                        Gt[idx] = wex ? a.tgt[(size_t)k * a.T + t] : (int8_t)(1 + ((tw >> lane) & 1u));
+                    }
+                    n += __popc(cw);
+                }
             }
         }
         __syncwarp();
@@ -169,7 +233,6 @@ __global__ void __launch_bounds__(kPairWarps * 32) snp_set_kernel(const __grid_c
                     }
                 }
                 a.score[it] = top;
-                a.nsnp[it] = (hi - lo) - nabs + n;
                 a.set_len[it] = cnt;
             }
         } else if (lane == 0 && top_j >= 0) {

@@ -858,7 +858,7 @@ extern "C" int sstar_b200_match_numerators(int device, void *stream, const int8_
 // ---- S* SNP sets (optional extension; see snpset_kernels.cuh) --------------------------------
 namespace {
 struct SetLayout {
-    size_t off_len, off_blocks, total;
+    size_t off_len, off_blocks, off_queue, off_qn, total;
     uint64_t arena_bytes;
     int64_t n, nb;
 };
@@ -872,6 +872,8 @@ SetLayout make_set_layout(const WsLayout &L, int32_t W, int32_t T) {
     size_t off = align_up(L.off_arena + (size_t)S.arena_bytes, 256);
     S.off_len = off;    off = align_up(off + (size_t)(S.n > 0 ? S.n : 1) * 4, 256);
     S.off_blocks = off; off = align_up(off + (size_t)(S.nb > 0 ? S.nb : 1) * 8, 256);
+    S.off_queue = off;  off = align_up(off + (size_t)(S.n > 0 ? S.n : 1) * 4, 256);
+    S.off_qn = off;     off += 256;
     S.total = off;
     return S;
 }
@@ -879,21 +881,45 @@ SetLayout make_set_layout(const WsLayout &L, int32_t W, int32_t T) {
 int launch_snp_sets(cudaStream_t st, bool fill, const int8_t *d_tgt, const int32_t *d_pos, int32_t T, int32_t W,
                     int32_t bonus, int32_t max_mm, int32_t penalty, int64_t *d_score, int32_t *d_nsnp,
                     const int64_t *d_set_off, int32_t *d_set_pos, int64_t capacity, uint8_t *ws, const WsLayout &L,
-                    const SetLayout &S) {
+                    const SetLayout &S, int32_t hint) {
     SnpSetArgs a = {};
     a.pos = d_pos; a.tgt = d_tgt;
     a.absent_bits = reinterpret_cast<const uint32_t *>(ws + L.off_absent);
+    a.exotic = reinterpret_cast<const uint32_t *>(ws + L.off_exotic);
+    a.carried = reinterpret_cast<const uint32_t *>(ws + L.off_carried);
+    a.two = reinterpret_cast<const uint32_t *>(ws + L.off_two);
     a.win_lo = reinterpret_cast<const int32_t *>(ws + L.off_win_lo);
     a.win_hi = reinterpret_cast<const int32_t *>(ws + L.off_win_hi);
-    a.T = T; a.W = W; a.bonus = bonus; a.max_mm = max_mm; a.penalty = penalty;
+    a.win_ex = reinterpret_cast<uint32_t *>(ws + L.off_bail);
+    a.queue = reinterpret_cast<int32_t *>(ws + S.off_queue);
+    a.queue_n = reinterpret_cast<int32_t *>(ws + S.off_qn);
+    a.T = T; a.Tp = L.Tp; a.W = W; a.bonus = bonus; a.max_mm = max_mm; a.penalty = penalty;
     a.score = d_score; a.nsnp = d_nsnp;
     a.set_len = reinterpret_cast<int32_t *>(ws + S.off_len);
     a.set_off = d_set_off; a.set_pos = d_set_pos; a.capacity = capacity;
     a.arena = ws + L.off_arena; a.arena_bytes = S.arena_bytes;
-    const size_t smem = (size_t)kPairWarps * kPairSmemCap * kSetEntryBytes;
+    // list entries per warp kept in shared memory: the largest window when the caller told us
+    // (more resident warps to hide the gather's latency), else the pairwise kernel's 1024
+    int32_t smem_cap = kPairSmemCap;
+    if (hint > 0 && hint < kPairSmemCap) smem_cap = (int32_t)align_up((size_t)(hint < 64 ? 64 : hint), 8);
+    a.smem_cap = smem_cap;
+    const size_t smem = (size_t)kPairWarps * smem_cap * kSetEntryBytes;
+    int per_sm = (int)(((size_t)200 << 10) / (smem + 1024));
+    if (per_sm > 16) per_sm = 16;
+    if (per_sm < 1) per_sm = 1;
     int64_t grid = (S.n + kPairWarps - 1) / kPairWarps;
-    if (grid > kNumSM * 3) grid = kNumSM * 3;
+    if (grid > (int64_t)kNumSM * per_sm) grid = (int64_t)kNumSM * per_sm;
     cudaError_t e;
+    if (!fill) {  // n, SNP counts and the NaN units from the planes; the rest is queued for the warps
+        e = cudaMemsetAsync(a.queue_n, 0, 4, st);
+        if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+        int bd = (T + 31) / 32 * 32;
+        if (bd > kCountThreads) bd = kCountThreads;
+        const int64_t cgrid = (int64_t)W * ((T + bd - 1) / bd);
+        if (cgrid > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "too many (window, column chunk) tiles%s");
+        e = launch(snp_count_kernel, (unsigned)cgrid, (unsigned)bd, 0, st, false, a);
+        if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "snp_count_kernel launch: %s", cudaGetErrorString(e));
+    }
     if (fill) {
         static thread_local SmemGrant grant;
         e = grant_smem(grant, snp_set_kernel<true>, smem);
@@ -942,7 +968,7 @@ extern "C" int sstar_b200_snp_set_offsets(int device, void *stream, const int8_t
     rc = launch_prep(st, 0, L.G, d_ref_gt, d_tgt_gt, V, R, T, d_pos, d_win_start, d_win_end, nullptr, 0, 0, W, ws, L);
     if (rc) return rc;
     rc = launch_snp_sets(st, false, d_tgt_gt, d_pos, T, W, match_bonus, max_mismatch, mismatch_penalty, d_score, d_nsnp,
-                         nullptr, nullptr, 0, ws, L, S);
+                         nullptr, nullptr, 0, ws, L, S, opts ? opts->max_win_variants : 0);
     if (rc) return rc;
     const int32_t *len = reinterpret_cast<const int32_t *>(ws + S.off_len);
     int64_t *blocks = reinterpret_cast<int64_t *>(ws + S.off_blocks);
@@ -971,5 +997,5 @@ extern "C" int sstar_b200_snp_set_fill(int device, void *stream, const int8_t *d
     if (guard.err != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
     return launch_snp_sets((cudaStream_t)stream, true, d_tgt_gt, d_pos, T, W, match_bonus, max_mismatch,
                            mismatch_penalty, nullptr, nullptr, d_set_off, d_set_pos, capacity,
-                           (uint8_t *)d_workspace, L, S);
+                           (uint8_t *)d_workspace, L, S, opts ? opts->max_win_variants : 0);
 }
