@@ -83,6 +83,7 @@ struct ScoreArgs {
     int32_t *nsnp;
     uint8_t *arena;  // pairwise only
     uint64_t arena_entries;
+    int32_t pair_smem_cap;  // pairwise only: list entries per warp that fit the launch's shared memory
 };
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }

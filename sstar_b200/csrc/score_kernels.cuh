@@ -431,9 +431,9 @@ __global__ void __launch_bounds__(kPairWarps * 32) score_pairwise_kernel(ScoreAr
     int64_t nw = (int64_t)gridDim.x * kPairWarps;
     uint8_t *slab;
     uint32_t slab_cap;
-    if (cap <= (uint32_t)kPairSmemCap) {
-        slab_cap = kPairSmemCap;
-        slab = smem + (size_t)warp * kPairSmemCap * 13;
+    if (cap <= (uint32_t)a.pair_smem_cap) {
+        slab_cap = (uint32_t)a.pair_smem_cap;
+        slab = smem + (size_t)warp * a.pair_smem_cap * 13;
     } else {
         slab_cap = cap;
         const int64_t nslabs = (int64_t)(a.arena_entries / cap);
@@ -451,21 +451,34 @@ __global__ void __launch_bounds__(kPairWarps * 32) score_pairwise_kernel(ScoreAr
         const int32_t lo = a.win_lo[w], hi = a.win_hi[w];
         int n = 0, nabs = 0;
         if (hi > lo) {
-            for (int gi = lo >> 5; gi <= ((hi - 1) >> 5); ++gi) {
-                const int k = (gi << 5) + lane;
-                const uint32_t ab = __ldg(a.absent_bits + gi);
-                const bool isab = k >= lo && k < hi && ((ab >> lane) & 1);
-                int g = 0;
-                if (isab) g = a.tgt[(size_t)k * a.T + t];
-                const uint32_t ab_m = __ballot_sync(0xffffffffu, isab);
-                const uint32_t car_m = __ballot_sync(0xffffffffu, g != 0);
-                nabs += __popc(ab_m);
-                if (g != 0) {
-                    const int idx = n + __popc(car_m & ((1u << lane) - 1u));
-                    P[idx] = __ldg(a.pos + k);
-                    Gt[idx] = (int8_t)g;
+            // Lanes fetch 32 words of the column's carried plane (and of the absent mask) in one
+            // round trip; the warp then walks the words that hold a site.  Genotype bytes are read
+            // for carried sites only.
+            const int wi0 = lo >> 5, wi1 = (hi - 1) >> 5;
+            for (int gb = wi0; gb <= wi1; gb += 32) {
+                const int gl = gb + lane;
+                uint32_t my_cw = 0, my_ab = 0;
+                if (gl <= wi1) {
+                    uint32_t rm = 0xffffffffu;
+                    if (gl == wi0) rm &= 0xffffffffu << (lo & 31);
+                    if (gl == wi1) rm &= 0xffffffffu >> (31 - ((hi - 1) & 31));
+                    my_cw = __ldg(a.carried + (size_t)gl * a.Tp + t) & rm;
+                    my_ab = __ldg(a.absent_bits + gl) & rm;
                 }
-                n += __popc(car_m);
+                nabs += __reduce_add_sync(0xffffffffu, __popc(my_ab));
+                uint32_t live = __ballot_sync(0xffffffffu, my_cw != 0);
+                while (live) {
+                    const int src = __ffs(live) - 1;
+                    live &= live - 1;
+                    const uint32_t cw = __shfl_sync(0xffffffffu, my_cw, src);
+                    if ((cw >> lane) & 1u) {
+                        const int k = ((gb + src) << 5) + lane;
+                        const int idx = n + __popc(cw & ((1u << lane) - 1u));
+                        P[idx] = __ldg(a.pos + k);
+                        Gt[idx] = a.tgt[(size_t)k * a.T + t];
+                    }
+                    n += __popc(cw);
+                }
             }
         }
         __syncwarp();

@@ -296,12 +296,21 @@ int launch_score(cudaStream_t st, const ScoreCall &c, const WsLayout &L, int32_t
                                Lslots, words_cap);
         if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "score_group_kernel launch: %s", cudaGetErrorString(e));
     }
-    const size_t psmem = (size_t)kPairWarps * kPairSmemCap * 13;
+    // list entries per warp kept in shared memory: the largest window when the caller told us (more
+    // resident warps to hide the gather's latency), else 1024; larger windows use the arena
+    int32_t pcap = kPairSmemCap;
+    if (c.max_win_variants > 0 && c.max_win_variants < kPairSmemCap)
+        pcap = (int32_t)align_up((size_t)(c.max_win_variants < 64 ? 64 : c.max_win_variants), 8);
+    s.pair_smem_cap = pcap;
+    const size_t psmem = (size_t)kPairWarps * pcap * 13;
     static thread_local SmemGrant pair_grant;
     cudaError_t ep = grant_smem(pair_grant, score_pairwise_kernel, psmem);
     if (ep != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaFuncSetAttribute(pairwise): %s", cudaGetErrorString(ep));
+    int per_sm = (int)(((size_t)200 << 10) / (psmem + 1024));
+    if (per_sm > 16) per_sm = 16;
+    if (per_sm < 4 || !s.force_slow) per_sm = 4;  // behind the grouped kernel the slow list is short or empty: keep the launch light
     int64_t pgrid = ((int64_t)W * T + kPairWarps - 1) / kPairWarps;
-    if (pgrid > kNumSM * 4) pgrid = kNumSM * 4;
+    if (pgrid > (int64_t)kNumSM * per_sm) pgrid = (int64_t)kNumSM * per_sm;
     cudaError_t e = launch(score_pairwise_kernel, (unsigned)pgrid, kPairWarps * 32, psmem, st, true, s);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "score_pairwise_kernel launch: %s", cudaGetErrorString(e));
     return 0;
