@@ -72,6 +72,19 @@ SSTAR_HD int64_t score_bound(int64_t span, int64_t nvar, int32_t bonus, int32_t 
 // only moves forward.  The caller terminates the list with kListSentinel at index cnt.
 // ---------------------------------------------------------------------------------------------
 // Scores exactly the n sites starting at `base` (a run of one column's list).  n >= 1.
+// kShift = 1: entries (position << 1 | genotype==2).  kShift = 8: general entries (position << 8 |
+// genotype byte) of a unit whose genotypes all are 1 or 2 -- the same DP, decoded differently.
+template <int kShift>
+SSTAR_HD bool entry_is_two(uint32_t e) { return kShift == 1 ? (e & 1u) != 0 : (e & 0xffu) == 2u; }
+
+// true when every one of the n general entries holds genotype 1 or 2
+SSTAR_HD bool general_run_is_plain(const uint32_t *base, int ls, int n) {
+    bool plain = true;
+    for (int k = 0; k < n; ++k) plain = plain && ((base[k * ls] & 0xffu) - 1u) < 2u;
+    return plain;
+}
+
+template <int kShift = 1>
 SSTAR_HD int64_t list_dp_run(const uint32_t *base, int ls, int n, int32_t bonus, int32_t pen_eff) {
     constexpr int32_t NEG = Sentinel<int32_t>::NEG, THR = Sentinel<int32_t>::THR;
     int32_t ring[kRingSlots];  // v of waiting sites older than k-1: thread-local memory, touched only
@@ -83,11 +96,11 @@ SSTAR_HD int64_t list_dp_run(const uint32_t *base, int ls, int n, int32_t bonus,
     int32_t pv = 0;
     for (int k = 0; k < n; ++k) {
         const uint32_t e = *pk;
-        const int32_t p = (int32_t)(e >> 1);
+        const int32_t p = (int32_t)(e >> kShift);
         if (c == k - 1) {  // common case: only the previous site waits, in registers
-            const int32_t pc = (int32_t)(pe >> 1);
+            const int32_t pc = (int32_t)(pe >> kShift);
             if (p - pc >= kMinPairDistance) {
-                if (pe & 1u) { A1 = imax(A1, pv - pc); B1 = imax(B1, pv); }
+                if (entry_is_two<kShift>(pe)) { A1 = imax(A1, pv - pc); B1 = imax(B1, pv); }
                 else         { A0 = imax(A0, pv - pc); B0 = imax(B0, pv); }
                 c = k;
             } else {
@@ -99,15 +112,15 @@ SSTAR_HD int64_t list_dp_run(const uint32_t *base, int ls, int n, int32_t bonus,
                 int32_t vc;
                 if (c == k - 1) { ec = pe; vc = pv; }
                 else            { ec = base[c * ls]; vc = ring[c & (kRingSlots - 1)]; }
-                const int32_t pc = (int32_t)(ec >> 1);
+                const int32_t pc = (int32_t)(ec >> kShift);
                 if (p - pc < kMinPairDistance) break;
-                if (ec & 1u) { A1 = imax(A1, vc - pc); B1 = imax(B1, vc); }
+                if (entry_is_two<kShift>(ec)) { A1 = imax(A1, vc - pc); B1 = imax(B1, vc); }
                 else         { A0 = imax(A0, vc - pc); B0 = imax(B0, vc); }
                 ++c;
             }
             if (c < k) ring[(k - 1) & (kRingSlots - 1)] = pv;
         }
-        const bool cls = (e & 1u) != 0;
+        const bool cls = entry_is_two<kShift>(e);
         const int32_t same = cls ? A1 : A0;
         const int32_t other = cls ? B0 : B1;
         const int32_t m = imax(same + (p + bonus), other + pen_eff);

@@ -34,6 +34,7 @@ struct GroupShared {
     int32_t red_nabs;
     uint32_t red_ex;
     int32_t n_work;
+    int32_t n_work_back;  // general body: units holding other genotypes than 1 / 2, queued from the far end
 };
 
 struct LdgU32 { __device__ __forceinline__ uint32_t operator()(const uint32_t *p) const { return __ldg(p); } };
@@ -98,13 +99,12 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
                 while (cbits) {
                     const int b = __ffs(cbits) - 1;
                     cbits &= cbits - 1;
-                    uint32_t rel;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rel) : "r"(sp + 4u * (uint32_t)b));
                     uint32_t e;
                     if (kGen) {
-                        const int8_t gb = a.tgt[(size_t)(((c.gi0 + jb + u) << 5) + b) * a.T + t];
-                        e = (rel << 8) | (uint32_t)(uint8_t)gb;
+                        e = (uint32_t)(((jb + u) << 5) + b);  // row within the tile; completed below
                     } else {
+                        uint32_t rel;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rel) : "r"(sp + 4u * (uint32_t)b));
                         e = (rel << 1) | ((tw[u] >> b) & 1u);
                     }
                     asm volatile("st.shared.u32 [%0], %1;" ::"r"(w_addr), "r"(e) : "memory");
@@ -113,9 +113,22 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
             }
         }
     }
+    if (kGen && t < a.T) {
+        // general entries: (relative position << 8 | genotype byte).  The bytes are fetched here,
+        // in a loop of independent iterations (several loads in flight), not one exposed memory
+        // latency per site inside the bit loop above.
+        const int m = min(cnt, L);
+        const int8_t *col = a.tgt + (size_t)(c.gi0 << 5) * a.T + t;
+#pragma unroll 4
+        for (int i = 0; i < m; ++i) {
+            const uint32_t row = s_list[i * bd + tid];
+            const int8_t gb = col[(size_t)row * a.T];
+            s_list[i * bd + tid] = (c.s_pos[row] << 8) | (uint32_t)(uint8_t)gb;
+        }
+    }
     const bool overflow = cnt >= L;  // one slot is the terminator
     if (t < a.T && !overflow) s_list[cnt * bd + tid] = kListSentinel;
-    if (tid == 0) g.n_work = 0;
+    if (tid == 0) { g.n_work = 0; g.n_work_back = 0; }
     __syncthreads();  // every list is built: the position tile becomes the worklist
 
     // a unit the general DP cannot take (more than kMaxClasses genotype values, or its column
@@ -156,16 +169,27 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
                                           a.max_mm, n, score);
                 }
             }
-            // warp-aggregated append of (column, window, first entry, length)
-            const uint32_t qm = __ballot_sync(0xffffffffu, queued);
+            // warp-aggregated append of (column, window, first entry, length).  In the general body the
+            // units whose genotypes all are 1 / 2 (most of them) queue from the front and take the
+            // four-maxima DP, the others queue from the far end and take the per-class DP: the
+            // warps of pass 2 then run one body at a time.
+            const bool other = kGen && queued && !general_run_is_plain(s_list + tid + cur_a * bd, bd, n);
+            const uint32_t qm = __ballot_sync(0xffffffffu, queued && !other);
+            const uint32_t om = kGen ? __ballot_sync(0xffffffffu, other) : 0u;
+            const uint32_t item = (uint32_t)tid | ((uint32_t)i << 7) | ((uint32_t)cur_a << 11) | ((uint32_t)n << 21);
             if (qm) {
                 const int lane = tid & 31;
                 int basei = 0;
                 if (lane == __ffs(qm) - 1) basei = atomicAdd(&g.n_work, __popc(qm));
                 basei = __shfl_sync(0xffffffffu, basei, __ffs(qm) - 1);
-                if (queued)
-                    s_work[basei + __popc(qm & ((1u << lane) - 1u))] =
-                        (uint32_t)tid | ((uint32_t)i << 7) | ((uint32_t)cur_a << 11) | ((uint32_t)n << 21);
+                if (queued && !other) s_work[basei + __popc(qm & ((1u << lane) - 1u))] = item;
+            }
+            if (om) {
+                const int lane = tid & 31;
+                int basei = 0;
+                if (lane == __ffs(om) - 1) basei = atomicAdd(&g.n_work_back, __popc(om));
+                basei = __shfl_sync(0xffffffffu, basei, __ffs(om) - 1);
+                if (other) s_work[nwin * bd - 1 - (basei + __popc(om & ((1u << lane) - 1u)))] = item;
             }
             if (t < a.T && !ex) {
                 const size_t o = (size_t)w * a.T + t;
@@ -178,13 +202,21 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
         for (int u = tid; u < n_work; u += bd) {
             const uint32_t e = s_work[u];
             const int col = e & 127, i = (e >> 7) & 15, ua = (e >> 11) & 1023, n = e >> 21;
-            int64_t score;
-            if (!kGen) score = list_dp_run(s_list + col + ua * bd, bd, n, a.bonus, c.pen_eff);
-            else if (!list_dp_run_general(s_list + col + ua * bd, bd, n, a.bonus, a.penalty, a.max_mm, score)) {
-                bail_window(w0 + i);
-                continue;
-            }
+            const int64_t score = list_dp_run<kShift>(s_list + col + ua * bd, bd, n, a.bonus, c.pen_eff);
             a.score[(size_t)(w0 + i) * a.T + chunk * bd + col] = score;
+        }
+        if (kGen) {
+            const int n_back = g.n_work_back;
+            for (int u = tid; u < n_back; u += bd) {
+                const uint32_t e = s_work[nwin * bd - 1 - u];
+                const int col = e & 127, i = (e >> 7) & 15, ua = (e >> 11) & 1023, n = e >> 21;
+                int64_t score;
+                if (!list_dp_run_general(s_list + col + ua * bd, bd, n, a.bonus, a.penalty, a.max_mm, score)) {
+                    bail_window(w0 + i);
+                    continue;
+                }
+                a.score[(size_t)(w0 + i) * a.T + chunk * bd + col] = score;
+            }
         }
         return;
     }

@@ -1,0 +1,17 @@
+"""A few passes over a workload with 0.5 % missing target calls (profiling aid for the general-genotype body)."""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from sstar_b200.engine import get_engine
+name = sys.argv[1] if len(sys.argv) > 1 else "c3-shard"
+wk = bench.make_workload(name, 0); st = bench.workload_stats(wk)
+dev = torch.device("cuda", 0); eng = get_engine(0)
+d = {k: torch.from_numpy(np.ascontiguousarray(wk[k])).to(dev) for k in ("ref", "tgt", "pos", "ws", "we")}
+torch.manual_seed(1)
+tgt_m = d["tgt"].clone()
+tgt_m[torch.rand(tgt_m.shape, device=dev) < 0.005] = -1
+for _ in range(5):
+    out = eng.score_device(d["ref"], tgt_m, d["pos"], d["ws"], d["we"], 5000, 5, -10000, max_win_variants=st["max_window_variants"])
+torch.cuda.synchronize()
+print("done", int((out[0] != np.iinfo(np.int64).min).sum()))
