@@ -167,7 +167,11 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
                                 if (!balanced) cur_b = cur;
                                 list_window_range_shifted<8>(list.data(), 1, cur, cur_b, plo, phi, balanced);
                                 n = cur_b - cur;
-                                if (n > 2 && !list_dp_run_general(list.data() + cur, 1, n, bonus, penalty, max_mm, sc)) { slow[w] = 1; continue; }
+                                // as on the device: in the balanced pass the units whose genotypes all are 1 / 2 take
+                                // the four-maxima DP on general entries, the others the per-class DP
+                                if (n > 2 && balanced && general_run_is_plain(list.data() + cur, 1, n))
+                                    sc = list_dp_run<8>(list.data() + cur, 1, n, bonus, pen_eff);
+                                else if (n > 2 && !list_dp_run_general(list.data() + cur, 1, n, bonus, penalty, max_mm, sc)) { slow[w] = 1; continue; }
                             } else if (!overflow && balanced) {
                                 list_window_range(list.data(), 1, cur, cur_b, plo, phi, true);
                                 n = cur_b - cur;
