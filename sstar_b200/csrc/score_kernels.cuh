@@ -386,17 +386,24 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
                 g.plo[s0 + tid] = hi > lo ? (uint32_t)(g.pfirst[s0 + tid] - p0) : 1u;
                 g.phi[s0 + tid] = hi > lo ? (uint32_t)(g.plast[s0 + tid] - p0) : 0u;
             }
-            // #absent variants and the exotic flag per window: one (window, word) item per thread
-            for (int it = tid; it < nsub * nwr; it += bd) {
-                const int i = s0 + it / nwr, gi = gi0 + it % nwr;
+            // #absent variants and the exotic flag per window: a warp per window, lanes over its words
+            for (int i = s0 + (tid >> 5); i < s1; i += bd >> 5) {
                 const int32_t lo = g.lo[i], hi = g.hi[i];
-                if (hi <= lo || gi < (lo >> 5) || gi > ((hi - 1) >> 5)) continue;
-                uint32_t rm = 0xffffffffu;
-                if (gi == (lo >> 5)) rm &= 0xffffffffu << (lo & 31);
-                if (gi == ((hi - 1) >> 5)) rm &= 0xffffffffu >> (31 - ((hi - 1) & 31));
-                const int na = __popc(__ldg(a.absent_bits + gi) & rm);
-                if (na) atomicAdd(&g.nabs[i], na);
-                if (__ldg(a.exotic + gi)) atomicOr(&g.ex[i], 1u);
+                int na = 0;
+                uint32_t ex = 0;
+                if (hi > lo) {
+                    const int wi0 = lo >> 5, wi1 = (hi - 1) >> 5;
+                    for (int gi = wi0 + (tid & 31); gi <= wi1; gi += 32) {
+                        uint32_t rm = 0xffffffffu;
+                        if (gi == wi0) rm &= 0xffffffffu << (lo & 31);
+                        if (gi == wi1) rm &= 0xffffffffu >> (31 - ((hi - 1) & 31));
+                        na += __popc(__ldg(a.absent_bits + gi) & rm);
+                        ex |= __ldg(a.exotic + gi);
+                    }
+                }
+                na = __reduce_add_sync(0xffffffffu, na);
+                ex = __reduce_or_sync(0xffffffffu, ex);
+                if ((tid & 31) == 0) { g.nabs[i] = na; g.ex[i] = ex != 0; }
             }
             __syncthreads();
 
