@@ -282,7 +282,6 @@ int launch_score(cudaStream_t st, const ScoreCall &c, const WsLayout &L, int32_t
         const int words_cap = kScoreWordsCap;
         int wg = kMaxGroup;
         while (wg > 1 && (int64_t)((W + wg - 1) / wg) * tchunks < 2 * 7 * kNumSM) wg >>= 1;
-        if (const char *env = getenv("SSTAR_B200_WG")) { const int v = atoi(env); if (v >= 1 && v <= kMaxGroup) wg = v; }  // experiment hook
         if (c.disjoint) wg = 1;  // replicates share no variants (and their positions restart)
         const int64_t ngroups = (W + wg - 1) / wg;
         if (ngroups * tchunks > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "too many (window group, column chunk) tiles%s");
@@ -384,9 +383,8 @@ int sstar_b200_pack(int device, void *stream, const int8_t *d_ref_gt, const int8
     if (V > 0 && (!d_ref_gt || !d_tgt_gt)) return fail(SSTAR_B200_EINVAL, "null genotype pointer%s");
     DeviceGuard guard(device);
     if (guard.err != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
-    const char *env = getenv("SSTAR_B200_PACK_CTAS");  // experiment hook (tools/exp_pack_ctas.py)
     return launch_prep((cudaStream_t)stream, 0, L.G, d_ref_gt, d_tgt_gt, V, R, T, nullptr, nullptr, nullptr, nullptr,
-                       0, 0, 0, (uint8_t *)d_workspace, L, env ? atoi(env) : 0);
+                       0, 0, 0, (uint8_t *)d_workspace, L);
 }
 
 int sstar_b200_score_packed(int device, void *stream, const int8_t *d_tgt_gt, const int32_t *d_pos,
