@@ -38,6 +38,7 @@ WORKLOADS = {
            "C2: synthetic 10 Mb msprime-style chromosome, 100 ref + 50 target diploids (unphased), "
            "50 kb windows / 10 kb step"),
     "c2-small": (1_000_000, 100, 50, False, 50_000, 10_000, "C2 shape at 1 Mb (debug)"),
+    "c2-x4": (40_000_000, 100, 50, False, 50_000, 10_000, "C2 shape at 40 Mb: 20 MB of genotypes (host-entry threshold check)"),
     # large shapes (generated on the device; not the headline line -- roofline evidence)
     "c3-shard": (31_250_000, 500, 500, True, 50_000, 10_000,
                  "C3 shard: 1/8 of a 250 Mb chromosome, 500 ref + 500 target diploids, haplotype mode "
