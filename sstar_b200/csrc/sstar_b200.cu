@@ -517,16 +517,21 @@ bool mapped_pointer(const void *h, void **dptr) {
 }  // namespace
 
 // The end-to-end call.  PCIe is the bound (the genotype matrices are 100x the kernels' HBM time),
-// so the job is to keep both directions of the link busy and hide everything else under it:
-//   * the two genotype matrices go host->device in row chunks on an internal copy stream
-//     (copy engine: full PCIe read rate even for small transfers);
-//   * while chunk k+1 is in flight the caller's stream packs chunk k and scores every window whose
-//     variants are now all packed (windows sorted by end), so only the last chunk's kernels are
-//     exposed;
-//   * the score kernels store both result tables straight into the mapped host buffers (posted
-//     PCIe writes that overlap the inbound copies -- the link is full duplex -- and no D2H copy
-//     latency at the end).  pos / windows are small and latency-critical (the bounds search
-//     chases them), so they are copied to the device first.
+// so the job is to keep the link busy and hide everything else under it.  With page-locked, mapped
+// host buffers:
+//   * matrices of 32 MB and more go host->device in row chunks on an internal copy stream (copy
+//     engine: the full PCIe rate); while chunk k+1 is in flight the caller's stream packs chunk k
+//     and scores every window whose variants are now all packed (windows sorted by end), so only
+//     the last chunk's kernels are exposed.  pos / windows are small and latency-critical (the
+//     bounds search chases them): they are copied first.
+//   * smaller matrices are packed IN PLACE: copies of a few MB do not reach the link rate (and
+//     crawl on some hosts), the SMs' own reads of mapped host memory hold 34-42 GB/s everywhere.
+//     One prep grid does it all -- fetch CTAs bring pos / windows into the scratch, pack CTAs
+//     stream the matrices over PCIe tile by tile, bounds CTAs wait for the fetch -- and no copy
+//     engine or second stream is involved.
+//   * result tables below 8 MB are stored by the score kernels straight into the mapped host
+//     buffers (posted PCIe writes, no D2H copy latency at the end); larger ones go back as D2H
+//     copies (per chunk on the chunked path, overlapping the inbound traffic).
 // Pageable buffers or SSTAR_B200_FLAG_STAGED_COPIES take plain H2D / D2H copies on `stream`.
 extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int8_t *h_ref_gt,
                                              const int8_t *h_tgt_gt, const int32_t *h_pos, int64_t V,
@@ -598,9 +603,9 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
     // than SM stores to host memory (measured on the C4 shard: 5.66 vs 6.08 ms)
     const bool copy_out = (flags & SSTAR_B200_FLAG_COPY_OUTPUTS) != 0 || (int64_t)W * T * 12 >= ((int64_t)8 << 20);
     // How do the genotype matrices cross PCIe?  Large inputs go through the copy engine in chunks
-    // (55 GB/s, overlapped with the kernels).  Copies of a few MB do not reach that rate -- 31-34
-    // GB/s on a healthy link, ~12 GB/s on some hosts -- while the SMs' own reads of mapped host
-    // memory hold ~34 GB/s everywhere, so inputs below 32 MB are packed straight out of host
+    // (55 GB/s, overlapped with the kernels).  Copies of a few MB do not reach that rate -- 31-50
+    // GB/s depending on the host, ~12 GB/s on some -- while the SMs' own reads of mapped host
+    // memory hold 34-42 GB/s everywhere, so inputs below 32 MB are packed straight out of host
     // memory: the pack CTAs' TMA tile loads ARE the transfer, and there is nothing to wait for.
     const int64_t in_bytes = V * ((int64_t)R + T);
     const bool zero_copy_in = (flags & SSTAR_B200_FLAG_ZERO_COPY_INPUTS) != 0 ||
@@ -615,9 +620,6 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
     int64_t rows_per = ((V + nchunks - 1) / nchunks + 255) / 256 * 256;
     if (rows_per < 256) rows_per = 256;
     nchunks = V > 0 ? (int)((V + rows_per - 1) / rows_per) : 1;
-    // windows can be scored chunk by chunk only if they are sorted by end
-    bool sorted = true;
-    for (int32_t w = 1; w < W && sorted; ++w) sorted = h_win_end[w] >= h_win_end[w - 1];
 
     if (zero_copy_in) {
         // Small input read in place, in ONE prep grid on the caller's stream and without the copy
@@ -641,6 +643,9 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
         }
         return 0;
     }
+    // windows can be scored chunk by chunk only if they are sorted by end
+    bool sorted = nchunks > 1;
+    for (int32_t w = 1; w < W && sorted; ++w) sorted = h_win_end[w] >= h_win_end[w - 1];
     // the copy stream starts after whatever the caller already queued (it reuses the scratch)
     CUDA_TRY(cudaEventRecord(pc->entry, st));
     CUDA_TRY(cudaStreamWaitEvent(pc->copy, pc->entry, 0));
