@@ -964,6 +964,7 @@ extern "C" int sstar_b200_snp_set_offsets(int device, void *stream, const int8_t
     if (rc) return rc;
     const SetLayout S = make_set_layout(L, W, T);
     if (workspace_bytes < S.total) return fail(SSTAR_B200_EWORKSPACE, "workspace too small for SNP sets%s");
+    if (S.n > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "more than 2^31 - 1 units in one SNP-set call%s");
     if (!d_set_off) return fail(SSTAR_B200_EINVAL, "null offsets pointer%s");
     if (W > 0 && (!d_win_start || !d_win_end || !d_score || !d_nsnp))
         return fail(SSTAR_B200_EINVAL, "null window/output pointer%s");
