@@ -328,6 +328,17 @@ def roofline_block(name, st, k, tot_ms, pack_ms, score_ms, launches):
             out["issue"] = {"warp_inst": winst, "achieved": winst / (ms / k * 1e-3) / 1e9, "peak": ipeak,
                             "unit": "G warp-inst/s", "frac": winst / (ms / k * 1e-3) / 1e9 / ipeak,
                             "peak_source": f"{sms} SMs x 4 schedulers x {mhz:.0f} MHz"}
+        if kname == "score_group_kernel":
+            # integer operations of the REFERENCE formulation -- 8 per pair
+            # evaluation of the O(n^2) recurrence plus one mask test per window variant and unit --
+            # over the time this kernel takes (the prefix-max DP executes fewer; see "issue").
+            ops = 8 * st["sum_pairs"] + st["units"] * st["mean_window_variants"]
+            ipeak, sms, mhz = issue_peak_ginst()
+            apeak = sms * 128 * mhz * 1e6 / 1e12
+            out["alu_reference_formulation"] = {
+                "int_ops": int(ops), "achieved": ops / (ms / k * 1e-3) / 1e12, "peak": apeak, "unit": "T int-op/s",
+                "frac": ops / (ms / k * 1e-3) / 1e12 / apeak, "peak_source": f"{sms} SMs x 128 lanes x {mhz:.0f} MHz",
+                "exact": bool(st["n_exact"])}
         if note:
             out["note"] = note
         return out
