@@ -74,6 +74,7 @@ class ScoreEngine:
         self.tdev = torch.device("cuda", self.device)
         self._dev = {}
         self._pin = {}
+        self._pinned_calls = {}
         self.launches = 0  # kernels enqueued by the last call
 
     # ------------------------------------------------------------------ buffers
@@ -417,12 +418,20 @@ class ScoreEngine:
         V, R = ref_p.shape
         T = tgt_p.shape[1]
         W = ws_p.shape[0]
-        need = self.lib.sstar_b200_host_scratch_bytes(V, R, T, W, int(max_win_variants))
-        if need == 0:
-            raise SstarB200Error("invalid shapes for scratch sizing")
+        # per-shape bookkeeping is cached: this call sits inside the end-to-end time
+        key = (V, R, T, W, int(max_win_variants), algo, bool(staged), int(flags))
+        cached = self._pinned_calls.get(key)
+        if cached is None:
+            need = self.lib.sstar_b200_host_scratch_bytes(V, R, T, W, int(max_win_variants))
+            if need == 0:
+                raise SstarB200Error("invalid shapes for scratch sizing")
+            opts = _cabi.Options(algo=_cabi.ALGOS[algo], max_win_variants=int(max_win_variants),
+                                 flags=(_cabi.FLAG_STAGED_COPIES if staged else 0) | int(flags))
+            if len(self._pinned_calls) > 64:
+                self._pinned_calls.clear()
+            cached = self._pinned_calls[key] = (need, opts)
+        need, opts = cached
         scratch = self._dbuf("host_scratch", need, self.torch.uint8)
-        opts = _cabi.Options(algo=_cabi.ALGOS[algo], max_win_variants=int(max_win_variants),
-                             flags=(_cabi.FLAG_STAGED_COPIES if staged else 0) | int(flags))
         s = stream if stream is not None else self.torch.cuda.current_stream(self.tdev)
         rc = self.lib.sstar_b200_score_windows_host(
             self.device, ctypes.c_void_p(s.cuda_stream), ref_p.data_ptr(), tgt_p.data_ptr(),
