@@ -174,7 +174,7 @@ int launch_prep(cudaStream_t st, int64_t g_begin, int64_t g_end, const int8_t *d
         // groups per CTA that still fit the whole grid in ONE wave (6 CTAs per SM by registers)
         const size_t per_group = (size_t)32 * ((size_t)R + (size_t)T);
         int gpc_max = (int)((size_t)(64 << 10) / per_group);
-        if (gpc_max > 8) gpc_max = 8;
+        if (gpc_max > 32) gpc_max = 32;  // narrow panels (a few dozen columns): tiles of up to 1,024 variants
         if (gpc_max < 1) gpc_max = 1;
         const int64_t wave = (int64_t)6 * kNumSM - n_bounds;
         int gpc = 1;
@@ -279,14 +279,23 @@ int launch_score(cudaStream_t st, const ScoreCall &c, const WsLayout &L, int32_t
         // Windows per CTA: up to 16 consecutive ones (the list build and the per-CTA set-up are
         // shared by them; the kernel itself cuts a group into sub-groups that fit its position
         // tile), but keep at least two full waves of CTAs (7 resident per SM) so the tail stays short.
-        const int words_cap = kScoreWordsCap;
+        int words_cap = kScoreWordsCap;
         int wg = kMaxGroup;
         while (wg > 1 && (int64_t)((W + wg - 1) / wg) * tchunks < 2 * 7 * kNumSM) wg >>= 1;
         if (c.disjoint) wg = 1;  // replicates share no variants (and their positions restart)
         const int64_t ngroups = (W + wg - 1) / wg;
         if (ngroups * tchunks > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "too many (window group, column chunk) tiles%s");
-        const int Lslots = kScoreListBytes / (bd * 4) - 1;  // list slots per column (one more row is the spill slot)
-        const size_t ring_b = (size_t)wg * bd * 4, pos_b = (size_t)words_cap * 32 * 4;  // worklist | position tile
+        int Lslots = kScoreListBytes / (bd * 4) - 1;  // list slots per column (one more row is the spill slot)
+        size_t pos_b = (size_t)words_cap * 32 * 4;    // position tile
+        if (wg == 1 && c.max_win_variants > 0) {
+            // one window per CTA and its size is known: neither a column's list nor the position
+            // tile can outgrow it -- narrow launches (replicate batches) then keep more CTAs resident
+            if (Lslots > c.max_win_variants + 1) Lslots = c.max_win_variants + 1;
+            const int need_words = (c.max_win_variants + 31) / 32 + 1;
+            if (need_words < words_cap) words_cap = need_words;  // (a larger window than promised is walked from the planes)
+            pos_b = (size_t)words_cap * 32 * 4;
+        }
+        const size_t ring_b = (size_t)wg * bd * 4;  // worklist (shares the position tile's region)
         const size_t smem = (size_t)(Lslots + 1) * bd * 4 + (ring_b > pos_b ? ring_b : pos_b);  // +1: spill slot
         static thread_local SmemGrant group_grant;
         cudaError_t e = grant_smem(group_grant, score_group_kernel, smem);
