@@ -371,3 +371,21 @@ def test_many_small_windows_in_place(eng):
     for flags in (0, 1):
         s, n = eng.score_host(ref, tgt, pos, ws, we, flags=flags)
         assert np.array_equal(s, so) and np.array_equal(n, no), flags
+
+
+def test_rows_too_wide_to_stage(eng):
+    # 7,000 genotype bytes per variant row: a 32-row tile does not fit shared memory, so the pack
+    # kernel takes its byte path straight from global memory; T = 4,000 is 32 column chunks
+    rng = np.random.default_rng(12)
+    V, R, T = 330, 3000, 4000
+    pos = np.cumsum(rng.integers(20, 400, size=V)).astype(np.int32)
+    ref = (rng.random((V, R)) < 0.0004).astype(np.int8)
+    ref[rng.random(V) < 0.1, 7] = -1            # signed sums: a -1 and a +1 cancel
+    tgt = rng.choice([0, 1, 2], size=(V, T), p=[0.7, 0.2, 0.1]).astype(np.int8)
+    tgt[rng.random((V, T)) < 0.0005] = -1       # a few missing calls
+    ws = np.arange(1, int(pos[-1]), 10_000, dtype=np.int32)
+    we = (ws + 49_999).astype(np.int32)
+    so, no = c_oracle.score_windows(ref, tgt, pos, ws, we)
+    for flags in (0, 1):
+        s, n = eng.score_host(ref, tgt, pos, ws, we, flags=flags)
+        assert np.array_equal(s, so) and np.array_equal(n, no), flags
