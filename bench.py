@@ -45,8 +45,11 @@ WORKLOADS = {
                  "(R = T = 1000 columns), 50 kb / 10 kb"),
     "c4-shard": (30_000_000, 100, 2000, False, 50_000, 10_000,
                  "C4 shard: 30 Mb, 100 ref + 2000 target diploids (unphased), 50 kb / 10 kb"),
+    # wide panels (debug): one 32-row tile is 163 KB (one pack CTA per SM) / does not fit at all (byte path)
+    "wide5k": (30_000_000, 50, 2500, True, 50_000, 10_000, "30 Mb, 50 ref + 2500 target diploids, haplotype mode (T = 5000)"),
+    "wide8k": (30_000_000, 50, 4000, True, 50_000, 10_000, "30 Mb, 50 ref + 4000 target diploids, haplotype mode (T = 8000)"),
 }
-LARGE = {"c3-shard", "c4-shard"}
+LARGE = {"c3-shard", "c4-shard", "wide5k", "wide8k"}
 
 
 def make_workload(name, rank):

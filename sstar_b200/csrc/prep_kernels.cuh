@@ -159,9 +159,12 @@ __device__ __forceinline__ void transpose4(uint32_t a0, uint32_t a1, uint32_t a2
     c[3] = __byte_perm(t2, t3, 0x7632);
 }
 
+// The staged target tile holds columns [c0, c0 + ncols) of the CTA's rows with a row pitch of
+// `tpitch` bytes (whole rows: c0 = 0, ncols = tpitch = T; wide panels: one column chunk).
 template <bool kAligned>
 __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int32_t g0, int ng, int nrows,
-                                          uint32_t ref_phase, uint32_t tgt_phase) {
+                                          uint32_t ref_phase, uint32_t tgt_phase, int32_t tpitch, int32_t c0,
+                                          int32_t ncols) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int nwarps = kPackThreads / 32;
     uint8_t *s_flag = smem;                                                  // [gpc*32] absent per row
@@ -226,24 +229,24 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
         if (lane == 0) {
             s_word[gl] = bits;
             s_exo[gl] = 0;
-            a.absent_bits[g0 + gl] = bits;
+            if (c0 == 0) a.absent_bits[g0 + gl] = bits;  // (every column chunk of a group computes the same word)
         }
     }
     __syncthreads();
 
     // B: 4 columns x 32 rows per thread
-    const int nq = (a.T + 3) >> 2;
+    const int nq = (ncols + 3) >> 2;
     const int nitems = ng * nq;
     for (int it = tid; it < nitems; it += kPackThreads) {
         const int gl = it / nq, q = it - gl * nq;
-        const uint32_t base = tgt_phase + (uint32_t)(gl * 32) * (uint32_t)a.T + 4u * q;
+        const uint32_t base = tgt_phase + (uint32_t)(gl * 32) * (uint32_t)tpitch + 4u * q;
         uint32_t nz[4], tw[4], e_or = 0, e_and = 0;
 #pragma unroll
         for (int blk = 0; blk < 4; ++blk) {
             uint32_t an = 0, at = 0;
 #pragma unroll
             for (int rr = 7; rr >= 0; --rr) {  // row 7 first: it ends up in bit 7 of each byte
-                const uint32_t w = lds_word<kAligned>(s_tgt, base + (uint32_t)(blk * 8 + rr) * (uint32_t)a.T);
+                const uint32_t w = lds_word<kAligned>(s_tgt, base + (uint32_t)(blk * 8 + rr) * (uint32_t)tpitch);
                 const uint32_t h = w >> 1;
                 an = an + an + ((w | h) & 0x01010101u);  // byte in {1,2,3} -> bit 0
                 at = at + at + (h & 0x01010101u);        // byte in {2,3}   -> bit 0
@@ -257,7 +260,7 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
         uint32_t car[4], two[4];
         transpose4(nz[0], nz[1], nz[2], nz[3], car);
         transpose4(tw[0], tw[1], tw[2], tw[3], two);
-        const int ncol = min(4, a.T - 4 * q);
+        const int ncol = min(4, ncols - 4 * q);
         bool exotic = false;
         if ((e_or & 0xfcfcfcfcu) | (e_and & 0x01010101u)) {
             // a byte outside {0,1,2} somewhere in this 32x4 block (or in the padding bytes of a
@@ -268,7 +271,7 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
                 if (c >= ncol) continue;
                 uint32_t m_nz = 0, m_two = 0;
                 for (int r = 0; r < 32; ++r) {
-                    const int b = (int8_t)bytes[(uint32_t)r * (uint32_t)a.T + c];
+                    const int b = (int8_t)bytes[(uint32_t)r * (uint32_t)tpitch + c];
                     const uint32_t isab = (ab >> r) & 1u;
                     m_nz |= ((uint32_t)(b != 0) & isab) << r;
                     m_two |= ((uint32_t)(b == 2) & isab) << r;
@@ -278,7 +281,7 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
                 two[c] = m_two;
             }
         }
-        const size_t o = (size_t)(g0 + gl) * a.Tp + 4 * q;
+        const size_t o = (size_t)(g0 + gl) * a.Tp + c0 + 4 * q;
         if (ncol == 4) {
             *reinterpret_cast<uint4 *>(a.carried + o) = make_uint4(car[0] & ab, car[1] & ab, car[2] & ab, car[3] & ab);
             *reinterpret_cast<uint4 *>(a.two + o) = make_uint4(two[0] & ab, two[1] & ab, two[2] & ab, two[3] & ab);
@@ -293,7 +296,10 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
         if (exotic) atomicOr(&s_exo[gl], 1u);
     }
     __syncthreads();
-    if (tid < ng) a.exotic[g0 + tid] = s_exo[tid];
+    if (tid < ng) {
+        if (a.cchunks > 1) { if (s_exo[tid]) atomicOr(&a.exotic[g0 + tid], 1u); }  // zeroed by the host; chunks share the flag
+        else a.exotic[g0 + tid] = s_exo[tid];
+    }
 }
 
 // Fallback for rows too wide to stage (32 * (R + T) bytes beyond shared memory): byte-wise from
@@ -348,7 +354,8 @@ __device__ __forceinline__ void pack_tile_direct(const PackArgs &a, uint8_t *sme
     if (tid < ng) a.exotic[g0 + tid] = s_exo[tid];
 }
 
-// mode: 0 = staged word path, 1 = direct byte path
+// mode: 0 = staged word path (whole rows), 1 = direct byte path, 2 = staged word path, one column chunk
+// of the target rows per tile (wide panels)
 __global__ void __launch_bounds__(kPackThreads)
 prep_kernel(const __grid_constant__ PackArgs p, const __grid_constant__ BoundsArgs b, int n_pack, int mode) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -373,7 +380,8 @@ prep_kernel(const __grid_constant__ PackArgs p, const __grid_constant__ BoundsAr
         fence_mbar_init();
     }
     for (int tile = blk; tile < p.n_tiles; tile += n_pack) {
-        const int32_t g0 = p.g_begin + tile * p.gpc;
+        const int cchunk = p.cchunks > 1 ? tile % p.cchunks : 0;
+        const int32_t g0 = p.g_begin + (p.cchunks > 1 ? tile / p.cchunks : tile) * p.gpc;
         const int ng = min(p.gpc, p.g_end - g0);
         const int32_t k0 = g0 * 32;
         const int nrows = min(ng * 32, p.V - k0);
@@ -385,8 +393,32 @@ prep_kernel(const __grid_constant__ PackArgs p, const __grid_constant__ BoundsAr
         uint8_t *s_ref = smem + p.gpc * 32 + align16(p.gpc * 8);
         uint8_t *s_tgt = s_ref + p.ref_tile_bytes;
         const int8_t *gref = p.ref + (size_t)k0 * p.R;
+        const uint32_t ref_bytes = (uint32_t)nrows * (uint32_t)p.R;
+        if (mode == 2) {
+            // Wide panel: the group's reference rows (one span) and ONE column chunk of its target
+            // rows (a 16-byte aligned segment per row: the host takes this mode only when T and the
+            // chunk width are multiples of 16) go to the TMA engine; the chunks of a group each
+            // redo the reference row sums rather than wait for one another.
+            const int32_t c0 = cchunk * p.ccols, ncols = min(p.ccols, p.T - c0);
+            const bool rbulk = (((uintptr_t)gref & 15) == 0) && ((ref_bytes & 15u) == 0);
+            uint32_t rph = 0;
+            if (tid == 0) {
+                mbar_expect_tx(&s_bar[0], (rbulk ? ref_bytes : 0u) + (uint32_t)nrows * (uint32_t)ncols);
+                if (rbulk) bulk_g2s(s_ref, gref, ref_bytes, &s_bar[0]);
+            }
+            if (tid < nrows)
+                bulk_g2s(s_tgt + (uint32_t)tid * (uint32_t)p.ccols, p.tgt + (size_t)(k0 + tid) * p.T + c0, (uint32_t)ncols,
+                         &s_bar[0]);
+            if (!rbulk) rph = stage_span(s_ref, gref, ref_bytes, tid, kPackThreads);
+            __syncthreads();
+            mbar_wait(&s_bar[0], parity);
+            parity ^= 1u;
+            pack_tile<true>(p, smem, g0, ng, nrows, rph, 0u, p.ccols, c0, ncols);
+            __syncthreads();
+            continue;
+        }
         const int8_t *gtgt = p.tgt + (size_t)k0 * p.T;
-        const uint32_t ref_bytes = (uint32_t)nrows * (uint32_t)p.R, tgt_bytes = (uint32_t)nrows * (uint32_t)p.T;
+        const uint32_t tgt_bytes = (uint32_t)nrows * (uint32_t)p.T;
         uint32_t rph = 0, tph = 0;
         const bool bulk = ((((uintptr_t)gref | (uintptr_t)gtgt) & 15) == 0) && (((ref_bytes | tgt_bytes) & 15u) == 0);
         if (bulk) {
@@ -405,8 +437,8 @@ prep_kernel(const __grid_constant__ PackArgs p, const __grid_constant__ BoundsAr
             __syncthreads();
         }
         const bool aligned = ((tph | (uint32_t)p.T) & 3u) == 0;
-        if (aligned) pack_tile<true>(p, smem, g0, ng, nrows, rph, tph);
-        else         pack_tile<false>(p, smem, g0, ng, nrows, rph, tph);
+        if (aligned) pack_tile<true>(p, smem, g0, ng, nrows, rph, tph, p.T, 0, p.T);
+        else         pack_tile<false>(p, smem, g0, ng, nrows, rph, tph, p.T, 0, p.T);
         __syncthreads();  // the tile and its flags are done with before the next one lands
     }
 }

@@ -185,11 +185,32 @@ int launch_prep(cudaStream_t st, int64_t g_begin, int64_t g_end, const int8_t *d
         p.tgt_tile_bytes = (uint32_t)align_up((size_t)gpc * 32 * T + 32, 16);
         const size_t fixed = (size_t)gpc * 32 + align16((uint32_t)gpc * 8);
         smem = fixed + p.ref_tile_bytes + p.tgt_tile_bytes;
-        if (smem > (size_t)200 << 10) {  // rows too wide to stage: byte path straight from global
+        n_pack = (int)((ngroups + gpc - 1) / gpc);
+        // Wide panels: once three 32-row tiles no longer fit an SM, stage the group's reference rows
+        // with ONE column chunk of its target rows (16-byte aligned row segments for the TMA engine:
+        // T a multiple of 16, base aligned; chunks of a multiple of 128 columns, tile <= 64 KB).
+        // Without those alignments: whole rows while one tile fits, else the byte path.
+        const size_t ref_b = align_up((size_t)32 * R + 32, 16);
+        if (smem > (size_t)73 << 10 && (T & 15) == 0 && ((uintptr_t)d_tgt & 15) == 0 && ref_b <= ((size_t)40 << 10)) {
+            mode = 2;
+            p.gpc = 1;
+            int32_t ccols = (int32_t)((((size_t)64 << 10) - ref_b - 64) / 32 / 128 * 128);
+            p.cchunks = (T + ccols - 1) / ccols;
+            ccols = (int32_t)align_up((size_t)(T + p.cchunks - 1) / p.cchunks, 128);  // even chunks
+            p.cchunks = (T + ccols - 1) / ccols;
+            p.ccols = ccols;
+            p.ref_tile_bytes = (uint32_t)ref_b;
+            p.tgt_tile_bytes = (uint32_t)(32 * ccols);
+            smem = (size_t)32 + align16(8u) + p.ref_tile_bytes + p.tgt_tile_bytes;
+            if (ngroups * p.cchunks > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "too many pack tiles%s");
+            n_pack = (int)(ngroups * p.cchunks);
+            // the chunks of a group OR their exotic flags together
+            cudaError_t em = cudaMemsetAsync(p.exotic + g_begin, 0, (size_t)ngroups * 4, st);
+            if (em != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaMemsetAsync: %s", cudaGetErrorString(em));
+        } else if (smem > (size_t)200 << 10) {  // rows too wide to stage: byte path straight from global
             mode = 1;
             smem = fixed;
         }
-        n_pack = (int)((ngroups + gpc - 1) / gpc);
         p.n_tiles = n_pack;
         if (pack_ctas > 0 && pack_ctas < n_pack) n_pack = pack_ctas;
     }

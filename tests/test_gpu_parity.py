@@ -389,3 +389,22 @@ def test_rows_too_wide_to_stage(eng):
     for flags in (0, 1):
         s, n = eng.score_host(ref, tgt, pos, ws, we, flags=flags)
         assert np.array_equal(s, so) and np.array_equal(n, no), flags
+
+
+@pytest.mark.parametrize("R,T", [(60, 4000), (16, 2512), (1200, 1600)])
+def test_wide_panels_take_column_chunks(eng, R, T):
+    # 32 rows of R + T bytes exceed a third of an SM's shared memory: the pack stages one column
+    # chunk of the target rows per CTA (T a multiple of 16), every chunk redoing the row sums
+    rng = np.random.default_rng(R + T)
+    V = 1000 + R % 7          # tail rows (V % 32 != 0)
+    pos = np.cumsum(rng.integers(20, 400, size=V)).astype(np.int32)
+    ref = (rng.random((V, R)) < 0.01).astype(np.int8)
+    ref[rng.random(V) < 0.1, R // 2] = -1
+    tgt = rng.choice([0, 1, 2], size=(V, T), p=[0.7, 0.2, 0.1]).astype(np.int8)
+    tgt[rng.random((V, T)) < 0.0005] = rng.choice([-1, 3]).astype(np.int8)
+    ws = np.arange(1, int(pos[-1]), 10_000, dtype=np.int32)
+    we = (ws + 49_999).astype(np.int32)
+    so, no = c_oracle.score_windows(ref, tgt, pos, ws, we)
+    for flags in (0, 1):
+        s, n = eng.score_host(ref, tgt, pos, ws, we, flags=flags)
+        assert np.array_equal(s, so) and np.array_equal(n, no), flags
