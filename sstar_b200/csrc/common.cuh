@@ -62,6 +62,7 @@ struct PackArgs {
     int32_t g_begin, g_end, gpc;  // 32-variant groups [g_begin, g_end) packed by this launch
     int32_t n_tiles;              // tiles of gpc groups; the grid's pack CTAs stride over them
     int32_t cchunks, ccols;       // wide panels (mode 2): a tile is one group x ccols target columns, cchunks per group
+    int32_t tpitch;               // ... staged with this row pitch (ccols, + 16 when the segments keep their 16-byte phase)
     uint32_t ref_tile_bytes;  // smem bytes reserved per tile (incl. alignment slack)
     uint32_t tgt_tile_bytes;
     uint32_t *absent_bits, *exotic, *carried, *two;

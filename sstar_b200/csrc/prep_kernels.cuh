@@ -109,6 +109,13 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// tx bytes announced by the thread that issues the copy, the (single) arrival made separately
+__device__ __forceinline__ void mbar_add_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -161,7 +168,9 @@ __device__ __forceinline__ void transpose4(uint32_t a0, uint32_t a1, uint32_t a2
 
 // The staged target tile holds columns [c0, c0 + ncols) of the CTA's rows with a row pitch of
 // `tpitch` bytes (whole rows: c0 = 0, ncols = tpitch = T; wide panels: one column chunk).
-template <bool kAligned>
+// kRowPhase: every row segment was staged keeping its own 16-byte phase (column chunks of a matrix
+// whose row length is not a multiple of 16): row r starts at r * tpitch + ((tgt_phase + r * T) & 15).
+template <bool kAligned, bool kRowPhase = false>
 __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int32_t g0, int ng, int nrows,
                                           uint32_t ref_phase, uint32_t tgt_phase, int32_t tpitch, int32_t c0,
                                           int32_t ncols) {
@@ -240,13 +249,19 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
     for (int it = tid; it < nitems; it += kPackThreads) {
         const int gl = it / nq, q = it - gl * nq;
         const uint32_t base = tgt_phase + (uint32_t)(gl * 32) * (uint32_t)tpitch + 4u * q;
+        const uint32_t pstep = (uint32_t)a.T & 15u;
+        auto row_off = [&](int r) -> uint32_t {  // r: row within the group
+            if (!kRowPhase) return base + (uint32_t)r * (uint32_t)tpitch;
+            const uint32_t rr = (uint32_t)(gl * 32 + r);
+            return rr * (uint32_t)tpitch + ((tgt_phase + rr * pstep) & 15u) + 4u * q;
+        };
         uint32_t nz[4], tw[4], e_or = 0, e_and = 0;
 #pragma unroll
         for (int blk = 0; blk < 4; ++blk) {
             uint32_t an = 0, at = 0;
 #pragma unroll
             for (int rr = 7; rr >= 0; --rr) {  // row 7 first: it ends up in bit 7 of each byte
-                const uint32_t w = lds_word<kAligned>(s_tgt, base + (uint32_t)(blk * 8 + rr) * (uint32_t)tpitch);
+                const uint32_t w = lds_word<kAligned>(s_tgt, row_off(blk * 8 + rr));
                 const uint32_t h = w >> 1;
                 an = an + an + ((w | h) & 0x01010101u);  // byte in {1,2,3} -> bit 0
                 at = at + at + (h & 0x01010101u);        // byte in {2,3}   -> bit 0
@@ -265,13 +280,12 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
         if ((e_or & 0xfcfcfcfcu) | (e_and & 0x01010101u)) {
             // a byte outside {0,1,2} somewhere in this 32x4 block (or in the padding bytes of a
             // ragged last quad / tail rows): redo it exactly, byte by byte
-            const uint8_t *bytes = s_tgt + base;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 if (c >= ncol) continue;
                 uint32_t m_nz = 0, m_two = 0;
                 for (int r = 0; r < 32; ++r) {
-                    const int b = (int8_t)bytes[(uint32_t)r * (uint32_t)tpitch + c];
+                    const int b = (int8_t)s_tgt[row_off(r) + c];
                     const uint32_t isab = (ab >> r) & 1u;
                     m_nz |= ((uint32_t)(b != 0) & isab) << r;
                     m_two |= ((uint32_t)(b == 2) & isab) << r;
@@ -401,19 +415,42 @@ prep_kernel(const __grid_constant__ PackArgs p, const __grid_constant__ BoundsAr
             // redo the reference row sums rather than wait for one another.
             const int32_t c0 = cchunk * p.ccols, ncols = min(p.ccols, p.T - c0);
             const bool rbulk = (((uintptr_t)gref & 15) == 0) && ((ref_bytes & 15u) == 0);
+            const int8_t *gt0 = p.tgt + (size_t)k0 * p.T + c0;  // first row's segment
+            const uint32_t tph0 = (uint32_t)((uintptr_t)gt0 & 15);
+            const bool seg16 = ((tph0 | (uint32_t)p.T) & 15u) == 0;  // every segment 16-byte aligned (chunks start at multiples of 128)
             uint32_t rph = 0;
-            if (tid == 0) {
-                mbar_expect_tx(&s_bar[0], (rbulk ? ref_bytes : 0u) + (uint32_t)nrows * (uint32_t)ncols);
-                if (rbulk) bulk_g2s(s_ref, gref, ref_bytes, &s_bar[0]);
+            if (tid == 0 && rbulk) {
+                mbar_add_tx(&s_bar[0], ref_bytes);
+                bulk_g2s(s_ref, gref, ref_bytes, &s_bar[0]);
             }
-            if (tid < nrows)
-                bulk_g2s(s_tgt + (uint32_t)tid * (uint32_t)p.ccols, p.tgt + (size_t)(k0 + tid) * p.T + c0, (uint32_t)ncols,
-                         &s_bar[0]);
+            int fallback_row = -1;
+            if (tid < nrows) {
+                // the 16-byte aligned superset of the row's segment: the row keeps its phase in the tile
+                const int8_t *src = gt0 + (size_t)tid * p.T;
+                const uint32_t ph = (uint32_t)((uintptr_t)src & 15);
+                const uint32_t bytes = (ncols + ph + 15u) & ~15u;
+                if (src - ph + bytes <= p.tgt + (size_t)p.V * p.T) {
+                    mbar_add_tx(&s_bar[0], bytes);
+                    bulk_g2s(s_tgt + (uint32_t)tid * (uint32_t)p.tpitch, src - ph, bytes, &s_bar[0]);
+                } else {
+                    fallback_row = tid;  // the superset would run past the end of the matrix (its last row)
+                }
+            }
             if (!rbulk) rph = stage_span(s_ref, gref, ref_bytes, tid, kPackThreads);
-            __syncthreads();
+            {   // at most the matrix's last row: one warp stages it with vector loads
+                const uint32_t fm = __ballot_sync(0xffffffffu, fallback_row >= 0);
+                if (tid < 32 && fm) {
+                    const int r = __ffs(fm) - 1;
+                    stage_span(s_tgt + (uint32_t)r * (uint32_t)p.tpitch, gt0 + (size_t)r * p.T, (uint32_t)ncols, tid, 32);
+                }
+            }
+            __syncthreads();  // every copy is announced before the barrier's one arrival
+            if (tid == 0) mbar_arrive(&s_bar[0]);
             mbar_wait(&s_bar[0], parity);
             parity ^= 1u;
-            pack_tile<true>(p, smem, g0, ng, nrows, rph, 0u, p.ccols, c0, ncols);
+            if (seg16) pack_tile<true>(p, smem, g0, ng, nrows, rph, 0u, p.tpitch, c0, ncols);
+            else if (((tph0 | (uint32_t)p.T) & 3u) == 0) pack_tile<true, true>(p, smem, g0, ng, nrows, rph, tph0, p.tpitch, c0, ncols);
+            else pack_tile<false, true>(p, smem, g0, ng, nrows, rph, tph0, p.tpitch, c0, ncols);
             __syncthreads();
             continue;
         }

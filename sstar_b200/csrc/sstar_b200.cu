@@ -187,20 +187,26 @@ int launch_prep(cudaStream_t st, int64_t g_begin, int64_t g_end, const int8_t *d
         smem = fixed + p.ref_tile_bytes + p.tgt_tile_bytes;
         n_pack = (int)((ngroups + gpc - 1) / gpc);
         // Wide panels: once three 32-row tiles no longer fit an SM, stage the group's reference rows
-        // with ONE column chunk of its target rows (16-byte aligned row segments for the TMA engine:
-        // T a multiple of 16, base aligned; chunks of a multiple of 128 columns, tile <= 64 KB).
-        // Without those alignments: whole rows while one tile fits, else the byte path.
+        // with ONE column chunk of its target rows (chunks of a multiple of 128 columns, tile <= 73
+        // KB).  Only a reference panel too wide for that keeps whole rows (while one tile fits) or
+        // the byte path.
         const size_t ref_b = align_up((size_t)32 * R + 32, 16);
-        if (smem > (size_t)73 << 10 && (T & 15) == 0 && ((uintptr_t)d_tgt & 15) == 0 && ref_b <= ((size_t)40 << 10)) {
+        if (smem > (size_t)73 << 10 && ref_b <= ((size_t)40 << 10)) {
             mode = 2;
             p.gpc = 1;
-            int32_t ccols = (int32_t)((((size_t)64 << 10) - ref_b - 64) / 32 / 128 * 128);
-            p.cchunks = (T + ccols - 1) / ccols;
-            ccols = (int32_t)align_up((size_t)(T + p.cchunks - 1) / p.cchunks, 128);  // even chunks
+            // chunk width: 2,048 or 1,024 columns give the 256 threads whole rounds of 4-column items
+            // (phase B); otherwise the widest multiple of 128 that keeps the tile within 73 KB
+            // (row segments that are not 16-byte aligned -- T not a multiple of 16 -- are staged by
+            // vector loads keeping each row's phase: 16 spare bytes per row)
+            const bool seg16 = (T & 15) == 0 && ((uintptr_t)d_tgt & 15) == 0;
+            int32_t ccols = (int32_t)((((size_t)73 << 10) - ref_b - 64 - (seg16 ? 0 : 32 * 16)) / 32 / 128 * 128);
+            if (ccols >= 2048) ccols = 2048;
+            else if (ccols >= 1024) ccols = 1024;
             p.cchunks = (T + ccols - 1) / ccols;
             p.ccols = ccols;
+            p.tpitch = seg16 ? ccols : ccols + 16;
             p.ref_tile_bytes = (uint32_t)ref_b;
-            p.tgt_tile_bytes = (uint32_t)(32 * ccols);
+            p.tgt_tile_bytes = (uint32_t)(32 * p.tpitch + 16);
             smem = (size_t)32 + align16(8u) + p.ref_tile_bytes + p.tgt_tile_bytes;
             if (ngroups * p.cchunks > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "too many pack tiles%s");
             n_pack = (int)(ngroups * p.cchunks);

@@ -391,10 +391,11 @@ def test_rows_too_wide_to_stage(eng):
         assert np.array_equal(s, so) and np.array_equal(n, no), flags
 
 
-@pytest.mark.parametrize("R,T", [(60, 4000), (16, 2512), (1200, 1600)])
+@pytest.mark.parametrize("R,T", [(60, 4000), (16, 2512), (1200, 1600),   # T % 16 == 0: row segments go through TMA
+                                 (60, 4004), (33, 3001), (7, 2406)])       # staged with their own 16-byte phases
 def test_wide_panels_take_column_chunks(eng, R, T):
     # 32 rows of R + T bytes exceed a third of an SM's shared memory: the pack stages one column
-    # chunk of the target rows per CTA (T a multiple of 16), every chunk redoing the row sums
+    # chunk of the target rows per CTA, every chunk redoing the row sums
     rng = np.random.default_rng(R + T)
     V = 1000 + R % 7          # tail rows (V % 32 != 0)
     pos = np.cumsum(rng.integers(20, 400, size=V)).astype(np.int32)
