@@ -170,10 +170,12 @@ __device__ __forceinline__ void transpose4(uint32_t a0, uint32_t a1, uint32_t a2
 // `tpitch` bytes (whole rows: c0 = 0, ncols = tpitch = T; wide panels: one column chunk).
 // kRowPhase: every row segment was staged keeping its own 16-byte phase (column chunks of a matrix
 // whose row length is not a multiple of 16): row r starts at r * tpitch + ((tgt_phase + r * T) & 15).
-template <bool kAligned, bool kRowPhase = false>
+// kChunked = false (whole rows) takes pitch, origin and width from T itself.
+template <bool kAligned, bool kRowPhase = false, bool kChunked = false>
 __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int32_t g0, int ng, int nrows,
-                                          uint32_t ref_phase, uint32_t tgt_phase, int32_t tpitch, int32_t c0,
-                                          int32_t ncols) {
+                                          uint32_t ref_phase, uint32_t tgt_phase, int32_t tpitch_ = 0, int32_t c0_ = 0,
+                                          int32_t ncols_ = 0) {
+    const int32_t tpitch = kChunked ? tpitch_ : a.T, c0 = kChunked ? c0_ : 0, ncols = kChunked ? ncols_ : a.T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int nwarps = kPackThreads / 32;
     uint8_t *s_flag = smem;                                                  // [gpc*32] absent per row
@@ -311,7 +313,7 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
     }
     __syncthreads();
     if (tid < ng) {
-        if (a.cchunks > 1) { if (s_exo[tid]) atomicOr(&a.exotic[g0 + tid], 1u); }  // zeroed by the host; chunks share the flag
+        if (kChunked) { if (s_exo[tid]) atomicOr(&a.exotic[g0 + tid], 1u); }  // zeroed by the host; chunks share the flag
         else a.exotic[g0 + tid] = s_exo[tid];
     }
 }
@@ -370,10 +372,11 @@ __device__ __forceinline__ void pack_tile_direct(const PackArgs &a, uint8_t *sme
 
 // mode: 0 = staged word path (whole rows), 1 = direct byte path, 2 = staged word path, one column chunk
 // of the target rows per tile (wide panels)
-__global__ void __launch_bounds__(kPackThreads)
-prep_kernel(const __grid_constant__ PackArgs p, const __grid_constant__ BoundsArgs b, int n_pack, int mode) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ __align__(8) uint64_t s_bar[2];
+// (kWide compiles the column-chunk mode in: it lives in a kernel of its own so that the common
+// kernel keeps its 48 registers and five resident CTAs per SM)
+template <bool kWide>
+__device__ __forceinline__ void prep_body(const PackArgs &p, const BoundsArgs &b, int n_pack, int mode, uint8_t *smem,
+                                          uint64_t *s_bar) {
     pdl_launch_dependents();  // let the next kernel's CTAs get scheduled while this grid drains
     if ((int)blockIdx.x < b.n_fetch) {
         fetch_block(b, (int)blockIdx.x, kPackThreads, threadIdx.x);
@@ -394,8 +397,8 @@ prep_kernel(const __grid_constant__ PackArgs p, const __grid_constant__ BoundsAr
         fence_mbar_init();
     }
     for (int tile = blk; tile < p.n_tiles; tile += n_pack) {
-        const int cchunk = p.cchunks > 1 ? tile % p.cchunks : 0;
-        const int32_t g0 = p.g_begin + (p.cchunks > 1 ? tile / p.cchunks : tile) * p.gpc;
+        const int cchunk = (kWide && mode == 2) ? tile % p.cchunks : 0;
+        const int32_t g0 = p.g_begin + ((kWide && mode == 2) ? tile / p.cchunks : tile) * p.gpc;
         const int ng = min(p.gpc, p.g_end - g0);
         const int32_t k0 = g0 * 32;
         const int nrows = min(ng * 32, p.V - k0);
@@ -408,7 +411,7 @@ prep_kernel(const __grid_constant__ PackArgs p, const __grid_constant__ BoundsAr
         uint8_t *s_tgt = s_ref + p.ref_tile_bytes;
         const int8_t *gref = p.ref + (size_t)k0 * p.R;
         const uint32_t ref_bytes = (uint32_t)nrows * (uint32_t)p.R;
-        if (mode == 2) {
+        if (kWide && mode == 2) {
             // Wide panel: the group's reference rows (one span) and ONE column chunk of its target
             // rows (a 16-byte aligned segment per row: the host takes this mode only when T and the
             // chunk width are multiples of 16) go to the TMA engine; the chunks of a group each
@@ -448,9 +451,9 @@ prep_kernel(const __grid_constant__ PackArgs p, const __grid_constant__ BoundsAr
             if (tid == 0) mbar_arrive(&s_bar[0]);
             mbar_wait(&s_bar[0], parity);
             parity ^= 1u;
-            if (seg16) pack_tile<true>(p, smem, g0, ng, nrows, rph, 0u, p.tpitch, c0, ncols);
-            else if (((tph0 | (uint32_t)p.T) & 3u) == 0) pack_tile<true, true>(p, smem, g0, ng, nrows, rph, tph0, p.tpitch, c0, ncols);
-            else pack_tile<false, true>(p, smem, g0, ng, nrows, rph, tph0, p.tpitch, c0, ncols);
+            if (seg16) pack_tile<true, false, true>(p, smem, g0, ng, nrows, rph, 0u, p.tpitch, c0, ncols);
+            else if (((tph0 | (uint32_t)p.T) & 3u) == 0) pack_tile<true, true, true>(p, smem, g0, ng, nrows, rph, tph0, p.tpitch, c0, ncols);
+            else pack_tile<false, true, true>(p, smem, g0, ng, nrows, rph, tph0, p.tpitch, c0, ncols);
             __syncthreads();
             continue;
         }
@@ -474,10 +477,24 @@ prep_kernel(const __grid_constant__ PackArgs p, const __grid_constant__ BoundsAr
             __syncthreads();
         }
         const bool aligned = ((tph | (uint32_t)p.T) & 3u) == 0;
-        if (aligned) pack_tile<true>(p, smem, g0, ng, nrows, rph, tph, p.T, 0, p.T);
-        else         pack_tile<false>(p, smem, g0, ng, nrows, rph, tph, p.T, 0, p.T);
+        if (aligned) pack_tile<true>(p, smem, g0, ng, nrows, rph, tph);
+        else         pack_tile<false>(p, smem, g0, ng, nrows, rph, tph);
         __syncthreads();  // the tile and its flags are done with before the next one lands
     }
+}
+
+__global__ void __launch_bounds__(kPackThreads)
+prep_kernel(const __grid_constant__ PackArgs p, const __grid_constant__ BoundsArgs b, int n_pack, int mode) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    prep_body<false>(p, b, n_pack, mode, smem, s_bar);
+}
+
+__global__ void __launch_bounds__(kPackThreads)
+prep_wide_kernel(const __grid_constant__ PackArgs p, const __grid_constant__ BoundsArgs b, int n_pack, int mode) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    prep_body<true>(p, b, n_pack, mode, smem, s_bar);
 }
 
 }  // namespace sstar

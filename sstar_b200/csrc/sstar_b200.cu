@@ -233,10 +233,12 @@ int launch_prep(cudaStream_t st, int64_t g_begin, int64_t g_end, const int8_t *d
     }
     if (n_pack + n_bounds == 0) return 0;
     const int n_fetch = b.n_fetch;
-    static thread_local SmemGrant prep_grant;
-    cudaError_t e = grant_smem(prep_grant, prep_kernel, smem);
+    static thread_local SmemGrant prep_grant, wide_grant;
+    const bool wide = mode == 2;
+    cudaError_t e = wide ? grant_smem(wide_grant, prep_wide_kernel, smem) : grant_smem(prep_grant, prep_kernel, smem);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaFuncSetAttribute(prep): %s", cudaGetErrorString(e));
-    e = launch(prep_kernel, (unsigned)(n_fetch + n_pack + n_bounds), kPackThreads, smem, st, false, p, b, n_pack, mode);
+    e = launch(wide ? prep_wide_kernel : prep_kernel, (unsigned)(n_fetch + n_pack + n_bounds), kPackThreads, smem, st, false,
+               p, b, n_pack, mode);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "prep_kernel launch: %s", cudaGetErrorString(e));
     return 0;
 }
