@@ -38,7 +38,7 @@ d = collections.OrderedDict()
 for r in rows[1:]:
     try: d.setdefault((r[ki][:40], r[gi]), []).append(float(r[vi]))
     except ValueError: pass
-for k, v in d.items(): print(k, len(v), round(sum(v) / len(v)))
+for k, v in d.items(): print(k, len(v), 'median', sorted(v)[len(v) // 2], 'mean', round(sum(v) / len(v)))
 for f in (f"{tag}_bench_default_n1.json", f"{tag}_bench_c3-shard.json", f"{tag}_bench_c4-shard.json"):
     x = json.loads(open("profiles/" + f).read().strip().splitlines()[-1]); r = x["roofline"]
     print(f, "pass us %.1f value %.3e frac %.3f e2e ms %.3f" % (x["ms_per_step"] * 1e3, x["value"], r["frac"], x["e2e"]["ms_per_step"]),
