@@ -37,6 +37,10 @@ struct GroupShared {
     int32_t n_work_back;  // general body: units holding other genotypes than 1 / 2, queued from the far end
 };
 
+// words between consecutive entries of one column's list: the CTA's thread count, or less when the
+// panel is narrower than a warp (host and device must agree: the launch sizes the list area by it)
+__host__ __device__ inline int score_list_stride(int T, int bd) { return T > 16 ? bd : (T > 8 ? 16 : 8); }
+
 struct LdgU32 { __device__ __forceinline__ uint32_t operator()(const uint32_t *p) const { return __ldg(p); } };
 struct LdgPos {
     const int32_t *pos;
@@ -56,7 +60,7 @@ struct GroupCtx {
 // (relative position << 1 | genotype==2), the four-maxima DP.  kGen = true: a window of the group
 // holds other genotypes (missing calls, multi-allelic sites): entries (relative position << 8 |
 // genotype byte, fetched from the target matrix) and the per-class DP of dp_core.cuh.
-template <bool kGen>
+template <bool kGen, bool kNarrow = false>
 __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c) {
     GroupShared &g = *c.g;
     const int32_t *glo = g.lo + c.io, *ghi = g.hi + c.io, *gnabs = g.nabs + c.io;
@@ -64,6 +68,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
     uint32_t *s_list = c.s_list;
     uint32_t *s_work = c.s_pos;  // [wg * bd] unit worklist, once the lists are built
     const int tid = c.tid, bd = c.bd, chunk = c.chunk, t = c.t, w0 = c.w0, nwin = c.nwin, L = c.L;
+    const int ls = kNarrow ? score_list_stride(a.T, bd) : bd;  // words between consecutive entries of a column's list
     constexpr int kShift = kGen ? 8 : 1;
     constexpr int kBatch = 8;  // plane words fetched per round trip
 
@@ -77,7 +82,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
         const uint32_t first_mask = 0xffffffffu << (c.rlo & 31);
         const uint32_t last_mask = 0xffffffffu >> (31 - ((c.rhi - 1) & 31));
         const uint32_t pos_addr = (uint32_t)__cvta_generic_to_shared(c.s_pos);
-        const uint32_t step = (uint32_t)bd * 4u;
+        const uint32_t step = (uint32_t)ls * 4u;
         uint32_t w_addr = (uint32_t)__cvta_generic_to_shared(s_list + tid);
         const uint32_t w_end = w_addr + (uint32_t)L * step;  // the spill slot
         const int nwr = c.nwr;
@@ -121,13 +126,13 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
         const int8_t *col = a.tgt + (size_t)(c.gi0 << 5) * a.T + t;
 #pragma unroll 4
         for (int i = 0; i < m; ++i) {
-            const uint32_t row = s_list[i * bd + tid];
+            const uint32_t row = s_list[i * ls + tid];
             const int8_t gb = col[(size_t)row * a.T];
-            s_list[i * bd + tid] = (c.s_pos[row] << 8) | (uint32_t)(uint8_t)gb;
+            s_list[i * ls + tid] = (c.s_pos[row] << 8) | (uint32_t)(uint8_t)gb;
         }
     }
     const bool overflow = cnt >= L;  // one slot is the terminator
-    if (t < a.T && !overflow) s_list[cnt * bd + tid] = kListSentinel;
+    if (t < a.T && !overflow) s_list[cnt * ls + tid] = kListSentinel;
     if (tid == 0) { g.n_work = 0; g.n_work_back = 0; }
     __syncthreads();  // every list is built: the position tile becomes the worklist
 
@@ -159,7 +164,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
             int64_t score = kNegInf64;
             if (t < a.T && !ex && hi > lo) {
                 if (!overflow) {
-                    list_window_range_shifted<kShift>(s_list + tid, bd, cur_a, cur_b, gplo[i], gphi[i], true);
+                    list_window_range_shifted<kShift>(s_list + tid, ls, cur_a, cur_b, gplo[i], gphi[i], true);
                     n = cur_b - cur_a;
                     queued = n > 2;
                 } else if (kGen) {
@@ -173,7 +178,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
             // units whose genotypes all are 1 / 2 (most of them) queue from the front and take the
             // four-maxima DP, the others queue from the far end and take the per-class DP: the
             // warps of pass 2 then run one body at a time.
-            const bool other = kGen && queued && !general_run_is_plain(s_list + tid + cur_a * bd, bd, n);
+            const bool other = kGen && queued && !general_run_is_plain(s_list + tid + cur_a * ls, ls, n);
             const uint32_t qm = __ballot_sync(0xffffffffu, queued && !other);
             const uint32_t om = kGen ? __ballot_sync(0xffffffffu, other) : 0u;
             const uint32_t item = (uint32_t)tid | ((uint32_t)i << 7) | ((uint32_t)cur_a << 11) | ((uint32_t)n << 21);
@@ -202,7 +207,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
         for (int u = tid; u < n_work; u += bd) {
             const uint32_t e = s_work[u];
             const int col = e & 127, i = (e >> 7) & 15, ua = (e >> 11) & 1023, n = e >> 21;
-            const int64_t score = list_dp_run<kShift>(s_list + col + ua * bd, bd, n, a.bonus, c.pen_eff);
+            const int64_t score = list_dp_run<kShift>(s_list + col + ua * ls, ls, n, a.bonus, c.pen_eff);
             a.score[(size_t)(w0 + i) * a.T + chunk * bd + col] = score;
         }
         if (kGen) {
@@ -211,7 +216,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
                 const uint32_t e = s_work[nwin * bd - 1 - u];
                 const int col = e & 127, i = (e >> 7) & 15, ua = (e >> 11) & 1023, n = e >> 21;
                 int64_t score;
-                if (!list_dp_run_general(s_list + col + ua * bd, bd, n, a.bonus, a.penalty, a.max_mm, score)) {
+                if (!list_dp_run_general(s_list + col + ua * ls, ls, n, a.bonus, a.penalty, a.max_mm, score)) {
                     bail_window(w0 + i);
                     continue;
                 }
@@ -236,11 +241,11 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
                                       a.max_mm, n, score);
             } else {
                 int b = cur;
-                list_window_range_shifted<kShift>(s_list + tid, bd, cur, b, gplo[i], gphi[i], false);
+                list_window_range_shifted<kShift>(s_list + tid, ls, cur, b, gplo[i], gphi[i], false);
                 n = b - cur;
                 if (n > 2) {
-                    if (!kGen) score = list_dp_run(s_list + tid + cur * bd, bd, n, a.bonus, c.pen_eff);
-                    else if (!list_dp_run_general(s_list + tid + cur * bd, bd, n, a.bonus, a.penalty, a.max_mm, score)) {
+                    if (!kGen) score = list_dp_run(s_list + tid + cur * ls, ls, n, a.bonus, c.pen_eff);
+                    else if (!list_dp_run_general(s_list + tid + cur * ls, ls, n, a.bonus, a.penalty, a.max_mm, score)) {
                         bail_window(w);
                         continue;
                     }
@@ -255,11 +260,14 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
 
 // the general instantiation lives out of line: it is rare, and its per-class tables must not
 // cost the common kernel body registers or stack
-__device__ __noinline__ void group_body_general(const ScoreArgs &a, const GroupCtx &c) { group_body<true>(a, c); }
+template <bool kNarrow>
+__device__ __noinline__ void group_body_general(const ScoreArgs &a, const GroupCtx &c) { group_body<true, kNarrow>(a, c); }
 
 // grid.x = tchunks * ngroups; dynamic smem: list [L + 1][bd] | max(positions [words_cap*32], worklist [wg*bd])
-__global__ void __launch_bounds__(kScoreMaxThreads)
-score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words_cap) {
+// kNarrow (panels of at most 16 columns) lives in a kernel of its own: there the lists of a column
+// sit 8 or 16 words apart instead of blockDim.x, which the common kernel must not pay registers for.
+template <bool kNarrow>
+__device__ __forceinline__ void score_group_body(const ScoreArgs &a, int wg, int L, int words_cap) {
     extern __shared__ __align__(16) uint8_t dyn[];
     __shared__ GroupShared g;
     pdl_launch_dependents();
@@ -271,7 +279,10 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
     // the position tile is only read while the lists are built, the unit worklist only after:
     // they share one region (a barrier separates the two phases)
     uint32_t *s_list = reinterpret_cast<uint32_t *>(dyn);
-    uint32_t *s_pos = s_list + (size_t)(L + 1) * bd;  // row L of the list area is the spill slot
+    // narrow panels keep their lists 8 or 16 words apart instead of a whole warp's 32 (less shared
+    // memory per CTA: replicate batches of a dozen columns then keep three times the CTAs resident)
+    const int ls = kNarrow ? score_list_stride(a.T, bd) : bd;
+    uint32_t *s_pos = s_list + (size_t)(L + 1) * ls;  // row L of the list area is the spill slot
 
     pdl_wait();  // bit-planes and window bounds come from the prep launch
     if (tid < nwin) {
@@ -415,12 +426,22 @@ score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words
             c.g = &g; c.s_list = s_list; c.s_pos = s_pos;
             c.tid = tid; c.bd = bd; c.chunk = chunk; c.t = t; c.w0 = w0 + s0; c.nwin = nsub; c.L = L; c.io = s0;
             c.rlo = rlo; c.rhi = rhi; c.gi0 = gi0; c.nwr = nwr; c.pen_eff = pen_eff; c.mono_hi = mono_hi;
-            if (any_ex && span < (int64_t(1) << kGeneralPosBits)) group_body_general(a, c);
-            else group_body<false>(a, c);
+            if (any_ex && span < (int64_t(1) << kGeneralPosBits)) group_body_general<kNarrow>(a, c);
+            else group_body<false, kNarrow>(a, c);
         }
         s0 = s1;
         if (s0 < nwin) __syncthreads();  // the lists / worklist are reused by the next sub-group
     }
+}
+
+__global__ void __launch_bounds__(kScoreMaxThreads)
+score_group_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words_cap) {
+    score_group_body<false>(a, wg, L, words_cap);
+}
+
+__global__ void __launch_bounds__(32)
+score_group_narrow_kernel(const __grid_constant__ ScoreArgs a, int wg, int L, int words_cap) {
+    score_group_body<true>(a, wg, L, words_cap);
 }
 
 // ------------------------------------------------------------------------------------------

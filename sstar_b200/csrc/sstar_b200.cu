@@ -314,7 +314,9 @@ int launch_score(cudaStream_t st, const ScoreCall &c, const WsLayout &L, int32_t
         if (c.disjoint) wg = 1;  // replicates share no variants (and their positions restart)
         const int64_t ngroups = (W + wg - 1) / wg;
         if (ngroups * tchunks > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "too many (window group, column chunk) tiles%s");
-        int Lslots = kScoreListBytes / (bd * 4) - 1;  // list slots per column (one more row is the spill slot)
+        const int ls = score_list_stride(T, bd);      // words between a column's list entries
+        int Lslots = kScoreListBytes / (ls * 4) - 1;  // list slots per column (one more row is the spill slot)
+        if (Lslots > 1000) Lslots = 1000;             // (the worklist keeps a unit's first entry in 10 bits)
         size_t pos_b = (size_t)words_cap * 32 * 4;    // position tile
         if (wg == 1 && c.max_win_variants > 0) {
             // one window per CTA and its size is known: neither a column's list nor the position
@@ -325,12 +327,14 @@ int launch_score(cudaStream_t st, const ScoreCall &c, const WsLayout &L, int32_t
             pos_b = (size_t)words_cap * 32 * 4;
         }
         const size_t ring_b = (size_t)wg * bd * 4;  // worklist (shares the position tile's region)
-        const size_t smem = (size_t)(Lslots + 1) * bd * 4 + (ring_b > pos_b ? ring_b : pos_b);  // +1: spill slot
-        static thread_local SmemGrant group_grant;
-        cudaError_t e = grant_smem(group_grant, score_group_kernel, smem);
+        const size_t smem = (size_t)(Lslots + 1) * ls * 4 + (ring_b > pos_b ? ring_b : pos_b);  // +1: spill slot
+        static thread_local SmemGrant group_grant, narrow_grant;
+        const bool narrow = ls != bd;
+        cudaError_t e = narrow ? grant_smem(narrow_grant, score_group_narrow_kernel, smem)
+                               : grant_smem(group_grant, score_group_kernel, smem);
         if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaFuncSetAttribute(score_group): %s", cudaGetErrorString(e));
-        e = launch(score_group_kernel, (unsigned)(ngroups * tchunks), (unsigned)bd, smem, st, true, s, wg,
-                               Lslots, words_cap);
+        e = launch(narrow ? score_group_narrow_kernel : score_group_kernel, (unsigned)(ngroups * tchunks), (unsigned)bd, smem,
+                   st, true, s, wg, Lslots, words_cap);
         if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "score_group_kernel launch: %s", cudaGetErrorString(e));
     }
     // list entries per warp kept in shared memory: the largest window when the caller told us (more
