@@ -75,3 +75,24 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "libsstar_oracle" not in src, f
+
+
+def test_hot_kernels_keep_their_register_budget():
+    """Occupancy of the two hot kernels is part of their measured performance: the pack kernel runs
+    five CTAs per SM at 48 registers, the score kernel eight-by-registers at 64 (profiles/README.md).
+    A code change that silently costs registers shows up here, not first in a benchmark."""
+    import re
+    import shutil
+    import subprocess
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    import __graft_entry__ as g
+    g.build()
+    out = subprocess.run([tool, "-res-usage", g.LIB], capture_output=True, text=True).stdout
+    regs = {}
+    for name, r in re.findall(r"Function (\S+):\s*\n\s*REG:(\d+)", out):
+        regs[name] = int(r)
+    find = lambda key: next(v for k, v in regs.items() if key in k)
+    assert find("11prep_kernelE") <= 48
+    assert find("18score_group_kernelE") <= 64
