@@ -171,7 +171,8 @@ __device__ __forceinline__ void transpose4(uint32_t a0, uint32_t a1, uint32_t a2
 // kRowPhase: every row segment was staged keeping its own 16-byte phase (column chunks of a matrix
 // whose row length is not a multiple of 16): row r starts at r * tpitch + ((tgt_phase + r * T) & 15).
 // kChunked = false (whole rows) takes pitch, origin and width from T itself.
-template <bool kAligned, bool kRowPhase = false, bool kChunked = false>
+// kLaneRows: a handful of reference columns (R <= 16, replicate batches): one LANE sums a row.
+template <bool kAligned, bool kRowPhase = false, bool kChunked = false, bool kLaneRows = false>
 __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int32_t g0, int ng, int nrows,
                                           uint32_t ref_phase, uint32_t tgt_phase, int32_t tpitch_ = 0, int32_t c0_ = 0,
                                           int32_t ncols_ = 0) {
@@ -188,6 +189,22 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
     // four rows at a time, eight lanes per row: four independent chains of loads per warp and a
     // three-step shuffle sum instead of one row, one REDUX.
     const uint32_t ralign = (ref_phase | (uint32_t)a.R) & 15u;
+    if (kLaneRows) {
+        const int nwr = (a.R + 3) >> 2;
+        const uint32_t last_mask = (a.R & 3) ? ((1u << (8 * (a.R & 3))) - 1u) : 0xffffffffu;
+        for (int r = tid; r < ng * 32; r += kPackThreads) {
+            int sum = 0;
+            if (r < nrows) {
+                const uint32_t row = ref_phase + (uint32_t)r * (uint32_t)a.R;
+                for (int i = 0; i < nwr; ++i) {
+                    uint32_t w = lds_word<false>(s_ref, row + 4u * i);
+                    if (i == nwr - 1) w &= last_mask;
+                    sum = __dp4a((int)w, 0x01010101, sum);
+                }
+            }
+            s_flag[r] = (r < nrows) && (sum == 0);
+        }
+    } else {
     constexpr int kLpr = 8, kRpw = 32 / kLpr;  // lanes per row (4 and 16 measure the same or worse), rows per warp step
     const int sub = lane / kLpr, l8 = lane % kLpr;
     for (int r4 = warp * kRpw; r4 < ng * 32; r4 += nwarps * kRpw) {
@@ -233,6 +250,7 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
 #pragma unroll
         for (int d = 1; d < kLpr; d <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
         if (l8 == 0) s_flag[r] = (r < nrows) && (sum == 0);
+    }
     }
     __syncthreads();
     for (int gl = warp; gl < ng; gl += nwarps) {
@@ -374,7 +392,7 @@ __device__ __forceinline__ void pack_tile_direct(const PackArgs &a, uint8_t *sme
 // of the target rows per tile (wide panels)
 // (kWide compiles the column-chunk mode in: it lives in a kernel of its own so that the common
 // kernel keeps its 48 registers and five resident CTAs per SM)
-template <bool kWide>
+template <bool kWide, bool kLaneRows = false>
 __device__ __forceinline__ void prep_body(const PackArgs &p, const BoundsArgs &b, int n_pack, int mode, uint8_t *smem,
                                           uint64_t *s_bar) {
     pdl_launch_dependents();  // let the next kernel's CTAs get scheduled while this grid drains
@@ -477,8 +495,8 @@ __device__ __forceinline__ void prep_body(const PackArgs &p, const BoundsArgs &b
             __syncthreads();
         }
         const bool aligned = ((tph | (uint32_t)p.T) & 3u) == 0;
-        if (aligned) pack_tile<true>(p, smem, g0, ng, nrows, rph, tph);
-        else         pack_tile<false>(p, smem, g0, ng, nrows, rph, tph);
+        if (aligned) pack_tile<true, false, false, kLaneRows>(p, smem, g0, ng, nrows, rph, tph);
+        else         pack_tile<false, false, false, kLaneRows>(p, smem, g0, ng, nrows, rph, tph);
         __syncthreads();  // the tile and its flags are done with before the next one lands
     }
 }
@@ -495,6 +513,14 @@ prep_wide_kernel(const __grid_constant__ PackArgs p, const __grid_constant__ Bou
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar[2];
     prep_body<true>(p, b, n_pack, mode, smem, s_bar);
+}
+
+// reference panels of at most 16 columns (whole-row tiles only)
+__global__ void __launch_bounds__(kPackThreads)
+prep_narrow_kernel(const __grid_constant__ PackArgs p, const __grid_constant__ BoundsArgs b, int n_pack, int mode) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    prep_body<false, true>(p, b, n_pack, mode, smem, s_bar);
 }
 
 }  // namespace sstar

@@ -233,12 +233,17 @@ int launch_prep(cudaStream_t st, int64_t g_begin, int64_t g_end, const int8_t *d
     }
     if (n_pack + n_bounds == 0) return 0;
     const int n_fetch = b.n_fetch;
-    static thread_local SmemGrant prep_grant, wide_grant;
-    const bool wide = mode == 2;
-    cudaError_t e = wide ? grant_smem(wide_grant, prep_wide_kernel, smem) : grant_smem(prep_grant, prep_kernel, smem);
+    // three instances of one body: whole-row tiles (the common one: 48 registers), column chunks
+    // for wide panels, and whole-row tiles with one lane per reference row for panels of <= 16
+    // reference columns (replicate batches)
+    static thread_local SmemGrant prep_grant, wide_grant, narrow_grant;
+    auto kernel = prep_kernel;
+    SmemGrant *grant = &prep_grant;
+    if (mode == 2) { kernel = prep_wide_kernel; grant = &wide_grant; }
+    else if (mode == 0 && n_pack > 0 && R <= 16) { kernel = prep_narrow_kernel; grant = &narrow_grant; }
+    cudaError_t e = grant_smem(*grant, kernel, smem);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaFuncSetAttribute(prep): %s", cudaGetErrorString(e));
-    e = launch(wide ? prep_wide_kernel : prep_kernel, (unsigned)(n_fetch + n_pack + n_bounds), kPackThreads, smem, st, false,
-               p, b, n_pack, mode);
+    e = launch(kernel, (unsigned)(n_fetch + n_pack + n_bounds), kPackThreads, smem, st, false, p, b, n_pack, mode);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "prep_kernel launch: %s", cudaGetErrorString(e));
     return 0;
 }
