@@ -362,12 +362,38 @@ def roofline_block(name, st, k, tot_ms, pack_ms, score_ms, launches):
     }
 
 
+def bind_near_gpu(torch, local):
+    """Multi-rank runs: keep this rank's threads (and so the pinned host buffers it first touches) on the
+    NUMA node its GPU hangs off; eight ranks reading host memory in place otherwise cross the
+    socket interconnect at random.  Returns a short description for the JSON line (None = unchanged)."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"numa node {node} ({len(cpus)} cpus)"
+    except Exception:
+        return None
+
+
 def run_ours(args, world, rank, local):
     import torch
     import __graft_entry__ as entry
     if rank == 0:
         entry.build()
     use_dist = world > 1
+    numa = bind_near_gpu(torch, local) if (use_dist and not args.no_numa) else None
     if use_dist:
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -490,6 +516,7 @@ def run_ours(args, world, rank, local):
                        "arithmetic": "int8 genotypes -> bit-planes -> int32 max-plus DP (int64 when a window's score "
                                      "bound exceeds 2^28) -> int64 scores, int32 SNP counts; bit-exact",
                        "per_rank": "every rank scores its own chromosome of this shape",
+                       "rank0_cpu_binding": numa,
                        "l2": "flushed between timed iterations (256 MiB device write)",
                        "timing": "CUDA events on the launching stream around each step, summed over K steps",
                        "launch": "direct launches" if args.no_graph
@@ -529,6 +556,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--at-scale", default="c3-shard", choices=["none"] + sorted(LARGE),
                     help="N=1 only: also time the same kernels on a shape that fills the GPU")
+    ap.add_argument("--no-numa", action="store_true", help="multi-rank runs: do not bind ranks to their GPU's NUMA node")
     ap.add_argument("--only-device", action="store_true", help="profiling aid: run only the device-resident passes")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels directly instead of replaying the CUDA graph")
     args = ap.parse_args()
