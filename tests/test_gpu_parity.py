@@ -392,7 +392,8 @@ def test_rows_too_wide_to_stage(eng):
 
 
 @pytest.mark.parametrize("R,T", [(60, 4000), (16, 2512), (1200, 1600),   # T % 16 == 0: row segments go through TMA
-                                 (60, 4004), (33, 3001), (7, 2406)])       # staged with their own 16-byte phases
+                                 (60, 4004), (33, 3001), (7, 2406),        # staged with their own 16-byte phases
+                                 (2000, 1000)])                            # reference too wide for chunks: whole rows, 96 KB tiles
 def test_wide_panels_take_column_chunks(eng, R, T):
     # 32 rows of R + T bytes exceed a third of an SM's shared memory: the pack stages one column
     # chunk of the target rows per CTA, every chunk redoing the row sums
