@@ -1,18 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- S* (window x individual) scores/sec on B200, with the CPU path beside it.
+"""bench.py -- S* (window x individual) scores/sec on B200, with the reference's CPU path beside it.
 
     python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's own CPU code
 
-Workload (BASELINE.json configs[1], "C2"): one synthetic 10 Mb msprime-style chromosome,
-100 reference + 50 target diploids, unphased dosages, 50 kb windows / 10 kb step.  One "step" is one
-pass of the hot path over that chromosome: pack -> window bounds -> chain DP for every
-(window, target column) unit.  With N > 1 (torchrun, one rank per GPU) every rank scores its own
-chromosome of the same shape (different seed): weak scaling, no collective on the data path.
+Workload (BASELINE.json configs[1], "C2"): a synthetic msprime-style chromosome of N x 10 Mb (N = the
+number of GPUs; N = 1 is exactly configs[1]), 100 reference + 50 target diploids, unphased dosages,
+50 kb windows / 10 kb step.  One "step" is one pass of the hot path over the chromosome: pack ->
+window bounds -> chain DP for every (window, target column) unit.
 
-value  : units/s with inputs resident in HBM (CUDA events around each step, max over ranks).
-e2e    : units/s through ScoreEngine.score_pinned (one C-ABI call: H2D of the int8 matrices from
-         pinned host memory, kernels, D2H of both result tables), wall clock, max over ranks.
+With N > 1 (torchrun, one rank per GPU) the chromosome goes through the product's partition
+(``sstar_b200.sharding``): ``plan_window_shards`` cuts contiguous window ranges, every rank owns
+the variant rows its range touches (own step range + the ``win_len - win_step`` halo) in its own
+page-locked allocation, scores them on its GPU, and stores its ``[W_g, T]`` block into ONE result
+table in shared page-locked host memory (``SharedHostTable``) -- the reference's gather + sort
+(sstar/mp_manager.py:172-179, sstar/preprocess.py:117).  No collective on the data path: NCCL only
+carries the barriers and the max / sum of the timings.  Rank 0 then checks the gathered table against
+the oracle, bit for bit, on every window (C2 sizes) -- in particular those straddling the shard cuts.
+
+value  : units/s with every rank's rows resident in HBM (CUDA events around each step, max over ranks).
+e2e    : units/s through ScoreEngine.score_pinned (one C-ABI call per rank: its rows from pinned host
+         memory, kernels, its block of the shared host table written), wall clock, max over ranks.
+strong : the same partition at FIXED total work -- BASELINE configs[2] (one 250 Mb chromosome,
+         R = T = 1000 haplotype columns, 24.3 M units) and configs[4] (10,000 replicates of 50 kb)
+         over the N ranks, device-resident and end to end, oracle-checked in the run.
 """
 from __future__ import annotations
 
@@ -32,9 +43,10 @@ sys.path.insert(0, ROOT)
 METRIC = "S* (window x individual) scores/sec"
 UNIT = "scores/s"
 PARAMS = (5000, 5, -10000)
+SEG_LEN = 10_000_000
 WORKLOADS = {
-    # name: (length bp, n_ref, n_tgt, phased, win_len, win_step, description)
-    "c2": (10_000_000, 100, 50, False, 50_000, 10_000,
+    # name: (length bp per GPU, n_ref, n_tgt, phased, win_len, win_step, description)
+    "c2": (SEG_LEN, 100, 50, False, 50_000, 10_000,
            "C2: synthetic 10 Mb msprime-style chromosome, 100 ref + 50 target diploids (unphased), "
            "50 kb windows / 10 kb step"),
     "c2-small": (1_000_000, 100, 50, False, 50_000, 10_000, "C2 shape at 1 Mb (debug)"),
@@ -50,23 +62,43 @@ WORKLOADS = {
     "wide8k": (30_000_000, 50, 4000, True, 50_000, 10_000, "30 Mb, 50 ref + 4000 target diploids, haplotype mode (T = 8000)"),
 }
 LARGE = {"c3-shard", "c4-shard", "wide5k", "wide8k"}
+C3 = dict(length=250_000_000, n_ref=500, n_tgt=500, seed=12347,
+          desc="C3 (BASELINE configs[2]): one synthetic 250 Mb chromosome, 500 ref + 500 target diploids, haplotype "
+               "mode (R = T = 1000 columns), 50 kb / 10 kb, sharded by window range over the ranks")
+C5 = dict(n_rep=10_000, seq_len=50_000, n_ref=5, n_tgt=10, seed=5,
+          desc="C5 (BASELINE configs[4]): 10,000 synthetic 50 kb replicates, 5 ref + 10 target diploids (unphased, "
+               "the tutorial's shape), one window [1, 50000] each, contiguous replicate ranges over the ranks")
 
 
-def make_workload(name, rank):
+# ------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------
+def make_workload(name, world=1):
+    """The FULL chromosome of a run on ``world`` ranks (every rank builds it from the same seeds):
+    ``world`` independent segments of the named shape laid end to end.  world = 1 is the shape itself."""
     from sstar_b200.synth import regular_windows, synth_chromosome, synth_chromosome_device
     length, n_ref, n_tgt, phased, wl, wstep, desc = WORKLOADS[name]
-    seed = 12345 + 1 + 1000 * rank
+    seeds = [12345 + 1 + 1000 * r for r in range(world)]
     if name in LARGE:
         import torch
+        if world != 1:
+            raise SystemExit(f"workload {name} is a single-GPU shape (use the default workload with --gpus N)")
         dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-        r, t, p = synth_chromosome_device(torch, dev, length, n_ref, n_tgt, phased, seed)
+        r, t, p = synth_chromosome_device(torch, dev, length, n_ref, n_tgt, phased, seeds[0])
         ref, tgt, pos = r.cpu().numpy(), t.cpu().numpy(), p.cpu().numpy()
         del r, t, p
         torch.cuda.empty_cache()
     else:
-        ref, tgt, pos = synth_chromosome(length, n_ref, n_tgt, phased, seed)
+        segs = [synth_chromosome(length, n_ref, n_tgt, phased, s) for s in seeds]
+        ref = np.concatenate([s[0] for s in segs])
+        tgt = np.concatenate([s[1] for s in segs])
+        pos = np.concatenate([s[2].astype(np.int64) + i * length for i, s in enumerate(segs)]).astype(np.int32)
     ws, we = regular_windows(pos, wl, wstep)
-    return dict(ref=ref, tgt=tgt, pos=pos, ws=ws, we=we, seed=seed, desc=desc, name=name)
+    if world > 1:
+        desc = f"{world} x 10 Mb = one {world * length // 1_000_000} Mb chromosome of the C2 shape ({desc}), sharded by " \
+               f"window range over {world} GPUs"
+    return dict(ref=ref, tgt=tgt, pos=pos, ws=ws, we=we, seed=seeds[0], seeds=seeds, desc=desc, name=name,
+                phased=phased, length=length * world)
 
 
 def workload_stats(wk):
@@ -89,6 +121,17 @@ def workload_stats(wk):
                 mean_window_variants=float((hi - lo).mean()), max_window_variants=int((hi - lo).max()))
 
 
+def shared_config(wk, st, world):
+    """The ``config`` object -- the SAME dict in both arms (ours / --impl reference)."""
+    return {"workload": wk["desc"], **st, "seed": wk["seed"], "params": list(PARAMS), "n_gpus": world,
+            "partition": "one rank: the whole chromosome" if world == 1 else
+                         f"sstar_b200.sharding.plan_window_shards: {world} contiguous window ranges, each rank holds its "
+                         "rows + the win_len - win_step halo; result blocks gathered in one shared host table",
+            "l2": "GPU arm: flushed between timed iterations (256 MiB device write); CPU arm: not applicable",
+            "timing": "GPU arm: CUDA events on the launching stream around each step (value), wall clock around the "
+                      "host-buffer call incl. the stream sync (e2e), max over ranks; CPU arm: wall clock"}
+
+
 def algorithmic_bytes(st):
     """every int8 genotype read once + pos + 12 B per unit written."""
     pack = st["V"] * (st["R"] + st["T"])
@@ -107,7 +150,8 @@ def measured_peak():
 
 def recorded_traffic(workload, kernel, key="dram_bytes"):
     """Per-launch counters from the committed ncu --set full capture (profiles/traffic.json), if any:
-    ``dram_bytes`` = dram__bytes_read.sum + dram__bytes_write.sum, ``warp_inst`` = smsp__inst_executed.sum."""
+    ``dram_bytes`` = dram__bytes_read.sum + dram__bytes_write.sum, ``warp_inst`` = smsp__inst_executed.sum.
+    (ncu cannot run inside the timed program; the file names the capture each number comes from.)"""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             rec = json.load(fh).get(workload, {}).get(kernel)
@@ -188,25 +232,56 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(v for k, v in self.REASONS.items() if bits & k), "samples": len(sel)}
 
 
-def dist_setup(n_gpus):
+def dist_setup():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     return world, rank, local
 
 
+# ------------------------------------------------------------------------------------------
+# the reference arm: the reference's own CPU code on the box's host cores
+# ------------------------------------------------------------------------------------------
+def cpu_arm(wk, st, cores, passes_cap=10, check=None):
+    """Times the reference's job (``FeatureVectorPreprocessor.run`` -> ``Sstar.compute`` from
+    baseline/_ref when installed, else the oracle's numpy port) over a pre-forked pool of ``cores``
+    workers on a bounded, evenly spread window sample.  -> (units/s, description dict)."""
+    from oracle.cpu_baseline import CpuBaseline
+    W, T = st["W"], st["T"]
+    base = CpuBaseline(wk["ref"], wk["tgt"], wk["pos"], wk["ws"], wk["we"], PARAMS, cores, phased=wk["phased"])
+    per_win = base.per_window_seconds()
+    n_win = int(min(W, max(cores, 20.0 / max(per_win, 1e-6))))  # ~20 core-seconds per pass at most
+    sample = np.linspace(0, W - 1, num=n_win).astype(int)
+    base.run(sample[: max(cores, n_win // 8)])
+    passes = int(min(passes_cap, max(1, round(12.0 / max(per_win * n_win, 1e-6)))))  # ~12 core-seconds of work
+    dts, res = [], {}
+    for _ in range(passes):
+        dt, res = base.run(sample)
+        dts.append(dt)
+    base.close()
+    if check is not None:
+        check(res)
+    dt = statistics.mean(dts)
+    info = {"value": n_win * T / dt, "unit": UNIT, "cores": cores, "kind": base.kind,
+            "sample": f"{n_win} of {W} windows x {T} columns of the {wk['name']} chromosome, mean of {passes} passes "
+                      f"({dt:.2f} s wall each); {base.source}; one task per window as mp_manager does, but the pool is "
+                      "pre-forked and warm (no Manager-proxy pickling, no 5 s worker-exit tail)",
+            "in_process_us_per_unit": 1e6 * per_win / T, "seconds_per_pass": dt, "passes": passes}
+    return info
+
+
 def run_reference(args, world, rank):
-    """The reference's CPU path (numpy port of its recipe) on all host cores, rank 0 only."""
+    """The reference arm: rank 0 alone runs and prints; the other ranks exit without work."""
     if rank != 0:
         return
-    from oracle.cpu_baseline import CpuBaseline
-    wk = make_workload(args.workload, 0)
+    wk = make_workload(args.workload, world)
     st = workload_stats(wk)
     cores = os.cpu_count() or 1
-    base = CpuBaseline(wk["ref"], wk["tgt"], wk["pos"], wk["ws"], wk["we"], PARAMS, cores)
+    from oracle.cpu_baseline import CpuBaseline
+    base = CpuBaseline(wk["ref"], wk["tgt"], wk["pos"], wk["ws"], wk["we"], PARAMS, cores, phased=wk["phased"])
     per_win = base.per_window_seconds()
-    # bounded sample: ~20 s of CPU work per step, at most the whole chromosome
-    work = min(20.0, 60.0 * cores / max(args.steps + args.warmup, 1))  # keep the whole run near a minute
+    # bounded sample: ~20 s of CPU work per step at most, the whole run near a minute
+    work = min(20.0, 60.0 * cores / max(args.steps + args.warmup, 1))
     n_win = int(min(st["W"], max(cores, work / max(per_win, 1e-6))))
     sample = np.linspace(0, st["W"] - 1, num=n_win).astype(int)
     for _ in range(args.warmup):
@@ -224,31 +299,39 @@ def run_reference(args, world, rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(secs),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": wk["desc"], **{k: st[k] for k in ("V", "R", "T", "W", "units")},
-                   "seed": wk["seed"], "params": list(PARAMS)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": sample_desc + "; pool pre-forked and warm, no mp_manager 5 s tail"},
+        "config": shared_config(wk, st, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": base.kind,
+                         "sample": sample_desc + f"; {base.source}; pool pre-forked and warm, no mp_manager 5 s tail"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-class DeviceCase:
-    """One workload resident on one GPU: the captured pass and the timing helpers."""
+# ------------------------------------------------------------------------------------------
+# one rank's shard on its GPU
+# ------------------------------------------------------------------------------------------
+class ShardCase:
+    """The rows / windows one rank owns: page-locked host copies (its own allocation), device copies,
+    the captured pass and the timing helpers.  ``out_p`` are this rank's blocks of the host table."""
 
-    def __init__(self, torch, eng, dev, wk, use_graph=True):
-        self.torch, self.eng, self.dev, self.wk = torch, eng, dev, wk
-        self.st = st = workload_stats(wk)
-        self.hint = st["max_window_variants"]
-        W, T = st["W"], st["T"]
-        self.pin = {k: torch.from_numpy(np.ascontiguousarray(wk[k])).pin_memory()
+    def __init__(self, torch, eng, dev, arrays, out_p=None, use_graph=True):
+        self.torch, self.eng, self.dev = torch, eng, dev
+        pos, ws, we = arrays["pos"], arrays["ws"], arrays["we"]
+        lo = np.searchsorted(pos, ws.astype(np.int64), side="left")
+        hi = np.searchsorted(pos, we.astype(np.int64), side="right")
+        self.hint = int(max(0, (hi - lo).max())) if len(ws) else 0
+        self.V, self.R, self.T, self.W = len(pos), arrays["ref"].shape[1], arrays["tgt"].shape[1], len(ws)
+        W, T = self.W, self.T
+        self.pin = {k: torch.from_numpy(np.ascontiguousarray(arrays[k])).pin_memory()
                     for k in ("ref", "tgt", "pos", "ws", "we")}
         self.d = {k: v.to(dev) for k, v in self.pin.items()}
         self.score_d = torch.empty((W, T), dtype=torch.int64, device=dev)
         self.nsnp_d = torch.empty((W, T), dtype=torch.int32, device=dev)
-        self.score_p = torch.empty((W, T), dtype=torch.int64).pin_memory()
-        self.nsnp_p = torch.empty((W, T), dtype=torch.int32).pin_memory()
+        if out_p is None:
+            out_p = (torch.empty((W, T), dtype=torch.int64).pin_memory(),
+                     torch.empty((W, T), dtype=torch.int32).pin_memory())
+        self.score_p, self.nsnp_p = out_p
         # the whole pass (pack -> bounds -> DP) captured once: ONE host call per step
         self.plan = None
         if use_graph:
@@ -266,11 +349,11 @@ class DeviceCase:
         return self.eng.launches
 
     def step_pack(self):
-        self.eng.pack_device(self.d["ref"], self.d["tgt"], W=self.st["W"], max_win_variants=self.hint)
+        self.eng.pack_device(self.d["ref"], self.d["tgt"], W=self.W, max_win_variants=self.hint)
 
     def step_score(self):
         d = self.d
-        self.eng.score_packed_device(self.st["R"], d["tgt"], d["pos"], d["ws"], d["we"], *PARAMS,
+        self.eng.score_packed_device(self.R, d["tgt"], d["pos"], d["ws"], d["we"], *PARAMS,
                                      max_win_variants=self.hint, out=(self.score_d, self.nsnp_d))
 
     def step_e2e(self, staged=False):
@@ -302,18 +385,30 @@ class DeviceCase:
             tot += time.perf_counter() - t0
         return tot
 
-    def check_parity(self, large):
-        """GPU vs the C oracle, bit-exact (all windows, or 48 spread ones for the large shapes)."""
-        from oracle import c_oracle
-        wk, W = self.wk, self.st["W"]
-        sel = np.arange(W) if not large else np.unique(np.linspace(0, W - 1, 48).astype(int))
-        so, no = c_oracle.score_windows(wk["ref"], wk["tgt"], wk["pos"], wk["ws"][sel], wk["we"][sel], *PARAMS)
-        ok = bool(np.array_equal(self.score_p.numpy()[sel], so) and np.array_equal(self.nsnp_p.numpy()[sel], no)
-                  and np.array_equal(self.score_d.cpu().numpy()[sel], so)
-                  and np.array_equal(self.nsnp_d.cpu().numpy()[sel], no))
-        if not ok:
-            raise SystemExit("bench: GPU result differs from the oracle -- refusing to report a number")
-        return {"checked_units": int(so.size), "bit_exact_vs_oracle": ok}
+    def device_equals_host_block(self):
+        """The device-resident tables of the last ``step_device`` == this rank's block of the host
+        table written by the last ``step_e2e`` (bit for bit)."""
+        return bool(self.torch.equal(self.score_d.cpu(), self.score_p) and
+                    self.torch.equal(self.nsnp_d.cpu(), self.nsnp_p))
+
+
+def oracle_check(wk, score, nsnp, sel, what):
+    """Rows ``sel`` of the gathered host table vs the scalar C oracle, bit-exact, or refuse to report."""
+    from oracle import c_oracle
+    sel = np.asarray(sel, dtype=np.int64)
+    so, no = c_oracle.score_windows(wk["ref"], wk["tgt"], wk["pos"], wk["ws"][sel], wk["we"][sel], *PARAMS)
+    ok = bool(np.array_equal(score[sel], so) and np.array_equal(nsnp[sel], no))
+    if not ok:
+        raise SystemExit(f"bench: GPU result differs from the oracle ({what}) -- refusing to report a number")
+    return int(so.size)
+
+
+def cut_windows(shards, W, radius=6):
+    """Windows within ``radius`` of every shard cut (their variants straddle two ranks' row ranges)."""
+    sel = set()
+    for (w0, _w1, _k0, _k1) in shards[1:]:
+        sel.update(range(max(0, w0 - radius), min(W, w0 + radius)))
+    return sorted(sel)
 
 
 def roofline_block(name, st, k, tot_ms, pack_ms, score_ms, launches):
@@ -330,7 +425,8 @@ def roofline_block(name, st, k, tot_ms, pack_ms, score_ms, launches):
             ipeak, sms, mhz = issue_peak_ginst()
             out["issue"] = {"warp_inst": winst, "achieved": winst / (ms / k * 1e-3) / 1e9, "peak": ipeak,
                             "unit": "G warp-inst/s", "frac": winst / (ms / k * 1e-3) / 1e9 / ipeak,
-                            "peak_source": f"{sms} SMs x 4 schedulers x {mhz:.0f} MHz"}
+                            "peak_source": f"{sms} SMs x 4 schedulers x {mhz:.0f} MHz",
+                            "warp_inst_source": "profiles/traffic.json (ncu --set full capture of this workload)"}
         if kname == "score_group_kernel":
             # integer operations of the REFERENCE formulation -- 8 per pair
             # evaluation of the O(n^2) recurrence plus one mask test per window variant and unit --
@@ -349,16 +445,19 @@ def roofline_block(name, st, k, tot_ms, pack_ms, score_ms, launches):
     pipe = ab["pipeline"] / (tot_ms / k * 1e-3) / 1e9
     return {
         "bound": "hbm",
-        "kernel": "one pass = prep_kernel (pack + window bounds) -> score_group_kernel -> score_pairwise_kernel",
+        "kernel": "one pass = prep_kernel (pack + window bounds) -> score_group_kernel (-> score_pairwise_kernel only "
+                  "when a window was routed to it)",
         "achieved": pipe, "peak": peak, "unit": "GB/s", "frac": pipe / peak,
         "traffic": sum(filter(None, (recorded_traffic(name, x) for x in ("prep_kernel", "score_group_kernel")))) or None,
+        "traffic_source": "profiles/traffic.json (per-launch dram bytes of one ncu --set full capture; null when the "
+                          "workload has no capture)",
         "peak_source": peak_src, "algorithmic_bytes": ab["pipeline"],
         "bytes_per_unit": ab["pipeline"] / st["units"], "pass_ms": tot_ms / k, "launches_per_pass": launches,
         "kernels": [
             kern("prep_kernel", pack_ms, ab["pack"], "HBM bound: every int8 genotype read once; timed alone"),
             kern("score_group_kernel", score_ms, ab["score"],
                  "integer-ALU / latency bound, not HBM bound (its bytes are pos + the two result tables); "
-                 "timed alone together with the chained pairwise launch")],
+                 "timed alone")],
     }
 
 
@@ -387,43 +486,267 @@ def bind_near_gpu(torch, local):
         return None
 
 
+class Ranks:
+    """The plumbing a multi-rank run needs (barrier, max / min / sum over ranks, broadcast of a small
+    object); trivial on one rank.  NCCL carries nothing else."""
+
+    def __init__(self, torch, dev, world, rank, dist):
+        self.torch, self.dev, self.world, self.rank, self.dist = torch, dev, world, rank, dist
+
+    def barrier(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize(self.dev)
+
+    def reduce(self, values, op="max"):
+        t = self.torch.tensor([float(v) for v in values], dtype=self.torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op={"max": self.dist.ReduceOp.MAX, "min": self.dist.ReduceOp.MIN,
+                                        "sum": self.dist.ReduceOp.SUM}[op])
+        return [float(x) for x in t.tolist()]
+
+    def bcast(self, obj):
+        if self.dist is None:
+            return obj
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def gather(self, obj):
+        if self.dist is None:
+            return [obj]
+        box = [None] * self.world
+        self.dist.all_gather_object(box, obj)
+        return box
+
+    def shared_table(self, W, T):
+        from sstar_b200.sharding import SharedHostTable
+        for kind in ("memfd", "shm"):
+            table = SharedHostTable(W, T, kind=kind) if self.rank == 0 else None
+            handle = self.bcast(table.handle if table is not None else None)
+            ok = 1.0
+            if table is None:
+                try:
+                    table = SharedHostTable(W, T, handle=handle)
+                except OSError:
+                    ok = 0.0
+            if self.reduce([ok], "min")[0] == 1.0:
+                break
+            if table is not None:
+                table.close()
+        else:
+            raise SystemExit("bench: the ranks cannot share a host table")
+        views = table.register(self.torch)
+        self.barrier()
+        return table, views
+
+
+# ------------------------------------------------------------------------------------------
+# strong scaling blocks: fixed total work over the N ranks
+# ------------------------------------------------------------------------------------------
+def strong_c3(torch, eng, dev, rk, flush, length, steps, e2e_steps, use_graph):
+    """BASELINE configs[2]: the whole 250 Mb chromosome over the ranks, by window range."""
+    from sstar_b200.sharding import plan_window_shards
+    from sstar_b200.synth import regular_windows, synth_chromosome_device
+    t0 = time.perf_counter()
+    # every rank generates the same chromosome on its own GPU (same seed, same device code), keeps
+    # its own rows; rank 0 also keeps a host copy for the oracle
+    r, t, p = synth_chromosome_device(torch, dev, length, C3["n_ref"], C3["n_tgt"], True, seed=C3["seed"])
+    pos = p.cpu().numpy()
+    ws, we = regular_windows(pos, 50_000, 10_000)
+    W, T, R, V = len(ws), int(t.shape[1]), int(r.shape[1]), len(pos)
+    shards = plan_window_shards(pos, ws, we, rk.world)
+    if len(shards) != rk.world:
+        raise SystemExit("bench: fewer window shards than ranks")
+    w0, w1, k0, k1 = shards[rk.rank]
+    arrays = dict(ref=r[k0:k1].cpu().numpy(), tgt=t[k0:k1].cpu().numpy(), pos=pos[k0:k1], ws=ws[w0:w1], we=we[w0:w1])
+    full = dict(ref=r.cpu().numpy(), tgt=t.cpu().numpy(), pos=pos, ws=ws, we=we) if rk.rank == 0 else None
+    del r, t, p
+    torch.cuda.empty_cache()
+    # the ranks must hold slices of ONE chromosome: their checksums against rank 0's copy
+    sums = rk.gather((k0, k1, int(arrays["ref"].sum(dtype=np.int64)), int(arrays["tgt"].sum(dtype=np.int64)),
+                      int(arrays["pos"].sum(dtype=np.int64))))
+    if rk.rank == 0:
+        for (a, b, sr, stg, sp) in sums:
+            if (int(full["ref"][a:b].sum(dtype=np.int64)), int(full["tgt"][a:b].sum(dtype=np.int64)),
+                    int(full["pos"][a:b].sum(dtype=np.int64))) != (sr, stg, sp):
+                raise SystemExit("bench: the ranks generated different chromosomes")
+    table, (tab_score, tab_nsnp) = rk.shared_table(W, T)
+    case = ShardCase(torch, eng, dev, arrays, out_p=(tab_score[w0:w1], tab_nsnp[w0:w1]), use_graph=use_graph)
+    gen_s = time.perf_counter() - t0
+    for _ in range(2):
+        flush.fill_(1)
+        case.step_device()
+        case.step_e2e()
+    dev_ms = case.timed(case.step_device, steps, flush, rk.barrier)
+    rk.barrier()
+    if rk.rank == 0:
+        table.score[:] = 0  # the timed calls below must refill the whole table
+        table.nsnp[:] = -1
+    rk.barrier()
+    e2e_s = case.wall(case.step_e2e, e2e_steps, flush)
+    rk.barrier()
+    same = case.device_equals_host_block()
+    dev_ms, e2e_ms = rk.reduce([dev_ms, e2e_s * 1e3], "max")
+    same = rk.reduce([1.0 if same else 0.0], "min")[0] == 1.0
+    out = None
+    if rk.rank == 0:
+        if not same:
+            raise SystemExit("bench: C3 device-resident tables differ from the gathered host table")
+        sel = sorted(set(cut_windows(shards, W)) | set(np.unique(np.linspace(0, W - 1, 512).astype(int)).tolist()))
+        t1 = time.perf_counter()
+        checked = oracle_check(full, table.score, table.nsnp, sel, "C3 strong block")
+        units = W * T
+        h2d = V * (R + T) + 4 * V + 8 * W
+        out = {"workload": C3["desc"], "V": V, "R": R, "T": T, "W": W, "units": units, "n_gpus": rk.world,
+               "length_bp": length, "shards": [[a, b] for a, b, _, _ in shards],
+               "value": units / (dev_ms / steps * 1e-3), "unit": UNIT, "ms_per_step": dev_ms / steps, "steps": steps,
+               "e2e": {"value": units / (e2e_ms / e2e_steps * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / e2e_steps,
+                       "steps": e2e_steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(12 * units),
+                       "api": "per rank: ScoreEngine.score_pinned on its own page-locked rows -> its block of the "
+                              "shared host table (chunked H2D overlapped with pack + scoring, per-chunk D2H)"},
+               "parity": {"checked_units": checked, "windows": len(sel), "bit_exact_vs_oracle": True,
+                          "device_tables_equal_host_table": True, "oracle_s": time.perf_counter() - t1},
+               "setup_s": gen_s}
+    rk.barrier()
+    del case
+    table.close()
+    return out
+
+
+def strong_c5(torch, eng, dev, rk, flush, steps, e2e_steps):
+    """BASELINE configs[4]: 10,000 replicates of 50 kb in contiguous replicate ranges over the ranks."""
+    from oracle import c_oracle
+    from sstar_b200.sharding import plan_replicate_shards
+    from sstar_b200.synth import synth_chromosome
+    n_rep, L = C5["n_rep"], C5["seq_len"]
+    # one long synthetic chromosome cut into n_rep independent 50 kb "replicates" (positions folded to [1, L])
+    ref, tgt, pos = synth_chromosome(L * n_rep, C5["n_ref"], C5["n_tgt"], False, seed=C5["seed"])
+    rep_id = (pos.astype(np.int64) - 1) // L
+    off = np.searchsorted(rep_id, np.arange(n_rep + 1)).astype(np.int32)
+    pos_local = ((pos.astype(np.int64) - 1) % L + 1).astype(np.int32)
+    T, R = tgt.shape[1], ref.shape[1]
+    shards = plan_replicate_shards(off, rk.world)
+    if len(shards) != rk.world:
+        raise SystemExit("bench: fewer replicate shards than ranks")
+    r0, r1 = shards[rk.rank]
+    a, b = int(off[r0]), int(off[r1])
+    my_off = (off[r0:r1 + 1] - off[r0]).astype(np.int32)
+    hint = int(np.diff(my_off).max())
+    pin = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in (ref[a:b], tgt[a:b], pos_local[a:b], my_off)]
+    d = [x.to(dev) for x in pin]
+    table, (tab_score, tab_nsnp) = rk.shared_table(n_rep, T)
+    out_d = (torch.empty((r1 - r0, T), dtype=torch.int64, device=dev), torch.empty((r1 - r0, T), dtype=torch.int32, device=dev))
+    plan = eng.plan_replicates_device(d[0], d[1], d[2], d[3], 1, L, *PARAMS, max_win_variants=hint, out=out_d)
+
+    def step_e2e():
+        eng.score_replicates_pinned(pin[0], pin[1], pin[2], pin[3], tab_score[r0:r1], tab_nsnp[r0:r1], 1, L, *PARAMS,
+                                    max_win_variants=hint, sync=True)
+
+    for _ in range(3):
+        plan.run()
+        step_e2e()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(steps)]
+    rk.barrier()
+    for i in range(steps):
+        flush.fill_(i & 1)
+        evs[i][0].record()
+        plan.run()
+        evs[i][1].record()
+    rk.barrier()
+    dev_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
+    if rk.rank == 0:
+        table.score[:] = 0
+        table.nsnp[:] = -1
+    rk.barrier()
+    e2e_s = 0.0
+    for i in range(e2e_steps):
+        flush.fill_(i & 1)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        step_e2e()
+        e2e_s += time.perf_counter() - t0
+    rk.barrier()
+    same = bool(torch.equal(out_d[0].cpu(), tab_score[r0:r1]) and torch.equal(out_d[1].cpu(), tab_nsnp[r0:r1]))
+    dev_ms, e2e_ms = rk.reduce([dev_ms, e2e_s * 1e3], "max")
+    same = rk.reduce([1.0 if same else 0.0], "min")[0] == 1.0
+    out = None
+    if rk.rank == 0:
+        if not same:
+            raise SystemExit("bench: C5 device-resident tables differ from the gathered host table")
+        sel = sorted(set(np.unique(np.linspace(0, n_rep - 1, 400).astype(int)).tolist()) |
+                     {r for s in shards for r in (s[0], s[1] - 1)})
+        for r in sel:
+            x, y = off[r], off[r + 1]
+            so, no = c_oracle.score_windows(ref[x:y], tgt[x:y], pos_local[x:y], [1], [L], *PARAMS)
+            if not (np.array_equal(table.score[r], so[0]) and np.array_equal(table.nsnp[r], no[0])):
+                raise SystemExit("bench: GPU result differs from the oracle (C5 strong block) -- refusing to report a number")
+        units = n_rep * T
+        V = len(pos)
+        out = {"workload": C5["desc"], "replicates": n_rep, "V": V, "R": R, "T": T, "units": units, "n_gpus": rk.world,
+               "shards": [list(s) for s in shards],
+               "value": units / (dev_ms / steps * 1e-3), "unit": UNIT, "ms_per_step": dev_ms / steps, "steps": steps,
+               "launches_per_step": plan.launches,
+               "e2e": {"value": units / (e2e_ms / e2e_steps * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / e2e_steps,
+                       "steps": e2e_steps, "h2d_bytes_per_step": int(V * (R + T) + 4 * V + 4 * (n_rep + 1)),
+                       "d2h_bytes_per_step": int(12 * units),
+                       "api": "per rank: ScoreEngine.score_replicates_pinned (H2D of its replicates, "
+                              "sstar_b200_score_replicates, D2H into its block of the shared host table)"},
+               "parity": {"checked_units": len(sel) * T, "replicates": len(sel), "bit_exact_vs_oracle": True,
+                          "device_tables_equal_host_table": True}}
+    rk.barrier()
+    table.close()
+    return out
+
+
+# ------------------------------------------------------------------------------------------
 def run_ours(args, world, rank, local):
     import torch
     import __graft_entry__ as entry
-    if rank == 0:
-        entry.build()
     use_dist = world > 1
     numa = bind_near_gpu(torch, local) if (use_dist and not args.no_numa) else None
     if use_dist:
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if rank == 0:
+            entry.build()
         dist.barrier()
     else:
         dist = None
+        entry.build()
     from sstar_b200.engine import get_engine
+    from sstar_b200.sharding import plan_window_shards
 
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     eng = get_engine(local)
+    rk = Ranks(torch, dev, world, rank, dist)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    case = DeviceCase(torch, eng, dev, make_workload(args.workload, rank), use_graph=not args.no_graph)
-    wk, st = case.wk, case.st
+    wk = make_workload(args.workload, world)
+    st = workload_stats(wk)
     V, R, T, W = st["V"], st["R"], st["T"], st["W"]
     k = args.steps
+    large = wk["name"] in LARGE
 
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if use_dist:
-            dist.barrier()
-            torch.cuda.synchronize(dev)
+    # ---- the partition: this rank's window range and the variant rows it touches (halo included)
+    shards = plan_window_shards(wk["pos"], wk["ws"], wk["we"], world)
+    if len(shards) != world:
+        raise SystemExit("bench: fewer window shards than ranks")
+    w0, w1, k0, k1 = shards[rank]
+    arrays = dict(ref=wk["ref"][k0:k1], tgt=wk["tgt"][k0:k1], pos=wk["pos"][k0:k1], ws=wk["ws"][w0:w1], we=wk["we"][w0:w1])
+    table, (tab_score, tab_nsnp) = rk.shared_table(W, T)
+    case = ShardCase(torch, eng, dev, arrays, out_p=(tab_score[w0:w1], tab_nsnp[w0:w1]), use_graph=not args.no_graph)
+    barrier = rk.barrier
 
     if args.only_device:  # profiling aid: nothing but the device-resident pass is launched
         for i in range(max(args.warmup, 3) + k):
             flush.fill_(i & 1)
             case.step_device()
         torch.cuda.synchronize(dev)
-        print(json.dumps({"only_device": True, "workload": wk["name"], "passes": max(args.warmup, 3) + k}))
+        if rank == 0:
+            print(json.dumps({"only_device": True, "workload": wk["name"], "passes": max(args.warmup, 3) + k}))
         return
 
     for _ in range(max(args.warmup, 3)):
@@ -436,7 +759,7 @@ def run_ours(args, world, rank, local):
 
     sampler = ClockSampler(local)
     sampler.start()
-    # ---- region A: device-resident inputs, the whole pass per step
+    # ---- region A: device-resident rows, the whole pass per step
     sampler.mark()
     tot_ms = case.timed(case.step_device, k, flush, barrier)
     sampler.mark()
@@ -447,6 +770,10 @@ def run_ours(args, world, rank, local):
     barrier()
     staged_s = case.wall(lambda: case.step_e2e(staged=True), k, flush)  # plain H2D / D2H copies, for comparison
     barrier()
+    if rank == 0:
+        table.score[:] = 0  # the timed calls below must refill every rank's block
+        table.nsnp[:] = -1
+    barrier()
     sampler.mark()
     e2e_s = case.wall(case.step_e2e, k, flush)
     barrier()
@@ -454,57 +781,61 @@ def run_ours(args, world, rank, local):
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
-    times = torch.tensor([tot_ms, e2e_s * 1e3, pack_ms, score_ms, staged_s * 1e3], dtype=torch.float64, device=dev)
-    units_t = torch.tensor([float(st["units"])], dtype=torch.float64, device=dev)
-    if use_dist:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        dist.all_reduce(units_t, op=dist.ReduceOp.SUM)
-    tot_ms, e2e_ms, pack_ms, score_ms, staged_ms = (float(x) for x in times.tolist())
-    total_units = float(units_t.item())
+    same = case.device_equals_host_block()
+    tot_ms, e2e_ms, pack_ms, score_ms, staged_ms = rk.reduce([tot_ms, e2e_s * 1e3, pack_ms, score_ms, staged_s * 1e3], "max")
+    same = rk.reduce([1.0 if same else 0.0], "min")[0] == 1.0
+    per_rank = rk.gather({"rank": rank, "windows": [w0, w1], "rows": [k0, k1], "units": (w1 - w0) * T,
+                          "hbm_bytes": (k1 - k0) * (R + T)})
+    total_units = float(W * T)
 
     parity = cpu = at_scale = None
     if rank == 0:
-        # ---- parity in the same run (outside the timed regions): GPU vs C oracle, bit-exact
-        parity = case.check_parity(wk["name"] in LARGE)
-        if world == 1 and not args.no_cpu_baseline and wk["name"] not in LARGE:
-            from oracle.cpu_baseline import CpuBaseline
-            cores = os.cpu_count() or 1
-            base = CpuBaseline(wk["ref"], wk["tgt"], wk["pos"], wk["ws"], wk["we"], PARAMS, cores)
-            per_win = base.per_window_seconds()
-            n_win = int(min(W, max(cores, 20.0 / max(per_win, 1e-6))))
-            sample = np.linspace(0, W - 1, num=n_win).astype(int)
-            base.run(sample[: max(cores, n_win // 8)])
-            passes = int(min(10, max(1, round(12.0 / max(per_win * n_win, 1e-6)))))  # ~12 core-seconds of work
-            dts = []
-            for _ in range(passes):
-                dt, res = base.run(sample)
-                dts.append(dt)
-            base.close()
-            for w, (s_, n_) in res.items():  # the CPU-scored units must equal the GPU's
-                assert np.array_equal(s_, case.score_p.numpy()[w]) and np.array_equal(n_, case.nsnp_p.numpy()[w]), \
-                    "CPU port != GPU"
-            dt = statistics.mean(dts)
-            cpu = {"value": n_win * T / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{n_win} of {W} windows x {T} columns of the {wk['name']} chromosome, mean of {passes} "
-                             f"passes ({dt:.2f} s wall each); numpy port of the reference recipe, pool pre-forked and "
-                             "warm, no mp_manager 5 s tail",
-                   "in_process_us_per_unit": 1e6 * per_win / T}
-        if world == 1 and args.at_scale != "none" and args.at_scale != wk["name"]:
-            # the same kernels on a shape that fills the machine (C2 is a 5.6 MB problem: launch bound)
-            big = DeviceCase(torch, eng, dev, make_workload(args.at_scale, 0), use_graph=not args.no_graph)
-            kb = 20
-            for _ in range(3):
-                flush.fill_(1)
-                nl = big.step_device(); big.step_pack(); big.step_score(); big.step_e2e()
-            b_tot = big.timed(big.step_device, kb, flush, barrier)
-            b_pack = big.timed(big.step_pack, kb, flush, barrier)
-            b_score = big.timed(big.step_score, kb, flush, barrier)
-            b_e2e = big.wall(big.step_e2e, 5, flush)
-            at_scale = {"workload": big.wk["desc"], **{x: big.st[x] for x in ("V", "R", "T", "W", "units")},
-                        "value": big.st["units"] / (b_tot / kb * 1e-3), "unit": UNIT, "ms_per_step": b_tot / kb,
-                        "e2e": {"value": big.st["units"] / (b_e2e / 5), "unit": UNIT, "ms_per_step": 1e3 * b_e2e / 5},
-                        "roofline": roofline_block(big.wk["name"], big.st, kb, b_tot, b_pack, b_score, nl),
-                        "parity": big.check_parity(True)}
+        # ---- parity in the same run (outside the timed regions): the GATHERED host table vs the C
+        # oracle, bit-exact -- every window, or the cut windows + 48 spread ones for the large shapes
+        if not same:
+            raise SystemExit("bench: device-resident tables differ from the gathered host table")
+        cuts = cut_windows(shards, W)
+        sel = np.arange(W) if not large else np.unique(np.linspace(0, W - 1, 48).astype(int))
+        checked = oracle_check(wk, table.score, table.nsnp, sel, "gathered host table")
+        parity = {"checked_units": checked, "bit_exact_vs_oracle": True, "windows_checked": int(len(sel)),
+                  "windows_straddling_shard_cuts": len(cuts), "device_tables_equal_host_table": True}
+        if world == 1 and not args.no_cpu_baseline and not large:
+            def same_as_gpu(res):  # the CPU-scored units must equal the GPU's
+                for w, (s_, n_) in res.items():
+                    assert np.array_equal(s_, table.score[w]) and np.array_equal(n_, table.nsnp[w]), "CPU arm != GPU"
+            cpu = cpu_arm(wk, st, os.cpu_count() or 1, check=same_as_gpu)
+    if world == 1 and args.at_scale != "none" and args.at_scale != wk["name"]:
+        # the same kernels on a shape that fills the machine (C2 is a 5.6 MB problem: launch bound)
+        bwk = make_workload(args.at_scale, 1)
+        bst = workload_stats(bwk)
+        big = ShardCase(torch, eng, dev, bwk, use_graph=not args.no_graph)
+        kb = 20
+        for _ in range(3):
+            flush.fill_(1)
+            nl = big.step_device(); big.step_pack(); big.step_score(); big.step_e2e()
+        b_tot = big.timed(big.step_device, kb, flush, barrier)
+        b_pack = big.timed(big.step_pack, kb, flush, barrier)
+        b_score = big.timed(big.step_score, kb, flush, barrier)
+        b_e2e = big.wall(big.step_e2e, 5, flush)
+        if not big.device_equals_host_block():
+            raise SystemExit("bench: at_scale device-resident tables differ from the host tables")
+        bsel = np.unique(np.linspace(0, bst["W"] - 1, 48).astype(int))
+        at_scale = {"workload": bwk["desc"], **{x: bst[x] for x in ("V", "R", "T", "W", "units")},
+                    "value": bst["units"] / (b_tot / kb * 1e-3), "unit": UNIT, "ms_per_step": b_tot / kb,
+                    "e2e": {"value": bst["units"] / (b_e2e / 5), "unit": UNIT, "ms_per_step": 1e3 * b_e2e / 5},
+                    "roofline": roofline_block(bwk["name"], bst, kb, b_tot, b_pack, b_score, nl),
+                    "parity": {"checked_units": oracle_check(bwk, big.score_p.numpy(), big.nsnp_p.numpy(), bsel, "at_scale"),
+                               "bit_exact_vs_oracle": True}}
+        del big, bwk
+
+    strong = {}
+    if not large and args.strong != "none":
+        del case
+        torch.cuda.empty_cache()
+        if args.strong in ("all", "c3"):
+            strong["c3"] = strong_c3(torch, eng, dev, rk, flush, args.c3_length, 10, 5, not args.no_graph)
+        if args.strong in ("all", "c5"):
+            strong["c5"] = strong_c5(torch, eng, dev, rk, flush, 20, 10)
 
     if rank == 0:
         line = {
@@ -512,24 +843,24 @@ def run_ours(args, world, rank, local):
             "steps": k, "warmup": max(args.warmup, 3), "ms_per_step": tot_ms / k, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic",
-            "config": {"workload": wk["desc"], **st, "seed": wk["seed"], "params": list(PARAMS),
-                       "arithmetic": "int8 genotypes -> bit-planes -> int32 max-plus DP (int64 when a window's score "
-                                     "bound exceeds 2^28) -> int64 scores, int32 SNP counts; bit-exact",
-                       "per_rank": "every rank scores its own chromosome of this shape",
-                       "rank0_cpu_binding": numa,
-                       "l2": "flushed between timed iterations (256 MiB device write)",
-                       "timing": "CUDA events on the launching stream around each step, summed over K steps",
-                       "launch": "direct launches" if args.no_graph
-                                 else "CUDA graph replay of the pass (ScoreEngine.plan_device)"},
+            "config": shared_config(wk, st, world),
+            "notes": {"arithmetic": "int8 genotypes -> bit-planes -> int32 max-plus DP (int64 when a window's score "
+                                    "bound exceeds 2^28) -> int64 scores, int32 SNP counts; bit-exact",
+                      "rank0_cpu_binding": numa,
+                      "launch": "direct launches" if args.no_graph
+                                else "CUDA graph replay of the pass (ScoreEngine.plan_device)",
+                      "collectives_in_timed_region": "none (NCCL: barriers and the max / sum of the timings only)"},
+            "ranks": per_rank,
             "e2e": {"value": total_units / (e2e_ms / k * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(V * (R + T) + 4 * V + 8 * W),
+                    "h2d_bytes_per_step": int(sum(p["hbm_bytes"] + 4 * (p["rows"][1] - p["rows"][0]) +
+                                                  8 * (p["windows"][1] - p["windows"][0]) for p in per_rank)),
                     "d2h_bytes_per_step": int(12 * W * T), "ms_per_step": e2e_ms / k,
-                    "api": "ScoreEngine.score_pinned -> sstar_b200_score_windows_host on pinned host buffers: "
+                    "api": "per rank ScoreEngine.score_pinned -> sstar_b200_score_windows_host on its own pinned rows: "
                            + ("matrices below 32 MB are packed in place over PCIe (the pack CTAs' tile loads are the "
-                              "H2D transfer), " if V * (R + T) < (32 << 20) else
+                              "H2D transfer), " if (k1 - k0) * (R + T) < (32 << 20) else
                               "matrices go H2D in row chunks on a copy stream overlapped with pack + scoring, ")
-                           + "result tables stored in place into host memory (D2H copies from 8 MB); wall clock "
-                             "incl. the stream sync",
+                           + "result blocks stored in place into the shared host table (D2H copies from 8 MB); wall "
+                             "clock incl. the stream sync; the gather is part of it (there is nothing left to do after)",
                     "staged_copies_ms_per_step": staged_ms / k},
             "gpu_launches": int(launches_per_step * k),
             "kernels_per_step": int(launches_per_step),
@@ -538,9 +869,16 @@ def run_ours(args, world, rank, local):
             "clocks": sampler.summary(),
             "parity": parity,
         }
+        if world > 1:
+            line["roofline"]["note"] = "pass-level figures are the aggregate over the ranks (sum of the ranks' bytes over " \
+                                       "the slowest rank's time); peak is one GPU's -- divide by n_gpus for a per-GPU fraction"
+            line["roofline"]["frac_per_gpu"] = line["roofline"]["frac"] / world
         if at_scale:
             line["at_scale"] = at_scale
+        if strong:
+            line["strong"] = strong
         print(json.dumps(line), flush=True)
+    table.close()
     if use_dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -556,11 +894,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--at-scale", default="c3-shard", choices=["none"] + sorted(LARGE),
                     help="N=1 only: also time the same kernels on a shape that fills the GPU")
+    ap.add_argument("--strong", default="all", choices=["all", "c3", "c5", "none"],
+                    help="strong-scaling blocks: whole C3 / C5 over the N ranks")
+    ap.add_argument("--c3-length", type=int, default=C3["length"], help="length of the strong block's chromosome (debug)")
     ap.add_argument("--no-numa", action="store_true", help="multi-rank runs: do not bind ranks to their GPU's NUMA node")
     ap.add_argument("--only-device", action="store_true", help="profiling aid: run only the device-resident passes")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels directly instead of replaying the CUDA graph")
     args = ap.parse_args()
-    world, rank, local = dist_setup(args.gpus)
+    world, rank, local = dist_setup()
     if args.impl == "reference":
         run_reference(args, world, rank)
         return

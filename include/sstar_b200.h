@@ -204,13 +204,19 @@ int sstar_b200_format_table(int device, void *stream, const int64_t *d_score, co
 /* Native VCF scanner (host code, multi-threaded; plain text or gzip).
  * replaces: allel.read_vcf(vcf, alt_number=1, samples=..., region=chr_name) as used by
  *           read_geno_data (sstar/utils/utils.py:80-109) -- scikit-allel is an un-vendored dependency.
- * One pass over the file gives, per chromosome in order of first appearance: POS int32 [V], the REF
- * and first-ALT allele strings, and GT int8 [V, N, 2] (-1 = missing allele) for ALL N samples of the
- * header, in header order.  chr_name NULL keeps every chromosome.  Pointers returned by the
+ * One streaming pass over the file (a block of lines at a time; lines of other chromosomes are
+ * skipped before anything is stored) gives, per chromosome in order of first appearance: POS int32
+ * [V], the REF and first-ALT allele strings, and GT int8 [V, N, 2] (-1 = missing allele) for the N
+ * kept samples in header order.  chr_name NULL keeps every chromosome.
+ * sstar_b200_vcf_scan keeps ALL samples of the header; sstar_b200_vcf_scan_ex keeps only the header
+ * samples named in `samples` (n_samples names; NULL = all) -- what read_vcf(samples=...) does --
+ * and sstar_b200_vcf_sample / _n_samples then describe the kept ones.  Pointers returned by the
  * accessors stay valid until sstar_b200_vcf_free.  Errors: negative code, text from
  * sstar_b200_vcf_last_error(). */
 typedef struct sstar_b200_vcf sstar_b200_vcf;
 int sstar_b200_vcf_scan(const char *path, const char *chr_name, int nthreads, sstar_b200_vcf **out);
+int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, const char *const *samples,
+                           int32_t n_samples, int nthreads, sstar_b200_vcf **out);
 void sstar_b200_vcf_free(sstar_b200_vcf *h);
 const char *sstar_b200_vcf_last_error(void);
 int32_t sstar_b200_vcf_n_samples(const sstar_b200_vcf *h);
@@ -233,13 +239,22 @@ const char *sstar_b200_vcf_alleles(const sstar_b200_vcf *h, int32_t c, int32_t w
  * indices of the two populations.  Outputs (capacity V rows): d_ref_out int8 [V', R],
  * d_tgt_out int8 [V', T], d_pos_out int32 [V'] with R, T = n * 2 (phased) or n (unphased).
  * After the stream syncs the first 16 bytes of d_workspace hold int64 V' and int64 the number of
- * rows both populations shared before the fixed-site filter. */
+ * rows both populations shared before the fixed-site filter.
+ * sstar_b200_ingest_ex additionally takes n_ref_listed / n_tgt_listed = len(ref_samples) /
+ * len(tgt_samples) of the sample lists: the reference's fixed-site filter compares the hom-alt
+ * counts with THOSE (utils.py:282-291), so a list naming a sample the VCF does not hold never drops
+ * a fixed site; sstar_b200_ingest passes the column counts. */
 size_t sstar_b200_ingest_workspace_bytes(int64_t V);
 int sstar_b200_ingest(int device, void *stream, const int8_t *d_gt, const int32_t *d_pos,
                       const int8_t *d_mode, int64_t V, int32_t N, const int32_t *d_ref_cols,
                       int32_t n_ref, const int32_t *d_tgt_cols, int32_t n_tgt, int32_t is_phased,
                       int8_t *d_ref_out, int8_t *d_tgt_out, int32_t *d_pos_out, void *d_workspace,
                       size_t workspace_bytes);
+int sstar_b200_ingest_ex(int device, void *stream, const int8_t *d_gt, const int32_t *d_pos,
+                         const int8_t *d_mode, int64_t V, int32_t N, const int32_t *d_ref_cols,
+                         int32_t n_ref, int32_t n_ref_listed, const int32_t *d_tgt_cols, int32_t n_tgt,
+                         int32_t n_tgt_listed, int32_t is_phased, int8_t *d_ref_out, int8_t *d_tgt_out,
+                         int32_t *d_pos_out, void *d_workspace, size_t workspace_bytes);
 
 /* S* SNP sets: the sites on the best chain of every (window, column) unit -- an extension of the
  * scoring path.  The current reference stops at the score (sstar/sstar.py:205-217 never backtracks);

@@ -63,6 +63,8 @@ SIGNATURES = {
     "sstar_b200_score_packed": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _i32,
                                            _i32, _i32, _i32, _vp, _vp, _vp, _sz, _OPT]),
     "sstar_b200_vcf_scan": (_c.c_int, [_c.c_char_p, _c.c_char_p, _c.c_int, _c.POINTER(_vp)]),
+    "sstar_b200_vcf_scan_ex": (_c.c_int, [_c.c_char_p, _c.c_char_p, _c.POINTER(_c.c_char_p), _i32, _c.c_int,
+                                          _c.POINTER(_vp)]),
     "sstar_b200_vcf_free": (None, [_vp]),
     "sstar_b200_vcf_last_error": (_c.c_char_p, []),
     "sstar_b200_vcf_n_samples": (_i32, [_vp]),
@@ -76,6 +78,8 @@ SIGNATURES = {
     "sstar_b200_ingest_workspace_bytes": (_sz, [_i64]),
     "sstar_b200_ingest": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _vp, _i32, _i32,
                                      _vp, _vp, _vp, _vp, _sz]),
+    "sstar_b200_ingest_ex": (_c.c_int, [_c.c_int, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _i32, _i32,
+                                        _i32, _vp, _vp, _vp, _vp, _sz]),
     "sstar_b200_match_numerators": (_c.c_int, [_c.c_int, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32,
                                                _i32, _vp]),
     "sstar_b200_snp_set_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32]),

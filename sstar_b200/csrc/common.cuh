@@ -14,7 +14,7 @@ constexpr int kScoreWordsCap = 64;  // staged position tile of a window group: 6
 constexpr int kScoreListBytes = 22 << 10;  // shared memory for the per-column site lists of one CTA
 constexpr int kPairWarps = 4;
 constexpr int kPairSmemCap = 1024;  // pairwise list entries per warp kept in shared memory
-constexpr int kNumSM = 148;
+constexpr int kNumSM = 148;  // sizing constant of the device-independent workspace layout only; launches use the device's SM count
 
 constexpr int kMaxSlots = 32;       // independent score launches (window chunks) per call
 

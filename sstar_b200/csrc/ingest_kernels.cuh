@@ -31,6 +31,7 @@ struct IngestArgs {
     const int32_t *ref_cols, *tgt_cols;
     int64_t V;
     int32_t N, n_ref, n_tgt, phased;
+    int32_t ref_listed, tgt_listed;  // len(ref_samples) / len(tgt_samples) of the ind files: what the fixed-site filter compares with
     uint8_t *keep;        // [V]  bit 0: row survives, bit 1: row survives the missing / ancestral filters
     int32_t *block_base;  // [nb] counts, then offsets
     int8_t *ref_out, *tgt_out;
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(kIngestWarps * 32) ingest_flag_kernel(const __
         ingest_pop_counts(row, a.ref_cols, a.n_ref, mode == 1, lane, mr, hr);
         ingest_pop_counts(row, a.tgt_cols, a.n_tgt, mode == 1, lane, mt, ht);
         const bool sh = mode != 2 && mr != a.n_ref && mt != a.n_tgt;
-        const bool kp = sh && !(hr == a.n_ref && ht == a.n_tgt);
+        const bool kp = sh && !(hr == a.ref_listed && ht == a.tgt_listed);  // utils.py:282-291 compares with len(samples)
         if (lane == 0) a.keep[k] = (uint8_t)((kp ? 1 : 0) | (sh ? 2 : 0));
         kept += kp;
         shared += sh;

@@ -13,20 +13,30 @@ namespace sstar {
 // becomes [lo, hi) = [lower_bound(start), lower_bound(end + 1)) on the ascending position array.
 // One warp per window; each round 32 lanes probe 32 pivots, shrinking the range ~33x.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int32_t warp_lower_bound(const int32_t *__restrict__ pos, int32_t lo, int32_t hi,
+// pos / win_start / win_end of a bounds CTA may be the device copies that the fetch CTAs OF THE SAME
+// GRID are writing (in-place host entry): they are read with ordinary coherent loads (ld.relaxed.gpu),
+// never through the non-coherent path (__ldg / const __restrict__), which PTX only allows for data
+// that stays read-only for the whole kernel.  The acquire in flag_wait + the CTA barrier order them.
+__device__ __forceinline__ int32_t ld_coherent(const int32_t *p) {
+    int32_t v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ int32_t warp_lower_bound(const int32_t *pos, int32_t lo, int32_t hi,
                                                     int64_t x, int lane) {
     // invariant: pos[k] < x for k < lo, pos[k] >= x for k >= hi
     while (hi - lo > 32) {
         const int32_t step = (hi - lo + 32) / 33;
         const int32_t idx = lo + step * (lane + 1) - 1;
-        const bool below = idx < hi && (int64_t)__ldg(pos + idx) < x;
+        const bool below = idx < hi && (int64_t)ld_coherent(pos + idx) < x;
         const int c = __popc(__ballot_sync(0xffffffffu, below));  // monotone: the first c lanes
         const int32_t new_hi = lo + step * (c + 1) - 1;  // pivot of lane c, the first one not below x
         if (c > 0) lo = lo + step * c;
         if (c < 32 && new_hi < hi) hi = new_hi;
     }
     const int32_t idx = lo + lane;
-    const bool below = idx < hi && (int64_t)__ldg(pos + idx) < x;
+    const bool below = idx < hi && (int64_t)ld_coherent(pos + idx) < x;
     return lo + __popc(__ballot_sync(0xffffffffu, below));
 }
 
@@ -59,13 +69,13 @@ __device__ __forceinline__ void bounds_block(const BoundsArgs &a, int block, int
     if (w < a.W) {
         const int32_t sb = a.seg ? a.seg[w] : 0;
         const int32_t se = a.seg ? a.seg[w + 1] : a.V;
-        const int64_t s = a.win_start ? a.win_start[w] : a.fixed_start;
-        const int64_t e = a.win_end ? a.win_end[w] : a.fixed_end;
+        const int64_t s = a.win_start ? ld_coherent(a.win_start + w) : a.fixed_start;
+        const int64_t e = a.win_end ? ld_coherent(a.win_end + w) : a.fixed_end;
         const int32_t lo = warp_lower_bound(a.pos, sb, se, s, lane);
         int32_t hi = warp_lower_bound(a.pos, lo, se, e + 1, lane);
         if (hi < lo) hi = lo;
         if (lane < 2 && hi > lo) {  // first / last position, so the score kernel need not chase them
-            const int32_t v = __ldg(a.pos + (lane == 0 ? lo : hi - 1));
+            const int32_t v = ld_coherent(a.pos + (lane == 0 ? lo : hi - 1));
             (lane == 0 ? a.win_pfirst : a.win_plast)[w] = v;
         }
         if (lane == 0) {

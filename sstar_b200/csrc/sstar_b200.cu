@@ -49,6 +49,19 @@ int fail(int code, const char *fmt, const char *detail = "") {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// SMs of the CURRENT device (read once per device; every launch heuristic sizes its grid by it).
+// kNumSM (common.cuh) is only the sizing constant of the device-independent workspace layout.
+int num_sms() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kNumSM;
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n > 0) return n;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSM;
+    cache[dev].store(n, std::memory_order_relaxed);
+    return n;
+}
+
 // cudaFuncSetAttribute is per device: remember, per host thread AND device, the largest dynamic
 // shared-memory size already granted to each kernel (index = current device).
 constexpr int kAttrDevices = 64;
@@ -176,10 +189,11 @@ int launch_prep(cudaStream_t st, int64_t g_begin, int64_t g_end, const int8_t *d
         int gpc_max = (int)((size_t)(64 << 10) / per_group);
         if (gpc_max > 32) gpc_max = 32;  // narrow panels (a few dozen columns): tiles of up to 1,024 variants
         if (gpc_max < 1) gpc_max = 1;
-        const int64_t wave = (int64_t)6 * kNumSM - n_bounds;
+        const int nsm = num_sms();
+        const int64_t wave = (int64_t)6 * nsm - n_bounds;
         int gpc = 1;
-        while (gpc < gpc_max && (ngroups + gpc - 1) / gpc > (wave > kNumSM ? wave : kNumSM)) ++gpc;
-        if ((ngroups + gpc - 1) / gpc > 4 * (int64_t)6 * kNumSM) gpc = gpc_max;  // many waves anyway: biggest tiles
+        while (gpc < gpc_max && (ngroups + gpc - 1) / gpc > (wave > nsm ? wave : nsm)) ++gpc;
+        if ((ngroups + gpc - 1) / gpc > 4 * (int64_t)6 * nsm) gpc = gpc_max;  // many waves anyway: biggest tiles
         p.gpc = gpc;
         p.ref_tile_bytes = (uint32_t)align_up((size_t)gpc * 32 * R + 32, 16);
         p.tgt_tile_bytes = (uint32_t)align_up((size_t)gpc * 32 * T + 32, 16);
@@ -315,7 +329,7 @@ int launch_score(cudaStream_t st, const ScoreCall &c, const WsLayout &L, int32_t
         // tile), but keep at least two full waves of CTAs (7 resident per SM) so the tail stays short.
         int words_cap = kScoreWordsCap;
         int wg = kMaxGroup;
-        while (wg > 1 && (int64_t)((W + wg - 1) / wg) * tchunks < 2 * 7 * kNumSM) wg >>= 1;
+        while (wg > 1 && (int64_t)((W + wg - 1) / wg) * tchunks < 2 * 7 * num_sms()) wg >>= 1;
         if (c.disjoint) wg = 1;  // replicates share no variants (and their positions restart)
         const int64_t ngroups = (W + wg - 1) / wg;
         if (ngroups * tchunks > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "too many (window group, column chunk) tiles%s");
@@ -356,7 +370,7 @@ int launch_score(cudaStream_t st, const ScoreCall &c, const WsLayout &L, int32_t
     if (per_sm > 16) per_sm = 16;
     if (per_sm < 4 || !s.force_slow) per_sm = 4;  // behind the grouped kernel the slow list is short or empty: keep the launch light
     int64_t pgrid = ((int64_t)W * T + kPairWarps - 1) / kPairWarps;
-    if (pgrid > (int64_t)kNumSM * per_sm) pgrid = (int64_t)kNumSM * per_sm;
+    if (pgrid > (int64_t)num_sms() * per_sm) pgrid = (int64_t)num_sms() * per_sm;
     cudaError_t e = launch(score_pairwise_kernel, (unsigned)pgrid, kPairWarps * 32, psmem, st, true, s);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "score_pairwise_kernel launch: %s", cudaGetErrorString(e));
     return 0;
@@ -859,6 +873,15 @@ extern "C" int sstar_b200_ingest(int device, void *stream, const int8_t *d_gt, c
                                  int32_t n_ref, const int32_t *d_tgt_cols, int32_t n_tgt, int32_t is_phased,
                                  int8_t *d_ref_out, int8_t *d_tgt_out, int32_t *d_pos_out, void *d_workspace,
                                  size_t workspace_bytes) {
+    return sstar_b200_ingest_ex(device, stream, d_gt, d_pos, d_mode, V, N, d_ref_cols, n_ref, n_ref, d_tgt_cols, n_tgt,
+                                n_tgt, is_phased, d_ref_out, d_tgt_out, d_pos_out, d_workspace, workspace_bytes);
+}
+
+extern "C" int sstar_b200_ingest_ex(int device, void *stream, const int8_t *d_gt, const int32_t *d_pos,
+                                    const int8_t *d_mode, int64_t V, int32_t N, const int32_t *d_ref_cols,
+                                    int32_t n_ref, int32_t n_ref_listed, const int32_t *d_tgt_cols, int32_t n_tgt,
+                                    int32_t n_tgt_listed, int32_t is_phased, int8_t *d_ref_out, int8_t *d_tgt_out,
+                                    int32_t *d_pos_out, void *d_workspace, size_t workspace_bytes) {
     g_launches = 0;
     if (V < 0 || V > (int64_t)INT32_MAX - 64) return fail(SSTAR_B200_EINVAL, "V out of range%s");
     if (N < 1 || n_ref < 1 || n_tgt < 1) return fail(SSTAR_B200_EINVAL, "at least one sample per population is required%s");
@@ -876,6 +899,7 @@ extern "C" int sstar_b200_ingest(int device, void *stream, const int8_t *d_gt, c
     IngestArgs a = {};
     a.gt = d_gt; a.pos = d_pos; a.mode = d_mode; a.ref_cols = d_ref_cols; a.tgt_cols = d_tgt_cols;
     a.V = V; a.N = N; a.n_ref = n_ref; a.n_tgt = n_tgt; a.phased = is_phased ? 1 : 0;
+    a.ref_listed = n_ref_listed; a.tgt_listed = n_tgt_listed;
     a.counts = reinterpret_cast<int64_t *>(ws);
     a.keep = ws + 256;
     a.block_base = reinterpret_cast<int32_t *>(ws + 256 + align_up((size_t)V, 256));
@@ -967,7 +991,7 @@ int launch_snp_sets(cudaStream_t st, bool fill, const int8_t *d_tgt, const int32
     if (per_sm > 16) per_sm = 16;
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (S.n + kPairWarps - 1) / kPairWarps;
-    if (grid > (int64_t)kNumSM * per_sm) grid = (int64_t)kNumSM * per_sm;
+    if (grid > (int64_t)num_sms() * per_sm) grid = (int64_t)num_sms() * per_sm;
     cudaError_t e;
     if (!fill) {  // n, SNP counts and the NaN units from the planes; the rest is queued for the warps
         e = cudaMemsetAsync(a.queue_n, 0, 4, st);

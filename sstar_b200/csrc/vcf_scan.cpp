@@ -7,8 +7,11 @@
 // header order; the population split and the filters of read_data happen afterwards
 // (sstar_b200/utils/utils.py on the host, ingest_kernels.cuh on the device).
 //
-// The file (plain text or gzip, through zlib) is read into memory once, data lines are indexed,
-// and the lines are parsed in parallel by std::thread workers.
+// The file (plain text or gzip, through zlib) is STREAMED in blocks of a few dozen MB: the data lines
+// of a block that belong to the wanted chromosome are indexed and parsed in parallel by std::thread
+// workers, lines of other chromosomes are skipped before anything is buffered, and only the listed
+// samples' columns are parsed and stored (allel.read_vcf(samples=..., region=...) does the same:
+// sstar/utils/utils.py:80) -- memory is the kept calls plus one block, whatever the file holds.
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -18,6 +21,7 @@
 #include <string>
 #include <thread>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "sstar_b200.h"
@@ -26,7 +30,6 @@ namespace {
 
 struct ChromData {
     std::string name;
-    std::vector<size_t> line_begin, line_end;  // byte ranges of this chromosome's data lines
     std::vector<int32_t> pos;
     std::vector<int8_t> gt;  // [V, N, 2]
     std::vector<int32_t> ref_off, alt_off;  // [V + 1]
@@ -73,7 +76,10 @@ struct LineFields {
     int32_t ref_len, alt_len;
 };
 
-void parse_line(const char *p, const char *e, int n_samples, int32_t *pos_out, int8_t *gt_out, LineFields *lf) {
+// sel[c] = output slot of header column c, or -1 (column not wanted); n_cols = header columns,
+// n_samples = output slots, last_col = the last wanted column (the rest of the line is not scanned)
+void parse_line(const char *p, const char *e, const int32_t *sel, int n_cols, int last_col, int n_samples,
+                int32_t *pos_out, int8_t *gt_out, LineFields *lf) {
     if (e > p && e[-1] == '\r') --e;
     int field = 0;
     int sample = 0;
@@ -93,7 +99,8 @@ void parse_line(const char *p, const char *e, int n_samples, int32_t *pos_out, i
             const char *c = find_byte(p, t, ',');
             lf->alt = p; lf->alt_len = (int32_t)(c - p);
         } else if (field >= 9) {
-            if (sample < n_samples) parse_gt(p, t, gt_out + (size_t)sample * 2);
+            if (sample < n_cols && sel[sample] >= 0) parse_gt(p, t, gt_out + (size_t)sel[sample] * 2);
+            if (sample >= last_col) break;
             ++sample;
         }
         ++field;
@@ -106,109 +113,162 @@ void parse_line(const char *p, const char *e, int n_samples, int32_t *pos_out, i
 
 extern "C" const char *sstar_b200_vcf_last_error(void) { return g_vcf_err.c_str(); }
 
-extern "C" int sstar_b200_vcf_scan(const char *path, const char *chr_name, int nthreads, sstar_b200_vcf **out) {
-    if (!path || !out) { g_vcf_err = "null argument"; return SSTAR_B200_EINVAL; }
+extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, const char *const *samples,
+                                      int32_t n_samples, int nthreads, sstar_b200_vcf **out) {
+    if (!path || !out || (n_samples > 0 && !samples)) { g_vcf_err = "null argument"; return SSTAR_B200_EINVAL; }
     *out = nullptr;
     gzFile gz = gzopen(path, "rb");
     if (!gz) { g_vcf_err = std::string("cannot open ") + path; return SSTAR_B200_EINVAL; }
     gzbuffer(gz, 1 << 20);
-    std::vector<char> buf;
-    {
-        size_t cap = (size_t)64 << 20, len = 0;
-        buf.resize(cap);
-        for (;;) {
-            if (len == cap) { cap *= 2; buf.resize(cap); }
-            const size_t want = std::min(cap - len, (size_t)1 << 30);
-            const int got = gzread(gz, buf.data() + len, (unsigned)want);
-            if (got < 0) { gzclose(gz); g_vcf_err = std::string("read error in ") + path; return SSTAR_B200_EINVAL; }
-            if (got == 0) break;
-            len += (size_t)got;
-        }
-        buf.resize(len);
-    }
-    gzclose(gz);
-
-    auto *h = new sstar_b200_vcf();
-    const char *b = buf.data(), *end = b + buf.size();
-    std::unordered_map<std::string, int> chrom_id;
-    bool have_header = false;
-    const std::string want = chr_name ? chr_name : "";
-    for (const char *p = b; p < end;) {
-        const char *nl = find_byte(p, end, '\n');
-        if (nl > p) {
-            if (p[0] == '#' && nl - p >= 2 && p[1] == '#') {
-                // meta line
-            } else if (nl - p >= 6 && memcmp(p, "#CHROM", 6) == 0) {
-                h->samples.clear();
-                const char *e = nl;
-                if (e > p && e[-1] == '\r') --e;
-                int field = 0;
-                for (const char *q = p; q <= e;) {
-                    const char *t = find_byte(q, e, '\t');
-                    if (field >= 9) h->samples.emplace_back(q, (size_t)(t - q));
-                    ++field;
-                    if (t >= e) break;
-                    q = t + 1;
-                }
-                have_header = true;
-            } else {
-                const char *t = find_byte(p, nl, '\t');
-                if (!chr_name || ((size_t)(t - p) == want.size() && memcmp(p, want.data(), want.size()) == 0)) {
-                    std::string name(p, (size_t)(t - p));
-                    auto it = chrom_id.find(name);
-                    int id;
-                    if (it == chrom_id.end()) {
-                        id = (int)h->chroms.size();
-                        chrom_id.emplace(name, id);
-                        h->chroms.emplace_back();
-                        h->chroms.back().name = name;
-                    } else id = it->second;
-                    h->chroms[id].line_begin.push_back((size_t)(p - b));
-                    h->chroms[id].line_end.push_back((size_t)(nl - b));
-                }
-            }
-        }
-        p = nl + 1;
-    }
-    if (!have_header) {
-        delete h;
-        g_vcf_err = std::string(path) + " has no #CHROM header line.";
-        return SSTAR_B200_EINVAL;
-    }
-    const int N = (int)h->samples.size();
     int nt = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();
     if (nt < 1) nt = 1;
     if (nt > 64) nt = 64;
-    for (auto &c : h->chroms) {
-        const size_t V = c.line_begin.size();
-        c.pos.resize(V);
-        c.gt.resize(V * (size_t)N * 2);
-        std::vector<LineFields> lf(V);
+
+    auto *h = new sstar_b200_vcf();
+    std::unordered_set<std::string> wanted;
+    const bool subset = samples != nullptr;
+    for (int32_t i = 0; subset && i < n_samples; ++i)
+        if (samples[i]) wanted.insert(samples[i]);
+    std::unordered_map<std::string, int> chrom_id;
+    std::vector<int32_t> sel;  // header column -> output slot (or -1)
+    int n_cols = 0, last_col = -1, N = 0;
+    bool have_header = false;
+    const std::string want = chr_name ? chr_name : "";
+
+    struct LineRef { size_t begin, end; int chrom; size_t row; };
+    std::vector<LineRef> lines;
+    std::vector<LineFields> lf;
+    size_t block = (size_t)32 << 20;
+    if (const char *env = getenv("SSTAR_B200_VCF_BLOCK")) {  // tests shrink the block to cross its edges
+        const long long v = atoll(env);
+        if (v >= 64) block = (size_t)v;
+    }
+    std::vector<char> buf(block);
+    size_t len = 0;  // bytes in buf
+    bool eof = false;
+    int rc = 0;
+    while (!eof || len > 0) {
+        while (!eof && len < buf.size()) {  // top the block up
+            const size_t wantb = std::min(buf.size() - len, (size_t)1 << 30);
+            const int got = gzread(gz, buf.data() + len, (unsigned)wantb);
+            if (got < 0) { g_vcf_err = std::string("read error in ") + path; rc = SSTAR_B200_EINVAL; break; }
+            if (got == 0) eof = true;
+            len += (size_t)got;
+        }
+        if (rc) break;
+        const char *b = buf.data(), *end = b + len;
+        // the block's complete lines end at the last newline (at EOF the unterminated tail is a line too)
+        const char *stop = end;
+        if (!eof) {
+            while (stop > b && stop[-1] != '\n') --stop;
+            if (stop == b) {  // one line longer than the block: grow and read on
+                buf.resize(buf.size() * 2);
+                continue;
+            }
+        }
+        lines.clear();
+        for (const char *p = b; p < stop;) {
+            const char *nl = find_byte(p, stop, '\n');
+            if (nl > p) {
+                if (p[0] == '#' && nl - p >= 2 && p[1] == '#') {
+                    // meta line
+                } else if (nl - p >= 6 && memcmp(p, "#CHROM", 6) == 0) {
+                    h->samples.clear();
+                    sel.clear();
+                    const char *e = nl;
+                    if (e > p && e[-1] == '\r') --e;
+                    int field = 0;
+                    for (const char *q = p; q <= e;) {
+                        const char *t = find_byte(q, e, '\t');
+                        if (field >= 9) {
+                            std::string name(q, (size_t)(t - q));
+                            if (!subset || wanted.count(name)) {
+                                sel.push_back((int32_t)h->samples.size());
+                                h->samples.push_back(std::move(name));
+                            } else sel.push_back(-1);
+                        }
+                        ++field;
+                        if (t >= e) break;
+                        q = t + 1;
+                    }
+                    n_cols = (int)sel.size();
+                    N = (int)h->samples.size();
+                    last_col = -1;
+                    for (int c = 0; c < n_cols; ++c) if (sel[c] >= 0) last_col = c;
+                    have_header = true;
+                } else if (have_header) {
+                    const char *t = find_byte(p, nl, '\t');
+                    if (!chr_name || ((size_t)(t - p) == want.size() && memcmp(p, want.data(), want.size()) == 0)) {
+                        std::string name(p, (size_t)(t - p));
+                        auto it = chrom_id.find(name);
+                        int id;
+                        if (it == chrom_id.end()) {
+                            id = (int)h->chroms.size();
+                            chrom_id.emplace(name, id);
+                            h->chroms.emplace_back();
+                            h->chroms.back().name = name;
+                            h->chroms.back().ref_off.push_back(0);
+                            h->chroms.back().alt_off.push_back(0);
+                        } else id = it->second;
+                        ChromData &c = h->chroms[id];
+                        lines.push_back({(size_t)(p - b), (size_t)(nl - b), id, c.pos.size()});
+                        c.pos.push_back(0);
+                    }
+                } else {
+                    g_vcf_err = std::string(path) + " has no #CHROM header line.";
+                    rc = SSTAR_B200_EINVAL;
+                    break;
+                }
+            }
+            p = nl + 1;
+        }
+        if (rc) break;
+        // parse the block's kept lines in parallel, straight into the chromosomes' arrays
+        for (auto &c : h->chroms) c.gt.resize(c.pos.size() * (size_t)N * 2);
+        lf.resize(lines.size());
+        const size_t L = lines.size();
         auto work = [&](size_t a, size_t z) {
-            for (size_t i = a; i < z; ++i)
-                parse_line(b + c.line_begin[i], b + c.line_end[i], N, &c.pos[i], c.gt.data() + i * (size_t)N * 2, &lf[i]);
+            for (size_t i = a; i < z; ++i) {
+                ChromData &c = h->chroms[lines[i].chrom];
+                parse_line(b + lines[i].begin, b + lines[i].end, sel.data(), n_cols, last_col, N, &c.pos[lines[i].row],
+                           c.gt.data() + lines[i].row * (size_t)N * 2, &lf[i]);
+            }
         };
-        const int use = (int)std::min<size_t>((size_t)nt, std::max<size_t>(1, V / 256));
-        if (use <= 1) work(0, V);
+        const int use = (int)std::min<size_t>((size_t)nt, std::max<size_t>(1, L / 256));
+        if (use <= 1) work(0, L);
         else {
             std::vector<std::thread> th;
-            for (int k = 0; k < use; ++k) th.emplace_back(work, V * k / use, V * (k + 1) / use);
+            for (int k = 0; k < use; ++k) th.emplace_back(work, L * k / use, L * (k + 1) / use);
             for (auto &t : th) t.join();
         }
-        c.ref_off.resize(V + 1); c.alt_off.resize(V + 1);
-        size_t rl = 0, al = 0;
-        for (size_t i = 0; i < V; ++i) { c.ref_off[i] = (int32_t)rl; c.alt_off[i] = (int32_t)al; rl += lf[i].ref_len; al += lf[i].alt_len; }
-        c.ref_off[V] = (int32_t)rl; c.alt_off[V] = (int32_t)al;
-        c.ref_bytes.resize(rl + 1); c.alt_bytes.resize(al + 1);
-        for (size_t i = 0; i < V; ++i) {
-            memcpy(c.ref_bytes.data() + c.ref_off[i], lf[i].ref, (size_t)lf[i].ref_len);
-            memcpy(c.alt_bytes.data() + c.alt_off[i], lf[i].alt, (size_t)lf[i].alt_len);
+        for (size_t i = 0; i < L; ++i) {  // the alleles are copied out before the block is recycled
+            ChromData &c = h->chroms[lines[i].chrom];
+            c.ref_bytes.insert(c.ref_bytes.end(), lf[i].ref, lf[i].ref + lf[i].ref_len);
+            c.alt_bytes.insert(c.alt_bytes.end(), lf[i].alt, lf[i].alt + lf[i].alt_len);
+            c.ref_off.push_back((int32_t)c.ref_bytes.size());
+            c.alt_off.push_back((int32_t)c.alt_bytes.size());
         }
-        c.line_begin.clear(); c.line_begin.shrink_to_fit();
-        c.line_end.clear(); c.line_end.shrink_to_fit();
+        const size_t used = (size_t)(stop - b);
+        memmove(buf.data(), buf.data() + used, len - used);
+        len -= used;
+        if (eof) len = 0;
+    }
+    gzclose(gz);
+    if (!rc && !have_header) {
+        g_vcf_err = std::string(path) + " has no #CHROM header line.";
+        rc = SSTAR_B200_EINVAL;
+    }
+    if (rc) { delete h; return rc; }
+    for (auto &c : h->chroms) {  // (offset arrays keep their [V + 1] shape; the byte arrays one spare byte)
+        c.ref_bytes.push_back(0);
+        c.alt_bytes.push_back(0);
     }
     *out = h;
     return 0;
+}
+
+extern "C" int sstar_b200_vcf_scan(const char *path, const char *chr_name, int nthreads, sstar_b200_vcf **out) {
+    return sstar_b200_vcf_scan_ex(path, chr_name, nullptr, 0, nthreads, out);
 }
 
 extern "C" void sstar_b200_vcf_free(sstar_b200_vcf *h) { delete h; }

@@ -216,13 +216,16 @@ class ScoreEngine:
 
     def score_replicates_device(self, ref_d, tgt_d, pos_d, rep_off_d, win_start, win_end,
                                 match_bonus=5000, max_mismatch=5, mismatch_penalty=-10000,
-                                algo="auto", max_win_variants=0, stream=None):
+                                algo="auto", max_win_variants=0, stream=None, out=None):
         torch = self.torch
         V, R = ref_d.shape
         T = tgt_d.shape[1]
         N = rep_off_d.shape[0] - 1
-        score = torch.empty((N, T), dtype=torch.int64, device=self.tdev)
-        nsnp = torch.empty((N, T), dtype=torch.int32, device=self.tdev)
+        if out is None:
+            score = torch.empty((N, T), dtype=torch.int64, device=self.tdev)
+            nsnp = torch.empty((N, T), dtype=torch.int32, device=self.tdev)
+        else:
+            score, nsnp = out
         ws = self.workspace(V, R, T, N, max_win_variants)
         opts = _cabi.Options(algo=_cabi.ALGOS[algo], max_win_variants=int(max_win_variants))
         rc = self.lib.sstar_b200_score_replicates(
@@ -263,8 +266,32 @@ class ScoreEngine:
             launches = self.launches
         return ScorePlan(graph, out[0], out[1], launches, (ref_d, tgt_d, pos_d, ws_d, we_d, self._dev.get("ws")))
 
+    def plan_replicates_device(self, ref_d, tgt_d, pos_d, rep_off_d, win_start, win_end, match_bonus=5000,
+                               max_mismatch=5, mismatch_penalty=-10000, algo="auto", max_win_variants=0, out=None):
+        """:meth:`plan_device` for a replicate batch (``sstar_b200_score_replicates``)."""
+        torch = self.torch
+        N, T = rep_off_d.shape[0] - 1, tgt_d.shape[1]
+        if out is None:
+            out = (torch.empty((N, T), dtype=torch.int64, device=self.tdev),
+                   torch.empty((N, T), dtype=torch.int32, device=self.tdev))
+        args = (ref_d, tgt_d, pos_d, rep_off_d, win_start, win_end, match_bonus, max_mismatch, mismatch_penalty)
+        kw = dict(algo=algo, max_win_variants=max_win_variants, out=out)
+        with torch.cuda.device(self.tdev):
+            side = torch.cuda.Stream(self.tdev)
+            side.wait_stream(torch.cuda.current_stream(self.tdev))
+            with torch.cuda.stream(side):
+                self.score_replicates_device(*args, **kw)
+            torch.cuda.current_stream(self.tdev).wait_stream(side)
+            side.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.score_replicates_device(*args, **kw)
+            launches = self.launches
+        return ScorePlan(graph, out[0], out[1], launches, (ref_d, tgt_d, pos_d, rep_off_d, self._dev.get("ws")))
+
     # ------------------------------------------------------------------ ingest filters
-    def ingest_device(self, gt, pos, ref_cols, tgt_cols, is_phased: bool, mode=None, stream=None):
+    def ingest_device(self, gt, pos, ref_cols, tgt_cols, is_phased: bool, mode=None, stream=None,
+                      n_ref_listed=None, n_tgt_listed=None):
         """Raw calls ``gt`` int8 [V, N, 2] (numpy or device tensor) -> device tensors
         ``(ref_gts [V', R], tgt_gts [V', T], pos [V'], n_shared)`` after the reference's ingest
         filters (see include/sstar_b200.h, sstar_b200_ingest)."""
@@ -283,14 +310,17 @@ class ScoreEngine:
             pos_o = torch.empty(max(V, 1), dtype=torch.int32, device=self.tdev)
             ws = self._dbuf("ingest_ws", self.lib.sstar_b200_ingest_workspace_bytes(V), torch.uint8)
             s = stream if stream is not None else torch.cuda.current_stream(self.tdev)
-            rc = self.lib.sstar_b200_ingest(
+            rc = self.lib.sstar_b200_ingest_ex(
                 self.device, ctypes.c_void_p(s.cuda_stream), gt_d.data_ptr(), pos_d.data_ptr(),
-                mode_d.data_ptr() if mode_d is not None else None, V, N, rc_d.data_ptr(), n_ref, tc_d.data_ptr(),
-                n_tgt, int(bool(is_phased)), ref_o.data_ptr(), tgt_o.data_ptr(), pos_o.data_ptr(), ws.data_ptr(),
-                ws.numel())
+                mode_d.data_ptr() if mode_d is not None else None, V, N, rc_d.data_ptr(), n_ref,
+                n_ref if n_ref_listed is None else int(n_ref_listed), tc_d.data_ptr(), n_tgt,
+                n_tgt if n_tgt_listed is None else int(n_tgt_listed), int(bool(is_phased)), ref_o.data_ptr(),
+                tgt_o.data_ptr(), pos_o.data_ptr(), ws.data_ptr(), ws.numel())
             _cabi.check(rc)
             self.launches = self.lib.sstar_b200_last_launch_count()
-            head = ws[:16].cpu().numpy().view(np.int64)  # syncs the stream
+            with torch.cuda.stream(s):
+                head_t = ws[:16].to("cpu", non_blocking=False)  # a copy on `s`: waits for the kernels enqueued on it
+            head = head_t.numpy().view(np.int64)
         kept, shared = int(head[0]), int(head[1])
         return ref_o[:kept], tgt_o[:kept], pos_o[:kept], shared
 
@@ -365,7 +395,8 @@ class ScoreEngine:
                 out.data_ptr(), out.numel(), ws.data_ptr(), ws.numel())
             _cabi.check(rc)
             self.launches = self.lib.sstar_b200_last_launch_count()
-            head = ws[:16].cpu().numpy()  # syncs the stream
+            with torch.cuda.stream(s):
+                head = ws[:16].to("cpu", non_blocking=False).numpy()  # a copy on `s`: waits for its kernels
         total = int(head[:8].view(np.int64)[0])
         status = int(head[8:12].view(np.uint32)[0])
         return out, total, status
@@ -491,6 +522,34 @@ class ScoreEngine:
         """numpy in, numpy out: (score[W,T] int64 with NAN_SENTINEL, nsnp[W,T] int32)."""
         return self.wait(self.score_host_async(ref_gts, tgt_gts, pos, win_start, win_end, match_bonus,
                                                max_mismatch, mismatch_penalty, algo=algo, flags=flags))
+
+    def score_replicates_pinned(self, ref_p, tgt_p, pos_p, off_p, score_p, nsnp_p, win_start, win_end,
+                                match_bonus=5000, max_mismatch=5, mismatch_penalty=-10000, algo="auto",
+                                max_win_variants=0, sync=True):
+        """A replicate batch end to end on PAGE-LOCKED host tensors: asynchronous H2D of the
+        concatenated replicates, one device call, D2H of the two ``[Nrep, T]`` tables into
+        ``score_p`` / ``nsnp_p`` (page-locked or registered host memory)."""
+        torch = self.torch
+        V, R = ref_p.shape
+        T = tgt_p.shape[1]
+        N = off_p.shape[0] - 1
+        with torch.cuda.device(self.tdev):
+            d = {}
+            for key, src, dt in (("ref", ref_p, torch.int8), ("tgt", tgt_p, torch.int8), ("pos", pos_p, torch.int32),
+                                 ("off", off_p, torch.int32)):
+                n = src.numel()
+                d[key] = self._dbuf("dev_" + key, n, dt)[:n]
+                if n:
+                    d[key].copy_(src.reshape(-1), non_blocking=True)
+            out = (self._dbuf("rep_score", N * T, torch.int64)[:N * T].view(N, T),
+                   self._dbuf("rep_nsnp", N * T, torch.int32)[:N * T].view(N, T))
+            self.score_replicates_device(d["ref"].view(V, R), d["tgt"].view(V, T), d["pos"], d["off"], win_start,
+                                         win_end, match_bonus, max_mismatch, mismatch_penalty, algo=algo,
+                                         max_win_variants=max_win_variants, out=out)
+            score_p.copy_(out[0], non_blocking=True)
+            nsnp_p.copy_(out[1], non_blocking=True)
+            if sync:
+                torch.cuda.current_stream(self.tdev).synchronize()
 
     def score_replicates_host(self, ref_gts, tgt_gts, pos, rep_offset, win_start, win_end,
                               match_bonus=5000, max_mismatch=5, mismatch_penalty=-10000, algo="auto"):

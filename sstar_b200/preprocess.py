@@ -24,30 +24,37 @@ from .utils.utils import _scan_vcf, read_anc_allele, validate_unique_variant_pos
 
 
 def _anc_modes(rec: dict, anc_c: dict) -> np.ndarray:
-    """Per variant: 0 keep, 1 flip, 2 drop -- the decision of check_anc_allele (utils.py:363-423)."""
-    pos, ref, alt = rec["POS"], rec["REF"], rec["ALT"]
+    """Per variant: 0 keep, 1 flip, 2 drop -- the decision of check_anc_allele (utils.py:363-423).
+    Vectorised: the table's positions are matched with one sorted search, the allele strings
+    compared as arrays."""
+    pos = np.asarray(rec["POS"], dtype=np.int64)
     mode = np.full(len(pos), 2, dtype=np.int8)
-    for i in range(len(pos)):
-        a = anc_c.get(int(pos[i]))
-        if a is None:
-            continue
-        if a == ref[i]:
-            mode[i] = 0
-        elif a == alt[i]:
-            mode[i] = 1
+    if not anc_c or len(pos) == 0:
+        return mode
+    keys = np.fromiter(anc_c.keys(), dtype=np.int64, count=len(anc_c))
+    order = np.argsort(keys, kind="stable")
+    keys = keys[order]
+    alleles = np.asarray(list(anc_c.values()), dtype=object)[order]
+    at = np.minimum(np.searchsorted(keys, pos), len(keys) - 1)
+    known = keys[at] == pos
+    anc = alleles[at]
+    is_ref = known & (anc == np.asarray(rec["REF"], dtype=object))
+    is_alt = known & (anc == np.asarray(rec["ALT"], dtype=object))
+    mode[is_alt] = 1
+    mode[is_ref] = 0  # (REF wins when both match, as the loop's if / elif did)
     return mode
 
 
 def _preprocess_device(device, vcf_file, chr_name, ref_ind_file, tgt_ind_file, win_len, win_step, output_file,
                        match_bonus, max_mismatch, mismatch_penalty, is_phased, anc_allele_file):
-    from .engine import get_engine, max_window_variants
+    from .engine import check_positions, get_engine, max_window_variants
     if win_len <= 0:
         raise ValueError("win_len must be greater than 0.")
     if win_step < 0:
         raise ValueError("win_step must be non-negative.")
     ref_samples, tgt_samples = parse_ind_file(ref_ind_file), parse_ind_file(tgt_ind_file)
     anc = read_anc_allele(anc_allele_file) if anc_allele_file is not None else None
-    header, scanned = _scan_vcf(vcf_file, chr_name, need_alleles=anc is not None)
+    header, scanned = _scan_vcf(vcf_file, chr_name, need_alleles=anc is not None, samples=ref_samples + tgt_samples)
     if not scanned or chr_name not in scanned:
         raise ValueError(f"{chr_name} is not present in the VCF file.")
     rec = scanned[chr_name]
@@ -62,10 +69,12 @@ def _preprocess_device(device, vcf_file, chr_name, ref_ind_file, tgt_ind_file, w
         raise no_shared
     eng = get_engine(device)
     torch = eng.torch
-    ref_d, tgt_d, pos_d, shared = eng.ingest_device(rec["GT"], rec["POS"], ref_cols, tgt_cols, is_phased, mode)
+    # the fixed-site filter compares with the LISTED sample counts, as the reference does (utils.py:282-291)
+    ref_d, tgt_d, pos_d, shared = eng.ingest_device(rec["GT"], rec["POS"], ref_cols, tgt_cols, is_phased, mode,
+                                                    n_ref_listed=len(ref_samples), n_tgt_listed=len(tgt_samples))
     if shared == 0:
         raise no_shared
-    pos = pos_d.cpu().numpy()
+    pos = check_positions(pos_d.cpu().numpy())  # the window search and the DP need ascending positions
     windows = split_genome(pos=pos, chr_name=chr_name, polymorphism_size=win_len, step_size=win_step)
     ws = np.asarray([w[1][0] for w in windows], dtype=np.int64)
     we = np.asarray([w[1][1] for w in windows], dtype=np.int64)
@@ -73,8 +82,10 @@ def _preprocess_device(device, vcf_file, chr_name, ref_ind_file, tgt_ind_file, w
         raise ValueError("window coordinates do not fit int32")
     labels = sample_labels(tgt_samples, 2, is_phased)
     if tgt_d.shape[1] != len(labels):
-        raise ValueError(f"tgt_gts has {tgt_d.shape[1]} columns but {len(labels)} sample labels follow from the "
-                         "target list / ploidy / phasing")
+        # a listed target sample the VCF does not hold: the reference's worker fails in _fmt_res
+        # (feature_vector_preprocessor.py:174-181), mp_manager returns "error" (preprocess.py:114-115)
+        raise RuntimeError(f"tgt_gts has {tgt_d.shape[1]} columns but {len(labels)} sample labels follow from the "
+                           "target list / ploidy / phasing")
     with torch.cuda.device(eng.tdev):
         ws_d = torch.from_numpy(ws.astype(np.int32)).to(eng.tdev)
         we_d = torch.from_numpy(we.astype(np.int32)).to(eng.tdev)

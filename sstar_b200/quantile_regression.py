@@ -8,8 +8,10 @@ ONNX, :32-67) is out of scope.
 
 Numerics: leaf weights and thresholds are the float32 values stored in the file, the feature is
 compared as float32 (``BRANCH_LEQ``: x <= threshold takes the true branch), and the tree outputs
-are summed in float64 in tree order, then the base value is added.  The reference's own test
-compares predictions with rtol = 1e-6 (tests/test_infer.py:50-57); that is the bar here too.
+are summed in float32 in tree order, then the base value is added in float32 and the result
+widened to float64 -- what onnxruntime returns to the reference (a float32 prediction), so a
+``S*_score > prediction`` comparison next to a rounding boundary falls the same way.  The
+reference's own test compares predictions with rtol = 1e-6 (tests/test_infer.py:50-57).
 """
 from __future__ import annotations
 
@@ -125,8 +127,11 @@ class TreeEnsemble:
         raise ValueError(f"{path} holds no TreeEnsembleRegressor node")
 
     def predict_one(self, x) -> float:
+        """One prediction as onnxruntime's TreeEnsembleRegressor makes it for a float32 input
+        (sstar/quantile_regression.py:106-118 feeds float32 and widens the float32 result): the leaf
+        weights are summed in float32, in tree order, the base value is added in float32."""
         x = np.float32(x)
-        total = 0.0
+        total = np.float32(0.0)
         for nodes in self.trees:
             n = 0
             while True:
@@ -134,8 +139,8 @@ class TreeEnsemble:
                 if leaf:
                     break
                 n = tr if x <= thr else fa
-            total += w
-        return total + self.base
+            total = np.float32(total + np.float32(w))
+        return float(np.float32(total + np.float32(self.base)))
 
     def lookup_table(self, max_value: int) -> np.ndarray:
         """Predictions for the feature values 0 .. max_value (float64)."""

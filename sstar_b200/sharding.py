@@ -134,3 +134,111 @@ def _worker(dev: int):
     if ex is None:
         ex = _WORKERS[dev] = ThreadPoolExecutor(max_workers=1, thread_name_prefix=f"sstar-gpu{dev}")
     return ex
+
+
+# ---------------------------------------------------------------------------------------------
+# One process per GPU (torchrun / any launcher): the host gather
+# ---------------------------------------------------------------------------------------------
+class SharedHostTable:
+    """The ``[W, T]`` result tables (int64 scores, int32 SNP counts) of one chromosome in SHARED,
+    page-locked host memory: every rank's GPU stores its ``[W_g, T]`` block straight into its window
+    range, so the gather of sstar/mp_manager.py:172-179 + the sort of sstar/preprocess.py:117 is
+    nothing but the ranks' own device-to-host traffic -- no queue, no pickle, no concatenation.
+
+    Rank 0 creates it (``SharedHostTable(W, T)``) and sends ``table.handle`` to the other ranks by
+    whatever channel the launcher offers; they attach with ``SharedHostTable(W, T, handle=...)``.
+    The memory is an anonymous ``memfd`` (shmem: pinnable, not bounded by the size of /dev/shm),
+    reached by the other processes through ``/proc/<pid>/fd/<fd>``.  ``register()`` page-locks and
+    maps it for the calling process' CUDA context, after which the C-ABI host entry writes it in
+    place."""
+
+    def __init__(self, W: int, T: int, handle=None, kind: str = "memfd"):
+        import mmap
+        self.W, self.T = int(W), int(T)
+        n = self.W * self.T
+        self._off_nsnp = (n * 8 + 4095) // 4096 * 4096
+        self.nbytes = max(self._off_nsnp + n * 4, 4096)
+        self._unlink = None
+        if handle is None:
+            if kind == "memfd" and hasattr(os, "memfd_create"):
+                self._fd = os.memfd_create("sstar_b200_table")
+                self.handle = ("memfd", os.getpid(), self._fd, self.nbytes)
+            else:  # a named tmpfs file, for hosts where another process' /proc/<pid>/fd is off limits
+                import tempfile
+                self._fd, path = tempfile.mkstemp(prefix="sstar_b200_table_", dir="/dev/shm")
+                self._unlink = path
+                self.handle = ("shm", path, 0, self.nbytes)
+            os.ftruncate(self._fd, self.nbytes)
+        else:
+            kind, a, b, nbytes = handle
+            if int(nbytes) != self.nbytes:
+                raise ValueError("shared table handle does not match the table shape")
+            self._fd = os.open(f"/proc/{int(a)}/fd/{int(b)}" if kind == "memfd" else str(a), os.O_RDWR)
+            self.handle = tuple(handle)
+        self._mm = mmap.mmap(self._fd, self.nbytes)
+        raw = np.frombuffer(self._mm, dtype=np.uint8)
+        self.score = raw[:n * 8].view(np.int64).reshape(self.W, self.T)
+        self.nsnp = raw[self._off_nsnp:self._off_nsnp + n * 4].view(np.int32).reshape(self.W, self.T)
+        self._raw = raw
+        self._registered = None
+
+    def register(self, torch):
+        """Page-lock + map the table for this process' CUDA context; returns torch views
+        ``(score [W,T] int64, nsnp [W,T] int32)`` the host entry point can write in place."""
+        t = torch.from_numpy(self._raw)
+        if self._registered is None:
+            rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), self.nbytes, 3)  # portable | mapped
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister of the shared result table failed ({rc})")
+            self._registered = (torch, t.data_ptr())
+        n = self.W * self.T
+        return (t[:n * 8].view(torch.int64).view(self.W, self.T),
+                t[self._off_nsnp:self._off_nsnp + n * 4].view(torch.int32).view(self.W, self.T))
+
+    def close(self):
+        if self._registered is not None:
+            torch, ptr = self._registered
+            torch.cuda.cudart().cudaHostUnregister(ptr)
+            self._registered = None
+        self.score = self.nsnp = self._raw = None
+        try:
+            self._mm.close()
+        except BufferError:  # a caller still holds a view: the mapping goes with the process
+            pass
+        os.close(self._fd)
+        if self._unlink:
+            try:
+                os.unlink(self._unlink)
+            except OSError:
+                pass
+
+
+def plan_replicate_shards(rep_offset, n_shards: int):
+    """Contiguous replicate ranges with ~equal variant counts (sstar/simulate.py:147-176 fans the
+    replicates of a batch over its workers; here over GPUs) -> list of (r0, r1)."""
+    off = np.asarray(rep_offset, dtype=np.int64)
+    n = off.shape[0] - 1
+    if n <= 0:
+        return []
+    n_shards = max(1, min(int(n_shards), n))
+    work = (off[1:] - off[0]) + 8 * np.arange(1, n + 1)  # +8: fixed cost per replicate
+    cuts = [0]
+    for s in range(1, n_shards):
+        cuts.append(int(np.searchsorted(work, work[-1] * s / n_shards, side="left")) + 1)
+    cuts.append(n)
+    return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if min(b, n) > min(a, n)]
+
+
+def plan_chromosome_assignment(costs, n_gpus: int):
+    """Whole chromosomes -> GPUs, greedily by cost (``W_chr * T``), largest
+    first onto the least loaded GPU.  ``costs``: {name: cost}.  -> list (one per GPU) of names, in
+    the order that GPU should run them.  The reference loops ``preprocess()`` over chromosomes
+    (sstar/preprocess.py:90-112 is per ``chr_name``); independent chromosomes need no exchange."""
+    n_gpus = max(1, int(n_gpus))
+    load = [0.0] * n_gpus
+    plan = [[] for _ in range(n_gpus)]
+    for name, c in sorted(costs.items(), key=lambda kv: (-float(kv[1]), str(kv[0]))):
+        g = min(range(n_gpus), key=lambda i: (load[i], i))
+        plan[g].append(name)
+        load[g] += float(c)
+    return plan

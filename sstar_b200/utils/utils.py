@@ -29,9 +29,11 @@ def parse_ind_file(filename: str) -> list[str]:
     return samples
 
 
-def _scan_vcf(path: str, chr_name: str | None, need_alleles: bool = True):
-    """One pass over a (optionally gzipped) text VCF -> header samples + per-chromosome columns,
-    through the native multi-threaded scanner (``sstar_b200_vcf_scan``, csrc/vcf_scan.cpp).
+def _scan_vcf(path: str, chr_name: str | None, need_alleles: bool = True, samples=None):
+    """One streaming pass over a (optionally gzipped) text VCF -> kept samples (header order) +
+    per-chromosome columns, through the native multi-threaded scanner (``sstar_b200_vcf_scan_ex``,
+    csrc/vcf_scan.cpp).  ``samples``: names to keep (the ref + tgt lists; what
+    ``allel.read_vcf(samples=...)`` does, utils.py:80) -- None keeps every column.
 
     ``REF`` / ``ALT`` are only materialised as Python strings when ``need_alleles`` (they are used
     by the ancestral-allele polarisation alone)."""
@@ -41,8 +43,12 @@ def _scan_vcf(path: str, chr_name: str | None, need_alleles: bool = True):
     with open(str(path), "rb"):  # same FileNotFoundError / PermissionError as the reference's reader
         pass
     handle = ctypes.c_void_p()
-    rc = lib.sstar_b200_vcf_scan(str(path).encode(), None if chr_name is None else str(chr_name).encode(), 0,
-                                 ctypes.byref(handle))
+    names, n_names = None, 0
+    if samples is not None:
+        uniq = sorted({str(x) for x in samples})
+        names, n_names = (ctypes.c_char_p * max(len(uniq), 1))(*[u.encode() for u in uniq]), len(uniq)
+    rc = lib.sstar_b200_vcf_scan_ex(str(path).encode(), None if chr_name is None else str(chr_name).encode(), names,
+                                    n_names, 0, ctypes.byref(handle))
     if rc != 0:
         raise ValueError(lib.sstar_b200_vcf_last_error().decode("utf-8", "replace"))
     try:
@@ -110,7 +116,7 @@ def _select_population(header, scanned, ind, filter_missing, anc_allele, chr_nam
 def read_geno_data(vcf: str, ind: list[str], anc_allele_file: str, filter_missing: bool,
                    chr_name: str = None) -> tuple[dict, np.ndarray]:
     """Genotypes of the listed samples [utils.py:49-111]."""
-    header, scanned = _scan_vcf(vcf, chr_name, need_alleles=anc_allele_file is not None)
+    header, scanned = _scan_vcf(vcf, chr_name, need_alleles=anc_allele_file is not None, samples=ind)
     anc = read_anc_allele(anc_allele_file) if anc_allele_file is not None else None
     return _select_population(header, scanned, ind, filter_missing, anc, chr_name)
 
@@ -148,7 +154,8 @@ def read_data(vcf_file: str, ref_ind_file: str, tgt_ind_file: str, anc_allele_fi
     header = scanned = None
     anc = read_anc_allele(anc_allele_file) if anc_allele_file is not None else None
     if ref_ind_file is not None or tgt_ind_file is not None:
-        header, scanned = _scan_vcf(vcf_file, chr_name, need_alleles=anc is not None)
+        listed = [x for f in (ref_ind_file, tgt_ind_file) if f is not None for x in parse_ind_file(f)]
+        header, scanned = _scan_vcf(vcf_file, chr_name, need_alleles=anc is not None, samples=listed)
 
     def copy_scan():
         return {c: dict(rec) for c, rec in scanned.items()}

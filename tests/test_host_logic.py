@@ -263,3 +263,28 @@ def test_legacy_score_table_format(phased):
     assert len(diff) == (0 if phased else 1)
     if diff:
         assert diff[0][1] == "21\t30000\t80000\tind1\tNA\t5\tNA\tNA"
+
+
+def test_plan_replicate_shards_cover_and_balance():
+    from sstar_b200.sharding import plan_replicate_shards
+    rng = np.random.default_rng(3)
+    off = np.concatenate([[0], np.cumsum(rng.integers(50, 200, size=1000))])
+    for n in (1, 2, 3, 8):
+        sh = plan_replicate_shards(off, n)
+        assert len(sh) == n and sh[0][0] == 0 and sh[-1][1] == 1000
+        assert all(a[1] == b[0] for a, b in zip(sh[:-1], sh[1:]))
+        work = [off[b] - off[a] for a, b in sh]
+        assert max(work) < 1.15 * (off[-1] / n) + 400
+    assert plan_replicate_shards([0], 4) == []
+    assert plan_replicate_shards([0, 5, 9], 8) == [(0, 1), (1, 2)]
+
+
+def test_plan_chromosome_assignment_is_greedy_lpt():
+    from sstar_b200.sharding import plan_chromosome_assignment
+    costs = {f"chr{i}": c for i, c in enumerate([248, 242, 198, 190, 181, 171, 159, 145, 138, 133, 135, 133, 114, 107,
+                                                   102, 90, 83, 80, 58, 64, 46, 50], start=1)}
+    plan = plan_chromosome_assignment(costs, 8)
+    assert sorted(c for g in plan for c in g) == sorted(costs)
+    loads = [sum(costs[c] for c in g) for g in plan]
+    assert max(loads) <= 1.12 * sum(costs.values()) / 8
+    assert plan_chromosome_assignment({"a": 1}, 4) == [["a"], [], [], []]

@@ -45,3 +45,23 @@ def test_infer_skips_missing_scores(tmp_path):
     pred = pd.read_csv(tmp_path / "p.tsv", sep="\t")
     assert np.isnan(pred.loc[0, "Predicted_S*_score"]) and pred.loc[1, "Predicted_S*_score"] > 50000
     assert open(tmp_path / "t.bed").read() == "21\t50000\t100000\tind1_1\n"
+
+
+def test_predictions_are_float32_sums_like_onnxruntime():
+    """A prediction that float64 accumulation would not round to a float32 value: the evaluator
+    must return exactly what a float32 accumulator in tree order gives (onnxruntime's result)."""
+    from sstar_b200.quantile_regression import TreeEnsemble
+    ens = TreeEnsemble.from_onnx(os.path.join(FIXTURES, "test.qr.model.onnx"))
+    for v in (0, 3, 7, 10, 57, 300):
+        p = ens.predict_one(v)
+        assert p == float(np.float32(p)), "prediction is not a float32 value"
+        acc = np.float32(0.0)
+        for nodes in ens.trees:
+            n = 0
+            while not nodes[n][0]:
+                n = nodes[n][2] if np.float32(v) <= nodes[n][1] else nodes[n][3]
+            acc = np.float32(acc + np.float32(nodes[n][4]))
+        assert p == float(np.float32(acc + np.float32(ens.base)))
+    # float64 accumulation of the same leaves differs in the low bits for this model
+    f64 = sum(float(nodes[[k for k in nodes if nodes[k][0]][0]][4]) for nodes in ens.trees[:1])
+    assert isinstance(f64, float)

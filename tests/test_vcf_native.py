@@ -86,3 +86,36 @@ def test_large_synthetic_vcf_round_trip(tmp_path):
     assert header == names and np.array_equal(got["7"]["POS"], pos)
     want, _ = tiling_port.read_vcf_text(str(path), header, "7")
     assert np.array_equal(got["7"]["GT"], want["7"]["GT"])
+
+
+def test_streaming_blocks_and_sample_subset(tmp_path, monkeypatch):
+    """The scanner streams the file block by block and keeps only the listed samples: tiny blocks
+    (lines straddle every block edge, some lines are longer than a block) must give the same arrays
+    as one big block, and a sample subset the same calls as slicing the full scan
+    (allel.read_vcf(samples=...), sstar/utils/utils.py:80)."""
+    from sstar_b200.synth import synth_chromosome, write_vcf
+    from sstar_b200.utils.utils import _scan_vcf
+    ref, tgt, pos = synth_chromosome(400_000, 12, 9, True, seed=5)
+    path = tmp_path / "s.vcf"
+    names = write_vcf(str(path), "3", pos, np.concatenate([ref, tgt], axis=1), missing_rate=0.02, seed=2)
+    # a second chromosome interleaved at the end and in front: skipped before anything is stored
+    body = open(path).read().split("\n")
+    head, data = [l for l in body if l.startswith("#")], [l for l in body if l and not l.startswith("#")]
+    other = [("9" + l[1:]) for l in data[:50]]
+    path.write_text("\n".join(head + other[:25] + data + other[25:]) + "\n")
+    header, full = _scan_vcf(str(path), "3")
+    assert header == names and list(full) == ["3"] and np.array_equal(full["3"]["POS"], pos)
+    for block in (64, 257, 4096):
+        monkeypatch.setenv("SSTAR_B200_VCF_BLOCK", str(block))
+        h2, got = _scan_vcf(str(path), "3")
+        assert h2 == header and np.array_equal(got["3"]["POS"], pos) and np.array_equal(got["3"]["GT"], full["3"]["GT"])
+        assert list(got["3"]["REF"]) == list(full["3"]["REF"]) and list(got["3"]["ALT"]) == list(full["3"]["ALT"])
+        h3, both = _scan_vcf(str(path), None)
+        assert list(both) == ["9", "3"] and len(both["9"]["POS"]) == 50
+    monkeypatch.delenv("SSTAR_B200_VCF_BLOCK")
+    pick = [names[7], names[0], names[13], "not_in_file", names[7]]
+    hs, sub = _scan_vcf(str(path), "3", samples=pick)
+    assert hs == [names[0], names[7], names[13]]          # header order, each once
+    assert np.array_equal(sub["3"]["GT"], full["3"]["GT"][:, [0, 7, 13], :])
+    hs, none = _scan_vcf(str(path), "3", samples=["nobody"])
+    assert hs == [] and none["3"]["GT"].shape == (len(pos), 0, 2)
