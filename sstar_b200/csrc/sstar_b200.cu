@@ -16,6 +16,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <mutex>
 
 #include "sstar_b200.h"
 #include "common.cuh"
@@ -62,19 +63,27 @@ int num_sms() {
     return n;
 }
 
-// cudaFuncSetAttribute is per device: remember, per host thread AND device, the largest dynamic
-// shared-memory size already granted to each kernel (index = current device).
+// cudaFuncSetAttribute is per device and PROCESS-wide (a smaller value set by another host thread
+// would lower the limit under a launch already sized for the larger one): the largest dynamic
+// shared-memory size granted to each kernel is remembered per device for the whole process and only
+// ever raised, under one lock.
 constexpr int kAttrDevices = 64;
-struct SmemGrant { size_t bytes[kAttrDevices] = {}; };
+struct SmemGrant { std::atomic<size_t> bytes[kAttrDevices]; };
+std::mutex g_grant_mutex;
 template <typename Kernel>
 cudaError_t grant_smem(SmemGrant &g, Kernel kernel, size_t smem) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= kAttrDevices) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (smem <= g.bytes[dev]) return cudaSuccess;
+    if (dev < 0 || dev >= kAttrDevices) {
+        std::lock_guard<std::mutex> lock(g_grant_mutex);
+        return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 << 10));
+    }
+    if (smem <= g.bytes[dev].load(std::memory_order_acquire)) return cudaSuccess;
+    std::lock_guard<std::mutex> lock(g_grant_mutex);
+    if (smem <= g.bytes[dev].load(std::memory_order_relaxed)) return cudaSuccess;
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) g.bytes[dev] = smem;
+    if (e == cudaSuccess) g.bytes[dev].store(smem, std::memory_order_release);
     return e;
 }
 
@@ -250,7 +259,7 @@ int launch_prep(cudaStream_t st, int64_t g_begin, int64_t g_end, const int8_t *d
     // three instances of one body: whole-row tiles (the common one: 48 registers), column chunks
     // for wide panels, and whole-row tiles with one lane per reference row for panels of <= 16
     // reference columns (replicate batches)
-    static thread_local SmemGrant prep_grant, wide_grant, narrow_grant;
+    static SmemGrant prep_grant, wide_grant, narrow_grant;
     auto kernel = prep_kernel;
     SmemGrant *grant = &prep_grant;
     if (mode == 2) { kernel = prep_wide_kernel; grant = &wide_grant; }
@@ -347,7 +356,7 @@ int launch_score(cudaStream_t st, const ScoreCall &c, const WsLayout &L, int32_t
         }
         const size_t ring_b = (size_t)wg * bd * 4;  // worklist (shares the position tile's region)
         const size_t smem = (size_t)(Lslots + 1) * ls * 4 + (ring_b > pos_b ? ring_b : pos_b);  // +1: spill slot
-        static thread_local SmemGrant group_grant, narrow_grant;
+        static SmemGrant group_grant, narrow_grant;
         const bool narrow = ls != bd;
         cudaError_t e = narrow ? grant_smem(narrow_grant, score_group_narrow_kernel, smem)
                                : grant_smem(group_grant, score_group_kernel, smem);
@@ -363,7 +372,7 @@ int launch_score(cudaStream_t st, const ScoreCall &c, const WsLayout &L, int32_t
         pcap = (int32_t)align_up((size_t)(c.max_win_variants < 64 ? 64 : c.max_win_variants), 8);
     s.pair_smem_cap = pcap;
     const size_t psmem = (size_t)kPairWarps * pcap * 13;
-    static thread_local SmemGrant pair_grant;
+    static SmemGrant pair_grant;
     cudaError_t ep = grant_smem(pair_grant, score_pairwise_kernel, psmem);
     if (ep != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaFuncSetAttribute(pairwise): %s", cudaGetErrorString(ep));
     int per_sm = (int)(((size_t)200 << 10) / (psmem + 1024));
@@ -837,7 +846,7 @@ extern "C" int sstar_b200_format_table(int device, void *stream, const int64_t *
     const int64_t nb = (int64_t)outer * a.blocks_per_win;
     if (nb > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "table too large for one emitter call%s");
     if (nb == 0 || W == 0) return 0;
-    static thread_local SmemGrant emit_grant;
+    static SmemGrant emit_grant;
     CUDA_TRY(grant_smem(emit_grant, emit_format_kernel, smem));
     cudaError_t e = launch(emit_len_kernel, (unsigned)nb, kEmitThreads, 0, st, false, a);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "emit_len_kernel launch: %s", cudaGetErrorString(e));
@@ -1004,11 +1013,11 @@ int launch_snp_sets(cudaStream_t st, bool fill, const int8_t *d_tgt, const int32
         if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "snp_count_kernel launch: %s", cudaGetErrorString(e));
     }
     if (fill) {
-        static thread_local SmemGrant grant;
+        static SmemGrant grant;
         e = grant_smem(grant, snp_set_kernel<true>, smem);
         if (e == cudaSuccess) e = launch(snp_set_kernel<true>, (unsigned)grid, kPairWarps * 32, smem, st, false, a);
     } else {
-        static thread_local SmemGrant grant;
+        static SmemGrant grant;
         e = grant_smem(grant, snp_set_kernel<false>, smem);
         if (e == cudaSuccess) e = launch(snp_set_kernel<false>, (unsigned)grid, kPairWarps * 32, smem, st, false, a);
     }

@@ -20,9 +20,11 @@ def visible_devices(devices=None) -> list[int]:
         if not env:
             return [0]
         devices = [int(x) for x in env.split(",")] if "," in env else int(env)
-    if isinstance(devices, int):
-        return list(range(devices))
-    return [int(d) for d in devices]
+    out = list(range(devices)) if isinstance(devices, int) else [int(d) for d in devices]
+    if not out:
+        raise ValueError("no GPU selected: SSTAR_GPUS / devices must be a positive count (\"4\") or a list of device "
+                         "indices (\"0,2,3\")")
+    return out
 
 
 def plan_window_shards(pos, win_start, win_end, n_shards: int):

@@ -49,10 +49,17 @@ def sample_names(nref: int, ntgt: int, identifier: str = "tsk_"):
 
 def score_replicate_batch(replicates, reps, nref: int, ntgt: int, ploidy: int, seq_len: int,
                           is_phased: bool, match_bonus: int, max_mismatch: int,
-                          mismatch_penalty: int, device: int = 0, algo: str = "auto") -> FeatureTable:
+                          mismatch_penalty: int, device: int = None, algo: str = "auto",
+                          devices=None) -> FeatureTable:
     """``replicates``: list of ``(positions, genotype_matrix)``; ``reps``: their replicate numbers.
-    Returns a FeatureTable with one "window" per replicate and a ``Replicate`` column."""
+    Returns a FeatureTable with one "window" per replicate and a ``Replicate`` column.
+
+    The reference fans the replicates of a batch over its worker processes
+    (sstar/simulate.py:147-176); here they go over the GPUs ``SSTAR_GPUS`` names (or ``devices``)
+    as contiguous replicate ranges of equal variant work, one device call and one host thread per
+    GPU, results concatenated in replicate order.  ``device=k`` pins the batch to one GPU."""
     from .engine import get_engine
+    from .sharding import _worker, plan_replicate_shards, visible_devices
     refs, tgts, poss, starts, ends, off = [], [], [], [], [], [0]
     for pos, gts in replicates:
         r, t, p, s, e = build_feature_input(pos, gts, nref, ntgt, ploidy, seq_len, is_phased)
@@ -61,11 +68,23 @@ def score_replicate_batch(replicates, reps, nref: int, ntgt: int, ploidy: int, s
     if len(set(starts)) != 1 or len(set(ends)) != 1:
         # windows differ between replicates (first site beyond seq_len): fall back to per-window bounds
         raise ValueError("replicates do not share the window [1, seq_len]")
-    eng = get_engine(device)
-    score, nsnp = eng.score_replicates_host(np.concatenate(refs), np.concatenate(tgts),
-                                            np.concatenate(poss), np.asarray(off, dtype=np.int32),
-                                            starts[0], ends[0], match_bonus, max_mismatch,
-                                            mismatch_penalty, algo=algo)
+    devs = [int(device)] if device is not None else visible_devices(devices)
+    ref_all, tgt_all, pos_all = np.concatenate(refs), np.concatenate(tgts), np.concatenate(poss)
+    off = np.asarray(off, dtype=np.int64)
+    shards = plan_replicate_shards(off, len(devs)) if len(devs) > 1 else [(0, len(replicates))]
+
+    def work(dev, r0, r1):
+        a, b = int(off[r0]), int(off[r1])
+        return get_engine(dev).score_replicates_host(ref_all[a:b], tgt_all[a:b], pos_all[a:b],
+                                                     (off[r0:r1 + 1] - off[r0]).astype(np.int32), starts[0], ends[0],
+                                                     match_bonus, max_mismatch, mismatch_penalty, algo=algo)
+
+    if len(shards) == 1:
+        score, nsnp = work(devs[0], *shards[0])
+    else:
+        parts = [f.result() for f in [_worker(dev).submit(work, dev, r0, r1) for dev, (r0, r1) in zip(devs, shards)]]
+        score = np.concatenate([p[0] for p in parts])
+        nsnp = np.concatenate([p[1] for p in parts])
     _, tgt_names = sample_names(nref, ntgt)
     labels = sample_labels(tgt_names, ploidy, is_phased)
     n = len(replicates)

@@ -439,3 +439,106 @@ def test_run_match_random_against_oracle(tmp_path):
         want.append("NA" if r == "NA" else repr(r))
     assert got["match_rate"].tolist() == want          # bit-identical rates (ploidy 2)
     assert "NA" in want and len(set(want)) > 50
+
+
+# ---- multi-GPU product routes.  Listing a device several times ("0,0,0") runs the same sharded code
+# on a one-GPU box (shards queue on the device's worker thread); with more GPUs present the real
+# devices are used as well.
+def _device_lists():
+    import torch
+    n = torch.cuda.device_count()
+    return ["0,0,0"] + ([",".join(str(i) for i in range(n))] if n > 1 else [])
+
+
+@pytest.mark.parametrize("phased", [True, False])
+def test_preprocess_sharded_device_route_prints_the_same_bytes(tmp_path, monkeypatch, phased):
+    """preprocess() with several GPUs stays device-resident (ingest per raw row range, halo rows by
+    peer copy, one text block per GPU) and prints what one GPU prints (and what the numpy-ingest
+    route prints)."""
+    from sstar_b200.preprocess import preprocess
+    vcf, rl, tl, anc_file = _write_case_vcf(tmp_path, 11, n_ind=16, V=5000, anc=True)
+    kw = dict(vcf_file=vcf, chr_name="9", ref_ind_file=rl, tgt_ind_file=tl, win_len=50000, win_step=10000,
+              match_bonus=5000, max_mismatch=5, mismatch_penalty=-10000, is_phased=phased, anc_allele_file=anc_file)
+    monkeypatch.setenv("SSTAR_B200_MIN_SHARD_ROWS", "256")
+    monkeypatch.setenv("SSTAR_GPUS", "1")
+    preprocess(output_file=str(tmp_path / "one.tsv"), **kw)
+    one = open(tmp_path / "one.tsv", "rb").read()
+    assert one.count(b"\n") > 300
+    for devs in _device_lists():
+        monkeypatch.setenv("SSTAR_GPUS", devs)
+        preprocess(output_file=str(tmp_path / "many.tsv"), **kw)
+        assert open(tmp_path / "many.tsv", "rb").read() == one, devs
+    monkeypatch.setenv("SSTAR_B200_HOST_INGEST", "1")
+    preprocess(output_file=str(tmp_path / "host.tsv"), **kw)
+    assert open(tmp_path / "host.tsv", "rb").read() == one
+
+
+def test_preprocess_chromosomes_one_scan_many_gpus(tmp_path, monkeypatch):
+    """Several chromosomes of one VCF: scanned once, whole chromosomes assigned to GPUs by cost
+    (or each sharded when there are fewer chromosomes than GPUs); same bytes as preprocess() per
+    chromosome."""
+    from sstar_b200.preprocess import preprocess, preprocess_chromosomes
+    parts, names = [], None
+    for i, (c, V) in enumerate((("3", 700), ("5", 1500), ("8", 400), ("11", 900))):
+        vcf, rl, tl, _ = _write_case_vcf(tmp_path, 20 + i, n_ind=12, V=V)
+        lines = open(vcf).read().splitlines()
+        head = [l for l in lines if l.startswith("#")]
+        parts += [c + l[1:] for l in lines if not l.startswith("#")]
+    allvcf = tmp_path / "all.vcf"
+    allvcf.write_text("\n".join(head + parts) + "\n")
+    kw = dict(ref_ind_file=rl, tgt_ind_file=tl, win_len=50000, win_step=10000, match_bonus=5000, max_mismatch=5,
+              mismatch_penalty=-10000, is_phased=False)
+    chroms = ["3", "5", "8", "11"]
+    monkeypatch.setenv("SSTAR_GPUS", "1")
+    for c in chroms:
+        preprocess(vcf_file=str(allvcf), chr_name=c, output_file=str(tmp_path / f"want.{c}.tsv"), **kw)
+    monkeypatch.setenv("SSTAR_B200_MIN_SHARD_ROWS", "128")
+    for devs in ["1", "0,0"] + _device_lists()[1:] + ["0,0,0,0,0,0"]:   # the last: fewer chromosomes than "GPUs"
+        monkeypatch.setenv("SSTAR_GPUS", devs)
+        out = preprocess_chromosomes(str(allvcf), chroms, output_files=str(tmp_path / "got.{chr}.tsv"), **kw)
+        for c in chroms:
+            assert open(out[c], "rb").read() == open(tmp_path / f"want.{c}.tsv", "rb").read(), (devs, c)
+    with pytest.raises(ValueError, match="12 is not present in the VCF file"):
+        preprocess_chromosomes(str(allvcf), ["3", "12"], output_files=str(tmp_path / "x.{chr}.tsv"), **kw)
+
+
+def test_listed_sample_absent_from_vcf(tmp_path, monkeypatch):
+    """An ind file naming a sample the VCF does not hold: the reference compares the hom-alt counts of
+    its fixed-site filter with len(samples) of the LIST (utils.py:282-291), so no fixed site is ever
+    dropped -- on the device route as on the numpy route.  A missing TARGET sample ends in
+    SystemExit (the reference's worker fails while formatting: feature_vector_preprocessor.py:174-181)."""
+    from sstar_b200.preprocess import preprocess
+    vcf, rl, tl, _ = _write_case_vcf(tmp_path, 31, n_ind=12, V=1200)
+    kw = dict(vcf_file=vcf, chr_name="9", tgt_ind_file=tl, win_len=50000, win_step=10000, match_bonus=5000,
+              max_mismatch=5, mismatch_penalty=-10000, is_phased=False)
+    rl2 = tmp_path / "ref_plus.list"
+    rl2.write_text(open(rl).read() + "ghost\n")
+    monkeypatch.setenv("SSTAR_GPUS", "1")
+    preprocess(ref_ind_file=rl, output_file=str(tmp_path / "plain.tsv"), **kw)
+    preprocess(ref_ind_file=str(rl2), output_file=str(tmp_path / "dev.tsv"), **kw)
+    monkeypatch.setenv("SSTAR_B200_HOST_INGEST", "1")
+    preprocess(ref_ind_file=str(rl2), output_file=str(tmp_path / "host.tsv"), **kw)
+    monkeypatch.delenv("SSTAR_B200_HOST_INGEST")
+    dev, host, plain = (open(tmp_path / f, "rb").read() for f in ("dev.tsv", "host.tsv", "plain.tsv"))
+    assert dev == host and dev != plain   # the fixed sites stay in: Region_ind_SNP_number differs
+    tl2 = tmp_path / "tgt_plus.list"
+    tl2.write_text(open(tl).read() + "ghost\n")
+    with pytest.raises(SystemExit):
+        preprocess(ref_ind_file=rl, output_file=str(tmp_path / "x.tsv"), **{**kw, "tgt_ind_file": str(tl2)})
+
+
+def test_replicate_batch_over_gpus_equals_one_gpu():
+    """simulate()'s batches spread over SSTAR_GPUS as contiguous replicate ranges
+    (sstar/simulate.py:147-176 fans them over worker processes)."""
+    import torch
+    import test_simulate_host as host
+    from sstar_b200.simulate_batch import score_replicate_batch
+    nref, ntgt, ploidy, L = 4, 9, 2, 50_000
+    reps = [host._fake_replicate(r, 1000 + r, nref, ntgt, ploidy, L) for r in range(57)]
+    ids = list(range(200, 257))
+    for phased in (False, True):
+        one = score_replicate_batch(reps, ids, nref, ntgt, ploidy, L, phased, 5000, 5, -10000, device=0)
+        for devs in ([0, 0, 0], list(range(torch.cuda.device_count()))):
+            many = score_replicate_batch(reps, ids, nref, ntgt, ploidy, L, phased, 5000, 5, -10000, devices=devs)
+            assert np.array_equal(many.score, one.score) and np.array_equal(many.nsnp, one.nsnp), devs
+            assert many.replicate == one.replicate

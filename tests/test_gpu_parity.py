@@ -109,6 +109,17 @@ def test_test0_vcf_windows(eng, test0_golden, phased, algo):
     (3, 70, True, 300_000),        # T > 128 columns
 ])
 def test_synthetic_vs_oracle(eng, algo, n_ref, n_tgt, phased, length):
+    _synthetic_vs_oracle(eng, algo, n_ref, n_tgt, phased, length)
+
+
+def test_c4_panel_shape_vs_oracle(eng):
+    """BASELINE configs[3]'s panel: 100 reference + 2,000 target diploids, unphased dosages
+    (R = 100, T = 2,000), more than 200 windows of 50 kb / 10 kb, every unit against the C oracle."""
+    n_win = _synthetic_vs_oracle(eng, "auto", 100, 2000, False, 2_200_000)
+    assert n_win >= 200
+
+
+def _synthetic_vs_oracle(eng, algo, n_ref, n_tgt, phased, length):
     from sstar_b200.synth import regular_windows, synth_chromosome
     ref, tgt, pos = synth_chromosome(length, n_ref, n_tgt, phased, seed=1000 + n_ref)
     ws, we = regular_windows(pos, 50_000, 10_000)
@@ -116,6 +127,7 @@ def test_synthetic_vs_oracle(eng, algo, n_ref, n_tgt, phased, length):
     so, no = c_oracle.score_windows(ref, tgt, pos, ws, we)
     assert np.array_equal(s, so)
     assert np.array_equal(n, no)
+    return len(ws)
 
 
 @pytest.mark.parametrize("params", [(5000, 5, -10000), (5000, 0, -10000), (1, 1, 0), (123, 4, -7),
@@ -410,3 +422,27 @@ def test_wide_panels_take_column_chunks(eng, R, T):
     for flags in (0, 1):
         s, n = eng.score_host(ref, tgt, pos, ws, we, flags=flags)
         assert np.array_equal(s, so) and np.array_equal(n, no), flags
+
+
+def test_host_threads_share_the_kernels_shared_memory_limits(eng):
+    """cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is process-wide: a call from another host
+    thread that needs little shared memory must not lower the limit under a later large launch
+    (the multi-GPU routes run one host thread per device next to the caller's own thread)."""
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(5)
+
+    def case(V, R, T):
+        pos = np.sort(rng.choice(np.arange(1, 40 * V), size=V, replace=False)).astype(np.int32)
+        ref = (rng.random((V, R)) < 0.02).astype(np.int8)
+        tgt = (rng.random((V, T)) < 0.05).astype(np.int8)
+        ws = np.arange(1, int(pos[-1]), 10_000, dtype=np.int32)
+        return ref, tgt, pos, ws, (ws + 49_999).astype(np.int32)
+
+    wide, small = case(3000, 100, 1900), case(300, 4, 6)   # 64 KB pack tiles vs a few hundred bytes
+    want_w, want_s = c_oracle.score_windows(*wide), c_oracle.score_windows(*small)
+    with ThreadPoolExecutor(max_workers=1) as other:
+        for _ in range(2):
+            got = eng.score_host(*wide)
+            assert np.array_equal(got[0], want_w[0]) and np.array_equal(got[1], want_w[1])
+            got = other.submit(eng.score_host, *small).result()
+            assert np.array_equal(got[0], want_s[0]) and np.array_equal(got[1], want_s[1])
