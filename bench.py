@@ -315,8 +315,8 @@ class ShardCase:
     """The rows / windows one rank owns: page-locked host copies (its own allocation), device copies,
     the captured pass and the timing helpers.  ``out_p`` are this rank's blocks of the host table."""
 
-    def __init__(self, torch, eng, dev, arrays, out_p=None, use_graph=True):
-        self.torch, self.eng, self.dev = torch, eng, dev
+    def __init__(self, torch, eng, dev, arrays, out_p=None, use_graph=True, flags=0):
+        self.torch, self.eng, self.dev, self.flags = torch, eng, dev, flags
         pos, ws, we = arrays["pos"], arrays["ws"], arrays["we"]
         lo = np.searchsorted(pos, ws.astype(np.int64), side="left")
         hi = np.searchsorted(pos, we.astype(np.int64), side="right")
@@ -337,7 +337,7 @@ class ShardCase:
         if use_graph:
             d = self.d
             self.plan = eng.plan_device(d["ref"], d["tgt"], d["pos"], d["ws"], d["we"], *PARAMS,
-                                        max_win_variants=self.hint, out=(self.score_d, self.nsnp_d))
+                                        max_win_variants=self.hint, out=(self.score_d, self.nsnp_d), flags=flags)
 
     def step_device(self):
         if self.plan is not None:
@@ -345,7 +345,7 @@ class ShardCase:
             return self.plan.launches
         d = self.d
         self.eng.score_device(d["ref"], d["tgt"], d["pos"], d["ws"], d["we"], *PARAMS,
-                              max_win_variants=self.hint, out=(self.score_d, self.nsnp_d))
+                              max_win_variants=self.hint, out=(self.score_d, self.nsnp_d), flags=self.flags)
         return self.eng.launches
 
     def step_pack(self):
@@ -443,16 +443,22 @@ def roofline_block(name, st, k, tot_ms, pack_ms, score_ms, launches):
         return out
 
     pipe = ab["pipeline"] / (tot_ms / k * 1e-3) / 1e9
+    fused = launches == 1
     return {
         "bound": "hbm",
-        "kernel": "one pass = prep_kernel (pack + window bounds) -> score_group_kernel (-> score_pairwise_kernel only "
-                  "when a window was routed to it)",
+        "kernel": ("one pass = ONE launch of fused_score_kernel (window bounds + TMA row staging + pack + chain DP per "
+                   "CTA of a few windows; csrc/fused_kernels.cuh)" if fused else
+                   "one pass = prep_kernel (pack + window bounds) -> score_group_kernel (-> score_pairwise_kernel only "
+                   "when a window was routed to it)"),
         "achieved": pipe, "peak": peak, "unit": "GB/s", "frac": pipe / peak,
-        "traffic": sum(filter(None, (recorded_traffic(name, x) for x in ("prep_kernel", "score_group_kernel")))) or None,
+        "traffic": (recorded_traffic(name, "fused_score_kernel") if fused else
+                    sum(filter(None, (recorded_traffic(name, x) for x in ("prep_kernel", "score_group_kernel")))) or None),
         "traffic_source": "profiles/traffic.json (per-launch dram bytes of one ncu --set full capture; null when the "
                           "workload has no capture)",
         "peak_source": peak_src, "algorithmic_bytes": ab["pipeline"],
         "bytes_per_unit": ab["pipeline"] / st["units"], "pass_ms": tot_ms / k, "launches_per_pass": launches,
+        "kernels_note": ("the pass is the fused kernel (its roofline is the pass-level one above); the two kernels below "
+                         "are the launch pipeline's, which larger inputs take, timed alone on this input") if fused else None,
         "kernels": [
             kern("prep_kernel", pack_ms, ab["pack"], "HBM bound: every int8 genotype read once; timed alone"),
             kern("score_group_kernel", score_ms, ab["score"],
@@ -737,7 +743,10 @@ def run_ours(args, world, rank, local):
     w0, w1, k0, k1 = shards[rank]
     arrays = dict(ref=wk["ref"][k0:k1], tgt=wk["tgt"][k0:k1], pos=wk["pos"][k0:k1], ws=wk["ws"][w0:w1], we=wk["we"][w0:w1])
     table, (tab_score, tab_nsnp) = rk.shared_table(W, T)
-    case = ShardCase(torch, eng, dev, arrays, out_p=(tab_score[w0:w1], tab_nsnp[w0:w1]), use_graph=not args.no_graph)
+    from sstar_b200 import _cabi
+    flags = _cabi.FLAG_NO_FUSED if args.no_fused else 0
+    case = ShardCase(torch, eng, dev, arrays, out_p=(tab_score[w0:w1], tab_nsnp[w0:w1]), use_graph=not args.no_graph,
+                     flags=flags)
     barrier = rk.barrier
 
     if args.only_device:  # profiling aid: nothing but the device-resident pass is launched
@@ -847,8 +856,9 @@ def run_ours(args, world, rank, local):
             "notes": {"arithmetic": "int8 genotypes -> bit-planes -> int32 max-plus DP (int64 when a window's score "
                                     "bound exceeds 2^28) -> int64 scores, int32 SNP counts; bit-exact",
                       "rank0_cpu_binding": numa,
-                      "launch": "direct launches" if args.no_graph
-                                else "CUDA graph replay of the pass (ScoreEngine.plan_device)",
+                      "launch": ("direct launches" if args.no_graph
+                                 else "CUDA graph replay of the pass (ScoreEngine.plan_device)") +
+                                ("; one-launch kernel disabled (--no-fused)" if args.no_fused else ""),
                       "collectives_in_timed_region": "none (NCCL: barriers and the max / sum of the timings only)"},
             "ranks": per_rank,
             "e2e": {"value": total_units / (e2e_ms / k * 1e-3), "unit": UNIT,
@@ -899,6 +909,8 @@ def main():
     ap.add_argument("--c3-length", type=int, default=C3["length"], help="length of the strong block's chromosome (debug)")
     ap.add_argument("--no-numa", action="store_true", help="multi-rank runs: do not bind ranks to their GPU's NUMA node")
     ap.add_argument("--only-device", action="store_true", help="profiling aid: run only the device-resident passes")
+    ap.add_argument("--no-fused", action="store_true", help="headline workload: take the pack -> score launches instead of "
+                                                            "the one-launch kernel (comparison)")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels directly instead of replaying the CUDA graph")
     args = ap.parse_args()
     world, rank, local = dist_setup()

@@ -59,6 +59,11 @@ extern "C" {
 #define SSTAR_B200_FLAG_SINGLE_CHUNK 8      /* no row chunking */
 #define SSTAR_B200_FLAG_ZERO_COPY_INPUTS 32 /* the pack kernel reads the genotype matrices from mapped host memory */
 #define SSTAR_B200_FLAG_COPY_INPUTS 64      /* ... never (default: inputs below 32 MB are read in place, larger ones copied in chunks) */
+/* device entry points: which kernels score.  Default: small problems with a window-size hint (and
+ * every replicate batch) take the one-launch kernel (bounds + staging + pack + DP in one CTA per few
+ * windows), everything else pack -> score launches.  Both give identical results. */
+#define SSTAR_B200_FLAG_NO_FUSED 128        /* never the one-launch kernel */
+#define SSTAR_B200_FLAG_FORCE_FUSED 256     /* always (T <= 128), whatever the size and the hint */
 
 typedef struct sstar_b200_options {
     int32_t algo;             /* SSTAR_B200_ALGO_* */

@@ -33,6 +33,8 @@ FLAG_COPY_OUTPUTS = 4
 FLAG_SINGLE_CHUNK = 8
 FLAG_ZERO_COPY_INPUTS = 32
 FLAG_COPY_INPUTS = 64
+FLAG_NO_FUSED = 128
+FLAG_FORCE_FUSED = 256
 
 
 class SstarB200Error(RuntimeError):

@@ -271,4 +271,193 @@ SSTAR_HD void walk_dp_unit(LoadU32 ld, LoadPos ldpos, const uint32_t *carried, c
     score_out = (n <= 2 || top <= THR) ? kNegInf64 : (int64_t)top;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Walk DP, register form: the same walk with list_dp_run's waiting-site scheme -- the previous site
+// waits in registers (the common case: carried sites >= 10 bp apart are committed straight from
+// there), only crowded sites are parked in the thread-local ring.  For planes that sit in shared
+// memory (the fused kernel), where the loads are cheap and the local-memory ring of walk_dp_unit
+// was the latency.
+// ---------------------------------------------------------------------------------------------
+template <typename acc_t, typename LoadU32, typename LoadPos>
+SSTAR_HD void walk_dp_unit_reg(LoadU32 ld, LoadPos ldpos, const uint32_t *carried, const uint32_t *two, int32_t Tp,
+                               int t, int32_t lo, int32_t hi, int32_t bonus_i, int32_t penalty_i, int32_t max_mm,
+                               int &n_out, int64_t &score_out) {
+    constexpr acc_t NEG = Sentinel<acc_t>::NEG, THR = Sentinel<acc_t>::THR;
+    const acc_t bonus = (acc_t)bonus_i;
+    const acc_t pen_eff = (max_mm >= 1) ? (acc_t)penalty_i : NEG;
+    acc_t A0 = NEG, A1 = NEG, B0 = NEG, B1 = NEG, top = NEG;
+    acc_t ring_p[kRingSlots], ring_v[kRingSlots];  // parked sites older than the previous one: p, v << 1 | class
+    acc_t pp = 0, pv = 0;                          // the previous site
+    int k = 0, c = 0;                              // sites seen, next site to commit
+    const auto p0 = ldpos(lo);  // (a loader returning uint32 keeps the position arithmetic 32-bit: differences
+                                //  inside a window are never negative and below 2^32)
+    const int gi0 = lo >> 5, gi1 = (hi - 1) >> 5;
+    for (int gi = gi0; gi <= gi1; ++gi) {
+        uint32_t cb = ld(carried + (size_t)gi * Tp + t);
+        if (gi == gi0) cb &= 0xffffffffu << (lo & 31);
+        if (gi == gi1) cb &= 0xffffffffu >> (31 - ((hi - 1) & 31));
+        if (cb == 0) continue;
+        const uint32_t tw = ld(two + (size_t)gi * Tp + t);
+        while (cb) {
+            const int b = ctz32(cb);
+            cb &= cb - 1;
+            const acc_t p = (acc_t)(ldpos((gi << 5) + b) - p0);
+            const int cls = (int)((tw >> b) & 1u);
+            if (c == k - 1) {  // common case: only the previous site waits, in registers
+                if (p - pp >= kMinPairDistance) {
+                    const acc_t v = pv >> 1;
+                    if (pv & 1) { A1 = imax(A1, v - pp); B1 = imax(B1, v); }
+                    else        { A0 = imax(A0, v - pp); B0 = imax(B0, v); }
+                    c = k;
+                } else {
+                    ring_p[(k - 1) & (kRingSlots - 1)] = pp;  // it keeps waiting: park it
+                    ring_v[(k - 1) & (kRingSlots - 1)] = pv;
+                }
+            } else if (c < k) {  // crowded sites: older ones wait in the ring
+                while (c < k) {
+                    acc_t pc, vc;
+                    if (c == k - 1) { pc = pp; vc = pv; }
+                    else            { pc = ring_p[c & (kRingSlots - 1)]; vc = ring_v[c & (kRingSlots - 1)]; }
+                    if (p - pc < kMinPairDistance) break;
+                    const acc_t v = vc >> 1;
+                    if (vc & 1) { A1 = imax(A1, v - pc); B1 = imax(B1, v); }
+                    else        { A0 = imax(A0, v - pc); B0 = imax(B0, v); }
+                    ++c;
+                }
+                if (c < k) {
+                    ring_p[(k - 1) & (kRingSlots - 1)] = pp;
+                    ring_v[(k - 1) & (kRingSlots - 1)] = pv;
+                }
+            }
+            const acc_t same = cls ? A1 : A0;
+            const acc_t other = cls ? B0 : B1;
+            const acc_t m = imax(same + (p + bonus), other + pen_eff);
+            top = imax(top, m);
+            pp = p;
+            pv = (imax(m, (acc_t)0) << 1) | (acc_t)cls;
+            ++k;
+        }
+    }
+    n_out = k;
+    score_out = (k <= 2 || top <= THR) ? kNegInf64 : (int64_t)top;
+}
+
+// ---------------------------------------------------------------------------------------------
+// General-genotype walk DP: walk_dp_unit for ANY int8 genotype (missing calls, multi-allelic
+// dosages), straight from a carried plane plus the genotype bytes; int64 accumulators.  Per-class
+// running maxima as in list_dp_run_general (<= kMaxClasses distinct values per unit, else false:
+// the caller takes the class-table DP below).  `ldgt(k)` returns the genotype byte of row k.
+// ---------------------------------------------------------------------------------------------
+template <typename LoadU32, typename LoadPos, typename LoadGt>
+SSTAR_HD_COLD bool walk_dp_unit_general(LoadU32 ld, LoadPos ldpos, LoadGt ldgt, const uint32_t *carried, int32_t Tp, int t,
+                                        int32_t lo, int32_t hi, int32_t bonus, int32_t penalty, int32_t max_mm,
+                                        int &n_out, int64_t &score_out) {
+    constexpr int64_t NEG = Sentinel<int64_t>::NEG, THR = Sentinel<int64_t>::THR;
+    int64_t A[kMaxClasses], B[kMaxClasses];
+    int32_t val[kMaxClasses];
+    int64_t wait_p[kRingSlots], wait_v[kRingSlots];
+    int8_t wait_c[kRingSlots];
+    int K = 0, q = 0, head = 0, n = 0;
+    int64_t top = NEG;
+    const int64_t p0 = ldpos(lo);
+    const int gi0 = lo >> 5, gi1 = (hi - 1) >> 5;
+    for (int gi = gi0; gi <= gi1; ++gi) {
+        uint32_t c = ld(carried + (size_t)gi * Tp + t);
+        if (gi == gi0) c &= 0xffffffffu << (lo & 31);
+        if (gi == gi1) c &= 0xffffffffu >> (31 - ((hi - 1) & 31));
+        while (c) {
+            const int b = ctz32(c);
+            c &= c - 1;
+            const int32_t row = (gi << 5) + b;
+            const int64_t p = ldpos(row) - p0;
+            const int32_t g = (int32_t)ldgt(row);
+            while (q > 0) {  // sites >= 10 bp behind become eligible predecessors
+                const int64_t pi = wait_p[head];
+                if (p - pi < kMinPairDistance) break;
+                const int ci = wait_c[head];
+                const int64_t v = wait_v[head];
+                A[ci] = imax(A[ci], v - pi);
+                B[ci] = imax(B[ci], v);
+                head = (head + 1) & (kRingSlots - 1);
+                --q;
+            }
+            int idx = -1;
+            for (int i = 0; i < K; ++i)
+                if (val[i] == g) idx = i;
+            if (idx < 0) {
+                if (K == kMaxClasses) return false;
+                idx = K++;
+                val[idx] = g; A[idx] = NEG; B[idx] = NEG;
+            }
+            int64_t other = NEG;
+            for (int i = 0; i < K; ++i) {
+                const int32_t d = val[i] > g ? val[i] - g : g - val[i];
+                if (i != idx && d <= max_mm) other = imax(other, B[i]);
+            }
+            const int64_t m = imax(A[idx] + (p + bonus), other + penalty);
+            top = imax(top, m);
+            const int tail = (head + q) & (kRingSlots - 1);
+            wait_p[tail] = p;
+            wait_v[tail] = imax(m, (int64_t)0);
+            wait_c[tail] = (int8_t)idx;
+            ++q;
+            ++n;
+        }
+    }
+    n_out = n;
+    score_out = (n <= 2 || top <= THR) ? kNegInf64 : top;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Class-table DP: the same prefix-max recurrence with the running maxima in two tables indexed
+// DIRECTLY by the genotype byte (256 entries each, caller-provided memory: shared memory on the
+// device) -- any number of distinct genotype values, any window length, bounded state.  Sites are
+// fed one at a time in ascending position (`site`), so the caller can stream a window of any size.
+// The last resort of the fused kernel (a unit with more than kMaxClasses values, a window larger
+// than its tile); int64 throughout.
+// ---------------------------------------------------------------------------------------------
+constexpr int kClassTableSize = 256;
+
+struct StreamDP {
+    int64_t *A, *B;            // [kClassTableSize], index = genotype byte + 128
+    int64_t *wait_p, *wait_v;  // [kRingSlots]
+    int32_t *wait_g;           // [kRingSlots]
+    int head, q, n;
+    int64_t top;
+
+    SSTAR_HD void begin() { head = 0; q = 0; n = 0; top = Sentinel<int64_t>::NEG; }  // (tables reset by the caller)
+
+    SSTAR_HD void site(int64_t p, int32_t g, int32_t bonus, int32_t penalty, int32_t max_mm) {
+        constexpr int64_t NEG = Sentinel<int64_t>::NEG;
+        while (q > 0) {
+            const int64_t pi = wait_p[head];
+            if (p - pi < kMinPairDistance) break;
+            const int ci = wait_g[head] + 128;
+            const int64_t v = wait_v[head];
+            A[ci] = imax(A[ci], v - pi);
+            B[ci] = imax(B[ci], v);
+            head = (head + 1) & (kRingSlots - 1);
+            --q;
+        }
+        int64_t other = NEG;
+        const int64_t g_lo = imax((int64_t)g - (int64_t)imax(max_mm, (int32_t)0), (int64_t)-128);
+        const int64_t g_hi = -imax(-((int64_t)g + (int64_t)imax(max_mm, (int32_t)0)), (int64_t)-127);
+        for (int64_t x = g_lo; x <= g_hi; ++x)
+            if (x != g) other = imax(other, B[x + 128]);
+        const int64_t m = imax(A[g + 128] + (p + bonus), other + penalty);
+        top = imax(top, m);
+        const int tail = (head + q) & (kRingSlots - 1);
+        wait_p[tail] = p;
+        wait_v[tail] = imax(m, (int64_t)0);
+        wait_g[tail] = g;
+        ++q;
+        ++n;
+    }
+
+    SSTAR_HD int64_t result() const {
+        return (n <= 2 || top <= Sentinel<int64_t>::THR) ? kNegInf64 : top;
+    }
+};
+
 }  // namespace sstar

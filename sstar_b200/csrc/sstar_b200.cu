@@ -26,6 +26,7 @@
 #include "ingest_kernels.cuh"
 #include "match_kernels.cuh"
 #include "snpset_kernels.cuh"
+#include "fused_kernels.cuh"
 
 using namespace sstar;
 
@@ -385,6 +386,105 @@ int launch_score(cudaStream_t st, const ScoreCall &c, const WsLayout &L, int32_t
     return 0;
 }
 
+// The one-launch path (fused_kernels.cuh).  Returns 1 when it scored the call, 0 when the shapes do
+// not qualify (the caller then takes the pack -> score launches), a negative code on error.
+int launch_fused(cudaStream_t st, const int8_t *d_ref, const int8_t *d_tgt, const int32_t *d_pos, int64_t V, int32_t R,
+                 int32_t T, const int32_t *d_ws, const int32_t *d_we, const int32_t *d_seg, int32_t fixed_s,
+                 int32_t fixed_e, int32_t W, int32_t bonus, int32_t max_mm, int32_t penalty, int64_t *d_score,
+                 int32_t *d_nsnp, int32_t hint, int32_t flags) {
+    if (flags & SSTAR_B200_FLAG_NO_FUSED) return 0;
+    if (T > 128 || W <= 0) return 0;  // (a window's columns must fit one CTA: T <= the replicate kernel's 256 threads)
+    const bool force = (flags & SSTAR_B200_FLAG_FORCE_FUSED) != 0;
+    const bool disjoint = d_seg != nullptr;  // replicates: no row is shared by two windows
+    if (!force) {
+        if (hint <= 0) return 0;  // the tile is sized by the largest window
+        // overlapping windows re-read rows through the L2: only while the whole input sits there
+        static const int64_t max_bytes = [] {
+            const char *e = getenv("SSTAR_B200_FUSED_MAX_MB");
+            return (int64_t)(e ? atoll(e) : 16) << 20;
+        }();
+        if (!disjoint && V * ((int64_t)R + T) > max_bytes) return 0;
+    }
+    const int32_t tc = (T + 31) / 32 * 32;
+    const int64_t rows1 = hint > 0 ? hint : 256;
+    FusedArgs a = {};
+    a.tc = tc;
+    auto bytes_for = [&](int64_t c) {
+        return align_up((size_t)c * 32 * R + 32, 16) + align_up((size_t)c * 32 * T + 32, 16) + (size_t)c * 32 * 4 +
+               2 * (size_t)c * tc * 4 + 2 * (size_t)c * 4 + (size_t)c * 32 + 16 + 4 * (size_t)kFusedListCap * 4;
+    };
+    size_t limit = (size_t)100 << 10;  // two CTAs per SM at least
+    int64_t cap = 0;
+    unsigned grid = 1;
+    if (disjoint) {
+        // a CTA per `wg` consecutive replicates (as many as it scores at a time), their rows side by side
+        int32_t wg = kFusedRepThreads / T;
+        if (wg > kFusedMaxSlots) wg = kFusedMaxSlots;
+        if (wg < 1) wg = 1;
+        for (;; wg = wg / 2) {
+            cap = (rows1 * wg + 31) / 32 + 1;  // + the range's phase inside its first group
+            if (bytes_for(cap) <= limit || wg == 1) break;
+        }
+        a.wg = wg;
+        grid = (unsigned)((W + wg - 1) / wg);
+    } else {
+        // a CTA per S home rows; its tile adds the largest window's rows behind them
+        // S: one CTA per SM when the problem allows (a single wave, every SM busy from the first
+        // instruction), but no more windows per CTA than it scores at a time
+        static const int32_t home_env = [] {
+            const char *e = getenv("SSTAR_B200_FUSED_S");
+            const int v = e ? atoi(e) : 0;
+            return v >= 32 ? v / 32 * 32 : 0;
+        }();
+        int32_t S = home_env;
+        if (S == 0) {
+            const int nsm = num_sms();
+            S = (int32_t)(((V + nsm - 1) / nsm + 31) / 32 * 32);
+            int32_t slots = kFusedThreads / T;
+            if (slots > kFusedMaxSlots) slots = kFusedMaxSlots;
+            const int64_t s_max = V > 0 ? (V * slots / (W > 0 ? W : 1)) / 32 * 32 : 32;  // ~`slots` windows per CTA
+            if (S > s_max) S = (int32_t)s_max;
+            if (S < 64) S = 64;
+            if (S > 1024) S = 1024;
+        }
+        limit = (size_t)160 << 10;  // one 512-thread CTA per SM is the plan
+        for (;; S = (S / 2 + 31) / 32 * 32) {
+            cap = (S + rows1 + 31) / 32;
+            if (bytes_for(cap) <= limit || S == 32) break;
+        }
+        a.home_rows = S;
+        a.wg = 0;
+        grid = (unsigned)(V > 0 ? (V + S - 1) / S : 1);
+        if ((int64_t)grid * W > ((int64_t)64 << 20) && !force) return 0;  // the list scan is O(W) per CTA
+    }
+    if (bytes_for(cap) > limit) {
+        if (!force) return 0;
+        while (cap > 2 && bytes_for(cap) > limit) --cap;  // forced: windows beyond the tile are streamed
+        if (!disjoint && cap * 32 < a.home_rows) { a.home_rows = (int32_t)(cap * 32); grid = (unsigned)(V > 0 ? (V + a.home_rows - 1) / a.home_rows : 1); }
+        if (bytes_for(cap) > ((size_t)200 << 10)) return 0;
+    }
+    size_t smem = bytes_for(cap);
+    a.cap_groups = (int32_t)cap;
+    a.ref_tile_bytes = (uint32_t)align_up((size_t)cap * 32 * R + 32, 16);
+    a.tgt_tile_bytes = (uint32_t)align_up((size_t)cap * 32 * T + 32, 16);
+    if (smem < kFusedStreamMinBytes) smem = kFusedStreamMinBytes;
+    smem = align_up(smem, 16);
+    a.smem_bytes = (uint32_t)smem;
+    a.ref = d_ref; a.tgt = d_tgt; a.pos = d_pos; a.win_start = d_ws; a.win_end = d_we; a.seg = d_seg;
+    a.fixed_start = fixed_s; a.fixed_end = fixed_e;
+    a.V = (int32_t)V; a.R = R; a.T = T; a.W = W;
+    a.bonus = bonus; a.max_mm = max_mm; a.penalty = penalty;
+    a.score = d_score; a.nsnp = d_nsnp;
+    static SmemGrant fused_grant, rep_grant;
+    cudaError_t e = disjoint ? grant_smem(rep_grant, fused_score_rep_kernel, smem)
+                             : grant_smem(fused_grant, fused_score_kernel, smem);
+    if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaFuncSetAttribute(fused): %s", cudaGetErrorString(e));
+    e = disjoint ? launch(fused_score_rep_kernel, grid, kFusedRepThreads, smem, st, false, a)
+                 : launch(fused_score_kernel, grid, kFusedThreads, smem, st, false, a);
+    if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "fused_score_kernel launch: %s", cudaGetErrorString(e));
+    return 1;
+}
+
 int check_common(int device, int64_t V, int32_t R, int32_t T, int32_t W, const void *ws,
                  size_t ws_bytes, const sstar_b200_options *opts, WsLayout *L, int *algo,
                  bool pack_only = false) {
@@ -411,9 +511,14 @@ int run_pipeline(int device, cudaStream_t st, bool do_pack, const int8_t *d_ref,
                  const int32_t *d_pos, int64_t V, int32_t R, int32_t T, const int32_t *d_ws,
                  const int32_t *d_we, const int32_t *d_seg, int32_t fixed_s, int32_t fixed_e, int32_t W,
                  int32_t bonus, int32_t max_mm, int32_t penalty, int64_t *d_score, int32_t *d_nsnp,
-                 uint8_t *ws, const WsLayout &L, int algo, int32_t max_win_variants) {
+                 uint8_t *ws, const WsLayout &L, int algo, int32_t max_win_variants, int32_t flags = 0) {
     DeviceGuard guard(device);
     if (guard.err != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(guard.err));
+    if (do_pack && algo == SSTAR_B200_ALGO_AUTO) {  // small problems, replicate batches: one launch does it all
+        const int frc = launch_fused(st, d_ref, d_tgt, d_pos, V, R, T, d_ws, d_we, d_seg, fixed_s, fixed_e, W, bonus, max_mm,
+                                     penalty, d_score, d_nsnp, max_win_variants, flags);
+        if (frc != 0) return frc < 0 ? frc : 0;
+    }
     int rc = launch_prep(st, 0, do_pack ? L.G : 0, d_ref, d_tgt, V, R, T, d_pos, d_ws, d_we, d_seg, fixed_s, fixed_e, W,
                          ws, L);
     if (rc) return rc;
@@ -488,7 +593,8 @@ int sstar_b200_score_windows_ex(int device, void *stream, const int8_t *d_ref_gt
     if (V > 0 && (!d_pos || !d_tgt_gt || !d_ref_gt)) return fail(SSTAR_B200_EINVAL, "null input pointer%s");
     return run_pipeline(device, (cudaStream_t)stream, true, d_ref_gt, d_tgt_gt, d_pos, V, R, T, d_win_start,
                         d_win_end, nullptr, 0, 0, W, match_bonus, max_mismatch, mismatch_penalty, d_score,
-                        d_nsnp, (uint8_t *)d_workspace, L, algo, opts ? opts->max_win_variants : 0);
+                        d_nsnp, (uint8_t *)d_workspace, L, algo, opts ? opts->max_win_variants : 0,
+                        opts ? opts->flags : 0);
 }
 
 int sstar_b200_score_windows(int device, void *stream, const int8_t *d_ref_gt, const int8_t *d_tgt_gt,
@@ -515,7 +621,8 @@ int sstar_b200_score_replicates(int device, void *stream, const int8_t *d_ref_gt
     if (V > 0 && (!d_pos || !d_tgt_gt || !d_ref_gt)) return fail(SSTAR_B200_EINVAL, "null input pointer%s");
     return run_pipeline(device, (cudaStream_t)stream, true, d_ref_gt, d_tgt_gt, d_pos, V, R, T, nullptr, nullptr,
                         d_rep_offset, win_start, win_end, Nrep, match_bonus, max_mismatch, mismatch_penalty,
-                        d_score, d_nsnp, (uint8_t *)d_workspace, L, algo, opts ? opts->max_win_variants : 0);
+                        d_score, d_nsnp, (uint8_t *)d_workspace, L, algo, opts ? opts->max_win_variants : 0,
+                        opts ? opts->flags : 0);
 }
 
 }  // extern "C"
@@ -654,7 +761,8 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
         }
         rc = run_pipeline(device, st, true, d_ref, d_tgt, d_pos, V, R, T, (const int32_t *)(d + h.off_ws),
                           (const int32_t *)(d + h.off_we), nullptr, 0, 0, W, match_bonus, max_mismatch,
-                          mismatch_penalty, (int64_t *)(d + h.off_score), (int32_t *)(d + h.off_nsnp), ws, L, algo, hint);
+                          mismatch_penalty, (int64_t *)(d + h.off_score), (int32_t *)(d + h.off_nsnp), ws, L, algo, hint,
+                          opts ? opts->flags : 0);
         if (rc) return rc;
         if (W > 0) {
             CUDA_TRY(cudaMemcpyAsync(h_score, d + h.off_score, (size_t)W * T * 8, cudaMemcpyDeviceToHost, st));
@@ -1092,3 +1200,11 @@ extern "C" int sstar_b200_snp_set_fill(int device, void *stream, const int8_t *d
                            mismatch_penalty, nullptr, nullptr, d_set_off, d_set_pos, capacity,
                            (uint8_t *)d_workspace, L, S, opts ? opts->max_win_variants : 0);
 }
+
+#ifdef SSTAR_B200_FUSED_TIMING
+// debug build only (tools/exp_fused_timing.py): the fused kernel's phase stamps, [4096][8] u64
+extern "C" int sstar_b200_debug_fused_stamps(unsigned long long *h_out) {
+    CUDA_TRY(cudaMemcpyFromSymbol(h_out, sstar::g_fused_stamps, sizeof(unsigned long long) * 4096 * 8));
+    return 0;
+}
+#endif

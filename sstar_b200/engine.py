@@ -104,7 +104,7 @@ class ScoreEngine:
 
     # ------------------------------------------------------------------ device API
     def score_device(self, ref_d, tgt_d, pos_d, ws_d, we_d, match_bonus=5000, max_mismatch=5,
-                     mismatch_penalty=-10000, algo="auto", max_win_variants=0, out=None, stream=None):
+                     mismatch_penalty=-10000, algo="auto", max_win_variants=0, out=None, stream=None, flags=0):
         """All inputs are device tensors (int8 [V,R], int8 [V,T], int32 [V], int32 [W] x2)."""
         torch = self.torch
         V, R = ref_d.shape
@@ -118,7 +118,7 @@ class ScoreEngine:
         else:
             score, nsnp = out
         ws = self.workspace(V, R, T, W, max_win_variants)
-        opts = _cabi.Options(algo=_cabi.ALGOS[algo], max_win_variants=int(max_win_variants))
+        opts = _cabi.Options(algo=_cabi.ALGOS[algo], max_win_variants=int(max_win_variants), flags=int(flags))
         rc = self.lib.sstar_b200_score_windows_ex(
             self.device, self._stream_ptr(stream), ref_d.data_ptr(), tgt_d.data_ptr(), pos_d.data_ptr(),
             V, R, T, ws_d.data_ptr(), we_d.data_ptr(), W, int(match_bonus), int(max_mismatch),
@@ -216,7 +216,7 @@ class ScoreEngine:
 
     def score_replicates_device(self, ref_d, tgt_d, pos_d, rep_off_d, win_start, win_end,
                                 match_bonus=5000, max_mismatch=5, mismatch_penalty=-10000,
-                                algo="auto", max_win_variants=0, stream=None, out=None):
+                                algo="auto", max_win_variants=0, stream=None, out=None, flags=0):
         torch = self.torch
         V, R = ref_d.shape
         T = tgt_d.shape[1]
@@ -227,7 +227,7 @@ class ScoreEngine:
         else:
             score, nsnp = out
         ws = self.workspace(V, R, T, N, max_win_variants)
-        opts = _cabi.Options(algo=_cabi.ALGOS[algo], max_win_variants=int(max_win_variants))
+        opts = _cabi.Options(algo=_cabi.ALGOS[algo], max_win_variants=int(max_win_variants), flags=int(flags))
         rc = self.lib.sstar_b200_score_replicates(
             self.device, self._stream_ptr(stream), ref_d.data_ptr(), tgt_d.data_ptr(), pos_d.data_ptr(),
             V, R, T, rep_off_d.data_ptr(), N, int(win_start), int(win_end), int(match_bonus),
@@ -238,7 +238,7 @@ class ScoreEngine:
         return score, nsnp
 
     def plan_device(self, ref_d, tgt_d, pos_d, ws_d, we_d, match_bonus=5000, max_mismatch=5,
-                    mismatch_penalty=-10000, algo="auto", max_win_variants=0, out=None):
+                    mismatch_penalty=-10000, algo="auto", max_win_variants=0, out=None, flags=0):
         """Capture one whole scoring pass over fixed device buffers into a CUDA graph.
 
         Returns a :class:`ScorePlan`; ``plan.run()`` replays pack -> bounds -> DP with ONE host
@@ -252,7 +252,7 @@ class ScoreEngine:
             out = (torch.empty((W, T), dtype=torch.int64, device=self.tdev),
                    torch.empty((W, T), dtype=torch.int32, device=self.tdev))
         kw = dict(match_bonus=match_bonus, max_mismatch=max_mismatch, mismatch_penalty=mismatch_penalty,
-                  algo=algo, max_win_variants=max_win_variants, out=out)
+                  algo=algo, max_win_variants=max_win_variants, out=out, flags=flags)
         with torch.cuda.device(self.tdev):
             side = torch.cuda.Stream(self.tdev)
             side.wait_stream(torch.cuda.current_stream(self.tdev))
@@ -267,7 +267,8 @@ class ScoreEngine:
         return ScorePlan(graph, out[0], out[1], launches, (ref_d, tgt_d, pos_d, ws_d, we_d, self._dev.get("ws")))
 
     def plan_replicates_device(self, ref_d, tgt_d, pos_d, rep_off_d, win_start, win_end, match_bonus=5000,
-                               max_mismatch=5, mismatch_penalty=-10000, algo="auto", max_win_variants=0, out=None):
+                               max_mismatch=5, mismatch_penalty=-10000, algo="auto", max_win_variants=0, out=None,
+                               flags=0):
         """:meth:`plan_device` for a replicate batch (``sstar_b200_score_replicates``)."""
         torch = self.torch
         N, T = rep_off_d.shape[0] - 1, tgt_d.shape[1]
@@ -275,7 +276,7 @@ class ScoreEngine:
             out = (torch.empty((N, T), dtype=torch.int64, device=self.tdev),
                    torch.empty((N, T), dtype=torch.int32, device=self.tdev))
         args = (ref_d, tgt_d, pos_d, rep_off_d, win_start, win_end, match_bonus, max_mismatch, mismatch_penalty)
-        kw = dict(algo=algo, max_win_variants=max_win_variants, out=out)
+        kw = dict(algo=algo, max_win_variants=max_win_variants, out=out, flags=flags)
         with torch.cuda.device(self.tdev):
             side = torch.cuda.Stream(self.tdev)
             side.wait_stream(torch.cuda.current_stream(self.tdev))

@@ -190,3 +190,90 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
     }
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Scalar emulation of the fused kernel's unit paths (fused_kernels.cuh): the clean walk DP, the
+// general walk DP (<= kMaxClasses genotype values) and the class-table streaming DP behind it.
+// path: 0 empty window, 1 walk int32, 2 walk int64, 3 general walk, 4 class-table stream.
+// force_stream != 0 sends every unit through the streaming DP (the oversize-window route).
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct HostGt {
+    const int8_t *tgt; int32_t T, t;
+    int operator()(int32_t k) const { return (int)tgt[(size_t)k * T + t]; }
+};
+}  // namespace
+
+extern "C" int emul_fused_windows(const int8_t *ref, const int8_t *tgt, const int32_t *pos, int64_t V, int32_t R,
+                                  int32_t T, const int32_t *ws, const int32_t *we, int32_t W, int32_t bonus,
+                                  int32_t max_mm, int32_t penalty, int32_t force_stream, int64_t *score, int32_t *nsnp,
+                                  int32_t *path) {
+    const int64_t G = (V + 31) / 32;
+    const int32_t Tp = (T + 31) / 32 * 32;
+    std::vector<uint32_t> absent(G > 0 ? G : 1, 0), exotic(G > 0 ? G : 1, 0);
+    std::vector<uint32_t> carried((size_t)(G > 0 ? G : 1) * Tp, 0), two((size_t)(G > 0 ? G : 1) * Tp, 0);
+    for (int64_t k = 0; k < V; ++k) {
+        int sum = 0;
+        for (int r = 0; r < R; ++r) sum += ref[k * R + r];
+        if (sum != 0) continue;
+        absent[k >> 5] |= 1u << (k & 31);
+        for (int t = 0; t < T; ++t) {
+            const int b = tgt[k * T + t];
+            if (b != 0) carried[(size_t)(k >> 5) * Tp + t] |= 1u << (k & 31);
+            if (b == 2) two[(size_t)(k >> 5) * Tp + t] |= 1u << (k & 31);
+            if ((unsigned)b > 2u) exotic[k >> 5] = 1;
+        }
+    }
+    std::vector<int64_t> A(kClassTableSize), B(kClassTableSize), wp(kRingSlots), wv(kRingSlots);
+    std::vector<int32_t> wgt(kRingSlots);
+    for (int w = 0; w < W; ++w) {
+        const int32_t lo = lower_bound_i64(pos, V, ws[w]);
+        const int32_t hi = std::max(lo, lower_bound_i64(pos, V, (int64_t)we[w] + 1));
+        int32_t na = 0; uint32_t ex = 0;
+        if (hi > lo)
+            for (int gi = lo >> 5; gi <= ((hi - 1) >> 5); ++gi) {
+                uint32_t rm = 0xffffffffu;
+                if (gi == (lo >> 5)) rm &= 0xffffffffu << (lo & 31);
+                if (gi == ((hi - 1) >> 5)) rm &= 0xffffffffu >> (31 - ((hi - 1) & 31));
+                na += __builtin_popcount(absent[gi] & rm);
+                ex |= exotic[gi];
+            }
+        for (int t = 0; t < T; ++t) {
+            int n = 0; int64_t sc = kNegInf64; int pth = 0;
+            bool done = hi <= lo;
+            if (!done && !force_stream) {
+                if (ex) {
+                    done = walk_dp_unit_general(HostLd(), HostPos{pos}, HostGt{tgt, T, t}, carried.data(), Tp, t, lo, hi, bonus,
+                                                penalty, max_mm, n, sc);
+                    pth = 3;
+                } else {
+                    const int64_t span = (int64_t)pos[hi - 1] - (int64_t)pos[lo];
+                    if (score_bound(span, hi - lo, bonus, penalty) < kSmallBound) {
+                        walk_dp_unit_reg<int32_t>(HostLd(), HostPos{pos}, carried.data(), two.data(), Tp, t, lo, hi, bonus, penalty, max_mm, n, sc);
+                        pth = 1;
+                    } else {
+                        walk_dp_unit_reg<int64_t>(HostLd(), HostPos{pos}, carried.data(), two.data(), Tp, t, lo, hi, bonus, penalty, max_mm, n, sc);
+                        pth = 2;
+                    }
+                    done = true;
+                }
+            }
+            if (!done) {  // class tables indexed by the genotype byte, rows streamed in order
+                StreamDP dp;
+                dp.A = A.data(); dp.B = B.data(); dp.wait_p = wp.data(); dp.wait_v = wv.data(); dp.wait_g = wgt.data();
+                std::fill(A.begin(), A.end(), Sentinel<int64_t>::NEG);
+                std::fill(B.begin(), B.end(), Sentinel<int64_t>::NEG);
+                dp.begin();
+                const int64_t p0 = pos[lo];
+                for (int32_t k = lo; k < hi; ++k) {
+                    if (!((absent[k >> 5] >> (k & 31)) & 1u)) continue;
+                    const int g = tgt[(size_t)k * T + t];
+                    if (g != 0) dp.site((int64_t)pos[k] - p0, g, bonus, penalty, max_mm);
+                }
+                n = dp.n; sc = dp.result(); pth = 4;
+            }
+            score[(size_t)w * T + t] = sc; nsnp[(size_t)w * T + t] = (hi - lo) - na + n; path[(size_t)w * T + t] = pth;
+        }
+    }
+    return 0;
+}

@@ -153,3 +153,61 @@ def test_replicate_style_disjoint_windows(emul):
     we = ws + 49_999
     path, _ = check(emul, ref, tgt, pos, ws, we, wg=8, L=512, words_cap=64)
     assert (path[path > 0] == 1).any()
+
+
+# ---- the fused kernel's unit paths (fused_kernels.cuh), scalar emulation ----------------------
+@pytest.fixture(scope="module")
+def emul_fused(emul):
+    lib = ctypes.CDLL(LIB)
+    lib.emul_fused_windows.restype = ctypes.c_int
+    lib.emul_fused_windows.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                                               ctypes.c_void_p, ctypes.c_void_p] + \
+        [ctypes.c_int32] * 5 + [ctypes.c_void_p] * 3
+
+    def run(ref, tgt, pos, ws, we, params=(5000, 5, -10000), force_stream=0):
+        ref = np.ascontiguousarray(ref, dtype=np.int8)
+        tgt = np.ascontiguousarray(tgt, dtype=np.int8)
+        pos = np.ascontiguousarray(pos, dtype=np.int32)
+        ws = np.ascontiguousarray(ws, dtype=np.int32)
+        we = np.ascontiguousarray(we, dtype=np.int32)
+        V, R = ref.shape
+        T, W = tgt.shape[1], len(ws)
+        score = np.empty((W, T), np.int64)
+        nsnp = np.empty((W, T), np.int32)
+        path = np.zeros((W, T), np.int32)
+        assert lib.emul_fused_windows(ref.ctypes.data, tgt.ctypes.data, pos.ctypes.data, V, R, T, ws.ctypes.data,
+                                      we.ctypes.data, W, *params, force_stream, score.ctypes.data, nsnp.ctypes.data,
+                                      path.ctypes.data) == 0
+        so, no = c_oracle.score_windows(ref, tgt, pos, ws, we, *params)
+        assert np.array_equal(score, so) and np.array_equal(nsnp, no)
+        return path
+    return run
+
+
+@pytest.mark.parametrize("params", [(5000, 5, -10000), (5000, 0, -10000), (1, 1, 0), (123, 4, -7), (5000, 300, -10000),
+                                    (2 ** 27, 2, -(2 ** 27))])
+def test_fused_unit_paths_match_oracle(emul_fused, params):
+    rng = np.random.default_rng(abs(hash(params)) % 2 ** 31)
+    ref, tgt, pos = synth_chromosome(500_000, 12, 9, False, seed=41)
+    ws, we = regular_windows(pos, 50_000, 10_000)
+    assert set(np.unique(emul_fused(ref, tgt, pos, ws, we, params))) <= {0, 1, 2}
+    assert set(np.unique(emul_fused(ref, tgt, pos, ws, we, params, force_stream=1))) <= {0, 4}
+    # missing calls / multi-allelic dosages: a few genotype values -> the general walk
+    few = tgt.copy()
+    few[rng.random(few.shape) < 0.03] = -1
+    few[rng.random(few.shape) < 0.01] = 3
+    p = emul_fused(ref, few, pos, ws, we, params)
+    assert 3 in p and 4 not in p
+    emul_fused(ref, few, pos, ws, we, params, force_stream=1)
+    # many genotype values per unit -> the class tables, incl. the int8 extremes and crowded sites
+    many = tgt.copy().astype(np.int16)
+    hit = rng.random(many.shape) < 0.4
+    many[hit] = rng.integers(-128, 128, size=int(hit.sum()))
+    many = many.astype(np.int8)
+    dense_pos = np.sort(rng.choice(np.arange(1, 4 * len(pos)), size=len(pos), replace=False)).astype(np.int32)
+    dws, dwe = regular_windows(dense_pos, 500, 100)
+    p = emul_fused(np.zeros_like(ref), many, dense_pos, dws[:200], dwe[:200], params)
+    assert 4 in p
+    # clean genotypes on crowded positions (several sites inside 9 bp): the parked-site ring of the register walk
+    p = emul_fused(np.zeros_like(ref), tgt, dense_pos, dws[:300], dwe[:300], params)
+    assert set(np.unique(p)) <= {0, 1, 2}

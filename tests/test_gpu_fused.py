@@ -1,0 +1,182 @@
+"""GPU parity of the one-launch path (csrc/fused_kernels.cuh) through the C-ABI device entry
+points: forced on every shape it accepts, against the C oracle and the golden fixtures, and
+against the pack -> score launches (which must give the same tables).  Bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import __graft_entry__ as g
+    g.build()
+    from sstar_b200.engine import get_engine
+    return get_engine(0)
+
+
+def _score(eng, ref, tgt, pos, ws, we, params=(5000, 5, -10000), hint=None, fused=True, offset=0):
+    """Device entry point; ``offset`` rows of padding in front make the base pointers unaligned."""
+    import torch
+    from sstar_b200 import _cabi
+    from sstar_b200.engine import max_window_variants
+    dev = eng.tdev
+    ref = np.ascontiguousarray(ref, dtype=np.int8)
+    tgt = np.ascontiguousarray(tgt, dtype=np.int8)
+    pos = np.ascontiguousarray(pos, dtype=np.int32)
+    ws = np.ascontiguousarray(ws, dtype=np.int32)
+    we = np.ascontiguousarray(we, dtype=np.int32)
+
+    def up(a):
+        if offset == 0 or a.ndim == 1:
+            return torch.from_numpy(a).to(dev)
+        pad = torch.zeros((offset,) + a.shape[1:], dtype=torch.int8, device=dev)
+        return torch.cat([pad, torch.from_numpy(a).to(dev)])[offset:]
+
+    if hint is None:
+        hint = max_window_variants(pos, ws, we)
+    flags = _cabi.FLAG_FORCE_FUSED if fused else _cabi.FLAG_NO_FUSED
+    s, n = eng.score_device(up(ref), up(tgt), torch.from_numpy(pos).to(dev), torch.from_numpy(ws).to(dev),
+                            torch.from_numpy(we).to(dev), *params, max_win_variants=hint, flags=flags)
+    torch.cuda.synchronize()
+    assert eng.launches == (1 if fused and tgt.shape[1] <= 128 and len(ws) else eng.launches)
+    return s.cpu().numpy(), n.cpu().numpy()
+
+
+def _check(eng, ref, tgt, pos, ws, we, params=(5000, 5, -10000), **kw):
+    so, no = c_oracle.score_windows(ref, tgt, pos, ws, we, *params)
+    s, n = _score(eng, ref, tgt, pos, ws, we, params, **kw)
+    assert np.array_equal(s, so), np.argwhere(s != so)[:5]
+    assert np.array_equal(n, no), np.argwhere(n != no)[:5]
+    return so
+
+
+def test_fuzz_golden_single_windows(eng, fuzz_cases):
+    """The reference-generated single-window cases (tests/golden/make_golden.py), each a fused call."""
+    for c in fuzz_cases:
+        if len(c["pos"]) == 0:
+            continue
+        ws = np.array([int(c["pos"].min())], dtype=np.int32)
+        we = np.array([int(c["pos"].max())], dtype=np.int32)
+        s, n = _score(eng, c["ref"], c["tgt"], c["pos"], ws, we, c["params"])
+        assert np.array_equal(s[0], c["score"]) and np.array_equal(n[0], c["nsnp"])
+
+
+@pytest.mark.parametrize("n_ref,n_tgt,phased,length", [
+    (100, 50, False, 1_500_000),   # C2 shape: 4 windows per CTA
+    (5, 10, False, 600_000),       # tutorial shape: narrow reference panel, 8 windows per CTA
+    (20, 33, True, 800_000),       # 66 columns -> 96 column slots, 2 windows per CTA
+    (3, 64, True, 300_000),        # T = 128: one window per CTA
+    (40, 16, True, 700_000),       # T = 32 exactly
+    (300, 60, False, 400_000),     # wide reference panel: the tile limit cuts the windows per CTA
+])
+def test_synthetic_shapes(eng, n_ref, n_tgt, phased, length):
+    from sstar_b200.synth import regular_windows, synth_chromosome
+    ref, tgt, pos = synth_chromosome(length, n_ref, n_tgt, phased, seed=2000 + n_ref)
+    ws, we = regular_windows(pos, 50_000, 10_000)
+    so = _check(eng, ref, tgt, pos, ws, we)
+    s2, n2 = _score(eng, ref, tgt, pos, ws, we, fused=False)   # the pack -> score launches agree
+    assert np.array_equal(s2, so)
+    _check(eng, ref, tgt, pos, ws, we, offset=3)               # unaligned bases: spans staged by vector loads
+    _check(eng, ref[:-5], tgt[:-5], pos[:-5], ws, we)          # V not a multiple of 32: ragged last group
+
+
+@pytest.mark.parametrize("params", [(5000, 5, -10000), (5000, 0, -10000), (1, 1, 0), (123, 4, -7),
+                                    (2 ** 27, 2, -(2 ** 27))])
+def test_parameters_missing_calls_and_many_genotype_values(eng, params):
+    from sstar_b200.synth import regular_windows, synth_chromosome
+    rng = np.random.default_rng(7)
+    ref, tgt, pos = synth_chromosome(500_000, 12, 9, False, seed=41)
+    ws, we = regular_windows(pos, 50_000, 10_000)
+    _check(eng, ref, tgt, pos, ws, we, params)
+    few = tgt.copy()
+    few[rng.random(few.shape) < 0.03] = -1   # missing calls: negative dosages (utils.py:305-306)
+    few[rng.random(few.shape) < 0.01] = 3
+    miss_ref = ref.copy()
+    miss_ref[rng.random(ref.shape) < 0.01] = -1
+    miss_ref[rng.random(ref.shape) < 0.01] = 1  # +1 / -1 can cancel in the signed row sum (sstar.py:87)
+    _check(eng, miss_ref, few, pos, ws, we, params)
+    # more than 8 genotype values per unit: the class-table streaming DP inside the same kernel
+    many = tgt.astype(np.int16)
+    hit = rng.random(many.shape) < 0.4
+    many[hit] = rng.integers(-128, 128, size=int(hit.sum()))
+    dense = np.sort(rng.choice(np.arange(1, 4 * len(pos)), size=len(pos), replace=False)).astype(np.int32)
+    dws, dwe = regular_windows(dense, 500, 100)
+    _check(eng, np.zeros_like(ref), many.astype(np.int8), dense, dws[:300], dwe[:300], params)
+
+
+def test_windows_larger_than_the_tile_are_streamed(eng):
+    """An understated size hint (or a tile cut by the shared-memory limit) is safe: the CTA streams
+    such windows from global memory through the class-table DP."""
+    from sstar_b200.synth import regular_windows, synth_chromosome
+    ref, tgt, pos = synth_chromosome(600_000, 30, 20, False, seed=77)
+    ws, we = regular_windows(pos, 50_000, 10_000)
+    for hint in (1, 8, 40, 150):
+        _check(eng, ref, tgt, pos, ws, we, hint=hint)
+    # one window over everything next to normal ones, a 2,000-column-free... wide rows: tile rows < window rows
+    ws2 = np.concatenate([ws[:5], [1], ws[5:9]]).astype(np.int32)
+    we2 = np.concatenate([we[:5], [int(pos[-1])], we[5:9]]).astype(np.int32)
+    _check(eng, ref, tgt, pos, ws2, we2, hint=64)
+    rng = np.random.default_rng(3)
+    tgt_m = tgt.copy()
+    tgt_m[rng.random(tgt.shape) < 0.02] = -2
+    _check(eng, ref, tgt_m, pos, ws2, we2, hint=16)
+
+
+def test_edge_windows_and_tiny_inputs(eng):
+    rng = np.random.default_rng(11)
+    pos = np.array([5, 100, 104, 113, 2000, 2001, 2010, 2019, 2028, 5000, 5011, 90_000], dtype=np.int32)
+    ref = np.zeros((12, 3), dtype=np.int8)
+    ref[4, 1] = 1
+    tgt = rng.integers(0, 3, size=(12, 5)).astype(np.int8)
+    ws = np.array([1, 1, 50, 2000, 2001, 6000, 95_000, -50, 5011, 90_000, 1, 113], dtype=np.int32)
+    we = np.array([100_000, 4, 120, 2028, 2028, 80_000, 99_000, 5, 5011, 90_000, 1, 104], dtype=np.int32)  # last: end < start
+    _check(eng, ref, tgt, pos, ws, we)
+    _check(eng, ref, tgt, pos, ws[::-1].copy(), we[::-1].copy())            # unordered windows
+    _check(eng, ref, tgt, pos, np.repeat(ws, 3), np.repeat(we, 3))          # duplicates
+    for V in (1, 2, 3, 31, 32, 33):
+        _check(eng, ref[:V] if V <= 12 else np.zeros((V, 3), np.int8),
+               tgt[:V] if V <= 12 else rng.integers(0, 3, size=(V, 5)).astype(np.int8),
+               pos[:V] if V <= 12 else (np.arange(V, dtype=np.int32) * 37 + 1), ws[:4], we[:4])
+
+
+def test_columns_beyond_the_fused_limit_take_the_launch_pipeline(eng):
+    from sstar_b200.synth import regular_windows, synth_chromosome
+    ref, tgt, pos = synth_chromosome(300_000, 3, 70, True, seed=5)   # T = 140 > 128
+    ws, we = regular_windows(pos, 50_000, 10_000)
+    so, no = c_oracle.score_windows(ref, tgt, pos, ws, we)
+    s, n = _score(eng, ref, tgt, pos, ws, we, fused=True)
+    assert eng.launches > 1 and np.array_equal(s, so) and np.array_equal(n, no)
+
+
+def test_replicate_batches_take_the_fused_kernel(eng):
+    """sstar_b200_score_replicates: disjoint windows, positions restart per replicate."""
+    import torch
+    rng = np.random.default_rng(19)
+    n_rep, L = 300, 50_000
+    refs, tgts, poss, off = [], [], [], [0]
+    for r in range(n_rep):
+        v = int(rng.integers(0, 220)) if r % 17 else 0            # some replicates are empty
+        p = np.sort(rng.choice(np.arange(0, L + 200), size=v, replace=False)).astype(np.int32)  # 0 and > L fall outside
+        refs.append((rng.random((v, 6)) < 0.1).astype(np.int8))
+        tgts.append(rng.integers(0, 3, size=(v, 11)).astype(np.int8) * (rng.random((v, 11)) < 0.5))
+        poss.append(p)
+        off.append(off[-1] + v)
+    ref, tgt, pos = np.concatenate(refs), np.concatenate(tgts).astype(np.int8), np.concatenate(poss)
+    dev = eng.tdev
+    d = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (ref, tgt, pos, np.asarray(off, np.int32))]
+    hint = int(np.diff(off).max())
+    from sstar_b200 import _cabi
+    got = {}
+    for name, flags in (("fused", 0), ("launches", _cabi.FLAG_NO_FUSED)):
+        s, n = eng.score_replicates_device(d[0], d[1], d[2], d[3], 1, L, max_win_variants=hint, flags=flags)
+        torch.cuda.synchronize()
+        got[name] = (s.cpu().numpy(), n.cpu().numpy(), eng.launches)
+    assert got["fused"][2] == 1 and got["launches"][2] > 1
+    for r in range(n_rep):
+        a, b = off[r], off[r + 1]
+        so, no = c_oracle.score_windows(ref[a:b], tgt[a:b], pos[a:b], [1], [L])
+        for name in got:
+            assert np.array_equal(got[name][0][r], so[0]) and np.array_equal(got[name][1][r], no[0]), (name, r)
