@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_score_kernel(const __g
 }
 
 // replicate batches: 256 threads, several CTAs per SM
-__global__ void __launch_bounds__(kFusedRepThreads, 2) fused_score_rep_kernel(const __grid_constant__ FusedArgs a) {
+__global__ void __launch_bounds__(kFusedRepThreads, 3) fused_score_rep_kernel(const __grid_constant__ FusedArgs a) {
     fused_body<kFusedRepThreads>(a);
 }
 
