@@ -551,7 +551,7 @@ class Ranks:
 # ------------------------------------------------------------------------------------------
 # strong scaling blocks: fixed total work over the N ranks
 # ------------------------------------------------------------------------------------------
-def strong_c3(torch, eng, dev, rk, flush, length, steps, e2e_steps, use_graph):
+def strong_c3(torch, eng, dev, rk, flush, length, steps, e2e_steps, use_graph, flags=0):
     """BASELINE configs[2]: the whole 250 Mb chromosome over the ranks, by window range."""
     from sstar_b200.sharding import plan_window_shards
     from sstar_b200.synth import regular_windows, synth_chromosome_device
@@ -579,7 +579,7 @@ def strong_c3(torch, eng, dev, rk, flush, length, steps, e2e_steps, use_graph):
                     int(full["pos"][a:b].sum(dtype=np.int64))) != (sr, stg, sp):
                 raise SystemExit("bench: the ranks generated different chromosomes")
     table, (tab_score, tab_nsnp) = rk.shared_table(W, T)
-    case = ShardCase(torch, eng, dev, arrays, out_p=(tab_score[w0:w1], tab_nsnp[w0:w1]), use_graph=use_graph)
+    case = ShardCase(torch, eng, dev, arrays, out_p=(tab_score[w0:w1], tab_nsnp[w0:w1]), use_graph=use_graph, flags=flags)
     gen_s = time.perf_counter() - t0
     for _ in range(2):
         flush.fill_(1)
@@ -817,7 +817,7 @@ def run_ours(args, world, rank, local):
         # the same kernels on a shape that fills the machine (C2 is a 5.6 MB problem: launch bound)
         bwk = make_workload(args.at_scale, 1)
         bst = workload_stats(bwk)
-        big = ShardCase(torch, eng, dev, bwk, use_graph=not args.no_graph)
+        big = ShardCase(torch, eng, dev, bwk, use_graph=not args.no_graph, flags=flags)
         kb = 20
         for _ in range(3):
             flush.fill_(1)
@@ -842,7 +842,7 @@ def run_ours(args, world, rank, local):
         del case
         torch.cuda.empty_cache()
         if args.strong in ("all", "c3"):
-            strong["c3"] = strong_c3(torch, eng, dev, rk, flush, args.c3_length, 10, 5, not args.no_graph)
+            strong["c3"] = strong_c3(torch, eng, dev, rk, flush, args.c3_length, 10, 5, not args.no_graph, flags)
         if args.strong in ("all", "c5"):
             strong["c5"] = strong_c5(torch, eng, dev, rk, flush, 20, 10)
 

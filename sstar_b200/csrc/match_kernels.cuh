@@ -6,10 +6,15 @@
 // dosage, summed over the sites where both are called (:62-73), divided by the number of sites in
 // the tract; the tract's rate is the mean over the sources.
 //
-// Here one warp takes one (tract, source) pair and returns the INTEGER numerator
+// Here one warp takes one TRACT and returns, for every source, the INTEGER numerator
 //     N = sum over callable sites of (P - |x - y|)
 // so that the host forms (N / P) / count and the mean over sources exactly as the reference does
 // (for P = 2 every term of the reference's float sum is a multiple of 1/2, hence exact).
+// Layout: the calls of one variant are one contiguous row of 2N bytes, so the lanes of the warp
+// spread over (row, source): Sp = the source count rounded up to a power of two (<= 32) sources
+// side by side -- their columns of a row sit in a few 32-byte sectors -- and 32 / Sp consecutive rows;
+// the tract's target column is read once per row (a broadcast within the lanes of that row) instead
+// of once per (row, source) pair, and each needed sector of a row once per tract.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -37,31 +42,39 @@ __device__ __forceinline__ int match_diploid_dosage(char2 g) {
 
 __global__ void __launch_bounds__(256) match_kernel(const __grid_constant__ MatchArgs a) {
     const int lane = threadIdx.x & 31;
-    const int64_t pair = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (pair >= (int64_t)a.K * a.S) return;
-    const int k = (int)(pair / a.S), s = (int)(pair % a.S);
+    const int k = (int)((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5));
+    if (k >= a.K) return;
     const int32_t lo = a.tract_lo[k], hi = a.tract_hi[k];
-    const int tcol = a.tract_tgt[k], hap = a.tract_hap[k], scol = a.src_cols[s];
-    int64_t acc = 0;
-    for (int32_t i = lo + lane; i < hi; i += 32) {
-        const int8_t *row = a.gt + (size_t)i * a.N * 2;
-        const char2 tg = *reinterpret_cast<const char2 *>(row + 2 * (size_t)tcol);
-        const char2 sg = *reinterpret_cast<const char2 *>(row + 2 * (size_t)scol);
-        int x;
-        if (hap < 0) x = match_diploid_dosage(tg);
-        else {
-            const int al = hap == 0 ? tg.x : tg.y;
-            x = al >= 0 ? al * a.P : -1;
+    const int tcol = a.tract_tgt[k], hap = a.tract_hap[k];
+    int Sp = 1;
+    while (Sp < a.S && Sp < 32) Sp <<= 1;
+    const int rows_per = 32 / Sp, r = lane / Sp, sl = lane - r * Sp;
+    const size_t pitch = (size_t)a.N * 2;
+    for (int s0 = 0; s0 < a.S; s0 += 32) {  // (more than 32 sources: blocks of 32)
+        const int s = s0 + sl;
+        const bool live = s < a.S;
+        const int scol = live ? a.src_cols[s] : 0;
+        int64_t acc = 0;
+#pragma unroll 4
+        for (int32_t i = lo + r; i < hi; i += rows_per) {
+            const int8_t *row = a.gt + (size_t)i * pitch;
+            const char2 tg = *reinterpret_cast<const char2 *>(row + 2 * (size_t)tcol);
+            const char2 sg = *reinterpret_cast<const char2 *>(row + 2 * (size_t)scol);
+            int x;
+            if (hap < 0) x = match_diploid_dosage(tg);
+            else {
+                const int al = hap == 0 ? tg.x : tg.y;
+                x = al >= 0 ? al * a.P : -1;
+            }
+            const int y = match_diploid_dosage(sg);
+            if (live && x >= 0 && y >= 0) {
+                const int d = x > y ? x - y : y - x;
+                acc += a.P - d;
+            }
         }
-        const int y = match_diploid_dosage(sg);
-        if (x >= 0 && y >= 0) {
-            const int d = x > y ? x - y : y - x;
-            acc += a.P - d;
-        }
+        for (int o = Sp; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);  // the lanes of one source
+        if (live && r == 0) a.numer[(size_t)k * a.S + s] = acc;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    if (lane == 0) a.numer[pair] = acc;
 }
 
 }  // namespace sstar

@@ -294,7 +294,6 @@ __device__ __forceinline__ void score_group_body(const ScoreArgs &a, int wg, int
         g.ex[tid] = 0;
     }
     __syncthreads();
-
     const int32_t pen_eff = (a.max_mm >= 1) ? a.penalty : Sentinel<int32_t>::NEG;
 
     // The group is consumed as one or more SUB-GROUPS [s0, s1): the longest run of windows that

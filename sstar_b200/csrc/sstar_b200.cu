@@ -506,6 +506,32 @@ int check_common(int device, int64_t V, int32_t R, int32_t T, int32_t W, const v
     return 0;
 }
 
+// Per (host thread, device): one copy stream and a ring of events for the host pipeline.  Created
+// on first use and kept for the life of the thread (not caller-visible memory).
+constexpr int kMaxChunks = 16;
+constexpr int kMaxDevices = 64;
+struct PipeCtx {
+    bool ready = false;
+    cudaStream_t copy = nullptr;
+    cudaEvent_t entry = nullptr, done = nullptr;
+    cudaEvent_t chunk[kMaxChunks] = {};
+};
+thread_local PipeCtx g_pipe[kMaxDevices];
+
+int pipe_ctx(int device, PipeCtx **out) {
+    if (device < 0 || device >= kMaxDevices) return fail(SSTAR_B200_EINVAL, "device index out of range%s");
+    PipeCtx &c = g_pipe[device];
+    if (!c.ready) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&c.entry, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+        for (int i = 0; i < kMaxChunks; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c.chunk[i], cudaEventDisableTiming));
+        c.ready = true;
+    }
+    *out = &c;
+    return 0;
+}
+
 // pack (optional) + bounds + score, the common body of every device-pointer entry point
 int run_pipeline(int device, cudaStream_t st, bool do_pack, const int8_t *d_ref, const int8_t *d_tgt,
                  const int32_t *d_pos, int64_t V, int32_t R, int32_t T, const int32_t *d_ws,
@@ -519,11 +545,11 @@ int run_pipeline(int device, cudaStream_t st, bool do_pack, const int8_t *d_ref,
                                      penalty, d_score, d_nsnp, max_win_variants, flags);
         if (frc != 0) return frc < 0 ? frc : 0;
     }
+    const ScoreCall c = {d_tgt, d_pos, V, T, bonus, max_mm, penalty, d_score, d_nsnp, ws, algo, max_win_variants,
+                         d_seg != nullptr};
     int rc = launch_prep(st, 0, do_pack ? L.G : 0, d_ref, d_tgt, V, R, T, d_pos, d_ws, d_we, d_seg, fixed_s, fixed_e, W,
                          ws, L);
     if (rc) return rc;
-    const ScoreCall c = {d_tgt, d_pos, V, T, bonus, max_mm, penalty, d_score, d_nsnp, ws, algo, max_win_variants,
-                         d_seg != nullptr};
     return launch_score(st, c, L, 0, W, 0);
 }
 
@@ -655,32 +681,6 @@ extern "C" size_t sstar_b200_host_scratch_bytes(int64_t V, int32_t R, int32_t T,
 }
 
 namespace {
-
-// Per (host thread, device): one copy stream and a ring of events for the host pipeline.  Created
-// on first use and kept for the life of the thread (not caller-visible memory).
-constexpr int kMaxChunks = 16;
-constexpr int kMaxDevices = 64;
-struct PipeCtx {
-    bool ready = false;
-    cudaStream_t copy = nullptr;
-    cudaEvent_t entry = nullptr, done = nullptr;
-    cudaEvent_t chunk[kMaxChunks] = {};
-};
-thread_local PipeCtx g_pipe[kMaxDevices];
-
-int pipe_ctx(int device, PipeCtx **out) {
-    if (device < 0 || device >= kMaxDevices) return fail(SSTAR_B200_EINVAL, "device index out of range%s");
-    PipeCtx &c = g_pipe[device];
-    if (!c.ready) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreateWithFlags(&c.entry, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
-        for (int i = 0; i < kMaxChunks; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c.chunk[i], cudaEventDisableTiming));
-        c.ready = true;
-    }
-    *out = &c;
-    return 0;
-}
 
 bool mapped_pointer(const void *h, void **dptr) {
     if (!h) { *dptr = nullptr; return true; }  // absent because V == 0 or W == 0
@@ -1048,8 +1048,7 @@ extern "C" int sstar_b200_match_numerators(int device, void *stream, const int8_
     MatchArgs a = {};
     a.gt = d_gt; a.N = N; a.tract_lo = d_tract_lo; a.tract_hi = d_tract_hi; a.tract_tgt = d_tract_tgt;
     a.tract_hap = d_tract_hap; a.src_cols = d_src_cols; a.K = K; a.S = S; a.P = ploidy; a.numer = d_numer;
-    const int64_t pairs = (int64_t)K * S, blocks = (pairs + 7) / 8;
-    if (blocks > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "too many (tract, source) pairs for one call%s");
+    const int64_t blocks = ((int64_t)K + 7) / 8;  // a warp per tract
     cudaError_t e = launch(match_kernel, (unsigned)blocks, 256u, 0, (cudaStream_t)stream, false, a);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "match_kernel launch: %s", cudaGetErrorString(e));
     return 0;
