@@ -65,12 +65,12 @@ def test_fuzz_golden_single_windows(eng, fuzz_cases):
 
 
 @pytest.mark.parametrize("n_ref,n_tgt,phased,length", [
-    (100, 50, False, 1_500_000),   # C2 shape: 4 windows per CTA
-    (5, 10, False, 600_000),       # tutorial shape: narrow reference panel, 8 windows per CTA
-    (20, 33, True, 800_000),       # 66 columns -> 96 column slots, 2 windows per CTA
-    (3, 64, True, 300_000),        # T = 128: one window per CTA
+    (100, 50, False, 1_500_000),   # C2 shape: 10 windows scored at a time by a 512-thread CTA
+    (5, 10, False, 600_000),       # tutorial shape: narrow reference panel (unaligned 5-byte rows)
+    (20, 33, True, 800_000),       # 66 columns: 7 windows at a time
+    (3, 64, True, 300_000),        # T = 128: the widest panel the fused kernel takes
     (40, 16, True, 700_000),       # T = 32 exactly
-    (300, 60, False, 400_000),     # wide reference panel: the tile limit cuts the windows per CTA
+    (300, 60, False, 400_000),     # wide reference panel: the tile limit shrinks the home rows per CTA
 ])
 def test_synthetic_shapes(eng, n_ref, n_tgt, phased, length):
     from sstar_b200.synth import regular_windows, synth_chromosome
@@ -115,7 +115,7 @@ def test_windows_larger_than_the_tile_are_streamed(eng):
     ws, we = regular_windows(pos, 50_000, 10_000)
     for hint in (1, 8, 40, 150):
         _check(eng, ref, tgt, pos, ws, we, hint=hint)
-    # one window over everything next to normal ones, a 2,000-column-free... wide rows: tile rows < window rows
+    # one window over everything next to normal ones
     ws2 = np.concatenate([ws[:5], [1], ws[5:9]]).astype(np.int32)
     we2 = np.concatenate([we[:5], [int(pos[-1])], we[5:9]]).astype(np.int32)
     _check(eng, ref, tgt, pos, ws2, we2, hint=64)
@@ -180,3 +180,19 @@ def test_replicate_batches_take_the_fused_kernel(eng):
         so, no = c_oracle.score_windows(ref[a:b], tgt[a:b], pos[a:b], [1], [L])
         for name in got:
             assert np.array_equal(got[name][0][r], so[0]) and np.array_equal(got[name][1][r], no[0]), (name, r)
+
+
+def test_many_windows_per_cta_and_several_list_rounds(eng):
+    """Dense window lists: more windows than a CTA scores at a time (several batches) and more than
+    one round of the window-list scan (W > 1,024), in shuffled order with duplicates."""
+    from sstar_b200.synth import regular_windows, synth_chromosome
+    ref, tgt, pos = synth_chromosome(1_200_000, 30, 25, False, seed=91)
+    ws, we = regular_windows(pos, 50_000, 500)          # ~2,300 windows, ~3 rows apart
+    assert len(ws) > 2 * 1024
+    _check(eng, ref, tgt, pos, ws, we)
+    rng = np.random.default_rng(2)
+    perm = rng.permutation(len(ws))
+    perm = np.concatenate([perm, perm[:300]])
+    _check(eng, ref, tgt, pos, ws[perm], we[perm])
+    # an understated hint with this many windows: every round leaves windows to the streaming fallback
+    _check(eng, ref[:4000], tgt[:4000], pos[:4000], ws[:1200], we[:1200], hint=60)
