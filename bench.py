@@ -21,9 +21,10 @@ the oracle, bit for bit, on every window (C2 sizes) -- in particular those strad
 value  : units/s with every rank's rows resident in HBM (CUDA events around each step, max over ranks).
 e2e    : units/s through ScoreEngine.score_pinned (one C-ABI call per rank: its rows from pinned host
          memory, kernels, its block of the shared host table written), wall clock, max over ranks.
-strong : the same partition at FIXED total work -- BASELINE configs[2] (one 250 Mb chromosome,
-         R = T = 1000 haplotype columns, 24.3 M units) and configs[4] (10,000 replicates of 50 kb)
-         over the N ranks, device-resident and end to end, oracle-checked in the run.
+strong : the product's partitions at FIXED total work -- BASELINE configs[2] (one 250 Mb chromosome,
+         R = T = 1000 haplotype columns, 24.3 M units, by window range), configs[4] (10,000 replicates
+         of 50 kb, by replicate range) and configs[3] (22 autosomes, T = 2,000, whole chromosomes by
+         cost; device-resident only) over the N ranks, oracle-checked in the run.
 """
 from __future__ import annotations
 
@@ -65,6 +66,13 @@ LARGE = {"c3-shard", "c4-shard", "wide5k", "wide8k"}
 C3 = dict(length=250_000_000, n_ref=500, n_tgt=500, seed=12347,
           desc="C3 (BASELINE configs[2]): one synthetic 250 Mb chromosome, 500 ref + 500 target diploids, haplotype "
                "mode (R = T = 1000 columns), 50 kb / 10 kb, sharded by window range over the ranks")
+# GRCh38 autosome lengths (Mb), chr1 .. chr22: 2.88 Gb
+C4_MB = [248.96, 242.19, 198.30, 190.21, 181.54, 170.81, 159.35, 145.14, 138.39, 133.80, 135.09, 133.28, 114.36, 107.04, 101.99,
+         90.34, 83.26, 80.37, 58.62, 64.44, 46.71, 50.82]
+C4 = dict(n_ref=100, n_tgt=2000, seed=12349,
+          desc="C4 (BASELINE configs[3]): synthetic 22-autosome genome (GRCh38 lengths, 2.88 Gb), 100 ref + 2,000 target "
+               "diploids (unphased; R is not given by BASELINE: 100 as in configs[1]), 50 kb / 10 kb, whole chromosomes assigned "
+               "to the ranks greedily by length (sstar_b200.sharding.plan_chromosome_assignment)")
 C5 = dict(n_rep=10_000, seq_len=50_000, n_ref=5, n_tgt=10, seed=5,
           desc="C5 (BASELINE configs[4]): 10,000 synthetic 50 kb replicates, 5 ref + 10 target diploids (unphased, "
                "the tutorial's shape), one window [1, 50000] each, contiguous replicate ranges over the ranks")
@@ -621,6 +629,82 @@ def strong_c3(torch, eng, dev, rk, flush, length, steps, e2e_steps, use_graph, f
     return out
 
 
+def strong_c4(torch, eng, dev, rk, flush, scale, steps):
+    """BASELINE configs[3]: 22 autosomes over the ranks, whole chromosomes by cost.  Device-resident only
+    (27 GB of genotypes at full size: every rank generates ITS chromosomes on its GPU and keeps them there);
+    ``scale`` shortens every chromosome (debug)."""
+    from oracle import c_oracle
+    from sstar_b200.engine import max_window_variants
+    from sstar_b200.sharding import plan_chromosome_assignment
+    from sstar_b200.synth import regular_windows, synth_chromosome_device
+    t0 = time.perf_counter()
+    lengths = {f"chr{i + 1}": int(mb * 1e6 * scale) for i, mb in enumerate(C4_MB)}
+    plan = plan_chromosome_assignment(lengths, rk.world)
+    mine = plan[rk.rank]
+    cases, units, V_tot, W_tot = [], 0, 0, 0
+    for name in mine:
+        r, t, p = synth_chromosome_device(torch, dev, lengths[name], C4["n_ref"], C4["n_tgt"], False,
+                                          seed=C4["seed"] + int(name[3:]))
+        pos = p.cpu().numpy()
+        ws, we = regular_windows(pos, 50_000, 10_000)
+        ws_d, we_d = torch.from_numpy(ws).to(dev), torch.from_numpy(we).to(dev)
+        out = (torch.empty((len(ws), t.shape[1]), dtype=torch.int64, device=dev),
+               torch.empty((len(ws), t.shape[1]), dtype=torch.int32, device=dev))
+        hint = max_window_variants(pos, ws, we)
+        plan_c = eng.plan_device(r, t, p, ws_d, we_d, *PARAMS, max_win_variants=hint, out=out)
+        cases.append(dict(name=name, ref=r, tgt=t, pos=pos, ws=ws, we=we, out=out, plan=plan_c))
+        units += len(ws) * int(t.shape[1]); V_tot += len(pos); W_tot += len(ws)
+    setup_s = time.perf_counter() - t0
+
+    def step():
+        for c in cases:
+            c["plan"].run()
+
+    for _ in range(2):
+        step()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(steps)]
+    rk.barrier()
+    for i in range(steps):
+        flush.fill_(i & 1)
+        evs[i][0].record()
+        step()
+        evs[i][1].record()
+    rk.barrier()
+    ms = sum(e[0].elapsed_time(e[1]) for e in evs)
+    # parity: 24 spread windows of this rank's first and last chromosome against the C oracle
+    ok, checked = True, 0
+    for c in ([cases[0], cases[-1]] if len(cases) > 1 else cases):
+        sel = np.unique(np.linspace(0, len(c["ws"]) - 1, 24).astype(int))
+        lo = int(np.searchsorted(c["pos"], c["ws"][sel].min(), side="left"))
+        hi = int(np.searchsorted(c["pos"], c["we"][sel].max(), side="right"))
+        for w in sel:
+            a = int(np.searchsorted(c["pos"], c["ws"][w], side="left")); b = int(np.searchsorted(c["pos"], c["we"][w], side="right"))
+            so, no = c_oracle.score_windows(c["ref"][a:b].cpu().numpy(), c["tgt"][a:b].cpu().numpy(), c["pos"][a:b],
+                                            c["ws"][w:w + 1], c["we"][w:w + 1], *PARAMS)
+            ok = ok and bool(np.array_equal(c["out"][0][w].cpu().numpy(), so[0]) and np.array_equal(c["out"][1][w].cpu().numpy(), no[0]))
+            checked += so.size
+    ms, = rk.reduce([ms], "max")
+    units_t, v_t, w_t, checked_t = rk.reduce([units, V_tot, W_tot, checked], "sum")
+    ok = rk.reduce([1.0 if ok else 0.0], "min")[0] == 1.0
+    loads = rk.gather({"rank": rk.rank, "chromosomes": mine, "units": units})
+    out = None
+    if rk.rank == 0:
+        if not ok:
+            raise SystemExit("bench: GPU result differs from the oracle (C4 strong block) -- refusing to report a number")
+        out = {"workload": C4["desc"] + ("" if scale == 1.0 else f"; every chromosome at {scale:g} of its length"),
+               "V": int(v_t), "R": C4["n_ref"], "T": C4["n_tgt"], "W": int(w_t), "units": int(units_t), "n_gpus": rk.world,
+               "assignment": loads, "value": units_t / (ms / steps * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+               "hbm_bytes": int(v_t * (C4["n_ref"] + C4["n_tgt"])),
+               "e2e": None, "e2e_note": "not measured: 27 GB of int8 genotypes would be 0.5 s of PCIe per pass on one GPU",
+               "parity": {"checked_units": int(checked_t), "bit_exact_vs_oracle": True,
+                          "windows": "24 spread windows of every rank's first and last chromosome"},
+               "setup_s": setup_s}
+    rk.barrier()
+    del cases
+    torch.cuda.empty_cache()
+    return out
+
+
 def strong_c5(torch, eng, dev, rk, flush, steps, e2e_steps):
     """BASELINE configs[4]: 10,000 replicates of 50 kb in contiguous replicate ranges over the ranks."""
     from oracle import c_oracle
@@ -845,6 +929,8 @@ def run_ours(args, world, rank, local):
             strong["c3"] = strong_c3(torch, eng, dev, rk, flush, args.c3_length, 10, 5, not args.no_graph, flags)
         if args.strong in ("all", "c5"):
             strong["c5"] = strong_c5(torch, eng, dev, rk, flush, 20, 10)
+        if args.strong in ("all", "c4"):
+            strong["c4"] = strong_c4(torch, eng, dev, rk, flush, args.c4_scale, 5)
 
     if rank == 0:
         line = {
@@ -904,8 +990,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--at-scale", default="c3-shard", choices=["none"] + sorted(LARGE),
                     help="N=1 only: also time the same kernels on a shape that fills the GPU")
-    ap.add_argument("--strong", default="all", choices=["all", "c3", "c5", "none"],
-                    help="strong-scaling blocks: whole C3 / C5 over the N ranks")
+    ap.add_argument("--strong", default="all", choices=["all", "c3", "c4", "c5", "none"],
+                    help="strong-scaling blocks: whole C3 / C4 genome / C5 over the N ranks")
+    ap.add_argument("--c4-scale", type=float, default=1.0, help="length factor of the C4 block's chromosomes (debug)")
     ap.add_argument("--c3-length", type=int, default=C3["length"], help="length of the strong block's chromosome (debug)")
     ap.add_argument("--no-numa", action="store_true", help="multi-rank runs: do not bind ranks to their GPU's NUMA node")
     ap.add_argument("--only-device", action="store_true", help="profiling aid: run only the device-resident passes")
