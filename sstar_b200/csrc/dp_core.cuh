@@ -460,4 +460,105 @@ struct StreamDP {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Walk DP with backpointers: the sites on the unit's best chain (the legacy S*_SNP_number / S*_SNPs
+// columns) out of the O(n) prefix-max form.  The rule on the literal
+// recurrence -- backpointer of j = the FIRST i attaining M[j]; the chain is extended there when
+// M[i] >= 0, else it starts afresh with the pair (i, j); it ends at the FIRST j attaining the final
+// max -- survives the four running maxima when each keeps the index of its first maximiser (sites
+// are committed in index order, updates are strict), and the two candidates of site j (same class,
+// other class) tie-break to the smaller index.
+// Per site the caller's arrays get: row[k] = its row relative to `lo`, back[k] = -1 (no valid
+// predecessor) or (first << 1 | extended).  Returns false when the unit has more than kChainCap
+// sites (the caller then takes the pairwise kernels).  Genotypes in {0,1,2} only.
+// ---------------------------------------------------------------------------------------------
+constexpr int kChainCap = 128;
+
+template <typename acc_t, typename LoadU32, typename LoadPos>
+SSTAR_HD bool walk_dp_unit_chain(LoadU32 ld, LoadPos ldpos, const uint32_t *carried, const uint32_t *two, int32_t Tp,
+                                 int t, int32_t lo, int32_t hi, int32_t bonus_i, int32_t penalty_i, int32_t max_mm,
+                                 uint16_t *row, int16_t *back, int &n_out, int &top_j_out, int64_t &score_out) {
+    constexpr acc_t NEG = Sentinel<acc_t>::NEG, THR = Sentinel<acc_t>::THR;
+    const acc_t bonus = (acc_t)bonus_i;
+    const acc_t pen_eff = (max_mm >= 1) ? (acc_t)penalty_i : NEG;
+    acc_t A[2] = {NEG, NEG}, B[2] = {NEG, NEG};
+    int iA[2] = {-1, -1}, iB[2] = {-1, -1};
+    acc_t wait_p[kRingSlots], wait_v[kRingSlots];
+    int16_t wait_i[kRingSlots];  // index << 1 | class
+    uint32_t nonneg[kChainCap / 32] = {};  // bit k: M[k] is valid and >= 0
+    acc_t top = NEG;
+    int q = 0, head = 0, n = 0, top_j = -1;
+    const int64_t p0 = ldpos(lo);
+    const int gi0 = lo >> 5, gi1 = (hi - 1) >> 5;
+    for (int gi = gi0; gi <= gi1; ++gi) {
+        uint32_t c = ld(carried + (size_t)gi * Tp + t);
+        if (gi == gi0) c &= 0xffffffffu << (lo & 31);
+        if (gi == gi1) c &= 0xffffffffu >> (31 - ((hi - 1) & 31));
+        if (c == 0) continue;
+        const uint32_t tw = ld(two + (size_t)gi * Tp + t);
+        while (c) {
+            const int b = ctz32(c);
+            c &= c - 1;
+            if (n >= kChainCap) return false;
+            const int32_t r = (gi << 5) + b;
+            const acc_t p = (acc_t)(ldpos(r) - p0);
+            const int cls = (int)((tw >> b) & 1u);
+            while (q > 0) {  // sites >= 10 bp behind become eligible predecessors, in index order
+                const acc_t pi = wait_p[head];
+                if (p - pi < kMinPairDistance) break;
+                const acc_t v = wait_v[head];
+                const int wi = wait_i[head] >> 1, wc = wait_i[head] & 1;
+                if (v - pi > A[wc]) { A[wc] = v - pi; iA[wc] = wi; }
+                if (v > B[wc]) { B[wc] = v; iB[wc] = wi; }
+                head = (head + 1) & (kRingSlots - 1);
+                --q;
+            }
+            const acc_t ca = A[cls] + (p + bonus), cb = B[cls ^ 1] + pen_eff;
+            const acc_t m = imax(ca, cb);
+            int first = -1;
+            if (m > THR) first = ca > cb ? iA[cls] : (cb > ca ? iB[cls ^ 1] : (iA[cls] < iB[cls ^ 1] ? iA[cls] : iB[cls ^ 1]));
+            row[n] = (uint16_t)(r - lo);
+            back[n] = first < 0 ? (int16_t)-1 : (int16_t)((first << 1) | (int)((nonneg[first >> 5] >> (first & 31)) & 1u));
+            if (m > THR && m >= 0) nonneg[n >> 5] |= 1u << (n & 31);
+            if (m > THR && m > top) { top = m; top_j = n; }
+            const int tail = (head + q) & (kRingSlots - 1);
+            wait_p[tail] = p;
+            wait_v[tail] = imax(m, (acc_t)0);
+            wait_i[tail] = (int16_t)((n << 1) | cls);
+            ++q;
+            ++n;
+        }
+    }
+    n_out = n;
+    top_j_out = (n <= 2) ? -1 : top_j;
+    score_out = (n <= 2 || top_j < 0) ? kNegInf64 : (int64_t)top;
+    return true;
+}
+
+// sites on the chain that ends at top_j (0 when there is none)
+SSTAR_HD int chain_length(const int16_t *back, int top_j) {
+    int cnt = 0;
+    for (int j = top_j; j >= 0;) {
+        ++cnt;
+        const int b = back[j];
+        if (b < 0) break;            // (cannot happen for a site with a valid M: kept for safety)
+        if (b & 1) j = b >> 1;       // extension of the chain ending at its first maximiser
+        else { ++cnt; break; }       // fresh start with the pair (first, j)
+    }
+    return cnt;
+}
+
+// rows (relative to lo) of the chain's sites, ascending, into out[0 .. len)
+template <typename Out>
+SSTAR_HD void chain_rows(const uint16_t *row, const int16_t *back, int top_j, int len, Out out) {
+    int k = len - 1;
+    for (int j = top_j; j >= 0 && k >= 0;) {
+        out(k--, row[j]);
+        const int b = back[j];
+        if (b < 0) break;
+        if (b & 1) j = b >> 1;
+        else { if (k >= 0) out(k--, row[b >> 1]); break; }
+    }
+}
+
 }  // namespace sstar

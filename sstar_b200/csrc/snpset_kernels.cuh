@@ -9,13 +9,19 @@
 //     at that i the chain is extended when M[i] >= 0, else it starts afresh with the pair (i, j);
 //     the chain ends at the FIRST j attaining max_j M[j].
 //
-// snp_count_kernel, one thread per unit: n from the packed planes (popcounts), the SNP count, and
-// -- most units of sparse data end here -- NaN for n <= 2; the others are queued.
-// snp_set_kernel, one warp per QUEUED unit: the site list comes from the planes (genotype bytes are
+// snp_count_kernel, one thread per unit (a CTA per window x run of columns): #absent rows and the exotic
+// flag of the window, then -- in clean windows (genotypes in {0,1,2}, int32-safe scores, at most 65,535
+// rows) -- the O(n) prefix-max DP with backpointers right there (dp_core.cuh: walk_dp_unit_chain: each
+// running maximum keeps its first maximiser; thread-local backpointers): score, SNP count and chain
+// length of the unit in ONE walk of its plane words.  Units it cannot take (a window with other
+// genotypes, more than kChainCap sites) get their n from popcounts; those with n > 2 are queued.
+// snp_set_kernel, one warp per QUEUED unit (the literal O(n^2) recurrence):
+// the site list comes from the planes (genotype bytes are
 // fetched only in windows holding values outside {0,1,2}), lanes stride over i < j, the row max is
 // a REDUX pair, the first i attaining it a REDUX min.  The result is ragged, so the work is two
-// passes around a scan (lengths -> offsets -> fill); the fill pass walks the same queue and recomputes
-// the recurrence for the units that have a chain.
+// passes around a scan (lengths -> offsets -> fill): the fill pass re-walks the units that have a chain
+// (snp_chain_fill_kernel, a thread per unit, for the units the count kernel scored; snp_set_kernel<true>
+// over the queue for the others).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -34,9 +40,11 @@ struct SnpSetArgs {
     const int8_t *tgt;
     const uint32_t *absent_bits, *exotic, *carried, *two;
     const int32_t *win_lo, *win_hi;
+    const int32_t *win_pfirst, *win_plast;  // position of each window's first / last variant
     uint32_t *win_ex;        // [W] count pass: the window holds genotypes outside {0,1,2}
-    int32_t *queue;          // [W * T] units with n > 2, in no particular order
-    int32_t *queue_n;        // their number (zeroed before the count pass)
+    int32_t *queue;          // [W * T] from the front: units with n > 2 that the count kernel could not score itself;
+                             //          from the far end: units it scored that have a chain (the fill pass's work list)
+    int32_t *queue_n;        // [2] their numbers (zeroed before the count pass)
     int32_t T, Tp, W;
     int32_t bonus, max_mm, penalty;
     int64_t *score;          // lengths pass: [W, T] (INT64_MIN = NaN)
@@ -60,6 +68,18 @@ __device__ __forceinline__ int64_t set_warp_max_i64(int64_t v) {
 
 constexpr int kCountThreads = 128;
 
+struct ChainLdg { __device__ __forceinline__ uint32_t operator()(const uint32_t *p) const { return __ldg(p); } };
+struct ChainPos {
+    const int32_t *pos;
+    __device__ __forceinline__ int64_t operator()(int32_t k) const { return (int64_t)__ldg(pos + k); }
+};
+
+// a window whose units the O(n) chain DP takes (the same test in the count and the fill kernel)
+__device__ __forceinline__ bool chain_window(const SnpSetArgs &a, int w, int32_t lo, int32_t hi, uint32_t ex) {
+    return hi > lo && ex == 0 && hi - lo <= 65535 &&
+           score_bound((int64_t)a.win_plast[w] - (int64_t)a.win_pfirst[w], hi - lo, a.bonus, a.penalty) < kSmallBound;
+}
+
 // grid.x = W * ceil(T / blockDim.x): one window x one run of columns per CTA
 __global__ void __launch_bounds__(kCountThreads) snp_count_kernel(const __grid_constant__ SnpSetArgs a) {
     __shared__ int s_nabs;
@@ -70,10 +90,9 @@ __global__ void __launch_bounds__(kCountThreads) snp_count_kernel(const __grid_c
     if (tid == 0) { s_nabs = 0; s_ex = 0; }
     __syncthreads();
     const int32_t lo = a.win_lo[w], hi = a.win_hi[w];
-    int n = 0;
+    const int wi0 = lo >> 5, wi1 = (hi - 1) >> 5;
+    const uint32_t m0 = 0xffffffffu << (lo & 31), m1 = 0xffffffffu >> (31 - ((hi - 1) & 31));
     if (hi > lo) {
-        const int wi0 = lo >> 5, wi1 = (hi - 1) >> 5;
-        const uint32_t m0 = 0xffffffffu << (lo & 31), m1 = 0xffffffffu >> (31 - ((hi - 1) & 31));
         int na = 0;
         uint32_t ex = 0;
         for (int gi = wi0 + tid; gi <= wi1; gi += bd) {
@@ -87,29 +106,74 @@ __global__ void __launch_bounds__(kCountThreads) snp_count_kernel(const __grid_c
             atomicAdd(&s_nabs, na);
             if (ex) atomicOr(&s_ex, 1u);
         }
-        if (t < a.T) {
-            const uint32_t *cp = a.carried + (size_t)wi0 * a.Tp + t;
-            for (int gi = wi0; gi <= wi1; ++gi, cp += a.Tp) {
-                const uint32_t rm = (gi == wi0 ? m0 : 0xffffffffu) & (gi == wi1 ? m1 : 0xffffffffu);
-                n += __popc(__ldg(cp) & rm);
-            }
-        }
     }
     __syncthreads();
     if (blockIdx.x % tchunks == 0 && tid == 0) a.win_ex[w] = s_ex;
-    const bool queued = t < a.T && n > 2;
+    int n = 0, len = 0;
+    int64_t score = INT64_MIN;
+    if (t < a.T && hi > lo) {  // n from popcounts: two thirds of the units of sparse data end here (n <= 2: NaN)
+        const uint32_t *cp = a.carried + (size_t)wi0 * a.Tp + t;
+        for (int gi = wi0; gi <= wi1; ++gi, cp += a.Tp) {
+            const uint32_t rm = (gi == wi0 ? m0 : 0xffffffffu) & (gi == wi1 ? m1 : 0xffffffffu);
+            n += __popc(__ldg(cp) & rm);
+        }
+    }
+    bool scored = n <= 2;
+    if (t < a.T && !scored && n <= kChainCap && chain_window(a, w, lo, hi, s_ex)) {
+        // score and chain length by the O(n) DP with backpointers (the plane words are in L1 by now)
+        uint16_t row[kChainCap];
+        int16_t back[kChainCap];
+        int top_j = -1, n2;
+        scored = walk_dp_unit_chain<int32_t>(ChainLdg(), ChainPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus, a.penalty,
+                                             a.max_mm, row, back, n2, top_j, score);
+        if (scored) len = chain_length(back, top_j);
+    }
+    const bool queued = t < a.T && !scored;
     if (t < a.T) {
         const size_t o = (size_t)w * a.T + t;
         a.nsnp[o] = (hi - lo) - s_nabs + n;
-        if (!queued) { a.score[o] = INT64_MIN; a.set_len[o] = 0; }
+        if (!queued) { a.score[o] = score; a.set_len[o] = len; }
     }
+    const int lane = tid & 31;
     const uint32_t qm = __ballot_sync(0xffffffffu, queued);
     if (qm) {
-        const int lane = tid & 31, leader = __ffs(qm) - 1;
+        const int leader = __ffs(qm) - 1;
         int base = 0;
         if (lane == leader) base = atomicAdd(a.queue_n, __popc(qm));
         base = __shfl_sync(0xffffffffu, base, leader);
         if (queued) a.queue[base + __popc(qm & ((1u << lane) - 1u))] = w * a.T + t;
+    }
+    const bool chained = t < a.T && scored && len > 0;  // the fill pass's work list, from the far end
+    const uint32_t cm = __ballot_sync(0xffffffffu, chained);
+    if (cm) {
+        const int leader = __ffs(cm) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(a.queue_n + 1, __popc(cm));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (chained) a.queue[(int64_t)a.W * a.T - 1 - (base + __popc(cm & ((1u << lane) - 1u)))] = w * a.T + t;
+    }
+}
+
+// ---- fill pass of the units the count kernel scored itself: a thread per unit of its work list
+constexpr int kChainThreads = 128;
+__global__ void __launch_bounds__(kChainThreads) snp_chain_fill_kernel(const __grid_constant__ SnpSetArgs a) {
+    const int64_t total = a.queue_n[1];
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t it = a.queue[(int64_t)a.W * a.T - 1 - q];
+        const int64_t off = a.set_off[it];
+        const int len = (int)(a.set_off[it + 1] - off);
+        if (len == 0 || off + len > a.capacity) continue;
+        const int w = (int)(it / a.T), t = (int)(it % a.T);
+        const int32_t lo = a.win_lo[w], hi = a.win_hi[w];
+        uint16_t row[kChainCap];
+        int16_t back[kChainCap];
+        int n = 0, top_j = -1;
+        int64_t score;
+        walk_dp_unit_chain<int32_t>(ChainLdg(), ChainPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus, a.penalty, a.max_mm,
+                                    row, back, n, top_j, score);
+        int32_t *dst = a.set_pos + off;
+        const int32_t *psrc = a.pos + lo;
+        chain_rows(row, back, top_j, len, [&](int k, uint16_t r) { dst[k] = __ldg(psrc + r); });
     }
 }
 
@@ -118,6 +182,7 @@ __global__ void __launch_bounds__(kPairWarps * 32) snp_set_kernel(const __grid_c
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int s_maxvw;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (*a.queue_n == 0) return;  // the count pass scored every unit itself (clean data)
     if (threadIdx.x == 0) s_maxvw = 0;
     __syncthreads();
     {   // the largest window decides where the lists live
@@ -129,7 +194,7 @@ __global__ void __launch_bounds__(kPairWarps * 32) snp_set_kernel(const __grid_c
     __syncthreads();
     const int64_t total = *a.queue_n;
     const uint32_t cap = (uint32_t)((s_maxvw + 7) & ~7);
-    if (cap == 0 || total == 0) return;  // the count pass has written every unit
+    if (cap == 0 || total == 0) return;  // the count pass has written every other unit
     int64_t gw = (int64_t)blockIdx.x * kPairWarps + warp;
     int64_t nw = (int64_t)gridDim.x * kPairWarps;
     uint8_t *slab;

@@ -1089,6 +1089,8 @@ int launch_snp_sets(cudaStream_t st, bool fill, const int8_t *d_tgt, const int32
     a.two = reinterpret_cast<const uint32_t *>(ws + L.off_two);
     a.win_lo = reinterpret_cast<const int32_t *>(ws + L.off_win_lo);
     a.win_hi = reinterpret_cast<const int32_t *>(ws + L.off_win_hi);
+    a.win_pfirst = reinterpret_cast<const int32_t *>(ws + L.off_win_pfirst);
+    a.win_plast = reinterpret_cast<const int32_t *>(ws + L.off_win_plast);
     a.win_ex = reinterpret_cast<uint32_t *>(ws + L.off_bail);
     a.queue = reinterpret_cast<int32_t *>(ws + S.off_queue);
     a.queue_n = reinterpret_cast<int32_t *>(ws + S.off_qn);
@@ -1110,7 +1112,7 @@ int launch_snp_sets(cudaStream_t st, bool fill, const int8_t *d_tgt, const int32
     if (grid > (int64_t)num_sms() * per_sm) grid = (int64_t)num_sms() * per_sm;
     cudaError_t e;
     if (!fill) {  // n, SNP counts and the NaN units from the planes; the rest is queued for the warps
-        e = cudaMemsetAsync(a.queue_n, 0, 4, st);
+        e = cudaMemsetAsync(a.queue_n, 0, 8, st);
         if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
         int bd = (T + 31) / 32 * 32;
         if (bd > kCountThreads) bd = kCountThreads;
@@ -1118,6 +1120,12 @@ int launch_snp_sets(cudaStream_t st, bool fill, const int8_t *d_tgt, const int32
         if (cgrid > (int64_t)INT32_MAX) return fail(SSTAR_B200_EINVAL, "too many (window, column chunk) tiles%s");
         e = launch(snp_count_kernel, (unsigned)cgrid, (unsigned)bd, 0, st, false, a);
         if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "snp_count_kernel launch: %s", cudaGetErrorString(e));
+    }
+    if (fill) {  // the units the count kernel scored itself: their chains, a thread per unit
+        int64_t cgrid = (S.n + kChainThreads - 1) / kChainThreads;
+        if (cgrid > (int64_t)num_sms() * 16) cgrid = (int64_t)num_sms() * 16;
+        e = launch(snp_chain_fill_kernel, (unsigned)cgrid, kChainThreads, 0, st, false, a);
+        if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "snp_chain_fill_kernel launch: %s", cudaGetErrorString(e));
     }
     if (fill) {
         static SmemGrant grant;

@@ -277,3 +277,53 @@ extern "C" int emul_fused_windows(const int8_t *ref, const int8_t *tgt, const in
     }
     return 0;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// The O(n) chain DP with backpointers (dp_core.cuh: walk_dp_unit_chain) per unit: score, chain
+// length and the positions on the chain.  fast[u] = 0 when the unit has more than kChainCap sites.
+// ---------------------------------------------------------------------------------------------
+extern "C" int emul_chain_windows(const int8_t *ref, const int8_t *tgt, const int32_t *pos, int64_t V, int32_t R,
+                                  int32_t T, const int32_t *ws, const int32_t *we, int32_t W, int32_t bonus,
+                                  int32_t max_mm, int32_t penalty, int64_t *score, int32_t *set_len,
+                                  int32_t *set_pos /*[W*T*kChainCap]*/, uint8_t *fast) {
+    const int64_t G = (V + 31) / 32;
+    const int32_t Tp = (T + 31) / 32 * 32;
+    std::vector<uint32_t> carried((size_t)(G > 0 ? G : 1) * Tp, 0), two((size_t)(G > 0 ? G : 1) * Tp, 0);
+    for (int64_t k = 0; k < V; ++k) {
+        int sum = 0;
+        for (int r = 0; r < R; ++r) sum += ref[k * R + r];
+        if (sum != 0) continue;
+        for (int t = 0; t < T; ++t) {
+            const int b = tgt[k * T + t];
+            if (b != 0) carried[(size_t)(k >> 5) * Tp + t] |= 1u << (k & 31);
+            if (b == 2) two[(size_t)(k >> 5) * Tp + t] |= 1u << (k & 31);
+        }
+    }
+    uint16_t row[kChainCap];
+    int16_t back[kChainCap];
+    for (int w = 0; w < W; ++w) {
+        const int32_t lo = lower_bound_i64(pos, V, ws[w]);
+        const int32_t hi = std::max(lo, lower_bound_i64(pos, V, (int64_t)we[w] + 1));
+        for (int t = 0; t < T; ++t) {
+            const size_t u = (size_t)w * T + t;
+            score[u] = kNegInf64; set_len[u] = 0; fast[u] = 1;
+            if (hi <= lo) continue;
+            int n = 0, top_j = -1;
+            int64_t sc = kNegInf64;
+            const int64_t span = (int64_t)pos[hi - 1] - (int64_t)pos[lo];
+            bool ok;
+            if (score_bound(span, hi - lo, bonus, penalty) < kSmallBound)
+                ok = walk_dp_unit_chain<int32_t>(HostLd(), HostPos{pos}, carried.data(), two.data(), Tp, t, lo, hi, bonus, penalty, max_mm, row, back, n, top_j, sc);
+            else
+                ok = walk_dp_unit_chain<int64_t>(HostLd(), HostPos{pos}, carried.data(), two.data(), Tp, t, lo, hi, bonus, penalty, max_mm, row, back, n, top_j, sc);
+            if (!ok) { fast[u] = 0; continue; }
+            score[u] = sc;
+            const int len = chain_length(back, top_j);
+            set_len[u] = len;
+            int32_t *dst = set_pos + u * kChainCap;
+            chain_rows(row, back, top_j, len, [&](int k, uint16_t r) { dst[k] = pos[lo + r]; });
+        }
+    }
+    return 0;
+}

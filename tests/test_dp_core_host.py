@@ -211,3 +211,55 @@ def test_fused_unit_paths_match_oracle(emul_fused, params):
     # clean genotypes on crowded positions (several sites inside 9 bp): the parked-site ring of the register walk
     p = emul_fused(np.zeros_like(ref), tgt, dense_pos, dws[:300], dwe[:300], params)
     assert set(np.unique(p)) <= {0, 1, 2}
+
+
+# ---- the O(n) chain DP with backpointers (SNP sets) against the oracle's literal chains ----------
+@pytest.mark.parametrize("params", [(5000, 5, -10000), (5000, 0, -10000), (1, 1, 0), (0, 3, 0), (123, 4, -7), (10, 1, -10),
+                                    (2 ** 27, 2, -(2 ** 27))])
+def test_chain_backpointers_match_oracle(emul, params):
+    lib = ctypes.CDLL(LIB)
+    lib.emul_chain_windows.restype = ctypes.c_int
+    lib.emul_chain_windows.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                                               ctypes.c_void_p, ctypes.c_void_p] + \
+        [ctypes.c_int32] * 4 + [ctypes.c_void_p] * 4
+    CAP = 128
+    rng = np.random.default_rng(abs(hash(params)) % 2 ** 31)
+
+    def run(ref, tgt, pos, ws, we):
+        ref = np.ascontiguousarray(ref, dtype=np.int8); tgt = np.ascontiguousarray(tgt, dtype=np.int8)
+        pos = np.ascontiguousarray(pos, dtype=np.int32)
+        ws = np.ascontiguousarray(ws, dtype=np.int32); we = np.ascontiguousarray(we, dtype=np.int32)
+        V, R = ref.shape
+        T, W = tgt.shape[1], len(ws)
+        score = np.empty(W * T, np.int64); ln = np.empty(W * T, np.int32)
+        sp = np.zeros(W * T * CAP, np.int32); fast = np.zeros(W * T, np.uint8)
+        assert lib.emul_chain_windows(ref.ctypes.data, tgt.ctypes.data, pos.ctypes.data, V, R, T, ws.ctypes.data, we.ctypes.data,
+                                      W, *params, score.ctypes.data, ln.ctypes.data, sp.ctypes.data, fast.ctypes.data) == 0
+        so, no, off, sets = c_oracle.snp_sets(ref, tgt, pos, ws, we, *params)
+        nfast = 0
+        for u in range(W * T):
+            if not fast[u]:
+                continue
+            nfast += 1
+            assert score[u] == so.reshape(-1)[u], u
+            want = sets[off[u]:off[u + 1]]
+            assert ln[u] == len(want), (u, ln[u], len(want))
+            assert np.array_equal(sp[u * CAP:u * CAP + ln[u]], want), u
+        return nfast, W * T
+
+    ref, tgt, pos = synth_chromosome(500_000, 12, 9, False, seed=43)
+    ws, we = regular_windows(pos, 50_000, 10_000)
+    nf, tot = run(ref, tgt, pos, ws, we)
+    assert nf == tot
+    # tie-heavy: equally spaced sites, few genotype classes, every site reference-absent
+    V = 400
+    tpos = (np.arange(V) * 10 + 1).astype(np.int32)
+    ttgt = rng.integers(0, 3, size=(V, 7)).astype(np.int8)
+    tws = np.arange(1, 3500, 250, dtype=np.int32)
+    nf, tot = run(np.zeros((V, 2), np.int8), ttgt, tpos, tws, tws + 999)
+    assert nf == tot
+    # crowded positions and long units (some beyond the cap are skipped, the rest must agree)
+    dpos = np.sort(rng.choice(np.arange(1, 3000), size=900, replace=False)).astype(np.int32)
+    dtgt = (rng.random((900, 5)) < 0.5).astype(np.int8) * rng.integers(1, 3, size=(900, 5)).astype(np.int8)
+    nf, tot = run(np.zeros((900, 2), np.int8), dtgt, dpos, [1, 1, 500, 1500], [400, 3000, 900, 1700])
+    assert 0 < nf < tot

@@ -7,7 +7,7 @@ import bench
 from sstar_b200.engine import get_engine
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
-wk = bench.make_workload(name, 0)
+wk = bench.make_workload(name, 1)
 st = bench.workload_stats(wk)
 dev = torch.device("cuda", 0)
 eng = get_engine(0)

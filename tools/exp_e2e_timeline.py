@@ -3,7 +3,7 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from sstar_b200.engine import get_engine
-wk = bench.make_workload("c2", 0); st = bench.workload_stats(wk)
+wk = bench.make_workload("c2", 1); st = bench.workload_stats(wk)
 dev = torch.device("cuda", 0); eng = get_engine(0)
 pin = {k: torch.from_numpy(np.ascontiguousarray(wk[k])).pin_memory() for k in ("ref", "tgt", "pos", "ws", "we")}
 d = {k: torch.empty_like(v, device=dev) for k, v in pin.items()}

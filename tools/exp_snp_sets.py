@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from sstar_b200.engine import get_engine
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
-wk = bench.make_workload(name, 0); st = bench.workload_stats(wk)
+wk = bench.make_workload(name, 1); st = bench.workload_stats(wk)
 dev = torch.device("cuda", 0); eng = get_engine(0)
 d = {k: torch.from_numpy(np.ascontiguousarray(wk[k])).to(dev) for k in ("ref", "tgt", "pos", "ws", "we")}
 hint = st["max_window_variants"]

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from sstar_b200.engine import get_engine
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
-wk = bench.make_workload(name, 0)
+wk = bench.make_workload(name, 1)
 dev = torch.device("cuda", 0); eng = get_engine(0)
 case = bench.DeviceCase(torch, eng, dev, wk)
 big = torch.empty(256 << 20, dtype=torch.uint8, device=dev); tiny = torch.empty(1, dtype=torch.uint8, device=dev)
