@@ -29,7 +29,7 @@ struct WsLayout {
     int64_t G;   // 32-variant groups
     int32_t Tp;  // plane row pitch in words (T rounded up to 32)
     size_t off_absent, off_exotic, off_carried, off_two, off_win_lo, off_win_hi, off_win_pfirst, off_win_plast, off_slow, off_bail,
-        off_fflag, off_arena;
+        off_arena;
     size_t arena_entries;
     size_t total;
 };
@@ -45,14 +45,13 @@ struct BoundsArgs {
     uint32_t *win_bail;               // zeroed here: set once a window is routed to the pairwise kernel by a unit
     WsHeader *hdr;
     int force_slow;
-    // In-place host entry (n_fetch > 0): pos / win_start / win_end above are device COPIES that the
-    // first n_fetch CTAs of this same grid fill from mapped host memory (no copy engine involved:
-    // small DMA copies are slow on some hosts and queue behind the SMs' own PCIe reads); each
-    // publishes fflag[cta] = stamp, the bounds CTAs wait for all of them.
+    // In-place host entry (n_fetch > 0): pos / win_start / win_end above are device COPIES that
+    // fetch_kernel -- the launch right before this one, n_fetch CTAs -- fills from mapped host memory (no
+    // copy engine involved: small DMA copies are slow on some hosts and queue behind the SMs' own PCIe
+    // reads).  The prep grid is a programmatic dependent launch: its pack CTAs start under the fetch,
+    // its bounds CTAs wait for it (griddepcontrol.wait).
     const int32_t *src_pos, *src_ws, *src_we;
     int32_t n_fetch;
-    uint64_t *fflag;
-    uint64_t stamp;
 };
 constexpr int kMaxFetchCtas = 32;
 
@@ -96,30 +95,6 @@ __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 
-// Flags between CTAs of one grid (a producer CTA has a lower block index than its consumers, so it
-// is resident or done before they exist): the producer's threads fence, meet at a barrier, one
-// thread publishes the stamp; a consumer thread polls with acquire loads, then meets its CTA at
-// a barrier.
-__device__ __forceinline__ void flag_publish(uint64_t *flag, uint64_t stamp) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(flag), "l"(stamp) : "memory");
-}
-__device__ __forceinline__ void flag_wait(const uint64_t *flag, uint64_t stamp) {
-    uint64_t v;
-    uint64_t t0 = 0;
-    uint32_t pause = 128;
-    for (uint32_t spins = 0;; ++spins) {
-        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-        if (v == stamp) return;
-        __nanosleep(pause);  // back off: thousands of waiting CTAs must not crowd the L2
-        if (pause < 2048) pause += pause;
-        if ((spins & 255u) == 255u) {  // a producer that never comes is a bug: fail loudly, do not hang
-            uint64_t now;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000ull) __trap();
-        }
-    }
-}
 constexpr int kBoundsWindowsPerCta = kPackThreads / 32;
 
 }  // namespace sstar

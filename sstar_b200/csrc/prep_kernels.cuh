@@ -13,10 +13,11 @@ namespace sstar {
 // becomes [lo, hi) = [lower_bound(start), lower_bound(end + 1)) on the ascending position array.
 // One warp per window; each round 32 lanes probe 32 pivots, shrinking the range ~33x.
 // ------------------------------------------------------------------------------------------
-// pos / win_start / win_end of a bounds CTA may be the device copies that the fetch CTAs OF THE SAME
-// GRID are writing (in-place host entry): they are read with ordinary coherent loads (ld.relaxed.gpu),
-// never through the non-coherent path (__ldg / const __restrict__), which PTX only allows for data
-// that stays read-only for the whole kernel.  The acquire in flag_wait + the CTA barrier order them.
+// pos / win_start / win_end of a bounds CTA may be the device copies that fetch_kernel -- the grid this
+// one is a programmatic dependent of -- was still writing when this grid started (in-place host entry):
+// they are read after griddepcontrol.wait with ordinary coherent loads (ld.relaxed.gpu), never through
+// the non-coherent path (__ldg / const __restrict__), which PTX only allows for data that stays
+// read-only for the whole kernel.
 __device__ __forceinline__ int32_t ld_coherent(const int32_t *p) {
     int32_t v;
     asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -53,19 +54,13 @@ __device__ __forceinline__ void fetch_block(const BoundsArgs &a, int blk, int nt
         else if (i < V + W) dws[i - V] = a.src_ws[i - V];
         else dwe[i - V - W] = a.src_we[i - V - W];
     }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) flag_publish(a.fflag + blk, a.stamp);
 }
 
 __device__ __forceinline__ void bounds_block(const BoundsArgs &a, int block, int nthreads, int tid) {
     const int lane = tid & 31;
     const int w = block * (nthreads >> 5) + (tid >> 5);
     if (block == 0 && tid < kMaxSlots) a.hdr->n_slow[tid] = 0;
-    if (a.n_fetch) {  // pos / windows are being fetched by the grid's first CTAs
-        if (tid < a.n_fetch) flag_wait(a.fflag + tid, a.stamp);
-        __syncthreads();
-    }
+    if (a.n_fetch) pdl_wait();  // pos / windows come from fetch_kernel, the launch before this grid
     if (w < a.W) {
         const int32_t sb = a.seg ? a.seg[w] : 0;
         const int32_t se = a.seg ? a.seg[w + 1] : a.V;
@@ -406,11 +401,7 @@ template <bool kWide, bool kLaneRows = false>
 __device__ __forceinline__ void prep_body(const PackArgs &p, const BoundsArgs &b, int n_pack, int mode, uint8_t *smem,
                                           uint64_t *s_bar) {
     pdl_launch_dependents();  // let the next kernel's CTAs get scheduled while this grid drains
-    if ((int)blockIdx.x < b.n_fetch) {
-        fetch_block(b, (int)blockIdx.x, kPackThreads, threadIdx.x);
-        return;
-    }
-    const int blk = (int)blockIdx.x - b.n_fetch;
+    const int blk = (int)blockIdx.x;
     if (blk >= n_pack) {
         bounds_block(b, blk - n_pack, kPackThreads, threadIdx.x);
         return;
@@ -509,6 +500,13 @@ __device__ __forceinline__ void prep_body(const PackArgs &p, const BoundsArgs &b
         else         pack_tile<false, false, false, kLaneRows>(p, smem, g0, ng, nrows, rph, tph);
         __syncthreads();  // the tile and its flags are done with before the next one lands
     }
+}
+
+// in-place host entry: pos | win_start | win_end from mapped host memory into the scratch; the prep
+// grid behind it starts right away (its pack CTAs need none of this)
+__global__ void __launch_bounds__(kPackThreads) fetch_kernel(const __grid_constant__ BoundsArgs b) {
+    pdl_launch_dependents();
+    fetch_block(b, (int)blockIdx.x, kPackThreads, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(kPackThreads)

@@ -105,7 +105,6 @@ WsLayout make_layout(int64_t V, int32_t T, int32_t W, int32_t max_win_variants) 
     L.off_win_plast = off;  off = align_up(off + w * 4, 256);
     L.off_slow = off;    off = align_up(off + w * 4, 256);
     L.off_bail = off;    off = align_up(off + w * 4, 256);
-    L.off_fflag = off;   off += align_up((size_t)kMaxFetchCtas * 8, 256);
     // pairwise list arena: at least one slab of the worst-case window must fit
     size_t worst = (size_t)(V > 0 ? V : 1);
     size_t want;
@@ -170,12 +169,10 @@ cudaError_t launch(void (*kernel)(KArgs...), unsigned grid, unsigned block, size
 int launch_prep(cudaStream_t st, int64_t g_begin, int64_t g_end, const int8_t *d_ref, const int8_t *d_tgt,
                 int64_t V, int32_t R, int32_t T, const int32_t *d_pos, const int32_t *d_ws, const int32_t *d_we,
                 const int32_t *d_seg, int32_t fixed_s, int32_t fixed_e, int32_t W, uint8_t *ws,
-                const WsLayout &L, int pack_ctas = 0, uint64_t stamp = 0, const int32_t *const *fetch_src = nullptr) {
+                const WsLayout &L, int pack_ctas = 0, const int32_t *const *fetch_src = nullptr) {
     PackArgs p = {};
     BoundsArgs b = {};
-    b.stamp = stamp;
-    b.fflag = reinterpret_cast<uint64_t *>(ws + L.off_fflag);
-    if (fetch_src && W > 0 && stamp) {  // {pos, win_start, win_end} in mapped host memory
+    if (fetch_src && W > 0) {  // {pos, win_start, win_end} in mapped host memory
         b.src_pos = fetch_src[0]; b.src_ws = fetch_src[1]; b.src_we = fetch_src[2];
         const int64_t words = V + 2 * (int64_t)W;
         b.n_fetch = (int32_t)((words + 2047) / 2048);
@@ -267,7 +264,11 @@ int launch_prep(cudaStream_t st, int64_t g_begin, int64_t g_end, const int8_t *d
     else if (mode == 0 && n_pack > 0 && R <= 16) { kernel = prep_narrow_kernel; grant = &narrow_grant; }
     cudaError_t e = grant_smem(*grant, kernel, smem);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaFuncSetAttribute(prep): %s", cudaGetErrorString(e));
-    e = launch(kernel, (unsigned)(n_fetch + n_pack + n_bounds), kPackThreads, smem, st, false, p, b, n_pack, mode);
+    if (n_fetch > 0) {  // the fetch first; the prep grid is its programmatic dependent
+        e = launch(fetch_kernel, (unsigned)n_fetch, kPackThreads, 0, st, false, b);
+        if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "fetch_kernel launch: %s", cudaGetErrorString(e));
+    }
+    e = launch(kernel, (unsigned)(n_pack + n_bounds), kPackThreads, smem, st, n_fetch > 0, p, b, n_pack, mode);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "prep_kernel launch: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -275,17 +276,6 @@ int launch_prep(cudaStream_t st, int64_t g_begin, int64_t g_end, const int8_t *d
 // CTAs of the pack grid when the matrices are read in place over PCIe: 32 already saturate the
 // link (profiles/r01_side_measurements.txt); a short grid keeps the tiles arriving front to back
 constexpr int kInPlacePackCtas = 64;
-
-// A fresh 64-bit value per call: the fetch flags left in the workspace by earlier calls (or
-// whatever an uninitialised workspace holds) never match it.
-uint64_t next_stamp() {
-    static std::atomic<uint64_t> counter{(uint64_t)std::chrono::steady_clock::now().time_since_epoch().count()};
-    uint64_t z = counter.fetch_add(0x9e3779b97f4a7c15ull) + 0x9e3779b97f4a7c15ull;
-    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
-    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
-    z ^= z >> 31;
-    return z ? z : 1;
-}
 
 struct ScoreCall {
     const int8_t *d_tgt;
@@ -807,7 +797,7 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
         const int32_t *const fetch_src[3] = {(const int32_t *)m_pos, (const int32_t *)m_ws, (const int32_t *)m_we};
         rc = launch_prep(st, 0, L.G, (const int8_t *)m_ref, (const int8_t *)m_tgt, V, R, T, d_pos,
                          (const int32_t *)(d + h.off_ws), (const int32_t *)(d + h.off_we), nullptr, 0, 0, W, ws, L,
-                         kInPlacePackCtas, next_stamp(), fetch_src);
+                         kInPlacePackCtas, fetch_src);
         if (rc) return rc;
         int64_t *z_score = copy_out ? (int64_t *)(d + h.off_score) : (int64_t *)m_score;
         int32_t *z_nsnp = copy_out ? (int32_t *)(d + h.off_nsnp) : (int32_t *)m_nsnp;
