@@ -68,9 +68,12 @@ extern "C" {
 typedef struct sstar_b200_options {
     int32_t algo;             /* SSTAR_B200_ALGO_* */
     int32_t max_win_variants; /* upper bound on variants inside any window (hi - lo): sizes the
-                                 pairwise list arena and the window groups of the score kernel;
-                                 0 = unknown (sized for V).  An understated hint is safe: it
-                                 only leaves the pairwise kernel fewer concurrent list slabs */
+                                 pairwise list arena and the window groups of the score kernel,
+                                 and lets small inputs (and every replicate batch) run as ONE
+                                 launch whose shared-memory tile it sizes; 0 = unknown (sized for
+                                 V, always the pack -> score launches).  An understated hint is
+                                 safe: it costs parallelism (windows larger than promised are
+                                 streamed from global memory), never results */
     int32_t flags;            /* SSTAR_B200_FLAG_* */
     int32_t reserved[5];      /* must be zero */
 } sstar_b200_options;
