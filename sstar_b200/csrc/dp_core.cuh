@@ -159,6 +159,7 @@ SSTAR_HD_COLD bool list_dp_run_general(const uint32_t *base, int ls, int n, int3
     constexpr int32_t NEG = Sentinel<int32_t>::NEG, THR = Sentinel<int32_t>::THR;
     int32_t A[kMaxClasses], B[kMaxClasses], val[kMaxClasses];
     int32_t ring_v[kRingSlots];
+    int8_t ring_c[kRingSlots];  // class of the waiting sites (found when they were scored)
     int K = 0;
     int c = 0;  // next site to commit
     int32_t top = NEG;
@@ -175,7 +176,7 @@ SSTAR_HD_COLD bool list_dp_run_general(const uint32_t *base, int ls, int n, int3
             const uint32_t ec = base[c * ls];
             const int32_t pc = (int32_t)(ec >> 8);
             if (p - pc < kMinPairDistance) break;
-            const int ci = class_of((int32_t)(int8_t)(ec & 0xffu));  // registered when it was scored
+            const int ci = ring_c[c & (kRingSlots - 1)];
             const int32_t vc = ring_v[c & (kRingSlots - 1)];
             A[ci] = imax(A[ci], vc - pc);
             B[ci] = imax(B[ci], vc);
@@ -195,9 +196,22 @@ SSTAR_HD_COLD bool list_dp_run_general(const uint32_t *base, int ls, int n, int3
         const int32_t m = imax(A[idx] + (p + bonus), other + penalty);
         top = imax(top, m);
         ring_v[k & (kRingSlots - 1)] = imax(m, (int32_t)0);
+        ring_c[k & (kRingSlots - 1)] = (int8_t)idx;
     }
     score_out = (n <= 2 || top <= THR) ? kNegInf64 : (int64_t)top;
     return true;
+}
+
+// list_window_range_shifted<8> for general entries that also keeps, for both cursors, the number of
+// entries passed whose genotype is not 1 / 2: a unit is "plain" (the four-maxima DP takes it) iff the
+// two counts agree -- O(1) per unit instead of a scan of its entries.
+SSTAR_HD void list_window_range_general(const uint32_t *list, int ls, int &a, int &b, int &odd_a, int &odd_b, uint32_t plo,
+                                        uint32_t phi) {
+    const uint32_t *pa = list + a * ls;
+    while ((*pa >> 8) < plo) { odd_a += (int)(((*pa & 0xffu) - 1u) >= 2u); pa += ls; ++a; }
+    if (b < a) { b = a; odd_b = odd_a; }
+    const uint32_t *pb = list + b * ls;
+    while ((*pb >> 8) <= phi) { odd_b += (int)(((*pb & 0xffu) - 1u) >= 2u); pb += ls; ++b; }
 }
 
 // list_window_range_shifted moves the cursors to the window [plo, phi]: a = first entry with

@@ -154,7 +154,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
         // NaN and finished here (most units of sparse haplotype data), the others are queued.
         // Pass 2: the CTA's threads share the queued units evenly, so a warp's DP loop no longer
         // runs for the longest of 32 unrelated columns in every window.
-        int cur_a = 0, cur_b = 0;
+        int cur_a = 0, cur_b = 0, odd_a = 0, odd_b = 0;  // (general body: entries passed whose genotype is not 1 / 2)
         for (int i = 0; i < nwin; ++i) {
             const int w = w0 + i;
             const int32_t lo = glo[i], hi = ghi[i];
@@ -164,7 +164,8 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
             int64_t score = kNegInf64;
             if (t < a.T && !ex && hi > lo) {
                 if (!overflow) {
-                    list_window_range_shifted<kShift>(s_list + tid, ls, cur_a, cur_b, gplo[i], gphi[i], true);
+                    if (kGen) list_window_range_general(s_list + tid, ls, cur_a, cur_b, odd_a, odd_b, gplo[i], gphi[i]);
+                    else list_window_range_shifted<kShift>(s_list + tid, ls, cur_a, cur_b, gplo[i], gphi[i], true);
                     n = cur_b - cur_a;
                     queued = n > 2;
                 } else if (kGen) {
@@ -178,7 +179,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
             // units whose genotypes all are 1 / 2 (most of them) queue from the front and take the
             // four-maxima DP, the others queue from the far end and take the per-class DP: the
             // warps of pass 2 then run one body at a time.
-            const bool other = kGen && queued && !general_run_is_plain(s_list + tid + cur_a * ls, ls, n);
+            const bool other = kGen && queued && odd_b != odd_a;  // some genotype of the unit is not 1 / 2
             const uint32_t qm = __ballot_sync(0xffffffffu, queued && !other);
             const uint32_t om = kGen ? __ballot_sync(0xffffffffu, other) : 0u;
             const uint32_t item = (uint32_t)tid | ((uint32_t)i << 7) | ((uint32_t)cur_a << 11) | ((uint32_t)n << 21);

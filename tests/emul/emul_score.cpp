@@ -151,7 +151,7 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
                     }
                     const bool overflow = cnt >= L;  // one slot is the terminator
                     if (!overflow) list[cnt] = kListSentinel;
-                    int cur = 0, cur_b = 0;
+                    int cur = 0, cur_b = 0, odd_a = 0, odd_b = 0;
                     const bool balanced = (s1 - s0) > 1 && mono_hi;  // the kernel's two-pass path
                     for (int i = s0; i < s1; ++i) {
                         const int w = w0 + i;
@@ -165,11 +165,14 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
                             if (gen) {
                                 if (overflow) { slow[w] = 1; continue; }
                                 if (!balanced) cur_b = cur;
-                                list_window_range_shifted<8>(list.data(), 1, cur, cur_b, plo, phi, balanced);
+                                if (balanced) list_window_range_general(list.data(), 1, cur, cur_b, odd_a, odd_b, plo, phi);
+                                else list_window_range_shifted<8>(list.data(), 1, cur, cur_b, plo, phi, false);
                                 n = cur_b - cur;
-                                // as on the device: in the balanced pass the units whose genotypes all are 1 / 2 take
-                                // the four-maxima DP on general entries, the others the per-class DP
-                                if (n > 2 && balanced && general_run_is_plain(list.data() + cur, 1, n))
+                                // as on the device: in the balanced pass the units whose genotypes all are 1 / 2 (the
+                                // cursors' counts of other genotypes agree) take the four-maxima DP on general
+                                // entries, the others the per-class DP
+                                if (balanced && (odd_a == odd_b) != general_run_is_plain(list.data() + cur, 1, n)) return -7;
+                                if (n > 2 && balanced && odd_a == odd_b)
                                     sc = list_dp_run<8>(list.data() + cur, 1, n, bonus, pen_eff);
                                 else if (n > 2 && !list_dp_run_general(list.data() + cur, 1, n, bonus, penalty, max_mm, sc)) { slow[w] = 1; continue; }
                             } else if (!overflow && balanced) {

@@ -64,3 +64,17 @@ for label, fn, fl in (("tiny torch kernel (x.add_), flushed", lambda: one.add_(1
             torch.cuda.synchronize()
             ts.append(ev[0].elapsed_time(ev[1]) * 1e3)
     print(f"{label}: median {np.median(ts):.2f} us, min {min(ts):.2f} us")
+# does the flush's own dirty data sit in front of the timed kernel?  write-only flush vs write + read of another buffer
+other = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+other.fill_(3)
+for label, pre in (("flush = 256 MiB write", lambda i: flush.fill_(i & 1)),
+                   ("flush = 256 MiB write, then 256 MiB read of another buffer", lambda i: (flush.fill_(i & 1), other.view(torch.int64).sum())),
+                   ("flush = 256 MiB write, then 20 us of idle-ish work (tiny kernels)", lambda i: (flush.fill_(i & 1), [one.add_(1) for _ in range(8)]))):
+    for name, fn in (("fused kernel", lambda: eng.score_device(*d, max_win_variants=hint)), ("tiny kernel", lambda: one.add_(1))):
+        ts = []
+        for i in range(40):
+            pre(i)
+            ev[0].record(); fn(); ev[1].record()
+            torch.cuda.synchronize()
+            ts.append(ev[0].elapsed_time(ev[1]) * 1e3)
+        print(f"{label} | {name}: median {np.median(ts):.2f} us, min {min(ts):.2f} us")
