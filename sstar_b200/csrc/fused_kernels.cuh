@@ -255,38 +255,45 @@ __device__ __forceinline__ void fused_pack(const FusedArgs &a, const uint8_t *s_
                 e_and |= w & h;
             }
         }
+        uint32_t bad = (e_or & 0xfcfcfcfcu) | (e_and & 0x01010101u);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, 1);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, 2);
+        uint32_t ax = 0;
+        if (bad && valid) {
+            // a byte outside {0,1,2} somewhere in the 32 x 4 block (missing calls, multi-allelic dosages -- or
+            // the padding bytes of a ragged last quad / tail rows): the four lanes redo their rows with the
+            // EXACT byte tests, plus the plane of bytes outside {0,1,2} for the group's exotic flag
+            an = 0; at = 0;
+#pragma unroll
+            for (int rr = 7; rr >= 0; --rr) {
+                const uint32_t off = base + (uint32_t)rr * (uint32_t)a.T;
+                const uint32_t w = aligned ? lds_word<true>(s_tgt, off) : lds_word<false>(s_tgt, off);
+                an = an + an + (bytes_nonzero(w) >> 7);
+                at = at + at + (bytes_zero(w ^ 0x02020202u) >> 7);
+                ax = ax + ax + ((bytes_nonzero(w & 0xfcfcfcfcu) | bytes_zero(w ^ 0x03030303u)) >> 7);
+            }
+        }
+        const bool any_bad = __any_sync(0xffffffffu, bad != 0);
         const int l0 = lane & ~3;
-        uint32_t nz[4], tw[4];
+        uint32_t nz[4], tw[4], xw[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             nz[j] = __shfl_sync(0xffffffffu, an, l0 + j);
             tw[j] = __shfl_sync(0xffffffffu, at, l0 + j);
         }
-        uint32_t bad = (e_or & 0xfcfcfcfcu) | (e_and & 0x01010101u);
-        bad |= __shfl_xor_sync(0xffffffffu, bad, 1);
-        bad |= __shfl_xor_sync(0xffffffffu, bad, 2);
-        uint32_t car[4], two[4];
+        if (any_bad) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xw[j] = __shfl_sync(0xffffffffu, ax, l0 + j);
+        }
+        uint32_t car[4], two[4], exo[4];
         transpose4(nz[0], nz[1], nz[2], nz[3], car);
         transpose4(tw[0], tw[1], tw[2], tw[3], two);
+        transpose4(xw[0], xw[1], xw[2], xw[3], exo);
         const int c = blk;  // this lane's column within the quad
         if (valid && 4 * q + c < a.T) {
-            const uint32_t ab = s_absent[gl];
-            uint32_t m_nz = car[c], m_two = two[c];
-            if (bad) {
-                // a byte outside {0,1,2} somewhere in the block (or in the padding bytes of a ragged last
-                // quad / tail rows): this lane redoes its column exactly, byte by byte
-                m_nz = 0; m_two = 0;
-                bool exotic = false;
-                const uint32_t col = tph + (uint32_t)(gl * 32) * (uint32_t)a.T + 4u * q + (uint32_t)c;
-                for (int r = 0; r < 32; ++r) {
-                    const int b = (gl * 32 + r < nrows) ? (int)(int8_t)s_tgt[col + (uint32_t)r * (uint32_t)a.T] : 0;
-                    const uint32_t isab = (ab >> r) & 1u;
-                    m_nz |= ((uint32_t)(b != 0) & isab) << r;
-                    m_two |= ((uint32_t)(b == 2) & isab) << r;
-                    exotic |= ((unsigned)b > 2u) && isab;
-                }
-                if (exotic) atomicOr(&s_exotic[gl], 1u);
-            }
+            const uint32_t ab = s_absent[gl];  // (rows past the matrix's end have no absent bit)
+            const uint32_t m_nz = car[c], m_two = two[c];
+            if (exo[c] & ab) atomicOr(&s_exotic[gl], 1u);
             s_carried[gl * a.tc + 4 * q + c] = m_nz & ab;
             s_two[gl * a.tc + 4 * q + c] = m_two & ab;
         }

@@ -160,6 +160,12 @@ __device__ __forceinline__ uint32_t lds_word(const uint8_t *region, uint32_t off
     return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
 }
 
+// SIMD-within-word byte tests, exact for any byte value: bit 7 of each byte of the result
+__device__ __forceinline__ uint32_t bytes_nonzero(uint32_t w) {
+    return (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t bytes_zero(uint32_t w) { return ~(((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u; }
+
 // 4x4 byte transpose: a0..a3 hold (rows 0-7, 8-15, 16-23, 24-31) x (4 columns, one per byte);
 // c[k] becomes the 32-row word of column k.
 __device__ __forceinline__ void transpose4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t c[4]) {
@@ -169,6 +175,43 @@ __device__ __forceinline__ void transpose4(uint32_t a0, uint32_t a1, uint32_t a2
     c[1] = __byte_perm(t0, t1, 0x7632);
     c[2] = __byte_perm(t2, t3, 0x5410);
     c[3] = __byte_perm(t2, t3, 0x7632);
+}
+
+// One 32-row x 4-column block redone with the EXACT byte tests, still four columns at a time (bit 7 of
+// each byte: "!= 0", "== 2", "> 2 unsigned"): the planes' words of the four columns, and whether a
+// reference-absent row of a real column holds a byte outside {0,1,2} (the group's exotic flag).
+// Rows are addressed as in pack_tile (kRowPhase: each row segment keeps its own 16-byte phase).
+template <bool kAligned, bool kRowPhase>
+__device__ __noinline__ bool pack_block_exact(const uint8_t *s_tgt, uint32_t base, uint32_t tpitch, uint32_t tgt_phase,
+                                              uint32_t pstep, uint32_t row0, uint32_t col_off, uint32_t ab, int ncol,
+                                              uint32_t car[4], uint32_t two[4]) {
+    uint32_t nz[4], tw[4], ex[4];
+#pragma unroll
+    for (int blk = 0; blk < 4; ++blk) {
+        uint32_t an = 0, at = 0, ax = 0;
+#pragma unroll
+        for (int rr = 7; rr >= 0; --rr) {
+            const uint32_t r = (uint32_t)(blk * 8 + rr);
+            const uint32_t off = kRowPhase ? (row0 + r) * tpitch + ((tgt_phase + (row0 + r) * pstep) & 15u) + col_off
+                                           : base + r * tpitch;
+            const uint32_t w = lds_word<kAligned>(s_tgt, off);
+            an = an + an + (bytes_nonzero(w) >> 7);
+            at = at + at + (bytes_zero(w ^ 0x02020202u) >> 7);
+            ax = ax + ax + ((bytes_nonzero(w & 0xfcfcfcfcu) | bytes_zero(w ^ 0x03030303u)) >> 7);
+        }
+        nz[blk] = an;
+        tw[blk] = at;
+        ex[blk] = ax;
+    }
+    uint32_t exo[4];
+    transpose4(nz[0], nz[1], nz[2], nz[3], car);
+    transpose4(tw[0], tw[1], tw[2], tw[3], two);
+    transpose4(ex[0], ex[1], ex[2], ex[3], exo);
+    bool exotic = false;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (c < ncol) exotic |= (exo[c] & ab) != 0;  // (rows past the matrix's end have no absent bit)
+    return exotic;
 }
 
 // The staged target tile holds columns [c0, c0 + ncols) of the CTA's rows with a row pitch of
@@ -302,24 +345,12 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
         transpose4(tw[0], tw[1], tw[2], tw[3], two);
         const int ncol = min(4, ncols - 4 * q);
         bool exotic = false;
-        if ((e_or & 0xfcfcfcfcu) | (e_and & 0x01010101u)) {
-            // a byte outside {0,1,2} somewhere in this 32x4 block (or in the padding bytes of a
-            // ragged last quad / tail rows): redo it exactly, byte by byte
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (c >= ncol) continue;
-                uint32_t m_nz = 0, m_two = 0;
-                for (int r = 0; r < 32; ++r) {
-                    const int b = (int8_t)s_tgt[row_off(r) + c];
-                    const uint32_t isab = (ab >> r) & 1u;
-                    m_nz |= ((uint32_t)(b != 0) & isab) << r;
-                    m_two |= ((uint32_t)(b == 2) & isab) << r;
-                    exotic |= ((unsigned)b > 2u) && isab;
-                }
-                car[c] = m_nz;
-                two[c] = m_two;
-            }
-        }
+        if ((e_or & 0xfcfcfcfcu) | (e_and & 0x01010101u))
+            // a byte outside {0,1,2} somewhere in this 32x4 block (missing calls, multi-allelic dosages --
+            // or the padding bytes of a ragged last quad / tail rows): redone with the exact byte tests,
+            // out of line (the common path keeps its registers)
+            exotic = pack_block_exact<kAligned, kRowPhase>(s_tgt, base, (uint32_t)tpitch, tgt_phase, pstep, (uint32_t)(gl * 32),
+                                                           4u * q, ab, ncol, car, two);
         const size_t o = (size_t)(g0 + gl) * a.Tp + c0 + 4 * q;
         if (ncol == 4) {
             *reinterpret_cast<uint4 *>(a.carried + o) = make_uint4(car[0] & ab, car[1] & ab, car[2] & ab, car[3] & ab);
