@@ -350,6 +350,9 @@ __device__ __forceinline__ void fused_body(const FusedArgs &a) {
     const bool tbulk = nrows > 0 && (((uintptr_t)gtgt & 15) == 0) && ((tgt_bytes & 15u) == 0);
     const bool pbulk = nrows > 0 && (((uintptr_t)gpos & 15) == 0) && ((pos_bytes & 15u) == 0);
     auto issue_tile = [&]() {  // thread 0: the three spans to the TMA engine, the (small) positions first
+        // (a tile staged AGAIN lands on shared memory the streaming fallback wrote through the generic
+        //  proxy: order those writes before the async proxy's)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (pbulk) {
             mbar_expect_tx(&s_bar[0], pos_bytes);
             bulk_g2s(s_pos, gpos, pos_bytes, &s_bar[0]);

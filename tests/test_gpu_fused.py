@@ -196,3 +196,36 @@ def test_many_windows_per_cta_and_several_list_rounds(eng):
     _check(eng, ref, tgt, pos, ws[perm], we[perm])
     # an understated hint with this many windows: every round leaves windows to the streaming fallback
     _check(eng, ref[:4000], tgt[:4000], pos[:4000], ws[:1200], we[:1200], hint=60)
+
+
+def test_random_shapes_windows_and_genotypes(eng):
+    """Fuzz of the one-launch path: panel shapes, row counts, position densities, window lists (any
+    order, any length), genotype alphabets, parameters, hints and base alignments drawn at random;
+    every case twice (a race would show as a difference between the runs) and against the oracle."""
+    rng = np.random.default_rng(20260101)
+    for case in range(60):
+        R = int(rng.choice([1, 2, 3, 5, 16, 17, 40, 100, 129]))
+        T = int(rng.choice([1, 2, 7, 10, 31, 32, 33, 50, 64, 96, 127, 128]))
+        V = int(rng.choice([1, 5, 31, 33, 200, 777, 3000]))
+        span = int(rng.choice([V * 3, V * 40, V * 900]))
+        pos = np.sort(rng.choice(np.arange(1, span + 2), size=V, replace=False)).astype(np.int32)
+        ref = (rng.random((V, R)) < rng.choice([0.0, 0.02, 0.3])).astype(np.int8)
+        alphabet = [np.array([0, 1]), np.array([0, 1, 2]), np.array([0, 0, 0, 1, 2, -1]), np.arange(-3, 6)][int(rng.integers(0, 4))]
+        tgt = rng.choice(alphabet, size=(V, T)).astype(np.int8)
+        tgt[rng.random((V, T)) < 0.5] = 0
+        if rng.random() < 0.3:
+            ref[rng.random((V, R)) < 0.02] = -1
+        W = int(rng.choice([1, 3, 40, 300]))
+        ws = rng.integers(-10, span + 10, size=W).astype(np.int32)
+        we = (ws + rng.choice([0, 9, 50, span // 20 + 1, span // 3 + 1, span], size=W)).astype(np.int32)
+        if rng.random() < 0.4:
+            order = np.argsort(ws, kind="stable")
+            ws, we = ws[order], we[order]
+        params = [(5000, 5, -10000), (1, 1, 0), (7, 0, -3), (100, 2, -50)][int(rng.integers(0, 4))]
+        hint = None if rng.random() < 0.6 else int(rng.choice([1, 5, 64]))
+        off = int(rng.choice([0, 0, 1, 3]))
+        so, no = c_oracle.score_windows(ref, tgt, pos, ws, we, *params)
+        s1, n1 = _score(eng, ref, tgt, pos, ws, we, params, hint=hint, offset=off)
+        s2, n2 = _score(eng, ref, tgt, pos, ws, we, params, hint=hint, offset=off)
+        assert np.array_equal(s1, s2) and np.array_equal(n1, n2), f"case {case}: two runs differ"
+        assert np.array_equal(s1, so) and np.array_equal(n1, no), f"case {case}: R={R} T={T} V={V} W={W} hint={hint}"
