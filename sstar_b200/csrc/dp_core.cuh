@@ -482,11 +482,12 @@ struct StreamDP {
 // max -- survives the four running maxima when each keeps the index of its first maximiser (sites
 // are committed in index order, updates are strict), and the two candidates of site j (same class,
 // other class) tie-break to the smaller index.
-// Per site the caller's arrays get: row[k] = its row relative to `lo`, back[k] = -1 (no valid
-// predecessor) or (first << 1 | extended).  Returns false when the unit has more than kChainCap
+// Per site the caller's arrays get: row[k] = its row relative to `lo` (bit 15: M[k] is valid and >= 0;
+// windows of at most kChainMaxRows rows), back[k] = -1 (no valid predecessor) or (first << 1 | extended).  Returns false when the unit has more than kChainCap
 // sites (the caller then takes the pairwise kernels).  Genotypes in {0,1,2} only.
 // ---------------------------------------------------------------------------------------------
 constexpr int kChainCap = 128;
+constexpr int kChainMaxRows = 32767;  // rows per window the chain DP takes: row[] keeps bit 15 for "M >= 0"
 
 template <typename acc_t, typename LoadU32, typename LoadPos>
 SSTAR_HD bool walk_dp_unit_chain(LoadU32 ld, LoadPos ldpos, const uint32_t *carried, const uint32_t *two, int32_t Tp,
@@ -495,57 +496,64 @@ SSTAR_HD bool walk_dp_unit_chain(LoadU32 ld, LoadPos ldpos, const uint32_t *carr
     constexpr acc_t NEG = Sentinel<acc_t>::NEG, THR = Sentinel<acc_t>::THR;
     const acc_t bonus = (acc_t)bonus_i;
     const acc_t pen_eff = (max_mm >= 1) ? (acc_t)penalty_i : NEG;
-    acc_t A[2] = {NEG, NEG}, B[2] = {NEG, NEG};
-    int iA[2] = {-1, -1}, iB[2] = {-1, -1};
-    acc_t wait_p[kRingSlots], wait_v[kRingSlots];
-    int16_t wait_i[kRingSlots];  // index << 1 | class
-    uint32_t nonneg[kChainCap / 32] = {};  // bit k: M[k] is valid and >= 0
+    acc_t A0 = NEG, A1 = NEG, B0 = NEG, B1 = NEG;  // the four running maxima ...
+    int iA0 = -1, iA1 = -1, iB0 = -1, iB1 = -1;    // ... and the index of the first site attaining each
+    acc_t ring_p[kRingSlots], ring_v[kRingSlots];  // parked sites older than the previous one: p, v << 1 | class
+    acc_t pp = 0, pv = 0;                          // the previous site (waits in registers)
     acc_t top = NEG;
-    int q = 0, head = 0, n = 0, top_j = -1;
-    const int64_t p0 = ldpos(lo);
+    int k = 0, c = 0, top_j = -1;                  // sites seen, next site to commit
+    const auto p0 = ldpos(lo);
     const int gi0 = lo >> 5, gi1 = (hi - 1) >> 5;
+    auto commit = [&](int idx, acc_t pc, acc_t vc) {  // site idx becomes an eligible predecessor (index order, strict updates)
+        const acc_t v = vc >> 1;
+        if (vc & 1) { if (v - pc > A1) { A1 = v - pc; iA1 = idx; } if (v > B1) { B1 = v; iB1 = idx; } }
+        else        { if (v - pc > A0) { A0 = v - pc; iA0 = idx; } if (v > B0) { B0 = v; iB0 = idx; } }
+    };
     for (int gi = gi0; gi <= gi1; ++gi) {
-        uint32_t c = ld(carried + (size_t)gi * Tp + t);
-        if (gi == gi0) c &= 0xffffffffu << (lo & 31);
-        if (gi == gi1) c &= 0xffffffffu >> (31 - ((hi - 1) & 31));
-        if (c == 0) continue;
+        uint32_t cb = ld(carried + (size_t)gi * Tp + t);
+        if (gi == gi0) cb &= 0xffffffffu << (lo & 31);
+        if (gi == gi1) cb &= 0xffffffffu >> (31 - ((hi - 1) & 31));
+        if (cb == 0) continue;
         const uint32_t tw = ld(two + (size_t)gi * Tp + t);
-        while (c) {
-            const int b = ctz32(c);
-            c &= c - 1;
-            if (n >= kChainCap) return false;
+        while (cb) {
+            const int b = ctz32(cb);
+            cb &= cb - 1;
+            if (k >= kChainCap) return false;
             const int32_t r = (gi << 5) + b;
             const acc_t p = (acc_t)(ldpos(r) - p0);
             const int cls = (int)((tw >> b) & 1u);
-            while (q > 0) {  // sites >= 10 bp behind become eligible predecessors, in index order
-                const acc_t pi = wait_p[head];
-                if (p - pi < kMinPairDistance) break;
-                const acc_t v = wait_v[head];
-                const int wi = wait_i[head] >> 1, wc = wait_i[head] & 1;
-                if (v - pi > A[wc]) { A[wc] = v - pi; iA[wc] = wi; }
-                if (v > B[wc]) { B[wc] = v; iB[wc] = wi; }
-                head = (head + 1) & (kRingSlots - 1);
-                --q;
+            if (c == k - 1) {  // common case: only the previous site waits, in registers
+                if (p - pp >= kMinPairDistance) { commit(k - 1, pp, pv); c = k; }
+                else { ring_p[(k - 1) & (kRingSlots - 1)] = pp; ring_v[(k - 1) & (kRingSlots - 1)] = pv; }
+            } else if (c < k) {  // crowded sites: older ones wait in the ring
+                while (c < k) {
+                    acc_t pc, vc;
+                    if (c == k - 1) { pc = pp; vc = pv; }
+                    else            { pc = ring_p[c & (kRingSlots - 1)]; vc = ring_v[c & (kRingSlots - 1)]; }
+                    if (p - pc < kMinPairDistance) break;
+                    commit(c, pc, vc);
+                    ++c;
+                }
+                if (c < k) { ring_p[(k - 1) & (kRingSlots - 1)] = pp; ring_v[(k - 1) & (kRingSlots - 1)] = pv; }
             }
-            const acc_t ca = A[cls] + (p + bonus), cb = B[cls ^ 1] + pen_eff;
-            const acc_t m = imax(ca, cb);
+            const acc_t ca = (cls ? A1 : A0) + (p + bonus), cb2 = (cls ? B0 : B1) + pen_eff;
+            const int ia = cls ? iA1 : iA0, ib = cls ? iB0 : iB1;
+            const acc_t m = imax(ca, cb2);
+            const bool valid = m > THR;
             int first = -1;
-            if (m > THR) first = ca > cb ? iA[cls] : (cb > ca ? iB[cls ^ 1] : (iA[cls] < iB[cls ^ 1] ? iA[cls] : iB[cls ^ 1]));
-            row[n] = (uint16_t)(r - lo);
-            back[n] = first < 0 ? (int16_t)-1 : (int16_t)((first << 1) | (int)((nonneg[first >> 5] >> (first & 31)) & 1u));
-            if (m > THR && m >= 0) nonneg[n >> 5] |= 1u << (n & 31);
-            if (m > THR && m > top) { top = m; top_j = n; }
-            const int tail = (head + q) & (kRingSlots - 1);
-            wait_p[tail] = p;
-            wait_v[tail] = imax(m, (acc_t)0);
-            wait_i[tail] = (int16_t)((n << 1) | cls);
-            ++q;
-            ++n;
+            if (valid) first = ca > cb2 ? ia : (cb2 > ca ? ib : (ia < ib ? ia : ib));
+            // back: -1 (no valid predecessor) or first << 1 | (M[first] >= 0: the chain is extended there)
+            back[k] = first < 0 ? (int16_t)-1 : (int16_t)((first << 1) | (int)(row[first] >> 15));
+            row[k] = (uint16_t)((uint32_t)(r - lo) | ((valid && m >= 0) ? 0x8000u : 0u));
+            if (valid && m > top) { top = m; top_j = k; }
+            pp = p;
+            pv = (imax(m, (acc_t)0) << 1) | (acc_t)cls;
+            ++k;
         }
     }
-    n_out = n;
-    top_j_out = (n <= 2) ? -1 : top_j;
-    score_out = (n <= 2 || top_j < 0) ? kNegInf64 : (int64_t)top;
+    n_out = k;
+    top_j_out = (k <= 2) ? -1 : top_j;
+    score_out = (k <= 2 || top_j < 0) ? kNegInf64 : (int64_t)top;
     return true;
 }
 
@@ -567,11 +575,11 @@ template <typename Out>
 SSTAR_HD void chain_rows(const uint16_t *row, const int16_t *back, int top_j, int len, Out out) {
     int k = len - 1;
     for (int j = top_j; j >= 0 && k >= 0;) {
-        out(k--, row[j]);
+        out(k--, (uint16_t)(row[j] & 0x7fffu));
         const int b = back[j];
         if (b < 0) break;
         if (b & 1) j = b >> 1;
-        else { if (k >= 0) out(k--, row[b >> 1]); break; }
+        else { if (k >= 0) out(k--, (uint16_t)(row[b >> 1] & 0x7fffu)); break; }
     }
 }
 

@@ -10,7 +10,7 @@
 //     the chain ends at the FIRST j attaining max_j M[j].
 //
 // snp_count_kernel, one thread per unit (a CTA per window x run of columns): #absent rows and the exotic
-// flag of the window, then -- in clean windows (genotypes in {0,1,2}, int32-safe scores, at most 65,535
+// flag of the window, then -- in clean windows (genotypes in {0,1,2}, int32-safe scores, at most 32,767
 // rows) -- the O(n) prefix-max DP with backpointers right there (dp_core.cuh: walk_dp_unit_chain: each
 // running maximum keeps its first maximiser; thread-local backpointers): score, SNP count and chain
 // length of the unit in ONE walk of its plane words.  Units it cannot take (a window with other
@@ -76,18 +76,19 @@ struct ChainPos {
 
 // a window whose units the O(n) chain DP takes (the same test in the count and the fill kernel)
 __device__ __forceinline__ bool chain_window(const SnpSetArgs &a, int w, int32_t lo, int32_t hi, uint32_t ex) {
-    return hi > lo && ex == 0 && hi - lo <= 65535 &&
+    return hi > lo && ex == 0 && hi - lo <= kChainMaxRows &&
            score_bound((int64_t)a.win_plast[w] - (int64_t)a.win_pfirst[w], hi - lo, a.bonus, a.penalty) < kSmallBound;
 }
 
 // grid.x = W * ceil(T / blockDim.x): one window x one run of columns per CTA
 __global__ void __launch_bounds__(kCountThreads) snp_count_kernel(const __grid_constant__ SnpSetArgs a) {
-    __shared__ int s_nabs;
+    __shared__ int s_nabs, s_nwork;
     __shared__ uint32_t s_ex;
+    __shared__ uint8_t s_work[kCountThreads];  // threads (columns of this CTA) whose unit takes the chain DP
     const int tid = threadIdx.x, bd = blockDim.x;
     const int tchunks = (a.T + bd - 1) / bd;
     const int w = blockIdx.x / tchunks, t = (blockIdx.x % tchunks) * bd + tid;
-    if (tid == 0) { s_nabs = 0; s_ex = 0; }
+    if (tid == 0) { s_nabs = 0; s_ex = 0; s_nwork = 0; }
     __syncthreads();
     const int32_t lo = a.win_lo[w], hi = a.win_hi[w];
     const int wi0 = lo >> 5, wi1 = (hi - 1) >> 5;
@@ -109,8 +110,7 @@ __global__ void __launch_bounds__(kCountThreads) snp_count_kernel(const __grid_c
     }
     __syncthreads();
     if (blockIdx.x % tchunks == 0 && tid == 0) a.win_ex[w] = s_ex;
-    int n = 0, len = 0;
-    int64_t score = INT64_MIN;
+    int n = 0;
     if (t < a.T && hi > lo) {  // n from popcounts: two thirds of the units of sparse data end here (n <= 2: NaN)
         const uint32_t *cp = a.carried + (size_t)wi0 * a.Tp + t;
         for (int gi = wi0; gi <= wi1; ++gi, cp += a.Tp) {
@@ -118,23 +118,27 @@ __global__ void __launch_bounds__(kCountThreads) snp_count_kernel(const __grid_c
             n += __popc(__ldg(cp) & rm);
         }
     }
-    bool scored = n <= 2;
-    if (t < a.T && !scored && n <= kChainCap && chain_window(a, w, lo, hi, s_ex)) {
-        // score and chain length by the O(n) DP with backpointers (the plane words are in L1 by now)
-        uint16_t row[kChainCap];
-        int16_t back[kChainCap];
-        int top_j = -1, n2;
-        scored = walk_dp_unit_chain<int32_t>(ChainLdg(), ChainPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus, a.penalty,
-                                             a.max_mm, row, back, n2, top_j, score);
-        if (scored) len = chain_length(back, top_j);
+    // Units with n > 2 in a window the O(n) chain DP takes go on the CTA's work list and are then
+    // shared out evenly: a third of the units of sparse data have work, and a warp whose lanes each ran
+    // their own column would idle two lanes in three.
+    const bool dp_unit = t < a.T && n > 2 && n <= kChainCap && chain_window(a, w, lo, hi, s_ex);
+    const bool queued = t < a.T && n > 2 && !dp_unit;  // other genotypes in the window, too many sites, int64 scores
+    const int lane = tid & 31;
+    {
+        const uint32_t dm = __ballot_sync(0xffffffffu, dp_unit);
+        if (dm) {
+            const int leader = __ffs(dm) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&s_nwork, __popc(dm));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (dp_unit) s_work[base + __popc(dm & ((1u << lane) - 1u))] = (uint8_t)tid;
+        }
     }
-    const bool queued = t < a.T && !scored;
     if (t < a.T) {
         const size_t o = (size_t)w * a.T + t;
         a.nsnp[o] = (hi - lo) - s_nabs + n;
-        if (!queued) { a.score[o] = score; a.set_len[o] = len; }
+        if (!queued && !dp_unit) { a.score[o] = INT64_MIN; a.set_len[o] = 0; }  // n <= 2 (or an empty window): NaN
     }
-    const int lane = tid & 31;
     const uint32_t qm = __ballot_sync(0xffffffffu, queued);
     if (qm) {
         const int leader = __ffs(qm) - 1;
@@ -143,14 +147,35 @@ __global__ void __launch_bounds__(kCountThreads) snp_count_kernel(const __grid_c
         base = __shfl_sync(0xffffffffu, base, leader);
         if (queued) a.queue[base + __popc(qm & ((1u << lane) - 1u))] = w * a.T + t;
     }
-    const bool chained = t < a.T && scored && len > 0;  // the fill pass's work list, from the far end
-    const uint32_t cm = __ballot_sync(0xffffffffu, chained);
-    if (cm) {
-        const int leader = __ffs(cm) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(a.queue_n + 1, __popc(cm));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (chained) a.queue[(int64_t)a.W * a.T - 1 - (base + __popc(cm & ((1u << lane) - 1u)))] = w * a.T + t;
+    __syncthreads();
+    // ---- the work list: score and chain length by the O(n) DP with backpointers
+    const int n_work = s_nwork;
+    for (int u0 = 0; u0 < n_work; u0 += bd) {
+        const int u = u0 + tid;
+        bool chained = false;
+        int tu = 0;
+        if (u < n_work) {
+            tu = (blockIdx.x % tchunks) * bd + s_work[u];
+            uint16_t row[kChainCap];
+            int16_t back[kChainCap];
+            int top_j = -1, n2;
+            int64_t score;
+            walk_dp_unit_chain<int32_t>(ChainLdg(), ChainPos{a.pos}, a.carried, a.two, a.Tp, tu, lo, hi, a.bonus, a.penalty, a.max_mm,
+                                        row, back, n2, top_j, score);
+            const int len = chain_length(back, top_j);
+            const size_t o = (size_t)w * a.T + tu;
+            a.score[o] = score;
+            a.set_len[o] = len;
+            chained = len > 0;
+        }
+        const uint32_t cm = __ballot_sync(0xffffffffu, chained);  // the fill pass's work list, from the far end
+        if (cm) {
+            const int leader = __ffs(cm) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(a.queue_n + 1, __popc(cm));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (chained) a.queue[(int64_t)a.W * a.T - 1 - (base + __popc(cm & ((1u << lane) - 1u)))] = w * a.T + tu;
+        }
     }
 }
 

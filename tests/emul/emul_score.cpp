@@ -312,6 +312,7 @@ extern "C" int emul_chain_windows(const int8_t *ref, const int8_t *tgt, const in
             const size_t u = (size_t)w * T + t;
             score[u] = kNegInf64; set_len[u] = 0; fast[u] = 1;
             if (hi <= lo) continue;
+            if (hi - lo > kChainMaxRows) { fast[u] = 0; continue; }
             int n = 0, top_j = -1;
             int64_t sc = kNegInf64;
             const int64_t span = (int64_t)pos[hi - 1] - (int64_t)pos[lo];
