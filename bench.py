@@ -135,9 +135,15 @@ def shared_config(wk, st, world):
             "partition": "one rank: the whole chromosome" if world == 1 else
                          f"sstar_b200.sharding.plan_window_shards: {world} contiguous window ranges, each rank holds its "
                          "rows + the win_len - win_step halo; result blocks gathered in one shared host table",
-            "l2": "GPU arm: flushed between timed iterations (256 MiB device write); CPU arm: not applicable",
-            "timing": "GPU arm: CUDA events on the launching stream around each step (value), wall clock around the "
-                      "host-buffer call incl. the stream sync (e2e), max over ranks; CPU arm: wall clock"}
+            "l2": "GPU arm, value: inputs larger than the L2 -- consecutive steps read DISTINCT device copies of the rows "
+                  "(a ring of copies of 256 MB or more together; no flush needed); single_pass, e2e and the large "
+                  "shapes (at_scale, strong): L2 flushed between timed iterations (256 MiB device write); CPU arm: "
+                  "not applicable",
+            "timing": "GPU arm, value: exactly K steps between two CUDA events on the launching stream, barrier + device "
+                      "synchronize on both sides, max over ranks; the steps are independent calls "
+                      "(SSTAR_B200_FLAG_INDEPENDENT) replayed from one CUDA graph per ring, so consecutive one-launch "
+                      "kernels overlap; e2e: wall clock around the host-buffer call incl. the stream sync, max over "
+                      "ranks; CPU arm: wall clock"}
 
 
 def algorithmic_bytes(st):
@@ -369,6 +375,62 @@ class ShardCase:
         self.eng.score_pinned(p["ref"], p["tgt"], p["pos"], p["ws"], p["we"], self.score_p, self.nsnp_p,
                               *PARAMS, max_win_variants=self.hint, sync=True, staged=staged)
 
+    def make_stream(self, min_bytes=256 << 20, max_ring=64):
+        """A ring of DISTINCT device copies of this rank's rows (together larger than the L2) and ONE graph
+        that scores them one after the other (``ScoreEngine.plan_device_stream``: the calls carry
+        SSTAR_B200_FLAG_INDEPENDENT, so consecutive one-launch kernels overlap).  One step = one pass over
+        one copy; consecutive steps read different copies, so every step's rows come from HBM."""
+        torch = self.torch
+        nbytes = self.V * (self.R + self.T + 4) + 8 * self.W
+        self.ring = int(min(max_ring, max(2, -(-min_bytes // max(nbytes, 1)))))
+        self.ring_bytes = self.ring * nbytes
+        self.ring_cases = []
+        for _ in range(self.ring):
+            out = (torch.empty_like(self.score_d), torch.empty_like(self.nsnp_d))
+            self.ring_cases.append(tuple(self.d[k].clone() for k in ("ref", "tgt", "pos", "ws", "we")) + (out,))
+        self._stream_plans = {}
+
+    def _stream_plan(self, n):
+        if n not in self._stream_plans:
+            self._stream_plans[n] = self.eng.plan_device_stream(self.ring_cases[:n], *PARAMS, max_win_variants=self.hint,
+                                                                flags=self.flags)
+        return self._stream_plans[n]
+
+    def run_stream(self, steps):
+        """Enqueue exactly ``steps`` passes (whole rings, then the remainder); returns the launches enqueued."""
+        full, rest = divmod(steps, self.ring)
+        n = 0
+        if full:
+            plan = self._stream_plan(self.ring)
+            for _ in range(full):
+                plan.run()
+            n += full * plan.launches
+        if rest:
+            plan = self._stream_plan(rest)
+            plan.run()
+            n += plan.launches
+        return n
+
+    def timed_stream(self, steps, barrier):
+        """EXACTLY ``steps`` passes between two CUDA events on the launching stream, a barrier + device
+        synchronize on both sides.  No flush: the ring of inputs is larger than the L2."""
+        torch = self.torch
+        self._stream_plan(self.ring)
+        if steps % self.ring:
+            self._stream_plan(steps % self.ring)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        n = self.run_stream(steps)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1), n
+
+    def stream_tables_equal(self, used):
+        """Every ring copy scored in the timed region holds the tables of ``step_device`` (same rows)."""
+        t = self.torch
+        return all(bool(t.equal(c[5][0], self.score_d) and t.equal(c[5][1], self.nsnp_d)) for c in self.ring_cases[:used])
+
     def timed(self, fn, steps, flush, barrier):
         """K steps, L2 flushed before each, CUDA events around each step on the launching stream."""
         torch = self.torch
@@ -419,7 +481,7 @@ def cut_windows(shards, W, radius=6):
     return sorted(sel)
 
 
-def roofline_block(name, st, k, tot_ms, pack_ms, score_ms, launches):
+def roofline_block(name, st, k, tot_ms, pack_ms, score_ms, launches, stream=None):
     """Pass-level and per-kernel HBM roofline (SURVEY.md section 8d bytes; measured peak)."""
     ab = algorithmic_bytes(st)
     peak, peak_src = measured_peak()
@@ -452,14 +514,18 @@ def roofline_block(name, st, k, tot_ms, pack_ms, score_ms, launches):
 
     pipe = ab["pipeline"] / (tot_ms / k * 1e-3) / 1e9
     fused = launches == 1
+    kname = "fused_score_pair_kernel" if stream else "fused_score_kernel"
     return {
         "bound": "hbm",
-        "kernel": ("one pass = ONE launch of fused_score_kernel (window bounds + TMA row staging + pack + chain DP per "
-                   "CTA of a few windows; csrc/fused_kernels.cuh)" if fused else
+        "kernel": (f"one pass = ONE launch of {kname} (window bounds + TMA row staging + pack + chain DP per "
+                   "CTA of a few windows; csrc/fused_kernels.cuh)" +
+                   (f"; average launch duration = the timed region / its {stream['launches']} launches, which overlap "
+                    f"(independent calls, two CTAs per SM): ring of {stream['ring']} input copies = "
+                    f"{stream['ring_bytes'] / 1e6:.0f} MB" if stream else "") if fused else
                    "one pass = prep_kernel (pack + window bounds) -> score_group_kernel (-> score_pairwise_kernel only "
                    "when a window was routed to it)"),
         "achieved": pipe, "peak": peak, "unit": "GB/s", "frac": pipe / peak,
-        "traffic": (recorded_traffic(name, "fused_score_kernel") if fused else
+        "traffic": ((recorded_traffic(name, kname) or recorded_traffic(name, "fused_score_kernel")) if fused else
                     sum(filter(None, (recorded_traffic(name, x) for x in ("prep_kernel", "score_group_kernel")))) or None),
         "traffic_source": "profiles/traffic.json (per-launch dram bytes of one ncu --set full capture; null when the "
                           "workload has no capture)",
@@ -850,11 +916,28 @@ def run_ours(args, world, rank, local):
         case.step_e2e()
         case.step_e2e(staged=True)
 
+    # the headline region: small shapes (the one-launch kernel) are timed as a STREAM of passes over a ring
+    # of distinct device copies larger than the L2; shapes that exceed the L2 by themselves keep one
+    # flushed, event-bracketed pass per step
+    use_stream = (not large) and (not args.no_stream) and (not args.no_graph)
+    if use_stream:
+        case.make_stream()
+        case.run_stream(min(k, 2 * case.ring))  # warm-up of the stream graphs (captures them, too)
+        torch.cuda.synchronize(dev)
+
     sampler = ClockSampler(local)
     sampler.start()
     # ---- region A: device-resident rows, the whole pass per step
     sampler.mark()
-    tot_ms = case.timed(case.step_device, k, flush, barrier)
+    single_k = k if not use_stream else min(k, 200)
+    single_ms = case.timed(case.step_device, single_k, flush, barrier)
+    stream_launches = None
+    if use_stream:
+        tot_ms, stream_launches = case.timed_stream(k, barrier)
+        if not case.stream_tables_equal(min(k, case.ring)):
+            raise SystemExit("bench: a pass of the timed stream differs from the single pass")
+    else:
+        tot_ms = single_ms
     sampler.mark()
     # ---- per-kernel split for the roofline: the pack launch alone, the DP launches alone
     pack_ms = case.timed(case.step_pack, k, flush, barrier)
@@ -875,7 +958,9 @@ def run_ours(args, world, rank, local):
     sampler.join(timeout=2)
 
     same = case.device_equals_host_block()
-    tot_ms, e2e_ms, pack_ms, score_ms, staged_ms = rk.reduce([tot_ms, e2e_s * 1e3, pack_ms, score_ms, staged_s * 1e3], "max")
+    case_ring = (case.ring, case.ring_bytes) if use_stream else None
+    tot_ms, e2e_ms, pack_ms, score_ms, staged_ms, single_ms = rk.reduce(
+        [tot_ms, e2e_s * 1e3, pack_ms, score_ms, staged_s * 1e3, single_ms], "max")
     same = rk.reduce([1.0 if same else 0.0], "min")[0] == 1.0
     per_rank = rk.gather({"rank": rank, "windows": [w0, w1], "rows": [k0, k1], "units": (w1 - w0) * T,
                           "hbm_bytes": (k1 - k0) * (R + T)})
@@ -942,8 +1027,10 @@ def run_ours(args, world, rank, local):
             "notes": {"arithmetic": "int8 genotypes -> bit-planes -> int32 max-plus DP (int64 when a window's score "
                                     "bound exceeds 2^28) -> int64 scores, int32 SNP counts; bit-exact",
                       "rank0_cpu_binding": numa,
-                      "launch": ("direct launches" if args.no_graph
-                                 else "CUDA graph replay of the pass (ScoreEngine.plan_device)") +
+                      "launch": ("direct launches" if args.no_graph else
+                                 "a stream of independent passes: one CUDA graph per ring of input copies "
+                                 "(ScoreEngine.plan_device_stream)" if use_stream else
+                                 "CUDA graph replay of the pass (ScoreEngine.plan_device)") +
                                 ("; one-launch kernel disabled (--no-fused)" if args.no_fused else ""),
                       "collectives_in_timed_region": "none (NCCL: barriers and the max / sum of the timings only)"},
             "ranks": per_rank,
@@ -958,9 +1045,16 @@ def run_ours(args, world, rank, local):
                            + "result blocks stored in place into the shared host table (D2H copies from 8 MB); wall "
                              "clock incl. the stream sync; the gather is part of it (there is nothing left to do after)",
                     "staged_copies_ms_per_step": staged_ms / k},
-            "gpu_launches": int(launches_per_step * k),
+            "gpu_launches": int(stream_launches if use_stream else launches_per_step * k),
             "kernels_per_step": int(launches_per_step),
-            "roofline": roofline_block(wk["name"], st, k, tot_ms, pack_ms, score_ms, int(launches_per_step)),
+            "single_pass": {"ms_per_step": single_ms / single_k, "value": total_units / (single_ms / single_k * 1e-3),
+                            "unit": UNIT, "steps": single_k,
+                            "note": "ONE pass at a time: L2 flushed (256 MiB device write) before it, CUDA events around "
+                                    "the one graph replay -- the latency of a lone call, event-to-event floor of an "
+                                    "empty kernel after a flush (about 6 us) included"},
+            "roofline": roofline_block(wk["name"], st, k, tot_ms, pack_ms, score_ms, int(launches_per_step),
+                                       stream={"launches": int(stream_launches), "ring": case_ring[0],
+                                               "ring_bytes": case_ring[1]} if use_stream else None),
             "cpu_baseline": cpu,
             "clocks": sampler.summary(),
             "parity": parity,
@@ -998,6 +1092,8 @@ def main():
     ap.add_argument("--only-device", action="store_true", help="profiling aid: run only the device-resident passes")
     ap.add_argument("--no-fused", action="store_true", help="headline workload: take the pack -> score launches instead of "
                                                             "the one-launch kernel (comparison)")
+    ap.add_argument("--no-stream", action="store_true", help="headline: one flushed, event-bracketed pass per step (the "
+                                                             "round-1 method) instead of the stream of independent passes")
     ap.add_argument("--no-graph", action="store_true", help="launch the kernels directly instead of replaying the CUDA graph")
     args = ap.parse_args()
     world, rank, local = dist_setup()

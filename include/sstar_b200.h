@@ -64,6 +64,14 @@ extern "C" {
  * windows), everything else pack -> score launches.  Both give identical results. */
 #define SSTAR_B200_FLAG_NO_FUSED 128        /* never the one-launch kernel */
 #define SSTAR_B200_FLAG_FORCE_FUSED 256     /* always (T <= 128), whatever the size and the hint */
+/* A stream of independent calls (one chromosome after the other, sstar/preprocess.py:90-112): calls
+ * that carry this flag promise that they touch no buffer a NEIGHBOURING flagged call on the same
+ * stream reads or writes, so consecutive flagged one-launch kernels may overlap (programmatic
+ * dependent launch, no wait: the next chromosome's CTAs load their tiles while this one's finish
+ * their DP).  Everything else on the stream -- unflagged calls, copies, events -- keeps full stream
+ * order after all flagged calls before it.  Ignored by the pack -> score launches (they share the
+ * workspace). */
+#define SSTAR_B200_FLAG_INDEPENDENT 512
 
 typedef struct sstar_b200_options {
     int32_t algo;             /* SSTAR_B200_ALGO_* */

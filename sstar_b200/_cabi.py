@@ -35,6 +35,7 @@ FLAG_ZERO_COPY_INPUTS = 32
 FLAG_COPY_INPUTS = 64
 FLAG_NO_FUSED = 128
 FLAG_FORCE_FUSED = 256
+FLAG_INDEPENDENT = 512
 
 
 class SstarB200Error(RuntimeError):

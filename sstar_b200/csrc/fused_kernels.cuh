@@ -56,6 +56,7 @@ struct FusedArgs {
     uint32_t ref_tile_bytes, tgt_tile_bytes;  // shared memory reserved per matrix (incl. alignment slack)
     uint32_t smem_bytes;                      // the launch's dynamic shared memory
     int32_t bonus, max_mm, penalty;
+    int32_t early_trigger;  // SSTAR_B200_FLAG_INDEPENDENT: the next flagged launch may start under this one
     int64_t *score;
     int32_t *nsnp;
 };
@@ -310,6 +311,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs &a) {
     constexpr int nwarps = kThreads / 32;
     constexpr int kPerThread = (kFusedListCap + kThreads - 1) / kThreads;  // windows a thread examines per round
     const bool replicates = a.seg != nullptr;
+    if (a.early_trigger) pdl_launch_dependents();  // (never followed by a wait: flagged calls are independent)
     FUSED_STAMP(0);
 
     // ---- shared-memory map
@@ -561,6 +563,12 @@ __device__ __forceinline__ void fused_body(const FusedArgs &a) {
 }
 
 __global__ void __launch_bounds__(kFusedThreads, 1) fused_score_kernel(const __grid_constant__ FusedArgs a) {
+    fused_body<kFusedThreads>(a);
+}
+
+// the same body within 64 registers: two CTAs per SM, for streams of independent calls
+// (SSTAR_B200_FLAG_INDEPENDENT) whose consecutive launches overlap
+__global__ void __launch_bounds__(kFusedThreads, 2) fused_score_pair_kernel(const __grid_constant__ FusedArgs a) {
     fused_body<kFusedThreads>(a);
 }
 

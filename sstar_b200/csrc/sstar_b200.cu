@@ -386,6 +386,10 @@ int launch_fused(cudaStream_t st, const int8_t *d_ref, const int8_t *d_tgt, cons
     if (T > 128 || W <= 0) return 0;  // (a window's columns must fit one CTA: T <= the replicate kernel's 256 threads)
     const bool force = (flags & SSTAR_B200_FLAG_FORCE_FUSED) != 0;
     const bool disjoint = d_seg != nullptr;  // replicates: no row is shared by two windows
+    const bool indep = (flags & SSTAR_B200_FLAG_INDEPENDENT) != 0;
+    // independent calls in a stream take the 64-register instance, so that the next call's CTA fits an
+    // SM beside this one's (two 512-thread CTAs and two tiles per SM)
+    static const int pair_env = [] { const char *e = getenv("SSTAR_B200_FUSED_PAIR"); return e ? atoi(e) : 1; }();
     if (!force) {
         if (hint <= 0) return 0;  // the tile is sized by the largest window
         // overlapping windows re-read rows through the L2: only while the whole input sits there
@@ -426,21 +430,29 @@ int launch_fused(cudaStream_t st, const int8_t *d_ref, const int8_t *d_tgt, cons
             const int v = e ? atoi(e) : 0;
             return v >= 32 ? v / 32 * 32 : 0;
         }();
-        int32_t S = home_env;
-        if (S == 0) {
-            const int nsm = num_sms();
-            S = (int32_t)(((V + nsm - 1) / nsm + 31) / 32 * 32);
-            int32_t slots = kFusedThreads / T;
-            if (slots > kFusedMaxSlots) slots = kFusedMaxSlots;
-            const int64_t s_max = V > 0 ? (V * slots / (W > 0 ? W : 1)) / 32 * 32 : 32;  // ~`slots` windows per CTA
-            if (S > s_max) S = (int32_t)s_max;
-            if (S < 64) S = 64;
-            if (S > 1024) S = 1024;
-        }
-        limit = (size_t)160 << 10;  // one 512-thread CTA per SM is the plan
-        for (;; S = (S / 2 + 31) / 32 * 32) {
-            cap = (S + rows1 + 31) / 32;
-            if (bytes_for(cap) <= limit || S == 32) break;
+        int32_t slots = kFusedThreads / T;
+        if (slots > kFusedMaxSlots) slots = kFusedMaxSlots;
+        const int64_t s_max = V > 0 ? (V * slots / (W > 0 ? W : 1)) / 32 * 32 : 32;  // ~`slots` windows per CTA
+        int32_t S = 0;
+        // a call of its own: one 512-thread CTA per SM, one wave, every SM busy from the first instruction.
+        // One of a stream of independent calls (tried first when flagged): the SMs are kept busy by the
+        // neighbouring calls, so a CTA takes as many windows as it scores at a time (fewer CTAs, less
+        // halo re-read and re-packed) and its tile leaves room for a CTA of the next call beside it
+        for (int stream_mode = (indep && pair_env) ? 1 : 0; stream_mode >= 0; --stream_mode) {
+            S = home_env;
+            if (S == 0) {
+                const int nsm = num_sms();
+                S = stream_mode ? (int32_t)(s_max < 1024 ? s_max : 1024) : (int32_t)(((V + nsm - 1) / nsm + 31) / 32 * 32);
+                if (S > s_max) S = (int32_t)s_max;
+                if (S < 64) S = 64;
+                if (S > 1024) S = 1024;
+            }
+            limit = stream_mode ? ((size_t)111 << 10) : ((size_t)160 << 10);
+            for (;; S = stream_mode ? S - 32 : (S / 2 + 31) / 32 * 32) {
+                cap = (S + rows1 + 31) / 32;
+                if (bytes_for(cap) <= limit || S == 32) break;
+            }
+            if (bytes_for(cap) <= limit) break;
         }
         a.home_rows = S;
         a.wg = 0;
@@ -465,12 +477,16 @@ int launch_fused(cudaStream_t st, const int8_t *d_ref, const int8_t *d_tgt, cons
     a.V = (int32_t)V; a.R = R; a.T = T; a.W = W;
     a.bonus = bonus; a.max_mm = max_mm; a.penalty = penalty;
     a.score = d_score; a.nsnp = d_nsnp;
-    static SmemGrant fused_grant, rep_grant;
+    a.early_trigger = indep ? 1 : 0;
+    static SmemGrant fused_grant, rep_grant, pair_grant;
+    const bool pair = indep && !disjoint && pair_env && 2 * (smem + 2048) <= ((size_t)227 << 10);
     cudaError_t e = disjoint ? grant_smem(rep_grant, fused_score_rep_kernel, smem)
+                    : pair   ? grant_smem(pair_grant, fused_score_pair_kernel, smem)
                              : grant_smem(fused_grant, fused_score_kernel, smem);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "cudaFuncSetAttribute(fused): %s", cudaGetErrorString(e));
-    e = disjoint ? launch(fused_score_rep_kernel, grid, kFusedRepThreads, smem, st, false, a)
-                 : launch(fused_score_kernel, grid, kFusedThreads, smem, st, false, a);
+    e = disjoint ? launch(fused_score_rep_kernel, grid, kFusedRepThreads, smem, st, indep, a)
+        : pair   ? launch(fused_score_pair_kernel, grid, kFusedThreads, smem, st, indep, a)
+                 : launch(fused_score_kernel, grid, kFusedThreads, smem, st, indep, a);
     if (e != cudaSuccess) return fail(SSTAR_B200_ECUDA, "fused_score_kernel launch: %s", cudaGetErrorString(e));
     return 1;
 }

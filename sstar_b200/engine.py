@@ -266,6 +266,35 @@ class ScoreEngine:
             launches = self.launches
         return ScorePlan(graph, out[0], out[1], launches, (ref_d, tgt_d, pos_d, ws_d, we_d, self._dev.get("ws")))
 
+    def plan_device_stream(self, cases, match_bonus=5000, max_mismatch=5, mismatch_penalty=-10000, algo="auto",
+                           max_win_variants=0, flags=0):
+        """Capture a STREAM of independent passes -- one chromosome after the other, the loop of
+        sstar/preprocess.py:90-112 -- into ONE graph.  ``cases``: a list of
+        ``(ref_d, tgt_d, pos_d, ws_d, we_d, (score, nsnp))`` over DISTINCT buffers.  Every call carries
+        ``SSTAR_B200_FLAG_INDEPENDENT``: consecutive one-launch kernels overlap (the next chromosome's
+        CTAs stage their tiles while this one's finish their DP).  Returns a :class:`ScorePlan` whose
+        ``outs`` lists the result tables in order."""
+        torch = self.torch
+        kw = dict(match_bonus=match_bonus, max_mismatch=max_mismatch, mismatch_penalty=mismatch_penalty,
+                  algo=algo, max_win_variants=max_win_variants, flags=int(flags) | _cabi.FLAG_INDEPENDENT)
+        with torch.cuda.device(self.tdev):
+            side = torch.cuda.Stream(self.tdev)
+            side.wait_stream(torch.cuda.current_stream(self.tdev))
+            with torch.cuda.stream(side):  # warm-up: sizes the workspace, sets kernel attributes
+                for c in cases[:1]:
+                    self.score_device(*c[:5], out=c[5], **kw)
+            torch.cuda.current_stream(self.tdev).wait_stream(side)
+            side.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            launches = 0
+            with torch.cuda.graph(graph):
+                for c in cases:
+                    self.score_device(*c[:5], out=c[5], **kw)
+                    launches += self.launches
+        plan = ScorePlan(graph, cases[0][5][0], cases[0][5][1], launches, (cases, self._dev.get("ws")))
+        plan.outs = [c[5] for c in cases]
+        return plan
+
     def plan_replicates_device(self, ref_d, tgt_d, pos_d, rep_off_d, win_start, win_end, match_bonus=5000,
                                max_mismatch=5, mismatch_penalty=-10000, algo="auto", max_win_variants=0, out=None,
                                flags=0):

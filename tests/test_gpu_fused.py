@@ -229,3 +229,69 @@ def test_random_shapes_windows_and_genotypes(eng):
         s2, n2 = _score(eng, ref, tgt, pos, ws, we, params, hint=hint, offset=off)
         assert np.array_equal(s1, s2) and np.array_equal(n1, n2), f"case {case}: two runs differ"
         assert np.array_equal(s1, so) and np.array_equal(n1, no), f"case {case}: R={R} T={T} V={V} W={W} hint={hint}"
+
+
+def test_stream_of_independent_calls(eng):
+    """SSTAR_B200_FLAG_INDEPENDENT: a stream of DIFFERENT chromosomes (own buffers each) scored back to
+    back -- direct launches, then one graph (ScoreEngine.plan_device_stream) replayed twice; consecutive
+    one-launch kernels overlap.  Every table against the oracle; an unflagged call and a copy behind the
+    stream keep full stream order."""
+    import torch
+    from oracle import tiling_port
+    from sstar_b200 import _cabi
+    from sstar_b200.engine import max_window_variants
+    from sstar_b200.synth import synth_chromosome
+    dev = eng.tdev
+    params = (5000, 5, -10000)
+    chroms, want = [], []
+    for i, (length, n_ref, n_tgt, phased) in enumerate([(900_000, 30, 20, False), (400_000, 100, 50, False),
+                                                         (1_500_000, 10, 25, True), (300_000, 5, 3, False),
+                                                         (2_000_000, 60, 40, False), (50_000, 4, 64, True)]):
+        ref, tgt, pos = synth_chromosome(length=length, n_ref=n_ref, n_tgt=n_tgt, phased=phased, seed=100 + i)
+        if i == 2:
+            tgt = tgt.copy()
+            tgt[::97, ::3] = -1  # missing calls: the general walk inside the one-launch kernel
+        wins = tiling_port.split_windows(pos, 50_000, 10_000)
+        ws = np.asarray([w[0] for w in wins], dtype=np.int32)
+        we = np.asarray([w[1] for w in wins], dtype=np.int32)
+        chroms.append((ref, tgt, pos.astype(np.int32), ws, we))
+        want.append(c_oracle.score_windows(ref, tgt, pos, ws, we, *params))
+    hint = max(max_window_variants(c[2], c[3], c[4]) for c in chroms)
+    cases = []
+    for ref, tgt, pos, ws, we in chroms:
+        d = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (ref, tgt, pos, ws, we)]
+        out = (torch.zeros((len(ws), tgt.shape[1]), dtype=torch.int64, device=dev),
+               torch.zeros((len(ws), tgt.shape[1]), dtype=torch.int32, device=dev))
+        cases.append(tuple(d) + (out,))
+
+    def check(tag):
+        torch.cuda.synchronize()
+        for i, c in enumerate(cases):
+            assert np.array_equal(c[5][0].cpu().numpy(), want[i][0]), f"{tag}: chromosome {i} scores"
+            assert np.array_equal(c[5][1].cpu().numpy(), want[i][1]), f"{tag}: chromosome {i} SNP counts"
+            c[5][0].zero_(); c[5][1].zero_()
+
+    # direct launches, three rounds back to back
+    for _ in range(3):
+        for c in cases:
+            eng.score_device(*c[:5], *params, max_win_variants=hint, out=c[5], flags=_cabi.FLAG_INDEPENDENT)
+            assert eng.launches == 1
+    check("direct")
+    # an unflagged call that CONSUMES a flagged call's output position: a device copy of its table right
+    # behind the stream must see the finished table (full stream order for everything unflagged)
+    for c in cases:
+        eng.score_device(*c[:5], *params, max_win_variants=hint, out=c[5], flags=_cabi.FLAG_INDEPENDENT)
+    snap = [c[5][0].clone() for c in cases]
+    torch.cuda.synchronize()
+    for i, s in enumerate(snap):
+        assert np.array_equal(s.cpu().numpy(), want[i][0]), f"copy behind the stream: chromosome {i}"
+    check("before the graph")
+    plan = eng.plan_device_stream(cases, *params, max_win_variants=hint)
+    assert plan.launches == len(cases)
+    for c in cases:
+        c[5][0].zero_(); c[5][1].zero_()
+    plan.run()
+    plan.run()
+    check("graph")
+    plan.run()
+    check("graph again")
