@@ -70,7 +70,9 @@ extern "C" {
  * dependent launch, no wait: the next chromosome's CTAs load their tiles while this one's finish
  * their DP).  Everything else on the stream -- unflagged calls, copies, events -- keeps full stream
  * order after all flagged calls before it.  Ignored by the pack -> score launches (they share the
- * workspace). */
+ * workspace).  No two flagged calls of an uninterrupted run may share a buffer one of them writes
+ * (an unflagged call, a copy or a synchronisation ends the run).  On the host entry the flag also
+ * pipelines the transfers of consecutive calls (see sstar_b200_score_windows_host). */
 #define SSTAR_B200_FLAG_INDEPENDENT 512
 
 typedef struct sstar_b200_options {
@@ -157,6 +159,12 @@ int sstar_b200_score_packed(int device, void *stream, const int8_t *d_tgt_gt, co
  *     smaller ones are read in place by the pack kernel (its TMA tile loads are the transfer).
  *     Result tables below 8 MB are stored by the score kernels straight into h_score / h_nsnp,
  *     larger ones copied back per chunk.
+ *   - SSTAR_B200_FLAG_INDEPENDENT (mapped buffers, inputs below 32 MB): one of a STREAM of calls, each
+ *     with its own host buffers and its own `d_scratch` (the caller cycles through a few).  Inputs
+ *     go through the copy engine on the internal copy stream, queued right behind the previous
+ *     call's copies, so the link stays busy while `stream` scores that call; tables are stored in
+ *     place.  The library orders a call's copies after the previous call that used the SAME scratch
+ *     (an event recorded behind its kernels) -- the caller synchronises `stream` once, at the end.
  *   - Otherwise (pageable memory, or SSTAR_B200_FLAG_STAGED_COPIES) inputs are copied to device
  *     staging buffers, scored, and the tables copied back, all on `stream`.
  * `d_scratch` is device memory of at least sstar_b200_host_scratch_bytes(...) either way. */

@@ -516,11 +516,23 @@ int check_common(int device, int64_t V, int32_t R, int32_t T, int32_t W, const v
 // on first use and kept for the life of the thread (not caller-visible memory).
 constexpr int kMaxChunks = 16;
 constexpr int kMaxDevices = 64;
+// A stream of independent host calls (SSTAR_B200_FLAG_INDEPENDENT): the hazards of a scratch buffer
+// that comes round again are tracked HERE, per scratch -- its next call's copies wait for the event
+// recorded behind the kernels of its previous call, nothing else.
+constexpr int kMaxScratchSlots = 32;
+struct ScratchSlot {
+    const void *scratch = nullptr;
+    cudaEvent_t in = nullptr, in2 = nullptr, done = nullptr;
+    bool live = false;  // `done` is recorded and nothing unflagged has used the scratch since
+    uint64_t tick = 0;
+};
 struct PipeCtx {
     bool ready = false;
-    cudaStream_t copy = nullptr;
+    cudaStream_t copy = nullptr, copy2 = nullptr;
     cudaEvent_t entry = nullptr, done = nullptr;
     cudaEvent_t chunk[kMaxChunks] = {};
+    ScratchSlot slots[kMaxScratchSlots];
+    uint64_t tick = 0;
 };
 thread_local PipeCtx g_pipe[kMaxDevices];
 
@@ -529,6 +541,7 @@ int pipe_ctx(int device, PipeCtx **out) {
     PipeCtx &c = g_pipe[device];
     if (!c.ready) {
         CUDA_TRY(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c.copy2, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&c.entry, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
         for (int i = 0; i < kMaxChunks; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c.chunk[i], cudaEventDisableTiming));
@@ -536,6 +549,34 @@ int pipe_ctx(int device, PipeCtx **out) {
     }
     *out = &c;
     return 0;
+}
+
+// the slot of `scratch` (least recently used one recycled); *fresh: it carries no recorded `done`
+int scratch_slot(PipeCtx *pc, const void *scratch, ScratchSlot **out, bool *fresh) {
+    ScratchSlot *hit = nullptr, *lru = &pc->slots[0];
+    for (ScratchSlot &sl : pc->slots) {
+        if (sl.scratch == scratch) { hit = &sl; break; }
+        if (sl.tick < lru->tick) lru = &sl;
+    }
+    if (!hit) {
+        hit = lru;
+        hit->scratch = scratch;
+        hit->live = false;
+        if (!hit->in) {
+            CUDA_TRY(cudaEventCreateWithFlags(&hit->in, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&hit->in2, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&hit->done, cudaEventDisableTiming));
+        }
+    }
+    hit->tick = ++pc->tick;
+    *fresh = !hit->live;
+    *out = hit;
+    return 0;
+}
+// an unflagged call is about to use `scratch`: whatever a flagged call recorded for it is void
+void scratch_forget(PipeCtx *pc, const void *scratch) {
+    for (ScratchSlot &sl : pc->slots)
+        if (sl.scratch == scratch) sl.live = false;
 }
 
 // pack (optional) + bounds + score, the common body of every device-pointer entry point
@@ -756,6 +797,7 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
              mapped_pointer(h_ref_gt, &m_ref) && mapped_pointer(h_tgt_gt, &m_tgt);
 
     if (!mapped) {  // staged: copy in, run, copy out, all on the caller's stream
+        if (device >= 0 && device < kMaxDevices && g_pipe[device].ready) scratch_forget(&g_pipe[device], d_scratch);
         if (V > 0) {
             CUDA_TRY(cudaMemcpyAsync(d_pos, h_pos, (size_t)V * 4, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(d_ref, h_ref_gt, (size_t)V * R, cudaMemcpyHostToDevice, st));
@@ -805,6 +847,55 @@ extern "C" int sstar_b200_score_windows_host(int device, void *stream, const int
     if (rows_per < 256) rows_per = 256;
     nchunks = V > 0 ? (int)((V + rows_per - 1) / rows_per) : 1;
 
+    if ((flags & SSTAR_B200_FLAG_INDEPENDENT) && in_bytes < ((int64_t)32 << 20) && !copy_out) {
+        // One of a STREAM of independent host calls (own host buffers and own scratch each; the
+        // caller cycles through a few scratch buffers).  The inputs go through the copy engine on
+        // the internal copy stream -- queued right behind the previous call's copies, so the link
+        // stays busy while the caller's stream scores that call -- and the kernels store both
+        // tables in place.  The only thing this call's copies wait for is the previous call that
+        // used the SAME scratch (its recorded `done`); a scratch seen for the first time waits for
+        // everything the caller has queued.
+        ScratchSlot *sl;
+        bool fresh;
+        rc = scratch_slot(pc, d_scratch, &sl, &fresh);
+        if (rc) return rc;
+        static const int two_streams = [] { const char *e = getenv("SSTAR_B200_HOST_STREAMS"); return e ? atoi(e) : 1; }() > 1;
+        cudaStream_t c1 = pc->copy, c2 = two_streams ? pc->copy2 : pc->copy;
+        if (fresh) {
+            CUDA_TRY(cudaEventRecord(pc->entry, st));
+            CUDA_TRY(cudaStreamWaitEvent(c1, pc->entry, 0));
+            if (c2 != c1) CUDA_TRY(cudaStreamWaitEvent(c2, pc->entry, 0));
+        } else {
+            CUDA_TRY(cudaStreamWaitEvent(c1, sl->done, 0));
+            if (c2 != c1) CUDA_TRY(cudaStreamWaitEvent(c2, sl->done, 0));
+        }
+        // (SSTAR_B200_HOST_STREAMS=2: the reference matrix on one copy stream, everything else on a
+        // second one -- measured equal, 112.8 vs 114.1 us per C2 call: the link, not the per-copy cost,
+        // is the limit)
+        if (V > 0) {
+            CUDA_TRY(cudaMemcpyAsync(d_ref, h_ref_gt, (size_t)V * R, cudaMemcpyHostToDevice, c1));
+            CUDA_TRY(cudaMemcpyAsync(d_pos, h_pos, (size_t)V * 4, cudaMemcpyHostToDevice, c2));
+            CUDA_TRY(cudaMemcpyAsync(d_tgt, h_tgt_gt, (size_t)V * T, cudaMemcpyHostToDevice, c2));
+        }
+        if (W > 0) {
+            CUDA_TRY(cudaMemcpyAsync(d + h.off_ws, h_win_start, (size_t)W * 4, cudaMemcpyHostToDevice, c2));
+            CUDA_TRY(cudaMemcpyAsync(d + h.off_we, h_win_end, (size_t)W * 4, cudaMemcpyHostToDevice, c2));
+        }
+        CUDA_TRY(cudaEventRecord(sl->in, c1));
+        CUDA_TRY(cudaStreamWaitEvent(st, sl->in, 0));
+        if (c2 != c1) {
+            CUDA_TRY(cudaEventRecord(sl->in2, c2));
+            CUDA_TRY(cudaStreamWaitEvent(st, sl->in2, 0));
+        }
+        rc = run_pipeline(device, st, true, d_ref, d_tgt, d_pos, V, R, T, (const int32_t *)(d + h.off_ws),
+                          (const int32_t *)(d + h.off_we), nullptr, 0, 0, W, match_bonus, max_mismatch,
+                          mismatch_penalty, (int64_t *)m_score, (int32_t *)m_nsnp, ws, L, algo, hint, flags);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(sl->done, st));
+        sl->live = true;
+        return 0;
+    }
+    scratch_forget(pc, d_scratch);
     if (zero_copy_in) {
         // Small input read in place, in ONE prep grid on the caller's stream and without the copy
         // engine.  Its first CTAs fetch pos / windows from mapped host memory; a short run of pack

@@ -468,13 +468,17 @@ class ScoreEngine:
 
     def score_pinned(self, ref_p, tgt_p, pos_p, ws_p, we_p, score_p, nsnp_p, match_bonus=5000,
                      max_mismatch=5, mismatch_penalty=-10000, algo="auto", max_win_variants=0,
-                     stream=None, sync=True, staged=False, flags=0):
+                     stream=None, sync=True, staged=False, flags=0, scratch_slot=0):
         """End-to-end call on HOST tensors: one C-ABI call.  With page-locked (pinned) tensors the
         kernels read the inputs and write both result tables in place over PCIe (zero-copy);
         ``staged=True`` (or pageable tensors) goes through H2D / D2H copies instead.
 
         ref_p int8 [V,R], tgt_p int8 [V,T], pos_p int32 [V], ws_p/we_p int32 [W],
         score_p int64 [W,T] and nsnp_p int32 [W,T] (outputs, written when the stream has synced).
+
+        A stream of independent calls: ``flags=FLAG_INDEPENDENT, sync=False`` with ``scratch_slot``
+        cycling through a few values (own device scratch each) and distinct host tensors per slot;
+        the transfers of consecutive calls then overlap the scoring (one ``synchronize`` at the end).
         """
         V, R = ref_p.shape
         T = tgt_p.shape[1]
@@ -492,7 +496,8 @@ class ScoreEngine:
                 self._pinned_calls.clear()
             cached = self._pinned_calls[key] = (need, opts)
         need, opts = cached
-        scratch = self._dbuf("host_scratch", need, self.torch.uint8)
+        scratch = self._dbuf("host_scratch" if not scratch_slot else f"host_scratch{int(scratch_slot)}", need,
+                             self.torch.uint8)
         s = stream if stream is not None else self.torch.cuda.current_stream(self.tdev)
         rc = self.lib.sstar_b200_score_windows_host(
             self.device, ctypes.c_void_p(s.cuda_stream), ref_p.data_ptr(), tgt_p.data_ptr(),

@@ -295,3 +295,49 @@ def test_stream_of_independent_calls(eng):
     check("graph")
     plan.run()
     check("graph again")
+
+
+def test_host_stream_of_independent_calls(eng):
+    """The host entry with SSTAR_B200_FLAG_INDEPENDENT: different chromosomes back to back, TWO scratch
+    buffers cycled (so every scratch comes round again while earlier calls may still be running: the
+    library orders its copies behind the previous call that used it), one synchronize at the end; then
+    an unflagged call on a scratch the stream used.  Every table against the oracle."""
+    import torch
+    from oracle import tiling_port
+    from sstar_b200 import _cabi
+    from sstar_b200.engine import max_window_variants
+    from sstar_b200.synth import synth_chromosome
+    params = (5000, 5, -10000)
+    jobs = []
+    for i, (length, n_ref, n_tgt, phased) in enumerate([(2_000_000, 100, 50, False), (300_000, 30, 20, False),
+                                                         (2_000_000, 100, 50, False), (1_000_000, 10, 25, True),
+                                                         (2_000_000, 100, 50, False), (600_000, 8, 64, True),
+                                                         (2_000_000, 100, 50, False)]):
+        ref, tgt, pos = synth_chromosome(length=length, n_ref=n_ref, n_tgt=n_tgt, phased=phased, seed=300 + i)
+        wins = tiling_port.split_windows(pos, 50_000, 10_000)
+        ws = np.asarray([w[0] for w in wins], dtype=np.int32)
+        we = np.asarray([w[1] for w in wins], dtype=np.int32)
+        pos = pos.astype(np.int32)
+        want = c_oracle.score_windows(ref, tgt, pos, ws, we, *params)
+        pin = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (ref, tgt, pos, ws, we)]
+        out = (torch.zeros((len(ws), tgt.shape[1]), dtype=torch.int64).pin_memory(),
+               torch.zeros((len(ws), tgt.shape[1]), dtype=torch.int32).pin_memory())
+        jobs.append((pin, out, want, max_window_variants(pos, ws, we)))
+    for rounds in range(2):
+        for i, (pin, out, _want, hint) in enumerate(jobs):
+            eng.score_pinned(*pin, out[0], out[1], *params, max_win_variants=hint, sync=False,
+                             flags=_cabi.FLAG_INDEPENDENT, scratch_slot=1 + i % 2)
+        torch.cuda.synchronize()
+        for i, (_pin, out, want, _hint) in enumerate(jobs):
+            assert np.array_equal(out[0].numpy(), want[0]), f"round {rounds}: chromosome {i} scores"
+            assert np.array_equal(out[1].numpy(), want[1]), f"round {rounds}: chromosome {i} SNP counts"
+            out[0].zero_(); out[1].zero_()
+    # stream, then an unflagged call on the same scratch without a synchronize in between
+    pin, out, want, hint = jobs[0]
+    eng.score_pinned(*pin, out[0], out[1], *params, max_win_variants=hint, sync=False, flags=_cabi.FLAG_INDEPENDENT,
+                     scratch_slot=1)
+    pin1, out1, want1, hint1 = jobs[1]
+    eng.score_pinned(*pin1, out1[0], out1[1], *params, max_win_variants=hint1, sync=True, scratch_slot=1)
+    torch.cuda.synchronize()
+    assert np.array_equal(out[0].numpy(), want[0]) and np.array_equal(out1[0].numpy(), want1[0])
+    assert np.array_equal(out[1].numpy(), want[1]) and np.array_equal(out1[1].numpy(), want1[1])
