@@ -28,7 +28,7 @@ struct WsHeader {
 struct WsLayout {
     int64_t G;   // 32-variant groups
     int32_t Tp;  // plane row pitch in words (T rounded up to 32)
-    size_t off_absent, off_exotic, off_carried, off_two, off_win_lo, off_win_hi, off_win_pfirst, off_win_plast, off_slow, off_bail,
+    size_t off_absent, off_exotic, off_carried, off_two, off_neg, off_win_lo, off_win_hi, off_win_pfirst, off_win_plast, off_slow, off_bail,
         off_arena;
     size_t arena_entries;
     size_t total;
@@ -65,12 +65,15 @@ struct PackArgs {
     uint32_t ref_tile_bytes;  // smem bytes reserved per tile (incl. alignment slack)
     uint32_t tgt_tile_bytes;
     uint32_t *absent_bits, *exotic, *carried, *two;
+    // sign plane: written (for every column of the group) only where exotic[g] != 0, see pack_tile
+    uint32_t *neg;
 };
 
 struct ScoreArgs {
     const int32_t *pos;
     const int8_t *tgt;
     const uint32_t *absent_bits, *exotic, *carried, *two;
+    const uint32_t *neg;  // sign plane, valid where exotic[g] != 0
     const int32_t *win_lo, *win_hi, *win_pfirst, *win_plast;
     int32_t *slow_list;
     uint32_t *win_bail;

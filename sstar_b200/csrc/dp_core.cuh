@@ -202,6 +202,79 @@ SSTAR_HD_COLD bool list_dp_run_general(const uint32_t *base, int ls, int n, int3
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small signed genotypes: the per-class DP for units whose carried genotypes all lie in
+// {-2, -1, 1, 2} -- what missing calls give (an allele of -1: sstar/utils/utils.py:305-306 sums the
+// alleles, so "./." is -2, a missing haploid call or "./0" -1).  Four classes, their running maxima
+// in REGISTERS (list_dp_run_general keeps them in thread-local tables, whose loads and stores are the
+// latency of that loop); waiting sites as in list_dp_run.  General entries (position << 8 | byte).
+// `compat` comes from small_compat_mask(max_mismatch).
+// ---------------------------------------------------------------------------------------------
+SSTAR_HD int small_class(uint32_t e) {  // genotype byte -2, -1, 1, 2 -> class 0..3
+    const int32_t g = (int32_t)(int8_t)(e & 0xffu);
+    return g + 2 - (int)(g > 0);
+}
+// bit (4 * i + j): classes i != j whose genotype values differ by at most max_mm (sstar.py:202-206)
+SSTAR_HD uint32_t small_compat_mask(int32_t max_mm) {
+    uint32_t m = 0;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            const int vi = i - 2 + (int)(i > 1), vj = j - 2 + (int)(j > 1);
+            const int d = vi > vj ? vi - vj : vj - vi;
+            if (i != j && d <= max_mm) m |= 1u << (4 * i + j);
+        }
+    return m;
+}
+
+SSTAR_HD_COLD int64_t list_dp_run_small(const uint32_t *base, int ls, int n, int32_t bonus, int32_t penalty, uint32_t compat) {
+    constexpr int32_t NEG = Sentinel<int32_t>::NEG, THR = Sentinel<int32_t>::THR;
+    int32_t ring[kRingSlots];  // v of waiting sites older than k-1 (crowded sites only)
+    int32_t A0 = NEG, A1 = NEG, A2 = NEG, A3 = NEG, B0 = NEG, B1 = NEG, B2 = NEG, B3 = NEG, top = NEG;
+    auto commit = [&](uint32_t ec, int32_t vc) {  // the site becomes an eligible predecessor
+        const int32_t d = vc - (int32_t)(ec >> 8);
+        const int ci = small_class(ec);
+        if (ci == 0)      { A0 = imax(A0, d); B0 = imax(B0, vc); }
+        else if (ci == 1) { A1 = imax(A1, d); B1 = imax(B1, vc); }
+        else if (ci == 2) { A2 = imax(A2, d); B2 = imax(B2, vc); }
+        else              { A3 = imax(A3, d); B3 = imax(B3, vc); }
+    };
+    const uint32_t *pk = base;
+    int c = 0;        // next site to commit
+    uint32_t pe = 0;  // entry k-1 and its v
+    int32_t pv = 0;
+    for (int k = 0; k < n; ++k) {
+        const uint32_t e = *pk;
+        const int32_t p = (int32_t)(e >> 8);
+        if (c == k - 1) {  // common case: only the previous site waits, in registers
+            if (p - (int32_t)(pe >> 8) >= kMinPairDistance) { commit(pe, pv); c = k; }
+            else ring[(k - 1) & (kRingSlots - 1)] = pv;
+        } else if (c < k) {  // crowded sites: older ones wait in the ring
+            while (c < k) {
+                const uint32_t ec = (c == k - 1) ? pe : base[c * ls];
+                const int32_t vc = (c == k - 1) ? pv : ring[c & (kRingSlots - 1)];
+                if (p - (int32_t)(ec >> 8) < kMinPairDistance) break;
+                commit(ec, vc);
+                ++c;
+            }
+            if (c < k) ring[(k - 1) & (kRingSlots - 1)] = pv;
+        }
+        const int ci = small_class(e);
+        const int32_t same = ci == 0 ? A0 : (ci == 1 ? A1 : (ci == 2 ? A2 : A3));
+        const uint32_t cm = compat >> (4 * ci);
+        int32_t other = NEG;
+        if (cm & 1u) other = imax(other, B0);
+        if (cm & 2u) other = imax(other, B1);
+        if (cm & 4u) other = imax(other, B2);
+        if (cm & 8u) other = imax(other, B3);
+        const int32_t m = imax(same + (p + bonus), other + penalty);
+        top = imax(top, m);
+        pe = e;
+        pv = imax(m, (int32_t)0);
+        pk += ls;
+    }
+    return (n <= 2 || top <= THR) ? kNegInf64 : (int64_t)top;
+}
+
 // list_window_range_shifted<8> for general entries that also keeps, for both cursors, the number of
 // entries passed whose genotype is not 1 / 2: a unit is "plain" (the four-maxima DP takes it) iff the
 // two counts agree -- O(1) per unit instead of a scan of its entries.

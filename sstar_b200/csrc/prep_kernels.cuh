@@ -177,41 +177,121 @@ __device__ __forceinline__ void transpose4(uint32_t a0, uint32_t a1, uint32_t a2
     c[3] = __byte_perm(t2, t3, 0x7632);
 }
 
-// One 32-row x 4-column block redone with the EXACT byte tests, still four columns at a time (bit 7 of
-// each byte: "!= 0", "== 2", "> 2 unsigned"): the planes' words of the four columns, and whether a
-// reference-absent row of a real column holds a byte outside {0,1,2} (the group's exotic flag).
+// A 32-row x 4-column block holding bytes outside {0,1,2} is redone on |b| and the sign, still four columns
+// at a time.  Missing calls give -1 / -2 (sstar/utils/utils.py:305-306 sums alleles of -1), and a block whose
+// other bytes all are -1 / -2 keeps the cheap bit tests: with n = b >> 7 (0 / 1 per byte) and s = n * 0xff,
+// |b| = (b ^ s) + n never carries across bytes (|b| <= 0x80), "b != 0" and "|b| == 2" then are the bit tests of
+// the clean path on |b|, and n itself is the sign plane.  Returns true when some byte of the block has |b| > 2
+// (multi-allelic dosages, garbage in the padding of a ragged last quad): pack_block_exact then redoes it.
 // Rows are addressed as in pack_tile (kRowPhase: each row segment keeps its own 16-byte phase).
 template <bool kAligned, bool kRowPhase>
-__device__ __noinline__ bool pack_block_exact(const uint8_t *s_tgt, uint32_t base, uint32_t tpitch, uint32_t tgt_phase,
-                                              uint32_t pstep, uint32_t row0, uint32_t col_off, uint32_t ab, int ncol,
-                                              uint32_t car[4], uint32_t two[4]) {
-    uint32_t nz[4], tw[4], ex[4];
+__device__ __noinline__ bool pack_block_signed(const uint8_t *s_tgt, uint32_t base, uint32_t tpitch, uint32_t tgt_phase,
+                                               uint32_t pstep, uint32_t row0, uint32_t col_off, uint32_t car[4],
+                                               uint32_t two[4], uint32_t neg[4]) {
+    uint32_t nz[4], tw[4], ng[4], e_or = 0, e_and = 0;
 #pragma unroll
     for (int blk = 0; blk < 4; ++blk) {
-        uint32_t an = 0, at = 0, ax = 0;
+        uint32_t an = 0, at = 0, ag = 0;
 #pragma unroll
         for (int rr = 7; rr >= 0; --rr) {
             const uint32_t r = (uint32_t)(blk * 8 + rr);
             const uint32_t off = kRowPhase ? (row0 + r) * tpitch + ((tgt_phase + (row0 + r) * pstep) & 15u) + col_off
                                            : base + r * tpitch;
             const uint32_t w = lds_word<kAligned>(s_tgt, off);
-            an = an + an + (bytes_nonzero(w) >> 7);
-            at = at + at + (bytes_zero(w ^ 0x02020202u) >> 7);
-            ax = ax + ax + ((bytes_nonzero(w & 0xfcfcfcfcu) | bytes_zero(w ^ 0x03030303u)) >> 7);
+            const uint32_t n01 = (w >> 7) & 0x01010101u;
+            const uint32_t m = (w ^ ((n01 << 8) - n01)) + n01;  // |b| per byte
+            const uint32_t h = m >> 1;
+            an = an + an + ((m | h) & 0x01010101u);  // |b| in {1,2,3} -> bit 0
+            at = at + at + (h & 0x01010101u);        // |b| in {2,3}   -> bit 0
+            ag = ag + ag + n01;
+            e_or |= m;
+            e_and |= m & h;
         }
         nz[blk] = an;
         tw[blk] = at;
+        ng[blk] = ag;
+    }
+    transpose4(nz[0], nz[1], nz[2], nz[3], car);
+    transpose4(tw[0], tw[1], tw[2], tw[3], two);
+    transpose4(ng[0], ng[1], ng[2], ng[3], neg);
+    return ((e_or & 0xfcfcfcfcu) | (e_and & 0x01010101u)) != 0;
+}
+
+// The same block with the EXACT byte tests on |b| (bit 7 of each byte: "!= 0", "|b| == 2", "|b| > 2"): the
+// three planes' words of the four columns, and the block's level -- 2 when a reference-absent row of a real
+// column holds |b| > 2, else 1 when one holds a negative byte, else 0.
+template <bool kAligned, bool kRowPhase>
+__device__ __noinline__ uint32_t pack_block_exact(const uint8_t *s_tgt, uint32_t base, uint32_t tpitch, uint32_t tgt_phase,
+                                                  uint32_t pstep, uint32_t row0, uint32_t col_off, uint32_t ab, int ncol,
+                                                  uint32_t car[4], uint32_t two[4], uint32_t neg[4]) {
+    uint32_t nz[4], tw[4], ng[4], ex[4];
+#pragma unroll
+    for (int blk = 0; blk < 4; ++blk) {
+        uint32_t an = 0, at = 0, ag = 0, ax = 0;
+#pragma unroll
+        for (int rr = 7; rr >= 0; --rr) {
+            const uint32_t r = (uint32_t)(blk * 8 + rr);
+            const uint32_t off = kRowPhase ? (row0 + r) * tpitch + ((tgt_phase + (row0 + r) * pstep) & 15u) + col_off
+                                           : base + r * tpitch;
+            const uint32_t w = lds_word<kAligned>(s_tgt, off);
+            const uint32_t n01 = (w >> 7) & 0x01010101u;
+            const uint32_t m = (w ^ ((n01 << 8) - n01)) + n01;  // |b| per byte, 0 .. 0x80
+            an = an + an + (bytes_nonzero(m) >> 7);
+            at = at + at + (bytes_zero(m ^ 0x02020202u) >> 7);
+            ax = ax + ax + ((bytes_nonzero(m & 0xfcfcfcfcu) | bytes_zero(m ^ 0x03030303u)) >> 7);
+            ag = ag + ag + n01;
+        }
+        nz[blk] = an;
+        tw[blk] = at;
+        ng[blk] = ag;
         ex[blk] = ax;
     }
     uint32_t exo[4];
     transpose4(nz[0], nz[1], nz[2], nz[3], car);
     transpose4(tw[0], tw[1], tw[2], tw[3], two);
+    transpose4(ng[0], ng[1], ng[2], ng[3], neg);
     transpose4(ex[0], ex[1], ex[2], ex[3], exo);
-    bool exotic = false;
+    uint32_t big = 0, sgn = 0;
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-        if (c < ncol) exotic |= (exo[c] & ab) != 0;  // (rows past the matrix's end have no absent bit)
-    return exotic;
+        if (c < ncol) {  // (rows past the matrix's end have no absent bit)
+            big |= exo[c] & ab;
+            sgn |= neg[c] & ab;
+        }
+    return big ? 2u : (sgn ? 1u : 0u);
+}
+
+// The out-of-line redo of a block that holds a byte outside {0,1,2}: planes on |b| into car / two, the
+// block's sign words stored to `neg_out` (masked by the absent word `ab`), its bit set in the tile's redo
+// map.  Returns the block's level (0: nothing outside {0,1,2} in a reference-absent row of a real column,
+// 1: such bytes, all -1 / -2, 2: others).  Column chunks of a group cannot see one another's blocks, and
+// the tile remembers kRedoWords * 32 redone blocks: there a flagged block is level 2 (its group's genotype
+// bytes are read, never the sign plane).
+constexpr int kRedoWords = 64;
+template <bool kAligned, bool kRowPhase, bool kChunked>
+__device__ __noinline__ uint32_t pack_block_odd(const uint8_t *s_tgt, uint32_t base, uint32_t tpitch, uint32_t tgt_phase,
+                                                uint32_t pstep, uint32_t row0, uint32_t col_off, uint32_t ab, int ncol,
+                                                uint32_t car[4], uint32_t two[4], uint32_t *neg_out, uint32_t *s_redo, int it) {
+    uint32_t neg[4];
+    uint32_t level = 0;
+    if (pack_block_signed<kAligned, kRowPhase>(s_tgt, base, tpitch, tgt_phase, pstep, row0, col_off, car, two, neg)) {
+        level = pack_block_exact<kAligned, kRowPhase>(s_tgt, base, tpitch, tgt_phase, pstep, row0, col_off, ab, ncol, car, two, neg);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c < ncol && (neg[c] & ab)) level = 1u;
+    }
+    if (level && (kChunked || it >= kRedoWords * 32)) level = 2u;
+    if (it < kRedoWords * 32) atomicOr(&s_redo[it >> 5], 1u << (it & 31));
+    if (level) s_redo[kRedoWords] = 1u;  // some group of the tile is flagged
+    if (ncol == 4) {
+        *reinterpret_cast<uint4 *>(neg_out) = make_uint4(neg[0] & ab, neg[1] & ab, neg[2] & ab, neg[3] & ab);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            if (c < ncol) neg_out[c] = neg[c] & ab;
+    }
+    return level;
 }
 
 // The staged target tile holds columns [c0, c0 + ncols) of the CTA's rows with a row pitch of
@@ -232,6 +312,7 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
     uint32_t *s_exo = s_word + a.gpc;                                        // [gpc] exotic flag
     const uint8_t *s_ref = smem + a.gpc * 32 + align16(a.gpc * 8);
     const uint8_t *s_tgt = s_ref + a.ref_tile_bytes;
+    __shared__ uint32_t s_redo[kRedoWords + 1];  // (last word: some group of the tile is flagged) bit per 32x4 block of the tile: redone out of line (its sign words are written)
 
     // A: signed row sums of the reference panel (dp4a over the widest aligned vector).  A warp takes
     // four rows at a time, eight lanes per row: four independent chains of loads per warp and a
@@ -309,6 +390,7 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
             if (c0 == 0) a.absent_bits[g0 + gl] = bits;  // (every column chunk of a group computes the same word)
         }
     }
+    if (tid <= kRedoWords) s_redo[tid] = 0u;
     __syncthreads();
 
     // B: 4 columns x 32 rows per thread
@@ -344,14 +426,14 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
         transpose4(nz[0], nz[1], nz[2], nz[3], car);
         transpose4(tw[0], tw[1], tw[2], tw[3], two);
         const int ncol = min(4, ncols - 4 * q);
-        bool exotic = false;
+        const size_t o = (size_t)(g0 + gl) * a.Tp + c0 + 4 * q;
+        uint32_t level = 0;
         if ((e_or & 0xfcfcfcfcu) | (e_and & 0x01010101u))
             // a byte outside {0,1,2} somewhere in this 32x4 block (missing calls, multi-allelic dosages --
-            // or the padding bytes of a ragged last quad / tail rows): redone with the exact byte tests,
-            // out of line (the common path keeps its registers)
-            exotic = pack_block_exact<kAligned, kRowPhase>(s_tgt, base, (uint32_t)tpitch, tgt_phase, pstep, (uint32_t)(gl * 32),
-                                                           4u * q, ab, ncol, car, two);
-        const size_t o = (size_t)(g0 + gl) * a.Tp + c0 + 4 * q;
+            // or the padding bytes of a ragged last quad / tail rows): redone on |b| and the sign, out of
+            // line (the common path keeps its registers)
+            level = pack_block_odd<kAligned, kRowPhase, kChunked>(s_tgt, base, (uint32_t)tpitch, tgt_phase, pstep,
+                                                                  (uint32_t)(gl * 32), 4u * q, ab, ncol, car, two, a.neg + o, s_redo, it);
         if (ncol == 4) {
             *reinterpret_cast<uint4 *>(a.carried + o) = make_uint4(car[0] & ab, car[1] & ab, car[2] & ab, car[3] & ab);
             *reinterpret_cast<uint4 *>(a.two + o) = make_uint4(two[0] & ab, two[1] & ab, two[2] & ab, two[3] & ab);
@@ -363,11 +445,26 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
                 a.two[o + c] = two[c] & ab;
             }
         }
-        if (exotic) atomicOr(&s_exo[gl], 1u);
+        if (level) atomicOr(&s_exo[gl], level);
     }
     __syncthreads();
+    // A flagged group's sign plane is read for ALL its columns: the blocks that took the clean path store
+    // zero words now (clean groups -- all of them on clean data -- never write or read the plane).
+    if (!kChunked && s_redo[kRedoWords]) {
+        for (int it = tid; it < nitems; it += kPackThreads) {
+            const int gl = it / nq, q = it - gl * nq;
+            if (s_exo[gl] == 0 || it >= kRedoWords * 32 || ((s_redo[it >> 5] >> (it & 31)) & 1u)) continue;
+            const int ncol = min(4, ncols - 4 * q);
+            const size_t o = (size_t)(g0 + gl) * a.Tp + 4 * q;
+            if (ncol == 4) {
+                *reinterpret_cast<uint4 *>(a.neg + o) = make_uint4(0u, 0u, 0u, 0u);
+            } else {
+                for (int c = 0; c < ncol; ++c) a.neg[o + c] = 0u;
+            }
+        }
+    }
     if (tid < ng) {
-        if (kChunked) { if (s_exo[tid]) atomicOr(&a.exotic[g0 + tid], 1u); }  // zeroed by the host; chunks share the flag
+        if (kChunked) { if (s_exo[tid]) atomicOr(&a.exotic[g0 + tid], s_exo[tid]); }  // zeroed by the host; chunks share the flag
         else a.exotic[g0 + tid] = s_exo[tid];
     }
 }
@@ -418,7 +515,7 @@ __device__ __forceinline__ void pack_tile_direct(const PackArgs &a, uint8_t *sme
         const size_t o = (size_t)(g0 + gl) * a.Tp + t;
         a.carried[o] = car;
         a.two[o] = two;
-        if (ex) atomicOr(&s_exo[gl], 1u);
+        if (ex) atomicOr(&s_exo[gl], 2u);  // (level 2: the genotype bytes are read, never the sign plane)
     }
     __syncthreads();
     if (tid < ng) a.exotic[g0 + tid] = s_exo[tid];
@@ -540,6 +637,9 @@ __global__ void __launch_bounds__(kPackThreads) fetch_kernel(const __grid_consta
     fetch_block(b, (int)blockIdx.x, kPackThreads, threadIdx.x);
 }
 
+// (shapes that fill the machine keep three 64 KB tiles per SM, so the registers of the out-of-line redo of odd
+// blocks -- the kernel's count is the call tree's maximum -- cost no occupancy there; capping them made the
+// clean path spill)
 __global__ void __launch_bounds__(kPackThreads)
 prep_kernel(const __grid_constant__ PackArgs p, const __grid_constant__ BoundsArgs b, int n_pack, int mode) {
     extern __shared__ __align__(16) uint8_t smem[];

@@ -54,14 +54,64 @@ struct GroupCtx {
     int io;                              // its first window's slot in the GroupShared arrays
     int32_t rlo, rhi, gi0, nwr, pen_eff;
     bool mono_hi;
+    bool small;  // general body: every other genotype of the sub-group is -1 / -2 (group levels <= 1)
 };
+
+// The site list of this thread's column for a sub-group whose other genotypes all are -1 / -2: general
+// entries (relative position << 8 | genotype byte) with the byte taken from the planes -- carried, "|g| == 2"
+// and the sign plane, which exists only where the group is flagged (clean groups never write it):
+// byte = sign ? -(1 + two) : 1 + two.  No genotype byte is fetched.  Out of line: the common body must not pay
+// its registers.  Returns the column's site count (entries beyond L - 1 land in the spill slot).
+__device__ __noinline__ int build_list_small(const ScoreArgs &a, const GroupCtx &c, int ls) {
+    if (c.t >= a.T) return 0;
+    const uint32_t *cp = a.carried + (size_t)c.gi0 * a.Tp + c.t;
+    const uint32_t *tp = a.two + (size_t)c.gi0 * a.Tp + c.t;
+    const uint32_t *np = a.neg + (size_t)c.gi0 * a.Tp + c.t;
+    const uint32_t first_mask = 0xffffffffu << (c.rlo & 31);
+    const uint32_t last_mask = 0xffffffffu >> (31 - ((c.rhi - 1) & 31));
+    const uint32_t *s_pos = c.s_pos;
+    uint32_t *w = c.s_list + c.tid;
+    uint32_t *const w_end = w + (size_t)c.L * ls;  // the spill slot
+    const int nwr = c.nwr;
+    int cnt = 0;
+    constexpr int kBatch = 4;
+    for (int jb = 0; jb < nwr; jb += kBatch) {
+        uint32_t cw[kBatch], tw[kBatch], ng[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const bool in = jb + u < nwr;
+            cw[u] = in ? __ldg(cp + (size_t)(jb + u) * a.Tp) : 0u;
+            tw[u] = in ? __ldg(tp + (size_t)(jb + u) * a.Tp) : 0u;
+            ng[u] = (in && __ldg(a.exotic + c.gi0 + jb + u)) ? __ldg(np + (size_t)(jb + u) * a.Tp) : 0u;
+            if (jb + u == 0) cw[u] &= first_mask;
+            if (jb + u == nwr - 1) cw[u] &= last_mask;
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            uint32_t cbits = cw[u];
+            cnt += __popc(cbits);
+            while (cbits) {
+                const int b = __ffs(cbits) - 1;
+                cbits &= cbits - 1;
+                const uint32_t t2 = (tw[u] >> b) & 1u, sg = (ng[u] >> b) & 1u;
+                *w = (s_pos[((jb + u) << 5) + b] << 8) | ((((1u + t2) ^ (0u - sg)) + sg) & 0xffu);
+                w = (w + ls < w_end) ? w + ls : w_end;
+            }
+        }
+    }
+    return cnt;
+}
 
 // List build + DP of one window group.  kGen = false: genotypes in {0,1,2}, entries
 // (relative position << 1 | genotype==2), the four-maxima DP.  kGen = true: a window of the group
 // holds other genotypes (missing calls, multi-allelic sites): entries (relative position << 8 |
-// genotype byte, fetched from the target matrix) and the per-class DP of dp_core.cuh.
-template <bool kGen, bool kNarrow = false>
+// genotype byte) and a per-class DP of dp_core.cuh.  When those other genotypes all are -1 / -2
+// (missing calls: c.small) the byte comes from the planes -- "|g| == 2" and the sign plane the pack
+// kernel writes for flagged groups -- and the classes live in registers (list_dp_run_small); otherwise
+// the bytes are fetched from the target matrix and the classes sit in thread-local tables.
+template <int kGenMode, bool kNarrow = false>
 __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c) {
+    constexpr bool kGen = kGenMode != 0;     // general entries (position << 8 | genotype byte)
     GroupShared &g = *c.g;
     const int32_t *glo = g.lo + c.io, *ghi = g.hi + c.io, *gnabs = g.nabs + c.io;
     const uint32_t *gplo = g.plo + c.io, *gphi = g.phi + c.io, *gex = g.ex + c.io;
@@ -76,7 +126,10 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
     // shared-window addresses (ld/st.shared) and the write cursor is clamped to a spill slot
     // (index L) instead of branching on overflow.
     int cnt = 0;
-    if (t < a.T) {
+    const bool small = kGen && c.small;
+    if (small) {
+        cnt = build_list_small(a, c, ls);
+    } else if (t < a.T) {
         const uint32_t *cp = a.carried + (size_t)c.gi0 * a.Tp + t;
         const uint32_t *tp = a.two + (size_t)c.gi0 * a.Tp + t;
         const uint32_t first_mask = 0xffffffffu << (c.rlo & 31);
@@ -118,7 +171,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
             }
         }
     }
-    if (kGen && t < a.T) {
+    if (kGen && !small && t < a.T) {
         // general entries: (relative position << 8 | genotype byte).  The bytes are fetched here,
         // in a loop of independent iterations (several loads in flight), not one exposed memory
         // latency per site inside the bit loop above.
@@ -132,6 +185,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
         }
     }
     const bool overflow = cnt >= L;  // one slot is the terminator
+    const uint32_t compat = small ? small_compat_mask(a.max_mm) : 0u;
     if (t < a.T && !overflow) s_list[cnt * ls + tid] = kListSentinel;
     if (tid == 0) { g.n_work = 0; g.n_work_back = 0; }
     __syncthreads();  // every list is built: the position tile becomes the worklist
@@ -217,7 +271,9 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
                 const uint32_t e = s_work[nwin * bd - 1 - u];
                 const int col = e & 127, i = (e >> 7) & 15, ua = (e >> 11) & 1023, n = e >> 21;
                 int64_t score;
-                if (!list_dp_run_general(s_list + col + ua * ls, ls, n, a.bonus, a.penalty, a.max_mm, score)) {
+                if (small) {
+                    score = list_dp_run_small(s_list + col + ua * ls, ls, n, a.bonus, a.penalty, compat);
+                } else if (!list_dp_run_general(s_list + col + ua * ls, ls, n, a.bonus, a.penalty, a.max_mm, score)) {
                     bail_window(w0 + i);
                     continue;
                 }
@@ -246,6 +302,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
                 n = b - cur;
                 if (n > 2) {
                     if (!kGen) score = list_dp_run(s_list + tid + cur * ls, ls, n, a.bonus, c.pen_eff);
+                    else if (small) score = list_dp_run_small(s_list + tid + cur * ls, ls, n, a.bonus, a.penalty, compat);
                     else if (!list_dp_run_general(s_list + tid + cur * ls, ls, n, a.bonus, a.penalty, a.max_mm, score)) {
                         bail_window(w);
                         continue;
@@ -262,7 +319,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
 // the general instantiation lives out of line: it is rare, and its per-class tables must not
 // cost the common kernel body registers or stack
 template <bool kNarrow>
-__device__ __noinline__ void group_body_general(const ScoreArgs &a, const GroupCtx &c) { group_body<true, kNarrow>(a, c); }
+__device__ __noinline__ void group_body_general(const ScoreArgs &a, const GroupCtx &c) { group_body<1, kNarrow>(a, c); }
 
 // grid.x = tchunks * ngroups; dynamic smem: list [L + 1][bd] | max(positions [words_cap*32], worklist [wg*bd])
 // kNarrow (panels of at most 16 columns) lives in a kernel of its own: there the lists of a column
@@ -414,20 +471,22 @@ __device__ __forceinline__ void score_group_body(const ScoreArgs &a, int wg, int
                 }
                 na = __reduce_add_sync(0xffffffffu, na);
                 ex = __reduce_or_sync(0xffffffffu, ex);
-                if ((tid & 31) == 0) { g.nabs[i] = na; g.ex[i] = ex != 0; }
+                if ((tid & 31) == 0) { g.nabs[i] = na; g.ex[i] = ex; }  // ex: OR of the groups' levels (0 clean, 1 = -1 / -2 only, >= 2 any byte)
             }
             __syncthreads();
 
             // Windows holding genotypes outside {0,1,2}: the whole sub-group takes the general body.
             // Only when it spans more than 2^23 bp do such windows go to the pairwise kernel.
-            bool any_ex = false;
-            for (int i = s0; i < s1; ++i) any_ex = any_ex || g.ex[i] != 0;
+            uint32_t ex_or = 0;
+            for (int i = s0; i < s1; ++i) ex_or |= g.ex[i];
+            const bool any_ex = ex_or != 0;
             GroupCtx c;
             c.g = &g; c.s_list = s_list; c.s_pos = s_pos;
             c.tid = tid; c.bd = bd; c.chunk = chunk; c.t = t; c.w0 = w0 + s0; c.nwin = nsub; c.L = L; c.io = s0;
             c.rlo = rlo; c.rhi = rhi; c.gi0 = gi0; c.nwr = nwr; c.pen_eff = pen_eff; c.mono_hi = mono_hi;
+            c.small = ex_or < 2u;
             if (any_ex && span < (int64_t(1) << kGeneralPosBits)) group_body_general<kNarrow>(a, c);
-            else group_body<false, kNarrow>(a, c);
+            else group_body<0, kNarrow>(a, c);
         }
         s0 = s1;
         if (s0 < nwin) __syncthreads();  // the lists / worklist are reused by the next sub-group

@@ -64,6 +64,21 @@ int num_sms() {
     return n;
 }
 
+// Pack CTAs an SM holds when only registers and threads bound them (small tiles): what "one wave" of the pack
+// grid means for small problems.  Asked of the runtime once per device -- the kernel's register count is
+// the maximum over its call tree, out-of-line redo paths included -- never below 2.
+int pack_ctas_per_sm() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 4;
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n > 0) return n;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, prep_kernel, kPackThreads, 0) != cudaSuccess || n < 2) n = n < 2 ? 2 : 4;
+    if (n > 6) n = 6;
+    cache[dev].store(n, std::memory_order_relaxed);
+    return n;
+}
+
 // cudaFuncSetAttribute is per device and PROCESS-wide (a smaller value set by another host thread
 // would lower the limit under a launch already sized for the larger one): the largest dynamic
 // shared-memory size granted to each kernel is remembered per device for the whole process and only
@@ -98,6 +113,7 @@ WsLayout make_layout(int64_t V, int32_t T, int32_t W, int32_t max_win_variants) 
     L.off_exotic = off;  off = align_up(off + g * 4, 256);
     L.off_carried = off; off = align_up(off + g * (size_t)L.Tp * 4, 256);
     L.off_two = off;     off = align_up(off + g * (size_t)L.Tp * 4, 256);
+    L.off_neg = off;     off = align_up(off + g * (size_t)L.Tp * 4, 256);
     size_t w = (size_t)(W > 0 ? W : 1);
     L.off_win_lo = off;  off = align_up(off + w * 4, 256);
     L.off_win_hi = off;  off = align_up(off + w * 4, 256);
@@ -190,17 +206,18 @@ int launch_prep(cudaStream_t st, int64_t g_begin, int64_t g_end, const int8_t *d
         p.exotic = reinterpret_cast<uint32_t *>(ws + L.off_exotic);
         p.carried = reinterpret_cast<uint32_t *>(ws + L.off_carried);
         p.two = reinterpret_cast<uint32_t *>(ws + L.off_two);
+        p.neg = reinterpret_cast<uint32_t *>(ws + L.off_neg);
         // groups per CTA: staged tile <= ~64 KB, at most 8 groups; small problems get the fewest
-        // groups per CTA that still fit the whole grid in ONE wave (6 CTAs per SM by registers)
+        // groups per CTA that still fit the whole grid in ONE wave (the pack kernel's CTAs per SM by registers)
         const size_t per_group = (size_t)32 * ((size_t)R + (size_t)T);
         int gpc_max = (int)((size_t)(64 << 10) / per_group);
         if (gpc_max > 32) gpc_max = 32;  // narrow panels (a few dozen columns): tiles of up to 1,024 variants
         if (gpc_max < 1) gpc_max = 1;
         const int nsm = num_sms();
-        const int64_t wave = (int64_t)6 * nsm - n_bounds;
+        const int64_t wave = (int64_t)pack_ctas_per_sm() * nsm - n_bounds;
         int gpc = 1;
         while (gpc < gpc_max && (ngroups + gpc - 1) / gpc > (wave > nsm ? wave : nsm)) ++gpc;
-        if ((ngroups + gpc - 1) / gpc > 4 * (int64_t)6 * nsm) gpc = gpc_max;  // many waves anyway: biggest tiles
+        if ((ngroups + gpc - 1) / gpc > 4 * (int64_t)pack_ctas_per_sm() * nsm) gpc = gpc_max;  // many waves anyway: biggest tiles
         p.gpc = gpc;
         p.ref_tile_bytes = (uint32_t)align_up((size_t)gpc * 32 * R + 32, 16);
         p.tgt_tile_bytes = (uint32_t)align_up((size_t)gpc * 32 * T + 32, 16);
@@ -304,6 +321,7 @@ int launch_score(cudaStream_t st, const ScoreCall &c, const WsLayout &L, int32_t
     s.exotic = reinterpret_cast<const uint32_t *>(ws + L.off_exotic);
     s.carried = reinterpret_cast<const uint32_t *>(ws + L.off_carried);
     s.two = reinterpret_cast<const uint32_t *>(ws + L.off_two);
+    s.neg = reinterpret_cast<const uint32_t *>(ws + L.off_neg);
     s.win_lo = reinterpret_cast<const int32_t *>(ws + L.off_win_lo);
     s.win_hi = reinterpret_cast<const int32_t *>(ws + L.off_win_hi);
     s.win_pfirst = reinterpret_cast<const int32_t *>(ws + L.off_win_pfirst);

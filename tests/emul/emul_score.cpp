@@ -45,9 +45,25 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
             const int b = tgt[k * T + t];
             if (b != 0) carried[(size_t)(k >> 5) * Tp + t] |= 1u << (k & 31);
             if (b == 2) two[(size_t)(k >> 5) * Tp + t] |= 1u << (k & 31);
-            if ((unsigned)b > 2u) exotic[k >> 5] = 1;
+            // group level as the pack kernel raises it: 1 = other genotypes, all in {-2,-1} (the planes then
+            // hold |g| == 2 and the sign, for the whole group); 2 = anything else (the bytes are read)
+            if ((unsigned)b > 2u) exotic[k >> 5] |= (b == -1 || b == -2) ? 1u : 2u;
         }
     }
+    std::vector<uint32_t> neg((size_t)(G > 0 ? G : 1) * Tp, 0xdeadbeefu);  // (unwritten where the group is clean)
+    for (int64_t k = 0; k < V; ++k) {
+        if (!exotic[k >> 5]) continue;
+        const uint32_t bit = 1u << (k & 31);
+        for (int t = 0; t < T; ++t) {
+            uint32_t &nw = neg[(size_t)(k >> 5) * Tp + t], &tw = two[(size_t)(k >> 5) * Tp + t];
+            if ((k & 31) == 0) nw = 0;
+            const int b = tgt[k * T + t];
+            if (!(absent[k >> 5] & bit)) continue;
+            if (b < 0) nw |= bit;
+            if (b == -2) tw |= bit;
+        }
+    }
+    const uint32_t compat = small_compat_mask(max_mm);
     std::vector<int32_t> wlo(W), whi(W);
     for (int w = 0; w < W; ++w) {
         wlo[w] = lower_bound_i64(pos, V, ws[w]);
@@ -133,6 +149,13 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
                     any_ex = any_ex || ex;
                 }
                 const bool gen = any_ex && span < (int64_t(1) << kGeneralPosBits);
+                uint32_t ex_or = 0;
+                for (int i = s0; i < s1; ++i) {
+                    int32_t na; uint32_t ex;
+                    window_absent(wlo[w0 + i], whi[w0 + i], na, ex);
+                    ex_or |= ex;
+                }
+                const bool small = gen && ex_or < 2u;  // every other genotype of the sub-group is -1 / -2: entries from the planes
                 for (int t = 0; t < T; ++t) {
                     int cnt = 0;
                     for (int j = 0; j < nwr; ++j) {
@@ -145,6 +168,13 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
                             c &= c - 1;
                             uint32_t e = (spos[(j << 5) + b] << 1) | ((tw >> b) & 1u);
                             if (gen) e = (spos[(j << 5) + b] << 8) | (uint32_t)(uint8_t)tgt[(size_t)(base + (j << 5) + b) * T + t];
+                            if (small) {  // the genotype byte from the three planes (the sign plane only where the group is flagged)
+                                const uint32_t ngw = exotic[gi0 + j] ? neg[(size_t)(gi0 + j) * Tp + t] : 0u;
+                                const uint32_t t2 = (tw >> b) & 1u, sg = (ngw >> b) & 1u;
+                                const uint32_t byte = (((1u + t2) ^ (0u - sg)) + sg) & 0xffu;
+                                if (((spos[(j << 5) + b] << 8) | byte) != e) return -8;
+                                e = (spos[(j << 5) + b] << 8) | byte;
+                            }
                             if (cnt < L) list[cnt] = e;
                             ++cnt;
                         }
@@ -174,6 +204,7 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
                                 if (balanced && (odd_a == odd_b) != general_run_is_plain(list.data() + cur, 1, n)) return -7;
                                 if (n > 2 && balanced && odd_a == odd_b)
                                     sc = list_dp_run<8>(list.data() + cur, 1, n, bonus, pen_eff);
+                                else if (n > 2 && small) sc = list_dp_run_small(list.data() + cur, 1, n, bonus, penalty, compat);
                                 else if (n > 2 && !list_dp_run_general(list.data() + cur, 1, n, bonus, penalty, max_mm, sc)) { slow[w] = 1; continue; }
                             } else if (!overflow && balanced) {
                                 list_window_range(list.data(), 1, cur, cur_b, plo, phi, true);
@@ -184,7 +215,7 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
                         }
                         score[(size_t)w * T + t] = sc;
                         nsnp[(size_t)w * T + t] = (hi - lo) - na + n;
-                        path[(size_t)w * T + t] = gen ? 5 : overflow ? 2 : 1;
+                        path[(size_t)w * T + t] = gen ? (small ? 6 : 5) : overflow ? 2 : 1;
                     }
                 }
             }
@@ -197,6 +228,7 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
 // ---------------------------------------------------------------------------------------------
 // Scalar emulation of the fused kernel's unit paths (fused_kernels.cuh): the clean walk DP, the
 // general walk DP (<= kMaxClasses genotype values) and the class-table streaming DP behind it.
+// (score_group emulation above: 1 list, 2 walk after a list overflow, 3 / 4 walk alone, 5 general bytes, 6 small signed genotypes from the planes)
 // path: 0 empty window, 1 walk int32, 2 walk int64, 3 general walk, 4 class-table stream.
 // force_stream != 0 sends every unit through the streaming DP (the oversize-window route).
 // ---------------------------------------------------------------------------------------------
@@ -224,9 +256,25 @@ extern "C" int emul_fused_windows(const int8_t *ref, const int8_t *tgt, const in
             const int b = tgt[k * T + t];
             if (b != 0) carried[(size_t)(k >> 5) * Tp + t] |= 1u << (k & 31);
             if (b == 2) two[(size_t)(k >> 5) * Tp + t] |= 1u << (k & 31);
-            if ((unsigned)b > 2u) exotic[k >> 5] = 1;
+            // group level as the pack kernel raises it: 1 = other genotypes, all in {-2,-1} (the planes then
+            // hold |g| == 2 and the sign, for the whole group); 2 = anything else (the bytes are read)
+            if ((unsigned)b > 2u) exotic[k >> 5] |= (b == -1 || b == -2) ? 1u : 2u;
         }
     }
+    std::vector<uint32_t> neg((size_t)(G > 0 ? G : 1) * Tp, 0xdeadbeefu);  // (unwritten where the group is clean)
+    for (int64_t k = 0; k < V; ++k) {
+        if (!exotic[k >> 5]) continue;
+        const uint32_t bit = 1u << (k & 31);
+        for (int t = 0; t < T; ++t) {
+            uint32_t &nw = neg[(size_t)(k >> 5) * Tp + t], &tw = two[(size_t)(k >> 5) * Tp + t];
+            if ((k & 31) == 0) nw = 0;
+            const int b = tgt[k * T + t];
+            if (!(absent[k >> 5] & bit)) continue;
+            if (b < 0) nw |= bit;
+            if (b == -2) tw |= bit;
+        }
+    }
+    const uint32_t compat = small_compat_mask(max_mm);
     std::vector<int64_t> A(kClassTableSize), B(kClassTableSize), wp(kRingSlots), wv(kRingSlots);
     std::vector<int32_t> wgt(kRingSlots);
     for (int w = 0; w < W; ++w) {

@@ -78,8 +78,11 @@ def test_product_never_imports_oracle():
 
 
 def test_hot_kernels_keep_their_register_budget():
-    """Occupancy of the two hot kernels is part of their measured performance: the pack kernel runs
-    five CTAs per SM at 48 registers, the score kernel eight-by-registers at 64 (profiles/README.md).
+    """Occupancy of the two hot kernels is part of their measured performance: the score kernel runs
+    seven CTAs per SM by shared memory, which registers allow up to 72 (65,536 / (128 x 72) = 7.1), the pack
+    kernel three 64 KB tiles per SM at scale -- its count is the maximum over its call tree (the out-of-line
+    redo of blocks holding missing calls: 64; capping it made the clean path spill and measured 1-3 % slower),
+    and four CTAs per SM by registers is what the one-wave sizing of small grids asks the runtime for.
     A code change that silently costs registers shows up here, not first in a benchmark."""
     import re
     import shutil
@@ -94,5 +97,5 @@ def test_hot_kernels_keep_their_register_budget():
     for name, r in re.findall(r"Function (\S+):\s*\n\s*REG:(\d+)", out):
         regs[name] = int(r)
     find = lambda key: next(v for k, v in regs.items() if key in k)
-    assert find("11prep_kernelE") <= 48
-    assert find("18score_group_kernelE") <= 64
+    assert find("11prep_kernelE") <= 64
+    assert find("18score_group_kernelE") <= 72

@@ -106,7 +106,30 @@ def test_missing_data_takes_the_general_dp(emul):
     for params in [(5000, 5, -10000), (5000, 0, -10000), (5000, 2, -10000), (1, 1, 0), (123, 3, -7)]:
         for wg in (1, 8):
             path, slow = check(emul, ref, tgt, pos, ws, we, params, wg=wg, L=512)
-            assert not slow.any() and (path == 5).mean() > 0.8
+            # -1 / -2 only: the genotype bytes come from the three planes, the classes live in registers
+            assert not slow.any() and (path == 6).mean() > 0.8
+    # a sprinkle of multi-allelic dosages on top: those sub-groups read the bytes (per-class tables)
+    tgt3 = tgt.copy()
+    tgt3[rng.random(tgt.shape) < 0.0005] = 3
+    path, slow = check(emul, ref, tgt3, pos, ws, we, wg=8, L=512)
+    assert not slow.any() and (path == 5).any() and (path == 6).any()
+
+
+def test_small_signed_dp_crowding_and_every_mismatch_bound(emul):
+    # sites within 9 bp of each other (several waiting at once) holding -2 / -1 / 1 / 2, every max_mismatch
+    # that changes which classes may follow one another (differences are 1, 2, 3 and 4)
+    rng = np.random.default_rng(16)
+    V = 3000
+    pos = np.cumsum(rng.choice([1, 2, 3, 9, 10, 11, 40], size=V)).astype(np.int32)
+    ref = np.zeros((V, 2), np.int8)
+    ref[rng.random(V) < 0.1, 0] = 1
+    ws = np.arange(1, int(pos[-1]), 400, dtype=np.int32)
+    we = ws + 1999
+    tgt = rng.choice([0, -2, -1, 1, 2], size=(V, 6), p=[0.4, 0.1, 0.15, 0.2, 0.15]).astype(np.int8)
+    for mm in range(0, 6):
+        for bonus, pen in [(5000, -10000), (7, -3), (0, 5)]:
+            path, slow = check(emul, ref, tgt, pos, ws, we, (bonus, mm, pen), wg=4, L=2048)
+            assert not slow.any() and (path == 6).all()
 
 
 def test_general_dp_many_classes_and_crowding(emul):

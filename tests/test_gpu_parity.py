@@ -446,3 +446,42 @@ def test_host_threads_share_the_kernels_shared_memory_limits(eng):
             assert np.array_equal(got[0], want_w[0]) and np.array_equal(got[1], want_w[1])
             got = other.submit(eng.score_host, *small).result()
             assert np.array_equal(got[0], want_s[0]) and np.array_equal(got[1], want_s[1])
+
+
+@pytest.mark.parametrize("n_ref,n_tgt,phased,length,values,rate", [
+    (10, 24, False, 600_000, [-2, -1], 0.01),          # T = 24: -1 / -2 only, entries from the three planes
+    (10, 25, False, 600_000, [-2, -1], 0.01),          # T = 25: ragged last quad of every row
+    (50, 500, True, 400_000, [-1], 0.005),             # T = 1000 haplotypes, missing alleles (the C3 shape)
+    (50, 500, True, 400_000, [-2, -1, 3], 0.004),      # ... with multi-allelic dosages: groups of level 2 among level 1
+    (8, 130, False, 500_000, [-2, -1, -3, 4], 0.01),   # T = 130 (two column chunks of the score grid), |g| > 2 both signs
+    (8, 64, False, 500_000, [-128, 127, -2], 0.01),    # the int8 extremes
+])
+def test_missing_calls_through_the_launch_pipeline(eng, n_ref, n_tgt, phased, length, values, rate):
+    """Missing calls (-1 / -2) and other int8 genotypes through pack -> score launches (no one-launch kernel):
+    sub-groups whose other genotypes all are -1 / -2 build their entries from the planes (|g| == 2, sign) and
+    keep the classes in registers, any other byte switches the sub-group to the bytes of the matrix; clean
+    groups, flagged groups and both kinds of flagged groups next to each other.  Bit-exact vs the oracle for
+    several mismatch bounds, both algorithms; some rows cluster the missing calls so that whole 32-row groups
+    stay clean while their neighbours are flagged."""
+    from sstar_b200 import _cabi
+    from sstar_b200.synth import regular_windows, synth_chromosome
+    ref, tgt, pos = synth_chromosome(length, n_ref, n_tgt, phased, seed=9100 + n_tgt)
+    rng = np.random.default_rng(n_tgt + len(values))
+    tgt = tgt.copy()
+    m = rng.random(tgt.shape) < rate
+    m[(np.arange(len(pos)) // 32) % 3 == 0] = False  # every third 32-row group keeps clean genotypes
+    tgt[m] = rng.choice(values, size=int(m.sum())).astype(np.int8)
+    ref = ref.copy()
+    ref[rng.random(ref.shape) < 0.001] = -1
+    ws, we = regular_windows(pos, 50_000, 10_000)
+    for params in [(5000, 5, -10000), (5000, 1, -10000), (77, 3, -5), (5000, 0, -10000)]:
+        so, no = c_oracle.score_windows(ref, tgt, pos, ws, we, *params)
+        for algo in ALGOS:
+            s, n = eng.score_host(ref, tgt, pos, ws, we, *params, algo=algo, flags=_cabi.FLAG_NO_FUSED)
+            assert np.array_equal(n, no), (params, algo)
+            assert np.array_equal(s, so), (params, algo)
+    # the workspace is reused: clean data right after flagged data must not see stale sign words
+    ref2, tgt2, pos2 = synth_chromosome(length, n_ref, n_tgt, phased, seed=9100 + n_tgt)
+    so, no = c_oracle.score_windows(ref2, tgt2, pos2, ws, we)
+    s, n = eng.score_host(ref2, tgt2, pos2, ws, we, flags=_cabi.FLAG_NO_FUSED)
+    assert np.array_equal(s, so) and np.array_equal(n, no)
