@@ -74,8 +74,9 @@ SSTAR_HD int64_t score_bound(int64_t span, int64_t nvar, int32_t bonus, int32_t 
 // Scores exactly the n sites starting at `base` (a run of one column's list).  n >= 1.
 // kShift = 1: entries (position << 1 | genotype==2).  kShift = 8: general entries (position << 8 |
 // genotype byte) of a unit whose genotypes all are 1 or 2 -- the same DP, decoded differently.
+// kShift = 2: signed entries (position << 2 | sign << 1 | |genotype|==2) of a unit without a negative genotype.
 template <int kShift>
-SSTAR_HD bool entry_is_two(uint32_t e) { return kShift == 1 ? (e & 1u) != 0 : (e & 0xffu) == 2u; }
+SSTAR_HD bool entry_is_two(uint32_t e) { return kShift == 8 ? (e & 0xffu) == 2u : (e & 1u) != 0; }
 
 // true when every one of the n general entries holds genotype 1 or 2
 SSTAR_HD bool general_run_is_plain(const uint32_t *base, int ls, int n) {
@@ -203,36 +204,37 @@ SSTAR_HD_COLD bool list_dp_run_general(const uint32_t *base, int ls, int n, int3
 }
 
 // ---------------------------------------------------------------------------------------------
-// Small signed genotypes: the per-class DP for units whose carried genotypes all lie in
-// {-2, -1, 1, 2} -- what missing calls give (an allele of -1: sstar/utils/utils.py:305-306 sums the
-// alleles, so "./." is -2, a missing haploid call or "./0" -1).  Four classes, their running maxima
-// in REGISTERS (list_dp_run_general keeps them in thread-local tables, whose loads and stores are the
-// latency of that loop); waiting sites as in list_dp_run.  General entries (position << 8 | byte).
-// `compat` comes from small_compat_mask(max_mismatch).
+// Small signed genotypes: units whose carried genotypes all lie in {-2, -1, 1, 2} -- what missing calls
+// give (an allele of -1: sstar/utils/utils.py:305-306 sums the alleles, so "./." is -2, a missing
+// haploid call or "./0" -1).  Signed entries = (relative position << 2) | (g < 0) << 1 | (|g| == 2), built
+// from three bit-planes without touching the genotype bytes; the low two bits are the class:
+// 0: g = 1, 1: g = 2, 2: g = -1, 3: g = -2.  A unit without a negative genotype is scored by
+// list_dp_run<2> (the four-maxima DP reads bit 0 and the position only); the others by
+// list_dp_run_signed: four classes, their running maxima in REGISTERS (list_dp_run_general keeps
+// them in thread-local tables, whose loads and stores are the latency of that loop), waiting sites as
+// in list_dp_run.  `compat` comes from signed_compat_mask(max_mismatch).
 // ---------------------------------------------------------------------------------------------
-SSTAR_HD int small_class(uint32_t e) {  // genotype byte -2, -1, 1, 2 -> class 0..3
-    const int32_t g = (int32_t)(int8_t)(e & 0xffu);
-    return g + 2 - (int)(g > 0);
-}
+constexpr int kSignedShift = 2;
+SSTAR_HD int signed_class_value(int ci) { return (ci & 2) ? -1 - (ci & 1) : 1 + (ci & 1); }
 // bit (4 * i + j): classes i != j whose genotype values differ by at most max_mm (sstar.py:202-206)
-SSTAR_HD uint32_t small_compat_mask(int32_t max_mm) {
+SSTAR_HD uint32_t signed_compat_mask(int32_t max_mm) {
     uint32_t m = 0;
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 4; ++j) {
-            const int vi = i - 2 + (int)(i > 1), vj = j - 2 + (int)(j > 1);
+            const int vi = signed_class_value(i), vj = signed_class_value(j);
             const int d = vi > vj ? vi - vj : vj - vi;
             if (i != j && d <= max_mm) m |= 1u << (4 * i + j);
         }
     return m;
 }
 
-SSTAR_HD_COLD int64_t list_dp_run_small(const uint32_t *base, int ls, int n, int32_t bonus, int32_t penalty, uint32_t compat) {
+SSTAR_HD_COLD int64_t list_dp_run_signed(const uint32_t *base, int ls, int n, int32_t bonus, int32_t penalty, uint32_t compat) {
     constexpr int32_t NEG = Sentinel<int32_t>::NEG, THR = Sentinel<int32_t>::THR;
     int32_t ring[kRingSlots];  // v of waiting sites older than k-1 (crowded sites only)
     int32_t A0 = NEG, A1 = NEG, A2 = NEG, A3 = NEG, B0 = NEG, B1 = NEG, B2 = NEG, B3 = NEG, top = NEG;
     auto commit = [&](uint32_t ec, int32_t vc) {  // the site becomes an eligible predecessor
-        const int32_t d = vc - (int32_t)(ec >> 8);
-        const int ci = small_class(ec);
+        const int32_t d = vc - (int32_t)(ec >> kSignedShift);
+        const int ci = (int)(ec & 3u);
         if (ci == 0)      { A0 = imax(A0, d); B0 = imax(B0, vc); }
         else if (ci == 1) { A1 = imax(A1, d); B1 = imax(B1, vc); }
         else if (ci == 2) { A2 = imax(A2, d); B2 = imax(B2, vc); }
@@ -244,21 +246,21 @@ SSTAR_HD_COLD int64_t list_dp_run_small(const uint32_t *base, int ls, int n, int
     int32_t pv = 0;
     for (int k = 0; k < n; ++k) {
         const uint32_t e = *pk;
-        const int32_t p = (int32_t)(e >> 8);
+        const int32_t p = (int32_t)(e >> kSignedShift);
         if (c == k - 1) {  // common case: only the previous site waits, in registers
-            if (p - (int32_t)(pe >> 8) >= kMinPairDistance) { commit(pe, pv); c = k; }
+            if (p - (int32_t)(pe >> kSignedShift) >= kMinPairDistance) { commit(pe, pv); c = k; }
             else ring[(k - 1) & (kRingSlots - 1)] = pv;
         } else if (c < k) {  // crowded sites: older ones wait in the ring
             while (c < k) {
                 const uint32_t ec = (c == k - 1) ? pe : base[c * ls];
                 const int32_t vc = (c == k - 1) ? pv : ring[c & (kRingSlots - 1)];
-                if (p - (int32_t)(ec >> 8) < kMinPairDistance) break;
+                if (p - (int32_t)(ec >> kSignedShift) < kMinPairDistance) break;
                 commit(ec, vc);
                 ++c;
             }
             if (c < k) ring[(k - 1) & (kRingSlots - 1)] = pv;
         }
-        const int ci = small_class(e);
+        const int ci = (int)(e & 3u);
         const int32_t same = ci == 0 ? A0 : (ci == 1 ? A1 : (ci == 2 ? A2 : A3));
         const uint32_t cm = compat >> (4 * ci);
         int32_t other = NEG;
@@ -273,6 +275,17 @@ SSTAR_HD_COLD int64_t list_dp_run_small(const uint32_t *base, int ls, int n, int
         pk += ls;
     }
     return (n <= 2 || top <= THR) ? kNegInf64 : (int64_t)top;
+}
+
+// list_window_range_shifted<2> for signed entries that also keeps, for both cursors, the number of entries
+// passed whose genotype is negative: a unit is "plain" (list_dp_run<2> takes it) iff the two counts agree.
+SSTAR_HD void list_window_range_signed(const uint32_t *list, int ls, int &a, int &b, int &odd_a, int &odd_b, uint32_t plo,
+                                       uint32_t phi) {
+    const uint32_t *pa = list + a * ls;
+    while ((*pa >> kSignedShift) < plo) { odd_a += (int)((*pa >> 1) & 1u); pa += ls; ++a; }
+    if (b < a) { b = a; odd_b = odd_a; }
+    const uint32_t *pb = list + b * ls;
+    while ((*pb >> kSignedShift) <= phi) { odd_b += (int)((*pb >> 1) & 1u); pb += ls; ++b; }
 }
 
 // list_window_range_shifted<8> for general entries that also keeps, for both cursors, the number of

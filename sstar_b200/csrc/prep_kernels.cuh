@@ -94,8 +94,9 @@ __device__ __forceinline__ void bounds_block(const BoundsArgs &a, int block, int
 //                   word read, "byte != 0" and "byte == 2" folded to bit 0 of each byte and
 //                   shifted into per-8-row accumulators; PRMT transposes them into 4 column
 //                   words per plane; masked by the group's absent word   (sstar.py:163-164)
-//   Genotypes outside {0,1,2} are detected by two running ORs; only a thread that sees one
-//   rescans its 32x4 bytes exactly (absent rows, real columns) and raises the group's flag.
+//   Genotypes outside {0,1,2} are detected by two running ORs; the warp redoes such a 32x4 block with
+//   ballots (a lane per row: exact planes on |b|, plus the sign plane of a flagged group) and raises the
+//   group's level (1: the other bytes all are -1 / -2, 2: anything else).
 // Output planes are word-major [G][Tp]: 128-bit coalesced stores here, coalesced loads in K2.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 ldg_stream_v4(const uint4 *p) {
@@ -177,121 +178,70 @@ __device__ __forceinline__ void transpose4(uint32_t a0, uint32_t a1, uint32_t a2
     c[3] = __byte_perm(t2, t3, 0x7632);
 }
 
-// A 32-row x 4-column block holding bytes outside {0,1,2} is redone on |b| and the sign, still four columns
-// at a time.  Missing calls give -1 / -2 (sstar/utils/utils.py:305-306 sums alleles of -1), and a block whose
-// other bytes all are -1 / -2 keeps the cheap bit tests: with n = b >> 7 (0 / 1 per byte) and s = n * 0xff,
-// |b| = (b ^ s) + n never carries across bytes (|b| <= 0x80), "b != 0" and "|b| == 2" then are the bit tests of
-// the clean path on |b|, and n itself is the sign plane.  Returns true when some byte of the block has |b| > 2
-// (multi-allelic dosages, garbage in the padding of a ragged last quad): pack_block_exact then redoes it.
+// A 32-row x 4-column block holding a byte outside {0,1,2} (missing calls give -1 / -2: sstar/utils/utils.py:305-306
+// sums alleles of -1; multi-allelic dosages; garbage in the padding of a ragged last quad) is redone by the WHOLE
+// warp, a lane per row: each lane reads its row's four bytes and sixteen ballots give the four columns' words of
+// "b != 0", "|b| == 2", "b < 0" and "|b| > 2" -- exact for any byte, ~70 warp instructions per block, where a
+// lane redoing its own block alone kept 31 lanes waiting for 700 (a handful of missing calls per tile, the
+// common case of real data, doubled the tile's pack time).  Only when more than kDenseOddLanes blocks of a
+// warp step are odd do the lanes redo their own blocks in parallel (SIMD within a word on |b|), leaving the
+// ballots the blocks that hold |b| > 2.  The block's level: 2 when a reference-absent row
+// of a real column holds |b| > 2, else 1 when one holds a negative byte, else 0.  The tile remembers which
+// blocks were redone (their sign words are written) in kRedoWords * 32 bits.
+constexpr int kRedoWords = 64;
+constexpr int kDenseOddLanes = 8;  // more odd blocks than this in a warp step: per-lane redo (700 instructions flat) beats the ballots (70 a block)
+
+// The per-lane redo of a block on |b| and the sign (dense case above), out of line: the clean path must not
+// pay its registers.  Returns true when some byte of the block has |b| > 2.
 // Rows are addressed as in pack_tile (kRowPhase: each row segment keeps its own 16-byte phase).
 template <bool kAligned, bool kRowPhase>
-__device__ __noinline__ bool pack_block_signed(const uint8_t *s_tgt, uint32_t base, uint32_t tpitch, uint32_t tgt_phase,
+__device__ __forceinline__ bool pack_block_signed(const uint8_t *s_tgt, uint32_t base, uint32_t tpitch, uint32_t tgt_phase,
                                                uint32_t pstep, uint32_t row0, uint32_t col_off, uint32_t car[4],
                                                uint32_t two[4], uint32_t neg[4]) {
-    uint32_t nz[4], tw[4], ng[4], e_or = 0, e_and = 0;
+    // two sweeps over the block's rows (the planes on |b|, then the sign words): fewer values live at a time
+    uint32_t e_or = 0, e_and = 0;
+    {
+        uint32_t nz[4], tw[4];
 #pragma unroll
-    for (int blk = 0; blk < 4; ++blk) {
-        uint32_t an = 0, at = 0, ag = 0;
+        for (int blk = 0; blk < 4; ++blk) {
+            uint32_t an = 0, at = 0;
 #pragma unroll
-        for (int rr = 7; rr >= 0; --rr) {
-            const uint32_t r = (uint32_t)(blk * 8 + rr);
-            const uint32_t off = kRowPhase ? (row0 + r) * tpitch + ((tgt_phase + (row0 + r) * pstep) & 15u) + col_off
-                                           : base + r * tpitch;
-            const uint32_t w = lds_word<kAligned>(s_tgt, off);
-            const uint32_t n01 = (w >> 7) & 0x01010101u;
-            const uint32_t m = (w ^ ((n01 << 8) - n01)) + n01;  // |b| per byte
-            const uint32_t h = m >> 1;
-            an = an + an + ((m | h) & 0x01010101u);  // |b| in {1,2,3} -> bit 0
-            at = at + at + (h & 0x01010101u);        // |b| in {2,3}   -> bit 0
-            ag = ag + ag + n01;
-            e_or |= m;
-            e_and |= m & h;
+            for (int rr = 7; rr >= 0; --rr) {
+                const uint32_t r = (uint32_t)(blk * 8 + rr);
+                const uint32_t off = kRowPhase ? (row0 + r) * tpitch + ((tgt_phase + (row0 + r) * pstep) & 15u) + col_off
+                                               : base + r * tpitch;
+                const uint32_t w = lds_word<kAligned>(s_tgt, off);
+                const uint32_t n01 = (w >> 7) & 0x01010101u;
+                const uint32_t m = (w ^ ((n01 << 8) - n01)) + n01;  // |b| per byte
+                const uint32_t h = m >> 1;
+                an = an + an + ((m | h) & 0x01010101u);  // |b| in {1,2,3} -> bit 0
+                at = at + at + (h & 0x01010101u);        // |b| in {2,3}   -> bit 0
+                e_or |= m;
+                e_and |= m & h;
+            }
+            nz[blk] = an;
+            tw[blk] = at;
         }
-        nz[blk] = an;
-        tw[blk] = at;
-        ng[blk] = ag;
+        transpose4(nz[0], nz[1], nz[2], nz[3], car);
+        transpose4(tw[0], tw[1], tw[2], tw[3], two);
     }
-    transpose4(nz[0], nz[1], nz[2], nz[3], car);
-    transpose4(tw[0], tw[1], tw[2], tw[3], two);
-    transpose4(ng[0], ng[1], ng[2], ng[3], neg);
+    {
+        uint32_t ng[4];
+#pragma unroll
+        for (int blk = 0; blk < 4; ++blk) {
+            uint32_t ag = 0;
+#pragma unroll
+            for (int rr = 7; rr >= 0; --rr) {
+                const uint32_t r = (uint32_t)(blk * 8 + rr);
+                const uint32_t off = kRowPhase ? (row0 + r) * tpitch + ((tgt_phase + (row0 + r) * pstep) & 15u) + col_off
+                                               : base + r * tpitch;
+                ag = ag + ag + ((lds_word<kAligned>(s_tgt, off) >> 7) & 0x01010101u);
+            }
+            ng[blk] = ag;
+        }
+        transpose4(ng[0], ng[1], ng[2], ng[3], neg);
+    }
     return ((e_or & 0xfcfcfcfcu) | (e_and & 0x01010101u)) != 0;
-}
-
-// The same block with the EXACT byte tests on |b| (bit 7 of each byte: "!= 0", "|b| == 2", "|b| > 2"): the
-// three planes' words of the four columns, and the block's level -- 2 when a reference-absent row of a real
-// column holds |b| > 2, else 1 when one holds a negative byte, else 0.
-template <bool kAligned, bool kRowPhase>
-__device__ __noinline__ uint32_t pack_block_exact(const uint8_t *s_tgt, uint32_t base, uint32_t tpitch, uint32_t tgt_phase,
-                                                  uint32_t pstep, uint32_t row0, uint32_t col_off, uint32_t ab, int ncol,
-                                                  uint32_t car[4], uint32_t two[4], uint32_t neg[4]) {
-    uint32_t nz[4], tw[4], ng[4], ex[4];
-#pragma unroll
-    for (int blk = 0; blk < 4; ++blk) {
-        uint32_t an = 0, at = 0, ag = 0, ax = 0;
-#pragma unroll
-        for (int rr = 7; rr >= 0; --rr) {
-            const uint32_t r = (uint32_t)(blk * 8 + rr);
-            const uint32_t off = kRowPhase ? (row0 + r) * tpitch + ((tgt_phase + (row0 + r) * pstep) & 15u) + col_off
-                                           : base + r * tpitch;
-            const uint32_t w = lds_word<kAligned>(s_tgt, off);
-            const uint32_t n01 = (w >> 7) & 0x01010101u;
-            const uint32_t m = (w ^ ((n01 << 8) - n01)) + n01;  // |b| per byte, 0 .. 0x80
-            an = an + an + (bytes_nonzero(m) >> 7);
-            at = at + at + (bytes_zero(m ^ 0x02020202u) >> 7);
-            ax = ax + ax + ((bytes_nonzero(m & 0xfcfcfcfcu) | bytes_zero(m ^ 0x03030303u)) >> 7);
-            ag = ag + ag + n01;
-        }
-        nz[blk] = an;
-        tw[blk] = at;
-        ng[blk] = ag;
-        ex[blk] = ax;
-    }
-    uint32_t exo[4];
-    transpose4(nz[0], nz[1], nz[2], nz[3], car);
-    transpose4(tw[0], tw[1], tw[2], tw[3], two);
-    transpose4(ng[0], ng[1], ng[2], ng[3], neg);
-    transpose4(ex[0], ex[1], ex[2], ex[3], exo);
-    uint32_t big = 0, sgn = 0;
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-        if (c < ncol) {  // (rows past the matrix's end have no absent bit)
-            big |= exo[c] & ab;
-            sgn |= neg[c] & ab;
-        }
-    return big ? 2u : (sgn ? 1u : 0u);
-}
-
-// The out-of-line redo of a block that holds a byte outside {0,1,2}: planes on |b| into car / two, the
-// block's sign words stored to `neg_out` (masked by the absent word `ab`), its bit set in the tile's redo
-// map.  Returns the block's level (0: nothing outside {0,1,2} in a reference-absent row of a real column,
-// 1: such bytes, all -1 / -2, 2: others).  Column chunks of a group cannot see one another's blocks, and
-// the tile remembers kRedoWords * 32 redone blocks: there a flagged block is level 2 (its group's genotype
-// bytes are read, never the sign plane).
-constexpr int kRedoWords = 64;
-template <bool kAligned, bool kRowPhase, bool kChunked>
-__device__ __noinline__ uint32_t pack_block_odd(const uint8_t *s_tgt, uint32_t base, uint32_t tpitch, uint32_t tgt_phase,
-                                                uint32_t pstep, uint32_t row0, uint32_t col_off, uint32_t ab, int ncol,
-                                                uint32_t car[4], uint32_t two[4], uint32_t *neg_out, uint32_t *s_redo, int it) {
-    uint32_t neg[4];
-    uint32_t level = 0;
-    if (pack_block_signed<kAligned, kRowPhase>(s_tgt, base, tpitch, tgt_phase, pstep, row0, col_off, car, two, neg)) {
-        level = pack_block_exact<kAligned, kRowPhase>(s_tgt, base, tpitch, tgt_phase, pstep, row0, col_off, ab, ncol, car, two, neg);
-    } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-            if (c < ncol && (neg[c] & ab)) level = 1u;
-    }
-    if (level && (kChunked || it >= kRedoWords * 32)) level = 2u;
-    if (it < kRedoWords * 32) atomicOr(&s_redo[it >> 5], 1u << (it & 31));
-    if (level) s_redo[kRedoWords] = 1u;  // some group of the tile is flagged
-    if (ncol == 4) {
-        *reinterpret_cast<uint4 *>(neg_out) = make_uint4(neg[0] & ab, neg[1] & ab, neg[2] & ab, neg[3] & ab);
-    } else {
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-            if (c < ncol) neg_out[c] = neg[c] & ab;
-    }
-    return level;
 }
 
 // The staged target tile holds columns [c0, c0 + ncols) of the CTA's rows with a row pitch of
@@ -393,13 +343,15 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
     if (tid <= kRedoWords) s_redo[tid] = 0u;
     __syncthreads();
 
-    // B: 4 columns x 32 rows per thread
+    // B: 4 columns x 32 rows per thread (a warp's 32 consecutive items per step, the trip count warp-uniform)
     const int nq = (ncols + 3) >> 2;
     const int nitems = ng * nq;
-    for (int it = tid; it < nitems; it += kPackThreads) {
+    const uint32_t pstep = (uint32_t)a.T & 15u;
+    for (int it0 = tid - lane; it0 < nitems; it0 += kPackThreads) {
+        const bool valid = it0 + lane < nitems;
+        const int it = valid ? it0 + lane : nitems - 1;  // (idle lanes of the last step shadow the last item, without stores)
         const int gl = it / nq, q = it - gl * nq;
         const uint32_t base = tgt_phase + (uint32_t)(gl * 32) * (uint32_t)tpitch + 4u * q;
-        const uint32_t pstep = (uint32_t)a.T & 15u;
         auto row_off = [&](int r) -> uint32_t {  // r: row within the group
             if (!kRowPhase) return base + (uint32_t)r * (uint32_t)tpitch;
             const uint32_t rr = (uint32_t)(gl * 32 + r);
@@ -427,13 +379,71 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
         transpose4(tw[0], tw[1], tw[2], tw[3], two);
         const int ncol = min(4, ncols - 4 * q);
         const size_t o = (size_t)(g0 + gl) * a.Tp + c0 + 4 * q;
-        uint32_t level = 0;
-        if ((e_or & 0xfcfcfcfcu) | (e_and & 0x01010101u))
-            // a byte outside {0,1,2} somewhere in this 32x4 block (missing calls, multi-allelic dosages --
-            // or the padding bytes of a ragged last quad / tail rows): redone on |b| and the sign, out of
-            // line (the common path keeps its registers)
-            level = pack_block_odd<kAligned, kRowPhase, kChunked>(s_tgt, base, (uint32_t)tpitch, tgt_phase, pstep,
-                                                                  (uint32_t)(gl * 32), 4u * q, ab, ncol, car, two, a.neg + o, s_redo, it);
+        // a byte outside {0,1,2} somewhere in this lane's block: the warp redoes such blocks one by one
+        const bool odd = valid && (((e_or & 0xfcfcfcfcu) | (e_and & 0x01010101u)) != 0);
+        uint32_t oddmask = __ballot_sync(0xffffffffu, odd);
+        if (oddmask) {
+            uint32_t neg[4] = {0u, 0u, 0u, 0u}, big = 0;
+            if (__popc(oddmask) > kDenseOddLanes) {
+                // many of the warp's blocks are odd (missing calls at a percent of all calls): every such lane redoes
+                // its own block on |b| and the sign with the bit tests of the clean path -- with n = b >> 7 (0 / 1 per
+                // byte) and s = n * 0xff, |b| = (b ^ s) + n never carries across bytes (|b| <= 0x80) -- which is exact
+                // while every |b| <= 2; the blocks holding a larger one are left to the ballots below
+                bool left = false;
+                if (odd) left = pack_block_signed<kAligned, kRowPhase>(s_tgt, base, (uint32_t)tpitch, tgt_phase, pstep,
+                                                                       (uint32_t)(gl * 32), 4u * q, car, two, neg);
+                oddmask = __ballot_sync(0xffffffffu, left);
+            }
+            while (oddmask) {
+                const int src = __ffs(oddmask) - 1;
+                oddmask &= oddmask - 1;
+                const int its = it0 + src, gls = its / nq, qs = its - gls * nq;  // lane src's block; this lane reads row `lane` of it
+                const uint32_t rr = (uint32_t)(gls * 32 + lane);
+                const uint32_t off = kRowPhase ? rr * (uint32_t)tpitch + ((tgt_phase + rr * pstep) & 15u) + 4u * qs
+                                               : tgt_phase + rr * (uint32_t)tpitch + 4u * qs;
+                const uint32_t w = lds_word<kAligned>(s_tgt, off);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int b = (int)(w << (24 - 8 * c)) >> 24;  // the row's byte of column c, sign-extended
+                    const int mag = b < 0 ? -b : b;
+                    const uint32_t m_nz = __ballot_sync(0xffffffffu, b != 0);
+                    const uint32_t m_tw = __ballot_sync(0xffffffffu, mag == 2);
+                    const uint32_t m_ng = __ballot_sync(0xffffffffu, b < 0);
+                    const uint32_t m_bg = __ballot_sync(0xffffffffu, mag > 2);
+                    if (lane == src) {
+                        car[c] = m_nz;
+                        two[c] = m_tw;
+                        neg[c] = m_ng;
+                        if (c < ncol) big |= m_bg;  // (rows past the matrix's end have no absent bit)
+                    }
+                }
+            }
+            if (odd) {
+                uint32_t level = 0;
+                if (big & ab) level = 2u;
+                else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c < ncol && (neg[c] & ab)) level = 1u;
+                }
+                // column chunks of a group cannot see one another's blocks, and the tile remembers kRedoWords * 32
+                // redone blocks: such groups read the genotype bytes (level 2), never the sign plane
+                if (level && (kChunked || it >= kRedoWords * 32)) level = 2u;
+                if (it < kRedoWords * 32) atomicOr(&s_redo[it >> 5], 1u << (it & 31));
+                if (level) {
+                    s_redo[kRedoWords] = 1u;  // some group of the tile is flagged
+                    atomicOr(&s_exo[gl], level);
+                }
+                if (ncol == 4) {
+                    *reinterpret_cast<uint4 *>(a.neg + o) = make_uint4(neg[0] & ab, neg[1] & ab, neg[2] & ab, neg[3] & ab);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        if (c < ncol) a.neg[o + c] = neg[c] & ab;
+                }
+            }
+        }
+        if (!valid) continue;
         if (ncol == 4) {
             *reinterpret_cast<uint4 *>(a.carried + o) = make_uint4(car[0] & ab, car[1] & ab, car[2] & ab, car[3] & ab);
             *reinterpret_cast<uint4 *>(a.two + o) = make_uint4(two[0] & ab, two[1] & ab, two[2] & ab, two[3] & ab);
@@ -445,7 +455,6 @@ __device__ __forceinline__ void pack_tile(const PackArgs &a, uint8_t *smem, int3
                 a.two[o + c] = two[c] & ab;
             }
         }
-        if (level) atomicOr(&s_exo[gl], level);
     }
     __syncthreads();
     // A flagged group's sign plane is read for ALL its columns: the blocks that took the clean path store
@@ -637,9 +646,6 @@ __global__ void __launch_bounds__(kPackThreads) fetch_kernel(const __grid_consta
     fetch_block(b, (int)blockIdx.x, kPackThreads, threadIdx.x);
 }
 
-// (shapes that fill the machine keep three 64 KB tiles per SM, so the registers of the out-of-line redo of odd
-// blocks -- the kernel's count is the call tree's maximum -- cost no occupancy there; capping them made the
-// clean path spill)
 __global__ void __launch_bounds__(kPackThreads)
 prep_kernel(const __grid_constant__ PackArgs p, const __grid_constant__ BoundsArgs b, int n_pack, int mode) {
     extern __shared__ __align__(16) uint8_t smem[];

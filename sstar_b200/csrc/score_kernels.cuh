@@ -54,64 +54,23 @@ struct GroupCtx {
     int io;                              // its first window's slot in the GroupShared arrays
     int32_t rlo, rhi, gi0, nwr, pen_eff;
     bool mono_hi;
-    bool small;  // general body: every other genotype of the sub-group is -1 / -2 (group levels <= 1)
 };
 
-// The site list of this thread's column for a sub-group whose other genotypes all are -1 / -2: general
-// entries (relative position << 8 | genotype byte) with the byte taken from the planes -- carried, "|g| == 2"
-// and the sign plane, which exists only where the group is flagged (clean groups never write it):
-// byte = sign ? -(1 + two) : 1 + two.  No genotype byte is fetched.  Out of line: the common body must not pay
-// its registers.  Returns the column's site count (entries beyond L - 1 land in the spill slot).
-__device__ __noinline__ int build_list_small(const ScoreArgs &a, const GroupCtx &c, int ls) {
-    if (c.t >= a.T) return 0;
-    const uint32_t *cp = a.carried + (size_t)c.gi0 * a.Tp + c.t;
-    const uint32_t *tp = a.two + (size_t)c.gi0 * a.Tp + c.t;
-    const uint32_t *np = a.neg + (size_t)c.gi0 * a.Tp + c.t;
-    const uint32_t first_mask = 0xffffffffu << (c.rlo & 31);
-    const uint32_t last_mask = 0xffffffffu >> (31 - ((c.rhi - 1) & 31));
-    const uint32_t *s_pos = c.s_pos;
-    uint32_t *w = c.s_list + c.tid;
-    uint32_t *const w_end = w + (size_t)c.L * ls;  // the spill slot
-    const int nwr = c.nwr;
-    int cnt = 0;
-    constexpr int kBatch = 4;
-    for (int jb = 0; jb < nwr; jb += kBatch) {
-        uint32_t cw[kBatch], tw[kBatch], ng[kBatch];
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-            const bool in = jb + u < nwr;
-            cw[u] = in ? __ldg(cp + (size_t)(jb + u) * a.Tp) : 0u;
-            tw[u] = in ? __ldg(tp + (size_t)(jb + u) * a.Tp) : 0u;
-            ng[u] = (in && __ldg(a.exotic + c.gi0 + jb + u)) ? __ldg(np + (size_t)(jb + u) * a.Tp) : 0u;
-            if (jb + u == 0) cw[u] &= first_mask;
-            if (jb + u == nwr - 1) cw[u] &= last_mask;
-        }
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-            uint32_t cbits = cw[u];
-            cnt += __popc(cbits);
-            while (cbits) {
-                const int b = __ffs(cbits) - 1;
-                cbits &= cbits - 1;
-                const uint32_t t2 = (tw[u] >> b) & 1u, sg = (ng[u] >> b) & 1u;
-                *w = (s_pos[((jb + u) << 5) + b] << 8) | ((((1u + t2) ^ (0u - sg)) + sg) & 0xffu);
-                w = (w + ls < w_end) ? w + ls : w_end;
-            }
-        }
-    }
-    return cnt;
-}
-
-// List build + DP of one window group.  kGen = false: genotypes in {0,1,2}, entries
-// (relative position << 1 | genotype==2), the four-maxima DP.  kGen = true: a window of the group
-// holds other genotypes (missing calls, multi-allelic sites): entries (relative position << 8 |
-// genotype byte) and a per-class DP of dp_core.cuh.  When those other genotypes all are -1 / -2
-// (missing calls: c.small) the byte comes from the planes -- "|g| == 2" and the sign plane the pack
-// kernel writes for flagged groups -- and the classes live in registers (list_dp_run_small); otherwise
-// the bytes are fetched from the target matrix and the classes sit in thread-local tables.
-template <int kGenMode, bool kNarrow = false>
+// List build + DP of one window group, in one of three modes.
+//   0  genotypes in {0,1,2}: entries (relative position << 1 | genotype==2), the four-maxima DP.
+//   2  some window holds other genotypes and they all are -1 / -2 (missing calls; group levels <= 1): signed
+//      entries (relative position << 2 | sign << 1 | |g|==2) from the planes -- "|g| == 2" and the sign plane
+//      the pack kernel writes for flagged groups, no genotype byte is fetched.  A column without a negative
+//      site (nearly all of them when missing calls are sparse) runs the clean body on these entries; the
+//      others count the negative entries their cursors pass, units without one still take the four-maxima
+//      DP, the rest the four-class DP with the classes in registers (list_dp_run_signed).
+//   1  any other byte: entries (relative position << 8 | genotype byte, fetched from the target matrix) and
+//      the per-class DP with thread-local tables (list_dp_run_general).
+template <int kMode, bool kNarrow = false>
 __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c) {
-    constexpr bool kGen = kGenMode != 0;     // general entries (position << 8 | genotype byte)
+    constexpr bool kGen = kMode == 1;     // general entries, genotype bytes
+    constexpr bool kSigned = kMode == 2;  // signed entries from three planes
+    constexpr bool kTwoQueues = kGen || kSigned;
     GroupShared &g = *c.g;
     const int32_t *glo = g.lo + c.io, *ghi = g.hi + c.io, *gnabs = g.nabs + c.io;
     const uint32_t *gplo = g.plo + c.io, *gphi = g.phi + c.io, *gex = g.ex + c.io;
@@ -119,19 +78,18 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
     uint32_t *s_work = c.s_pos;  // [wg * bd] unit worklist, once the lists are built
     const int tid = c.tid, bd = c.bd, chunk = c.chunk, t = c.t, w0 = c.w0, nwin = c.nwin, L = c.L;
     const int ls = kNarrow ? score_list_stride(a.T, bd) : bd;  // words between consecutive entries of a column's list
-    constexpr int kShift = kGen ? 8 : 1;
-    constexpr int kBatch = 8;  // plane words fetched per round trip
+    constexpr int kShift = kGen ? 8 : (kSigned ? kSignedShift : 1);
+    constexpr int kBatch = kSigned ? 4 : 8;  // plane words fetched per round trip (the signed body holds three planes' words)
 
     // this thread's column: plane words -> site list.  Shared memory is addressed with 32-bit
     // shared-window addresses (ld/st.shared) and the write cursor is clamped to a spill slot
     // (index L) instead of branching on overflow.
     int cnt = 0;
-    const bool small = kGen && c.small;
-    if (small) {
-        cnt = build_list_small(a, c, ls);
-    } else if (t < a.T) {
+    bool col_neg = false;  // signed body: this column's list holds a negative genotype
+    if (t < a.T) {
         const uint32_t *cp = a.carried + (size_t)c.gi0 * a.Tp + t;
         const uint32_t *tp = a.two + (size_t)c.gi0 * a.Tp + t;
+        const uint32_t *np = a.neg + (size_t)c.gi0 * a.Tp + t;
         const uint32_t first_mask = 0xffffffffu << (c.rlo & 31);
         const uint32_t last_mask = 0xffffffffu >> (31 - ((c.rhi - 1) & 31));
         const uint32_t pos_addr = (uint32_t)__cvta_generic_to_shared(c.s_pos);
@@ -139,8 +97,9 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
         uint32_t w_addr = (uint32_t)__cvta_generic_to_shared(s_list + tid);
         const uint32_t w_end = w_addr + (uint32_t)L * step;  // the spill slot
         const int nwr = c.nwr;
+        uint32_t neg_any = 0;
         for (int jb = 0; jb < nwr; jb += kBatch) {
-            uint32_t cw[kBatch], tw[kBatch];
+            uint32_t cw[kBatch], tw[kBatch], ng[kSigned ? kBatch : 1];
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) cw[u] = (jb + u < nwr) ? __ldg(cp + (size_t)(jb + u) * a.Tp) : 0u;
 #pragma unroll
@@ -148,6 +107,11 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
                 if (jb + u == 0) cw[u] &= first_mask;
                 if (jb + u == nwr - 1) cw[u] &= last_mask;
                 tw[u] = (!kGen && jb + u < nwr) ? __ldg(tp + (size_t)(jb + u) * a.Tp) : 0u;  // not chained to cw
+                // the sign plane exists only where the group is flagged (clean groups never write it)
+                if (kSigned) {
+                    ng[u] = (jb + u < nwr && __ldg(a.exotic + c.gi0 + jb + u)) ? __ldg(np + (size_t)(jb + u) * a.Tp) : 0u;
+                    neg_any |= ng[u] & cw[u];
+                }
             }
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
@@ -163,15 +127,17 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
                     } else {
                         uint32_t rel;
                         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rel) : "r"(sp + 4u * (uint32_t)b));
-                        e = (rel << 1) | ((tw[u] >> b) & 1u);
+                        if (kSigned) e = (rel << 2) | (((ng[kSigned ? u : 0] >> b) & 1u) << 1) | ((tw[u] >> b) & 1u);
+                        else e = (rel << 1) | ((tw[u] >> b) & 1u);
                     }
                     asm volatile("st.shared.u32 [%0], %1;" ::"r"(w_addr), "r"(e) : "memory");
                     w_addr = min(w_addr + step, w_end);
                 }
             }
         }
+        col_neg = neg_any != 0;
     }
-    if (kGen && !small && t < a.T) {
+    if (kGen && t < a.T) {
         // general entries: (relative position << 8 | genotype byte).  The bytes are fetched here,
         // in a loop of independent iterations (several loads in flight), not one exposed memory
         // latency per site inside the bit loop above.
@@ -185,7 +151,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
         }
     }
     const bool overflow = cnt >= L;  // one slot is the terminator
-    const uint32_t compat = small ? small_compat_mask(a.max_mm) : 0u;
+    const uint32_t compat = kSigned ? signed_compat_mask(a.max_mm) : 0u;
     if (t < a.T && !overflow) s_list[cnt * ls + tid] = kListSentinel;
     if (tid == 0) { g.n_work = 0; g.n_work_back = 0; }
     __syncthreads();  // every list is built: the position tile becomes the worklist
@@ -197,7 +163,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
     };
     // windows with genotypes outside {0,1,2} that the list path is not taking in general mode
     auto route_exotic = [&](int i) -> bool {
-        if (kGen || !gex[i]) return false;
+        if (kTwoQueues || !gex[i]) return false;
         if (chunk == 0 && tid == 0) a.slow_list[a.w_begin + atomicAdd(&a.hdr->n_slow[a.slot], 1)] = w0 + i;
         return true;
     };
@@ -219,11 +185,12 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
             if (t < a.T && !ex && hi > lo) {
                 if (!overflow) {
                     if (kGen) list_window_range_general(s_list + tid, ls, cur_a, cur_b, odd_a, odd_b, gplo[i], gphi[i]);
+                    else if (kSigned && col_neg) list_window_range_signed(s_list + tid, ls, cur_a, cur_b, odd_a, odd_b, gplo[i], gphi[i]);
                     else list_window_range_shifted<kShift>(s_list + tid, ls, cur_a, cur_b, gplo[i], gphi[i], true);
                     n = cur_b - cur_a;
                     queued = n > 2;
-                } else if (kGen) {
-                    bail_window(w);
+                } else if (kGen || (kSigned && col_neg)) {
+                    bail_window(w);  // (a signed column without a negative site walks its clean planes below)
                 } else {
                     walk_dp_unit<int32_t>(LdgU32(), LdgPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus, a.penalty,
                                           a.max_mm, n, score);
@@ -233,9 +200,9 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
             // units whose genotypes all are 1 / 2 (most of them) queue from the front and take the
             // four-maxima DP, the others queue from the far end and take the per-class DP: the
             // warps of pass 2 then run one body at a time.
-            const bool other = kGen && queued && odd_b != odd_a;  // some genotype of the unit is not 1 / 2
+            const bool other = kTwoQueues && queued && odd_b != odd_a;  // some genotype of the unit is not 1 / 2
             const uint32_t qm = __ballot_sync(0xffffffffu, queued && !other);
-            const uint32_t om = kGen ? __ballot_sync(0xffffffffu, other) : 0u;
+            const uint32_t om = kTwoQueues ? __ballot_sync(0xffffffffu, other) : 0u;
             const uint32_t item = (uint32_t)tid | ((uint32_t)i << 7) | ((uint32_t)cur_a << 11) | ((uint32_t)n << 21);
             if (qm) {
                 const int lane = tid & 31;
@@ -265,14 +232,14 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
             const int64_t score = list_dp_run<kShift>(s_list + col + ua * ls, ls, n, a.bonus, c.pen_eff);
             a.score[(size_t)(w0 + i) * a.T + chunk * bd + col] = score;
         }
-        if (kGen) {
+        if (kTwoQueues) {
             const int n_back = g.n_work_back;
             for (int u = tid; u < n_back; u += bd) {
                 const uint32_t e = s_work[nwin * bd - 1 - u];
                 const int col = e & 127, i = (e >> 7) & 15, ua = (e >> 11) & 1023, n = e >> 21;
                 int64_t score;
-                if (small) {
-                    score = list_dp_run_small(s_list + col + ua * ls, ls, n, a.bonus, a.penalty, compat);
+                if (kSigned) {
+                    score = list_dp_run_signed(s_list + col + ua * ls, ls, n, a.bonus, a.penalty, compat);
                 } else if (!list_dp_run_general(s_list + col + ua * ls, ls, n, a.bonus, a.penalty, a.max_mm, score)) {
                     bail_window(w0 + i);
                     continue;
@@ -293,7 +260,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
         int64_t score = kNegInf64;
         if (hi > lo) {
             if (overflow) {
-                if (kGen) { bail_window(w); continue; }
+                if (kGen || (kSigned && col_neg)) { bail_window(w); continue; }
                 walk_dp_unit<int32_t>(LdgU32(), LdgPos{a.pos}, a.carried, a.two, a.Tp, t, lo, hi, a.bonus, a.penalty,
                                       a.max_mm, n, score);
             } else {
@@ -301,8 +268,8 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
                 list_window_range_shifted<kShift>(s_list + tid, ls, cur, b, gplo[i], gphi[i], false);
                 n = b - cur;
                 if (n > 2) {
-                    if (!kGen) score = list_dp_run(s_list + tid + cur * ls, ls, n, a.bonus, c.pen_eff);
-                    else if (small) score = list_dp_run_small(s_list + tid + cur * ls, ls, n, a.bonus, a.penalty, compat);
+                    if (kSigned && col_neg) score = list_dp_run_signed(s_list + tid + cur * ls, ls, n, a.bonus, a.penalty, compat);
+                    else if (!kGen) score = list_dp_run<kShift>(s_list + tid + cur * ls, ls, n, a.bonus, c.pen_eff);
                     else if (!list_dp_run_general(s_list + tid + cur * ls, ls, n, a.bonus, a.penalty, a.max_mm, score)) {
                         bail_window(w);
                         continue;
@@ -320,6 +287,8 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
 // cost the common kernel body registers or stack
 template <bool kNarrow>
 __device__ __noinline__ void group_body_general(const ScoreArgs &a, const GroupCtx &c) { group_body<1, kNarrow>(a, c); }
+template <bool kNarrow>
+__device__ __noinline__ void group_body_signed(const ScoreArgs &a, const GroupCtx &c) { group_body<2, kNarrow>(a, c); }
 
 // grid.x = tchunks * ngroups; dynamic smem: list [L + 1][bd] | max(positions [words_cap*32], worklist [wg*bd])
 // kNarrow (panels of at most 16 columns) lives in a kernel of its own: there the lists of a column
@@ -484,8 +453,10 @@ __device__ __forceinline__ void score_group_body(const ScoreArgs &a, int wg, int
             c.g = &g; c.s_list = s_list; c.s_pos = s_pos;
             c.tid = tid; c.bd = bd; c.chunk = chunk; c.t = t; c.w0 = w0 + s0; c.nwin = nsub; c.L = L; c.io = s0;
             c.rlo = rlo; c.rhi = rhi; c.gi0 = gi0; c.nwr = nwr; c.pen_eff = pen_eff; c.mono_hi = mono_hi;
-            c.small = ex_or < 2u;
-            if (any_ex && span < (int64_t(1) << kGeneralPosBits)) group_body_general<kNarrow>(a, c);
+            // other genotypes, all -1 / -2: signed entries from the planes; any other byte: general entries
+            // (only a sub-group spanning more than 2^23 bp sends such windows to the pairwise kernel)
+            if (ex_or == 1u) group_body_signed<kNarrow>(a, c);
+            else if (any_ex && span < (int64_t(1) << kGeneralPosBits)) group_body_general<kNarrow>(a, c);
             else group_body<0, kNarrow>(a, c);
         }
         s0 = s1;

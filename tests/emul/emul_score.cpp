@@ -63,7 +63,7 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
             if (b == -2) tw |= bit;
         }
     }
-    const uint32_t compat = small_compat_mask(max_mm);
+    const uint32_t compat = signed_compat_mask(max_mm);
     std::vector<int32_t> wlo(W), whi(W);
     for (int w = 0; w < W; ++w) {
         wlo[w] = lower_bound_i64(pos, V, ws[w]);
@@ -148,16 +148,18 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
                     window_absent(wlo[w0 + i], whi[w0 + i], na, ex);
                     any_ex = any_ex || ex;
                 }
-                const bool gen = any_ex && span < (int64_t(1) << kGeneralPosBits);
+                const bool gen_span = any_ex && span < (int64_t(1) << kGeneralPosBits);
                 uint32_t ex_or = 0;
                 for (int i = s0; i < s1; ++i) {
                     int32_t na; uint32_t ex;
                     window_absent(wlo[w0 + i], whi[w0 + i], na, ex);
                     ex_or |= ex;
                 }
-                const bool small = gen && ex_or < 2u;  // every other genotype of the sub-group is -1 / -2: entries from the planes
+                const bool sgn = ex_or == 1u;  // every other genotype of the sub-group is -1 / -2: signed entries from the planes
+                const bool gen = !sgn && gen_span;
                 for (int t = 0; t < T; ++t) {
                     int cnt = 0;
+                    bool col_neg = false;
                     for (int j = 0; j < nwr; ++j) {
                         uint32_t c = carried[(size_t)(gi0 + j) * Tp + t];
                         if (j == 0) c &= 0xffffffffu << (rlo & 31);
@@ -168,12 +170,13 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
                             c &= c - 1;
                             uint32_t e = (spos[(j << 5) + b] << 1) | ((tw >> b) & 1u);
                             if (gen) e = (spos[(j << 5) + b] << 8) | (uint32_t)(uint8_t)tgt[(size_t)(base + (j << 5) + b) * T + t];
-                            if (small) {  // the genotype byte from the three planes (the sign plane only where the group is flagged)
+                            if (sgn) {  // signed entries from the three planes (the sign plane only where the group is flagged)
                                 const uint32_t ngw = exotic[gi0 + j] ? neg[(size_t)(gi0 + j) * Tp + t] : 0u;
                                 const uint32_t t2 = (tw >> b) & 1u, sg = (ngw >> b) & 1u;
-                                const uint32_t byte = (((1u + t2) ^ (0u - sg)) + sg) & 0xffu;
-                                if (((spos[(j << 5) + b] << 8) | byte) != e) return -8;
-                                e = (spos[(j << 5) + b] << 8) | byte;
+                                const int gb = tgt[(size_t)(base + (j << 5) + b) * T + t];
+                                if (gb != (sg ? -(int)(1 + t2) : (int)(1 + t2))) return -8;  // the planes reproduce the byte
+                                e = (spos[(j << 5) + b] << 2) | (sg << 1) | t2;
+                                col_neg = col_neg || sg;
                             }
                             if (cnt < L) list[cnt] = e;
                             ++cnt;
@@ -188,7 +191,7 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
                         const int32_t lo = wlo[w], hi = whi[w];
                         int32_t na; uint32_t ex;
                         window_absent(lo, hi, na, ex);
-                        if (ex && !gen) { slow[w] = 1; continue; }
+                        if (ex && !gen && !sgn) { slow[w] = 1; continue; }
                         int n = 0; int64_t sc = kNegInf64;
                         if (hi > lo) {
                             const uint32_t plo = (uint32_t)(pos[lo] - p0), phi = (uint32_t)(pos[hi - 1] - p0);
@@ -204,8 +207,25 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
                                 if (balanced && (odd_a == odd_b) != general_run_is_plain(list.data() + cur, 1, n)) return -7;
                                 if (n > 2 && balanced && odd_a == odd_b)
                                     sc = list_dp_run<8>(list.data() + cur, 1, n, bonus, pen_eff);
-                                else if (n > 2 && small) sc = list_dp_run_small(list.data() + cur, 1, n, bonus, penalty, compat);
                                 else if (n > 2 && !list_dp_run_general(list.data() + cur, 1, n, bonus, penalty, max_mm, sc)) { slow[w] = 1; continue; }
+                            } else if (sgn) {
+                                // a column without a negative site runs the clean body on signed entries; the others
+                                // count the negative entries their cursors pass (balanced pass) or take the four-class DP
+                                if (overflow && col_neg) { slow[w] = 1; continue; }
+                                if (overflow) walk_dp_unit<int32_t>(HostLd(), HostPos{pos}, carried.data(), two.data(), Tp, t, lo, hi, bonus, penalty, max_mm, n, sc);
+                                else if (balanced) {
+                                    if (col_neg) list_window_range_signed(list.data(), 1, cur, cur_b, odd_a, odd_b, plo, phi);
+                                    else list_window_range_shifted<kSignedShift>(list.data(), 1, cur, cur_b, plo, phi, true);
+                                    n = cur_b - cur;
+                                    if (n > 2 && odd_a == odd_b) sc = list_dp_run<kSignedShift>(list.data() + cur, 1, n, bonus, pen_eff);
+                                    else if (n > 2) sc = list_dp_run_signed(list.data() + cur, 1, n, bonus, penalty, compat);
+                                } else {
+                                    cur_b = cur;
+                                    list_window_range_shifted<kSignedShift>(list.data(), 1, cur, cur_b, plo, phi, false);
+                                    n = cur_b - cur;
+                                    if (n > 2 && col_neg) sc = list_dp_run_signed(list.data() + cur, 1, n, bonus, penalty, compat);
+                                    else if (n > 2) sc = list_dp_run<kSignedShift>(list.data() + cur, 1, n, bonus, pen_eff);
+                                }
                             } else if (!overflow && balanced) {
                                 list_window_range(list.data(), 1, cur, cur_b, plo, phi, true);
                                 n = cur_b - cur;
@@ -215,7 +235,7 @@ extern "C" int emul_score_windows(const int8_t *ref, const int8_t *tgt, const in
                         }
                         score[(size_t)w * T + t] = sc;
                         nsnp[(size_t)w * T + t] = (hi - lo) - na + n;
-                        path[(size_t)w * T + t] = gen ? (small ? 6 : 5) : overflow ? 2 : 1;
+                        path[(size_t)w * T + t] = sgn ? 6 : gen ? 5 : overflow ? 2 : 1;
                     }
                 }
             }
@@ -256,25 +276,9 @@ extern "C" int emul_fused_windows(const int8_t *ref, const int8_t *tgt, const in
             const int b = tgt[k * T + t];
             if (b != 0) carried[(size_t)(k >> 5) * Tp + t] |= 1u << (k & 31);
             if (b == 2) two[(size_t)(k >> 5) * Tp + t] |= 1u << (k & 31);
-            // group level as the pack kernel raises it: 1 = other genotypes, all in {-2,-1} (the planes then
-            // hold |g| == 2 and the sign, for the whole group); 2 = anything else (the bytes are read)
-            if ((unsigned)b > 2u) exotic[k >> 5] |= (b == -1 || b == -2) ? 1u : 2u;
+            if ((unsigned)b > 2u) exotic[k >> 5] = 1;
         }
     }
-    std::vector<uint32_t> neg((size_t)(G > 0 ? G : 1) * Tp, 0xdeadbeefu);  // (unwritten where the group is clean)
-    for (int64_t k = 0; k < V; ++k) {
-        if (!exotic[k >> 5]) continue;
-        const uint32_t bit = 1u << (k & 31);
-        for (int t = 0; t < T; ++t) {
-            uint32_t &nw = neg[(size_t)(k >> 5) * Tp + t], &tw = two[(size_t)(k >> 5) * Tp + t];
-            if ((k & 31) == 0) nw = 0;
-            const int b = tgt[k * T + t];
-            if (!(absent[k >> 5] & bit)) continue;
-            if (b < 0) nw |= bit;
-            if (b == -2) tw |= bit;
-        }
-    }
-    const uint32_t compat = small_compat_mask(max_mm);
     std::vector<int64_t> A(kClassTableSize), B(kClassTableSize), wp(kRingSlots), wv(kRingSlots);
     std::vector<int32_t> wgt(kRingSlots);
     for (int w = 0; w < W; ++w) {
