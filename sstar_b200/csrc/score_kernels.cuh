@@ -35,6 +35,7 @@ struct GroupShared {
     uint32_t red_ex;
     int32_t n_work;
     int32_t n_work_back;  // general body: units holding other genotypes than 1 / 2, queued from the far end
+    uint32_t exm[2];      // signed body: bit j = word j of the sub-group's union range belongs to a flagged group
 };
 
 // words between consecutive entries of one column's list: the CTA's thread count, or less when the
@@ -79,11 +80,21 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
     const int tid = c.tid, bd = c.bd, chunk = c.chunk, t = c.t, w0 = c.w0, nwin = c.nwin, L = c.L;
     const int ls = kNarrow ? score_list_stride(a.T, bd) : bd;  // words between consecutive entries of a column's list
     constexpr int kShift = kGen ? 8 : (kSigned ? kSignedShift : 1);
-    constexpr int kBatch = kSigned ? 4 : 8;  // plane words fetched per round trip (the signed body holds three planes' words)
+    constexpr int kBatch = kSigned ? 4 : 8;  // plane words fetched per round trip (the signed body holds three planes' words: 8 would cost the kernel 80 registers)
 
     // this thread's column: plane words -> site list.  Shared memory is addressed with 32-bit
     // shared-window addresses (ld/st.shared) and the write cursor is clamped to a spill slot
     // (index L) instead of branching on overflow.
+    if (kSigned) {
+        // which words of the union range have a sign plane (flagged groups): a bit mask in shared memory, so
+        // that the sign words are fetched next to the other planes' instead of behind a flag load each
+        for (int j0 = tid & ~31; j0 < 64; j0 += bd) {
+            const int j = j0 + (tid & 31);
+            const uint32_t m = __ballot_sync(0xffffffffu, j < c.nwr && __ldg(a.exotic + c.gi0 + j) != 0u);
+            if ((tid & 31) == 0) g.exm[j0 >> 5] = m;
+        }
+        __syncthreads();
+    }
     int cnt = 0;
     bool col_neg = false;  // signed body: this column's list holds a negative genotype
     if (t < a.T) {
@@ -98,6 +109,7 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
         const uint32_t w_end = w_addr + (uint32_t)L * step;  // the spill slot
         const int nwr = c.nwr;
         uint32_t neg_any = 0;
+        const uint32_t exm0 = kSigned ? g.exm[0] : 0u, exm1 = kSigned ? g.exm[1] : 0u;
         for (int jb = 0; jb < nwr; jb += kBatch) {
             uint32_t cw[kBatch], tw[kBatch], ng[kSigned ? kBatch : 1];
 #pragma unroll
@@ -109,7 +121,8 @@ __device__ __forceinline__ void group_body(const ScoreArgs &a, const GroupCtx &c
                 tw[u] = (!kGen && jb + u < nwr) ? __ldg(tp + (size_t)(jb + u) * a.Tp) : 0u;  // not chained to cw
                 // the sign plane exists only where the group is flagged (clean groups never write it)
                 if (kSigned) {
-                    ng[u] = (jb + u < nwr && __ldg(a.exotic + c.gi0 + jb + u)) ? __ldg(np + (size_t)(jb + u) * a.Tp) : 0u;
+                    const uint32_t has = (((jb + u) & 32) ? exm1 : exm0) >> ((jb + u) & 31);  // (no bit beyond nwr)
+                    ng[u] = (has & 1u) ? __ldg(np + (size_t)(jb + u) * a.Tp) : 0u;
                     neg_any |= ng[u] & cw[u];
                 }
             }
