@@ -455,6 +455,8 @@ def test_host_threads_share_the_kernels_shared_memory_limits(eng):
     (50, 500, True, 400_000, [-2, -1, 3], 0.004),      # ... with multi-allelic dosages: groups of level 2 among level 1
     (8, 130, False, 500_000, [-2, -1, -3, 4], 0.01),   # T = 130 (two column chunks of the score grid), |g| > 2 both signs
     (8, 64, False, 500_000, [-128, 127, -2], 0.01),    # the int8 extremes
+    (50, 500, True, 400_000, [-1], 0.0003),            # sparse missing calls: a few odd blocks per warp step (the ballots)
+    (20, 150, False, 500_000, [-2, -1, 5, -7], 0.0004),  # ... with |g| > 2 among them, T = 150 (ragged last quad: 150 % 4 = 2)
 ])
 def test_missing_calls_through_the_launch_pipeline(eng, n_ref, n_tgt, phased, length, values, rate):
     """Missing calls (-1 / -2) and other int8 genotypes through pack -> score launches (no one-launch kernel):
