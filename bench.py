@@ -198,7 +198,7 @@ class ClockSampler(threading.Thread):
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, index, period=0.01):
+    def __init__(self, index, period=float(os.environ.get("SSTAR_BENCH_CLOCK_PERIOD", "0.01"))):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.marks = [], []
@@ -999,12 +999,16 @@ def run_ours(args, world, rank, local):
             table.score[:] = 0
             table.nsnp[:] = -1
         barrier()
-        e2e_s = case.wall_e2e_stream(k, barrier)
+        # three repetitions of the K-call region, the median reported and all three listed (wall-clock regions that
+        # the host drives see the host's hiccups: on the pool's VMs single repetitions scatter by tens of percent)
+        e2e_reps = sorted(case.wall_e2e_stream(k, barrier) for _ in range(3))
+        e2e_s = e2e_reps[1]
         barrier()
         if not case.e2e_slots_equal():
             raise SystemExit("bench: a slot of the e2e stream differs from the shared host table's block")
     else:
         e2e_s = e2e_single_s
+        e2e_reps = [e2e_single_s]
     sampler.mark()
     sampler.stop_flag.set()
     sampler.join(timeout=2)
@@ -1050,12 +1054,32 @@ def run_ours(args, world, rank, local):
         if not big.device_equals_host_block():
             raise SystemExit("bench: at_scale device-resident tables differ from the host tables")
         bsel = np.unique(np.linspace(0, bst["W"] - 1, 48).astype(int))
+        # the same shape with missing calls (-1) sprinkled over the target panel: the signed body of the score
+        # kernel and the warp-cooperative redo of the pack kernel; device-resident pass, oracle-checked
+        missing = {}
+        for rate in (5e-5, 5e-3):
+            g = torch.Generator(device=dev)
+            g.manual_seed(7)
+            tgt_m = big.d["tgt"].clone()
+            tgt_m[torch.rand(tgt_m.shape, device=dev, generator=g) < rate] = -1
+            run = lambda: eng.score_device(big.d["ref"], tgt_m, big.d["pos"], big.d["ws"], big.d["we"], *PARAMS,
+                                           max_win_variants=big.hint, flags=flags)
+            for _ in range(3):
+                out_m = run()
+            t_m = big.timed(run, 10, flush, barrier) / 10
+            mwk = dict(bwk, tgt=tgt_m.cpu().numpy())
+            msel = bsel[::3]
+            n_m = oracle_check(mwk, out_m[0].cpu().numpy(), out_m[1].cpu().numpy(), msel, "at_scale, missing calls")
+            missing[f"{rate:g}"] = {"ms_per_step": t_m, "vs_clean": t_m / (b_tot / kb), "checked_units": n_m, "bit_exact_vs_oracle": True}
+            del tgt_m, out_m, mwk
         at_scale = {"workload": bwk["desc"], **{x: bst[x] for x in ("V", "R", "T", "W", "units")},
                     "value": bst["units"] / (b_tot / kb * 1e-3), "unit": UNIT, "ms_per_step": b_tot / kb,
                     "e2e": {"value": bst["units"] / (b_e2e / 5), "unit": UNIT, "ms_per_step": 1e3 * b_e2e / 5},
                     "roofline": roofline_block(bwk["name"], bst, kb, b_tot, b_pack, b_score, nl),
                     "parity": {"checked_units": oracle_check(bwk, big.score_p.numpy(), big.nsnp_p.numpy(), bsel, "at_scale"),
-                               "bit_exact_vs_oracle": True}}
+                               "bit_exact_vs_oracle": True},
+                    "missing_calls": {"what": "share of the target calls set to -1 -> device-resident pass (un-graphed call, L2 flushed)",
+                                      **missing}}
         del big, bwk
 
     strong = {}
@@ -1090,12 +1114,14 @@ def run_ours(args, world, rank, local):
                     "h2d_bytes_per_step": int(sum(p["hbm_bytes"] + 4 * (p["rows"][1] - p["rows"][0]) +
                                                   8 * (p["windows"][1] - p["windows"][0]) for p in per_rank)),
                     "d2h_bytes_per_step": int(12 * W * T), "ms_per_step": e2e_ms / k,
+                    "repeats_ms_per_step": [1e3 * x / k for x in e2e_reps],
                     "api": ("per rank K calls of ScoreEngine.score_pinned -> sstar_b200_score_windows_host with "
                             "SSTAR_B200_FLAG_INDEPENDENT, back to back over a ring of 4 page-locked copies of its rows (own "
                             "device scratch and result tables each; slot 0 stores into the shared host table): every "
                             "call's rows go H2D through the copy engine under the previous call's scoring, its tables are "
                             "stored in place in pinned host memory; wall clock from the first call to ONE stream "
-                            "synchronize after the last; the gather is part of it" if use_stream else
+                            "synchronize after the last; the gather is part of it; the K-call region is run three times, "
+                            "the median is reported (this rank's three: repeats_ms_per_step)" if use_stream else
                             "per rank ScoreEngine.score_pinned -> sstar_b200_score_windows_host on its own pinned rows: "
                             + ("matrices below 32 MB are packed in place over PCIe (the pack CTAs' tile loads are the "
                                "H2D transfer), " if (k1 - k0) * (R + T) < (32 << 20) else
