@@ -513,9 +513,11 @@ def cut_windows(shards, W, radius=6):
     return sorted(sel)
 
 
-def roofline_block(name, st, k, tot_ms, pack_ms, score_ms, launches, stream=None):
-    """Pass-level and per-kernel HBM roofline (SURVEY.md section 8d bytes; measured peak)."""
-    ab = algorithmic_bytes(st)
+def roofline_block(name, st, k, tot_ms, pack_ms, score_ms, launches, stream=None, world=1):
+    """Pass-level and per-kernel HBM roofline (SURVEY.md section 8d bytes; measured peak).  PER GPU: a launch
+    processes one rank's share of the job, so the whole job's algorithmic bytes are divided by the ranks (the
+    halo rows a shard re-reads are not counted) and set against ONE GPU's measured peak."""
+    ab = {key: v / world for key, v in algorithmic_bytes(st).items()}
     peak, peak_src = measured_peak()
 
     def kern(kname, ms, nbytes, note=None):
@@ -533,7 +535,7 @@ def roofline_block(name, st, k, tot_ms, pack_ms, score_ms, launches, stream=None
             # integer operations of the REFERENCE formulation -- 8 per pair
             # evaluation of the O(n^2) recurrence plus one mask test per window variant and unit --
             # over the time this kernel takes (the prefix-max DP executes fewer; see "issue").
-            ops = 8 * st["sum_pairs"] + st["units"] * st["mean_window_variants"]
+            ops = (8 * st["sum_pairs"] + st["units"] * st["mean_window_variants"]) / world
             ipeak, sms, mhz = issue_peak_ginst()
             apeak = sms * 128 * mhz * 1e6 / 1e12
             out["alu_reference_formulation"] = {
@@ -561,8 +563,8 @@ def roofline_block(name, st, k, tot_ms, pack_ms, score_ms, launches, stream=None
                     sum(filter(None, (recorded_traffic(name, x) for x in ("prep_kernel", "score_group_kernel")))) or None),
         "traffic_source": "profiles/traffic.json (per-launch dram bytes of one ncu --set full capture; null when the "
                           "workload has no capture)",
-        "peak_source": peak_src, "algorithmic_bytes": ab["pipeline"],
-        "bytes_per_unit": ab["pipeline"] / st["units"], "pass_ms": tot_ms / k, "launches_per_pass": launches,
+        "peak_source": peak_src, "algorithmic_bytes": ab["pipeline"], "per_gpu": True, "n_gpus": world,
+        "bytes_per_unit": ab["pipeline"] * world / st["units"], "pass_ms": tot_ms / k, "launches_per_pass": launches,
         "kernels_note": ("the pass is the fused kernel (its roofline is the pass-level one above); the two kernels below "
                          "are the launch pipeline's, which larger inputs take, timed alone on this input") if fused else None,
         "kernels": [
@@ -1143,7 +1145,7 @@ def run_ours(args, world, rank, local):
                                     "empty kernel after a flush (about 6 us) included"},
             "roofline": roofline_block(wk["name"], st, k, tot_ms, pack_ms, score_ms, int(launches_per_step),
                                        stream={"launches": int(stream_launches), "ring": case_ring[0],
-                                               "ring_bytes": case_ring[1]} if use_stream else None),
+                                               "ring_bytes": case_ring[1]} if use_stream else None, world=world),
             "cpu_baseline": cpu,
             "clocks": sampler.summary(),
             "parity": parity,
