@@ -533,7 +533,7 @@ __device__ __forceinline__ void pack_tile_direct(const PackArgs &a, uint8_t *sme
 // mode: 0 = staged word path (whole rows), 1 = direct byte path, 2 = staged word path, one column chunk
 // of the target rows per tile (wide panels)
 // (kWide compiles the column-chunk mode in: it lives in a kernel of its own so that the common
-// kernel keeps its 48 registers and five resident CTAs per SM)
+// kernel keeps its registers)
 template <bool kWide, bool kLaneRows = false>
 __device__ __forceinline__ void prep_body(const PackArgs &p, const BoundsArgs &b, int n_pack, int mode, uint8_t *smem,
                                           uint64_t *s_bar) {

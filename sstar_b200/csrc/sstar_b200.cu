@@ -271,7 +271,7 @@ int launch_prep(cudaStream_t st, int64_t g_begin, int64_t g_end, const int8_t *d
     }
     if (n_pack + n_bounds == 0) return 0;
     const int n_fetch = b.n_fetch;
-    // three instances of one body: whole-row tiles (the common one: 48 registers), column chunks
+    // three instances of one body: whole-row tiles (the common one), column chunks
     // for wide panels, and whole-row tiles with one lane per reference row for panels of <= 16
     // reference columns (replicate batches)
     static SmemGrant prep_grant, wide_grant, narrow_grant;
