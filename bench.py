@@ -494,6 +494,22 @@ class ShardCase:
                     self.torch.equal(self.nsnp_d.cpu(), self.nsnp_p))
 
 
+_HOST_JUNK = {}
+
+
+def host_cache_flush(torch, nbytes=1 << 30):
+    """Put the page-locked host buffers where a pipeline's inputs are -- in DRAM, not in the CPU's caches.
+    The bench itself has just WRITTEN them (clones of the rows, table resets), and on this pool's hosts DMA
+    reads of lines that sit modified in the CPU's caches run at 13-40 GB/s instead of 50, for as long as
+    nothing evicts them (``tools/exp_pinned_slots.py``: 16 slices of one page-locked slab read at 49.8 ...
+    13.6 GB/s in the order they were written, all at 49 GB/s once the CPU has written 1 GiB elsewhere).  The
+    host-side twin of the L2 flush: outside every timed region, before the e2e ones."""
+    if "buf" not in _HOST_JUNK:
+        _HOST_JUNK["buf"], _HOST_JUNK["n"] = torch.empty(nbytes, dtype=torch.uint8), 0
+    _HOST_JUNK["n"] += 1
+    _HOST_JUNK["buf"].fill_(_HOST_JUNK["n"] & 1)
+
+
 def oracle_check(wk, score, nsnp, sel, what):
     """Rows ``sel`` of the gathered host table vs the scalar C oracle, bit-exact, or refuse to report."""
     from oracle import c_oracle
@@ -698,6 +714,7 @@ def strong_c3(torch, eng, dev, rk, flush, length, steps, e2e_steps, use_graph, f
     if rk.rank == 0:
         table.score[:] = 0  # the timed calls below must refill the whole table
         table.nsnp[:] = -1
+    host_cache_flush(torch)
     rk.barrier()
     e2e_s = case.wall(case.step_e2e, e2e_steps, flush)
     rk.barrier()
@@ -849,6 +866,7 @@ def strong_c5(torch, eng, dev, rk, flush, steps, e2e_steps):
     if rk.rank == 0:
         table.score[:] = 0
         table.nsnp[:] = -1
+    host_cache_flush(torch)
     rk.barrier()
     e2e_s = 0.0
     for i in range(e2e_steps):
@@ -982,11 +1000,13 @@ def run_ours(args, world, rank, local):
     score_ms = case.timed(case.step_score, k, flush, barrier)
     # ---- region B: end to end from pinned host buffers, wall clock per step (includes the sync)
     barrier()
+    host_cache_flush(torch)
     staged_s = case.wall(lambda: case.step_e2e(staged=True), k, flush)  # plain H2D / D2H copies, for comparison
     barrier()
     if rank == 0:
         table.score[:] = 0  # the timed calls below must refill every rank's block
         table.nsnp[:] = -1
+    host_cache_flush(torch)  # the rows and the table out of the CPU's caches (see host_cache_flush)
     barrier()
     sampler.mark()
     e2e_single_k = k if not use_stream else min(k, 200)
@@ -1000,6 +1020,7 @@ def run_ours(args, world, rank, local):
         if rank == 0:
             table.score[:] = 0
             table.nsnp[:] = -1
+        host_cache_flush(torch)  # the slots were written (cloned) a moment ago
         barrier()
         # three repetitions of the K-call region, the median reported and all three listed (wall-clock regions that
         # the host drives see the host's hiccups: on the pool's VMs single repetitions scatter by tens of percent)
@@ -1052,6 +1073,7 @@ def run_ours(args, world, rank, local):
         b_tot = big.timed(big.step_device, kb, flush, barrier)
         b_pack = big.timed(big.step_pack, kb, flush, barrier)
         b_score = big.timed(big.step_score, kb, flush, barrier)
+        host_cache_flush(torch)
         b_e2e = big.wall(big.step_e2e, 5, flush)
         if not big.device_equals_host_block():
             raise SystemExit("bench: at_scale device-resident tables differ from the host tables")
@@ -1116,6 +1138,9 @@ def run_ours(args, world, rank, local):
                     "h2d_bytes_per_step": int(sum(p["hbm_bytes"] + 4 * (p["rows"][1] - p["rows"][0]) +
                                                   8 * (p["windows"][1] - p["windows"][0]) for p in per_rank)),
                     "d2h_bytes_per_step": int(12 * W * T), "ms_per_step": e2e_ms / k,
+                    "host_caches": "the CPU writes 1 GiB elsewhere before every e2e region (outside it): the page-locked rows "
+                                   "are then read from DRAM, not from lines the bench's own set-up left modified in the "
+                                   "CPU's caches (13-40 instead of 50 GB/s on this pool's hosts, tools/exp_pinned_slots.py)",
                     "repeats_ms_per_step": [1e3 * x / k for x in e2e_reps],
                     "api": ("per rank K calls of ScoreEngine.score_pinned -> sstar_b200_score_windows_host with "
                             "SSTAR_B200_FLAG_INDEPENDENT, back to back over a ring of 4 page-locked copies of its rows (own "
