@@ -15,6 +15,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -28,10 +30,36 @@
 
 namespace {
 
+// A byte buffer that grows WITHOUT being zero-filled (std::vector::resize touches every new byte on the scanning
+// thread; here the pages are first touched by the parser threads that write them, or by the read that fills them).
+struct RawBuf {
+    char *p = nullptr;
+    size_t cap = 0;
+    RawBuf() = default;
+    RawBuf(const RawBuf &) = delete;
+    RawBuf &operator=(const RawBuf &) = delete;
+    RawBuf(RawBuf &&o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+    RawBuf &operator=(RawBuf &&o) noexcept {
+        if (this != &o) { free(p); p = o.p; cap = o.cap; o.p = nullptr; o.cap = 0; }
+        return *this;
+    }
+    ~RawBuf() { free(p); }
+    bool ensure(size_t n) {  // capacity >= n, contents kept; geometric growth
+        if (n <= cap) return true;
+        size_t nc = cap ? cap : n;
+        while (nc < n) nc *= 2;
+        char *q = (char *)realloc(p, nc);
+        if (!q) return false;
+        p = q;
+        cap = nc;
+        return true;
+    }
+};
+
 struct ChromData {
     std::string name;
     std::vector<int32_t> pos;
-    std::vector<int8_t> gt;  // [V, N, 2]
+    RawBuf gt;  // int8 [V, N, 2]
     std::vector<int32_t> ref_off, alt_off;  // [V + 1]
     std::vector<char> ref_bytes, alt_bytes;
 };
@@ -76,17 +104,20 @@ struct LineFields {
     int32_t ref_len, alt_len;
 };
 
+// one allele character of the common call shape: a digit or '.'
+inline bool allele_char(char c) { return (unsigned)(c - '0') < 10u || c == '.'; }
+inline int8_t allele_value(char c) { return c == '.' ? (int8_t)-1 : (int8_t)(c - '0'); }
+
 // sel[c] = output slot of header column c, or -1 (column not wanted); n_cols = header columns,
 // n_samples = output slots, last_col = the last wanted column (the rest of the line is not scanned)
 void parse_line(const char *p, const char *e, const int32_t *sel, int n_cols, int last_col, int n_samples,
                 int32_t *pos_out, int8_t *gt_out, LineFields *lf) {
     if (e > p && e[-1] == '\r') --e;
-    int field = 0;
-    int sample = 0;
-    memset(gt_out, 0xff, (size_t)n_samples * 2);  // -1 everywhere
+    if (n_samples > 0) memset(gt_out, 0xff, (size_t)n_samples * 2);  // -1 everywhere
     *pos_out = 0;
     lf->ref = lf->alt = p; lf->ref_len = lf->alt_len = 0;
-    while (p <= e) {
+    // the nine fixed fields: CHROM POS ID REF ALT QUAL FILTER INFO FORMAT
+    for (int field = 0; field < 9; ++field) {
         const char *t = find_byte(p, e, '\t');
         if (field == 1) {
             long v = 0; bool neg = false; const char *q = p;
@@ -98,13 +129,28 @@ void parse_line(const char *p, const char *e, const int32_t *sel, int n_cols, in
         } else if (field == 4) {
             const char *c = find_byte(p, t, ',');
             lf->alt = p; lf->alt_len = (int32_t)(c - p);
-        } else if (field >= 9) {
-            if (sample < n_cols && sel[sample] >= 0) parse_gt(p, t, gt_out + (size_t)sel[sample] * 2);
-            if (sample >= last_col) break;
-            ++sample;
         }
-        ++field;
-        if (t >= e) break;
+        if (t >= e) return;  // a line without sample fields
+        p = t + 1;
+    }
+    // the sample fields.  Nearly all of them are "a|b" / "a/b" with one character per allele and nothing
+    // behind: those are decoded in place (no search for the field's end); anything else -- haploid calls,
+    // multi-digit alleles, FORMAT fields behind the GT -- takes the general parser.
+    for (int sample = 0;; ++sample) {
+        const int32_t slot = sample < n_cols ? sel[sample] : -1;
+        const char *t;
+        if (e - p >= 3 && (p[1] == '|' || p[1] == '/') && (p + 3 == e || p[3] == '\t') && allele_char(p[0]) &&
+            allele_char(p[2])) {
+            if (slot >= 0) {
+                gt_out[(size_t)slot * 2] = allele_value(p[0]);
+                gt_out[(size_t)slot * 2 + 1] = allele_value(p[2]);
+            }
+            t = p + 3;
+        } else {
+            t = find_byte(p, e, '\t');
+            if (slot >= 0) parse_gt(p, t, gt_out + (size_t)slot * 2);
+        }
+        if (sample >= last_col || t >= e) break;
         p = t + 1;
     }
 }
@@ -117,9 +163,18 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
                                       int32_t n_samples, int nthreads, sstar_b200_vcf **out) {
     if (!path || !out || (n_samples > 0 && !samples)) { g_vcf_err = "null argument"; return SSTAR_B200_EINVAL; }
     *out = nullptr;
-    gzFile gz = gzopen(path, "rb");
-    if (!gz) { g_vcf_err = std::string("cannot open ") + path; return SSTAR_B200_EINVAL; }
-    gzbuffer(gz, 1 << 20);
+    // plain text is read straight into the block (read(2)); only a gzip stream goes through zlib
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) { g_vcf_err = std::string("cannot open ") + path; return SSTAR_B200_EINVAL; }
+    unsigned char magic[2] = {0, 0};
+    const ssize_t nm = pread(fd, magic, 2, 0);
+    gzFile gz = nullptr;
+    if (nm == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+        gz = gzdopen(fd, "rb");  // (owns fd from here on)
+        if (!gz) { close(fd); g_vcf_err = std::string("cannot open ") + path; return SSTAR_B200_EINVAL; }
+        gzbuffer(gz, 1 << 20);
+    }
+    auto close_input = [&]() { if (gz) gzclose(gz); else close(fd); };
     int nt = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();
     if (nt < 1) nt = 1;
     if (nt > 64) nt = 64;
@@ -143,26 +198,29 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
         const long long v = atoll(env);
         if (v >= 64) block = (size_t)v;
     }
-    std::vector<char> buf(block);
+    RawBuf buf;
+    if (!buf.ensure(block)) { close_input(); delete h; g_vcf_err = "out of memory"; return SSTAR_B200_EINVAL; }
     size_t len = 0;  // bytes in buf
+    std::string last_name;  // chromosome of the previous kept line (lines of one chromosome come in runs)
+    int last_id = -1;
     bool eof = false;
     int rc = 0;
     while (!eof || len > 0) {
-        while (!eof && len < buf.size()) {  // top the block up
-            const size_t wantb = std::min(buf.size() - len, (size_t)1 << 30);
-            const int got = gzread(gz, buf.data() + len, (unsigned)wantb);
+        while (!eof && len < buf.cap) {  // top the block up
+            const size_t wantb = std::min(buf.cap - len, (size_t)1 << 30);
+            const long got = gz ? (long)gzread(gz, buf.p + len, (unsigned)wantb) : (long)read(fd, buf.p + len, wantb);
             if (got < 0) { g_vcf_err = std::string("read error in ") + path; rc = SSTAR_B200_EINVAL; break; }
             if (got == 0) eof = true;
             len += (size_t)got;
         }
         if (rc) break;
-        const char *b = buf.data(), *end = b + len;
+        const char *b = buf.p, *end = b + len;
         // the block's complete lines end at the last newline (at EOF the unterminated tail is a line too)
         const char *stop = end;
         if (!eof) {
             while (stop > b && stop[-1] != '\n') --stop;
             if (stop == b) {  // one line longer than the block: grow and read on
-                buf.resize(buf.size() * 2);
+                if (!buf.ensure(buf.cap * 2)) { g_vcf_err = "out of memory"; rc = SSTAR_B200_EINVAL; break; }
                 continue;
             }
         }
@@ -199,17 +257,23 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
                 } else if (have_header) {
                     const char *t = find_byte(p, nl, '\t');
                     if (!chr_name || ((size_t)(t - p) == want.size() && memcmp(p, want.data(), want.size()) == 0)) {
-                        std::string name(p, (size_t)(t - p));
-                        auto it = chrom_id.find(name);
                         int id;
-                        if (it == chrom_id.end()) {
-                            id = (int)h->chroms.size();
-                            chrom_id.emplace(name, id);
-                            h->chroms.emplace_back();
-                            h->chroms.back().name = name;
-                            h->chroms.back().ref_off.push_back(0);
-                            h->chroms.back().alt_off.push_back(0);
-                        } else id = it->second;
+                        if (last_id >= 0 && (size_t)(t - p) == last_name.size() && memcmp(p, last_name.data(), last_name.size()) == 0) {
+                            id = last_id;
+                        } else {
+                            std::string name(p, (size_t)(t - p));
+                            auto it = chrom_id.find(name);
+                            if (it == chrom_id.end()) {
+                                id = (int)h->chroms.size();
+                                chrom_id.emplace(name, id);
+                                h->chroms.emplace_back();
+                                h->chroms.back().name = name;
+                                h->chroms.back().ref_off.push_back(0);
+                                h->chroms.back().alt_off.push_back(0);
+                            } else id = it->second;
+                            last_name = std::move(name);
+                            last_id = id;
+                        }
                         ChromData &c = h->chroms[id];
                         lines.push_back({(size_t)(p - b), (size_t)(nl - b), id, c.pos.size()});
                         c.pos.push_back(0);
@@ -224,14 +288,16 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
         }
         if (rc) break;
         // parse the block's kept lines in parallel, straight into the chromosomes' arrays
-        for (auto &c : h->chroms) c.gt.resize(c.pos.size() * (size_t)N * 2);
+        for (auto &c : h->chroms)
+            if (!c.gt.ensure(c.pos.size() * (size_t)N * 2)) { g_vcf_err = "out of memory"; rc = SSTAR_B200_EINVAL; }
+        if (rc) break;
         lf.resize(lines.size());
         const size_t L = lines.size();
         auto work = [&](size_t a, size_t z) {
             for (size_t i = a; i < z; ++i) {
                 ChromData &c = h->chroms[lines[i].chrom];
                 parse_line(b + lines[i].begin, b + lines[i].end, sel.data(), n_cols, last_col, N, &c.pos[lines[i].row],
-                           c.gt.data() + lines[i].row * (size_t)N * 2, &lf[i]);
+                           reinterpret_cast<int8_t *>(c.gt.p) + lines[i].row * (size_t)N * 2, &lf[i]);
             }
         };
         const int use = (int)std::min<size_t>((size_t)nt, std::max<size_t>(1, L / 256));
@@ -249,11 +315,11 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
             c.alt_off.push_back((int32_t)c.alt_bytes.size());
         }
         const size_t used = (size_t)(stop - b);
-        memmove(buf.data(), buf.data() + used, len - used);
+        memmove(buf.p, buf.p + used, len - used);
         len -= used;
         if (eof) len = 0;
     }
-    gzclose(gz);
+    close_input();
     if (!rc && !have_header) {
         g_vcf_err = std::string(path) + " has no #CHROM header line.";
         rc = SSTAR_B200_EINVAL;
@@ -284,7 +350,9 @@ extern "C" int64_t sstar_b200_vcf_n_variants(const sstar_b200_vcf *h, int32_t c)
     return (c >= 0 && (size_t)c < h->chroms.size()) ? (int64_t)h->chroms[c].pos.size() : -1;
 }
 extern "C" const int32_t *sstar_b200_vcf_pos(const sstar_b200_vcf *h, int32_t c) { return h->chroms[c].pos.data(); }
-extern "C" const int8_t *sstar_b200_vcf_gt(const sstar_b200_vcf *h, int32_t c) { return h->chroms[c].gt.data(); }
+extern "C" const int8_t *sstar_b200_vcf_gt(const sstar_b200_vcf *h, int32_t c) {
+    return reinterpret_cast<const int8_t *>(h->chroms[c].gt.p);
+}
 extern "C" const char *sstar_b200_vcf_alleles(const sstar_b200_vcf *h, int32_t c, int32_t which, const int32_t **off) {
     const ChromData &d = h->chroms[c];
     *off = which ? d.alt_off.data() : d.ref_off.data();
