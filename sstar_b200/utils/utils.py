@@ -51,31 +51,45 @@ def _scan_vcf(path: str, chr_name: str | None, need_alleles: bool = True, sample
                                     n_names, 0, ctypes.byref(handle))
     if rc != 0:
         raise ValueError(lib.sstar_b200_vcf_last_error().decode("utf-8", "replace"))
-    try:
-        n = lib.sstar_b200_vcf_n_samples(handle)
-        header = [lib.sstar_b200_vcf_sample(handle, i).decode() for i in range(n)]
-        out = {}
-        for c in range(lib.sstar_b200_vcf_n_chroms(handle)):
-            name = lib.sstar_b200_vcf_chrom(handle, c).decode()
-            v = lib.sstar_b200_vcf_n_variants(handle, c)
-            pos = np.ctypeslib.as_array(ctypes.cast(lib.sstar_b200_vcf_pos(handle, c),
-                                                    ctypes.POINTER(ctypes.c_int32)), shape=(v,)).copy() \
-                if v else np.zeros(0, dtype=np.int32)
-            gt = np.ctypeslib.as_array(ctypes.cast(lib.sstar_b200_vcf_gt(handle, c),
-                                                   ctypes.POINTER(ctypes.c_int8)), shape=(v, n, 2)).copy() \
-                if v and n else np.zeros((v, n, 2), dtype=np.int8)
-            rec = {"POS": pos, "REF": None, "ALT": None, "GT": gt}
-            if need_alleles:
-                for key, which in (("REF", 0), ("ALT", 1)):
-                    off_p = ctypes.c_void_p()
-                    base = lib.sstar_b200_vcf_alleles(handle, c, which, ctypes.byref(off_p))
-                    off = np.ctypeslib.as_array(ctypes.cast(off_p, ctypes.POINTER(ctypes.c_int32)), shape=(v + 1,))
-                    raw = ctypes.string_at(base, int(off[v])) if v else b""
-                    rec[key] = np.asarray([raw[off[i]:off[i + 1]].decode() for i in range(v)], dtype=object)
-            out[name] = rec
-    finally:
-        lib.sstar_b200_vcf_free(handle)
+    owner = _ScanOwner(lib, handle)  # POS / GT below are VIEWS of the scanner's arrays; it is freed with the last of them
+
+    def view(addr, ctype, count, dtype):
+        raw = (ctype * count).from_address(addr)
+        raw._owner = owner
+        return np.frombuffer(raw, dtype=dtype)
+
+    n = lib.sstar_b200_vcf_n_samples(handle)
+    header = [lib.sstar_b200_vcf_sample(handle, i).decode() for i in range(n)]
+    out = {}
+    for c in range(lib.sstar_b200_vcf_n_chroms(handle)):
+        name = lib.sstar_b200_vcf_chrom(handle, c).decode()
+        v = lib.sstar_b200_vcf_n_variants(handle, c)
+        pos = view(lib.sstar_b200_vcf_pos(handle, c), ctypes.c_int32, v, np.int32) if v else np.zeros(0, dtype=np.int32)
+        gt = view(lib.sstar_b200_vcf_gt(handle, c), ctypes.c_int8, v * n * 2, np.int8).reshape(v, n, 2) \
+            if v and n else np.zeros((v, n, 2), dtype=np.int8)
+        rec = {"POS": pos, "REF": None, "ALT": None, "GT": gt}
+        if need_alleles:
+            for key, which in (("REF", 0), ("ALT", 1)):
+                off_p = ctypes.c_void_p()
+                base = lib.sstar_b200_vcf_alleles(handle, c, which, ctypes.byref(off_p))
+                off = np.ctypeslib.as_array(ctypes.cast(off_p, ctypes.POINTER(ctypes.c_int32)), shape=(v + 1,))
+                raw = ctypes.string_at(base, int(off[v])) if v else b""
+                rec[key] = np.asarray([raw[off[i]:off[i + 1]].decode() for i in range(v)], dtype=object)
+        out[name] = rec
     return header, out
+
+
+class _ScanOwner:
+    """Keeps a native scan alive while numpy views of its arrays exist (no copy of the calls)."""
+
+    def __init__(self, lib, handle):
+        self._lib, self._handle = lib, handle
+
+    def __del__(self):
+        try:
+            self._lib.sstar_b200_vcf_free(self._handle)
+        except Exception:
+            pass
 
 
 def filter_data(data: dict, c: str, index: np.ndarray) -> dict:
