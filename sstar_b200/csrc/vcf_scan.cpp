@@ -20,6 +20,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -155,6 +156,133 @@ void parse_line(const char *p, const char *e, const int32_t *sel, int n_cols, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// BGZF (bgzip, what tabix-indexed VCFs are stored in): a gzip file made of independent members of at most
+// 64 KB of text, each carrying its compressed size in a 'BC' extra field (SAM specification, section 4.1).
+// The members of a batch are located by walking those sizes and inflated in PARALLEL, each into its place of
+// the batch's text (its length is the member's ISIZE trailer); CRC32 and length of every member are checked.
+// A plain gzip stream (one member, no sizes) cannot be split and goes through zlib's gzread on one thread.
+// ---------------------------------------------------------------------------------------------
+inline uint32_t le16(const unsigned char *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+inline uint32_t le32(const unsigned char *p) { return le16(p) | (le16(p + 2) << 16); }
+
+// total size of the BGZF member starting at p (n bytes available), 0 = not enough bytes to tell, -1 = not BGZF
+long bgzf_member_size(const unsigned char *p, size_t n) {
+    if (n < 12) return 0;
+    if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return -1;
+    const size_t xlen = le16(p + 10);
+    if (n < 12 + xlen) return 0;
+    for (size_t o = 12; o + 4 <= 12 + xlen;) {
+        const size_t slen = le16(p + o + 2);
+        if (p[o] == 'B' && p[o + 1] == 'C' && slen == 2 && o + 6 <= 12 + xlen) return (long)le16(p + o + 4) + 1;
+        o += 4 + slen;
+    }
+    return -1;
+}
+
+struct BgzfReader {
+    int fd = -1, nt = 1;
+    RawBuf cbuf, obuf;          // compressed bytes read ahead; carry buffer (a member that did not fit the caller's space)
+    size_t clen = 0, cpos = 0;  // bytes in cbuf, first unconsumed one
+    size_t olen = 0, opos = 0;
+    bool ceof = false, at_end = false;
+    std::string err;
+    struct Member { const unsigned char *src; uint32_t csize, isize; size_t off; };
+    std::vector<Member> batch;
+
+    // The next batch of members, inflated into `dst` (at most `cap` bytes of text; members are never split) ->
+    // bytes written; 0 = the file has ended, or the next member does not fit `cap`; -1 = error (err set).
+    long inflate_batch(char *dst, size_t cap) {
+        const size_t ccap = (size_t)4 << 20;  // compressed bytes read ahead (a batch: 64+ members)
+        if (!cbuf.ensure(ccap)) { err = "out of memory"; return -1; }
+        for (;;) {
+            if (cpos > 0) { memmove(cbuf.p, cbuf.p + cpos, clen - cpos); clen -= cpos; cpos = 0; }
+            while (!ceof && clen < cbuf.cap) {
+                const ssize_t got = read(fd, cbuf.p + clen, cbuf.cap - clen);
+                if (got < 0) { err = "read error"; return -1; }
+                if (got == 0) ceof = true;
+                clen += (size_t)got;
+            }
+            if (clen == 0) { at_end = true; return 0; }  // end of the file
+            batch.clear();
+            size_t total = 0;
+            bool full = false;
+            const unsigned char *base = reinterpret_cast<const unsigned char *>(cbuf.p);
+            while (cpos < clen) {
+                const long sz = bgzf_member_size(base + cpos, clen - cpos);
+                if (sz < 0) { err = "not a BGZF member (mixed gzip / BGZF stream?)"; return -1; }
+                if (sz == 0 || cpos + (size_t)sz > clen) {
+                    if (ceof) { err = "truncated BGZF member"; return -1; }
+                    break;  // the member continues in the bytes not read yet
+                }
+                const size_t xlen = le16(base + cpos + 10);
+                if ((size_t)sz < 12 + xlen + 8) { err = "malformed BGZF member"; return -1; }
+                const uint32_t isize = le32(base + cpos + sz - 4);
+                if (isize > (1u << 16)) { err = "malformed BGZF member (more than 64 KB of text)"; return -1; }
+                if (total + isize > cap) { full = true; break; }
+                batch.push_back({base + cpos, (uint32_t)sz, isize, total});
+                total += isize;
+                cpos += (size_t)sz;
+            }
+            if (batch.empty()) {
+                if (full) return 0;  // the caller's space is smaller than the next member
+                err = "malformed BGZF member";
+                return -1;
+            }
+            std::atomic<bool> bad(false);
+            auto work = [&](size_t a, size_t z) {
+                z_stream zs;
+                memset(&zs, 0, sizeof zs);
+                if (inflateInit2(&zs, -15) != Z_OK) { bad = true; return; }
+                for (size_t i = a; i < z; ++i) {
+                    const Member &m = batch[i];
+                    if (m.isize == 0) continue;  // (the empty member that ends a BGZF file)
+                    const size_t xlen = le16(m.src + 10);
+                    inflateReset(&zs);
+                    zs.next_in = const_cast<unsigned char *>(m.src + 12 + xlen);
+                    zs.avail_in = (uInt)(m.csize - 12 - xlen - 8);
+                    zs.next_out = reinterpret_cast<unsigned char *>(dst + m.off);
+                    zs.avail_out = m.isize;
+                    const int r = inflate(&zs, Z_FINISH);
+                    if (r != Z_STREAM_END || zs.avail_out != 0 ||
+                        (uint32_t)crc32(crc32(0L, Z_NULL, 0), reinterpret_cast<unsigned char *>(dst + m.off), m.isize) !=
+                            le32(m.src + m.csize - 8))
+                        bad = true;
+                }
+                inflateEnd(&zs);
+            };
+            const int use = (int)std::min<size_t>((size_t)nt, std::max<size_t>(1, batch.size() / 8));
+            if (use <= 1) work(0, batch.size());
+            else {
+                std::vector<std::thread> th;
+                for (int k = 0; k < use; ++k) th.emplace_back(work, batch.size() * k / use, batch.size() * (k + 1) / use);
+                for (auto &t : th) t.join();
+            }
+            if (bad) { err = "corrupt BGZF member (inflate / CRC32 / length check failed)"; return -1; }
+            if (total > 0) return (long)total;
+            // (only empty members so far: read on)
+        }
+    }
+
+    // up to `want` bytes of text into dst; 0 at the end, -1 on error.  Whole members are inflated straight into
+    // dst; only when the next member is larger than the space left does it go through the 64 KB carry buffer.
+    long fill(char *dst, size_t want) {
+        if (opos == olen) {
+            const long got = inflate_batch(dst, want);
+            if (got != 0 || at_end) return got;
+            if (!obuf.ensure((size_t)1 << 16)) { err = "out of memory"; return -1; }
+            const long one = inflate_batch(obuf.p, (size_t)1 << 16);  // (a member holds at most 64 KB)
+            if (one <= 0) return one;
+            olen = (size_t)one;
+            opos = 0;
+        }
+        const size_t n = std::min(want, olen - opos);
+        memcpy(dst, obuf.p + opos, n);
+        opos += n;
+        return (long)n;
+    }
+};
+
 }  // namespace
 
 extern "C" const char *sstar_b200_vcf_last_error(void) { return g_vcf_err.c_str(); }
@@ -166,18 +294,23 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
     // plain text is read straight into the block (read(2)); only a gzip stream goes through zlib
     int fd = open(path, O_RDONLY);
     if (fd < 0) { g_vcf_err = std::string("cannot open ") + path; return SSTAR_B200_EINVAL; }
-    unsigned char magic[2] = {0, 0};
-    const ssize_t nm = pread(fd, magic, 2, 0);
+    unsigned char magic[64] = {0};
+    const ssize_t nm = pread(fd, magic, sizeof magic, 0);
+    int nt = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > 64) nt = 64;
     gzFile gz = nullptr;
-    if (nm == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+    BgzfReader bg;  // BGZF members are inflated in parallel; any other gzip stream by zlib on this thread
+    const bool bgzf = nm >= 18 && bgzf_member_size(magic, (size_t)nm) > 0;
+    if (bgzf) {
+        bg.fd = fd;
+        bg.nt = nt;
+    } else if (nm >= 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
         gz = gzdopen(fd, "rb");  // (owns fd from here on)
         if (!gz) { close(fd); g_vcf_err = std::string("cannot open ") + path; return SSTAR_B200_EINVAL; }
         gzbuffer(gz, 1 << 20);
     }
     auto close_input = [&]() { if (gz) gzclose(gz); else close(fd); };
-    int nt = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();
-    if (nt < 1) nt = 1;
-    if (nt > 64) nt = 64;
 
     auto *h = new sstar_b200_vcf();
     std::unordered_set<std::string> wanted;
@@ -208,8 +341,13 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
     while (!eof || len > 0) {
         while (!eof && len < buf.cap) {  // top the block up
             const size_t wantb = std::min(buf.cap - len, (size_t)1 << 30);
-            const long got = gz ? (long)gzread(gz, buf.p + len, (unsigned)wantb) : (long)read(fd, buf.p + len, wantb);
-            if (got < 0) { g_vcf_err = std::string("read error in ") + path; rc = SSTAR_B200_EINVAL; break; }
+            const long got = bgzf ? bg.fill(buf.p + len, wantb)
+                             : gz ? (long)gzread(gz, buf.p + len, (unsigned)wantb) : (long)read(fd, buf.p + len, wantb);
+            if (got < 0) {
+                g_vcf_err = std::string("read error in ") + path + (bgzf && !bg.err.empty() ? ": " + bg.err : "");
+                rc = SSTAR_B200_EINVAL;
+                break;
+            }
             if (got == 0) eof = true;
             len += (size_t)got;
         }

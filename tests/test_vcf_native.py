@@ -119,3 +119,57 @@ def test_streaming_blocks_and_sample_subset(tmp_path, monkeypatch):
     assert np.array_equal(sub["3"]["GT"], full["3"]["GT"][:, [0, 7, 13], :])
     hs, none = _scan_vcf(str(path), "3", samples=["nobody"])
     assert hs == [] and none["3"]["GT"].shape == (len(pos), 0, 2)
+
+
+def _write_bgzf(path, data: bytes, chunk: int = 60000):
+    """bgzip's container (SAM specification 4.1): gzip members of <= 64 KB with a 'BC' extra field holding
+    the member's size - 1, closed by an empty member."""
+    import struct
+    import zlib
+    with open(path, "wb") as fh:
+        for i in list(range(0, len(data), chunk)) + [len(data)]:
+            raw = data[i:i + chunk] if i < len(data) else b""
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            comp = co.compress(raw) + co.flush()
+            fh.write(struct.pack("<BBBBIBBH", 0x1F, 0x8B, 8, 4, 0, 0, 0xFF, 6) + b"BC" +
+                     struct.pack("<HH", 2, len(comp) + 25) + comp + struct.pack("<II", zlib.crc32(raw), len(raw)))
+
+
+def test_bgzf_members_are_inflated_in_parallel_and_checked(tmp_path, monkeypatch):
+    """A bgzip'ed VCF (what tabix-indexed files are): the members are located by their 'BC' sizes and inflated
+    by the worker threads; same arrays as the plain file, whatever the member / block sizes (lines straddle
+    both kinds of edges); a corrupt or truncated member is an error, not silence."""
+    from sstar_b200.synth import synth_chromosome, write_vcf
+    from sstar_b200.utils.utils import _scan_vcf
+    ref, tgt, pos = synth_chromosome(2_000_000, 30, 20, True, seed=11)
+    plain = tmp_path / "p.vcf"
+    names = write_vcf(str(plain), "5", pos, np.concatenate([ref, tgt], axis=1), missing_rate=0.01, seed=4)
+    data = plain.read_bytes()
+    header, want = _scan_vcf(str(plain), "5")
+    for chunk, block in ((60000, None), (65280, None), (777, None), (60000, 4096), (5000, 257)):
+        bz = tmp_path / f"b{chunk}.vcf.gz"
+        _write_bgzf(str(bz), data, chunk)
+        assert gzip.open(bz, "rb").read() == data  # (a valid multi-member gzip file)
+        if block:
+            monkeypatch.setenv("SSTAR_B200_VCF_BLOCK", str(block))
+        h2, got = _scan_vcf(str(bz), "5")
+        monkeypatch.delenv("SSTAR_B200_VCF_BLOCK", raising=False)
+        assert h2 == header == names and np.array_equal(got["5"]["POS"], pos)
+        assert np.array_equal(got["5"]["GT"], want["5"]["GT"])
+        assert list(got["5"]["REF"]) == list(want["5"]["REF"]) and list(got["5"]["ALT"]) == list(want["5"]["ALT"])
+    _same(str(tmp_path / "b60000.vcf.gz"), "5")  # and the oracle's independent reader agrees
+    # the reference fixture, bgzip'ed
+    fx = tmp_path / "t.vcf.gz"
+    _write_bgzf(str(fx), open(os.path.join(FIXTURES, "test.vcf"), "rb").read(), 300)
+    _same(str(fx), "21")
+    # corruption: a flipped byte inside a member's deflate data, and a file cut inside a member
+    raw = bytearray((tmp_path / "b60000.vcf.gz").read_bytes())
+    raw[len(raw) // 2] ^= 0x5A
+    bad = tmp_path / "bad.vcf.gz"
+    bad.write_bytes(bytes(raw))
+    with pytest.raises(ValueError, match="BGZF"):
+        _scan_vcf(str(bad), "5")
+    cut = tmp_path / "cut.vcf.gz"
+    cut.write_bytes((tmp_path / "b60000.vcf.gz").read_bytes()[:-100])
+    with pytest.raises(ValueError, match="BGZF"):
+        _scan_vcf(str(cut), "5")
