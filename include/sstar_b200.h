@@ -225,7 +225,8 @@ int sstar_b200_format_table(int device, void *stream, const int64_t *d_score, co
                             const int32_t *d_col_order, const sstar_b200_table_options *topts,
                             char *d_out, size_t out_capacity, void *d_workspace, size_t workspace_bytes);
 
-/* Native VCF scanner (host code, multi-threaded; plain text or gzip).
+/* Native VCF scanner (host code, multi-threaded; plain text, gzip, or BGZF / bgzip -- whose members are
+ * inflated in parallel and checked against their CRC32 and length; one plain gzip stream is inflated on one thread).
  * replaces: allel.read_vcf(vcf, alt_number=1, samples=..., region=chr_name) as used by
  *           read_geno_data (sstar/utils/utils.py:80-109) -- scikit-allel is an un-vendored dependency.
  * One streaming pass over the file (a block of lines at a time; lines of other chromosomes are
