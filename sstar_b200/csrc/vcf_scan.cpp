@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
 
@@ -154,6 +155,15 @@ void parse_line(const char *p, const char *e, const int32_t *sel, int n_cols, in
         if (sample >= last_col || t >= e) break;
         p = t + 1;
     }
+}
+
+// f(k) for k in [0, n) on n threads (n == 1: on this one)
+template <typename F>
+void run_threads(int n, F f) {
+    if (n <= 1) { f(0); return; }
+    std::vector<std::thread> th;
+    for (int k = 0; k < n; ++k) th.emplace_back(f, k);
+    for (auto &t : th) t.join();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -311,6 +321,10 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
         gzbuffer(gz, 1 << 20);
     }
     auto close_input = [&]() { if (gz) gzclose(gz); else close(fd); };
+    // plain text in a regular file: the block is filled by the worker threads, a slice of the file each (pread)
+    struct stat sb;
+    const bool sliced = !bgzf && !gz && fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode);
+    size_t file_off = 0;
 
     auto *h = new sstar_b200_vcf();
     std::unordered_set<std::string> wanted;
@@ -326,6 +340,7 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
     struct LineRef { size_t begin, end; int chrom; size_t row; };
     std::vector<LineRef> lines;
     std::vector<LineFields> lf;
+    std::vector<std::vector<size_t>> nl_parts;  // newline offsets of the block, one list per worker slice
     size_t block = (size_t)32 << 20;
     if (const char *env = getenv("SSTAR_B200_VCF_BLOCK")) {  // tests shrink the block to cross its edges
         const long long v = atoll(env);
@@ -340,9 +355,33 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
     int rc = 0;
     while (!eof || len > 0) {
         while (!eof && len < buf.cap) {  // top the block up
-            const size_t wantb = std::min(buf.cap - len, (size_t)1 << 30);
-            const long got = bgzf ? bg.fill(buf.p + len, wantb)
-                             : gz ? (long)gzread(gz, buf.p + len, (unsigned)wantb) : (long)read(fd, buf.p + len, wantb);
+            size_t wantb = std::min(buf.cap - len, (size_t)1 << 30);
+            long got;
+            if (sliced) {
+                const size_t left = (size_t)sb.st_size > file_off ? (size_t)sb.st_size - file_off : 0;
+                wantb = std::min(wantb, left);
+                const int use = (int)std::min<size_t>((size_t)nt, std::max<size_t>(1, wantb >> 21));  // >= 2 MB a thread
+                std::atomic<long> total(0);
+                std::atomic<bool> failed(false);
+                char *dst = buf.p + len;
+                run_threads(use, [&](int k) {
+                    size_t a = wantb * (size_t)k / use;
+                    const size_t z = wantb * (size_t)(k + 1) / use;
+                    while (a < z) {
+                        const ssize_t g = pread(fd, dst + a, z - a, (off_t)(file_off + a));
+                        if (g < 0) { failed = true; return; }
+                        if (g == 0) return;  // (the file shrank under us: the short count below ends the scan)
+                        a += (size_t)g;
+                        total += (long)g;
+                    }
+                });
+                got = failed ? -1 : (total == (long)wantb ? (long)wantb : -1);
+                if (wantb == 0) got = 0;
+                if (got > 0) file_off += (size_t)got;
+            } else {
+                got = bgzf ? bg.fill(buf.p + len, wantb)
+                      : gz ? (long)gzread(gz, buf.p + len, (unsigned)wantb) : (long)read(fd, buf.p + len, wantb);
+            }
             if (got < 0) {
                 g_vcf_err = std::string("read error in ") + path + (bgzf && !bg.err.empty() ? ": " + bg.err : "");
                 rc = SSTAR_B200_EINVAL;
@@ -363,8 +402,26 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
             }
         }
         lines.clear();
+        // line ends of the block: every worker lists the newlines of its slice, the slices are walked in order
+        const size_t span = (size_t)(stop - b);
+        const int iuse = (int)std::min<size_t>((size_t)nt, std::max<size_t>(1, span >> 20));  // >= 1 MB a thread
+        if ((int)nl_parts.size() < iuse) nl_parts.resize(iuse);
+        run_threads(iuse, [&](int k) {
+            std::vector<size_t> &v = nl_parts[k];
+            v.clear();
+            const char *q = b + span * (size_t)k / iuse, *z = b + span * (size_t)(k + 1) / iuse;
+            while (q < z) {
+                const char *nl = find_byte(q, z, '\n');
+                if (nl >= z) break;
+                v.push_back((size_t)(nl - b));
+                q = nl + 1;
+            }
+        });
+        int part = 0;
+        size_t part_i = 0;
         for (const char *p = b; p < stop;) {
-            const char *nl = find_byte(p, stop, '\n');
+            while (part < iuse && part_i >= nl_parts[part].size()) { ++part; part_i = 0; }
+            const char *nl = part < iuse ? b + nl_parts[part][part_i++] : stop;  // (at EOF the tail has no newline)
             if (nl > p) {
                 if (p[0] == '#' && nl - p >= 2 && p[1] == '#') {
                     // meta line
