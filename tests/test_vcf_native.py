@@ -173,3 +173,42 @@ def test_bgzf_members_are_inflated_in_parallel_and_checked(tmp_path, monkeypatch
     cut.write_bytes((tmp_path / "b60000.vcf.gz").read_bytes()[:-100])
     with pytest.raises(ValueError, match="BGZF"):
         _scan_vcf(str(cut), "5")
+
+
+def test_random_call_fields_take_the_same_values_on_both_parser_paths(tmp_path):
+    """Seeded fuzz of the sample fields: the in-place decoder of the common call shape and the general
+    field parser must agree with the oracle's reader on every mixture -- one- and multi-digit alleles, '.',
+    '|' and '/', haploid calls, FORMAT fields behind the GT, any position in the line (first, last, behind a
+    long field)."""
+    rng = np.random.default_rng(20261020)
+    alle = ["0", "1", "2", ".", "7", "10", "12", "127"]
+    tails = ["", "", "", ":12", ":3,4:99", ":."]
+
+    def field():
+        kind = rng.integers(0, 10)
+        if kind < 6:
+            return f"{rng.choice(alle[:4])}{rng.choice(['|', '/'])}{rng.choice(alle[:4])}"
+        if kind < 8:
+            return f"{rng.choice(alle)}{rng.choice(['|', '/'])}{rng.choice(alle)}{rng.choice(tails)}"
+        if kind == 8:
+            return f"{rng.choice(alle)}{rng.choice(tails)}"  # haploid
+        return rng.choice([".", "./.", ".|.", "0|1:", "1/"])
+
+    n = 37
+    names = [f"s{i}" for i in range(n)]
+    lines = ["##fileformat=VCFv4.2", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(names)]
+    for v in range(400):
+        fmt = "GT" if rng.integers(0, 3) else "GT:DP:GQ"
+        lines.append("\t".join([str(1 + v % 3), str(10 + 7 * v), ".", "A", "T,G", ".", ".", ".", fmt] +
+                               [field() for _ in range(n)]))
+    p = tmp_path / "fuzz.vcf"
+    for ending in ("\n", "\r\n"):
+        p.write_bytes((ending.join(lines) + ending).encode())
+        _same(str(p), None)
+        _same(str(p), "2")
+    # a sample subset walks the same fields but stores only some of them
+    from sstar_b200.utils.utils import _scan_vcf
+    header, full = _scan_vcf(str(p), "1")
+    pick = [names[0], names[5], names[36]]
+    hs, sub = _scan_vcf(str(p), "1", samples=pick)
+    assert hs == pick and np.array_equal(sub["1"]["GT"], full["1"]["GT"][:, [0, 5, 36], :])
