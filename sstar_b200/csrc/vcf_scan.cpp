@@ -13,6 +13,7 @@
 // samples' columns are parsed and stored (allel.read_vcf(samples=..., region=...) does the same:
 // sstar/utils/utils.py:80) -- memory is the kept calls plus one block, whatever the file holds.
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <fcntl.h>
@@ -22,6 +23,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -353,7 +355,18 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
     int last_id = -1;
     bool eof = false;
     int rc = 0;
+    // SSTAR_B200_VCF_TIMING=1: milliseconds per phase on stderr (read / line ends / line loop / parse / alleles)
+    static const bool timing = [] { const char *e = getenv("SSTAR_B200_VCF_TIMING"); return e && atoi(e) != 0; }();
+    double phase_ms[5] = {0, 0, 0, 0, 0};
+    auto tick = [] { return std::chrono::steady_clock::now(); };
+    auto lap = [&](int i, std::chrono::steady_clock::time_point &t) {
+        if (!timing) return;
+        const auto n = tick();
+        phase_ms[i] += std::chrono::duration<double, std::milli>(n - t).count();
+        t = n;
+    };
     while (!eof || len > 0) {
+        auto t_phase = tick();
         while (!eof && len < buf.cap) {  // top the block up
             size_t wantb = std::min(buf.cap - len, (size_t)1 << 30);
             long got;
@@ -391,6 +404,7 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
             len += (size_t)got;
         }
         if (rc) break;
+        lap(0, t_phase);
         const char *b = buf.p, *end = b + len;
         // the block's complete lines end at the last newline (at EOF the unterminated tail is a line too)
         const char *stop = end;
@@ -417,6 +431,7 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
                 q = nl + 1;
             }
         });
+        lap(1, t_phase);
         int part = 0;
         size_t part_i = 0;
         for (const char *p = b; p < stop;) {
@@ -482,6 +497,7 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
             p = nl + 1;
         }
         if (rc) break;
+        lap(2, t_phase);
         // parse the block's kept lines in parallel, straight into the chromosomes' arrays
         for (auto &c : h->chroms)
             if (!c.gt.ensure(c.pos.size() * (size_t)N * 2)) { g_vcf_err = "out of memory"; rc = SSTAR_B200_EINVAL; }
@@ -502,6 +518,7 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
             for (int k = 0; k < use; ++k) th.emplace_back(work, L * k / use, L * (k + 1) / use);
             for (auto &t : th) t.join();
         }
+        lap(3, t_phase);
         for (size_t i = 0; i < L; ++i) {  // the alleles are copied out before the block is recycled
             ChromData &c = h->chroms[lines[i].chrom];
             c.ref_bytes.insert(c.ref_bytes.end(), lf[i].ref, lf[i].ref + lf[i].ref_len);
@@ -509,12 +526,16 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
             c.ref_off.push_back((int32_t)c.ref_bytes.size());
             c.alt_off.push_back((int32_t)c.alt_bytes.size());
         }
+        lap(4, t_phase);
         const size_t used = (size_t)(stop - b);
         memmove(buf.p, buf.p + used, len - used);
         len -= used;
         if (eof) len = 0;
     }
     close_input();
+    if (timing)
+        fprintf(stderr, "[vcf_scan] %d threads: read %.2f  line ends %.2f  line loop %.2f  parse %.2f  alleles %.2f ms\n", nt,
+                phase_ms[0], phase_ms[1], phase_ms[2], phase_ms[3], phase_ms[4]);
     if (!rc && !have_header) {
         g_vcf_err = std::string(path) + " has no #CHROM header line.";
         rc = SSTAR_B200_EINVAL;
