@@ -212,3 +212,55 @@ def test_random_call_fields_take_the_same_values_on_both_parser_paths(tmp_path):
     pick = [names[0], names[5], names[36]]
     hs, sub = _scan_vcf(str(p), "1", samples=pick)
     assert hs == pick and np.array_equal(sub["1"]["GT"], full["1"]["GT"][:, [0, 5, 36], :])
+
+
+def test_scanner_is_clean_under_address_and_ub_sanitizers(tmp_path):
+    """The scanner compiled with -fsanitize=address,undefined (g++) over the fixtures, BGZF files with tiny members,
+    a corrupt and a truncated one, an empty file, a file without header, lines that end early -- at three block
+    sizes and two thread counts: no report, and every input ends in a result or a clean error code."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    from conftest import REPO
+    main = tmp_path / "main.cpp"
+    main.write_text(
+        '#include "sstar_b200.h"\n#include <cstdio>\n#include <initializer_list>\n'
+        "int main(int argc, char **argv) {\n"
+        "  for (int i = 1; i < argc; ++i) for (int nt : {1, 4}) {\n"
+        "    sstar_b200_vcf *h = nullptr;\n"
+        "    const int rc = sstar_b200_vcf_scan(argv[i], nullptr, nt, &h);\n"
+        '    std::printf("%d %lld\\n", rc, rc == 0 && sstar_b200_vcf_n_chroms(h) ? (long long)sstar_b200_vcf_n_variants(h, 0) : -1LL);\n'
+        "    if (rc == 0) sstar_b200_vcf_free(h);\n"
+        "  }\n  return 0;\n}\n")
+    exe = tmp_path / "scan_asan"
+    build = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer",
+                            "-I", os.path.join(REPO, "include"), "-o", str(exe), str(main),
+                            os.path.join(REPO, "sstar_b200", "csrc", "vcf_scan.cpp"), "-lz", "-lpthread"],
+                           capture_output=True, text=True)
+    if build.returncode != 0:
+        pytest.skip("g++ cannot link the sanitizers here: " + build.stderr[-300:])
+    fx = open(os.path.join(FIXTURES, "test.vcf"), "rb").read()
+    files = {"ok.vcf": fx, "empty.vcf": b"", "nohdr.vcf": b"1\t5\t.\tA\tT\t.\t.\t.\tGT\t0|1",
+             "short.vcf": b"#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ta\tb\n1\t5\n1\t6\t.\tA\tT\t.\t.\t.\tGT\t0|\n"
+                          b"1\t7\t.\tA\tT\t.\t.\t.\tGT\t0|1\t1|\n1\t8\t.\tA\tT\t.\t.\t.\tGT\t\t\n1\t9\t.\tA\tT\t.\t.\t.\tGT\t0|1\t1"}
+    paths = []
+    for name, data in files.items():
+        (tmp_path / name).write_bytes(data)
+        paths.append(str(tmp_path / name))
+    _write_bgzf(str(tmp_path / "m.vcf.gz"), fx, 300)
+    raw = bytearray((tmp_path / "m.vcf.gz").read_bytes())
+    raw[len(raw) // 2] ^= 0x5A
+    (tmp_path / "bad.vcf.gz").write_bytes(bytes(raw))
+    (tmp_path / "cut.vcf.gz").write_bytes((tmp_path / "m.vcf.gz").read_bytes()[:-57])
+    with gzip.open(tmp_path / "std.vcf.gz", "wb") as fh:
+        fh.write(fx)
+    paths += [str(tmp_path / n) for n in ("m.vcf.gz", "bad.vcf.gz", "cut.vcf.gz", "std.vcf.gz")]
+    want = {"ok.vcf": (0, 19), "empty.vcf": (-1, -1), "nohdr.vcf": (-1, -1), "short.vcf": (0, 5), "m.vcf.gz": (0, 19),
+            "bad.vcf.gz": (-1, -1), "cut.vcf.gz": (-1, -1), "std.vcf.gz": (0, 19)}
+    for block in ("64", "4096", str(32 << 20)):
+        run = subprocess.run([str(exe)] + paths, capture_output=True, text=True, timeout=300,
+                             env=dict(os.environ, SSTAR_B200_VCF_BLOCK=block, ASAN_OPTIONS="detect_leaks=1"))
+        assert run.returncode == 0 and "Sanitizer" not in run.stderr and "runtime error" not in run.stderr, run.stderr[-2000:]
+        got = [tuple(int(x) for x in ln.split()) for ln in run.stdout.strip().splitlines()]
+        assert got == [want[os.path.basename(p)] for p in paths for _ in (1, 4)]
