@@ -288,3 +288,23 @@ def test_plan_chromosome_assignment_is_greedy_lpt():
     loads = [sum(costs[c] for c in g) for g in plan]
     assert max(loads) <= 1.12 * sum(costs.values()) / 8
     assert plan_chromosome_assignment({"a": 1}, 4) == [["a"], [], [], []]
+
+
+def test_call_level_helpers_equal_the_numpy_reductions():
+    """The slice forms of the per-call tests (missing allele, hom-alt, dosage) and the column selection
+    against the plain numpy expressions they replace (sstar/utils/utils.py:106,282-291,305-306)."""
+    from sstar_b200.utils import utils as u
+    rng = np.random.default_rng(5)
+    gt = rng.integers(-1, 4, (500, 23, 2)).astype(np.int8)
+    assert np.array_equal(u._any_allele_missing(gt), (gt < 0).any(axis=2))
+    first = gt[:, :, 0]
+    assert np.array_equal(u._is_hom_alt(gt), (first > 0) & (gt == first[:, :, None]).all(axis=2))
+    assert np.array_equal(u._dosage(gt), gt.sum(axis=2, dtype=np.int16).astype(np.int8))
+    for cols in ([3, 1, 17, 22, 0], [4, 5, 6], [0], [], list(range(23))):
+        got = u._take_columns(gt, cols)
+        assert got.shape == (500, len(cols), 2) and np.array_equal(got, gt[:, cols, :])
+    # a filter that drops nothing leaves the arrays alone; one that drops rows copies
+    data = {"1": {"POS": np.arange(500), "REF": None, "ALT": None, "GT": gt}}
+    assert u.filter_data(data, "1", np.ones(500, bool))["1"]["GT"] is gt
+    keep = np.arange(500) % 3 != 0
+    assert np.array_equal(u.filter_data(data, "1", keep)["1"]["GT"], gt[keep])
