@@ -511,7 +511,14 @@ def host_cache_flush(torch, nbytes=1 << 30):
     13.6 GB/s in the order they were written, all at 49 GB/s once the CPU has written 1 GiB elsewhere).  The
     host-side twin of the L2 flush: outside every timed region, before the e2e ones."""
     if "buf" not in _HOST_JUNK:
-        _HOST_JUNK["buf"], _HOST_JUNK["n"] = torch.empty(nbytes, dtype=torch.uint8), 0
+        while True:  # (a host short of memory gets a smaller sweep rather than a failed run)
+            try:
+                _HOST_JUNK["buf"], _HOST_JUNK["n"] = torch.empty(nbytes, dtype=torch.uint8), 0
+                break
+            except (RuntimeError, MemoryError):
+                if nbytes <= (64 << 20):
+                    raise
+                nbytes //= 2
     _HOST_JUNK["n"] += 1
     _HOST_JUNK["buf"].fill_(_HOST_JUNK["n"] & 1)
 
