@@ -30,7 +30,7 @@ def parse_ind_file(filename: str) -> list[str]:
 
 
 def _scan_vcf(path: str, chr_name: str | None, need_alleles: bool = True, samples=None):
-    """One streaming pass over a (optionally gzipped) text VCF -> kept samples (header order) +
+    """One streaming pass over a text VCF (plain, gzip or BGZF) -> kept samples (header order) +
     per-chromosome columns, through the native multi-threaded scanner (``sstar_b200_vcf_scan_ex``,
     csrc/vcf_scan.cpp).  ``samples``: names to keep (the ref + tgt lists; what
     ``allel.read_vcf(samples=...)`` does, utils.py:80) -- None keeps every column.
