@@ -24,6 +24,9 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -159,14 +162,74 @@ void parse_line(const char *p, const char *e, const int32_t *sel, int n_cols, in
     }
 }
 
-// f(k) for k in [0, n) on n threads (n == 1: on this one)
-template <typename F>
-void run_threads(int n, F f) {
-    if (n <= 1) { f(0); return; }
-    std::vector<std::thread> th;
-    for (int k = 0; k < n; ++k) th.emplace_back(f, k);
-    for (auto &t : th) t.join();
-}
+// The workers of one scan: created once, woken per phase (a block goes through four parallel phases -- fill, line
+// ends, parse, and for BGZF the inflate; spawning sixteen threads for each cost as much as the lighter phases took).
+// run(n, f): f(k) for k in [0, n) on workers 0 .. n-1, the caller waits for all of them; n <= 1 runs f(0) inline.
+class Workers {
+public:
+    explicit Workers(int n) : size_(n < 1 ? 1 : n) {}
+    Workers(const Workers &) = delete;
+    Workers &operator=(const Workers &) = delete;
+    ~Workers() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        wake_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    int size() const { return size_; }
+    void run(int n, const std::function<void(int)> &f) {
+        if (n <= 1) { f(0); return; }
+        if (n > size_) {  // (callers size n by the pool; more items than workers are taken in rounds)
+            for (int k0 = 0; k0 < n; k0 += size_) {
+                const int m = std::min(size_, n - k0);
+                if (m == 1) f(k0);
+                else run(m, [&](int k) { f(k0 + k); });
+            }
+            return;
+        }
+        if (th_.empty())  // started at the first phase that wants them (a small file never does)
+            for (int k = 0; k < size_; ++k) th_.emplace_back([this, k] { loop(k); });
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            job_ = &f;
+            active_ = n;
+            pending_ = n;
+            ++generation_;
+        }
+        wake_.notify_all();
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+private:
+    void loop(int k) {
+        uint64_t seen = 0;
+        std::unique_lock<std::mutex> lk(m_);
+        for (;;) {
+            wake_.wait(lk, [&] { return stop_ || generation_ != seen; });
+            if (stop_) return;
+            seen = generation_;
+            if (k < active_) {
+                const std::function<void(int)> *f = job_;
+                lk.unlock();
+                (*f)(k);
+                lk.lock();
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    const int size_;
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable wake_, done_;
+    const std::function<void(int)> *job_ = nullptr;
+    int active_ = 0, pending_ = 0;
+    uint64_t generation_ = 0;
+    bool stop_ = false;
+};
 
 // ---------------------------------------------------------------------------------------------
 // BGZF (bgzip, what tabix-indexed VCFs are stored in): a gzip file made of independent members of at most
@@ -193,7 +256,8 @@ long bgzf_member_size(const unsigned char *p, size_t n) {
 }
 
 struct BgzfReader {
-    int fd = -1, nt = 1;
+    int fd = -1;
+    Workers *pool = nullptr;
     RawBuf cbuf, obuf;          // compressed bytes read ahead; carry buffer (a member that did not fit the caller's space)
     size_t clen = 0, cpos = 0;  // bytes in cbuf, first unconsumed one
     size_t olen = 0, opos = 0;
@@ -263,13 +327,8 @@ struct BgzfReader {
                 }
                 inflateEnd(&zs);
             };
-            const int use = (int)std::min<size_t>((size_t)nt, std::max<size_t>(1, batch.size() / 8));
-            if (use <= 1) work(0, batch.size());
-            else {
-                std::vector<std::thread> th;
-                for (int k = 0; k < use; ++k) th.emplace_back(work, batch.size() * k / use, batch.size() * (k + 1) / use);
-                for (auto &t : th) t.join();
-            }
+            const int use = (int)std::min<size_t>((size_t)pool->size(), std::max<size_t>(1, batch.size() / 8));
+            pool->run(use, [&](int k) { work(batch.size() * (size_t)k / use, batch.size() * (size_t)(k + 1) / use); });
             if (bad) { err = "corrupt BGZF member (inflate / CRC32 / length check failed)"; return -1; }
             if (total > 0) return (long)total;
             // (only empty members so far: read on)
@@ -314,9 +373,10 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
     gzFile gz = nullptr;
     BgzfReader bg;  // BGZF members are inflated in parallel; any other gzip stream by zlib on this thread
     const bool bgzf = nm >= 18 && bgzf_member_size(magic, (size_t)nm) > 0;
+    Workers pool(nt);
     if (bgzf) {
         bg.fd = fd;
-        bg.nt = nt;
+        bg.pool = &pool;
     } else if (nm >= 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
         gz = gzdopen(fd, "rb");  // (owns fd from here on)
         if (!gz) { close(fd); g_vcf_err = std::string("cannot open ") + path; return SSTAR_B200_EINVAL; }
@@ -377,7 +437,7 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
                 std::atomic<long> total(0);
                 std::atomic<bool> failed(false);
                 char *dst = buf.p + len;
-                run_threads(use, [&](int k) {
+                pool.run(use, [&](int k) {
                     size_t a = wantb * (size_t)k / use;
                     const size_t z = wantb * (size_t)(k + 1) / use;
                     while (a < z) {
@@ -420,7 +480,7 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
         const size_t span = (size_t)(stop - b);
         const int iuse = (int)std::min<size_t>((size_t)nt, std::max<size_t>(1, span >> 20));  // >= 1 MB a thread
         if ((int)nl_parts.size() < iuse) nl_parts.resize(iuse);
-        run_threads(iuse, [&](int k) {
+        pool.run(iuse, [&](int k) {
             std::vector<size_t> &v = nl_parts[k];
             v.clear();
             const char *q = b + span * (size_t)k / iuse, *z = b + span * (size_t)(k + 1) / iuse;
@@ -512,12 +572,7 @@ extern "C" int sstar_b200_vcf_scan_ex(const char *path, const char *chr_name, co
             }
         };
         const int use = (int)std::min<size_t>((size_t)nt, std::max<size_t>(1, L / 256));
-        if (use <= 1) work(0, L);
-        else {
-            std::vector<std::thread> th;
-            for (int k = 0; k < use; ++k) th.emplace_back(work, L * k / use, L * (k + 1) / use);
-            for (auto &t : th) t.join();
-        }
+        pool.run(use, [&](int k) { work(L * (size_t)k / use, L * (size_t)(k + 1) / use); });
         lap(3, t_phase);
         for (size_t i = 0; i < L; ++i) {  // the alleles are copied out before the block is recycled
             ChromData &c = h->chroms[lines[i].chrom];
